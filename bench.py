@@ -1,0 +1,439 @@
+#!/usr/bin/env python
+"""bench.py — the headline measurement (BASELINE.json metric: rows/s and achieved HBM GB/s per query).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--workload cfg2f|cfg2i|cfg3|cfg4|cfg5]
+                    [--rows R] [--impl reference]
+
+A "step" is one pass of the hot path over one batch of synthetic input that is already resident in
+HBM. Default workload (N=1): BASELINE.json configs[1], the fused filter (a > k AND b < m) +
+projection (a*b + c) over a 100 M-row Float64 table. With N > 1 (torchrun, one rank per GPU) every
+rank processes its own row range of the same global table (weak scaling); filter+project has no
+exchange step, the aggregate workloads merge partials over NCCL inside the timed region.
+
+One JSON line on stdout (rank 0). `value` is device-resident throughput (CUDA events on the kernel
+stream, max over ranks); `e2e` is the same metric through the C ABI with HOST buffers (pinned
+host -> device copies in, result copied back, inside the timed region); `roofline` compares the
+dominant kernel's algorithmic bytes/launch with the measured HBM peak; `cpu_baseline` is the CPU
+oracle (a C++ restatement of the Kotlin operators — the reference itself cannot run here) timed on
+this box's host cores on a bounded sample.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, os.path.join(ROOT, "query-engines_b200"))
+sys.path.insert(0, ROOT)
+
+GEN = dict(I64=1, F64=2, F64_INT=3, F64_STEP=4, UTF8=5, DATE32=6, BOOL=7)
+STATES = "ALAKAZARCACOCTDEFLGAHIIDILINIAKSKYLAMEMDMAMIMNMSMOMTNENVNHNJNMNYNCNDOHOKORPARISCSDTNTXUTVTVAWAWVWIWY"
+assert len(STATES) == 100
+
+
+class Workload:
+    def __init__(self, name, rows, dtype):
+        self.name, self.rows, self.dtype = name, rows, dtype
+
+    # overridden
+    def specs(self): raise NotImplementedError
+    def run(self, E, batch, dist=None): raise NotImplementedError
+    def algo_bytes(self, n, out_rows): raise NotImplementedError
+    kernel = ""
+    describe = ""
+
+
+class FilterProject(Workload):
+    kernel = "k_filter_project"
+
+    def __init__(self, name, rows, flt):
+        super().__init__(name, rows, "f64" if flt else "int64")
+        self.flt = flt
+        self.describe = ("SELECT a*b+c WHERE a>k AND b<m, %s columns, selectivity 0.25" % ("Float64" if flt else "Int64"))
+
+    def specs(self):
+        if self.flt:
+            return [dict(kind=GEN["F64"], col_id=i, flo=0.0, fhi=1.0) for i in range(3)]
+        return [dict(kind=GEN["I64"], col_id=i, ilo=0, ihi=1 << 20) for i in range(3)]
+
+    def exprs(self, E):
+        k = E.lit_f64(0.5) if self.flt else E.lit_i64(1 << 19)
+        pred = E.binary("AND", E.binary("GT", E.col(0), k), E.binary("LT", E.col(1), k))
+        proj = E.binary("ADD", E.binary("MUL", E.col(0), E.col(1)), E.col(2))
+        return pred, [proj]
+
+    def run(self, E, batch, dist=None):
+        pred, proj = self.exprs(E)
+        return E.filter_project(pred, proj, batch)
+
+    def result_rows(self, res):
+        return res.row_count()
+
+    def algo_bytes(self, n, out_rows):
+        return 24 * n + 8 * out_rows
+
+
+class GroupBy(Workload):
+    kernel = "k_hash_aggregate"
+
+    def __init__(self, name, rows, kind):
+        super().__init__(name, rows, "f64")
+        self.kind = kind
+        self.describe = {"low": "GROUP BY 50-value Utf8 key: SUM/MIN/MAX/COUNT(Float64)",
+                         "high": "GROUP BY Int64 key (10M distinct): SUM/MIN/MAX/COUNT(Float64)",
+                         "q1": "TPC-H Q1 shape: date filter, derived projections, 2-key grouped SUMs + COUNT"}[kind]
+
+    def specs(self):
+        if self.kind == "low":
+            return [dict(kind=GEN["UTF8"], col_id=0, dict=STATES, dict_width=2), dict(kind=GEN["F64"], col_id=1, flo=0.0, fhi=1000.0)]
+        if self.kind == "high":
+            return [dict(kind=GEN["I64"], col_id=0, ilo=0, ihi=10_000_000), dict(kind=GEN["F64"], col_id=1, flo=0.0, fhi=1000.0)]
+        return [dict(kind=GEN["DATE32"], col_id=0, ilo=8036, ihi=10562),
+                dict(kind=GEN["UTF8"], col_id=1, dict="ANR", dict_width=1), dict(kind=GEN["UTF8"], col_id=2, dict="FO", dict_width=1),
+                dict(kind=GEN["F64_INT"], col_id=3, ilo=1, ihi=51), dict(kind=GEN["F64"], col_id=4, flo=900.0, fhi=105000.0),
+                dict(kind=GEN["F64_STEP"], col_id=5, ilo=0, ihi=11, fhi=100.0), dict(kind=GEN["F64_STEP"], col_id=6, ilo=0, ihi=9, fhi=100.0)]
+
+    def make(self, E):
+        if self.kind == "q1":
+            one = E.lit_f64(1.0)
+            disc_price = E.binary("MUL", E.col(4), E.binary("SUB", one, E.col(5)))
+            charge = E.binary("MUL", disc_price, E.binary("ADD", one, E.col(6)))
+            pred = E.binary("LE", E.col(0), E.lit_date32(10471))
+            return E.HashAggregate([E.col(1), E.col(2)], [("SUM", E.col(3)), ("SUM", E.col(4)), ("SUM", disc_price),
+                                                        ("SUM", charge), ("COUNT", E.lit_i64(1))], pred=pred)
+        hint = 10_000_000 if self.kind == "high" else 0
+        v = E.col(1)
+        return E.HashAggregate([E.col(0)], [("SUM", v), ("MIN", v), ("MAX", v), ("COUNT", v)], expected_groups=hint)
+
+    def run(self, E, batch, dist=None):
+        agg = self.make(E)
+        agg.update(batch)
+        if dist is not None and dist["world"] > 1:
+            if self.kind == "high":
+                agg.repartition_alltoall()
+            else:
+                agg.merge_allreduce()
+        return agg.finalize()
+
+    def result_rows(self, res):
+        return res.row_count()
+
+    def algo_bytes(self, n, out_rows):
+        per_row = {"low": 14, "high": 16, "q1": 46}[self.kind]
+        return per_row * n + 40 * out_rows
+
+
+WORKLOADS = {
+    "cfg2f": lambda rows: FilterProject("cfg2f", rows or 100_000_000, True),
+    "cfg2i": lambda rows: FilterProject("cfg2i", rows or 100_000_000, False),
+    "cfg3": lambda rows: GroupBy("cfg3", rows or 1_000_000_000, "low"),
+    "cfg4": lambda rows: GroupBy("cfg4", rows or 1_000_000_000, "high"),
+    "cfg5": lambda rows: GroupBy("cfg5", rows or 600_037_902, "q1"),
+}
+
+
+# ---------------------------------------------------------------------------------------------------
+class ClockSampler:
+    """nvidia-smi clocks/throttle reasons sampled DURING the timed region (B200_PROFILING.md)."""
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.lines, self.proc = [], None
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100",
+                                          "-i", str(index)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._pump, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+
+    def _pump(self):
+        for line in self.proc.stdout:
+            self.lines.append((time.time(), line.strip()))
+
+    def stop(self, t0, t1):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        rows = [l for t, l in self.lines if t0 - 0.05 <= t <= t1 + 0.15] or [l for _, l in self.lines]
+        sm, mx, reasons = [], None, set()
+        for l in rows:
+            p = [x.strip() for x in l.split(",")]
+            if len(p) < 7:
+                continue
+            try:
+                sm.append(float(p[0])); mx = float(p[1])
+            except ValueError:
+                continue
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), p[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": mx, "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def measured_peak():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    try:
+        with open(p) as f:
+            return float(json.load(f)["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs, burst copy)"
+    except Exception:
+        return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
+
+
+def ncu_traffic(workload, kernel):
+    """dram bytes/launch of the dominant kernel from the committed ncu capture, if any."""
+    try:
+        with open(os.path.join(ROOT, "profiles", "traffic.json")) as f:
+            return json.load(f).get(workload, {}).get(kernel)
+    except Exception:
+        return None
+
+
+# ---------------------------------------------------------------------------------------------------
+def cpu_reference(wl, sample_rows, threads, seed=42):
+    """Time the CPU oracle (port of the Kotlin operators) on `sample_rows` rows of the same workload."""
+    from oracle import oracle as O
+    O.build()
+    batch = O.generate(wl.specs(), seed, 0, sample_rows)
+
+    t0 = time.perf_counter()
+    if isinstance(wl, FilterProject):
+        pred, proj = wl.exprs(O)
+        out_rows = O.filter_project_mt(pred, proj, batch, threads)
+    else:
+        if wl.kind == "q1":
+            one = O.lit_f64(1.0)
+            dp = O.binary("MUL", O.col(4), O.binary("SUB", one, O.col(5)))
+            ch = O.binary("MUL", dp, O.binary("ADD", one, O.col(6)))
+            pred = O.binary("LE", O.col(0), O.lit_date32(10471))
+            res = O.hashagg_mt([O.col(1), O.col(2)], [("SUM", O.col(3)), ("SUM", O.col(4)), ("SUM", dp), ("SUM", ch),
+                                                      ("COUNT", O.lit_i64(1))], batch, threads, pred=pred)
+        else:
+            v = O.col(1)
+            res = O.hashagg_mt([O.col(0)], [("SUM", v), ("MIN", v), ("MAX", v), ("COUNT", v)], batch, threads)
+        out_rows = res.row_count()
+    dt = time.perf_counter() - t0
+    return sample_rows / dt, dt, out_rows
+
+
+def cpu_sample_rows(wl):
+    # sized for roughly 10-20 s of single-thread-equivalent CPU work (the oracle is row-at-a-time and boxed)
+    return {"cfg2f": 24_000_000, "cfg2i": 24_000_000, "cfg3": 16_000_000, "cfg4": 8_000_000, "cfg5": 8_000_000}[wl.name]
+
+
+def run_reference(args, wl, rank, world):
+    if rank != 0:
+        return
+    threads = os.cpu_count() or 1
+    sample = cpu_sample_rows(wl) // 4
+    for _ in range(args.warmup):
+        cpu_reference(wl, max(sample // 8, 100_000), threads)
+    t0 = time.perf_counter()
+    rows = 0
+    for _ in range(args.steps):
+        _, _, _ = cpu_reference(wl, sample, threads)
+        rows += sample
+    dt = time.perf_counter() - t0
+    v = rows / dt
+    line = {"impl": "reference", "metric": "rows/s", "value": v, "unit": "rows/s", "n_gpus": args.gpus, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": dt / args.steps * 1e3, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": wl.dtype, "data": "synthetic",
+            "config": {"workload": f"{wl.name}: {wl.describe}", "rows_per_gpu": wl.rows, "seed": 42},
+            "cpu_baseline": {"value": v, "unit": "rows/s", "cores": threads, "kind": "port",
+                             "sample": f"{sample} rows per step of the same seeded table (table generation included in the step), "
+                                       f"partition->partial->merge on {threads} threads"},
+            "e2e": {"value": v, "unit": "rows/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "note": "CPU oracle = C++ restatement of the Kotlin operators (the Kotlin reference cannot be built here: no JVM)"}
+    print(json.dumps(line), flush=True)
+
+
+# ---------------------------------------------------------------------------------------------------
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--workload", default="cfg2f", choices=sorted(WORKLOADS))
+    ap.add_argument("--rows", type=int, default=0, help="rows per GPU (default: the BASELINE config size)")
+    ap.add_argument("--impl", default="kqgpu", choices=["kqgpu", "reference"])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-e2e", action="store_true")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3) if args.impl == "kqgpu" else args.warmup
+
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    wl = WORKLOADS[args.workload](args.rows)
+
+    if args.impl == "reference":
+        run_reference(args, wl, rank, world)
+        return
+
+    import kqgpu
+    if kqgpu.device_count() < 1:
+        raise SystemExit("bench.py needs a CUDA device: there is no CPU fallback (use --impl reference for the CPU oracle)")
+
+    dist = None
+    if world > 1:
+        import torch
+        import torch.distributed as td
+        torch.cuda.set_device(local_rank)
+        td.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+        dist = {"td": td, "torch": torch, "world": world, "rank": rank}
+
+    ctx = kqgpu.Context(local_rank)
+    E = kqgpu.Engine(ctx)
+    if world > 1 and isinstance(wl, GroupBy):
+        import ctypes
+        idbuf = ctypes.create_string_buffer(kqgpu.COMM_ID_BYTES)
+        if rank == 0:
+            ctx.check(kqgpu.lib().kq_comm_unique_id(ctx.h, idbuf))
+        t = dist["torch"].frombuffer(bytearray(idbuf.raw), dtype=dist["torch"].uint8).cuda()
+        dist["td"].broadcast(t, 0)
+        idbytes = bytes(t.cpu().numpy().tobytes())
+        ctx.check(kqgpu.lib().kq_comm_init(ctx.h, idbytes, rank, world))
+
+    # each rank owns rows [rank*R, (rank+1)*R) of the same global table (weak scaling)
+    n = wl.rows
+    row0 = rank * n
+    batch = E.generate(wl.specs(), 42, row0, row0 + n)
+    ctx.sync()
+
+    def barrier():
+        ctx.sync()
+        if dist:
+            dist["td"].barrier()
+            dist["torch"].cuda.synchronize()
+
+    # warm-up
+    out_rows = 0
+    for _ in range(args.warmup):
+        res = wl.run(E, batch, dist)
+        out_rows = wl.result_rows(res)
+        del res
+    barrier()
+
+    sampler = ClockSampler(local_rank) if rank == 0 else None
+    launches0 = ctx.launch_count()
+    t_wall0 = time.time()
+    ctx.timer_begin()
+    keep = None
+    for _ in range(args.steps):
+        keep = wl.run(E, batch, dist)          # inputs (2.4-28 GB) are far larger than L2: no flush needed
+    ms = ctx.timer_end()
+    barrier()
+    t_wall1 = time.time()
+    launches = ctx.launch_count() - launches0
+    out_rows = wl.result_rows(keep)
+    del keep
+    if dist:
+        t = dist["torch"].tensor([ms], device="cuda")
+        dist["td"].all_reduce(t, op=dist["td"].ReduceOp.MAX)
+        ms = float(t.item())
+    ms_per_step = ms / args.steps
+    value = world * n / (ms_per_step * 1e-3)
+
+    # end to end through the C ABI from host (pinned) buffers, result copied back
+    e2e = None
+    if not args.no_e2e:
+        e2e = run_e2e(kqgpu, ctx, E, wl, batch, dist, min(args.steps, 5), world)
+    clocks = sampler.stop(t_wall0, time.time()) if sampler else None
+
+    peak, peak_src = measured_peak()
+    algo = wl.algo_bytes(n, out_rows)
+    achieved = algo / (ms_per_step * 1e-3) / 1e9
+    roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                "traffic": ncu_traffic(wl.name, wl.kernel), "kernel": wl.kernel, "algorithmic_bytes_per_launch": algo,
+                "peak_source": peak_src, "frac_of_8TBps": achieved / 8000.0,
+                "how": "algorithmic bytes of one step / (CUDA-event time of the timed region / steps) on the kernel stream"}
+
+    cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        threads = os.cpu_count() or 1
+        sample = cpu_sample_rows(wl)
+        v1, dt1, _ = cpu_reference(wl, sample // 8, 1)
+        vn, dtn, _ = cpu_reference(wl, sample, threads)
+        cpu = {"value": vn, "unit": "rows/s", "cores": threads, "kind": "port",
+               "sample": f"{sample} rows of the same seeded table, partition->partial->merge on {threads} threads ({dtn:.1f} s); "
+                         f"1 thread on {sample // 8} rows: {v1:.3e} rows/s",
+               "value_1thread": v1,
+               "note": "C++ restatement of the Kotlin operators (boxed, row-at-a-time); the Kotlin reference cannot run here (no JVM)"}
+
+    if rank == 0:
+        line = {"metric": "rows/s", "value": value, "unit": "rows/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+                "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": wl.dtype,
+                "data": "synthetic",
+                "config": {"workload": f"{wl.name}: {wl.describe}", "rows_per_gpu": n, "rows_total": n * world, "seed": 42,
+                           "output_rows_rank0": out_rows, "l2": "inputs larger than L2 (no flush needed)",
+                           "parallelism": f"row-sharded x{world}" + ("" if world == 1 or isinstance(wl, FilterProject) else
+                                                                    (", NCCL all-to-all repartition" if wl.kind == "high" else ", NCCL allreduce merge"))},
+                "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": launches, "clocks": clocks}
+        print(json.dumps(line), flush=True)
+    if dist:
+        dist["td"].destroy_process_group()
+
+
+def run_e2e(kqgpu, ctx, E, wl, batch, dist, steps, world):
+    """Same step, but inputs start in pinned HOST memory and the result ends in host memory."""
+    import ctypes as C
+    import numpy as np
+    import pyarrow as pa
+    cols = [batch.field(i) for i in range(batch.num_columns())]
+    host = []
+    h2d = 0
+    for c in cols:
+        n, nb, nn = c.sizes()
+        t = c.type()
+        ptr_d = ctx.host_alloc(max(nb, 1))
+        ptr_o = ctx.host_alloc((n + 1) * 4) if t == kqgpu.UTF8 else None
+        ptr_v = ctx.host_alloc((n + 7) // 8 + 8) if nn > 0 else None
+        ctx.check(kqgpu.lib().kq_column_download(ctx.h, c.h, C.c_void_p(ptr_v) if ptr_v else None,
+                                                 C.c_void_p(ptr_o) if ptr_o else None, C.c_void_p(ptr_d)))
+        host.append((t, n, ptr_v, ptr_o, ptr_d, nb))
+        h2d += nb + ((n + 1) * 4 if ptr_o else 0) + ((n + 7) // 8 if ptr_v else 0)
+
+    def one():
+        up = []
+        for (t, n, pv, po, pd, nb) in host:
+            out = C.c_void_p()
+            ctx.check(kqgpu.lib().kq_column_upload(ctx.h, t, n, C.c_void_p(pv) if pv else None, C.c_void_p(po) if po else None,
+                                                   C.c_void_p(pd), nb, C.byref(out)))
+            up.append(kqgpu.Column(ctx, out))
+        b = kqgpu.RecordBatch.from_columns(ctx, up)
+        res = wl.run(E, b, dist)
+        arrs = res.to_arrow()             # device -> host copy of the step's result
+        return sum(a.nbytes for a in arrs), len(arrs[0]) if arrs else 0
+
+    d2h, _ = one()                        # warm-up
+    if dist:
+        dist["td"].barrier()
+    ctx.sync()
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        d2h, _ = one()
+    ctx.sync()
+    dt = time.perf_counter() - t0
+    if dist:
+        t = dist["torch"].tensor([dt], device="cuda")
+        dist["td"].all_reduce(t, op=dist["td"].ReduceOp.MAX)
+        dt = float(t.item())
+    for (t, n, pv, po, pd, nb) in host:
+        for p in (pv, po, pd):
+            if p:
+                ctx.host_free(p)
+    return {"value": world * wl.rows * steps / dt, "unit": "rows/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+            "steps": steps, "ms_per_step": dt / steps * 1e3,
+            "how": "kq_column_upload from pinned host buffers -> operator -> kq_column_download, wall clock around synchronised steps"}
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,834 @@
+// kq_hashagg.cu — HashAggregateExec (Main.kt:605-660) and its accumulators (Main.kt:514-562).
+//
+// One kernel per input batch fuses: optional FilterExec predicate, the group-key and aggregate-input
+// expressions (fused ProjectionExec), and the accumulate step of the drain loop (Main.kt:620-632).
+//
+// Two tiers of state:
+//   * a GLOBAL open-addressing table in HBM (linear probing, one AoS record per group so that a probe
+//     and all accumulator updates of a row touch one or two 32-byte sectors), the source of truth;
+//   * a per-CTA FRONT END in shared memory for the first `fe_groups` distinct keys a CTA meets: a key
+//     directory shared by the CTA plus LANE-PRIVATE count/sum accumulators (one copy per lane per
+//     warp: no atomics, no bank conflicts) and a CTA-shared MIN/MAX table that is only touched when a
+//     value beats the current extreme. Front ends are merged into the global table once, at CTA exit.
+//     Low-cardinality GROUP BYs (BASELINE configs 3 and 5) run entirely in the front end; rows whose
+//     key does not fit go straight to the global table with atomics (config 4).
+//
+// Accumulator semantics (oracle: MaxAccumulator etc.): nulls are skipped; a group whose inputs were
+// all null yields null, except COUNT; MIN/MAX use a total order in which canonical NaN sorts above
+// +inf and -0.0 below +0.0 — where the reference is order-dependent (rule R9/E8) this is the one
+// deterministic choice; Float64 sums are reassociated (1e-9 relative tolerance, rule E6).
+#include <algorithm>
+#include <cstring>
+
+#include "kq_compile.h"
+#include "kq_scan.cuh"
+
+using namespace kq;
+
+namespace {
+
+constexpr int MAX_REC_WORDS = 32;
+constexpr int DIR_SLOTS = 256;
+constexpr int FE_MAX_GROUPS = 64;
+constexpr uint32_t DIR_EMPTY = 0, DIR_BUSY = 1, DIR_GLOBAL = 0xFFFFFFFFu;   // FULL = gid + 2
+constexpr uint64_t HDR_EMPTY = 0, HDR_BUSY = 1, HDR_FULL = 2;
+
+enum : int32_t { F_SUM = 1, F_MIN = 2, F_MAX = 4, F_INT = 8 };
+
+struct AggInput {
+    int32_t flags;
+    int32_t rec_nn, rec_sum, rec_min, rec_max;   // record word indices (-1 = absent)
+    int32_t fe_sum, fe_min, fe_max;              // front-end slot indices (-1 = absent); the count slot is the input index
+};
+
+struct AggArgs {
+    Program prog;
+    int64_t n, ntiles, tile_begin;
+    int32_t nkeys, ninputs;
+    uint32_t key_f64_mask;                 // keys whose NaNs must be canonicalised (Double.equals, rule R7)
+    int32_t stride;                        // record stride in 64-bit words
+    AggInput in[MAX_INPUTS];
+    uint64_t rec_init[MAX_REC_WORDS];
+    uint64_t* table;
+    uint64_t cap_mask;
+    unsigned long long* ngroups;
+    unsigned long long stop_threshold;
+    unsigned int* ticket;
+    uint32_t* err;
+    // front end
+    int32_t fe_groups, fe_nsum, fe_nmm;
+    int32_t fe_sum_word[MAX_INPUTS];       // front-end sum slot -> record word
+    uint32_t fe_sum_int;                   // bit s: slot s is an integer sum
+    int32_t fe_mm_word[2 * MAX_INPUTS];    // front-end min/max slot -> record word
+    uint32_t fe_mm_ismin;
+    // shared-memory layout (byte offsets)
+    int32_t off_dirkeys, off_dirstate, off_gid2slot, off_gslot, off_mm, off_cnt, off_sum, smem_bytes;
+};
+
+__device__ __forceinline__ uint64_t order_map(uint64_t bits, bool is_int) {
+    if (is_int) return bits ^ 0x8000000000000000ULL;
+    return bits ^ ((bits >> 63) ? ~0ULL : 0x8000000000000000ULL);
+}
+__host__ __device__ __forceinline__ uint64_t order_unmap(uint64_t u, bool is_int) {
+    if (is_int) return u ^ 0x8000000000000000ULL;
+    return u ^ ((u >> 63) ? 0x8000000000000000ULL : ~0ULL);
+}
+__device__ __forceinline__ uint64_t canon_nan(uint64_t bits) {
+    return ((bits & 0x7fffffffffffffffULL) > 0x7ff0000000000000ULL) ? 0x7ff8000000000000ULL : bits;
+}
+__device__ __forceinline__ uint64_t hash_key(const uint64_t (&kw)[MAX_KEYS], uint32_t nullmask, int nkeys) {
+    uint64_t h = 0x9E3779B97F4A7C15ULL + nullmask;
+#pragma unroll
+    for (int k = 0; k < MAX_KEYS; k++) if (k < nkeys) h = kq_mix64(h ^ kw[k]) + 0xD1B54A32D192ED03ULL * (k + 1);
+    return kq_mix64(h);
+}
+
+// Find the record of (kw, nullmask) in the global table, inserting it if absent. Claim protocol:
+// CAS header EMPTY -> BUSY|nullmask, write keys + accumulator identities, fence, publish FULL.
+// The table never fills up: the host sizes it so that ngroups stays below capacity/2 plus margin.
+__device__ __forceinline__ uint64_t* table_find_or_insert(const AggArgs& A, uint64_t h, const uint64_t (&kw)[MAX_KEYS], uint32_t nullmask) {
+    uint64_t slot = h & A.cap_mask;
+    const uint64_t full_hdr = HDR_FULL | ((uint64_t)nullmask << 32);
+    while (true) {
+        uint64_t* rec = A.table + slot * (uint64_t)A.stride;
+        uint64_t hdr = *reinterpret_cast<volatile uint64_t*>(rec);
+        uint32_t state = (uint32_t)hdr;
+        if (state == HDR_EMPTY) {
+            unsigned long long old = atomicCAS(reinterpret_cast<unsigned long long*>(rec), 0ULL, HDR_BUSY | ((uint64_t)nullmask << 32));
+            if (old == 0ULL) {
+                for (int w = 1 + A.nkeys; w < A.stride; w++) rec[w] = A.rec_init[w];
+#pragma unroll
+                for (int k = 0; k < MAX_KEYS; k++) if (k < A.nkeys) rec[1 + k] = kw[k];
+                __threadfence();
+                *reinterpret_cast<volatile uint64_t*>(rec) = full_hdr;
+                atomicAdd(A.ngroups, 1ULL);
+                return rec;
+            }
+            hdr = old; state = (uint32_t)hdr;
+        }
+        if (state == HDR_BUSY) continue;          // another thread is publishing this slot: re-read
+        if (hdr == full_hdr) {
+            bool eq = true;
+#pragma unroll
+            for (int k = 0; k < MAX_KEYS; k++) if (k < A.nkeys) eq &= (__ldcg(rec + 1 + k) == kw[k]);
+            if (eq) return rec;
+        }
+        slot = (slot + 1) & A.cap_mask;
+    }
+}
+
+__device__ __forceinline__ void global_accumulate(uint64_t* rec, const AggInput& d, uint64_t v) {
+    atomicAdd(reinterpret_cast<unsigned long long*>(rec + d.rec_nn), 1ULL);
+    const bool is_int = d.flags & F_INT;
+    if (d.flags & F_SUM) {
+        if (is_int) atomicAdd(reinterpret_cast<unsigned long long*>(rec + d.rec_sum), (unsigned long long)v);
+        else atomicAdd(reinterpret_cast<double*>(rec + d.rec_sum), __longlong_as_double((long long)v));
+    }
+    if (d.flags & (F_MIN | F_MAX)) {
+        uint64_t m = order_map(is_int ? v : canon_nan(v), is_int);
+        if ((d.flags & F_MIN) && m < __ldcg(rec + d.rec_min)) atomicMin(reinterpret_cast<unsigned long long*>(rec + d.rec_min), (unsigned long long)m);
+        if ((d.flags & F_MAX) && m > __ldcg(rec + d.rec_max)) atomicMax(reinterpret_cast<unsigned long long*>(rec + d.rec_max), (unsigned long long)m);
+    }
+}
+
+struct SinkBase {
+    __device__ __forceinline__ void emit(int, const uint64_t (&)[R], uint32_t, RowCtx&) {}
+};
+struct AggSink : SinkBase {
+    uint32_t sel;
+    uint64_t key[MAX_KEYS][R];
+    uint32_t keyok[MAX_KEYS];
+    uint64_t in[MAX_INPUTS][R];
+    uint32_t inok[MAX_INPUTS];
+    __device__ __forceinline__ void set_sel(const uint64_t (&v)[R], uint32_t ok, RowCtx& rc) {
+        uint32_t m = 0;
+#pragma unroll
+        for (int r = 0; r < R; r++) m |= (uint32_t)(v[r] & 1u) << r;
+        sel = m & ok & rc.inr;
+        rc.active = sel;
+    }
+    __device__ __forceinline__ void set_key(int k, const uint64_t (&v)[R], uint32_t ok, RowCtx&) {
+#pragma unroll
+        for (int kk = 0; kk < MAX_KEYS; kk++)
+            if (kk == k) {
+#pragma unroll
+                for (int r = 0; r < R; r++) key[kk][r] = v[r];
+                keyok[kk] = ok;
+            }
+    }
+    __device__ __forceinline__ void set_in(int i, const uint64_t (&v)[R], uint32_t ok, RowCtx&) {
+#pragma unroll
+        for (int ii = 0; ii < MAX_INPUTS; ii++)
+            if (ii == i) {
+#pragma unroll
+                for (int r = 0; r < R; r++) in[ii][r] = v[r];
+                inok[ii] = ok;
+            }
+    }
+};
+
+// Look the key up in the CTA directory; returns the front-end group id or -1 (row goes global).
+__device__ __forceinline__ int dir_lookup(const AggArgs& A, uint64_t* dirkeys, uint32_t* dirstate, uint32_t* gid2slot,
+                                          uint32_t* dir_count, uint64_t h, const uint64_t (&kw)[MAX_KEYS], uint32_t nullmask) {
+    const int KW = A.nkeys + 1;
+    uint32_t slot = (uint32_t)(h >> 40) & (DIR_SLOTS - 1);
+#pragma unroll 1
+    for (int probe = 0; probe < 8; probe++) {
+        uint32_t st = *reinterpret_cast<volatile uint32_t*>(dirstate + slot);
+        if (st == DIR_EMPTY) {
+            uint32_t old = atomicCAS(dirstate + slot, DIR_EMPTY, DIR_BUSY);
+            if (old == DIR_EMPTY) {
+                uint32_t gid = atomicAdd(dir_count, 1u);
+                uint64_t* dk = dirkeys + slot * KW;
+                dk[0] = nullmask;
+#pragma unroll
+                for (int k = 0; k < MAX_KEYS; k++) if (k < A.nkeys) dk[1 + k] = kw[k];
+                bool fits = gid < (uint32_t)A.fe_groups;
+                if (fits) gid2slot[gid] = slot;
+                __threadfence_block();
+                *reinterpret_cast<volatile uint32_t*>(dirstate + slot) = fits ? gid + 2 : DIR_GLOBAL;
+                return fits ? (int)gid : -1;
+            }
+            st = old;
+        }
+        if (st == DIR_BUSY) return -1;             // being published: this row takes the global path
+        const uint64_t* dk = dirkeys + slot * KW;
+        bool eq = dk[0] == (uint64_t)nullmask;
+#pragma unroll
+        for (int k = 0; k < MAX_KEYS; k++) if (k < A.nkeys) eq &= dk[1 + k] == kw[k];
+        if (eq) return st == DIR_GLOBAL ? -1 : (int)(st - 2);
+        slot = (slot + 1) & (DIR_SLOTS - 1);
+    }
+    return -1;
+}
+
+__global__ void __launch_bounds__(BLOCK, 1) k_hash_aggregate(const __grid_constant__ AggArgs A) {
+    extern __shared__ __align__(16) unsigned char smem[];
+    __shared__ long long s_tile[2];
+    __shared__ uint32_t s_dir_count;
+    uint64_t* dirkeys = reinterpret_cast<uint64_t*>(smem + A.off_dirkeys);
+    uint32_t* dirstate = reinterpret_cast<uint32_t*>(smem + A.off_dirstate);
+    uint32_t* gid2slot = reinterpret_cast<uint32_t*>(smem + A.off_gid2slot);
+    uint64_t* gslot = reinterpret_cast<uint64_t*>(smem + A.off_gslot);
+    uint64_t* mm = reinterpret_cast<uint64_t*>(smem + A.off_mm);
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int NI = A.ninputs, NS = A.fe_nsum, NM = A.fe_nmm, FG = A.fe_groups;
+    // lane-private accumulators of this warp: cnt[(gid*NI + i)*32 + lane], sum[(gid*NS + s)*32 + lane]
+    uint32_t* cnt = reinterpret_cast<uint32_t*>(smem + A.off_cnt) + (size_t)warp * FG * NI * 32;
+    uint64_t* sum = reinterpret_cast<uint64_t*>(smem + A.off_sum) + (size_t)warp * FG * NS * 32;
+
+    for (int i = threadIdx.x * 4; i < A.smem_bytes; i += BLOCK * 4) *reinterpret_cast<uint32_t*>(smem + i) = 0;
+    __syncthreads();
+    for (int i = threadIdx.x; i < FG * NM; i += BLOCK) mm[i] = ((A.fe_mm_ismin >> (i % NM)) & 1u) ? ~0ULL : 0ULL;
+    if (threadIdx.x == 0) s_dir_count = 0;
+    __syncthreads();
+
+    AggSink sink;
+    Stack st;
+    bool bypass = FG == 0;
+    for (int it = 0;; it++) {
+        if (threadIdx.x == 0) {
+            unsigned long long g = *reinterpret_cast<volatile unsigned long long*>(A.ngroups);
+            s_tile[it & 1] = (g > A.stop_threshold) ? -1LL : (long long)atomicAdd(A.ticket, 1u);
+        }
+        __syncthreads();
+        long long tile = s_tile[it & 1];
+        if (tile < 0) break;
+        tile += A.tile_begin;
+        if (tile >= A.ntiles) break;
+        RowCtx rc;
+        rowctx_init(rc, tile, A.n, A.err);
+        sink.sel = rc.inr;
+        run(A.prog, 0, A.prog.ninsn, st, rc, sink);
+
+        int fe_hits = 0, rows = 0;
+#pragma unroll
+        for (int r = 0; r < R; r++) {
+            if (!((sink.sel >> r) & 1u)) continue;
+            uint64_t kw[MAX_KEYS];
+            uint32_t nullmask = 0;
+#pragma unroll
+            for (int k = 0; k < MAX_KEYS; k++) {
+                kw[k] = 0;
+                if (k < A.nkeys) {
+                    if ((sink.keyok[k] >> r) & 1u) kw[k] = ((A.key_f64_mask >> k) & 1u) ? canon_nan(sink.key[k][r]) : sink.key[k][r];
+                    else nullmask |= 1u << k;
+                }
+            }
+            const uint64_t h = hash_key(kw, nullmask, A.nkeys);
+            int gid = -1;
+            if (!bypass) gid = dir_lookup(A, dirkeys, dirstate, gid2slot, &s_dir_count, h, kw, nullmask);
+            rows++;
+            if (gid >= 0) {
+                fe_hits++;
+#pragma unroll
+                for (int i = 0; i < MAX_INPUTS; i++) {
+                    if (i < NI && ((sink.inok[i] >> r) & 1u)) {
+                        const AggInput d = A.in[i];
+                        const uint64_t v = sink.in[i][r];
+                        cnt[(gid * NI + i) * 32 + lane] += 1u;
+                        if (d.flags & F_SUM) {
+                            uint64_t* p = sum + (gid * NS + d.fe_sum) * 32 + lane;
+                            if (d.flags & F_INT) *p += v;
+                            else *p = (uint64_t)__double_as_longlong(__dadd_rn(__longlong_as_double((long long)*p), __longlong_as_double((long long)v)));
+                        }
+                        if (d.flags & (F_MIN | F_MAX)) {
+                            const bool is_int = d.flags & F_INT;
+                            uint64_t m = order_map(is_int ? v : canon_nan(v), is_int);
+                            if (d.flags & F_MIN) { uint64_t* p = mm + gid * NM + d.fe_min; if (m < *reinterpret_cast<volatile uint64_t*>(p)) atomicMin(reinterpret_cast<unsigned long long*>(p), (unsigned long long)m); }
+                            if (d.flags & F_MAX) { uint64_t* p = mm + gid * NM + d.fe_max; if (m > *reinterpret_cast<volatile uint64_t*>(p)) atomicMax(reinterpret_cast<unsigned long long*>(p), (unsigned long long)m); }
+                        }
+                    }
+                }
+            } else {
+                uint64_t* rec = table_find_or_insert(A, h, kw, nullmask);
+#pragma unroll
+                for (int i = 0; i < MAX_INPUTS; i++)
+                    if (i < NI && ((sink.inok[i] >> r) & 1u)) global_accumulate(rec, A.in[i], sink.in[i][r]);
+            }
+        }
+        // once the directory is full and this warp mostly misses it, stop probing it (high cardinality)
+        if (!bypass) {
+            int hits = fe_hits, tot = rows;
+#pragma unroll
+            for (int o = 16; o; o >>= 1) { hits += __shfl_xor_sync(0xffffffffu, hits, o); tot += __shfl_xor_sync(0xffffffffu, tot, o); }
+            if (tot >= 64 && hits * 8 < tot && *reinterpret_cast<volatile uint32_t*>(&s_dir_count) >= (uint32_t)FG) bypass = true;
+        }
+    }
+
+    // ---- merge the front end into the global table ---------------------------------------------------
+    __syncthreads();
+    const int G = min((int)s_dir_count, FG);
+    for (int g = threadIdx.x; g < G; g += BLOCK) {
+        const uint64_t* dk = dirkeys + gid2slot[g] * (A.nkeys + 1);
+        uint64_t kw[MAX_KEYS];
+#pragma unroll
+        for (int k = 0; k < MAX_KEYS; k++) kw[k] = k < A.nkeys ? dk[1 + k] : 0;
+        uint32_t nullmask = (uint32_t)dk[0];
+        uint64_t* rec = table_find_or_insert(A, hash_key(kw, nullmask, A.nkeys), kw, nullmask);
+        gslot[g] = (uint64_t)(rec - A.table);
+    }
+    __syncthreads();
+    for (int g = 0; g < G; g++) {
+        uint64_t* rec = A.table + gslot[g];
+        for (int i = 0; i < NI; i++) {
+            unsigned long long c = cnt[(g * NI + i) * 32 + lane];
+#pragma unroll
+            for (int o = 16; o; o >>= 1) c += __shfl_xor_sync(0xffffffffu, c, o);
+            if (c == 0) continue;                                   // this warp saw no non-null value of input i in group g
+            const AggInput d = A.in[i];
+            if (lane == 0) atomicAdd(reinterpret_cast<unsigned long long*>(rec + d.rec_nn), c);
+            if (d.flags & F_SUM) {
+                uint64_t x = sum[(g * NS + d.fe_sum) * 32 + lane];
+                if (d.flags & F_INT) {
+#pragma unroll
+                    for (int o = 16; o; o >>= 1) x += __shfl_xor_sync(0xffffffffu, x, o);
+                    if (lane == 0) atomicAdd(reinterpret_cast<unsigned long long*>(rec + d.rec_sum), (unsigned long long)x);
+                } else {
+                    double f = __longlong_as_double((long long)x);
+#pragma unroll
+                    for (int o = 16; o; o >>= 1) f = __dadd_rn(f, __shfl_xor_sync(0xffffffffu, f, o));
+                    if (lane == 0) atomicAdd(reinterpret_cast<double*>(rec + d.rec_sum), f);
+                }
+            }
+        }
+    }
+    for (int t = threadIdx.x; t < G * NM; t += BLOCK) {
+        const int g = t / NM, m = t % NM;
+        const uint64_t v = mm[t];
+        uint64_t* p = A.table + gslot[g] + A.fe_mm_word[m];
+        if ((A.fe_mm_ismin >> m) & 1u) { if (v != ~0ULL) atomicMin(reinterpret_cast<unsigned long long*>(p), (unsigned long long)v); }
+        else if (v != 0ULL) atomicMax(reinterpret_cast<unsigned long long*>(p), (unsigned long long)v);
+    }
+}
+
+// ---- table maintenance ---------------------------------------------------------------------------------------
+__global__ void k_rehash(const uint64_t* __restrict__ old_table, uint64_t old_cap, uint64_t* table, uint64_t cap_mask, int stride, int nkeys) {
+    for (uint64_t s = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; s < old_cap; s += (uint64_t)gridDim.x * blockDim.x) {
+        const uint64_t* src = old_table + s * stride;
+        if ((uint32_t)src[0] != HDR_FULL) continue;
+        uint64_t kw[MAX_KEYS];
+#pragma unroll
+        for (int k = 0; k < MAX_KEYS; k++) kw[k] = k < nkeys ? src[1 + k] : 0;
+        uint64_t slot = hash_key(kw, (uint32_t)(src[0] >> 32), nkeys) & cap_mask;
+        while (true) {
+            uint64_t* rec = table + slot * stride;
+            if (atomicCAS(reinterpret_cast<unsigned long long*>(rec), 0ULL, (unsigned long long)src[0]) == 0ULL) {
+                for (int w = 1; w < stride; w++) rec[w] = src[w];
+                break;
+            }
+            slot = (slot + 1) & cap_mask;
+        }
+    }
+}
+
+// Merge records produced elsewhere (other ranks' partials) into this table: the merge step of
+// main()'s second query, MAX(max)/MIN(min)/SUM(sum)/SUM(count) (Main.kt:1320).
+__global__ void k_merge_records(const AggArgs A, const uint64_t* __restrict__ recs, uint64_t nrecs) {
+    for (uint64_t s = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; s < nrecs; s += (uint64_t)gridDim.x * blockDim.x) {
+        const uint64_t* src = recs + s * A.stride;
+        if ((uint32_t)src[0] != HDR_FULL) continue;
+        uint64_t kw[MAX_KEYS];
+#pragma unroll
+        for (int k = 0; k < MAX_KEYS; k++) kw[k] = k < A.nkeys ? src[1 + k] : 0;
+        uint32_t nullmask = (uint32_t)(src[0] >> 32);
+        uint64_t* rec = table_find_or_insert(A, hash_key(kw, nullmask, A.nkeys), kw, nullmask);
+        for (int i = 0; i < A.ninputs; i++) {
+            const AggInput d = A.in[i];
+            uint64_t c = src[d.rec_nn];
+            if (!c) continue;
+            atomicAdd(reinterpret_cast<unsigned long long*>(rec + d.rec_nn), (unsigned long long)c);
+            if (d.flags & F_SUM) {
+                if (d.flags & F_INT) atomicAdd(reinterpret_cast<unsigned long long*>(rec + d.rec_sum), (unsigned long long)src[d.rec_sum]);
+                else atomicAdd(reinterpret_cast<double*>(rec + d.rec_sum), __longlong_as_double((long long)src[d.rec_sum]));
+            }
+            if (d.flags & F_MIN) atomicMin(reinterpret_cast<unsigned long long*>(rec + d.rec_min), (unsigned long long)src[d.rec_min]);
+            if (d.flags & F_MAX) atomicMax(reinterpret_cast<unsigned long long*>(rec + d.rec_max), (unsigned long long)src[d.rec_max]);
+        }
+    }
+}
+
+// Compact FULL records into a dense array (for exchange between ranks); optional hash partitioning.
+__global__ void k_collect_records(const uint64_t* __restrict__ table, uint64_t cap, int stride, int nkeys, uint64_t* out,
+                                  unsigned long long* counters, int nparts, uint64_t part_capacity) {
+    for (uint64_t s = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; s < cap; s += (uint64_t)gridDim.x * blockDim.x) {
+        const uint64_t* src = table + s * stride;
+        if ((uint32_t)src[0] != HDR_FULL) continue;
+        int part = 0;
+        if (nparts > 1) {
+            uint64_t kw[MAX_KEYS];
+#pragma unroll
+            for (int k = 0; k < MAX_KEYS; k++) kw[k] = k < nkeys ? src[1 + k] : 0;
+            part = (int)((hash_key(kw, (uint32_t)(src[0] >> 32), nkeys) >> 20) % (uint64_t)nparts);
+        }
+        unsigned long long pos = atomicAdd(counters + part, 1ULL);
+        uint64_t* dst = out + ((uint64_t)part * part_capacity + pos) * stride;
+        for (int w = 0; w < stride; w++) dst[w] = src[w];
+    }
+}
+
+// ---- finalize: one output row per FULL record (Main.kt:639-647) -------------------------------------------------
+struct FinKey { void* data; uint32_t* validity; int32_t type; int32_t _pad; };
+struct FinAgg { void* data; uint32_t* validity; int32_t kind, word, nn_word, is_int, out_type, _pad; };
+struct FinArgs {
+    const uint64_t* table; uint64_t cap; int32_t stride, nkeys, naggs, _pad;
+    FinKey keys[MAX_KEYS];
+    FinAgg aggs[2 * MAX_INPUTS + 4];
+    unsigned long long* pos;
+};
+
+__global__ void k_finalize(const __grid_constant__ FinArgs F) {
+    const int lane = threadIdx.x & 31;
+    uint64_t total = (F.cap + 31) / 32 * 32;
+    for (uint64_t s = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; s < total; s += (uint64_t)gridDim.x * blockDim.x) {
+        const uint64_t* rec = F.table + s * F.stride;
+        bool full = s < F.cap && (uint32_t)rec[0] == HDR_FULL;
+        uint32_t b = __ballot_sync(0xffffffffu, full);
+        if (!b) continue;
+        unsigned long long base = 0;
+        if (lane == __ffs(b) - 1) base = atomicAdd(F.pos, (unsigned long long)__popc(b));
+        base = __shfl_sync(0xffffffffu, base, __ffs(b) - 1);
+        if (!full) continue;
+        const uint64_t row = base + __popc(b & ((1u << lane) - 1u));
+        const uint32_t nullmask = (uint32_t)(rec[0] >> 32);
+        for (int k = 0; k < F.nkeys; k++) {
+            const FinKey o = F.keys[k];
+            const uint64_t v = rec[1 + k];
+            const bool valid = !((nullmask >> k) & 1u);
+            if (o.validity && valid) atomicOr(o.validity + (row >> 5), 1u << (row & 31));
+            switch (o.type) {
+                case KQ_F64: case KQ_I64: case KQ_UTF8: reinterpret_cast<uint64_t*>(o.data)[row] = v; break;   // UTF8: packed, expanded later
+                case KQ_DATE32: case KQ_I32: reinterpret_cast<uint32_t*>(o.data)[row] = (uint32_t)v; break;
+                case KQ_BOOL: if (v & 1u) atomicOr(reinterpret_cast<uint32_t*>(o.data) + (row >> 5), 1u << (row & 31)); break;
+            }
+        }
+        for (int a = 0; a < F.naggs; a++) {
+            const FinAgg o = F.aggs[a];
+            const uint64_t nn = rec[o.nn_word];
+            if (o.kind == KQ_AGG_COUNT) { reinterpret_cast<uint64_t*>(o.data)[row] = nn; continue; }   // Int64, never null (rule E7)
+            if (nn == 0) continue;                                                                    // all-null group => null (R9)
+            atomicOr(o.validity + (row >> 5), 1u << (row & 31));
+            uint64_t v = rec[o.word];
+            if (o.kind != KQ_AGG_SUM) v = order_unmap(v, o.is_int);
+            if (o.out_type == KQ_DATE32) reinterpret_cast<uint32_t*>(o.data)[row] = (uint32_t)v;
+            else reinterpret_cast<uint64_t*>(o.data)[row] = v;
+        }
+    }
+}
+
+struct PackedLen {
+    const uint64_t* packed; const uint32_t* validity;
+    __device__ __forceinline__ int operator()(long long i) const {
+        if (validity && !((validity[i >> 5] >> (i & 31)) & 1u)) return 0;
+        return (int)(packed[i] >> 56);
+    }
+};
+__global__ void k_unpack_utf8(const uint64_t* __restrict__ packed, const int32_t* __restrict__ off, uint64_t n, uint8_t* out) {
+    for (uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; i < n; i += (uint64_t)gridDim.x * blockDim.x) {
+        int len = off[i + 1] - off[i];
+        uint64_t p = packed[i];
+        for (int b = 0; b < len; b++) out[off[i] + b] = (uint8_t)(p >> (8 * b));
+    }
+}
+
+int launch_check(kq_ctx* ctx, const char* what) {
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) return kq_cuda_fail(ctx, e, what);
+    ctx->launches++;
+    return KQ_OK;
+}
+int small_grid(kq_ctx* ctx, uint64_t items) {
+    uint64_t g = (items + 255) / 256, cap = (uint64_t)ctx->sm_count * 8;
+    return (int)std::max<uint64_t>(1, std::min(g, cap));
+}
+
+}  // namespace
+
+// ---- host state ------------------------------------------------------------------------------------------------------
+struct kq_hashagg {
+    std::atomic<int> rc{1};
+    kq_ctx* ctx = nullptr;
+    kq_expr* pred = nullptr;
+    std::vector<kq_expr*> groups;
+    std::vector<int> agg_kinds;
+    std::vector<int> agg_input_of;          // aggregate -> distinct input index
+    std::vector<kq_expr*> inputs;           // distinct aggregate input expressions
+    std::vector<bool> input_count_only;     // input used by COUNT only: validity is enough
+    // fixed at the first batch
+    bool typed = false;
+    std::vector<int> key_types, input_types;
+    // record layout (fixed at create)
+    int stride = 0;
+    AggInput in[MAX_INPUTS];
+    uint64_t rec_init[MAX_REC_WORDS];
+    // table
+    uint64_t* table = nullptr;
+    uint64_t capacity = 0;
+    unsigned long long* d_counters = nullptr;   // [0] ngroups, [1] ticket (low 32 bits)
+    int64_t ngroups_host = 0;
+    int64_t expected_groups = 0;
+};
+
+static bool expr_equal(const kq_expr* a, const kq_expr* b) {
+    if (a == b) return true;
+    if (!a || !b || a->kind != b->kind) return false;
+    switch (a->kind) {
+        case KQ_EX_COL: return a->col == b->col;
+        case KQ_EX_LIT: return a->type == b->type && a->is_null == b->is_null && a->i == b->i && memcmp(&a->f, &b->f, 8) == 0 && a->s == b->s;
+        case KQ_EX_CAST: return a->type == b->type && expr_equal(a->l, b->l);
+        case KQ_EX_BIN: return a->op == b->op && expr_equal(a->l, b->l) && expr_equal(a->r, b->r);
+    }
+    return false;
+}
+
+static int table_alloc(kq_ctx* ctx, kq_hashagg* h, uint64_t capacity) {
+    size_t bytes = (size_t)capacity * h->stride * 8;
+    KQ_RET(kq_dev_alloc(ctx, bytes, (void**)&h->table));
+    KQ_CUDA(ctx, cudaMemsetAsync(h->table, 0, bytes, ctx->stream));
+    h->capacity = capacity;
+    return KQ_OK;
+}
+
+static int table_grow(kq_ctx* ctx, kq_hashagg* h, uint64_t new_capacity) {
+    uint64_t* old = h->table; uint64_t old_cap = h->capacity;
+    h->table = nullptr;
+    int st = table_alloc(ctx, h, new_capacity);
+    if (st != KQ_OK) { h->table = old; h->capacity = old_cap; return st; }
+    k_rehash<<<small_grid(ctx, old_cap), 256, 0, ctx->stream>>>(old, old_cap, h->table, new_capacity - 1, h->stride, (int)h->groups.size());
+    st = launch_check(ctx, "k_rehash");
+    kq_dev_free(ctx, old);
+    return st;
+}
+
+static void fill_common_args(kq_hashagg* h, AggArgs& A) {
+    A.nkeys = (int)h->groups.size();
+    A.ninputs = (int)h->inputs.size();
+    A.stride = h->stride;
+    memcpy(A.in, h->in, sizeof h->in);
+    memcpy(A.rec_init, h->rec_init, sizeof h->rec_init);
+    A.table = h->table;
+    A.cap_mask = h->capacity - 1;
+    A.ngroups = h->d_counters;
+    A.ticket = (unsigned int*)(h->d_counters + 1);
+    A.err = h->ctx->d_err;
+    A.stop_threshold = ~0ULL;
+}
+
+extern "C" {
+
+int kq_hashagg_create(kq_ctx* ctx, kq_expr* pred, kq_expr* const* group_exprs, int ngroup, const int* agg_kinds,
+                      kq_expr* const* agg_inputs, int nagg, int64_t expected_groups, kq_hashagg** out) {
+    if (!ctx || !out || ngroup < 0 || nagg < 0) return KQ_ERR_ILLEGAL_ARGUMENT;
+    if (ngroup > MAX_KEYS) return kq_fail(ctx, KQ_ERR_UNSUPPORTED, "more than %d group expressions", MAX_KEYS);
+    for (int i = 0; i < nagg; i++)
+        if (agg_kinds[i] < KQ_AGG_MAX || agg_kinds[i] > KQ_AGG_COUNT)
+            return kq_fail(ctx, KQ_ERR_ILLEGAL_STATE, "Unsupported aggregate function: %d", agg_kinds[i]);   // Main.kt:696
+    cudaSetDevice(ctx->device);
+    kq_hashagg* h = new kq_hashagg();
+    h->ctx = ctx;
+    h->expected_groups = expected_groups;
+    if (pred) { pred->rc.fetch_add(1); h->pred = pred; }
+    for (int i = 0; i < ngroup; i++) { group_exprs[i]->rc.fetch_add(1); h->groups.push_back(group_exprs[i]); }
+    int flags[MAX_INPUTS] = {0};
+    for (int i = 0; i < nagg; i++) {
+        int idx = -1;
+        for (size_t j = 0; j < h->inputs.size(); j++) if (expr_equal(h->inputs[j], agg_inputs[i])) { idx = (int)j; break; }
+        if (idx < 0) {
+            if (h->inputs.size() >= (size_t)MAX_INPUTS) { kq_hashagg_free(h); return kq_fail(ctx, KQ_ERR_UNSUPPORTED, "more than %d distinct aggregate inputs", MAX_INPUTS); }
+            agg_inputs[i]->rc.fetch_add(1);
+            h->inputs.push_back(agg_inputs[i]);
+            idx = (int)h->inputs.size() - 1;
+        }
+        h->agg_kinds.push_back(agg_kinds[i]);
+        h->agg_input_of.push_back(idx);
+        if (agg_kinds[i] == KQ_AGG_SUM) flags[idx] |= F_SUM;
+        if (agg_kinds[i] == KQ_AGG_MIN) flags[idx] |= F_MIN;
+        if (agg_kinds[i] == KQ_AGG_MAX) flags[idx] |= F_MAX;
+    }
+    // record layout: [0] header {state:32, key nullmask:32}, [1..K] key words, then per input: nn, sum, min, max
+    int w = 1 + ngroup;
+    for (int i = 0; i < MAX_REC_WORDS; i++) h->rec_init[i] = 0;
+    for (size_t i = 0; i < h->inputs.size(); i++) {
+        AggInput& d = h->in[i];
+        d.flags = flags[i];
+        d.rec_nn = w++;
+        d.rec_sum = (flags[i] & F_SUM) ? w++ : -1;
+        d.rec_min = (flags[i] & F_MIN) ? w++ : -1;
+        d.rec_max = (flags[i] & F_MAX) ? w++ : -1;
+        if (d.rec_min >= 0) h->rec_init[d.rec_min] = ~0ULL;
+        d.fe_sum = d.fe_min = d.fe_max = -1;
+        h->input_count_only.push_back(flags[i] == 0);
+    }
+    h->stride = (w + 3) / 4 * 4;
+    if (h->stride > MAX_REC_WORDS) { kq_hashagg_free(h); return kq_fail(ctx, KQ_ERR_UNSUPPORTED, "aggregate record too wide"); }
+    cudaError_t e = cudaMalloc(&h->d_counters, 64);
+    if (e == cudaSuccess) e = cudaMemsetAsync(h->d_counters, 0, 64, ctx->stream);
+    if (e != cudaSuccess) { kq_hashagg_free(h); return kq_cuda_fail(ctx, e, "cudaMalloc"); }
+    uint64_t cap = 1ULL << 16;
+    while ((int64_t)cap < expected_groups * 2) cap <<= 1;
+    int st = table_alloc(ctx, h, cap);
+    if (st != KQ_OK) { kq_hashagg_free(h); return st; }
+    *out = h;
+    return KQ_OK;
+}
+
+int kq_hashagg_free(kq_hashagg* h) {
+    if (!h) return KQ_OK;
+    if (h->rc.fetch_sub(1) == 1) {
+        cudaSetDevice(h->ctx->device);
+        kq_expr_free(h->pred);
+        for (kq_expr* e : h->groups) kq_expr_free(e);
+        for (kq_expr* e : h->inputs) kq_expr_free(e);
+        kq_dev_free(h->ctx, h->table);
+        if (h->d_counters) { cudaStreamSynchronize(h->ctx->stream); cudaFree(h->d_counters); }
+        delete h;
+    }
+    return KQ_OK;
+}
+
+int kq_hashagg_update(kq_ctx* ctx, kq_hashagg* h, kq_batch* input) {
+    if (!ctx || !h || !input) return KQ_ERR_ILLEGAL_ARGUMENT;
+    cudaSetDevice(ctx->device);
+    int64_t n; KQ_RET(kq_batch_resolve_rows(ctx, input, &n));
+    for (kq_col* c : input->cols) KQ_RET(kq_col_resolve_rows(ctx, c, nullptr));
+
+    // compile: [predicate, SET_SEL] keys..., inputs...
+    KqCompiler cc;
+    KQ_RET(cc.begin(ctx, input));
+    if (h->pred) {
+        int t; bool nl;
+        KQ_RET(cc.value(h->pred, &t, &nl));
+        if (t != KQ_BOOL) return kq_fail(ctx, KQ_ERR_ILLEGAL_STATE, "filter predicate is not Bool");
+        KQ_RET(cc.sink(OP_SET_SEL, 0));
+    }
+    std::vector<int> kt, it;
+    uint32_t key_f64_mask = 0;
+    for (size_t k = 0; k < h->groups.size(); k++) {
+        int t; bool nl;
+        KQ_RET(cc.key_value(h->groups[k], &t, &nl));
+        KQ_RET(cc.sink(OP_SET_KEY, (int)k));
+        if (t == KQ_F64) key_f64_mask |= 1u << k;
+        kt.push_back(t);
+    }
+    for (size_t i = 0; i < h->inputs.size(); i++) {
+        int t; bool nl;
+        KQ_RET(cc.infer(h->inputs[i], &t, &nl));
+        if (h->input_count_only[i]) KQ_RET(cc.validity_only(h->inputs[i]));
+        else {
+            int fl = h->in[i].flags;
+            // MaxAccumulator throws UnsupportedOperationException for other types (Main.kt:548-550)
+            if (t != KQ_F64 && t != KQ_I64 && !(t == KQ_DATE32 && !(fl & F_SUM)))
+                return kq_fail(ctx, KQ_ERR_UNSUPPORTED, "%s is not implemented for data type %d", (fl & F_SUM) ? "SUM" : "MIN/MAX", t);
+            int t2; bool n2;
+            KQ_RET(cc.value(h->inputs[i], &t2, &n2));
+        }
+        KQ_RET(cc.sink(OP_SET_IN, (int)i));
+        it.push_back(t);
+    }
+    if (!h->typed) { h->key_types = kt; h->input_types = it; h->typed = true; }
+    else if (kt != h->key_types || it != h->input_types) return kq_fail(ctx, KQ_ERR_ILLEGAL_STATE, "batch schema differs from earlier batches");
+    for (size_t i = 0; i < h->inputs.size(); i++) {
+        if (it[i] != KQ_F64) h->in[i].flags |= F_INT; else h->in[i].flags &= ~F_INT;
+        bool is_int = h->in[i].flags & F_INT;
+        if (h->in[i].rec_max >= 0) h->rec_init[h->in[i].rec_max] = 0ULL;
+        (void)is_int;
+    }
+    if (n == 0) return KQ_OK;
+
+    AggArgs A;
+    memset(&A, 0, sizeof A);
+    A.prog = cc.prog;
+    A.n = n; A.ntiles = (n + TILE - 1) / TILE;
+    A.key_f64_mask = key_f64_mask;
+
+    // front-end layout
+    int NI = (int)h->inputs.size(), ns = 0, nm = 0;
+    for (int i = 0; i < NI; i++) {
+        AggInput& d = h->in[i];
+        d.fe_sum = (d.flags & F_SUM) ? ns++ : -1;
+        d.fe_min = (d.flags & F_MIN) ? nm++ : -1;
+        d.fe_max = (d.flags & F_MAX) ? nm++ : -1;
+        if (d.fe_sum >= 0) { A.fe_sum_word[d.fe_sum] = d.rec_sum; if (d.flags & F_INT) A.fe_sum_int |= 1u << d.fe_sum; }
+        if (d.fe_min >= 0) { A.fe_mm_word[d.fe_min] = d.rec_min; A.fe_mm_ismin |= 1u << d.fe_min; }
+        if (d.fe_max >= 0) A.fe_mm_word[d.fe_max] = d.rec_max;
+    }
+    A.fe_nsum = ns; A.fe_nmm = nm;
+    int KW = (int)h->groups.size() + 1;
+    int fixed = DIR_SLOTS * KW * 8 + DIR_SLOTS * 4 + FE_MAX_GROUPS * (4 + 8 + 8 * nm) + 64;
+    int per_group = WARPS * 32 * (4 * NI + 8 * ns);
+    int budget = ctx->max_smem_optin - 1024 - fixed;
+    int fg = per_group > 0 ? std::min(FE_MAX_GROUPS, budget / per_group) : FE_MAX_GROUPS;
+    if (fg < 1) fg = 0;
+    A.fe_groups = fg;
+    int off = 0;
+    A.off_dirkeys = off; off += DIR_SLOTS * KW * 8;
+    A.off_gslot = off; off += FE_MAX_GROUPS * 8;
+    A.off_mm = off; off += FE_MAX_GROUPS * 8 * nm;
+    A.off_sum = off; off += WARPS * fg * ns * 32 * 8;
+    A.off_cnt = off; off += WARPS * fg * NI * 32 * 4;
+    A.off_dirstate = off; off += DIR_SLOTS * 4;
+    A.off_gid2slot = off; off += FE_MAX_GROUPS * 4;
+    A.smem_bytes = (off + 15) / 16 * 16;
+    KQ_CUDA(ctx, cudaFuncSetAttribute(k_hash_aggregate, cudaFuncAttributeMaxDynamicSharedMemorySize, A.smem_bytes));
+    int bps = 1;
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&bps, k_hash_aggregate, BLOCK, A.smem_bytes);
+    if (bps < 1) bps = 1;
+    int grid = (int)std::min<int64_t>(A.ntiles, (int64_t)ctx->sm_count * bps);
+    // rows that may still create groups after a block has decided to continue: one tile per resident
+    // block plus its front end
+    const uint64_t margin = (uint64_t)grid * (TILE + FE_MAX_GROUPS);
+
+    int64_t tile_begin = 0;
+    while (tile_begin < A.ntiles) {
+        // capacity rule: stop taking tiles above capacity/2 groups; up to `margin` more may be created
+        // by tiles in flight, and the table must stay below 3/4 full.
+        uint64_t remaining_rows = (uint64_t)std::min<int64_t>(n - tile_begin * TILE, n);
+        uint64_t need = (uint64_t)h->ngroups_host + std::min(margin, remaining_rows);
+        uint64_t cap = h->capacity;
+        while (cap / 2 + std::min(margin, remaining_rows) > cap * 3 / 4 || need > cap * 3 / 4) cap <<= 1;
+        if ((uint64_t)h->ngroups_host > cap / 2) cap <<= 1;
+        if (cap != h->capacity) KQ_RET(table_grow(ctx, h, cap));
+        fill_common_args(h, A);
+        A.tile_begin = tile_begin;
+        A.stop_threshold = h->capacity / 2;
+        KQ_CUDA(ctx, cudaMemsetAsync(h->d_counters + 1, 0, 8, ctx->stream));
+        k_hash_aggregate<<<grid, BLOCK, A.smem_bytes, ctx->stream>>>(A);
+        KQ_RET(launch_check(ctx, "k_hash_aggregate"));
+        uint64_t c[2];
+        KQ_RET(kq_read_u64(ctx, h->d_counters, 2, c));
+        h->ngroups_host = (int64_t)c[0];
+        int64_t taken = (int64_t)(uint32_t)c[1];
+        tile_begin += std::min<int64_t>(taken, A.ntiles - tile_begin);
+        if (tile_begin < A.ntiles) {
+            // stopped early: the table crossed half full. Grow 4x and continue with the next tile.
+            KQ_RET(table_grow(ctx, h, h->capacity * 4));
+        }
+    }
+    return KQ_OK;
+}
+
+int kq_hashagg_num_groups(kq_ctx* ctx, kq_hashagg* h, int64_t* n) {
+    if (!ctx || !h || !n) return KQ_ERR_ILLEGAL_ARGUMENT;
+    uint64_t c; KQ_RET(kq_read_u64(ctx, h->d_counters, 1, &c));
+    h->ngroups_host = (int64_t)c;
+    *n = (int64_t)c;
+    return KQ_OK;
+}
+
+int kq_hashagg_finalize(kq_ctx* ctx, kq_hashagg* h, kq_batch** out) {
+    if (!ctx || !h || !out) return KQ_ERR_ILLEGAL_ARGUMENT;
+    cudaSetDevice(ctx->device);
+    if (!h->typed) return kq_fail(ctx, KQ_ERR_ILLEGAL_STATE, "finalize before any update: output types unknown");
+    KQ_RET(kq_check_device_errors(ctx));
+    int64_t G; KQ_RET(kq_hashagg_num_groups(ctx, h, &G));
+    if (G > 2147483647LL) return kq_fail(ctx, KQ_ERR_UNSUPPORTED, "more than 2^31-1 groups in one output batch");
+    FinArgs F;
+    memset(&F, 0, sizeof F);
+    F.table = h->table; F.cap = h->capacity; F.stride = h->stride;
+    F.nkeys = (int)h->groups.size(); F.naggs = (int)h->agg_kinds.size();
+    std::vector<kq_col*> cols;
+    std::vector<uint64_t*> packed((size_t)F.nkeys, nullptr);
+    int st = KQ_OK;
+    auto fail = [&](int s) { for (kq_col* c : cols) kq_column_free(c); for (uint64_t* p : packed) kq_dev_free(ctx, p); return s; };
+    for (int k = 0; k < F.nkeys; k++) {
+        kq_col* c = nullptr;
+        int t = h->key_types[(size_t)k];
+        if ((st = kq_col_new(ctx, t, G, true, t == KQ_UTF8 ? G * 7 : 0, &c)) != KQ_OK) return fail(st);
+        cols.push_back(c);
+        cudaMemsetAsync(c->validity, 0, (size_t)((G + 63) / 64) * 8, ctx->stream);
+        if (t == KQ_BOOL) cudaMemsetAsync(c->data, 0, (size_t)((G + 63) / 64) * 8, ctx->stream);
+        F.keys[k].validity = c->validity; F.keys[k].type = t;
+        if (t == KQ_UTF8) {
+            if ((st = kq_dev_alloc(ctx, (size_t)G * 8, (void**)&packed[(size_t)k])) != KQ_OK) return fail(st);
+            F.keys[k].data = packed[(size_t)k];
+        } else F.keys[k].data = c->data;
+    }
+    for (int a = 0; a < F.naggs; a++) {
+        int kind = h->agg_kinds[(size_t)a], i = h->agg_input_of[(size_t)a];
+        int in_t = h->input_types[(size_t)i];
+        int out_t = kind == KQ_AGG_COUNT ? KQ_I64 : in_t;
+        kq_col* c = nullptr;
+        if ((st = kq_col_new(ctx, out_t, G, kind != KQ_AGG_COUNT, 0, &c)) != KQ_OK) return fail(st);
+        cols.push_back(c);
+        if (c->validity) cudaMemsetAsync(c->validity, 0, (size_t)((G + 63) / 64) * 8, ctx->stream);
+        FinAgg& o = F.aggs[a];
+        o.data = c->data; o.validity = c->validity; o.kind = kind; o.out_type = out_t;
+        o.nn_word = h->in[i].rec_nn;
+        o.word = kind == KQ_AGG_SUM ? h->in[i].rec_sum : (kind == KQ_AGG_MIN ? h->in[i].rec_min : (kind == KQ_AGG_MAX ? h->in[i].rec_max : h->in[i].rec_nn));
+        o.is_int = in_t != KQ_F64;
+    }
+    unsigned long long* d_pos = h->d_counters + 2;
+    cudaMemsetAsync(d_pos, 0, 8, ctx->stream);
+    F.pos = d_pos;
+    if (G > 0) {
+        k_finalize<<<small_grid(ctx, h->capacity), 256, 0, ctx->stream>>>(F);
+        if ((st = launch_check(ctx, "k_finalize")) != KQ_OK) return fail(st);
+    }
+    for (int k = 0; k < F.nkeys; k++) {
+        if (h->key_types[(size_t)k] != KQ_UTF8) continue;
+        kq_col* c = cols[(size_t)k];
+        int64_t ntiles = (G + SCAN_TILE - 1) / SCAN_TILE + 1;
+        unsigned long long* scratch = nullptr;
+        if ((st = kq_dev_alloc(ctx, (size_t)(ntiles + 4) * 8, (void**)&scratch)) != KQ_OK) return fail(st);
+        cudaMemsetAsync(scratch, 0, (size_t)(ntiles + 4) * 8, ctx->stream);
+        PackedLen pl{packed[(size_t)k], c->validity};
+        int sg = (int)std::max<int64_t>(1, std::min<int64_t>(ntiles, (int64_t)ctx->sm_count * 4));
+        k_exclusive_offsets<PackedLen><<<sg, 256, 0, ctx->stream>>>(pl, h->d_counters, c->offsets, scratch + 4, (unsigned int*)scratch, scratch + 2);
+        if ((st = launch_check(ctx, "k_exclusive_offsets")) != KQ_OK) { kq_dev_free(ctx, scratch); return fail(st); }
+        if (G > 0) {
+            k_unpack_utf8<<<small_grid(ctx, (uint64_t)G), 256, 0, ctx->stream>>>(packed[(size_t)k], c->offsets, (uint64_t)G, (uint8_t*)c->data);
+            if ((st = launch_check(ctx, "k_unpack_utf8")) != KQ_OK) { kq_dev_free(ctx, scratch); return fail(st); }
+        }
+        uint64_t bytes;
+        if ((st = kq_read_u64(ctx, scratch + 2, 1, &bytes)) != KQ_OK) { kq_dev_free(ctx, scratch); return fail(st); }
+        c->data_bytes = (int64_t)bytes;
+        kq_dev_free(ctx, scratch);
+    }
+    for (uint64_t*& p : packed) { kq_dev_free(ctx, p); p = nullptr; }
+    st = kq_batch_create(ctx, cols.data(), (int)cols.size(), G, out);
+    for (kq_col* c : cols) kq_column_free(c);
+    cols.clear();
+    return st;
+}
+
+}  // extern "C"

@@ -1,0 +1,462 @@
+// kq_ops.cu — ProjectionExec, FilterExec and the fused filter+project kernel.
+//
+//   k_project         ProjectionExec.execute for one batch (Main.kt:589-594): every expression of the
+//                     projection evaluated in one pass, one 128-bit store per pair of output rows.
+//   k_filter_project  FilterExec (absent from the reference) fused with the
+//                     projection above it: predicate -> warp ballot/popc ranks -> ordered cross-block
+//                     prefix (decoupled look-back) -> compacted stores, all in a single pass over the
+//                     input (algorithmic bytes only: each input column read once, each output row
+//                     written once).
+#include <algorithm>
+#include <cstring>
+
+#include "kq_compile.h"
+#include "kq_scan.cuh"
+
+using namespace kq;
+
+namespace {
+
+struct DOut {
+    void* data;
+    uint32_t* validity;
+    int32_t type;
+    int32_t _pad;
+};
+
+struct OpArgs {
+    Program prog;
+    int64_t n, ntiles;
+    int32_t sel_end;          // instructions [0, sel_end) evaluate the predicate and end in OP_SET_SEL
+    int32_t nout;
+    DOut outs[MAX_OUT];
+    unsigned long long* tile_desc;
+    unsigned int* ticket;
+    unsigned long long* out_count;
+    int32_t* selvec;
+    uint32_t* err;
+};
+
+struct SinkBase {
+    __device__ __forceinline__ void set_sel(const uint64_t (&)[R], uint32_t, RowCtx&) {}
+    __device__ __forceinline__ void emit(int, const uint64_t (&)[R], uint32_t, RowCtx&) {}
+    __device__ __forceinline__ void set_key(int, const uint64_t (&)[R], uint32_t, RowCtx&) {}
+    __device__ __forceinline__ void set_in(int, const uint64_t (&)[R], uint32_t, RowCtx&) {}
+};
+
+// write the 64 row bits of chunk j (rows warp_base + 64j ...) of a bit-packed buffer
+__device__ __forceinline__ void store_chunk_bits(uint32_t* bits, const RowCtx& rc, int j, uint32_t m) {
+    uint32_t b0 = __ballot_sync(0xffffffffu, (m >> (2 * j)) & 1u);
+    uint32_t b1 = __ballot_sync(0xffffffffu, (m >> (2 * j + 1)) & 1u);
+    int64_t chunk_base = rc.warp_base + j * 64;
+    if (rc.lane == 0 && chunk_base < rc.n) {
+        uint2 w = interleave_ballots(b0, b1);
+        *reinterpret_cast<uint2*>(bits + (chunk_base >> 5)) = w;
+    }
+}
+
+struct ProjectSink : SinkBase {
+    const DOut* outs;
+    __device__ __forceinline__ void emit(int k, const uint64_t (&v)[R], uint32_t ok, RowCtx& rc) {
+        const DOut o = outs[k];
+        if (o.type == KQ_BOOL) {
+            uint32_t m = 0;
+#pragma unroll
+            for (int r = 0; r < R; r++) m |= (uint32_t)(v[r] & 1u) << r;
+            m &= rc.inr;
+#pragma unroll
+            for (int j = 0; j < NCHUNK; j++) store_chunk_bits(reinterpret_cast<uint32_t*>(o.data), rc, j, m);
+        } else if (o.type == KQ_DATE32 || o.type == KQ_I32) {
+#pragma unroll
+            for (int j = 0; j < NCHUNK; j++) {
+                int64_t r0 = rc.row0(j);
+                if (rc.full || r0 < rc.n) stg_v2(reinterpret_cast<uint2*>(o.data) + (r0 >> 1), make_uint2((uint32_t)v[2 * j], (uint32_t)v[2 * j + 1]));
+            }
+        } else {
+#pragma unroll
+            for (int j = 0; j < NCHUNK; j++) {
+                int64_t r0 = rc.row0(j);
+                if (rc.full || r0 < rc.n)
+                    stg_v4(reinterpret_cast<uint4*>(o.data) + (r0 >> 1),
+                           make_uint4((uint32_t)v[2 * j], (uint32_t)(v[2 * j] >> 32), (uint32_t)v[2 * j + 1], (uint32_t)(v[2 * j + 1] >> 32)));
+            }
+        }
+        if (o.validity) {
+#pragma unroll
+            for (int j = 0; j < NCHUNK; j++) store_chunk_bits(o.validity, rc, j, ok & rc.inr);
+        }
+    }
+};
+
+struct CompactSink : SinkBase {
+    const DOut* outs;
+    uint32_t sel;
+    int rank[R];
+    long long base;
+    __device__ __forceinline__ void set_sel(const uint64_t (&v)[R], uint32_t ok, RowCtx& rc) {
+        uint32_t m = 0;
+#pragma unroll
+        for (int r = 0; r < R; r++) m |= (uint32_t)(v[r] & 1u) << r;
+        sel = m & ok & rc.inr;        // TRUE only: null predicate drops the row (rule E3)
+    }
+    __device__ __forceinline__ void emit(int k, const uint64_t (&v)[R], uint32_t ok, RowCtx&) {
+        const DOut o = outs[k];
+#pragma unroll
+        for (int r = 0; r < R; r++) {
+            if ((sel >> r) & 1u) {
+                long long pos = base + rank[r];
+                if (o.type == KQ_BOOL) {
+                    if (v[r] & 1u) atomicOr(reinterpret_cast<uint32_t*>(o.data) + (pos >> 5), 1u << (pos & 31));
+                } else if (o.type == KQ_DATE32 || o.type == KQ_I32) {
+                    reinterpret_cast<uint32_t*>(o.data)[pos] = (uint32_t)v[r];
+                } else {
+                    reinterpret_cast<uint64_t*>(o.data)[pos] = v[r];
+                }
+                if (o.validity && ((ok >> r) & 1u)) atomicOr(o.validity + (pos >> 5), 1u << (pos & 31));
+            }
+        }
+    }
+};
+
+__global__ void __launch_bounds__(BLOCK) k_project(const __grid_constant__ OpArgs A) {
+    ProjectSink sink;
+    sink.outs = A.outs;
+    Stack st;
+    for (int64_t tile = blockIdx.x; tile < A.ntiles; tile += gridDim.x) {
+        RowCtx rc;
+        rowctx_init(rc, tile, A.n, A.err);
+        run(A.prog, 0, A.prog.ninsn, st, rc, sink);
+    }
+}
+
+__global__ void __launch_bounds__(BLOCK) k_filter_project(const __grid_constant__ OpArgs A) {
+    __shared__ long long s_tile;
+    __shared__ int s_wtot[WARPS];
+    __shared__ unsigned long long s_prefix;
+    CompactSink sink;
+    sink.outs = A.outs;
+    Stack st;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const uint32_t lt = (1u << lane) - 1u;
+    while (true) {
+        if (threadIdx.x == 0) s_tile = (long long)atomicAdd(A.ticket, 1u);
+        __syncthreads();
+        const long long tile = s_tile;
+        if (tile >= A.ntiles) break;
+        RowCtx rc;
+        rowctx_init(rc, tile, A.n, A.err);
+        sink.sel = 0;
+        run(A.prog, 0, A.sel_end, st, rc, sink);
+        rc.active = sink.sel;      // projection errors only count on surviving rows (FilterExec runs first)
+        // ranks inside the warp, in row order: chunk j, then lane, then the pair element
+        int wtot = 0;
+#pragma unroll
+        for (int j = 0; j < NCHUNK; j++) {
+            uint32_t s0 = (sink.sel >> (2 * j)) & 1u, s1 = (sink.sel >> (2 * j + 1)) & 1u;
+            uint32_t b0 = __ballot_sync(0xffffffffu, s0), b1 = __ballot_sync(0xffffffffu, s1);
+            int below = __popc(b0 & lt) + __popc(b1 & lt);
+            sink.rank[2 * j] = wtot + below;
+            sink.rank[2 * j + 1] = wtot + below + (int)s0;
+            wtot += __popc(b0) + __popc(b1);
+        }
+        if (lane == 0) s_wtot[warp] = wtot;
+        __syncthreads();
+        int woff = 0, ttot = 0;
+#pragma unroll
+        for (int w = 0; w < WARPS; w++) { int x = s_wtot[w]; if (w < warp) woff += x; ttot += x; }
+        if (warp == 0) {
+            unsigned long long excl = lookback_exclusive(A.tile_desc, tile, (unsigned long long)ttot);
+            if (lane == 0) {
+                s_prefix = excl;
+                if (tile == A.ntiles - 1) *A.out_count = excl + (unsigned long long)ttot;
+            }
+        }
+        __syncthreads();
+        sink.base = (long long)s_prefix + woff;
+        if (A.selvec) {
+#pragma unroll
+            for (int r = 0; r < R; r++)
+                if ((sink.sel >> r) & 1u) A.selvec[sink.base + sink.rank[r]] = (int32_t)(rc.row0(r >> 1) + (r & 1));
+        }
+        run(A.prog, A.sel_end, A.prog.ninsn, st, rc, sink);
+    }
+}
+
+// ---- gathers by selection vector (Utf8 pass-through columns and kq_filter) --------------------------------------
+template <typename T>
+__global__ void k_gather_fixed(const T* __restrict__ in, const uint32_t* __restrict__ in_valid, const int32_t* __restrict__ sel,
+                               const unsigned long long* __restrict__ d_count, T* __restrict__ out, uint32_t* out_valid) {
+    long long m = (long long)*d_count;
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < m; i += (long long)gridDim.x * blockDim.x) {
+        int32_t row = sel[i];
+        out[i] = in[row];
+        if (out_valid && ((in_valid[row >> 5] >> (row & 31)) & 1u)) atomicOr(out_valid + (i >> 5), 1u << (i & 31));
+    }
+}
+__global__ void k_gather_bits(const uint32_t* __restrict__ in, const uint32_t* __restrict__ in_valid, const int32_t* __restrict__ sel,
+                              const unsigned long long* __restrict__ d_count, uint32_t* out, uint32_t* out_valid) {
+    long long m = (long long)*d_count;
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < m; i += (long long)gridDim.x * blockDim.x) {
+        int32_t row = sel[i];
+        if ((in[row >> 5] >> (row & 31)) & 1u) atomicOr(out + (i >> 5), 1u << (i & 31));
+        if (out_valid && ((in_valid[row >> 5] >> (row & 31)) & 1u)) atomicOr(out_valid + (i >> 5), 1u << (i & 31));
+    }
+}
+
+// Utf8 gather: lengths of the selected rows -> exclusive prefix -> output offsets (kq_scan.cuh).
+struct GatherLen {
+    const int32_t* in_off; const uint32_t* in_valid; const int32_t* sel; uint32_t* out_valid;
+    __device__ __forceinline__ int operator()(long long i) const {
+        int32_t row = sel[i];
+        if (out_valid && ((in_valid[row >> 5] >> (row & 31)) & 1u)) atomicOr(out_valid + (i >> 5), 1u << (i & 31));
+        return in_off[row + 1] - in_off[row];
+    }
+};
+__global__ void k_utf8_gather_bytes(const int32_t* __restrict__ in_off, const uint8_t* __restrict__ in_data, const int32_t* __restrict__ sel,
+                                    const unsigned long long* __restrict__ d_count, const int32_t* __restrict__ out_off, uint8_t* out_data) {
+    long long m = (long long)*d_count;
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < m; i += (long long)gridDim.x * blockDim.x) {
+        int32_t row = sel[i];
+        int a = in_off[row], len = in_off[row + 1] - a, o = out_off[i];
+        for (int b = 0; b < len; b++) out_data[o + b] = in_data[a + b];
+    }
+}
+
+int blocks_per_sm(const void* fn) {
+    int nb = 1;
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, fn, BLOCK, 0) != cudaSuccess || nb < 1) nb = 1;
+    return nb;
+}
+
+int launch_check(kq_ctx* ctx, const char* what) {
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) return kq_cuda_fail(ctx, e, what);
+    ctx->launches++;
+    return KQ_OK;
+}
+
+int small_grid(kq_ctx* ctx, int64_t items) {
+    int64_t g = (items + 255) / 256, cap = (int64_t)ctx->sm_count * 8;
+    return (int)std::max<int64_t>(1, std::min(g, cap));
+}
+
+// Gather one whole column by a device-resident selection vector with a device-resident count.
+int gather_column(kq_ctx* ctx, kq_col* in, const int32_t* sel, kq_lazy_count* lazy, int64_t cap_rows, kq_col** out) {
+    kq_col* c = nullptr;
+    bool nullable = in->validity != nullptr;
+    KQ_RET(kq_col_new(ctx, in->type, cap_rows, nullable, in->type == KQ_UTF8 ? in->data_bytes : 0, &c));
+    c->n = -1; c->lazy = lazy; lazy->rc.fetch_add(1);
+    if (nullable) cudaMemsetAsync(c->validity, 0, (size_t)((cap_rows + 63) / 64) * 8, ctx->stream);
+    int g = small_grid(ctx, cap_rows);
+    int st = KQ_OK;
+    switch (in->type) {
+        case KQ_F64: case KQ_I64:
+            k_gather_fixed<uint64_t><<<g, 256, 0, ctx->stream>>>((const uint64_t*)in->data, in->validity, sel, lazy->d_slot, (uint64_t*)c->data, c->validity);
+            st = launch_check(ctx, "k_gather_fixed"); break;
+        case KQ_DATE32: case KQ_I32:
+            k_gather_fixed<uint32_t><<<g, 256, 0, ctx->stream>>>((const uint32_t*)in->data, in->validity, sel, lazy->d_slot, (uint32_t*)c->data, c->validity);
+            st = launch_check(ctx, "k_gather_fixed"); break;
+        case KQ_BOOL:
+            cudaMemsetAsync(c->data, 0, (size_t)((cap_rows + 63) / 64) * 8, ctx->stream);
+            k_gather_bits<<<g, 256, 0, ctx->stream>>>((const uint32_t*)in->data, in->validity, sel, lazy->d_slot, (uint32_t*)c->data, c->validity);
+            st = launch_check(ctx, "k_gather_bits"); break;
+        case KQ_UTF8: {
+            int64_t ntiles = (cap_rows + SCAN_TILE - 1) / SCAN_TILE + 1;
+            unsigned long long* scratch = nullptr;
+            st = kq_dev_alloc(ctx, (size_t)(ntiles + 2) * 8, (void**)&scratch);
+            if (st != KQ_OK) break;
+            cudaMemsetAsync(scratch, 0, (size_t)(ntiles + 2) * 8, ctx->stream);
+            if ((st = kq_dev_alloc(ctx, 8, (void**)&c->d_utf8_bytes)) != KQ_OK) break;
+            c->data_bytes = -1;
+            int sg = (int)std::max<int64_t>(1, std::min<int64_t>(ntiles, (int64_t)ctx->sm_count * 4));
+            GatherLen gl{in->offsets, in->validity, sel, c->validity};
+            k_exclusive_offsets<GatherLen><<<sg, 256, 0, ctx->stream>>>(gl, lazy->d_slot, c->offsets, scratch + 2, (unsigned int*)scratch, c->d_utf8_bytes);
+            st = launch_check(ctx, "k_exclusive_offsets");
+            if (st == KQ_OK) {
+                k_utf8_gather_bytes<<<g, 256, 0, ctx->stream>>>(in->offsets, (const uint8_t*)in->data, sel, lazy->d_slot, c->offsets, (uint8_t*)c->data);
+                st = launch_check(ctx, "k_utf8_gather_bytes");
+            }
+            kq_dev_free(ctx, scratch);
+            break;
+        }
+        default: st = kq_fail(ctx, KQ_ERR_ILLEGAL_STATE, "unknown column type");
+    }
+    if (st != KQ_OK) { kq_column_free(c); return st; }
+    *out = c;
+    return KQ_OK;
+}
+
+// Shared implementation of kq_project / kq_filter_project / kq_filter / kq_expr_evaluate.
+int run_operator(kq_ctx* ctx, kq_expr* pred, kq_expr* const* exprs, int nexprs, kq_batch* input, bool all_columns,
+                 kq_batch** out, kq_col** selection) {
+    if (!ctx || !input || !out || nexprs < 0) return KQ_ERR_ILLEGAL_ARGUMENT;
+    cudaSetDevice(ctx->device);
+    int64_t n; KQ_RET(kq_batch_resolve_rows(ctx, input, &n));
+    for (kq_col* c : input->cols) KQ_RET(kq_col_resolve_rows(ctx, c, nullptr));
+
+    // expressions of a filter-all: one ColumnExpression per input field
+    std::vector<kq_expr*> owned;
+    std::vector<kq_expr*> ex(exprs, exprs + nexprs);
+    if (all_columns) for (int i = 0; i < (int)input->cols.size(); i++) { owned.push_back(kq_expr_column(i)); ex.push_back(owned.back()); }
+    auto cleanup = [&]() { for (kq_expr* e : owned) kq_expr_free(e); };
+
+    KqCompiler cc;
+    int st = cc.begin(ctx, input);
+    std::vector<kq_col*> outs(ex.size(), nullptr);
+    auto fail = [&](int s) { for (kq_col* c : outs) kq_column_free(c); cleanup(); return s; };
+    if (st != KQ_OK) return fail(st);
+
+    OpArgs A;
+    memset(&A, 0, sizeof A);
+    A.n = n; A.ntiles = (n + TILE - 1) / TILE; A.err = ctx->d_err;
+    kq_lazy_count* lazy = nullptr;
+    if (pred) {
+        int t; bool nl;
+        if ((st = cc.value(pred, &t, &nl)) != KQ_OK) return fail(st);
+        if (t != KQ_BOOL) return fail(kq_fail(ctx, KQ_ERR_ILLEGAL_STATE, "filter predicate is not Bool"));
+        if ((st = cc.sink(OP_SET_SEL, 0)) != KQ_OK) return fail(st);
+        A.sel_end = cc.pc();
+        lazy = kq_lazy_new(ctx);
+        if (!lazy) return fail(kq_fail(ctx, KQ_ERR_OUT_OF_MEMORY, "lazy count"));
+    }
+    auto fail2 = [&](int s) { if (lazy) kq_lazy_release(ctx, lazy); return fail(s); };
+
+    // classify outputs: gather (Utf8 pass-through below a filter, or any column of kq_filter with
+    // too many fused outputs), alias (bare column without a filter, rule R4), or fused VM output.
+    std::vector<int> mode(ex.size(), 0);   // 0 = VM, 1 = alias, 2 = gather by selection vector
+    int nvm = 0;
+    for (size_t k = 0; k < ex.size(); k++) {
+        int bc = KqCompiler::bare_column(ex[k]);
+        int t; bool nl;
+        if ((st = cc.infer(ex[k], &t, &nl)) != KQ_OK) return fail2(st);
+        if (bc >= 0 && !pred) mode[k] = 1;
+        else if (bc >= 0 && (t == KQ_UTF8 || nvm >= MAX_OUT)) mode[k] = 2;
+        else {
+            if (t == KQ_UTF8) return fail2(kq_fail(ctx, KQ_ERR_UNSUPPORTED, "expressions cannot produce Utf8 values (only column pass-through)"));
+            if (nvm >= MAX_OUT) return fail2(kq_fail(ctx, KQ_ERR_UNSUPPORTED, "more than %d computed outputs in one kernel", MAX_OUT));
+            mode[k] = 0;
+            int t2; bool n2;
+            if ((st = cc.value(ex[k], &t2, &n2)) != KQ_OK) return fail2(st);
+            kq_col* c = nullptr;
+            if ((st = kq_col_new(ctx, t2, n, n2, 0, &c)) != KQ_OK) return fail2(st);
+            outs[k] = c;
+            if (pred) {
+                c->n = -1; c->lazy = lazy; lazy->rc.fetch_add(1);
+                if (c->validity) cudaMemsetAsync(c->validity, 0, (size_t)((n + 63) / 64) * 8, ctx->stream);
+                if (t2 == KQ_BOOL) cudaMemsetAsync(c->data, 0, (size_t)((n + 63) / 64) * 8, ctx->stream);
+            }
+            A.outs[nvm].data = c->data; A.outs[nvm].validity = c->validity; A.outs[nvm].type = t2;
+            if ((st = cc.sink(OP_EMIT, nvm)) != KQ_OK) return fail2(st);
+            nvm++;
+        }
+    }
+    A.nout = nvm;
+    A.prog = cc.prog;
+
+    bool need_sel = selection != nullptr;
+    for (int m : mode) need_sel |= (m == 2);
+    kq_col* selcol = nullptr;
+    if (pred && need_sel) {
+        if ((st = kq_col_new(ctx, KQ_I32, n, false, 0, &selcol)) != KQ_OK) return fail2(st);
+        selcol->n = -1; selcol->lazy = lazy; lazy->rc.fetch_add(1);
+        A.selvec = (int32_t*)selcol->data;
+    }
+    auto fail3 = [&](int s) { kq_column_free(selcol); return fail2(s); };
+
+    if (pred) {
+        unsigned long long* scratch = nullptr;     // [0]: ticket, [2..]: tile descriptors
+        if ((st = kq_dev_alloc(ctx, (size_t)(A.ntiles + 2) * 8, (void**)&scratch)) != KQ_OK) return fail3(st);
+        cudaMemsetAsync(scratch, 0, (size_t)(A.ntiles + 2) * 8, ctx->stream);
+        A.ticket = (unsigned int*)scratch;
+        A.tile_desc = scratch + 2;
+        A.out_count = lazy->d_slot;
+        if (n > 0) {
+            static int bps = blocks_per_sm((const void*)k_filter_project);
+            int grid = (int)std::min<int64_t>(A.ntiles, (int64_t)ctx->sm_count * bps);
+            k_filter_project<<<grid, BLOCK, 0, ctx->stream>>>(A);
+            if ((st = launch_check(ctx, "k_filter_project")) != KQ_OK) { kq_dev_free(ctx, scratch); return fail3(st); }
+        }
+        kq_dev_free(ctx, scratch);
+        for (size_t k = 0; k < ex.size(); k++) {
+            if (mode[k] != 2) continue;
+            kq_col* in = input->cols[(size_t)KqCompiler::bare_column(ex[k])];
+            if ((st = gather_column(ctx, in, (const int32_t*)selcol->data, lazy, n, &outs[k])) != KQ_OK) return fail3(st);
+        }
+        // the row count travels back asynchronously; it is only waited for when somebody asks
+        cudaMemcpyAsync(lazy->h_slot, lazy->d_slot, 8, cudaMemcpyDeviceToHost, ctx->stream);
+        cudaEventRecord(lazy->ev, ctx->stream);
+    } else {
+        for (size_t k = 0; k < ex.size(); k++)
+            if (mode[k] == 1) { outs[k] = input->cols[(size_t)KqCompiler::bare_column(ex[k])]; outs[k]->rc.fetch_add(1); }
+        if (nvm > 0 && n > 0) {
+            static int bps = blocks_per_sm((const void*)k_project);
+            int grid = (int)std::min<int64_t>(A.ntiles, (int64_t)ctx->sm_count * bps);
+            k_project<<<grid, BLOCK, 0, ctx->stream>>>(A);
+            if ((st = launch_check(ctx, "k_project")) != KQ_OK) return fail3(st);
+        }
+    }
+
+    kq_batch* b = new kq_batch();
+    b->ctx = ctx;
+    b->cols = outs;
+    if (pred) { b->n = -1; b->lazy = lazy; } else b->n = n;
+    *out = b;
+    if (selection) *selection = selcol; else kq_column_free(selcol);
+    cleanup();
+    return KQ_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+int kq_project(kq_ctx* ctx, kq_expr* const* exprs, int nexprs, kq_batch* input, kq_batch** out) {
+    return run_operator(ctx, nullptr, exprs, nexprs, input, false, out, nullptr);
+}
+
+int kq_filter_project(kq_ctx* ctx, kq_expr* pred, kq_expr* const* exprs, int nexprs, kq_batch* input, kq_batch** out) {
+    if (!pred) return kq_fail(ctx, KQ_ERR_ILLEGAL_ARGUMENT, "kq_filter_project needs a predicate");
+    return run_operator(ctx, pred, exprs, nexprs, input, false, out, nullptr);
+}
+
+int kq_filter(kq_ctx* ctx, kq_expr* pred, kq_batch* input, kq_batch** out, kq_col** selection) {
+    if (!pred) return kq_fail(ctx, KQ_ERR_ILLEGAL_ARGUMENT, "kq_filter needs a predicate");
+    return run_operator(ctx, pred, nullptr, 0, input, true, out, selection);
+}
+
+int kq_expr_evaluate(kq_ctx* ctx, kq_expr* e, kq_batch* input, kq_col** out) {
+    if (!out) return KQ_ERR_ILLEGAL_ARGUMENT;
+    kq_batch* b = nullptr;
+    kq_expr* ex[1] = {e};
+    KQ_RET(run_operator(ctx, nullptr, ex, 1, input, false, &b, nullptr));
+    *out = b->cols[0];
+    (*out)->rc.fetch_add(1);
+    kq_batch_free(b);
+    return KQ_OK;
+}
+
+int kq_filter_project_host(kq_ctx* ctx, kq_expr* pred, kq_expr* const* exprs, int nexprs, int ncols, const int* types,
+                           const uint8_t* const* validity, const void* const* data, int64_t n, void* const* out_data,
+                           uint8_t* const* out_validity, int64_t* out_rows) {
+    // v1: upload -> fused kernel -> download, sequential (chunked overlap is a later optimisation)
+    if (!ctx || ncols < 0) return KQ_ERR_ILLEGAL_ARGUMENT;
+    std::vector<kq_col*> cols((size_t)ncols, nullptr);
+    int st = KQ_OK;
+    for (int i = 0; i < ncols && st == KQ_OK; i++) {
+        if (types[i] == KQ_UTF8) st = kq_fail(ctx, KQ_ERR_UNSUPPORTED, "kq_filter_project_host: Utf8 columns not supported");
+        else st = kq_column_upload(ctx, types[i], n, validity ? validity[i] : nullptr, nullptr, data[i], 0, &cols[(size_t)i]);
+    }
+    kq_batch *in = nullptr, *res = nullptr;
+    if (st == KQ_OK) st = kq_batch_create(ctx, cols.data(), ncols, n, &in);
+    if (st == KQ_OK) st = kq_filter_project(ctx, pred, exprs, nexprs, in, &res);
+    int64_t m = 0;
+    if (st == KQ_OK) st = kq_batch_num_rows(ctx, res, &m);
+    for (int k = 0; k < nexprs && st == KQ_OK; k++)
+        st = kq_column_download(ctx, res->cols[(size_t)k], out_validity ? out_validity[k] : nullptr, nullptr, out_data[k]);
+    if (st == KQ_OK && out_rows) *out_rows = m;
+    kq_batch_free(res); kq_batch_free(in);
+    for (kq_col* c : cols) kq_column_free(c);
+    return st;
+}
+
+}  // extern "C"

@@ -1,0 +1,382 @@
+"""GPU parity tests: libkqgpu.so (through the C ABI) against the CPU oracle on the same inputs.
+
+Bit-exact for integer, boolean, string, row-count and group-key outputs and for Float64 results of
+expressions (no FMA contraction); Float64 SUMs within 1e-9 relative (reassociated reduction order,
+north_star); exact when the addends are integer-valued.
+"""
+import json
+import math
+import os
+
+import numpy as np
+import pyarrow as pa
+import pytest
+
+from planspec import b, build, col, lit, sort_rows
+
+pytestmark = pytest.mark.gpu
+
+GOLDEN = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "employee_golden.json")
+F64, UTF8, I64, BOOL, DATE32 = 1, 2, 3, 4, 5
+SUM_RTOL = 1e-9     # north_star: float64 sums within 1e-9 relative tolerance
+
+
+@pytest.fixture(scope="module")
+def G(gpu, gctx):
+    return gpu.Engine(gctx)
+
+
+def same(a: pa.Array, c: pa.Array):
+    """bit-exact equality of two arrow arrays, NaN == NaN, -0.0 != +0.0."""
+    assert a.type == c.type, (a.type, c.type)
+    assert len(a) == len(c), (len(a), len(c))
+    la, lc = a.to_pylist(), c.to_pylist()
+    if a.type == pa.float64():
+        ka = [None if v is None else np.float64(v).tobytes() if v == v else "nan" for v in la]
+        kc = [None if v is None else np.float64(v).tobytes() if v == v else "nan" for v in lc]
+        assert ka == kc
+    else:
+        assert la == lc
+
+
+def rand_table(rng, n, null_frac):
+    def mask(x, t):
+        return pa.array(x, type=t, mask=rng.random(n) < null_frac) if null_frac else pa.array(x, type=t)
+    return [mask(rng.integers(0, 1 << 20, n), pa.int64()), mask(rng.integers(0, 1 << 20, n), pa.int64()),
+            mask(rng.integers(-50, 50, n), pa.int64()),
+            mask(rng.random(n), pa.float64()), mask(rng.random(n), pa.float64()), mask(np.floor(rng.random(n) * 1000), pa.float64()),
+            mask(np.array(["AL", "AK", "AZ", "CO", "NY", "Uppsala", ""], dtype=object)[rng.integers(0, 7, n)], pa.string()),
+            mask(rng.random(n) < 0.5, pa.bool_()),
+            mask(rng.integers(8000, 11000, n).astype(np.int32), pa.int32()).cast(pa.date32())]
+
+
+SPECS = [
+    b("ADD", b("MUL", col(0), col(1)), col(2)),
+    b("ADD", b("MUL", col(3), col(4)), col(5)),
+    b("AND", b("GT", col(0), lit("i64", 1 << 19)), b("LT", col(1), lit("i64", 1 << 19))),
+    b("AND", b("GT", col(3), lit("f64", 0.5)), b("LT", col(4), lit("f64", 0.5))),
+    b("OR", b("EQ", col(6), lit("utf8", "CO")), b("AND", col(7), b("GE", col(5), lit("f64", 500.0)))),
+    b("SUB", col(2), b("DIV", col(0), b("ADD", col(2), lit("i64", 100)))),
+    b("DIV", col(3), b("SUB", col(4), lit("f64", 0.25))),
+    b("NE", col(6), col(6)),
+    b("LE", col(2), lit("i64", None)),
+    b("LE", col(8), lit("date32", 9500)),
+    b("LT", lit("utf8", "AZ"), col(6)),
+    b("GE", col(6), lit("utf8", "CO")),
+    ("cast", col(2), "f64"),
+    b("MUL", b("SUB", lit("f64", 1.0), col(3)), b("ADD", lit("f64", 1.0), col(4))),
+]
+
+
+# ---------------------------------------------------------------- golden vectors (employee.csv)
+@pytest.fixture(scope="module")
+def employee():
+    with open(GOLDEN, encoding="utf-8") as f:
+        return json.load(f)
+
+
+def employee_batch(E, g):
+    return E.RecordBatch.from_arrow([pa.array(g["columns"][name], pa.string()) for name in g["schema"]])
+
+
+def test_golden_roundtrip_and_group_by(G, employee):
+    batch = employee_batch(G, employee)
+    assert batch.row_count() == 3 and batch.num_columns() == 6
+    for name, arr in zip(employee["schema"], batch.to_arrow()):
+        assert arr.to_pylist() == employee["columns"][name]
+    s = employee["schema"]
+    agg = G.HashAggregate([G.col(s.index("state"))], [("MAX", G.cast(G.col(s.index("salary")), F64))])
+    agg.update(batch)
+    keys, mx = agg.finalize().to_arrow()
+    assert dict(zip(keys.to_pylist(), mx.to_pylist())) == employee["group_by_state_max_salary"]
+
+
+@pytest.mark.parametrize("state,key", [("CO", "config1_where_state_eq_CO"), ("Uppsala", "where_state_eq_Uppsala")])
+def test_golden_config1_filter_project(G, employee, state, key):
+    batch = employee_batch(G, employee)
+    s = employee["schema"]
+    names = ["id", "first_name", "last_name", "state", "salary"]
+    pred = G.binary("EQ", G.col(s.index("state")), G.lit_utf8(state))
+    out = G.filter_project(pred, [G.col(s.index(n)) for n in names], batch)
+    got = {n: a.to_pylist() for n, a in zip(names, out.to_arrow())}
+    assert got == employee[key] and out.row_count() == len(employee[key]["id"])
+
+
+# ---------------------------------------------------------------- expressions / projection
+@pytest.mark.parametrize("n", [0, 1, 1023, 1024, 1025, 70001])
+@pytest.mark.parametrize("null_frac", [0.0, 0.05])
+def test_projection_matches_oracle(G, oracle, n, null_frac):
+    rng = np.random.default_rng(42 + n)
+    arrs = rand_table(rng, n, null_frac)
+    gb, ob = G.RecordBatch.from_arrow(arrs), oracle.RecordBatch.from_arrow(arrs)
+    for lo in range(0, len(SPECS), 7):
+        chunk = SPECS[lo:lo + 7]
+        try:
+            want = oracle.project([build(oracle, s) for s in chunk], ob).to_arrow()
+        except oracle.OracleError as e:
+            assert e.code == 6          # the DIV spec may hit / by zero
+            with pytest.raises(G.KqError) as ge:
+                G.project([build(G, s) for s in chunk], gb).to_arrow()
+            assert ge.value.code == 6
+            chunk = [s for s in chunk if s is not SPECS[5]]
+            want = oracle.project([build(oracle, s) for s in chunk], ob).to_arrow()
+        got = G.project([build(G, s) for s in chunk], gb)
+        assert got.row_count() == n
+        for a, w in zip(got.to_arrow(), want):
+            same(a, w)
+
+
+def test_column_expression_is_alias(G):
+    batch = G.RecordBatch.from_arrow([pa.array([1.0, 2.0]), pa.array(["x", None])])
+    c = G.col(1).evaluate(batch)
+    assert c.to_arrow().to_pylist() == ["x", None]
+    assert c.device_ptrs() == batch.field(1).device_ptrs()      # zero copy (Main.kt:453-455)
+    assert c.get_value(0) == "x" and c.get_value(1) is None     # ColumnVector.getValue
+
+
+def test_no_fma_contraction(G):
+    a, bb, c = 1.0 + 2.0 ** -30, 1.0 + 2.0 ** -30, -(1.0 + 2.0 ** -29)
+    batch = G.RecordBatch.from_arrow([pa.array([a] * 5), pa.array([bb] * 5), pa.array([c] * 5)])
+    got = G.binary("ADD", G.binary("MUL", G.col(0), G.col(1)), G.col(2)).evaluate(batch).to_arrow().to_pylist()
+    assert got == [(a * bb) + c] * 5 and got[0] == 0.0          # fma would give 2^-60
+
+
+def test_error_classes_match_the_oracle(G, oracle):
+    arrs = [pa.array([1, 2]), pa.array([1.0, 2.0]), pa.array(["a", "b"])]
+    cases = [
+        (lambda E: E.binary("ADD", E.col(0), E.col(1)), 1),     # operand types differ
+        (lambda E: E.binary("AND", E.col(0), E.col(0)), 1),     # AND on non-Bool
+        (lambda E: E.col(7), 1),                                # field index out of range
+        (lambda E: E.cast(E.col(0), UTF8), 1),                  # cast target (Main.kt:799)
+        (lambda E: E.cast(E.binary("EQ", E.col(0), E.col(0)), F64), 1),   # Cannot cast value (Main.kt:792)
+        (lambda E: E.binary("DIV", E.col(0), E.lit_i64(0)), 6), # ArithmeticException
+        (lambda E: E.binary("MUL", E.col(2), E.col(2)), None),  # math on Utf8: both must fail
+    ]
+    for mk, code in cases:
+        with pytest.raises(oracle.OracleError) as oe:
+            mk(oracle).evaluate(oracle.RecordBatch.from_arrow(arrs)).to_arrow()
+        with pytest.raises(G.KqError) as ge:
+            mk(G).evaluate(G.RecordBatch.from_arrow(arrs)).to_arrow()
+        if code is not None:
+            assert oe.value.code == code and ge.value.code == code
+    G.ctx.sync()   # the context stays usable after errors
+    assert G.col(0).evaluate(G.RecordBatch.from_arrow(arrs)).to_arrow().to_pylist() == [1, 2]
+
+
+def test_cast_utf8_to_double(G, oracle):
+    vals = ["1337", " 6.5e1 ", None, "-0", "NaN", "Infinity", "-Infinity", "1d", ".5", "1.", "0.1", "52.5", "-3.00",
+            "123456789012345", "1e22", "1e-22", "9007199254740992", "0.000001", "+7"]
+    arr = [pa.array(vals)]
+    got = G.cast(G.col(0), F64).evaluate(G.RecordBatch.from_arrow(arr)).to_arrow()
+    want = oracle.cast(oracle.col(0), F64).evaluate(oracle.RecordBatch.from_arrow(arr)).to_arrow()
+    same(got, want)
+    for bad in ["", "abc", "1_0", "nan", "inf", "1e", "--1", "1 2"]:
+        with pytest.raises(G.KqError) as e:
+            G.cast(G.col(0), F64).evaluate(G.RecordBatch.from_arrow([pa.array([bad])])).to_arrow()
+        assert e.value.code == 5, bad
+
+
+# ---------------------------------------------------------------- filter
+@pytest.mark.parametrize("n", [0, 1, 1024, 4097, 200003])
+@pytest.mark.parametrize("null_frac", [0.0, 0.05])
+def test_filter_project_matches_oracle(G, oracle, n, null_frac):
+    rng = np.random.default_rng(7 + n)
+    arrs = rand_table(rng, n, null_frac)
+    for pred, proj in [(SPECS[2], [SPECS[0], col(6), SPECS[1], SPECS[3]]), (SPECS[4], [col(7), col(8), SPECS[9], col(0)])]:
+        want = oracle.filter_project(build(oracle, pred), [build(oracle, p) for p in proj], oracle.RecordBatch.from_arrow(arrs))
+        got = G.filter_project(build(G, pred), [build(G, p) for p in proj], G.RecordBatch.from_arrow(arrs))
+        assert got.row_count() == want.row_count()
+        for a, w in zip(got.to_arrow(), want.to_arrow()):
+            same(a, w)
+
+
+def test_filter_gathers_every_column_in_order(G, oracle):
+    rng = np.random.default_rng(11)
+    arrs = rand_table(rng, 50001, 0.1)
+    for pred in (SPECS[2], SPECS[4], b("EQ", col(6), lit("utf8", "nope")), b("GE", col(0), lit("i64", 0))):
+        want, wsel = oracle.filter(build(oracle, pred), oracle.RecordBatch.from_arrow(arrs), want_selection=True)
+        got, gsel = G.filter(build(G, pred), G.RecordBatch.from_arrow(arrs), want_selection=True)
+        same(gsel.to_arrow(), wsel.to_arrow())
+        assert got.num_columns() == len(arrs)
+        for a, w in zip(got.to_arrow(), want.to_arrow()):
+            same(a, w)
+
+
+def test_filter_then_downstream_operators(G, oracle):
+    """A filtered batch (row count still device-resident) feeds projection and aggregation."""
+    rng = np.random.default_rng(5)
+    arrs = rand_table(rng, 30000, 0.05)
+    def run(E):
+        f = E.filter(build(E, SPECS[2]), E.RecordBatch.from_arrow(arrs))
+        p = E.project([build(E, SPECS[0]), E.col(6)], f)
+        agg = E.HashAggregate([E.col(1)], [("SUM", E.col(0)), ("COUNT", E.col(0))])
+        agg.update(p)
+        return p.to_arrow(), sort_rows(agg.finalize().to_arrow(), 1)
+    (gp, ga), (op, oa) = run(G), run(oracle)
+    for a, w in zip(gp, op):
+        same(a, w)
+    assert ga == oa
+
+
+def test_div_by_zero_only_counts_on_rows_that_pass_the_filter(G, oracle):
+    a = pa.array([10, 20, 30, 40]); d = pa.array([2, 0, 5, 0])
+    pred = b("NE", col(1), lit("i64", 0))
+    for E in (G, oracle):
+        out = E.filter_project(build(E, pred), [build(E, b("DIV", col(0), col(1)))], E.RecordBatch.from_arrow([a, d]))
+        assert out.to_arrow()[0].to_pylist() == [5, 6]
+    with pytest.raises(G.KqError) as e:
+        G.filter_project(build(G, b("GE", col(1), lit("i64", 0))), [build(G, b("DIV", col(0), col(1)))],
+                         G.RecordBatch.from_arrow([a, d])).to_arrow()
+    assert e.value.code == 6
+
+
+# ---------------------------------------------------------------- hash aggregate
+AGGS = [("SUM", 5), ("MIN", 5), ("MAX", 5), ("COUNT", 5), ("SUM", 2), ("MAX", 0), ("MIN", 8), ("COUNT", 6)]
+
+
+@pytest.mark.parametrize("n", [0, 1, 1025, 60007])
+@pytest.mark.parametrize("null_frac", [0.0, 0.1])
+@pytest.mark.parametrize("keys", [[6], [2], [6, 7], [], [8, 2], [3]])
+def test_hash_aggregate_matches_oracle(G, oracle, keys, null_frac, n):
+    rng = np.random.default_rng(3 + n)
+    arrs = rand_table(rng, n, null_frac)
+    def run(E):
+        agg = E.HashAggregate([E.col(k) for k in keys], [(kind, E.col(c)) for kind, c in AGGS])
+        agg.update(E.RecordBatch.from_arrow(arrs))
+        return agg.finalize()
+    got, want = run(G), run(oracle)
+    assert got.row_count() == want.row_count()
+    ga, wa = got.to_arrow(), want.to_arrow()
+    assert [a.type for a in ga] == [a.type for a in wa]
+    assert sort_rows(ga, len(keys)) == sort_rows(wa, len(keys))
+
+
+def test_hash_aggregate_float_sums_within_tolerance(G, oracle):
+    rng = np.random.default_rng(9)
+    n = 300000
+    arrs = [pa.array(rng.integers(0, 50, n)), pa.array(rng.random(n) * 1000)]
+    def run(E):
+        agg = E.HashAggregate([E.col(0)], [("SUM", E.col(1)), ("MIN", E.col(1)), ("MAX", E.col(1)), ("COUNT", E.col(1))])
+        agg.update(E.RecordBatch.from_arrow(arrs))
+        return sort_rows(agg.finalize().to_arrow(), 1)
+    got, want = run(G), run(oracle)
+    assert len(got) == len(want) == 50
+    for g, w in zip(got, want):
+        assert g[0] == w[0] and g[2:] == w[2:]                       # key, MIN, MAX, COUNT bit-exact
+        assert abs(g[1] - w[1]) <= SUM_RTOL * abs(w[1])               # SUM: reassociated
+
+
+def test_hash_aggregate_is_independent_of_batch_boundaries(G, oracle):
+    rng = np.random.default_rng(21)
+    arrs = rand_table(rng, 20000, 0.05)
+    def run(E, cuts):
+        agg = E.HashAggregate([E.col(6), E.col(7)], [(k, E.col(c)) for k, c in AGGS])
+        for lo, hi in zip(cuts[:-1], cuts[1:]):
+            agg.update(E.RecordBatch.from_arrow([a.slice(lo, hi - lo) for a in arrs]))
+        return sort_rows(agg.finalize().to_arrow(), 2)
+    assert run(G, [0, 20000]) == run(G, [0, 1, 5000, 5000, 19999, 20000]) == run(oracle, [0, 20000])
+
+
+def test_high_cardinality_aggregate_grows_the_table(G, oracle):
+    rng = np.random.default_rng(33)
+    n = 400000
+    arrs = [pa.array(rng.integers(0, 150000, n)), pa.array(np.floor(rng.random(n) * 100))]
+    def run(E):
+        agg = E.HashAggregate([E.col(0)], [("SUM", E.col(1)), ("MIN", E.col(1)), ("MAX", E.col(1)), ("COUNT", E.col(1))])
+        agg.update(E.RecordBatch.from_arrow(arrs))
+        agg.update(E.RecordBatch.from_arrow(arrs))
+        return sort_rows(agg.finalize().to_arrow(), 1)
+    assert run(G) == run(oracle)
+
+
+def test_fused_filter_project_aggregate_q1_shape(G, oracle):
+    """TPC-H Q1 shape (BASELINE config 5) on a small seeded lineitem."""
+    specs = q1_specs()
+    for E in (G, oracle):
+        pass
+    def run(E):
+        batch = E.generate(specs, 42, 0, 150000)
+        return sort_rows(q1_aggregate(E, batch).to_arrow(), 2)
+    got, want = run(G), run(oracle)
+    assert len(got) == len(want) == 6
+    for g, w in zip(got, want):
+        assert g[:2] == w[:2] and g[6] == w[6]
+        for x, y in zip(g[2:6], w[2:6]):
+            assert abs(x - y) <= SUM_RTOL * abs(y)
+
+
+def q1_specs():
+    return [dict(kind=6, ilo=8036, ihi=10562),                    # l_shipdate 1992-01-02 .. 1998-12-01
+            dict(kind=5, dict="ANR", dict_width=1), dict(kind=5, dict="FO", dict_width=1),
+            dict(kind=3, ilo=1, ihi=51),                           # l_quantity
+            dict(kind=2, flo=900.0, fhi=105000.0),                 # l_extendedprice
+            dict(kind=4, ilo=0, ihi=11, fhi=100.0),                # l_discount
+            dict(kind=4, ilo=0, ihi=9, fhi=100.0)]                 # l_tax
+
+
+def q1_aggregate(E, batch):
+    one = E.lit_f64(1.0)
+    disc_price = E.binary("MUL", E.col(4), E.binary("SUB", one, E.col(5)))
+    charge = E.binary("MUL", disc_price, E.binary("ADD", one, E.col(6)))
+    pred = E.binary("LE", E.col(0), E.lit_date32(10471))          # 1998-09-02
+    agg = E.HashAggregate([E.col(1), E.col(2)],
+                          [("SUM", E.col(3)), ("SUM", E.col(4)), ("SUM", disc_price), ("SUM", charge), ("COUNT", E.lit_i64(1))],
+                          pred=pred)
+    agg.update(batch)
+    return agg.finalize()
+
+
+def test_group_key_equality_and_nan_order(G):
+    """R7 on the GPU: NaN == NaN is one group, +0.0 != -0.0, null is a group. MIN/MAX use the total
+    order documented in DESIGN.md (NaN above +inf) where the reference is order-dependent (R9)."""
+    k = pa.array([float("nan"), 0.0, -0.0, float("nan"), None, None, 1.0], pa.float64())
+    v = pa.array([1.0, 2.0, 3.0, 4.0, 5.0, 6.0, 7.0], pa.float64())
+    agg = G.HashAggregate([G.col(0)], [("COUNT", G.col(1)), ("MAX", G.col(1))])
+    agg.update(G.RecordBatch.from_arrow([k, v]))
+    keys, cnt, mx = [a.to_pylist() for a in agg.finalize().to_arrow()]
+    got = {}
+    for kk, c, m in zip(keys, cnt, mx):
+        tag = "null" if kk is None else ("nan" if kk != kk else ("-0" if (kk == 0 and math.copysign(1, kk) < 0) else kk))
+        got[tag] = (c, m)
+    assert got == {"nan": (2, 4.0), 0.0: (1, 2.0), "-0": (1, 3.0), "null": (2, 6.0), 1.0: (1, 7.0)}
+    def mm(vals):
+        agg = G.HashAggregate([], [("MAX", G.col(0)), ("MIN", G.col(0)), ("SUM", G.col(0)), ("COUNT", G.col(0))])
+        agg.update(G.RecordBatch.from_arrow([pa.array(vals, pa.float64())]))
+        return [a.to_pylist()[0] for a in agg.finalize().to_arrow()]
+    r = mm([5.0, float("nan"), -1.0])
+    assert math.isnan(r[0]) and r[1] == -1.0 and r[3] == 3
+    r = mm([0.0, -0.0])
+    assert math.copysign(1, r[0]) == 1 and math.copysign(1, r[1]) == -1
+    assert mm([None, None]) == [None, None, None, 0]
+
+
+def test_zero_rows_zero_groups(G):
+    agg = G.HashAggregate([], [("MAX", G.col(0)), ("COUNT", G.col(0))])
+    agg.update(G.RecordBatch.from_arrow([pa.array([], pa.float64())]))
+    out = agg.finalize()
+    assert out.row_count() == 0 and out.num_columns() == 2       # rule R10: no SQL "one row" rule
+
+
+def test_unsupported_aggregates_raise_like_the_reference(G, oracle):
+    arrs = [pa.array(["a", "b"]), pa.array([True, False])]
+    for c in (0, 1):
+        for E in (G, oracle):
+            Err = G.KqError if E is G else oracle.OracleError
+            with pytest.raises(Err) as e:
+                agg = E.HashAggregate([], [("MAX", E.col(c))])
+                agg.update(E.RecordBatch.from_arrow(arrs))
+                agg.finalize().to_arrow()
+            assert e.value.code == 2                                 # UnsupportedOperationException (Main.kt:548)
+
+
+# ---------------------------------------------------------------- generator
+def test_generator_matches_oracle_bit_for_bit(G, oracle):
+    specs = [dict(kind=1, ilo=0, ihi=1 << 20), dict(kind=2, flo=0.0, fhi=1000.0, null_per_10k=500),
+             dict(kind=3, ilo=0, ihi=1000), dict(kind=4, ilo=0, ihi=11, fhi=100.0),
+             dict(kind=5, dict="ALAKAZCO", dict_width=2, null_per_10k=300), dict(kind=6, ilo=8036, ihi=10561),
+             dict(kind=7, ilo=2500), dict(kind=2, flo=900.0, fhi=105000.0)]
+    for lo, hi in [(0, 0), (0, 1), (5, 70), (1000, 5097), (123456789012, 123456789012 + 3000)]:
+        got = G.generate(specs, 42, lo, hi).to_arrow()
+        want = oracle.generate(specs, 42, lo, hi).to_arrow()
+        for a, w in zip(got, want):
+            same(a, w)
