@@ -47,12 +47,10 @@ int KqCompiler::begin(kq_ctx* c, kq_batch* b) {
     return KQ_OK;
 }
 
-int KqCompiler::emit(int op, int arg, int delta) {
+int KqCompiler::emit(int op, int src, int a, uint32_t b) {
     if (prog.ninsn >= MAX_INSN) return kq_fail(ctx, KQ_ERR_UNSUPPORTED, "expression program too long (> %d instructions)", MAX_INSN);
-    if (sp + (delta > 0 ? delta : 0) > D) return kq_fail(ctx, KQ_ERR_UNSUPPORTED, "expression too deep (evaluation stack > %d)", D);
     Insn& in = prog.insn[prog.ninsn++];
-    in.op = (uint8_t)op; in.sp = (uint8_t)sp; in.arg = (uint16_t)arg;
-    sp += delta;
+    in.op = (uint8_t)op; in.src = (uint8_t)src; in.a = (uint16_t)a; in.b = b;
     return KQ_OK;
 }
 
@@ -63,6 +61,8 @@ int KqCompiler::use_col(int bc, int* slot) {
         kq_col* c = batch->cols[(size_t)bc];
         DCol& d = prog.cols[prog.ncols];
         d.data = c->data; d.validity = c->validity; d.offsets = c->offsets;
+        d.s_data = d.s_valid = d.s_off = -1;
+        slot_col[prog.ncols] = bc;
         colmap[bc] = prog.ncols++;
     }
     *slot = colmap[bc];
@@ -119,30 +119,47 @@ static uint32_t cmp_mask(int op) {
 }
 static uint32_t mirror_mask(uint32_t m) { return (m & 0xA) | ((m & 1) << 2) | ((m >> 2) & 1); }
 
+// A leaf can be fetched straight into TMP by the instruction that consumes it.
+bool KqCompiler::leaf_src(const kq_expr* e, int* src, int* a) {
+    if (e->kind == KQ_EX_COL) {
+        if (e->col < 0 || e->col >= (int)batch->cols.size()) return false;
+        int t = batch->cols[(size_t)e->col]->type;
+        int slot;
+        if (t == KQ_UTF8 || use_col(e->col, &slot) != KQ_OK) return false;
+        *src = (t == KQ_F64 || t == KQ_I64) ? S_COL64 : (t == KQ_BOOL ? S_COLBIT : S_COL32);
+        *a = slot;
+        return true;
+    }
+    if (e->kind == KQ_EX_LIT && e->type != KQ_UTF8) {
+        if (e->is_null) { *src = S_NULL; *a = 0; return true; }
+        uint64_t bits;
+        if (e->type == KQ_F64) memcpy(&bits, &e->f, 8); else bits = (uint64_t)e->i;
+        int idx;
+        if (add_lit(bits, &idx) != KQ_OK) return false;
+        *src = S_LIT; *a = idx;
+        return true;
+    }
+    return false;
+}
+
+// Emit code that leaves the value of e in ACC.
 int KqCompiler::value(const kq_expr* e, int* type, bool* nullable) {
     if (!e) return kq_fail(ctx, KQ_ERR_ILLEGAL_ARGUMENT, "null expression");
     switch (e->kind) {
         case KQ_EX_COL: {
             KQ_RET(infer(e, type, nullable));
-            int slot; KQ_RET(use_col(e->col, &slot));
-            switch (*type) {
-                case KQ_F64: case KQ_I64: return emit(OP_PUSH_COL64, slot, +1);
-                case KQ_DATE32: case KQ_I32: return emit(OP_PUSH_COL32, slot, +1);
-                case KQ_BOOL: return emit(OP_PUSH_COLBIT, slot, +1);
-                default: return kq_fail(ctx, KQ_ERR_UNSUPPORTED, "a Utf8 column cannot be an operand here (only comparisons, COUNT, group keys and pass-through)");
-            }
+            if (*type == KQ_UTF8) return kq_fail(ctx, KQ_ERR_UNSUPPORTED, "a Utf8 column cannot be an operand here (only comparisons, COUNT, group keys and pass-through)");
+            int src, a;
+            if (!leaf_src(e, &src, &a)) return kq_fail(ctx, KQ_ERR_UNSUPPORTED, "more than %d distinct columns in one kernel", MAX_COLS);
+            return emit(O_LOAD, src, a);
         }
         case KQ_EX_LIT: {
             *type = e->type; *nullable = e->is_null;
-            if (e->is_null) return emit(OP_PUSH_NULL, 0, +1);
-            uint64_t bits;
-            switch (e->type) {
-                case KQ_F64: memcpy(&bits, &e->f, 8); break;
-                case KQ_I64: case KQ_DATE32: case KQ_BOOL: case KQ_I32: bits = (uint64_t)e->i; break;
-                default: return kq_fail(ctx, KQ_ERR_UNSUPPORTED, "a Utf8 literal can only be compared with a Utf8 column");
-            }
-            int idx; KQ_RET(add_lit(bits, &idx));
-            return emit(OP_PUSH_LIT, idx, +1);
+            if (e->type == KQ_UTF8 && !e->is_null) return kq_fail(ctx, KQ_ERR_UNSUPPORTED, "a Utf8 literal can only be compared with a Utf8 column");
+            if (e->is_null) return emit(O_LOAD, S_NULL, 0);
+            int src, a;
+            if (!leaf_src(e, &src, &a)) return kq_fail(ctx, KQ_ERR_UNSUPPORTED, "more than %d literals in one kernel", MAX_LIT);
+            return emit(O_LOAD, src, a);
         }
         case KQ_EX_CAST: {
             if (e->type != KQ_F64) return kq_fail(ctx, KQ_ERR_ILLEGAL_STATE, "Cast to type %d is not supported", e->type);   // Main.kt:799
@@ -152,9 +169,9 @@ int KqCompiler::value(const kq_expr* e, int* type, bool* nullable) {
                 int bc = bare_column(e->l);
                 if (bc < 0) return kq_fail(ctx, KQ_ERR_UNSUPPORTED, "Utf8->Float64 cast needs a column operand");
                 int slot; KQ_RET(use_col(bc, &slot));
-                return emit(OP_UTF8_TO_F64, slot, +1);
+                return emit(O_LOAD, S_UTF8_F64, slot);
             }
-            if (st == KQ_I64) { int t; bool n; KQ_RET(value(e->l, &t, &n)); return emit(OP_I64_TO_F64, 0, 0); }
+            if (st == KQ_I64) { int t; bool n; KQ_RET(value(e->l, &t, &n)); return emit(O_I64_TO_F64, S_NONE, 0); }
             if (st == KQ_F64) { int t; bool n; return value(e->l, &t, &n); }
             return kq_fail(ctx, KQ_ERR_ILLEGAL_STATE, "Cannot cast value to Double");                                          // Main.kt:792
         }
@@ -163,54 +180,68 @@ int KqCompiler::value(const kq_expr* e, int* type, bool* nullable) {
             KQ_RET(infer(e->l, &lt, &ln)); KQ_RET(infer(e->r, &rt, &rn));
             if (lt != rt) return kq_fail(ctx, KQ_ERR_ILLEGAL_STATE, "binary operand types differ (%d vs %d)", lt, rt);      // rule E2
             *nullable = ln || rn;
-            int op = e->op;
-            bool is_cmp = op >= KQ_EQ && op <= KQ_GE, is_logic = op == KQ_AND || op == KQ_OR;
+            const int op = e->op;
+            const bool is_cmp = op >= KQ_EQ && op <= KQ_GE, is_logic = op == KQ_AND || op == KQ_OR;
             if (!is_cmp && !is_logic && !(op >= KQ_ADD && op <= KQ_DIV)) return kq_fail(ctx, KQ_ERR_ILLEGAL_STATE, "unknown binary operator %d", op);
-            if (is_logic) {
-                if (lt != KQ_BOOL) return kq_fail(ctx, KQ_ERR_ILLEGAL_STATE, "AND/OR need Bool operands");
-                int t; bool n;
-                KQ_RET(value(e->l, &t, &n)); KQ_RET(value(e->r, &t, &n));
-                *type = KQ_BOOL;
-                return emit(op == KQ_AND ? OP_AND : OP_OR, 0, -1);
-            }
-            if (is_cmp) {
+            if (is_logic && lt != KQ_BOOL) return kq_fail(ctx, KQ_ERR_ILLEGAL_STATE, "AND/OR need Bool operands");
+            if (is_cmp && lt == KQ_UTF8) {
                 *type = KQ_BOOL;
                 uint32_t m = cmp_mask(op);
-                if (lt == KQ_UTF8) {
-                    const kq_expr *a = e->l, *b = e->r;
-                    if ((a->kind == KQ_EX_LIT && a->is_null) || (b->kind == KQ_EX_LIT && b->is_null)) return emit(OP_PUSH_NULL, 0, +1);
-                    if (a->kind == KQ_EX_LIT && b->kind == KQ_EX_LIT) {
-                        int c = a->s.compare(b->s); int code = c < 0 ? 0 : (c == 0 ? 1 : 2);
-                        int idx; KQ_RET(add_lit((m >> code) & 1u, &idx));
-                        return emit(OP_PUSH_LIT, idx, +1);
-                    }
-                    if (a->kind == KQ_EX_LIT) { std::swap(a, b); m = mirror_mask(m); }
-                    int ca = bare_column(a);
-                    if (ca < 0) return kq_fail(ctx, KQ_ERR_UNSUPPORTED, "Utf8 comparison operands must be columns or literals");
-                    int sa; KQ_RET(use_col(ca, &sa));
-                    if (b->kind == KQ_EX_LIT) {
-                        int li; KQ_RET(add_utf8_lit(b->s, &li));
-                        return emit(OP_UTF8_CMP_LIT, sa | (li << 5) | (int)(m << 10), +1);
-                    }
-                    int cb = bare_column(b);
-                    if (cb < 0) return kq_fail(ctx, KQ_ERR_UNSUPPORTED, "Utf8 comparison operands must be columns or literals");
-                    int sb; KQ_RET(use_col(cb, &sb));
-                    return emit(OP_UTF8_CMP_COL, sa | (sb << 5) | (int)(m << 10), +1);
+                const kq_expr *a = e->l, *b = e->r;
+                if ((a->kind == KQ_EX_LIT && a->is_null) || (b->kind == KQ_EX_LIT && b->is_null)) return emit(O_LOAD, S_NULL, 0);
+                if (a->kind == KQ_EX_LIT && b->kind == KQ_EX_LIT) {
+                    int c = a->s.compare(b->s); int code = c < 0 ? 0 : (c == 0 ? 1 : 2);
+                    int idx; KQ_RET(add_lit((m >> code) & 1u, &idx));
+                    return emit(O_LOAD, S_LIT, idx);
                 }
-                if (lt == KQ_I32) return kq_fail(ctx, KQ_ERR_ILLEGAL_STATE, "compare on I32");
-                int t; bool n;
-                KQ_RET(value(e->l, &t, &n)); KQ_RET(value(e->r, &t, &n));
-                return emit(lt == KQ_F64 ? OP_CMP_F64 : OP_CMP_I64, (int)m, -1);
+                if (a->kind == KQ_EX_LIT) { std::swap(a, b); m = mirror_mask(m); }
+                int ca = bare_column(a);
+                if (ca < 0) return kq_fail(ctx, KQ_ERR_UNSUPPORTED, "Utf8 comparison operands must be columns or literals");
+                int sa; KQ_RET(use_col(ca, &sa));
+                if (b->kind == KQ_EX_LIT) {
+                    int li; KQ_RET(add_utf8_lit(b->s, &li));
+                    return emit(O_LOAD, S_UTF8_CMP_LIT, sa, (uint32_t)li | (m << 8));
+                }
+                int cb = bare_column(b);
+                if (cb < 0) return kq_fail(ctx, KQ_ERR_UNSUPPORTED, "Utf8 comparison operands must be columns or literals");
+                int sb; KQ_RET(use_col(cb, &sb));
+                return emit(O_LOAD, S_UTF8_CMP_COL, sa, (uint32_t)sb | (m << 8));
             }
-            if (lt != KQ_I64 && lt != KQ_F64) return kq_fail(ctx, KQ_ERR_ILLEGAL_STATE, "math needs Int64 or Float64 operands");
-            int t; bool n;
-            KQ_RET(value(e->l, &t, &n)); KQ_RET(value(e->r, &t, &n));
-            *type = lt;
-            int base = lt == KQ_F64 ? OP_ADD_F64 : OP_ADD_I64;
-            return emit(base + (op - KQ_ADD), 0, -1);
+            if (is_cmp && lt == KQ_I32) return kq_fail(ctx, KQ_ERR_ILLEGAL_STATE, "compare on I32");
+            if (!is_cmp && !is_logic && lt != KQ_I64 && lt != KQ_F64) return kq_fail(ctx, KQ_ERR_ILLEGAL_STATE, "math needs Int64 or Float64 operands");
+            *type = (is_cmp || is_logic) ? KQ_BOOL : lt;
+            // forward form: ACC = ACC op TMP; reverse form: ACC = TMP op ACC
+            int fwd, rev; uint32_t bf = 0, br = 0;
+            const bool f64 = lt == KQ_F64;
+            if (is_cmp) { fwd = rev = f64 ? O_CMP_F64 : O_CMP_I64; bf = cmp_mask(op); br = mirror_mask(bf); }
+            else if (is_logic) fwd = rev = op == KQ_AND ? O_AND : O_OR;
+            else switch (op) {
+                case KQ_ADD: fwd = rev = f64 ? O_ADD_F64 : O_ADD_I64; break;
+                case KQ_MUL: fwd = rev = f64 ? O_MUL_F64 : O_MUL_I64; break;
+                case KQ_SUB: fwd = f64 ? O_SUB_F64 : O_SUB_I64; rev = f64 ? O_RSUB_F64 : O_RSUB_I64; break;
+                default: fwd = f64 ? O_DIV_F64 : O_DIV_I64; rev = f64 ? O_RDIV_F64 : O_RDIV_I64; break;
+            }
+            int t; bool n; int src, a;
+            // Utf8 comparisons and casts are "loads" too, but they need ACC: treat only plain leaves as operands
+            if (is_plain_leaf(e->r) && leaf_src(e->r, &src, &a)) { KQ_RET(value(e->l, &t, &n)); return emit(fwd, src, a, bf); }
+            if (is_plain_leaf(e->l) && leaf_src(e->l, &src, &a)) { KQ_RET(value(e->r, &t, &n)); return emit(rev, src, a, br); }
+            if (sp >= DS) return kq_fail(ctx, KQ_ERR_UNSUPPORTED, "expression too deep (more than %d nested non-leaf operand pairs)", DS);
+            KQ_RET(value(e->l, &t, &n));
+            KQ_RET(emit(O_PUSH, S_NONE, sp));
+            sp++;
+            int st = value(e->r, &t, &n);
+            sp--;
+            KQ_RET(st);
+            return emit(rev, S_STACK, sp, br);
         }
     }
     return kq_fail(ctx, KQ_ERR_ILLEGAL_STATE, "Unknown expr");
+}
+
+bool KqCompiler::is_plain_leaf(const kq_expr* e) {
+    if (e->kind == KQ_EX_LIT) return e->type != KQ_UTF8;
+    if (e->kind != KQ_EX_COL || e->col < 0 || e->col >= (int)batch->cols.size()) return false;
+    return batch->cols[(size_t)e->col]->type != KQ_UTF8;
 }
 
 int KqCompiler::validity_only(const kq_expr* e) {
@@ -218,7 +249,7 @@ int KqCompiler::validity_only(const kq_expr* e) {
     if (bc >= 0) {
         int t; bool n; KQ_RET(infer(e, &t, &n));
         int slot; KQ_RET(use_col(bc, &slot));
-        return emit(OP_PUSH_VALID, slot, +1);
+        return emit(O_LOAD, S_VALID, slot);
     }
     int t; bool n;
     return value(e, &t, &n);
@@ -230,9 +261,39 @@ int KqCompiler::key_value(const kq_expr* e, int* type, bool* nullable) {
         int bc = bare_column(e);
         if (bc < 0) return kq_fail(ctx, KQ_ERR_UNSUPPORTED, "Utf8 group keys must be columns");
         int slot; KQ_RET(use_col(bc, &slot));
-        return emit(OP_UTF8_PACK, slot, +1);
+        return emit(O_LOAD, S_UTF8_PACK, slot);
     }
     return value(e, type, nullable);
 }
 
-int KqCompiler::sink(int op, int arg) { return emit(op, arg, -1); }
+// Hand ACC to a sink (O_SET_SEL / O_EMIT / O_SET_KEY / O_SET_IN); ACC stays valid.
+int KqCompiler::sink(int op, int arg) { return emit(op, S_NONE, arg); }
+
+void KqCompiler::plan_stages(int budget, int min_stages, int tile_rows, StagePlan* sp) {
+    const int TILE = tile_rows;
+    memset(sp, 0, sizeof *sp);
+    int off = 0;
+    auto add = [&](int kind, const void* g, int32_t* soff) {
+        int bytes = kind == SK_W8 ? TILE * 8 : (kind == SK_W4 ? TILE * 4 : (kind == SK_W4_PLUS1 ? TILE * 4 + 16 : TILE / 8));
+        bytes = (bytes + 127) / 128 * 128;
+        if (sp->nbuf >= MAX_STAGE_BUFS || (off + bytes) * min_stages > budget) return;   // stays on the direct global path
+        sp->buf[sp->nbuf].g = (const char*)g; sp->buf[sp->nbuf].soff = off; sp->buf[sp->nbuf].kind = kind;
+        sp->nbuf++;
+        *soff = off;
+        off += bytes;
+    };
+    for (int i = 0; i < prog.ncols; i++) {
+        kq_col* c = batch->cols[(size_t)slot_col[i]];
+        DCol& d = prog.cols[i];
+        switch (c->type) {
+            case KQ_F64: case KQ_I64: add(SK_W8, c->data, &d.s_data); break;
+            case KQ_DATE32: case KQ_I32: add(SK_W4, c->data, &d.s_data); break;
+            case KQ_BOOL: add(SK_BIT, c->data, &d.s_data); break;
+            case KQ_UTF8: add(SK_W4_PLUS1, c->offsets, &d.s_off); break;   // string bytes stay in global memory
+        }
+        if (c->validity) add(SK_BIT, c->validity, &d.s_valid);
+    }
+    sp->stage_bytes = off > 0 ? off : 128;
+    int ns = budget / sp->stage_bytes;
+    sp->nstages = ns > MAX_STAGES ? MAX_STAGES : (ns < 1 ? 1 : ns);
+}

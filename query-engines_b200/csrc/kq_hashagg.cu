@@ -21,12 +21,20 @@
 #include <cstring>
 
 #include "kq_compile.h"
+#include "kq_pipe.cuh"
 #include "kq_scan.cuh"
 
 using namespace kq;
 
 namespace {
 
+// 7 consumer warps (the lane-private front end scales with the warp count) + 1 service warp (TMA producer)
+constexpr int WARPS = 7;
+constexpr int BLOCK = WARPS * 32;
+constexpr int TILE = WARPS * WARP_ROWS;     // 896 rows
+constexpr int SERVICE_WARP = WARPS;
+constexpr int THREADS = BLOCK + 32;
+constexpr int AGG_MAX_STAGES = 4;
 constexpr int MAX_REC_WORDS = 32;
 constexpr int DIR_SLOTS = 256;
 constexpr int FE_MAX_GROUPS = 64;
@@ -61,8 +69,9 @@ struct AggArgs {
     uint32_t fe_sum_int;                   // bit s: slot s is an integer sum
     int32_t fe_mm_word[2 * MAX_INPUTS];    // front-end min/max slot -> record word
     uint32_t fe_mm_ismin;
-    // shared-memory layout (byte offsets)
-    int32_t off_dirkeys, off_dirstate, off_gid2slot, off_gslot, off_mm, off_cnt, off_sum, smem_bytes;
+    // shared-memory layout (byte offsets): [stage ring][front end]
+    int32_t off_fe, off_dirkeys, off_dirstate, off_gid2slot, off_gslot, off_mm, off_cnt, off_sum, smem_bytes;
+    StagePlan sp;
 };
 
 __device__ __forceinline__ uint64_t order_map(uint64_t bits, bool is_int) {
@@ -202,9 +211,10 @@ __device__ __forceinline__ int dir_lookup(const AggArgs& A, uint64_t* dirkeys, u
     return -1;
 }
 
-__global__ void __launch_bounds__(BLOCK, 1) k_hash_aggregate(const __grid_constant__ AggArgs A) {
-    extern __shared__ __align__(16) unsigned char smem[];
-    __shared__ long long s_tile[2];
+__global__ void __launch_bounds__(THREADS, 1) k_hash_aggregate(const __grid_constant__ AggArgs A) {
+    extern __shared__ __align__(128) unsigned char smem[];
+    __shared__ uint64_t full[MAX_STAGES], empty[MAX_STAGES];
+    __shared__ long long tile_of[MAX_STAGES];
     __shared__ uint32_t s_dir_count;
     uint64_t* dirkeys = reinterpret_cast<uint64_t*>(smem + A.off_dirkeys);
     uint32_t* dirstate = reinterpret_cast<uint32_t*>(smem + A.off_dirstate);
@@ -213,33 +223,51 @@ __global__ void __launch_bounds__(BLOCK, 1) k_hash_aggregate(const __grid_consta
     uint64_t* mm = reinterpret_cast<uint64_t*>(smem + A.off_mm);
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int NI = A.ninputs, NS = A.fe_nsum, NM = A.fe_nmm, FG = A.fe_groups;
+    const int S = A.sp.nstages;
     // lane-private accumulators of this warp: cnt[(gid*NI + i)*32 + lane], sum[(gid*NS + s)*32 + lane]
-    uint32_t* cnt = reinterpret_cast<uint32_t*>(smem + A.off_cnt) + (size_t)warp * FG * NI * 32;
-    uint64_t* sum = reinterpret_cast<uint64_t*>(smem + A.off_sum) + (size_t)warp * FG * NS * 32;
+    uint32_t* cnt = reinterpret_cast<uint32_t*>(smem + A.off_cnt) + (size_t)(warp % WARPS) * FG * NI * 32;
+    uint64_t* sum = reinterpret_cast<uint64_t*>(smem + A.off_sum) + (size_t)(warp % WARPS) * FG * NS * 32;
 
-    for (int i = threadIdx.x * 4; i < A.smem_bytes; i += BLOCK * 4) *reinterpret_cast<uint32_t*>(smem + i) = 0;
+    for (int i = A.off_fe + threadIdx.x * 4; i < A.smem_bytes; i += THREADS * 4) *reinterpret_cast<uint32_t*>(smem + i) = 0;
+    if (threadIdx.x == 0) {
+        s_dir_count = 0;
+        for (int s = 0; s < S; s++) { mbar_init(&full[s], 1); mbar_init(&empty[s], WARPS); }
+        mbar_fence_init();
+    }
     __syncthreads();
-    for (int i = threadIdx.x; i < FG * NM; i += BLOCK) mm[i] = ((A.fe_mm_ismin >> (i % NM)) & 1u) ? ~0ULL : 0ULL;
-    if (threadIdx.x == 0) s_dir_count = 0;
+    for (int i = threadIdx.x; i < FG * NM; i += THREADS) mm[i] = ((A.fe_mm_ismin >> (i % NM)) & 1u) ? ~0ULL : 0ULL;
     __syncthreads();
 
-    AggSink sink;
-    Stack st;
-    bool bypass = FG == 0;
-    for (int it = 0;; it++) {
-        if (threadIdx.x == 0) {
-            unsigned long long g = *reinterpret_cast<volatile unsigned long long*>(A.ngroups);
-            s_tile[it & 1] = (g > A.stop_threshold) ? -1LL : (long long)atomicAdd(A.ticket, 1u);
+    if (warp == SERVICE_WARP) {
+        if (lane == 0) {
+            for (int k = 0;; k++) {
+                const int s = k % S;
+                mbar_wait(&empty[s], ((k / S) & 1) ^ 1);
+                // stop taking tiles once the global table is half full: every ticket taken is processed,
+                // so the rows consumed so far are always a prefix of the batch (the host grows and resumes)
+                const unsigned long long g = *reinterpret_cast<volatile unsigned long long*>(A.ngroups);
+                long long tile = -1;
+                if (g <= A.stop_threshold) tile = (long long)atomicAdd(A.ticket, 1u) + A.tile_begin;
+                if (tile < 0 || tile >= A.ntiles) { tile_of[s] = -1; mbar_arrive(&full[s]); break; }
+                tile_of[s] = tile;
+                stage_issue(A.sp, smem + (size_t)s * A.sp.stage_bytes, &full[s], tile, TILE, A.n);
+            }
         }
-        __syncthreads();
-        long long tile = s_tile[it & 1];
+    } else {
+    AggSink sink;
+    Vm st;
+    bool bypass = FG == 0;
+    for (int k = 0;; k++) {
+        const int s = k % S;
+        mbar_wait(&full[s], (k / S) & 1);
+        const long long tile = tile_of[s];
         if (tile < 0) break;
-        tile += A.tile_begin;
-        if (tile >= A.ntiles) break;
         RowCtx rc;
-        rowctx_init(rc, tile, A.n, A.err);
+        rowctx_init(rc, tile, TILE, A.n, A.err, smem + (size_t)s * A.sp.stage_bytes);
         sink.sel = rc.inr;
         run(A.prog, 0, A.prog.ninsn, st, rc, sink);
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&empty[s]);       // everything needed is in registers now
 
         int fe_hits = 0, rows = 0;
 #pragma unroll
@@ -248,11 +276,11 @@ __global__ void __launch_bounds__(BLOCK, 1) k_hash_aggregate(const __grid_consta
             uint64_t kw[MAX_KEYS];
             uint32_t nullmask = 0;
 #pragma unroll
-            for (int k = 0; k < MAX_KEYS; k++) {
-                kw[k] = 0;
-                if (k < A.nkeys) {
-                    if ((sink.keyok[k] >> r) & 1u) kw[k] = ((A.key_f64_mask >> k) & 1u) ? canon_nan(sink.key[k][r]) : sink.key[k][r];
-                    else nullmask |= 1u << k;
+            for (int k2 = 0; k2 < MAX_KEYS; k2++) {
+                kw[k2] = 0;
+                if (k2 < A.nkeys) {
+                    if ((sink.keyok[k2] >> r) & 1u) kw[k2] = ((A.key_f64_mask >> k2) & 1u) ? canon_nan(sink.key[k2][r]) : sink.key[k2][r];
+                    else nullmask |= 1u << k2;
                 }
             }
             const uint64_t h = hash_key(kw, nullmask, A.nkeys);
@@ -295,11 +323,12 @@ __global__ void __launch_bounds__(BLOCK, 1) k_hash_aggregate(const __grid_consta
             if (tot >= 64 && hits * 8 < tot && *reinterpret_cast<volatile uint32_t*>(&s_dir_count) >= (uint32_t)FG) bypass = true;
         }
     }
+    }
 
     // ---- merge the front end into the global table ---------------------------------------------------
     __syncthreads();
     const int G = min((int)s_dir_count, FG);
-    for (int g = threadIdx.x; g < G; g += BLOCK) {
+    for (int g = threadIdx.x; g < G; g += THREADS) {
         const uint64_t* dk = dirkeys + gid2slot[g] * (A.nkeys + 1);
         uint64_t kw[MAX_KEYS];
 #pragma unroll
@@ -309,7 +338,7 @@ __global__ void __launch_bounds__(BLOCK, 1) k_hash_aggregate(const __grid_consta
         gslot[g] = (uint64_t)(rec - A.table);
     }
     __syncthreads();
-    for (int g = 0; g < G; g++) {
+    for (int g = 0; g < G && warp < WARPS; g++) {
         uint64_t* rec = A.table + gslot[g];
         for (int i = 0; i < NI; i++) {
             unsigned long long c = cnt[(g * NI + i) * 32 + lane];
@@ -333,7 +362,7 @@ __global__ void __launch_bounds__(BLOCK, 1) k_hash_aggregate(const __grid_consta
             }
         }
     }
-    for (int t = threadIdx.x; t < G * NM; t += BLOCK) {
+    for (int t = threadIdx.x; t < G * NM; t += THREADS) {
         const int g = t / NM, m = t % NM;
         const uint64_t v = mm[t];
         uint64_t* p = A.table + gslot[g] + A.fe_mm_word[m];
@@ -639,14 +668,14 @@ int kq_hashagg_update(kq_ctx* ctx, kq_hashagg* h, kq_batch* input) {
         int t; bool nl;
         KQ_RET(cc.value(h->pred, &t, &nl));
         if (t != KQ_BOOL) return kq_fail(ctx, KQ_ERR_ILLEGAL_STATE, "filter predicate is not Bool");
-        KQ_RET(cc.sink(OP_SET_SEL, 0));
+        KQ_RET(cc.sink(O_SET_SEL, 0));
     }
     std::vector<int> kt, it;
     uint32_t key_f64_mask = 0;
     for (size_t k = 0; k < h->groups.size(); k++) {
         int t; bool nl;
         KQ_RET(cc.key_value(h->groups[k], &t, &nl));
-        KQ_RET(cc.sink(OP_SET_KEY, (int)k));
+        KQ_RET(cc.sink(O_SET_KEY, (int)k));
         if (t == KQ_F64) key_f64_mask |= 1u << k;
         kt.push_back(t);
     }
@@ -662,7 +691,7 @@ int kq_hashagg_update(kq_ctx* ctx, kq_hashagg* h, kq_batch* input) {
             int t2; bool n2;
             KQ_RET(cc.value(h->inputs[i], &t2, &n2));
         }
-        KQ_RET(cc.sink(OP_SET_IN, (int)i));
+        KQ_RET(cc.sink(O_SET_IN, (int)i));
         it.push_back(t);
     }
     if (!h->typed) { h->key_types = kt; h->input_types = it; h->typed = true; }
@@ -696,11 +725,18 @@ int kq_hashagg_update(kq_ctx* ctx, kq_hashagg* h, kq_batch* input) {
     int KW = (int)h->groups.size() + 1;
     int fixed = DIR_SLOTS * KW * 8 + DIR_SLOTS * 4 + FE_MAX_GROUPS * (4 + 8 + 8 * nm) + 64;
     int per_group = WARPS * 32 * (4 * NI + 8 * ns);
-    int budget = ctx->max_smem_optin - 1024 - fixed;
+    // stage ring first (2..4 stages within ~64 KB, more only if two stages need it), front end gets the rest
+    cc.plan_stages(64 * 1024, 1, TILE, &A.sp);
+    if (A.sp.nstages < 2) cc.plan_stages(std::min(2 * A.sp.stage_bytes, 112 * 1024), 2, TILE, &A.sp);
+    A.sp.nstages = std::max(1, std::min(A.sp.nstages, AGG_MAX_STAGES));
+    A.prog = cc.prog;                  // plan_stages filled the staged offsets of the program columns
+    const int ring = A.sp.nstages * A.sp.stage_bytes;
+    int budget = ctx->max_smem_optin - 2048 - fixed - ring;
     int fg = per_group > 0 ? std::min(FE_MAX_GROUPS, budget / per_group) : FE_MAX_GROUPS;
     if (fg < 1) fg = 0;
     A.fe_groups = fg;
-    int off = 0;
+    int off = ring;
+    A.off_fe = off;
     A.off_dirkeys = off; off += DIR_SLOTS * KW * 8;
     A.off_gslot = off; off += FE_MAX_GROUPS * 8;
     A.off_mm = off; off += FE_MAX_GROUPS * 8 * nm;
@@ -711,28 +747,34 @@ int kq_hashagg_update(kq_ctx* ctx, kq_hashagg* h, kq_batch* input) {
     A.smem_bytes = (off + 15) / 16 * 16;
     KQ_CUDA(ctx, cudaFuncSetAttribute(k_hash_aggregate, cudaFuncAttributeMaxDynamicSharedMemorySize, A.smem_bytes));
     int bps = 1;
-    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&bps, k_hash_aggregate, BLOCK, A.smem_bytes);
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&bps, k_hash_aggregate, THREADS, A.smem_bytes);
     if (bps < 1) bps = 1;
     int grid = (int)std::min<int64_t>(A.ntiles, (int64_t)ctx->sm_count * bps);
     // rows that may still create groups after a block has decided to continue: one tile per resident
     // block plus its front end
-    const uint64_t margin = (uint64_t)grid * (TILE + FE_MAX_GROUPS);
+    const uint64_t margin = (uint64_t)grid * ((uint64_t)A.sp.nstages * TILE + FE_MAX_GROUPS);
 
     int64_t tile_begin = 0;
     while (tile_begin < A.ntiles) {
-        // capacity rule: stop taking tiles above capacity/2 groups; up to `margin` more may be created
-        // by tiles in flight, and the table must stay below 3/4 full.
-        uint64_t remaining_rows = (uint64_t)std::min<int64_t>(n - tile_begin * TILE, n);
-        uint64_t need = (uint64_t)h->ngroups_host + std::min(margin, remaining_rows);
+        // Capacity rule. If every remaining row could become a group and the table would still be
+        // below 3/4 full, run unthrottled. Otherwise the service warps stop taking tiles once the
+        // table is half full; tiles already in flight may add up to `inflight` more groups, which
+        // must fit in the next quarter.
+        const uint64_t remaining_rows = (uint64_t)(n - tile_begin * TILE);
+        const uint64_t inflight = std::min(margin, remaining_rows);
         uint64_t cap = h->capacity;
-        while (cap / 2 + std::min(margin, remaining_rows) > cap * 3 / 4 || need > cap * 3 / 4) cap <<= 1;
-        if ((uint64_t)h->ngroups_host > cap / 2) cap <<= 1;
+        bool unthrottled = false;
+        while (true) {
+            if ((uint64_t)h->ngroups_host + remaining_rows <= cap / 4 * 3) { unthrottled = true; break; }
+            if (cap / 4 >= inflight && (uint64_t)h->ngroups_host < cap / 2) break;
+            cap <<= 1;
+        }
         if (cap != h->capacity) KQ_RET(table_grow(ctx, h, cap));
         fill_common_args(h, A);
         A.tile_begin = tile_begin;
-        A.stop_threshold = h->capacity / 2;
+        A.stop_threshold = unthrottled ? ~0ULL : h->capacity / 2;
         KQ_CUDA(ctx, cudaMemsetAsync(h->d_counters + 1, 0, 8, ctx->stream));
-        k_hash_aggregate<<<grid, BLOCK, A.smem_bytes, ctx->stream>>>(A);
+        k_hash_aggregate<<<grid, THREADS, A.smem_bytes, ctx->stream>>>(A);
         KQ_RET(launch_check(ctx, "k_hash_aggregate"));
         uint64_t c[2];
         KQ_RET(kq_read_u64(ctx, h->d_counters, 2, c));

@@ -11,6 +11,7 @@
 #include <cstring>
 
 #include "kq_compile.h"
+#include "kq_pipe.cuh"
 #include "kq_scan.cuh"
 
 using namespace kq;
@@ -27,7 +28,7 @@ struct DOut {
 struct OpArgs {
     Program prog;
     int64_t n, ntiles;
-    int32_t sel_end;          // instructions [0, sel_end) evaluate the predicate and end in OP_SET_SEL
+    int32_t sel_end;          // instructions [0, sel_end) evaluate the predicate and end in O_SET_SEL
     int32_t nout;
     DOut outs[MAX_OUT];
     unsigned long long* tile_desc;
@@ -35,7 +36,16 @@ struct OpArgs {
     unsigned long long* out_count;
     int32_t* selvec;
     uint32_t* err;
+    StagePlan sp;
 };
+
+// One CTA per SM: 15 consumer warps evaluate, one service warp streams tiles in with TMA bulk copies
+// (and, in the filter kernel, resolves the cross-block prefix). 512 threads -> 128 registers each.
+constexpr int WARPS = 15;
+constexpr int BLOCK = WARPS * 32;
+constexpr int TILE = WARPS * WARP_ROWS;     // 1920 rows
+constexpr int SERVICE_WARP = WARPS;
+constexpr int THREADS = BLOCK + 32;
 
 struct SinkBase {
     __device__ __forceinline__ void set_sel(const uint64_t (&)[R], uint32_t, RowCtx&) {}
@@ -118,67 +128,181 @@ struct CompactSink : SinkBase {
     }
 };
 
-__global__ void __launch_bounds__(BLOCK) k_project(const __grid_constant__ OpArgs A) {
+// ProjectionExec for one batch (Main.kt:589-594).
+__global__ void __launch_bounds__(THREADS, 1) k_project(const __grid_constant__ OpArgs A) {
+    extern __shared__ __align__(128) unsigned char stages[];
+    __shared__ uint64_t full[MAX_STAGES], empty[MAX_STAGES];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int S = A.sp.nstages;
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < S; s++) { mbar_init(&full[s], 1); mbar_init(&empty[s], WARPS); }
+        mbar_fence_init();
+    }
+    __syncthreads();
+    if (warp == SERVICE_WARP) {
+        if (lane == 0) {
+            int k = 0;
+            for (int64_t tile = blockIdx.x; tile < A.ntiles; tile += gridDim.x, k++) {
+                const int s = k % S;
+                mbar_wait(&empty[s], ((k / S) & 1) ^ 1);
+                stage_issue(A.sp, stages + (size_t)s * A.sp.stage_bytes, &full[s], tile, TILE, A.n);
+            }
+        }
+        return;
+    }
     ProjectSink sink;
     sink.outs = A.outs;
-    Stack st;
-    for (int64_t tile = blockIdx.x; tile < A.ntiles; tile += gridDim.x) {
+    Vm st;
+    int k = 0;
+    for (int64_t tile = blockIdx.x; tile < A.ntiles; tile += gridDim.x, k++) {
+        const int s = k % S;
+        mbar_wait(&full[s], (k / S) & 1);
         RowCtx rc;
-        rowctx_init(rc, tile, A.n, A.err);
+        rowctx_init(rc, tile, TILE, A.n, A.err, stages + (size_t)s * A.sp.stage_bytes);
         run(A.prog, 0, A.prog.ninsn, st, rc, sink);
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&empty[s]);
     }
 }
 
-__global__ void __launch_bounds__(BLOCK) k_filter_project(const __grid_constant__ OpArgs A) {
-    __shared__ long long s_tile;
-    __shared__ int s_wtot[WARPS];
-    __shared__ unsigned long long s_prefix;
+// FilterExec + ProjectionExec, single pass. Per tile k the consumer warps run step A (predicate ->
+// selection mask, ballot/popc ranks, per-warp totals) one tile AHEAD of step B (cross-block prefix,
+// projection, compacted stores); the tile's columns wait in their shared-memory stage in between.
+// The service warp turns the per-warp totals of a tile into its global exclusive prefix (decoupled
+// look-back over tile descriptors in HBM) while the consumers are busy with step A of the next
+// tile, so the L2 round trips of the look-back stay off the critical path; in between it keeps the
+// stage ring full (tickets are taken in look-back order).
+__global__ void __launch_bounds__(THREADS, 1) k_filter_project(const __grid_constant__ OpArgs A) {
+    extern __shared__ __align__(128) unsigned char stages[];
+    __shared__ uint64_t full[MAX_STAGES], empty[MAX_STAGES], agg_ready[MAX_STAGES], prefix_ready[MAX_STAGES];
+    __shared__ long long tile_of[MAX_STAGES];
+    __shared__ unsigned long long prefix[MAX_STAGES];
+    __shared__ int wtot[MAX_STAGES][WARPS];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int S = A.sp.nstages;
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < S; s++) {
+            mbar_init(&full[s], 1); mbar_init(&empty[s], WARPS);
+            mbar_init(&agg_ready[s], WARPS); mbar_init(&prefix_ready[s], 1);
+        }
+        mbar_fence_init();
+    }
+    __syncthreads();
+
+    if (warp == SERVICE_WARP) {
+        int kp = 0, kl = 0;                    // next tile slot to produce / to look back
+        bool prod_done = false, lb_done = false;
+        while (!prod_done || !lb_done) {
+            bool did = false;
+            if (!prod_done) {
+                const int s = kp % S;
+                int go = 0;
+                if (lane == 0) go = mbar_try_wait(&empty[s], ((kp / S) & 1) ^ 1) ? 1 : 0;
+                go = __shfl_sync(0xffffffffu, go, 0);
+                if (go) {
+                    int end = 0;
+                    if (lane == 0) {
+                        const long long tile = (long long)atomicAdd(A.ticket, 1u);     // ticket order = look-back order
+                        tile_of[s] = tile;
+                        if (tile >= A.ntiles) { mbar_arrive(&full[s]); end = 1; }
+                        else stage_issue(A.sp, stages + (size_t)s * A.sp.stage_bytes, &full[s], tile, TILE, A.n);
+                    }
+                    end = __shfl_sync(0xffffffffu, end, 0);
+                    if (end) prod_done = true;
+                    kp++; did = true;
+                }
+            }
+            if (!lb_done) {
+                const int s = kl % S;
+                int go = 0;
+                if (lane == 0) go = mbar_try_wait(&agg_ready[s], (kl / S) & 1) ? 1 : 0;
+                go = __shfl_sync(0xffffffffu, go, 0);
+                if (go) {
+                    const long long tile = tile_of[s];
+                    if (tile >= A.ntiles) lb_done = true;
+                    else {
+                        int t = lane < WARPS ? wtot[s][lane] : 0;
+#pragma unroll
+                        for (int o = 16; o; o >>= 1) t += __shfl_xor_sync(0xffffffffu, t, o);
+                        unsigned long long excl = lookback_exclusive(A.tile_desc, tile, (unsigned long long)t);
+                        if (lane == 0) {
+                            prefix[s] = excl;
+                            if (tile == A.ntiles - 1) *A.out_count = excl + (unsigned long long)t;
+                            mbar_arrive(&prefix_ready[s]);
+                        }
+                    }
+                    kl++; did = true;
+                }
+            }
+            if (!did) __nanosleep(32);
+        }
+        return;
+    }
+
     CompactSink sink;
     sink.outs = A.outs;
-    Stack st;
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    Vm st;
     const uint32_t lt = (1u << lane) - 1u;
-    while (true) {
-        if (threadIdx.x == 0) s_tile = (long long)atomicAdd(A.ticket, 1u);
-        __syncthreads();
-        const long long tile = s_tile;
-        if (tile >= A.ntiles) break;
-        RowCtx rc;
-        rowctx_init(rc, tile, A.n, A.err);
-        sink.sel = 0;
-        run(A.prog, 0, A.sel_end, st, rc, sink);
-        rc.active = sink.sel;      // projection errors only count on surviving rows (FilterExec runs first)
-        // ranks inside the warp, in row order: chunk j, then lane, then the pair element
-        int wtot = 0;
+    // state of the tile whose step B is pending
+    bool have_prev = false;
+    uint32_t p_sel = 0; int p_rank[R]; long long p_tile = 0; int p_s = 0, p_k = 0;
 #pragma unroll
-        for (int j = 0; j < NCHUNK; j++) {
-            uint32_t s0 = (sink.sel >> (2 * j)) & 1u, s1 = (sink.sel >> (2 * j + 1)) & 1u;
-            uint32_t b0 = __ballot_sync(0xffffffffu, s0), b1 = __ballot_sync(0xffffffffu, s1);
-            int below = __popc(b0 & lt) + __popc(b1 & lt);
-            sink.rank[2 * j] = wtot + below;
-            sink.rank[2 * j + 1] = wtot + below + (int)s0;
-            wtot += __popc(b0) + __popc(b1);
-        }
-        if (lane == 0) s_wtot[warp] = wtot;
-        __syncthreads();
-        int woff = 0, ttot = 0;
+    for (int r = 0; r < R; r++) p_rank[r] = 0;
+    for (int k = 0;; k++) {
+        const int s = k % S;
+        mbar_wait(&full[s], (k / S) & 1);
+        const long long tile = tile_of[s];
+        const bool last = tile >= A.ntiles;
+        uint32_t c_sel = 0; int c_rank[R];
 #pragma unroll
-        for (int w = 0; w < WARPS; w++) { int x = s_wtot[w]; if (w < warp) woff += x; ttot += x; }
-        if (warp == 0) {
-            unsigned long long excl = lookback_exclusive(A.tile_desc, tile, (unsigned long long)ttot);
-            if (lane == 0) {
-                s_prefix = excl;
-                if (tile == A.ntiles - 1) *A.out_count = excl + (unsigned long long)ttot;
+        for (int r = 0; r < R; r++) c_rank[r] = 0;
+        if (!last) {
+            // ---- step A(k): predicate, ranks in row order (chunk, lane, pair element), warp total
+            RowCtx rc;
+            rowctx_init(rc, tile, TILE, A.n, A.err, stages + (size_t)s * A.sp.stage_bytes);
+            sink.sel = 0;
+            run(A.prog, 0, A.sel_end, st, rc, sink);
+            c_sel = sink.sel;
+            int wt = 0;
+#pragma unroll
+            for (int j = 0; j < NCHUNK; j++) {
+                uint32_t s0 = (c_sel >> (2 * j)) & 1u, s1 = (c_sel >> (2 * j + 1)) & 1u;
+                uint32_t b0 = __ballot_sync(0xffffffffu, s0), b1 = __ballot_sync(0xffffffffu, s1);
+                int below = __popc(b0 & lt) + __popc(b1 & lt);
+                c_rank[2 * j] = wt + below;
+                c_rank[2 * j + 1] = wt + below + (int)s0;
+                wt += __popc(b0) + __popc(b1);
             }
+            if (lane == 0) wtot[s][warp] = wt;
         }
-        __syncthreads();
-        sink.base = (long long)s_prefix + woff;
-        if (A.selvec) {
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&agg_ready[s]);          // also wakes the service warp for the end sentinel
+        if (have_prev) {
+            // ---- step B(k-1): prefix, projection, compacted stores
+            mbar_wait(&prefix_ready[p_s], (p_k / S) & 1);
+            int woff = 0;
 #pragma unroll
-            for (int r = 0; r < R; r++)
-                if ((sink.sel >> r) & 1u) A.selvec[sink.base + sink.rank[r]] = (int32_t)(rc.row0(r >> 1) + (r & 1));
+            for (int w = 0; w < WARPS; w++) { int x = wtot[p_s][w]; if (w < warp) woff += x; }
+            RowCtx rc;
+            rowctx_init(rc, p_tile, TILE, A.n, A.err, stages + (size_t)p_s * A.sp.stage_bytes);
+            rc.active = p_sel;        // projection errors only count on surviving rows (FilterExec runs first)
+            sink.sel = p_sel;
+#pragma unroll
+            for (int r = 0; r < R; r++) sink.rank[r] = p_rank[r];
+            sink.base = (long long)prefix[p_s] + woff;
+            if (A.selvec) {
+#pragma unroll
+                for (int r = 0; r < R; r++)
+                    if ((p_sel >> r) & 1u) A.selvec[sink.base + p_rank[r]] = (int32_t)(rc.row0(r >> 1) + (r & 1));
+            }
+            run(A.prog, A.sel_end, A.prog.ninsn, st, rc, sink);
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&empty[p_s]);
         }
-        run(A.prog, A.sel_end, A.prog.ninsn, st, rc, sink);
+        if (last) break;
+        have_prev = true; p_sel = c_sel; p_tile = tile; p_s = s; p_k = k;
+#pragma unroll
+        for (int r = 0; r < R; r++) p_rank[r] = c_rank[r];
     }
 }
 
@@ -222,9 +346,13 @@ __global__ void k_utf8_gather_bytes(const int32_t* __restrict__ in_off, const ui
     }
 }
 
-int blocks_per_sm(const void* fn) {
+// Shared memory available for the stage ring of one CTA when `ctas` CTAs share an SM.
+int stage_budget(kq_ctx* ctx, int ctas) {
+    return (ctx->max_smem_optin + 1024) / ctas - 1024 - 2048;   // 1 KB/CTA reserved by the driver, 2 KB static
+}
+int blocks_per_sm(const void* fn, int threads, int smem) {
     int nb = 1;
-    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, fn, BLOCK, 0) != cudaSuccess || nb < 1) nb = 1;
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, fn, threads, smem) != cudaSuccess || nb < 1) nb = 1;
     return nb;
 }
 
@@ -314,7 +442,7 @@ int run_operator(kq_ctx* ctx, kq_expr* pred, kq_expr* const* exprs, int nexprs, 
         int t; bool nl;
         if ((st = cc.value(pred, &t, &nl)) != KQ_OK) return fail(st);
         if (t != KQ_BOOL) return fail(kq_fail(ctx, KQ_ERR_ILLEGAL_STATE, "filter predicate is not Bool"));
-        if ((st = cc.sink(OP_SET_SEL, 0)) != KQ_OK) return fail(st);
+        if ((st = cc.sink(O_SET_SEL, 0)) != KQ_OK) return fail(st);
         A.sel_end = cc.pc();
         lazy = kq_lazy_new(ctx);
         if (!lazy) return fail(kq_fail(ctx, KQ_ERR_OUT_OF_MEMORY, "lazy count"));
@@ -346,12 +474,14 @@ int run_operator(kq_ctx* ctx, kq_expr* pred, kq_expr* const* exprs, int nexprs, 
                 if (t2 == KQ_BOOL) cudaMemsetAsync(c->data, 0, (size_t)((n + 63) / 64) * 8, ctx->stream);
             }
             A.outs[nvm].data = c->data; A.outs[nvm].validity = c->validity; A.outs[nvm].type = t2;
-            if ((st = cc.sink(OP_EMIT, nvm)) != KQ_OK) return fail2(st);
+            if ((st = cc.sink(O_EMIT, nvm)) != KQ_OK) return fail2(st);
             nvm++;
         }
     }
     A.nout = nvm;
+    cc.plan_stages(stage_budget(ctx, 1), pred ? 3 : 2, TILE, &A.sp);
     A.prog = cc.prog;
+    const int smem = A.sp.nstages * A.sp.stage_bytes;
 
     bool need_sel = selection != nullptr;
     for (int m : mode) need_sel |= (m == 2);
@@ -371,9 +501,10 @@ int run_operator(kq_ctx* ctx, kq_expr* pred, kq_expr* const* exprs, int nexprs, 
         A.tile_desc = scratch + 2;
         A.out_count = lazy->d_slot;
         if (n > 0) {
-            static int bps = blocks_per_sm((const void*)k_filter_project);
+            cudaFuncSetAttribute(k_filter_project, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+            int bps = blocks_per_sm((const void*)k_filter_project, THREADS, smem);
             int grid = (int)std::min<int64_t>(A.ntiles, (int64_t)ctx->sm_count * bps);
-            k_filter_project<<<grid, BLOCK, 0, ctx->stream>>>(A);
+            k_filter_project<<<grid, THREADS, smem, ctx->stream>>>(A);
             if ((st = launch_check(ctx, "k_filter_project")) != KQ_OK) { kq_dev_free(ctx, scratch); return fail3(st); }
         }
         kq_dev_free(ctx, scratch);
@@ -389,9 +520,10 @@ int run_operator(kq_ctx* ctx, kq_expr* pred, kq_expr* const* exprs, int nexprs, 
         for (size_t k = 0; k < ex.size(); k++)
             if (mode[k] == 1) { outs[k] = input->cols[(size_t)KqCompiler::bare_column(ex[k])]; outs[k]->rc.fetch_add(1); }
         if (nvm > 0 && n > 0) {
-            static int bps = blocks_per_sm((const void*)k_project);
+            cudaFuncSetAttribute(k_project, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+            int bps = blocks_per_sm((const void*)k_project, THREADS, smem);
             int grid = (int)std::min<int64_t>(A.ntiles, (int64_t)ctx->sm_count * bps);
-            k_project<<<grid, BLOCK, 0, ctx->stream>>>(A);
+            k_project<<<grid, THREADS, smem, ctx->stream>>>(A);
             if ((st = launch_check(ctx, "k_project")) != KQ_OK) return fail3(st);
         }
     }

@@ -1,0 +1,97 @@
+// kq_pipe.cuh — the tile pipeline every streaming kernel shares.
+//
+// A producer warp (one elected lane) moves the next tiles of every referenced column buffer from
+// HBM into a ring of shared-memory stages with 1-D TMA bulk copies (cp.async.bulk ... mbarrier::
+// complete_tx, SASS UBLKCP); consumer warps wait on the stage's "full" mbarrier, run the expression
+// VM out of shared memory and hand the stage back through its "empty" mbarrier. Bytes in flight per
+// SM = (stages - 1) x stage bytes, independent of occupancy and of how the VM serialises its loads —
+// this is what lets an HBM-bound integer/byte path approach the copy roofline on B200.
+#pragma once
+
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace kq {
+
+constexpr int MAX_STAGE_BUFS = 24;
+constexpr int MAX_STAGES = 8;
+
+enum StageKind : int32_t { SK_W8 = 0, SK_W4 = 1, SK_W4_PLUS1 = 2, SK_BIT = 3 };
+
+struct StageBuf {
+    const char* g;        // global base of the buffer
+    int32_t soff;         // byte offset inside a stage (128-byte aligned)
+    int32_t kind;         // StageKind
+};
+
+struct StagePlan {
+    int32_t nbuf;
+    int32_t stage_bytes;  // multiple of 128
+    int32_t nstages;
+    int32_t _pad;
+    StageBuf buf[MAX_STAGE_BUFS];
+};
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_fence_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t* bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
+    uint32_t ok;
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(ok) : "r"(smem_u32(bar)), "r"(parity) : "memory");
+    return ok != 0;
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+    while (!mbar_try_wait(bar, parity)) {}
+}
+// 1-D TMA bulk copy global -> shared, completion counted in bytes on `bar`.
+__device__ __forceinline__ void bulk_g2s(void* dst_smem, const void* src, uint32_t bytes, uint64_t* bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 ::"r"(smem_u32(dst_smem)), "l"(src), "r"(bytes), "r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void bulk_prefetch_l2(const void* src, uint32_t bytes) {
+    asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(src), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void named_bar_sync(int id, int nthreads) {
+    asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
+}
+
+// Issue the bulk copies of tile `tile` (rows [tile*tile_rows, ...)) into one stage. Called by one thread.
+__device__ __forceinline__ void stage_issue(const StagePlan& sp, unsigned char* stage, uint64_t* full, int64_t tile,
+                                            int tile_rows, int64_t n) {
+    int64_t row0 = tile * tile_rows;
+    int rows = (int)((n - row0) < tile_rows ? (n - row0) : tile_rows);
+    uint32_t total = 0;
+#pragma unroll 1
+    for (int b = 0; b < sp.nbuf; b++) {
+        const int kind = sp.buf[b].kind;
+        uint32_t bytes = kind == SK_W8 ? rows * 8 : (kind == SK_W4 ? rows * 4 : (kind == SK_W4_PLUS1 ? (rows + 1) * 4 : (rows + 7) / 8));
+        total += (bytes + 15u) & ~15u;
+    }
+    mbar_arrive_expect_tx(full, total);
+#pragma unroll 1
+    for (int b = 0; b < sp.nbuf; b++) {
+        const StageBuf sb = sp.buf[b];
+        uint32_t bytes; int64_t goff;
+        if (sb.kind == SK_W8) { bytes = rows * 8; goff = row0 * 8; }
+        else if (sb.kind == SK_W4) { bytes = rows * 4; goff = row0 * 4; }
+        else if (sb.kind == SK_W4_PLUS1) { bytes = (rows + 1) * 4; goff = row0 * 4; }
+        else { bytes = (rows + 7) / 8; goff = row0 / 8; }
+        bytes = (bytes + 15u) & ~15u;       // device buffers are padded (KQ_PAD), whole vectors past the end are readable
+        bulk_g2s(stage + sb.soff, sb.g + goff, bytes, full);
+    }
+}
+
+}  // namespace kq

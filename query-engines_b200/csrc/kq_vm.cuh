@@ -1,16 +1,20 @@
 // kq_vm.cuh — the fused expression evaluator shared by every operator kernel.
 //
 // An expression tree (Expression.evaluate, Main.kt:448-450; the reference materialises one Arrow
-// vector per node, Main.kt:780-803) is flattened on the host into a postfix program and executed
-// by ONE kernel. The program is uniform across the grid, so instruction dispatch is a
-// divergence-free branch whose cost is amortised over the KQ_R rows each thread carries. The
-// evaluation stack lives in registers: every stack access is indexed by the compile-time stack
-// pointer (template parameter SP — the host compiler stamps the stack pointer into each
-// instruction), so nothing spills to local memory.
+// vector per node, Main.kt:780-803) is flattened on the host into a short program and executed by
+// ONE kernel. The program is uniform across the grid, so instruction dispatch is a divergence-free
+// branch whose cost is amortised over the R rows each thread carries.
+//
+// The machine is an accumulator machine held entirely in registers: ACC (R values + validity mask),
+// one operand register TMP, and a small save stack. An instruction is {fetch TMP from a column /
+// literal / saved slot / Utf8 operator} followed by {ACC = ACC op TMP}. The host compiler evaluates
+// the non-leaf side of a binary node into ACC and feeds the leaf side straight from the column, so
+// typical expressions (a*b+c, a>k AND b<m) never touch the save stack, and every operator body
+// exists exactly once in the SASS (small code, no spills).
 //
 // Row ownership inside a tile of TILE = BLOCK*R rows: warp w owns rows [w*32R, (w+1)*32R); inside
 // that, chunk j (of R/2) covers 64 rows and lane l owns the adjacent pair (2l, 2l+1). One pair of
-// 8-byte values is one 128-bit coalesced load; one pair of validity bits comes from one 32-bit word.
+// 8-byte values is one 128-bit access; one pair of validity bits comes from one 32-bit word.
 #pragma once
 
 #include <cuda_runtime.h>
@@ -20,11 +24,8 @@ namespace kq {
 
 constexpr int R = 4;                 // rows per thread (even)
 constexpr int NCHUNK = R / 2;
-constexpr int BLOCK = 256;
-constexpr int WARPS = BLOCK / 32;
-constexpr int WARP_ROWS = 32 * R;
-constexpr int TILE = BLOCK * R;
-constexpr int D = 6;                 // evaluation stack depth
+constexpr int WARP_ROWS = 32 * R;    // rows one warp owns per tile; a tile is (consumer warps) x WARP_ROWS rows
+constexpr int DS = 3;                // save slots (nesting depth of binary nodes with two non-leaf operands)
 constexpr int MAX_COLS = 16;
 constexpr int MAX_INSN = 96;
 constexpr int MAX_LIT = 32;
@@ -34,31 +35,34 @@ constexpr int MAX_KEYS = 4;
 constexpr int MAX_INPUTS = 6;
 constexpr uint32_t RMASK = (1u << R) - 1u;
 
+// operand fetch
+enum Src : uint8_t {
+    S_NONE = 0, S_COL64, S_COL32, S_COLBIT, S_LIT, S_NULL, S_VALID, S_STACK,
+    S_UTF8_CMP_LIT,                  // a = col, b = lit | mask << 8 : Bool
+    S_UTF8_CMP_COL,                  // a = colA, b = colB | mask << 8 : Bool
+    S_UTF8_PACK,                     // a = col: short string (<= 7 bytes) -> packed u64 group key
+    S_UTF8_F64                       // a = col: CastExpression Utf8 -> Float64 (Main.kt:772-805)
+};
+// operation: ACC = ACC op TMP (R* variants: ACC = TMP op ACC)
 enum Op : uint8_t {
-    OP_END = 0,
-    OP_PUSH_COL64, OP_PUSH_COL32, OP_PUSH_COLBIT, OP_PUSH_LIT, OP_PUSH_NULL, OP_PUSH_VALID,
-    OP_ADD_I64, OP_SUB_I64, OP_MUL_I64, OP_DIV_I64,
-    OP_ADD_F64, OP_SUB_F64, OP_MUL_F64, OP_DIV_F64,
-    OP_CMP_I64, OP_CMP_F64,          // arg = 4-bit truth mask over {lt, eq, gt, unordered}
-    OP_AND, OP_OR,
-    OP_UTF8_CMP_LIT,                 // arg = col | lit << 5 | mask << 10
-    OP_UTF8_CMP_COL,                 // arg = colA | colB << 5 | mask << 10
-    OP_UTF8_PACK,                    // arg = col: short string (<= 7 bytes) -> packed u64 key
-    OP_I64_TO_F64,
-    OP_UTF8_TO_F64,                  // arg = col: CastExpression Utf8 -> Float64 (Main.kt:772-805)
-    OP_PICK,                         // arg = depth below top to copy
-    OP_SET_SEL, OP_EMIT, OP_SET_KEY, OP_SET_IN
+    O_END = 0, O_LOAD, O_PUSH,
+    O_ADD_I64, O_SUB_I64, O_RSUB_I64, O_MUL_I64, O_DIV_I64, O_RDIV_I64,
+    O_ADD_F64, O_SUB_F64, O_RSUB_F64, O_MUL_F64, O_DIV_F64, O_RDIV_F64,
+    O_CMP_I64, O_CMP_F64,            // b = 4-bit truth mask over {lt, eq, gt, unordered} of (ACC ? TMP)
+    O_AND, O_OR, O_I64_TO_F64,
+    O_SET_SEL, O_EMIT, O_SET_KEY, O_SET_IN
 };
 
 // comparison truth masks: bit0 = lt, bit1 = eq, bit2 = gt, bit3 = unordered (NaN)
 constexpr uint32_t CM_EQ = 0x2, CM_NE = 0xD, CM_LT = 0x1, CM_LE = 0x3, CM_GT = 0x4, CM_GE = 0x6;
 
-struct Insn { uint8_t op, sp; uint16_t arg; };
+struct Insn { uint8_t op, src; uint16_t a; uint32_t b; };
 
 struct DCol {
     const void* data;
     const uint32_t* validity;
     const int32_t* offsets;
+    int32_t s_data, s_valid, s_off, _pad;   // byte offsets of the staged copies inside a pipeline stage (-1: not staged)
 };
 
 struct Program {
@@ -70,10 +74,14 @@ struct Program {
     DCol cols[MAX_COLS];
 };
 
-struct Stack {
-    uint64_t v[D][R];
-    uint32_t ok[D];                  // R-bit validity mask per slot
+struct Vm {
+    uint64_t acc[R]; uint32_t aok;   // accumulator + R-bit validity mask
+    uint64_t tmp[R]; uint32_t tok;   // operand
+    // save slots are separate members on purpose: an array indexed by the instruction would be
+    // demoted to local memory by the compiler
+    uint64_t s0[R], s1[R], s2[R]; uint32_t k0, k1, k2;
 };
+static_assert(DS == 3, "Vm has exactly three save slots");
 
 // Per-thread view of the current tile.
 struct RowCtx {
@@ -84,7 +92,10 @@ struct RowCtx {
     uint32_t inr;                    // R-bit mask of owned rows that are < n
     uint32_t active;                 // rows whose errors count (in range and selected)
     uint32_t* err;
+    const unsigned char* stage;      // shared-memory stage holding this tile's staged buffers (kq_pipe.cuh)
+    int wrow;                        // first row of this warp inside the tile
     __device__ __forceinline__ int64_t row0(int j) const { return warp_base + j * 64 + lane * 2; }
+    __device__ __forceinline__ int trow0(int j) const { return wrow + j * 64 + lane * 2; }   // row inside the tile
 };
 
 __device__ __forceinline__ uint4 ldg_nc_v4(const void* p) {
@@ -122,7 +133,9 @@ __device__ __forceinline__ uint2 interleave_ballots(uint32_t b0, uint32_t b1) {
 }
 
 // ---- column loads --------------------------------------------------------------------------------------
-__device__ __forceinline__ uint32_t load_bits(const uint32_t* bits, const RowCtx& rc) {
+// Staged buffers are read from the tile's shared-memory stage (filled by TMA bulk copies); buffers
+// that did not fit the stage budget are read from global memory with 128-bit coalesced loads.
+__device__ __forceinline__ uint32_t load_bits_g(const uint32_t* bits, const RowCtx& rc) {
     uint32_t m = 0;
 #pragma unroll
     for (int j = 0; j < NCHUNK; j++) {
@@ -134,38 +147,79 @@ __device__ __forceinline__ uint32_t load_bits(const uint32_t* bits, const RowCtx
     }
     return m;
 }
-__device__ __forceinline__ uint32_t load_valid(const DCol& c, const RowCtx& rc) {
-    return c.validity ? (load_bits(c.validity, rc) & rc.inr) : rc.inr;
-}
-__device__ __forceinline__ void load64(const DCol& c, const RowCtx& rc, uint64_t (&v)[R], uint32_t& ok) {
-    const uint4* p = reinterpret_cast<const uint4*>(c.data);
+__device__ __forceinline__ uint32_t load_bits_s(const unsigned char* sbits, const RowCtx& rc) {
+    uint32_t m = 0;
 #pragma unroll
     for (int j = 0; j < NCHUNK; j++) {
-        int64_t r0 = rc.row0(j);
-        uint4 q = make_uint4(0, 0, 0, 0);
-        if (rc.full || r0 < rc.n) q = ldg_nc_v4(p + (r0 >> 1));
-        v[2 * j] = (uint64_t)q.x | ((uint64_t)q.y << 32);
-        v[2 * j + 1] = (uint64_t)q.z | ((uint64_t)q.w << 32);
+        int t0 = rc.trow0(j);
+        uint32_t w = *reinterpret_cast<const uint32_t*>(sbits + (t0 >> 5) * 4);
+        m |= ((w >> (t0 & 31)) & 3u) << (2 * j);
+    }
+    return m;
+}
+__device__ __forceinline__ uint32_t load_valid(const DCol& c, const RowCtx& rc) {
+    if (!c.validity) return rc.inr;
+    return (c.s_valid >= 0 ? load_bits_s(rc.stage + c.s_valid, rc) : load_bits_g(c.validity, rc)) & rc.inr;
+}
+__device__ __forceinline__ void load64(const DCol& c, const RowCtx& rc, uint64_t (&v)[R], uint32_t& ok) {
+    if (c.s_data >= 0) {
+        const unsigned char* p = rc.stage + c.s_data;
+#pragma unroll
+        for (int j = 0; j < NCHUNK; j++) {
+            uint4 q = *reinterpret_cast<const uint4*>(p + rc.trow0(j) * 8);
+            v[2 * j] = (uint64_t)q.x | ((uint64_t)q.y << 32);
+            v[2 * j + 1] = (uint64_t)q.z | ((uint64_t)q.w << 32);
+        }
+    } else {
+        const uint4* p = reinterpret_cast<const uint4*>(c.data);
+#pragma unroll
+        for (int j = 0; j < NCHUNK; j++) {
+            int64_t r0 = rc.row0(j);
+            uint4 q = make_uint4(0, 0, 0, 0);
+            if (rc.full || r0 < rc.n) q = ldg_nc_v4(p + (r0 >> 1));
+            v[2 * j] = (uint64_t)q.x | ((uint64_t)q.y << 32);
+            v[2 * j + 1] = (uint64_t)q.z | ((uint64_t)q.w << 32);
+        }
     }
     ok = load_valid(c, rc);
 }
 __device__ __forceinline__ void load32(const DCol& c, const RowCtx& rc, uint64_t (&v)[R], uint32_t& ok) {
-    const uint2* p = reinterpret_cast<const uint2*>(c.data);
+    if (c.s_data >= 0) {
+        const unsigned char* p = rc.stage + c.s_data;
 #pragma unroll
-    for (int j = 0; j < NCHUNK; j++) {
-        int64_t r0 = rc.row0(j);
-        uint2 q = make_uint2(0, 0);
-        if (rc.full || r0 < rc.n) q = ldg_nc_v2(p + (r0 >> 1));
-        v[2 * j] = (uint64_t)(int64_t)(int32_t)q.x;
-        v[2 * j + 1] = (uint64_t)(int64_t)(int32_t)q.y;
+        for (int j = 0; j < NCHUNK; j++) {
+            uint2 q = *reinterpret_cast<const uint2*>(p + rc.trow0(j) * 4);
+            v[2 * j] = (uint64_t)(int64_t)(int32_t)q.x;
+            v[2 * j + 1] = (uint64_t)(int64_t)(int32_t)q.y;
+        }
+    } else {
+        const uint2* p = reinterpret_cast<const uint2*>(c.data);
+#pragma unroll
+        for (int j = 0; j < NCHUNK; j++) {
+            int64_t r0 = rc.row0(j);
+            uint2 q = make_uint2(0, 0);
+            if (rc.full || r0 < rc.n) q = ldg_nc_v2(p + (r0 >> 1));
+            v[2 * j] = (uint64_t)(int64_t)(int32_t)q.x;
+            v[2 * j + 1] = (uint64_t)(int64_t)(int32_t)q.y;
+        }
     }
     ok = load_valid(c, rc);
 }
 __device__ __forceinline__ void loadbit(const DCol& c, const RowCtx& rc, uint64_t (&v)[R], uint32_t& ok) {
-    uint32_t m = load_bits(reinterpret_cast<const uint32_t*>(c.data), rc);
+    uint32_t m = c.s_data >= 0 ? load_bits_s(rc.stage + c.s_data, rc) : load_bits_g(reinterpret_cast<const uint32_t*>(c.data), rc);
 #pragma unroll
     for (int r = 0; r < R; r++) v[r] = (m >> r) & 1u;
     ok = load_valid(c, rc);
+}
+// byte range [a, b) of the string in owned row r (offsets from the stage when staged)
+__device__ __forceinline__ void utf8_bounds(const DCol& c, const RowCtx& rc, int r, int& a, int& b) {
+    if (c.s_off >= 0) {
+        const int32_t* o = reinterpret_cast<const int32_t*>(rc.stage + c.s_off) + rc.trow0(r >> 1) + (r & 1);
+        a = o[0]; b = o[1];
+    } else {
+        int64_t row = rc.row0(r >> 1) + (r & 1);
+        a = __ldg(c.offsets + row); b = __ldg(c.offsets + row + 1);
+    }
 }
 
 // ---- Utf8 ------------------------------------------------------------------------------------------------
@@ -242,255 +296,237 @@ __device__ __forceinline__ int parse_f64(const uint8_t* p, int n, double& out) {
     return 0;
 }
 
-// ---- one instruction at a compile-time stack pointer ---------------------------------------------------------
-template <int SP, class Sink>
-__device__ __forceinline__ void step(const Program& P, const Insn in, Stack& st, RowCtx& rc, Sink& sink) {
-    constexpr int T = SP - 1;      // top
-    constexpr int U = SP - 2;      // under top
-    switch (in.op) {
-        case OP_PUSH_COL64: if constexpr (SP < D) load64(P.cols[in.arg], rc, st.v[SP], st.ok[SP]); break;
-        case OP_PUSH_COL32: if constexpr (SP < D) load32(P.cols[in.arg], rc, st.v[SP], st.ok[SP]); break;
-        case OP_PUSH_COLBIT: if constexpr (SP < D) loadbit(P.cols[in.arg], rc, st.v[SP], st.ok[SP]); break;
-        case OP_PUSH_LIT:
-            if constexpr (SP < D) {
-                uint64_t x = P.lit[in.arg];
+// ---- Utf8 operators. The per-row bodies are out of line (big and rare: they must not bloat the main
+// loop or its register allocation); they take and return scalars so the VM registers stay registers.
+static __device__ __noinline__ uint32_t utf8_cmp_row(const uint8_t* p, int pn, const uint8_t* q, int qn, uint32_t mask) {
+    int code;
+    if ((mask == CM_EQ || mask == CM_NE) && pn != qn) code = 2;
+    else code = utf8_cmp3(p, pn, q, qn);
+    return (mask >> code) & 1u;
+}
+static __device__ __noinline__ unsigned long long utf8_pack_row(const uint8_t* p, int len) {
+    unsigned long long key = 0;
+    for (int i = 0; i < len; i++) key |= (unsigned long long)__ldg(p + i) << (8 * i);
+    return key | ((unsigned long long)len << 56);
+}
+static __device__ __noinline__ double parse_f64_row(const uint8_t* p, int n, uint32_t* err, bool active) {
+    double v = 0.0;
+    int pe = parse_f64(p, n, v);
+    if (pe && active) atomicOr(err, pe == 1 ? 4u : 8u);     // NumberFormatException / unsupported range
+    return v;
+}
+__device__ __forceinline__ void utf8_cmp_lit(const Program& P, const Insn in, const RowCtx& rc, uint64_t (&out)[R], uint32_t& ok_out) {
+    const DCol& c = P.cols[in.a];
+    const uint64_t L = P.lit[in.b & 0xff];
+    const uint8_t* q = P.pool + (uint32_t)(L >> 32);
+    const int qn = (int)(uint32_t)L;
+    const uint32_t mask = in.b >> 8;
+    const uint32_t ok = load_valid(c, rc);
+    const uint8_t* bytes = reinterpret_cast<const uint8_t*>(c.data);
 #pragma unroll
-                for (int r = 0; r < R; r++) st.v[SP][r] = x;
-                st.ok[SP] = rc.inr;
-            }
-            break;
-        case OP_PUSH_NULL:
-            if constexpr (SP < D) {
-#pragma unroll
-                for (int r = 0; r < R; r++) st.v[SP][r] = 0;
-                st.ok[SP] = 0;
-            }
-            break;
-        case OP_PUSH_VALID:        // COUNT(col) of any type only needs the validity bit
-            if constexpr (SP < D) {
-#pragma unroll
-                for (int r = 0; r < R; r++) st.v[SP][r] = 1;
-                st.ok[SP] = load_valid(P.cols[in.arg], rc);
-            }
-            break;
-        case OP_PICK:
-            if constexpr (SP < D && SP >= 1) {
-                // copy slot (T - arg) to the top; arg is small, resolved by a uniform switch
-                switch (in.arg) {
-#define KQ_PICK(k) case k: if constexpr (T - k >= 0) { _Pragma("unroll") for (int r = 0; r < R; r++) st.v[SP][r] = st.v[T - k][r]; st.ok[SP] = st.ok[T - k]; } break;
-                    KQ_PICK(0) KQ_PICK(1) KQ_PICK(2) KQ_PICK(3) KQ_PICK(4)
-#undef KQ_PICK
-                }
-            }
-            break;
-#define KQ_BIN(opname, expr)                                              \
-        case opname:                                                      \
-            if constexpr (SP >= 2) {                                      \
-                _Pragma("unroll") for (int r = 0; r < R; r++) {           \
-                    uint64_t a = st.v[U][r], b = st.v[T][r]; (void)a; (void)b; \
-                    st.v[U][r] = (expr);                                  \
-                }                                                         \
-                st.ok[U] &= st.ok[T];                                     \
-            }                                                             \
-            break;
-        KQ_BIN(OP_ADD_I64, a + b)
-        KQ_BIN(OP_SUB_I64, a - b)
-        KQ_BIN(OP_MUL_I64, a * b)
-        // separately rounded IEEE operations: never contracted into FMA (rule E4)
-        KQ_BIN(OP_ADD_F64, (uint64_t)__double_as_longlong(__dadd_rn(__longlong_as_double((long long)a), __longlong_as_double((long long)b))))
-        KQ_BIN(OP_SUB_F64, (uint64_t)__double_as_longlong(__dsub_rn(__longlong_as_double((long long)a), __longlong_as_double((long long)b))))
-        KQ_BIN(OP_MUL_F64, (uint64_t)__double_as_longlong(__dmul_rn(__longlong_as_double((long long)a), __longlong_as_double((long long)b))))
-        KQ_BIN(OP_DIV_F64, (uint64_t)__double_as_longlong(__ddiv_rn(__longlong_as_double((long long)a), __longlong_as_double((long long)b))))
-#undef KQ_BIN
-        case OP_DIV_I64:
-            if constexpr (SP >= 2) {
-                uint32_t both = st.ok[U] & st.ok[T];
-#pragma unroll
-                for (int r = 0; r < R; r++) {
-                    long long a = (long long)st.v[U][r], b = (long long)st.v[T][r];
-                    long long q = 0;
-                    if (b == 0) {
-                        if ((both & rc.active) >> r & 1u) atomicOr(rc.err, 1u);   // KQ_DEV_ERR_DIV0 (rule E4)
-                    } else if (b == -1) q = (long long)(0ULL - (unsigned long long)a);   // JVM ldiv wraps
-                    else q = a / b;
-                    st.v[U][r] = (uint64_t)q;
-                }
-                st.ok[U] = both;
-            }
-            break;
-        case OP_CMP_I64:
-            if constexpr (SP >= 2) {
-#pragma unroll
-                for (int r = 0; r < R; r++) {
-                    long long a = (long long)st.v[U][r], b = (long long)st.v[T][r];
-                    int code = a < b ? 0 : (a == b ? 1 : 2);
-                    st.v[U][r] = (in.arg >> code) & 1u;
-                }
-                st.ok[U] &= st.ok[T];
-            }
-            break;
-        case OP_CMP_F64:
-            if constexpr (SP >= 2) {
-#pragma unroll
-                for (int r = 0; r < R; r++) {
-                    double a = __longlong_as_double((long long)st.v[U][r]), b = __longlong_as_double((long long)st.v[T][r]);
-                    int code = a < b ? 0 : (a == b ? 1 : (a > b ? 2 : 3));
-                    st.v[U][r] = (in.arg >> code) & 1u;
-                }
-                st.ok[U] &= st.ok[T];
-            }
-            break;
-        case OP_AND:               // SQL three-valued logic (rule E3)
-            if constexpr (SP >= 2) {
-                uint32_t at = 0, bt = 0;
-#pragma unroll
-                for (int r = 0; r < R; r++) { at |= (uint32_t)(st.v[U][r] & 1u) << r; bt |= (uint32_t)(st.v[T][r] & 1u) << r; }
-                uint32_t oa = st.ok[U], ob = st.ok[T];
-                uint32_t f = (oa & ~at) | (ob & ~bt), t = (oa & at) & (ob & bt);
-#pragma unroll
-                for (int r = 0; r < R; r++) st.v[U][r] = (t >> r) & 1u;
-                st.ok[U] = (t | f) & rc.inr;
-            }
-            break;
-        case OP_OR:
-            if constexpr (SP >= 2) {
-                uint32_t at = 0, bt = 0;
-#pragma unroll
-                for (int r = 0; r < R; r++) { at |= (uint32_t)(st.v[U][r] & 1u) << r; bt |= (uint32_t)(st.v[T][r] & 1u) << r; }
-                uint32_t oa = st.ok[U], ob = st.ok[T];
-                uint32_t t = (oa & at) | (ob & bt), f = (oa & ~at) & (ob & ~bt);
-#pragma unroll
-                for (int r = 0; r < R; r++) st.v[U][r] = (t >> r) & 1u;
-                st.ok[U] = (t | f) & rc.inr;
-            }
-            break;
-        case OP_UTF8_CMP_LIT:
-            if constexpr (SP < D) {
-                const DCol& c = P.cols[in.arg & 31];
-                uint64_t L = P.lit[(in.arg >> 5) & 31];
-                const uint8_t* q = P.pool + (uint32_t)(L >> 32);
-                int qn = (int)(uint32_t)L;
-                uint32_t mask = in.arg >> 10;
-                uint32_t ok = load_valid(c, rc);
-                const uint8_t* bytes = reinterpret_cast<const uint8_t*>(c.data);
-#pragma unroll
-                for (int r = 0; r < R; r++) {
-                    uint64_t res = 0;
-                    if ((ok >> r) & 1u) {
-                        int64_t row = rc.row0(r >> 1) + (r & 1);
-                        int a = __ldg(c.offsets + row), b = __ldg(c.offsets + row + 1);
-                        int code;
-                        if ((mask == CM_EQ || mask == CM_NE) && (b - a) != qn) code = 2;
-                        else code = utf8_cmp3(bytes + a, b - a, q, qn);
-                        res = (mask >> code) & 1u;
-                    }
-                    st.v[SP][r] = res;
-                }
-                st.ok[SP] = ok;
-            }
-            break;
-        case OP_UTF8_CMP_COL:
-            if constexpr (SP < D) {
-                const DCol& c = P.cols[in.arg & 31];
-                const DCol& d = P.cols[(in.arg >> 5) & 31];
-                uint32_t mask = in.arg >> 10;
-                uint32_t ok = load_valid(c, rc) & load_valid(d, rc);
-#pragma unroll
-                for (int r = 0; r < R; r++) {
-                    uint64_t res = 0;
-                    if ((ok >> r) & 1u) {
-                        int64_t row = rc.row0(r >> 1) + (r & 1);
-                        int a = __ldg(c.offsets + row), b = __ldg(c.offsets + row + 1);
-                        int a2 = __ldg(d.offsets + row), b2 = __ldg(d.offsets + row + 1);
-                        int code = utf8_cmp3(reinterpret_cast<const uint8_t*>(c.data) + a, b - a,
-                                             reinterpret_cast<const uint8_t*>(d.data) + a2, b2 - a2);
-                        res = (mask >> code) & 1u;
-                    }
-                    st.v[SP][r] = res;
-                }
-                st.ok[SP] = ok;
-            }
-            break;
-        case OP_UTF8_PACK:
-            if constexpr (SP < D) {
-                const DCol& c = P.cols[in.arg];
-                uint32_t ok = load_valid(c, rc);
-                const uint8_t* bytes = reinterpret_cast<const uint8_t*>(c.data);
-#pragma unroll
-                for (int r = 0; r < R; r++) {
-                    uint64_t key = 0;
-                    if ((ok >> r) & 1u) {
-                        int64_t row = rc.row0(r >> 1) + (r & 1);
-                        int a = __ldg(c.offsets + row), b = __ldg(c.offsets + row + 1);
-                        int len = b - a;
-                        if (len > 7) { if ((rc.active >> r) & 1u) atomicOr(rc.err, 2u); len = 7; }   // KQ_DEV_ERR_LONG_KEY
-                        for (int i = 0; i < len; i++) key |= (uint64_t)__ldg(bytes + a + i) << (8 * i);
-                        key |= (uint64_t)len << 56;
-                    }
-                    st.v[SP][r] = key;
-                }
-                st.ok[SP] = ok;
-            }
-            break;
-        case OP_UTF8_TO_F64:
-            if constexpr (SP < D) {
-                const DCol& c = P.cols[in.arg];
-                uint32_t ok = load_valid(c, rc);
-                const uint8_t* bytes = reinterpret_cast<const uint8_t*>(c.data);
-#pragma unroll
-                for (int r = 0; r < R; r++) {
-                    double v = 0.0;
-                    if ((ok >> r) & 1u) {
-                        int64_t row = rc.row0(r >> 1) + (r & 1);
-                        int a = __ldg(c.offsets + row), b = __ldg(c.offsets + row + 1);
-                        int pe = parse_f64(bytes + a, b - a, v);
-                        if (pe && ((rc.active >> r) & 1u)) atomicOr(rc.err, pe == 1 ? 4u : 8u);   // NumberFormatException / unsupported range
-                    }
-                    st.v[SP][r] = (uint64_t)__double_as_longlong(v);
-                }
-                st.ok[SP] = ok;
-            }
-            break;
-        case OP_I64_TO_F64:
-            if constexpr (SP >= 1) {
-#pragma unroll
-                for (int r = 0; r < R; r++) st.v[T][r] = (uint64_t)__double_as_longlong((double)(long long)st.v[T][r]);
-            }
-            break;
-        case OP_SET_SEL: if constexpr (SP >= 1) sink.set_sel(st.v[T], st.ok[T], rc); break;
-        case OP_EMIT: if constexpr (SP >= 1) sink.emit(in.arg, st.v[T], st.ok[T], rc); break;
-        case OP_SET_KEY: if constexpr (SP >= 1) sink.set_key(in.arg, st.v[T], st.ok[T], rc); break;
-        case OP_SET_IN: if constexpr (SP >= 1) sink.set_in(in.arg, st.v[T], st.ok[T], rc); break;
-        default: break;
+    for (int r = 0; r < R; r++) {
+        uint64_t res = 0;
+        if ((ok >> r) & 1u) { int a, b; utf8_bounds(c, rc, r, a, b); res = utf8_cmp_row(bytes + a, b - a, q, qn, mask); }
+        out[r] = res;
     }
+    ok_out = ok;
+}
+__device__ __forceinline__ void utf8_cmp_col(const Program& P, const Insn in, const RowCtx& rc, uint64_t (&out)[R], uint32_t& ok_out) {
+    const DCol& c = P.cols[in.a];
+    const DCol& d = P.cols[in.b & 0xff];
+    const uint32_t mask = in.b >> 8;
+    const uint32_t ok = load_valid(c, rc) & load_valid(d, rc);
+#pragma unroll
+    for (int r = 0; r < R; r++) {
+        uint64_t res = 0;
+        if ((ok >> r) & 1u) {
+            int a, b, a2, b2; utf8_bounds(c, rc, r, a, b); utf8_bounds(d, rc, r, a2, b2);
+            res = utf8_cmp_row(reinterpret_cast<const uint8_t*>(c.data) + a, b - a, reinterpret_cast<const uint8_t*>(d.data) + a2, b2 - a2, mask);
+        }
+        out[r] = res;
+    }
+    ok_out = ok;
+}
+__device__ __forceinline__ void utf8_pack(const DCol& c, const RowCtx& rc, uint64_t (&out)[R], uint32_t& ok_out) {
+    const uint32_t ok = load_valid(c, rc);
+    const uint8_t* bytes = reinterpret_cast<const uint8_t*>(c.data);
+#pragma unroll
+    for (int r = 0; r < R; r++) {
+        uint64_t key = 0;
+        if ((ok >> r) & 1u) {
+            int a, b; utf8_bounds(c, rc, r, a, b);
+            int len = b - a;
+            if (len > 7) { if ((rc.active >> r) & 1u) atomicOr(rc.err, 2u); len = 7; }   // KQ_DEV_ERR_LONG_KEY
+            key = utf8_pack_row(bytes + a, len);
+        }
+        out[r] = key;
+    }
+    ok_out = ok;
+}
+__device__ __forceinline__ void utf8_to_f64(const Program& P, const Insn in, const RowCtx& rc, uint64_t (&out)[R], uint32_t& ok_out) {
+    const DCol& c = P.cols[in.a];
+    const uint32_t ok = load_valid(c, rc);
+    const uint8_t* bytes = reinterpret_cast<const uint8_t*>(c.data);
+#pragma unroll
+    for (int r = 0; r < R; r++) {
+        double v = 0.0;
+        if ((ok >> r) & 1u) { int a, b; utf8_bounds(c, rc, r, a, b); v = parse_f64_row(bytes + a, b - a, rc.err, (rc.active >> r) & 1u); }
+        out[r] = (uint64_t)__double_as_longlong(v);
+    }
+    ok_out = ok;
 }
 
-// Run instructions [pc, pc_end). in.sp is the stack pointer BEFORE the instruction.
+__device__ __forceinline__ double as_f64(uint64_t x) { return __longlong_as_double((long long)x); }
+__device__ __forceinline__ uint64_t as_u64(double x) { return (uint64_t)__double_as_longlong(x); }
+
+// Run instructions [pc, pc_end).
 template <class Sink>
-__device__ __forceinline__ void run(const Program& P, int pc, int pc_end, Stack& st, RowCtx& rc, Sink& sink) {
+__device__ __forceinline__ void run(const Program& P, int pc, int pc_end, Vm& vm, RowCtx& rc, Sink& sink) {
 #pragma unroll 1
     for (; pc < pc_end; ++pc) {
         const Insn in = P.insn[pc];
-        switch (in.sp) {
-            case 0: step<0>(P, in, st, rc, sink); break;
-            case 1: step<1>(P, in, st, rc, sink); break;
-            case 2: step<2>(P, in, st, rc, sink); break;
-            case 3: step<3>(P, in, st, rc, sink); break;
-            case 4: step<4>(P, in, st, rc, sink); break;
-            case 5: step<5>(P, in, st, rc, sink); break;
-            case 6: step<6>(P, in, st, rc, sink); break;
+        // ---- 1. operand fetch -> TMP
+        switch (in.src) {
+            case S_COL64: load64(P.cols[in.a], rc, vm.tmp, vm.tok); break;
+            case S_COL32: load32(P.cols[in.a], rc, vm.tmp, vm.tok); break;
+            case S_COLBIT: loadbit(P.cols[in.a], rc, vm.tmp, vm.tok); break;
+            case S_LIT: {
+                uint64_t x = P.lit[in.a];
+#pragma unroll
+                for (int r = 0; r < R; r++) vm.tmp[r] = x;
+                vm.tok = rc.inr;
+                break;
+            }
+            case S_NULL:
+#pragma unroll
+                for (int r = 0; r < R; r++) vm.tmp[r] = 0;
+                vm.tok = 0;
+                break;
+            case S_VALID:              // COUNT(col) of any type only needs the validity bit
+#pragma unroll
+                for (int r = 0; r < R; r++) vm.tmp[r] = 1;
+                vm.tok = load_valid(P.cols[in.a], rc);
+                break;
+            case S_STACK:
+                switch (in.a) {
+#define KQ_POP(d, S, K) case d: _Pragma("unroll") for (int r = 0; r < R; r++) vm.tmp[r] = vm.S[r]; vm.tok = vm.K; break;
+                    KQ_POP(0, s0, k0) KQ_POP(1, s1, k1) KQ_POP(2, s2, k2)
+#undef KQ_POP
+                    default: break;
+                }
+                break;
+            case S_UTF8_CMP_LIT: utf8_cmp_lit(P, in, rc, vm.tmp, vm.tok); break;
+            case S_UTF8_CMP_COL: utf8_cmp_col(P, in, rc, vm.tmp, vm.tok); break;
+            case S_UTF8_PACK: utf8_pack(P.cols[in.a], rc, vm.tmp, vm.tok); break;
+            case S_UTF8_F64: utf8_to_f64(P, in, rc, vm.tmp, vm.tok); break;
             default: break;
         }
+        // ---- 2. operation
+#define KQ_BIN(opname, expr)                                              \
+        case opname:                                                      \
+            _Pragma("unroll") for (int r = 0; r < R; r++) {               \
+                const uint64_t a = vm.acc[r], b = vm.tmp[r]; (void)a; (void)b; \
+                vm.acc[r] = (expr);                                       \
+            }                                                             \
+            vm.aok &= vm.tok;                                             \
+            break;
+        switch (in.op) {
+            case O_LOAD:
+#pragma unroll
+                for (int r = 0; r < R; r++) vm.acc[r] = vm.tmp[r];
+                vm.aok = vm.tok;
+                break;
+            case O_PUSH:
+                switch (in.a) {
+#define KQ_PUSH(d, S, K) case d: _Pragma("unroll") for (int r = 0; r < R; r++) vm.S[r] = vm.acc[r]; vm.K = vm.aok; break;
+                    KQ_PUSH(0, s0, k0) KQ_PUSH(1, s1, k1) KQ_PUSH(2, s2, k2)
+#undef KQ_PUSH
+                    default: break;
+                }
+                break;
+            KQ_BIN(O_ADD_I64, a + b)
+            KQ_BIN(O_SUB_I64, a - b)
+            KQ_BIN(O_RSUB_I64, b - a)
+            KQ_BIN(O_MUL_I64, a * b)
+            // separately rounded IEEE operations: never contracted into FMA (rule E4)
+            KQ_BIN(O_ADD_F64, as_u64(__dadd_rn(as_f64(a), as_f64(b))))
+            KQ_BIN(O_SUB_F64, as_u64(__dsub_rn(as_f64(a), as_f64(b))))
+            KQ_BIN(O_RSUB_F64, as_u64(__dsub_rn(as_f64(b), as_f64(a))))
+            KQ_BIN(O_MUL_F64, as_u64(__dmul_rn(as_f64(a), as_f64(b))))
+            KQ_BIN(O_DIV_F64, as_u64(__ddiv_rn(as_f64(a), as_f64(b))))
+            KQ_BIN(O_RDIV_F64, as_u64(__ddiv_rn(as_f64(b), as_f64(a))))
+            case O_DIV_I64:
+            case O_RDIV_I64: {
+                const uint32_t both = vm.aok & vm.tok;
+                const bool rev = in.op == O_RDIV_I64;
+#pragma unroll
+                for (int r = 0; r < R; r++) {
+                    long long a = (long long)(rev ? vm.tmp[r] : vm.acc[r]), b = (long long)(rev ? vm.acc[r] : vm.tmp[r]);
+                    long long q = 0;
+                    if (b == 0) {
+                        if ((both & rc.active) >> r & 1u) atomicOr(rc.err, 1u);           // KQ_DEV_ERR_DIV0 (rule E4)
+                    } else if (b == -1) q = (long long)(0ULL - (unsigned long long)a);    // JVM ldiv wraps
+                    else q = a / b;
+                    vm.acc[r] = (uint64_t)q;
+                }
+                vm.aok = both;
+                break;
+            }
+            case O_CMP_I64:
+#pragma unroll
+                for (int r = 0; r < R; r++) {
+                    long long a = (long long)vm.acc[r], b = (long long)vm.tmp[r];
+                    int code = a < b ? 0 : (a == b ? 1 : 2);
+                    vm.acc[r] = (in.b >> code) & 1u;
+                }
+                vm.aok &= vm.tok;
+                break;
+            case O_CMP_F64:
+#pragma unroll
+                for (int r = 0; r < R; r++) {
+                    double a = as_f64(vm.acc[r]), b = as_f64(vm.tmp[r]);
+                    int code = a < b ? 0 : (a == b ? 1 : (a > b ? 2 : 3));
+                    vm.acc[r] = (in.b >> code) & 1u;
+                }
+                vm.aok &= vm.tok;
+                break;
+            case O_AND:                // SQL three-valued logic (rule E3)
+            case O_OR: {
+                uint32_t at = 0, bt = 0;
+#pragma unroll
+                for (int r = 0; r < R; r++) { at |= (uint32_t)(vm.acc[r] & 1u) << r; bt |= (uint32_t)(vm.tmp[r] & 1u) << r; }
+                const uint32_t oa = vm.aok, ob = vm.tok;
+                uint32_t t, f;
+                if (in.op == O_AND) { f = (oa & ~at) | (ob & ~bt); t = (oa & at) & (ob & bt); }
+                else { t = (oa & at) | (ob & bt); f = (oa & ~at) & (ob & ~bt); }
+#pragma unroll
+                for (int r = 0; r < R; r++) vm.acc[r] = (t >> r) & 1u;
+                vm.aok = (t | f) & rc.inr;
+                break;
+            }
+            case O_I64_TO_F64:
+#pragma unroll
+                for (int r = 0; r < R; r++) vm.acc[r] = as_u64((double)(long long)vm.acc[r]);
+                break;
+            case O_SET_SEL: sink.set_sel(vm.acc, vm.aok, rc); break;
+            case O_EMIT: sink.emit(in.a, vm.acc, vm.aok, rc); break;
+            case O_SET_KEY: sink.set_key(in.a, vm.acc, vm.aok, rc); break;
+            case O_SET_IN: sink.set_in(in.a, vm.acc, vm.aok, rc); break;
+            default: break;
+        }
+#undef KQ_BIN
     }
 }
 
-__device__ __forceinline__ void rowctx_init(RowCtx& rc, int64_t tile, int64_t n, uint32_t* err) {
+__device__ __forceinline__ void rowctx_init(RowCtx& rc, int64_t tile, int tile_rows, int64_t n, uint32_t* err, const unsigned char* stage) {
     int warp = threadIdx.x >> 5;
     rc.lane = threadIdx.x & 31;
     rc.n = n;
-    int64_t tile_base = tile * TILE;
+    rc.stage = stage;
+    rc.wrow = warp * WARP_ROWS;
+    int64_t tile_base = tile * tile_rows;
     rc.warp_base = tile_base + (int64_t)warp * WARP_ROWS;
-    rc.full = tile_base + TILE <= n;
+    rc.full = tile_base + tile_rows <= n;
     uint32_t m = 0;
 #pragma unroll
     for (int j = 0; j < NCHUNK; j++) {
