@@ -133,7 +133,9 @@ bool KqCompiler::leaf_src(const kq_expr* e, int* src, int* a) {
     if (e->kind == KQ_EX_LIT && e->type != KQ_UTF8) {
         if (e->is_null) { *src = S_NULL; *a = 0; return true; }
         uint64_t bits;
-        if (e->type == KQ_F64) memcpy(&bits, &e->f, 8); else bits = (uint64_t)e->i;
+        if (e->type == KQ_F64) memcpy(&bits, &e->f, 8);
+        else if (e->type == KQ_BOOL) bits = e->i ? 0xFFFFFFFFULL : 0ULL;     // Bool values are truth masks (kq_vm.cuh)
+        else bits = (uint64_t)e->i;
         int idx;
         if (add_lit(bits, &idx) != KQ_OK) return false;
         *src = S_LIT; *a = idx;
@@ -191,7 +193,7 @@ int KqCompiler::value(const kq_expr* e, int* type, bool* nullable) {
                 if ((a->kind == KQ_EX_LIT && a->is_null) || (b->kind == KQ_EX_LIT && b->is_null)) return emit(O_LOAD, S_NULL, 0);
                 if (a->kind == KQ_EX_LIT && b->kind == KQ_EX_LIT) {
                     int c = a->s.compare(b->s); int code = c < 0 ? 0 : (c == 0 ? 1 : 2);
-                    int idx; KQ_RET(add_lit((m >> code) & 1u, &idx));
+                    int idx; KQ_RET(add_lit(((m >> code) & 1u) ? 0xFFFFFFFFULL : 0ULL, &idx));
                     return emit(O_LOAD, S_LIT, idx);
                 }
                 if (a->kind == KQ_EX_LIT) { std::swap(a, b); m = mirror_mask(m); }
@@ -210,21 +212,42 @@ int KqCompiler::value(const kq_expr* e, int* type, bool* nullable) {
             if (is_cmp && lt == KQ_I32) return kq_fail(ctx, KQ_ERR_ILLEGAL_STATE, "compare on I32");
             if (!is_cmp && !is_logic && lt != KQ_I64 && lt != KQ_F64) return kq_fail(ctx, KQ_ERR_ILLEGAL_STATE, "math needs Int64 or Float64 operands");
             *type = (is_cmp || is_logic) ? KQ_BOOL : lt;
-            // forward form: ACC = ACC op TMP; reverse form: ACC = TMP op ACC
-            int fwd, rev; uint32_t bf = 0, br = 0;
-            const bool f64 = lt == KQ_F64;
-            if (is_cmp) { fwd = rev = f64 ? O_CMP_F64 : O_CMP_I64; bf = cmp_mask(op); br = mirror_mask(bf); }
-            else if (is_logic) fwd = rev = op == KQ_AND ? O_AND : O_OR;
-            else switch (op) {
-                case KQ_ADD: fwd = rev = f64 ? O_ADD_F64 : O_ADD_I64; break;
-                case KQ_MUL: fwd = rev = f64 ? O_MUL_F64 : O_MUL_I64; break;
-                case KQ_SUB: fwd = f64 ? O_SUB_F64 : O_SUB_I64; rev = f64 ? O_RSUB_F64 : O_RSUB_I64; break;
-                default: fwd = f64 ? O_DIV_F64 : O_DIV_I64; rev = f64 ? O_RDIV_F64 : O_RDIV_I64; break;
+            int t; bool n;
+            if (lt == KQ_BOOL) {
+                // Bool operands are truth masks: ACC op operand, operand = Bool column / literal / save slot
+                const int bop = is_logic ? (op == KQ_AND ? O_AND : O_OR) : O_CMP_BOOL;
+                const uint32_t m = is_cmp ? cmp_mask(op) : 0, mr = is_cmp ? mirror_mask(m) : 0;
+                int src, a;
+                if (is_plain_leaf(e->r) && leaf_src(e->r, &src, &a)) { KQ_RET(value(e->l, &t, &n)); return emit(bop, src, a, m << 8); }
+                if (is_plain_leaf(e->l) && leaf_src(e->l, &src, &a)) { KQ_RET(value(e->r, &t, &n)); return emit(bop, src, a, mr << 8); }
+                if (sp >= DS) return kq_fail(ctx, KQ_ERR_UNSUPPORTED, "expression too deep (more than %d nested non-leaf operand pairs)", DS);
+                KQ_RET(value(e->l, &t, &n));
+                KQ_RET(emit(O_PUSH, S_NONE, sp));
+                sp++;
+                int st = value(e->r, &t, &n);
+                sp--;
+                KQ_RET(st);
+                return emit(bop, S_STACK, sp, mr << 8);       // ACC holds the right operand
             }
-            int t; bool n; int src, a;
-            // Utf8 comparisons and casts are "loads" too, but they need ACC: treat only plain leaves as operands
-            if (is_plain_leaf(e->r) && leaf_src(e->r, &src, &a)) { KQ_RET(value(e->l, &t, &n)); return emit(fwd, src, a, bf); }
-            if (is_plain_leaf(e->l) && leaf_src(e->l, &src, &a)) { KQ_RET(value(e->r, &t, &n)); return emit(rev, src, a, br); }
+            // 64-bit primitives, specialised per operand mode: ACC = X op Y in source order
+            const bool f64 = lt == KQ_F64;
+            int bin;
+            if (is_cmp) bin = f64 ? B_CMP_F64 : B_CMP_I64;
+            else bin = (f64 ? B_ADD_F64 : B_ADD_I64) + (op - KQ_ADD);
+            const uint32_t mb = is_cmp ? (cmp_mask(op) << 8) : 0;
+            auto prim = [&](int mode, int a, uint32_t b2) { return emit(O_BIN + bin * NMODES + mode, S_NONE, a, b2 | mb); };
+            int sl = 0, al = 0, sr = 0, ar = 0;
+            const bool ll = is_leaf64(e->l) && leaf_src(e->l, &sl, &al);
+            const bool rl = is_leaf64(e->r) && leaf_src(e->r, &sr, &ar);
+            if (ll && rl) {
+                if (sl == S_COL64 && sr == S_COL64) return prim(M_COL_COL, al, (uint32_t)ar);
+                if (sl == S_COL64) return prim(M_COL_LIT, al, (uint32_t)ar);
+                if (sr == S_COL64) return prim(M_LIT_COL, al, (uint32_t)ar);
+                KQ_RET(emit(O_LOAD, S_LIT, al));
+                return prim(M_ACC_LIT, ar, 0);
+            }
+            if (rl) { KQ_RET(value(e->l, &t, &n)); return prim(sr == S_COL64 ? M_ACC_COL : M_ACC_LIT, ar, 0); }
+            if (ll) { KQ_RET(value(e->r, &t, &n)); return prim(sl == S_COL64 ? M_COL_ACC : M_LIT_ACC, al, 0); }
             if (sp >= DS) return kq_fail(ctx, KQ_ERR_UNSUPPORTED, "expression too deep (more than %d nested non-leaf operand pairs)", DS);
             KQ_RET(value(e->l, &t, &n));
             KQ_RET(emit(O_PUSH, S_NONE, sp));
@@ -232,10 +255,18 @@ int KqCompiler::value(const kq_expr* e, int* type, bool* nullable) {
             int st = value(e->r, &t, &n);
             sp--;
             KQ_RET(st);
-            return emit(rev, S_STACK, sp, br);
+            return prim(M_STK_ACC, sp, 0);
         }
     }
     return kq_fail(ctx, KQ_ERR_ILLEGAL_STATE, "Unknown expr");
+}
+
+// a leaf the 64-bit primitives can read directly: a Float64/Int64 column or a non-null 64-bit literal
+bool KqCompiler::is_leaf64(const kq_expr* e) {
+    if (e->kind == KQ_EX_LIT) return !e->is_null && e->type != KQ_UTF8 && e->type != KQ_BOOL;
+    if (e->kind != KQ_EX_COL || e->col < 0 || e->col >= (int)batch->cols.size()) return false;
+    int t = batch->cols[(size_t)e->col]->type;
+    return t == KQ_F64 || t == KQ_I64;
 }
 
 bool KqCompiler::is_plain_leaf(const kq_expr* e) {
@@ -267,7 +298,7 @@ int KqCompiler::key_value(const kq_expr* e, int* type, bool* nullable) {
 }
 
 // Hand ACC to a sink (O_SET_SEL / O_EMIT / O_SET_KEY / O_SET_IN); ACC stays valid.
-int KqCompiler::sink(int op, int arg) { return emit(op, S_NONE, arg); }
+int KqCompiler::sink(int op, int arg, int type) { return emit(op, S_NONE, arg, type == KQ_BOOL ? 1u : 0u); }
 
 void KqCompiler::plan_stages(int budget, int min_stages, int tile_rows, StagePlan* sp) {
     const int TILE = tile_rows;

@@ -26,7 +26,7 @@ struct KqCompiler {
     // canonicalised by the aggregate kernel).
     int key_value(const kq_expr* e, int* type, bool* nullable);
     // Hand the accumulator to a sink (O_SET_SEL / O_EMIT / O_SET_KEY / O_SET_IN).
-    int sink(int op, int arg);
+    int sink(int op, int arg, int type = 0);   // type KQ_BOOL: ACC holds a truth mask
     int pc() const { return prog.ninsn; }
     // Decide which column buffers are staged through the shared-memory tile pipeline (kq_pipe.cuh):
     // fills prog.cols[].s_* and the plan. `budget` = bytes of shared memory available for stages,
@@ -39,6 +39,7 @@ struct KqCompiler {
     int emit(int op, int src, int a, uint32_t b = 0);
     bool leaf_src(const kq_expr* e, int* src, int* a);
     bool is_plain_leaf(const kq_expr* e);
+    bool is_leaf64(const kq_expr* e);
     int use_col(int batch_col, int* slot);
     int add_lit(uint64_t v, int* idx);
     int add_utf8_lit(const std::string& s, int* idx);

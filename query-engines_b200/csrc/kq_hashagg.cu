@@ -150,27 +150,24 @@ struct AggSink : SinkBase {
     uint64_t in[MAX_INPUTS][R];
     uint32_t inok[MAX_INPUTS];
     __device__ __forceinline__ void set_sel(const uint64_t (&v)[R], uint32_t ok, RowCtx& rc) {
-        uint32_t m = 0;
-#pragma unroll
-        for (int r = 0; r < R; r++) m |= (uint32_t)(v[r] & 1u) << r;
-        sel = m & ok & rc.inr;
+        sel = (uint32_t)v[0] & ok & rc.inr;        // Bool truth mask; TRUE only (null predicate drops the row, rule E3)
         rc.active = sel;
     }
-    __device__ __forceinline__ void set_key(int k, const uint64_t (&v)[R], uint32_t ok, RowCtx&) {
+    __device__ __forceinline__ void set_key(int k, bool is_bool, const uint64_t (&v)[R], uint32_t ok, RowCtx&) {
 #pragma unroll
         for (int kk = 0; kk < MAX_KEYS; kk++)
             if (kk == k) {
 #pragma unroll
-                for (int r = 0; r < R; r++) key[kk][r] = v[r];
+                for (int r = 0; r < R; r++) key[kk][r] = is_bool ? ((v[0] >> r) & 1u) : v[r];
                 keyok[kk] = ok;
             }
     }
-    __device__ __forceinline__ void set_in(int i, const uint64_t (&v)[R], uint32_t ok, RowCtx&) {
+    __device__ __forceinline__ void set_in(int i, bool is_bool, const uint64_t (&v)[R], uint32_t ok, RowCtx&) {
 #pragma unroll
         for (int ii = 0; ii < MAX_INPUTS; ii++)
             if (ii == i) {
 #pragma unroll
-                for (int r = 0; r < R; r++) in[ii][r] = v[r];
+                for (int r = 0; r < R; r++) in[ii][r] = is_bool ? ((v[0] >> r) & 1u) : v[r];
                 inok[ii] = ok;
             }
     }
@@ -675,7 +672,7 @@ int kq_hashagg_update(kq_ctx* ctx, kq_hashagg* h, kq_batch* input) {
     for (size_t k = 0; k < h->groups.size(); k++) {
         int t; bool nl;
         KQ_RET(cc.key_value(h->groups[k], &t, &nl));
-        KQ_RET(cc.sink(O_SET_KEY, (int)k));
+        KQ_RET(cc.sink(O_SET_KEY, (int)k, t));
         if (t == KQ_F64) key_f64_mask |= 1u << k;
         kt.push_back(t);
     }
@@ -691,7 +688,7 @@ int kq_hashagg_update(kq_ctx* ctx, kq_hashagg* h, kq_batch* input) {
             int t2; bool n2;
             KQ_RET(cc.value(h->inputs[i], &t2, &n2));
         }
-        KQ_RET(cc.sink(O_SET_IN, (int)i));
+        KQ_RET(cc.sink(O_SET_IN, (int)i, h->input_count_only[i] ? 0 : t));
         it.push_back(t);
     }
     if (!h->typed) { h->key_types = kt; h->input_types = it; h->typed = true; }

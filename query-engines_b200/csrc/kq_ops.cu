@@ -10,6 +10,7 @@
 #include <algorithm>
 #include <cstring>
 
+#define KQ_R 4      // rows per thread in the streaming kernels
 #include "kq_compile.h"
 #include "kq_pipe.cuh"
 #include "kq_scan.cuh"
@@ -39,8 +40,10 @@ struct OpArgs {
     StagePlan sp;
 };
 
-// One CTA per SM: 15 consumer warps evaluate, one service warp streams tiles in with TMA bulk copies
-// (and, in the filter kernel, resolves the cross-block prefix). 512 threads -> 128 registers each.
+// One CTA per SM: 15 consumer warps evaluate 4 rows per thread (thread-level parallelism keeps the
+// issue slots busy while each warp walks its dependent dispatch chain), one service warp streams
+// tiles in with TMA bulk copies (and, in the filter kernel, resolves the cross-block prefix).
+// 512 threads -> 128 registers each; bytes in flight come from the stage ring, not from occupancy.
 constexpr int WARPS = 15;
 constexpr int BLOCK = WARPS * 32;
 constexpr int TILE = WARPS * WARP_ROWS;     // 1920 rows
@@ -50,8 +53,8 @@ constexpr int THREADS = BLOCK + 32;
 struct SinkBase {
     __device__ __forceinline__ void set_sel(const uint64_t (&)[R], uint32_t, RowCtx&) {}
     __device__ __forceinline__ void emit(int, const uint64_t (&)[R], uint32_t, RowCtx&) {}
-    __device__ __forceinline__ void set_key(int, const uint64_t (&)[R], uint32_t, RowCtx&) {}
-    __device__ __forceinline__ void set_in(int, const uint64_t (&)[R], uint32_t, RowCtx&) {}
+    __device__ __forceinline__ void set_key(int, bool, const uint64_t (&)[R], uint32_t, RowCtx&) {}
+    __device__ __forceinline__ void set_in(int, bool, const uint64_t (&)[R], uint32_t, RowCtx&) {}
 };
 
 // write the 64 row bits of chunk j (rows warp_base + 64j ...) of a bit-packed buffer
@@ -70,10 +73,7 @@ struct ProjectSink : SinkBase {
     __device__ __forceinline__ void emit(int k, const uint64_t (&v)[R], uint32_t ok, RowCtx& rc) {
         const DOut o = outs[k];
         if (o.type == KQ_BOOL) {
-            uint32_t m = 0;
-#pragma unroll
-            for (int r = 0; r < R; r++) m |= (uint32_t)(v[r] & 1u) << r;
-            m &= rc.inr;
+            const uint32_t m = (uint32_t)v[0] & rc.inr;      // Bool values are truth masks
 #pragma unroll
             for (int j = 0; j < NCHUNK; j++) store_chunk_bits(reinterpret_cast<uint32_t*>(o.data), rc, j, m);
         } else if (o.type == KQ_DATE32 || o.type == KQ_I32) {
@@ -104,10 +104,7 @@ struct CompactSink : SinkBase {
     int rank[R];
     long long base;
     __device__ __forceinline__ void set_sel(const uint64_t (&v)[R], uint32_t ok, RowCtx& rc) {
-        uint32_t m = 0;
-#pragma unroll
-        for (int r = 0; r < R; r++) m |= (uint32_t)(v[r] & 1u) << r;
-        sel = m & ok & rc.inr;        // TRUE only: null predicate drops the row (rule E3)
+        sel = (uint32_t)v[0] & ok & rc.inr;        // truth mask; TRUE only: a null predicate drops the row (rule E3)
     }
     __device__ __forceinline__ void emit(int k, const uint64_t (&v)[R], uint32_t ok, RowCtx&) {
         const DOut o = outs[k];
@@ -116,7 +113,7 @@ struct CompactSink : SinkBase {
             if ((sel >> r) & 1u) {
                 long long pos = base + rank[r];
                 if (o.type == KQ_BOOL) {
-                    if (v[r] & 1u) atomicOr(reinterpret_cast<uint32_t*>(o.data) + (pos >> 5), 1u << (pos & 31));
+                    if ((v[0] >> r) & 1u) atomicOr(reinterpret_cast<uint32_t*>(o.data) + (pos >> 5), 1u << (pos & 31));
                 } else if (o.type == KQ_DATE32 || o.type == KQ_I32) {
                     reinterpret_cast<uint32_t*>(o.data)[pos] = (uint32_t)v[r];
                 } else {
@@ -178,63 +175,80 @@ __global__ void __launch_bounds__(THREADS, 1) k_filter_project(const __grid_cons
     __shared__ long long tile_of[MAX_STAGES];
     __shared__ unsigned long long prefix[MAX_STAGES];
     __shared__ int wtot[MAX_STAGES][WARPS];
+    __shared__ int tot[MAX_STAGES], arrived[MAX_STAGES];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int S = A.sp.nstages;
     if (threadIdx.x == 0) {
         for (int s = 0; s < S; s++) {
             mbar_init(&full[s], 1); mbar_init(&empty[s], WARPS);
-            mbar_init(&agg_ready[s], WARPS); mbar_init(&prefix_ready[s], 1);
+            mbar_init(&agg_ready[s], 1); mbar_init(&prefix_ready[s], 1);
+            tot[s] = 0; arrived[s] = 0;
         }
         mbar_fence_init();
     }
     __syncthreads();
 
     if (warp == SERVICE_WARP) {
-        int kp = 0, kl = 0;                    // next tile slot to produce / to look back
+        int kp = 0, kl = 0;                    // next tile slot to produce / to resolve
         bool prod_done = false, lb_done = false;
+        // the next ticket is always requested one step early: the L2 round trip of the atomic overlaps
+        // the TMA issue and the look-back of the current step (ticket order = look-back order)
+        long long next_ticket = 0;
+        if (lane == 0) next_ticket = (long long)atomicAdd(A.ticket, 1u);
         while (!prod_done || !lb_done) {
             bool did = false;
+            // (1) start the descriptor loads of the tile waiting for its prefix
+            bool lb_pending = false; long long lb_tile = 0; int lb_s = 0;
+            unsigned long long d[4] = {0, 0, 0, 0};
+            if (!lb_done) {
+                lb_s = kl % S;
+                int go = 0;
+                if (lane == 0) go = mbar_test(&agg_ready[lb_s], (kl / S) & 1) ? 1 : 0;
+                go = __shfl_sync(0xffffffffu, go, 0);
+                if (go) {
+                    lb_tile = tile_of[lb_s];
+                    if (lb_tile >= A.ntiles) { lb_done = true; kl++; did = true; }
+                    else { lb_pending = true; lb_load(A.tile_desc, lb_tile - 1, d); }
+                }
+            }
+            // (2) keep the stage ring full
             if (!prod_done) {
                 const int s = kp % S;
                 int go = 0;
-                if (lane == 0) go = mbar_try_wait(&empty[s], ((kp / S) & 1) ^ 1) ? 1 : 0;
+                if (lane == 0) go = mbar_test(&empty[s], ((kp / S) & 1) ^ 1) ? 1 : 0;
                 go = __shfl_sync(0xffffffffu, go, 0);
                 if (go) {
                     int end = 0;
                     if (lane == 0) {
-                        const long long tile = (long long)atomicAdd(A.ticket, 1u);     // ticket order = look-back order
+                        const long long tile = next_ticket;
                         tile_of[s] = tile;
                         if (tile >= A.ntiles) { mbar_arrive(&full[s]); end = 1; }
-                        else stage_issue(A.sp, stages + (size_t)s * A.sp.stage_bytes, &full[s], tile, TILE, A.n);
+                        else {
+                            next_ticket = (long long)atomicAdd(A.ticket, 1u);
+                            stage_issue(A.sp, stages + (size_t)s * A.sp.stage_bytes, &full[s], tile, TILE, A.n);
+                        }
                     }
                     end = __shfl_sync(0xffffffffu, end, 0);
                     if (end) prod_done = true;
                     kp++; did = true;
                 }
             }
-            if (!lb_done) {
-                const int s = kl % S;
-                int go = 0;
-                if (lane == 0) go = mbar_try_wait(&agg_ready[s], (kl / S) & 1) ? 1 : 0;
-                go = __shfl_sync(0xffffffffu, go, 0);
-                if (go) {
-                    const long long tile = tile_of[s];
-                    if (tile >= A.ntiles) lb_done = true;
-                    else {
-                        int t = lane < WARPS ? wtot[s][lane] : 0;
-#pragma unroll
-                        for (int o = 16; o; o >>= 1) t += __shfl_xor_sync(0xffffffffu, t, o);
-                        unsigned long long excl = lookback_exclusive(A.tile_desc, tile, (unsigned long long)t);
-                        if (lane == 0) {
-                            prefix[s] = excl;
-                            if (tile == A.ntiles - 1) *A.out_count = excl + (unsigned long long)t;
-                            mbar_arrive(&prefix_ready[s]);
-                        }
+            // (3) fold the descriptors; publish the inclusive prefix and hand the exclusive one to step B
+            if (lb_pending) {
+                unsigned long long excl = 0;
+                if (lb_finish(A.tile_desc, lb_tile, d, &excl)) {
+                    if (lane == 0) {
+                        const unsigned long long t = (unsigned long long)tot[lb_s];
+                        if (lb_tile > 0) A.tile_desc[lb_tile] = LB_INCL | (excl + t);
+                        prefix[lb_s] = excl;
+                        if (lb_tile == A.ntiles - 1) *A.out_count = excl + t;
+                        tot[lb_s] = 0; arrived[lb_s] = 0;      // consumers are done with them until the stage is reused
+                        mbar_arrive(&prefix_ready[lb_s]);
                     }
                     kl++; did = true;
                 }
             }
-            if (!did) __nanosleep(32);
+            if (!did) __nanosleep(40);
         }
         return;
     }
@@ -243,66 +257,96 @@ __global__ void __launch_bounds__(THREADS, 1) k_filter_project(const __grid_cons
     sink.outs = A.outs;
     Vm st;
     const uint32_t lt = (1u << lane) - 1u;
-    // state of the tile whose step B is pending
-    bool have_prev = false;
-    uint32_t p_sel = 0; int p_rank[R]; long long p_tile = 0; int p_s = 0, p_k = 0;
+    // ranks in row order (chunk, lane, pair element) from a selection mask: ballot + popc
+    auto ranks_of = [&](uint32_t sel, int (&rank)[R]) -> int {
+        int wt = 0;
 #pragma unroll
-    for (int r = 0; r < R; r++) p_rank[r] = 0;
-    for (int k = 0;; k++) {
+        for (int j = 0; j < NCHUNK; j++) {
+            const uint32_t s0 = (sel >> (2 * j)) & 1u, s1 = (sel >> (2 * j + 1)) & 1u;
+            const uint32_t b0 = __ballot_sync(0xffffffffu, s0), b1 = __ballot_sync(0xffffffffu, s1);
+            const int below = __popc(b0 & lt) + __popc(b1 & lt);
+            rank[2 * j] = wt + below;
+            rank[2 * j + 1] = wt + below + (int)s0;
+            wt += __popc(b0) + __popc(b1);
+        }
+        return wt;
+    };
+    // Step A runs up to LOOKAHEAD tiles ahead of step B; a pending tile is remembered by its selection
+    // mask only (ranks are recomputed with ballots), so the look-back latency of tile k hides behind
+    // the predicate work of tiles k+1..k+LOOKAHEAD.
+    constexpr int LOOKAHEAD = 3;
+    uint32_t q_sel[LOOKAHEAD]; long long q_tile[LOOKAHEAD];
+#pragma unroll
+    for (int i = 0; i < LOOKAHEAD; i++) { q_sel[i] = 0; q_tile[i] = -1; }
+    const int D = min(LOOKAHEAD, S - 1);           // tiles in flight between A and B (S >= 2)
+    auto step_b = [&](int kb, uint32_t p_sel, long long p_tile) {
+        const int p_s = kb % S;
+        RowCtx rc;
+        rowctx_init(rc, p_tile, TILE, A.n, A.err, stages + (size_t)p_s * A.sp.stage_bytes);
+        rc.active = p_sel;        // projection errors only count on surviving rows (FilterExec runs first)
+        sink.sel = p_sel;
+        ranks_of(p_sel, sink.rank);
+        mbar_wait(&prefix_ready[p_s], (kb / S) & 1);
+        int woff = 0;
+#pragma unroll
+        for (int w = 0; w < WARPS; w++) { int x = wtot[p_s][w]; if (w < warp) woff += x; }
+        sink.base = (long long)prefix[p_s] + woff;
+        if (A.selvec) {
+#pragma unroll
+            for (int r = 0; r < R; r++)
+                if ((p_sel >> r) & 1u) A.selvec[sink.base + sink.rank[r]] = (int32_t)(rc.row0(r >> 1) + (r & 1));
+        }
+        run(A.prog, A.sel_end, A.prog.ninsn, st, rc, sink);
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&empty[p_s]);
+    };
+    int k = 0;
+    for (;; k++) {
         const int s = k % S;
         mbar_wait(&full[s], (k / S) & 1);
         const long long tile = tile_of[s];
-        const bool last = tile >= A.ntiles;
-        uint32_t c_sel = 0; int c_rank[R];
+        if (tile >= A.ntiles) {
+            if (warp == 0 && lane == 0) mbar_arrive(&agg_ready[s]);     // end sentinel: wake the service warp
+            break;
+        }
+        // ---- step A(k): predicate -> selection mask -> warp total -> tile aggregate
+        RowCtx rc;
+        rowctx_init(rc, tile, TILE, A.n, A.err, stages + (size_t)s * A.sp.stage_bytes);
+        sink.sel = 0;
+        run(A.prog, 0, A.sel_end, st, rc, sink);
+        const uint32_t c_sel = sink.sel;
+        int wt = __popc(c_sel);
 #pragma unroll
-        for (int r = 0; r < R; r++) c_rank[r] = 0;
-        if (!last) {
-            // ---- step A(k): predicate, ranks in row order (chunk, lane, pair element), warp total
-            RowCtx rc;
-            rowctx_init(rc, tile, TILE, A.n, A.err, stages + (size_t)s * A.sp.stage_bytes);
-            sink.sel = 0;
-            run(A.prog, 0, A.sel_end, st, rc, sink);
-            c_sel = sink.sel;
-            int wt = 0;
-#pragma unroll
-            for (int j = 0; j < NCHUNK; j++) {
-                uint32_t s0 = (c_sel >> (2 * j)) & 1u, s1 = (c_sel >> (2 * j + 1)) & 1u;
-                uint32_t b0 = __ballot_sync(0xffffffffu, s0), b1 = __ballot_sync(0xffffffffu, s1);
-                int below = __popc(b0 & lt) + __popc(b1 & lt);
-                c_rank[2 * j] = wt + below;
-                c_rank[2 * j + 1] = wt + below + (int)s0;
-                wt += __popc(b0) + __popc(b1);
+        for (int o = 16; o; o >>= 1) wt += __shfl_xor_sync(0xffffffffu, wt, o);
+        if (lane == 0) {
+            wtot[s][warp] = wt;
+            atomicAdd(&tot[s], wt);
+            __threadfence_block();
+            if (atomicAdd(&arrived[s], 1) == WARPS - 1) {
+                // last warp of the tile: publish the aggregate right away so that no other block's
+                // look-back ever waits on this block's service warp
+                __threadfence_block();
+                const unsigned long long t = (unsigned long long)atomicAdd(&tot[s], 0);
+                A.tile_desc[tile] = (tile == 0 ? LB_INCL : LB_PART) | t;
+                mbar_arrive(&agg_ready[s]);
             }
-            if (lane == 0) wtot[s][warp] = wt;
         }
         __syncwarp();
-        if (lane == 0) mbar_arrive(&agg_ready[s]);          // also wakes the service warp for the end sentinel
-        if (have_prev) {
-            // ---- step B(k-1): prefix, projection, compacted stores
-            mbar_wait(&prefix_ready[p_s], (p_k / S) & 1);
-            int woff = 0;
+        // ---- step B(k - D) if that tile exists; then remember tile k in the queue slot k % LOOKAHEAD
+        if (k >= D) {
 #pragma unroll
-            for (int w = 0; w < WARPS; w++) { int x = wtot[p_s][w]; if (w < warp) woff += x; }
-            RowCtx rc;
-            rowctx_init(rc, p_tile, TILE, A.n, A.err, stages + (size_t)p_s * A.sp.stage_bytes);
-            rc.active = p_sel;        // projection errors only count on surviving rows (FilterExec runs first)
-            sink.sel = p_sel;
-#pragma unroll
-            for (int r = 0; r < R; r++) sink.rank[r] = p_rank[r];
-            sink.base = (long long)prefix[p_s] + woff;
-            if (A.selvec) {
-#pragma unroll
-                for (int r = 0; r < R; r++)
-                    if ((p_sel >> r) & 1u) A.selvec[sink.base + p_rank[r]] = (int32_t)(rc.row0(r >> 1) + (r & 1));
-            }
-            run(A.prog, A.sel_end, A.prog.ninsn, st, rc, sink);
-            __syncwarp();
-            if (lane == 0) mbar_arrive(&empty[p_s]);
+            for (int i = 0; i < LOOKAHEAD; i++)
+                if (i == (k - D) % LOOKAHEAD) step_b(k - D, q_sel[i], q_tile[i]);
         }
-        if (last) break;
-        have_prev = true; p_sel = c_sel; p_tile = tile; p_s = s; p_k = k;
 #pragma unroll
-        for (int r = 0; r < R; r++) p_rank[r] = c_rank[r];
+        for (int i = 0; i < LOOKAHEAD; i++)
+            if (i == k % LOOKAHEAD) { q_sel[i] = c_sel; q_tile[i] = tile; }
+    }
+    // drain: tiles k-D .. k-1 still owe their step B
+    for (int kb = max(0, k - D); kb < k; kb++) {
+#pragma unroll
+        for (int i = 0; i < LOOKAHEAD; i++)
+            if (i == kb % LOOKAHEAD) step_b(kb, q_sel[i], q_tile[i]);
     }
 }
 

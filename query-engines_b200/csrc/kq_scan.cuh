@@ -43,6 +43,42 @@ __device__ __forceinline__ unsigned long long lookback_exclusive(volatile unsign
     return excl;
 }
 
+// Non-blocking variant used by the filter kernel's service warp, split in two so that the L2 round
+// trip of the descriptor loads overlaps other work. The tile's own aggregate has already been
+// published (LB_PART) by the consumer warps. lb_load starts reading the 128 predecessor
+// descriptors (4 per lane); lb_finish folds them and returns false, without waiting, if a needed
+// predecessor has not published yet — the caller retries later.
+__device__ __forceinline__ void lb_load(const volatile unsigned long long* desc, long long base, unsigned long long (&d)[4]) {
+    const int lane = threadIdx.x & 31;
+#pragma unroll
+    for (int j = 0; j < 4; j++) {
+        long long idx = base - lane - 32 * j;
+        d[j] = 2ULL << 62;                 // out of range: an inclusive zero
+        if (idx >= 0) d[j] = desc[idx];
+    }
+}
+__device__ __forceinline__ bool lb_finish(const volatile unsigned long long* desc, long long tile, unsigned long long (&d)[4],
+                                          unsigned long long* excl_out) {
+    const int lane = threadIdx.x & 31;
+    unsigned long long excl = 0;
+    long long base = tile - 1;
+    while (true) {
+#pragma unroll
+        for (int j = 0; j < 4; j++) {
+            if (__any_sync(0xffffffffu, (d[j] >> 62) == 0)) return false;
+            unsigned incl = __ballot_sync(0xffffffffu, (d[j] >> 62) == 2);
+            unsigned long long val = d[j] & LB_VMASK;
+            if (incl) { int first = __ffs(incl) - 1; if (lane > first) val = 0; }
+#pragma unroll
+            for (int o = 16; o; o >>= 1) val += __shfl_xor_sync(0xffffffffu, val, o);
+            excl += val;
+            if (incl) { *excl_out = excl; return true; }
+        }
+        base -= 128;
+        lb_load(desc, base, d);
+    }
+}
+
 // Device-wide exclusive prefix over item lengths -> Arrow int32 offsets. `f(i)` returns the byte
 // length of output item i (and may do side effects such as setting its validity bit). The item
 // count is device-resident (*d_count) so no host round trip is needed after a filter.

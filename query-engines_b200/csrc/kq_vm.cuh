@@ -12,6 +12,9 @@
 // typical expressions (a*b+c, a>k AND b<m) never touch the save stack, and every operator body
 // exists exactly once in the SASS (small code, no spills).
 //
+// Bool values are kept as an R-bit truth mask in acc[0] / tmp[0] (bit r = row r), so AND / OR / NOT-like
+// steps and the predicate -> selection hand-off are a few bit operations per tile, not per row.
+//
 // Row ownership inside a tile of TILE = BLOCK*R rows: warp w owns rows [w*32R, (w+1)*32R); inside
 // that, chunk j (of R/2) covers 64 rows and lane l owns the adjacent pair (2l, 2l+1). One pair of
 // 8-byte values is one 128-bit access; one pair of validity bits comes from one 32-bit word.
@@ -22,7 +25,10 @@
 
 namespace kq {
 
-constexpr int R = 4;                 // rows per thread (even)
+#ifndef KQ_R
+#define KQ_R 4
+#endif
+constexpr int R = KQ_R;              // rows per thread (even); each kernel file picks its own before including this header
 constexpr int NCHUNK = R / 2;
 constexpr int WARP_ROWS = 32 * R;    // rows one warp owns per tile; a tile is (consumer warps) x WARP_ROWS rows
 constexpr int DS = 3;                // save slots (nesting depth of binary nodes with two non-leaf operands)
@@ -35,7 +41,7 @@ constexpr int MAX_KEYS = 4;
 constexpr int MAX_INPUTS = 6;
 constexpr uint32_t RMASK = (1u << R) - 1u;
 
-// operand fetch
+// Operand sources of the load / Bool instructions
 enum Src : uint8_t {
     S_NONE = 0, S_COL64, S_COL32, S_COLBIT, S_LIT, S_NULL, S_VALID, S_STACK,
     S_UTF8_CMP_LIT,                  // a = col, b = lit | mask << 8 : Bool
@@ -43,14 +49,22 @@ enum Src : uint8_t {
     S_UTF8_PACK,                     // a = col: short string (<= 7 bytes) -> packed u64 group key
     S_UTF8_F64                       // a = col: CastExpression Utf8 -> Float64 (Main.kt:772-805)
 };
-// operation: ACC = ACC op TMP (R* variants: ACC = TMP op ACC)
+// 64-bit binary primitives are specialised per operand mode, like the primitives of a vectorised
+// engine: ACC = X op Y with X, Y taken straight from a staged column, a literal, ACC or a save slot.
+enum Mode : uint8_t {
+    M_ACC_COL = 0, M_ACC_LIT, M_COL_ACC, M_LIT_ACC, M_COL_COL, M_COL_LIT, M_LIT_COL, M_STK_ACC, NMODES
+};
+enum Bin : uint8_t {
+    B_ADD_I64 = 0, B_SUB_I64, B_MUL_I64, B_DIV_I64, B_ADD_F64, B_SUB_F64, B_MUL_F64, B_DIV_F64, B_CMP_I64, B_CMP_F64, NBIN
+};
+// Opcodes. A binary primitive is O_BIN + bin * NMODES + mode; operand a = first column/literal/slot,
+// (b & 0xff) = second column/literal, (b >> 8) = comparison truth mask.
 enum Op : uint8_t {
     O_END = 0, O_LOAD, O_PUSH,
-    O_ADD_I64, O_SUB_I64, O_RSUB_I64, O_MUL_I64, O_DIV_I64, O_RDIV_I64,
-    O_ADD_F64, O_SUB_F64, O_RSUB_F64, O_MUL_F64, O_DIV_F64, O_RDIV_F64,
-    O_CMP_I64, O_CMP_F64,            // b = 4-bit truth mask over {lt, eq, gt, unordered} of (ACC ? TMP)
-    O_AND, O_OR, O_I64_TO_F64,
-    O_SET_SEL, O_EMIT, O_SET_KEY, O_SET_IN
+    O_AND, O_OR, O_CMP_BOOL,         // ACC (truth mask) op operand fetched through `src`
+    O_I64_TO_F64,
+    O_SET_SEL, O_EMIT, O_SET_KEY, O_SET_IN,
+    O_BIN                            // first of NBIN * NMODES primitives
 };
 
 // comparison truth masks: bit0 = lt, bit1 = eq, bit2 = gt, bit3 = unordered (NaN)
@@ -76,7 +90,6 @@ struct Program {
 
 struct Vm {
     uint64_t acc[R]; uint32_t aok;   // accumulator + R-bit validity mask
-    uint64_t tmp[R]; uint32_t tok;   // operand
     // save slots are separate members on purpose: an array indexed by the instruction would be
     // demoted to local memory by the compiler
     uint64_t s0[R], s1[R], s2[R]; uint32_t k0, k1, k2;
@@ -206,9 +219,7 @@ __device__ __forceinline__ void load32(const DCol& c, const RowCtx& rc, uint64_t
     ok = load_valid(c, rc);
 }
 __device__ __forceinline__ void loadbit(const DCol& c, const RowCtx& rc, uint64_t (&v)[R], uint32_t& ok) {
-    uint32_t m = c.s_data >= 0 ? load_bits_s(rc.stage + c.s_data, rc) : load_bits_g(reinterpret_cast<const uint32_t*>(c.data), rc);
-#pragma unroll
-    for (int r = 0; r < R; r++) v[r] = (m >> r) & 1u;
+    v[0] = c.s_data >= 0 ? load_bits_s(rc.stage + c.s_data, rc) : load_bits_g(reinterpret_cast<const uint32_t*>(c.data), rc);
     ok = load_valid(c, rc);
 }
 // byte range [a, b) of the string in owned row r (offsets from the stage when staged)
@@ -323,12 +334,11 @@ __device__ __forceinline__ void utf8_cmp_lit(const Program& P, const Insn in, co
     const uint32_t mask = in.b >> 8;
     const uint32_t ok = load_valid(c, rc);
     const uint8_t* bytes = reinterpret_cast<const uint8_t*>(c.data);
+    uint32_t m = 0;
 #pragma unroll
-    for (int r = 0; r < R; r++) {
-        uint64_t res = 0;
-        if ((ok >> r) & 1u) { int a, b; utf8_bounds(c, rc, r, a, b); res = utf8_cmp_row(bytes + a, b - a, q, qn, mask); }
-        out[r] = res;
-    }
+    for (int r = 0; r < R; r++)
+        if ((ok >> r) & 1u) { int a, b; utf8_bounds(c, rc, r, a, b); m |= utf8_cmp_row(bytes + a, b - a, q, qn, mask) << r; }
+    out[0] = m;
     ok_out = ok;
 }
 __device__ __forceinline__ void utf8_cmp_col(const Program& P, const Insn in, const RowCtx& rc, uint64_t (&out)[R], uint32_t& ok_out) {
@@ -336,15 +346,14 @@ __device__ __forceinline__ void utf8_cmp_col(const Program& P, const Insn in, co
     const DCol& d = P.cols[in.b & 0xff];
     const uint32_t mask = in.b >> 8;
     const uint32_t ok = load_valid(c, rc) & load_valid(d, rc);
+    uint32_t m = 0;
 #pragma unroll
-    for (int r = 0; r < R; r++) {
-        uint64_t res = 0;
+    for (int r = 0; r < R; r++)
         if ((ok >> r) & 1u) {
             int a, b, a2, b2; utf8_bounds(c, rc, r, a, b); utf8_bounds(d, rc, r, a2, b2);
-            res = utf8_cmp_row(reinterpret_cast<const uint8_t*>(c.data) + a, b - a, reinterpret_cast<const uint8_t*>(d.data) + a2, b2 - a2, mask);
+            m |= utf8_cmp_row(reinterpret_cast<const uint8_t*>(c.data) + a, b - a, reinterpret_cast<const uint8_t*>(d.data) + a2, b2 - a2, mask) << r;
         }
-        out[r] = res;
-    }
+    out[0] = m;
     ok_out = ok;
 }
 __device__ __forceinline__ void utf8_pack(const DCol& c, const RowCtx& rc, uint64_t (&out)[R], uint32_t& ok_out) {
@@ -376,8 +385,98 @@ __device__ __forceinline__ void utf8_to_f64(const Program& P, const Insn in, con
     ok_out = ok;
 }
 
+
+// ---- operand fetch for the binary primitives ------------------------------------------------------------
+__device__ __forceinline__ void fetch_lit(const Program& P, int idx, const RowCtx& rc, uint64_t (&v)[R], uint32_t& ok) {
+    const uint64_t x = P.lit[idx];
+#pragma unroll
+    for (int r = 0; r < R; r++) v[r] = x;
+    ok = rc.inr;
+}
+__device__ __forceinline__ void fetch_acc(const Vm& vm, uint64_t (&v)[R], uint32_t& ok) {
+#pragma unroll
+    for (int r = 0; r < R; r++) v[r] = vm.acc[r];
+    ok = vm.aok;
+}
+__device__ __forceinline__ void fetch_stk(const Vm& vm, int slot, uint64_t (&v)[R], uint32_t& ok) {
+    switch (slot) {
+#define KQ_POP(d, S, K) case d: _Pragma("unroll") for (int r = 0; r < R; r++) v[r] = vm.S[r]; ok = vm.K; break;
+        KQ_POP(0, s0, k0) KQ_POP(1, s1, k1)
+#undef KQ_POP
+        default:
+#pragma unroll
+            for (int r = 0; r < R; r++) v[r] = vm.s2[r];
+            ok = vm.k2;
+            break;
+    }
+}
+template <int MODE>
+__device__ __forceinline__ void fetch2(const Program& P, const Insn in, const Vm& vm, const RowCtx& rc,
+                                       uint64_t (&x)[R], uint32_t& okx, uint64_t (&y)[R], uint32_t& oky) {
+    if constexpr (MODE == M_ACC_COL) { fetch_acc(vm, x, okx); load64(P.cols[in.a], rc, y, oky); }
+    else if constexpr (MODE == M_ACC_LIT) { fetch_acc(vm, x, okx); fetch_lit(P, in.a, rc, y, oky); }
+    else if constexpr (MODE == M_COL_ACC) { load64(P.cols[in.a], rc, x, okx); fetch_acc(vm, y, oky); }
+    else if constexpr (MODE == M_LIT_ACC) { fetch_lit(P, in.a, rc, x, okx); fetch_acc(vm, y, oky); }
+    else if constexpr (MODE == M_COL_COL) { load64(P.cols[in.a], rc, x, okx); load64(P.cols[in.b & 0xff], rc, y, oky); }
+    else if constexpr (MODE == M_COL_LIT) { load64(P.cols[in.a], rc, x, okx); fetch_lit(P, in.b & 0xff, rc, y, oky); }
+    else if constexpr (MODE == M_LIT_COL) { fetch_lit(P, in.a, rc, x, okx); load64(P.cols[in.b & 0xff], rc, y, oky); }
+    else { fetch_stk(vm, in.a, x, okx); fetch_acc(vm, y, oky); }
+}
+
 __device__ __forceinline__ double as_f64(uint64_t x) { return __longlong_as_double((long long)x); }
 __device__ __forceinline__ uint64_t as_u64(double x) { return (uint64_t)__double_as_longlong(x); }
+
+template <int BIN, int MODE>
+__device__ __forceinline__ void binop(const Program& P, const Insn in, Vm& vm, RowCtx& rc) {
+    uint64_t x[R], y[R];
+    uint32_t okx, oky;
+    fetch2<MODE>(P, in, vm, rc, x, okx, y, oky);
+    const uint32_t both = okx & oky;
+    if constexpr (BIN == B_CMP_I64 || BIN == B_CMP_F64) {
+        // three relation masks, then the instruction's truth mask picks (IEEE: all three are false on NaN)
+        uint32_t ltm = 0, eqm = 0, gtm = 0;
+#pragma unroll
+        for (int r = 0; r < R; r++) {
+            if constexpr (BIN == B_CMP_I64) {
+                const long long a = (long long)x[r], b = (long long)y[r];
+                ltm |= (uint32_t)(a < b) << r; eqm |= (uint32_t)(a == b) << r; gtm |= (uint32_t)(a > b) << r;
+            } else {
+                const double a = as_f64(x[r]), b = as_f64(y[r]);
+                ltm |= (uint32_t)(a < b) << r; eqm |= (uint32_t)(a == b) << r; gtm |= (uint32_t)(a > b) << r;
+            }
+        }
+        const uint32_t m = in.b >> 8;
+        const uint32_t un = ~(ltm | eqm | gtm) & RMASK;
+        vm.acc[0] = ((m & 1u) ? ltm : 0u) | ((m & 2u) ? eqm : 0u) | ((m & 4u) ? gtm : 0u) | ((m & 8u) ? un : 0u);
+    } else if constexpr (BIN == B_DIV_I64) {
+#pragma unroll
+        for (int r = 0; r < R; r++) {
+            const long long a = (long long)x[r], b = (long long)y[r];
+            long long q = 0;
+            if (b == 0) {
+                if ((both & rc.active) >> r & 1u) atomicOr(rc.err, 1u);               // KQ_DEV_ERR_DIV0 (rule E4)
+            } else if (b == -1) q = (long long)(0ULL - (unsigned long long)a);        // JVM ldiv wraps
+            else q = a / b;
+            vm.acc[r] = (uint64_t)q;
+        }
+    } else {
+#pragma unroll
+        for (int r = 0; r < R; r++) {
+            const uint64_t a = x[r], b = y[r];
+            uint64_t o;
+            // Float64: separately rounded IEEE operations, never contracted into FMA (rule E4)
+            if constexpr (BIN == B_ADD_I64) o = a + b;
+            else if constexpr (BIN == B_SUB_I64) o = a - b;
+            else if constexpr (BIN == B_MUL_I64) o = a * b;
+            else if constexpr (BIN == B_ADD_F64) o = as_u64(__dadd_rn(as_f64(a), as_f64(b)));
+            else if constexpr (BIN == B_SUB_F64) o = as_u64(__dsub_rn(as_f64(a), as_f64(b)));
+            else if constexpr (BIN == B_MUL_F64) o = as_u64(__dmul_rn(as_f64(a), as_f64(b)));
+            else o = as_u64(__ddiv_rn(as_f64(a), as_f64(b)));
+            vm.acc[r] = o;
+        }
+    }
+    vm.aok = both;
+}
 
 // Run instructions [pc, pc_end).
 template <class Sink>
@@ -385,123 +484,71 @@ __device__ __forceinline__ void run(const Program& P, int pc, int pc_end, Vm& vm
 #pragma unroll 1
     for (; pc < pc_end; ++pc) {
         const Insn in = P.insn[pc];
-        // ---- 1. operand fetch -> TMP
-        switch (in.src) {
-            case S_COL64: load64(P.cols[in.a], rc, vm.tmp, vm.tok); break;
-            case S_COL32: load32(P.cols[in.a], rc, vm.tmp, vm.tok); break;
-            case S_COLBIT: loadbit(P.cols[in.a], rc, vm.tmp, vm.tok); break;
-            case S_LIT: {
-                uint64_t x = P.lit[in.a];
+        switch (in.op) {
+#define KQ_M(B, M) case O_BIN + B * NMODES + M: binop<B, M>(P, in, vm, rc); break;
+#define KQ_B(B) KQ_M(B, M_ACC_COL) KQ_M(B, M_ACC_LIT) KQ_M(B, M_COL_ACC) KQ_M(B, M_LIT_ACC) \
+                KQ_M(B, M_COL_COL) KQ_M(B, M_COL_LIT) KQ_M(B, M_LIT_COL) KQ_M(B, M_STK_ACC)
+            KQ_B(B_ADD_I64) KQ_B(B_SUB_I64) KQ_B(B_MUL_I64) KQ_B(B_DIV_I64)
+            KQ_B(B_ADD_F64) KQ_B(B_SUB_F64) KQ_B(B_MUL_F64) KQ_B(B_DIV_F64)
+            KQ_B(B_CMP_I64) KQ_B(B_CMP_F64)
+#undef KQ_B
+#undef KQ_M
+            case O_LOAD:
+                switch (in.src) {
+                    case S_COL64: load64(P.cols[in.a], rc, vm.acc, vm.aok); break;
+                    case S_COL32: load32(P.cols[in.a], rc, vm.acc, vm.aok); break;
+                    case S_COLBIT: loadbit(P.cols[in.a], rc, vm.acc, vm.aok); break;
+                    case S_LIT: fetch_lit(P, in.a, rc, vm.acc, vm.aok); break;
+                    case S_NULL:
 #pragma unroll
-                for (int r = 0; r < R; r++) vm.tmp[r] = x;
-                vm.tok = rc.inr;
-                break;
-            }
-            case S_NULL:
+                        for (int r = 0; r < R; r++) vm.acc[r] = 0;
+                        vm.aok = 0;
+                        break;
+                    case S_VALID:              // COUNT(col) of any type only needs the validity bit
 #pragma unroll
-                for (int r = 0; r < R; r++) vm.tmp[r] = 0;
-                vm.tok = 0;
-                break;
-            case S_VALID:              // COUNT(col) of any type only needs the validity bit
-#pragma unroll
-                for (int r = 0; r < R; r++) vm.tmp[r] = 1;
-                vm.tok = load_valid(P.cols[in.a], rc);
-                break;
-            case S_STACK:
-                switch (in.a) {
-#define KQ_POP(d, S, K) case d: _Pragma("unroll") for (int r = 0; r < R; r++) vm.tmp[r] = vm.S[r]; vm.tok = vm.K; break;
-                    KQ_POP(0, s0, k0) KQ_POP(1, s1, k1) KQ_POP(2, s2, k2)
-#undef KQ_POP
+                        for (int r = 0; r < R; r++) vm.acc[r] = 1;
+                        vm.aok = load_valid(P.cols[in.a], rc);
+                        break;
+                    case S_UTF8_CMP_LIT: utf8_cmp_lit(P, in, rc, vm.acc, vm.aok); break;
+                    case S_UTF8_CMP_COL: utf8_cmp_col(P, in, rc, vm.acc, vm.aok); break;
+                    case S_UTF8_PACK: utf8_pack(P.cols[in.a], rc, vm.acc, vm.aok); break;
+                    case S_UTF8_F64: utf8_to_f64(P, in, rc, vm.acc, vm.aok); break;
                     default: break;
                 }
-                break;
-            case S_UTF8_CMP_LIT: utf8_cmp_lit(P, in, rc, vm.tmp, vm.tok); break;
-            case S_UTF8_CMP_COL: utf8_cmp_col(P, in, rc, vm.tmp, vm.tok); break;
-            case S_UTF8_PACK: utf8_pack(P.cols[in.a], rc, vm.tmp, vm.tok); break;
-            case S_UTF8_F64: utf8_to_f64(P, in, rc, vm.tmp, vm.tok); break;
-            default: break;
-        }
-        // ---- 2. operation
-#define KQ_BIN(opname, expr)                                              \
-        case opname:                                                      \
-            _Pragma("unroll") for (int r = 0; r < R; r++) {               \
-                const uint64_t a = vm.acc[r], b = vm.tmp[r]; (void)a; (void)b; \
-                vm.acc[r] = (expr);                                       \
-            }                                                             \
-            vm.aok &= vm.tok;                                             \
-            break;
-        switch (in.op) {
-            case O_LOAD:
-#pragma unroll
-                for (int r = 0; r < R; r++) vm.acc[r] = vm.tmp[r];
-                vm.aok = vm.tok;
                 break;
             case O_PUSH:
                 switch (in.a) {
 #define KQ_PUSH(d, S, K) case d: _Pragma("unroll") for (int r = 0; r < R; r++) vm.S[r] = vm.acc[r]; vm.K = vm.aok; break;
-                    KQ_PUSH(0, s0, k0) KQ_PUSH(1, s1, k1) KQ_PUSH(2, s2, k2)
+                    KQ_PUSH(0, s0, k0) KQ_PUSH(1, s1, k1)
 #undef KQ_PUSH
-                    default: break;
+                    default:
+#pragma unroll
+                        for (int r = 0; r < R; r++) vm.s2[r] = vm.acc[r];
+                        vm.k2 = vm.aok;
+                        break;
                 }
                 break;
-            KQ_BIN(O_ADD_I64, a + b)
-            KQ_BIN(O_SUB_I64, a - b)
-            KQ_BIN(O_RSUB_I64, b - a)
-            KQ_BIN(O_MUL_I64, a * b)
-            // separately rounded IEEE operations: never contracted into FMA (rule E4)
-            KQ_BIN(O_ADD_F64, as_u64(__dadd_rn(as_f64(a), as_f64(b))))
-            KQ_BIN(O_SUB_F64, as_u64(__dsub_rn(as_f64(a), as_f64(b))))
-            KQ_BIN(O_RSUB_F64, as_u64(__dsub_rn(as_f64(b), as_f64(a))))
-            KQ_BIN(O_MUL_F64, as_u64(__dmul_rn(as_f64(a), as_f64(b))))
-            KQ_BIN(O_DIV_F64, as_u64(__ddiv_rn(as_f64(a), as_f64(b))))
-            KQ_BIN(O_RDIV_F64, as_u64(__ddiv_rn(as_f64(b), as_f64(a))))
-            case O_DIV_I64:
-            case O_RDIV_I64: {
-                const uint32_t both = vm.aok & vm.tok;
-                const bool rev = in.op == O_RDIV_I64;
-#pragma unroll
-                for (int r = 0; r < R; r++) {
-                    long long a = (long long)(rev ? vm.tmp[r] : vm.acc[r]), b = (long long)(rev ? vm.acc[r] : vm.tmp[r]);
-                    long long q = 0;
-                    if (b == 0) {
-                        if ((both & rc.active) >> r & 1u) atomicOr(rc.err, 1u);           // KQ_DEV_ERR_DIV0 (rule E4)
-                    } else if (b == -1) q = (long long)(0ULL - (unsigned long long)a);    // JVM ldiv wraps
-                    else q = a / b;
-                    vm.acc[r] = (uint64_t)q;
+            case O_AND: case O_OR: case O_CMP_BOOL: {
+                // Bool operand (truth mask + validity) through `src`: a Bool column, a literal or a save slot
+                uint32_t bt = 0, ob = 0;
+                switch (in.src) {
+                    case S_COLBIT: { uint64_t t[R]; loadbit(P.cols[in.a], rc, t, ob); bt = (uint32_t)t[0]; break; }
+                    case S_LIT: bt = (uint32_t)P.lit[in.a]; ob = rc.inr; break;
+                    case S_NULL: bt = 0; ob = 0; break;
+                    default: { uint64_t t[R]; fetch_stk(vm, in.a, t, ob); bt = (uint32_t)t[0]; break; }
                 }
-                vm.aok = both;
-                break;
-            }
-            case O_CMP_I64:
-#pragma unroll
-                for (int r = 0; r < R; r++) {
-                    long long a = (long long)vm.acc[r], b = (long long)vm.tmp[r];
-                    int code = a < b ? 0 : (a == b ? 1 : 2);
-                    vm.acc[r] = (in.b >> code) & 1u;
+                const uint32_t at = (uint32_t)vm.acc[0], oa = vm.aok;
+                if (in.op == O_AND) {          // SQL three-valued logic (rule E3) on truth masks
+                    const uint32_t f = (oa & ~at) | (ob & ~bt), t = (oa & at) & (ob & bt);
+                    vm.acc[0] = t; vm.aok = (t | f) & rc.inr;
+                } else if (in.op == O_OR) {
+                    const uint32_t t = (oa & at) | (ob & bt), f = (oa & ~at) & (ob & ~bt);
+                    vm.acc[0] = t; vm.aok = (t | f) & rc.inr;
+                } else {                       // ACC ? operand with truth mask b >> 8
+                    const uint32_t ltm = ~at & bt, eqm = ~(at ^ bt), gtm = at & ~bt, m = in.b >> 8;
+                    vm.acc[0] = (((m & 1u) ? ltm : 0u) | ((m & 2u) ? eqm : 0u) | ((m & 4u) ? gtm : 0u)) & RMASK;
+                    vm.aok = oa & ob;
                 }
-                vm.aok &= vm.tok;
-                break;
-            case O_CMP_F64:
-#pragma unroll
-                for (int r = 0; r < R; r++) {
-                    double a = as_f64(vm.acc[r]), b = as_f64(vm.tmp[r]);
-                    int code = a < b ? 0 : (a == b ? 1 : (a > b ? 2 : 3));
-                    vm.acc[r] = (in.b >> code) & 1u;
-                }
-                vm.aok &= vm.tok;
-                break;
-            case O_AND:                // SQL three-valued logic (rule E3)
-            case O_OR: {
-                uint32_t at = 0, bt = 0;
-#pragma unroll
-                for (int r = 0; r < R; r++) { at |= (uint32_t)(vm.acc[r] & 1u) << r; bt |= (uint32_t)(vm.tmp[r] & 1u) << r; }
-                const uint32_t oa = vm.aok, ob = vm.tok;
-                uint32_t t, f;
-                if (in.op == O_AND) { f = (oa & ~at) | (ob & ~bt); t = (oa & at) & (ob & bt); }
-                else { t = (oa & at) | (ob & bt); f = (oa & ~at) & (ob & ~bt); }
-#pragma unroll
-                for (int r = 0; r < R; r++) vm.acc[r] = (t >> r) & 1u;
-                vm.aok = (t | f) & rc.inr;
                 break;
             }
             case O_I64_TO_F64:
@@ -510,11 +557,10 @@ __device__ __forceinline__ void run(const Program& P, int pc, int pc_end, Vm& vm
                 break;
             case O_SET_SEL: sink.set_sel(vm.acc, vm.aok, rc); break;
             case O_EMIT: sink.emit(in.a, vm.acc, vm.aok, rc); break;
-            case O_SET_KEY: sink.set_key(in.a, vm.acc, vm.aok, rc); break;
-            case O_SET_IN: sink.set_in(in.a, vm.acc, vm.aok, rc); break;
+            case O_SET_KEY: sink.set_key(in.a, in.b != 0, vm.acc, vm.aok, rc); break;     // b: ACC is a Bool truth mask
+            case O_SET_IN: sink.set_in(in.a, in.b != 0, vm.acc, vm.aok, rc); break;
             default: break;
         }
-#undef KQ_BIN
     }
 }
 
