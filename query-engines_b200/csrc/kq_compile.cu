@@ -235,7 +235,7 @@ int KqCompiler::value(const kq_expr* e, int* type, bool* nullable) {
             if (is_cmp) bin = f64 ? B_CMP_F64 : B_CMP_I64;
             else bin = (f64 ? B_ADD_F64 : B_ADD_I64) + (op - KQ_ADD);
             const uint32_t mb = is_cmp ? (cmp_mask(op) << 8) : 0;
-            auto prim = [&](int mode, int a, uint32_t b2) { return emit(O_BIN + bin * NMODES + mode, S_NONE, a, b2 | mb); };
+            auto prim = [&](int mode, int a, uint32_t b2) { return emit(O_BIN + bin, mode, a, b2 | mb); };
             int sl = 0, al = 0, sr = 0, ar = 0;
             const bool ll = is_leaf64(e->l) && leaf_src(e->l, &sl, &al);
             const bool rl = is_leaf64(e->r) && leaf_src(e->r, &sr, &ar);

@@ -57,14 +57,14 @@ enum Mode : uint8_t {
 enum Bin : uint8_t {
     B_ADD_I64 = 0, B_SUB_I64, B_MUL_I64, B_DIV_I64, B_ADD_F64, B_SUB_F64, B_MUL_F64, B_DIV_F64, B_CMP_I64, B_CMP_F64, NBIN
 };
-// Opcodes. A binary primitive is O_BIN + bin * NMODES + mode; operand a = first column/literal/slot,
-// (b & 0xff) = second column/literal, (b >> 8) = comparison truth mask.
+// Opcodes. A binary primitive is op = O_BIN + bin with the operand mode in `src`; a = first
+// column/literal/slot, (b & 0xff) = second column/literal, (b >> 8) = comparison truth mask.
 enum Op : uint8_t {
     O_END = 0, O_LOAD, O_PUSH,
     O_AND, O_OR, O_CMP_BOOL,         // ACC (truth mask) op operand fetched through `src`
     O_I64_TO_F64,
     O_SET_SEL, O_EMIT, O_SET_KEY, O_SET_IN,
-    O_BIN                            // first of NBIN * NMODES primitives
+    O_BIN                            // first of NBIN binary primitives
 };
 
 // comparison truth masks: bit0 = lt, bit1 = eq, bit2 = gt, bit3 = unordered (NaN)
@@ -148,7 +148,7 @@ __device__ __forceinline__ uint2 interleave_ballots(uint32_t b0, uint32_t b1) {
 // ---- column loads --------------------------------------------------------------------------------------
 // Staged buffers are read from the tile's shared-memory stage (filled by TMA bulk copies); buffers
 // that did not fit the stage budget are read from global memory with 128-bit coalesced loads.
-__device__ __forceinline__ uint32_t load_bits_g(const uint32_t* bits, const RowCtx& rc) {
+static __device__ __noinline__ uint32_t load_bits_g(const uint32_t* bits, const RowCtx& rc) {
     uint32_t m = 0;
 #pragma unroll
     for (int j = 0; j < NCHUNK; j++) {
@@ -426,28 +426,26 @@ __device__ __forceinline__ void fetch2(const Program& P, const Insn in, const Vm
 __device__ __forceinline__ double as_f64(uint64_t x) { return __longlong_as_double((long long)x); }
 __device__ __forceinline__ uint64_t as_u64(double x) { return (uint64_t)__double_as_longlong(x); }
 
-template <int BIN, int MODE>
-__device__ __forceinline__ void binop(const Program& P, const Insn in, Vm& vm, RowCtx& rc) {
-    uint64_t x[R], y[R];
-    uint32_t okx, oky;
-    fetch2<MODE>(P, in, vm, rc, x, okx, y, oky);
-    const uint32_t both = okx & oky;
+template <int BIN>
+__device__ __forceinline__ void apply(const Insn in, Vm& vm, RowCtx& rc, const uint64_t (&x)[R], const uint64_t (&y)[R], uint32_t both) {
     if constexpr (BIN == B_CMP_I64 || BIN == B_CMP_F64) {
-        // three relation masks, then the instruction's truth mask picks (IEEE: all three are false on NaN)
-        uint32_t ltm = 0, eqm = 0, gtm = 0;
-#pragma unroll
-        for (int r = 0; r < R; r++) {
-            if constexpr (BIN == B_CMP_I64) {
-                const long long a = (long long)x[r], b = (long long)y[r];
-                ltm |= (uint32_t)(a < b) << r; eqm |= (uint32_t)(a == b) << r; gtm |= (uint32_t)(a > b) << r;
-            } else {
-                const double a = as_f64(x[r]), b = as_f64(y[r]);
-                ltm |= (uint32_t)(a < b) << r; eqm |= (uint32_t)(a == b) << r; gtm |= (uint32_t)(a > b) << r;
-            }
+        // one relation per instruction; the switch is uniform (IEEE: every relation but != is false on NaN)
+        uint32_t m = 0;
+#define KQ_REL(REL)                                                                                   \
+        _Pragma("unroll") for (int r = 0; r < R; r++) {                                               \
+            if constexpr (BIN == B_CMP_I64) { const long long a = (long long)x[r], b = (long long)y[r]; if (REL) m |= 1u << r; } \
+            else { const double a = as_f64(x[r]), b = as_f64(y[r]); if (REL) m |= 1u << r; }          \
         }
-        const uint32_t m = in.b >> 8;
-        const uint32_t un = ~(ltm | eqm | gtm) & RMASK;
-        vm.acc[0] = ((m & 1u) ? ltm : 0u) | ((m & 2u) ? eqm : 0u) | ((m & 4u) ? gtm : 0u) | ((m & 8u) ? un : 0u);
+        switch (in.b >> 8) {
+            case CM_EQ: KQ_REL(a == b) break;
+            case CM_NE: KQ_REL(a != b) break;
+            case CM_LT: KQ_REL(a < b) break;
+            case CM_LE: KQ_REL(a <= b) break;
+            case CM_GT: KQ_REL(a > b) break;
+            default: KQ_REL(a >= b) break;
+        }
+#undef KQ_REL
+        vm.acc[0] = m;
     } else if constexpr (BIN == B_DIV_I64) {
 #pragma unroll
         for (int r = 0; r < R; r++) {
@@ -478,21 +476,44 @@ __device__ __forceinline__ void binop(const Program& P, const Insn in, Vm& vm, R
     vm.aok = both;
 }
 
-// Run instructions [pc, pc_end).
+// Run instructions [pc, pc_end). P should live in shared memory (the kernels copy it there once):
+// the instruction stream and the column table are then read with uniform LDS instead of indexed
+// constant-bank loads.
 template <class Sink>
 __device__ __forceinline__ void run(const Program& P, int pc, int pc_end, Vm& vm, RowCtx& rc, Sink& sink) {
 #pragma unroll 1
     for (; pc < pc_end; ++pc) {
         const Insn in = P.insn[pc];
+        if (in.op >= O_BIN) {
+            // binary primitive: operands by mode (8 small bodies), then the operation (10 small bodies)
+            uint64_t x[R], y[R];
+            uint32_t okx, oky;
+            switch (in.src) {
+                case M_ACC_COL: fetch2<M_ACC_COL>(P, in, vm, rc, x, okx, y, oky); break;
+                case M_ACC_LIT: fetch2<M_ACC_LIT>(P, in, vm, rc, x, okx, y, oky); break;
+                case M_COL_ACC: fetch2<M_COL_ACC>(P, in, vm, rc, x, okx, y, oky); break;
+                case M_LIT_ACC: fetch2<M_LIT_ACC>(P, in, vm, rc, x, okx, y, oky); break;
+                case M_COL_COL: fetch2<M_COL_COL>(P, in, vm, rc, x, okx, y, oky); break;
+                case M_COL_LIT: fetch2<M_COL_LIT>(P, in, vm, rc, x, okx, y, oky); break;
+                case M_LIT_COL: fetch2<M_LIT_COL>(P, in, vm, rc, x, okx, y, oky); break;
+                default: fetch2<M_STK_ACC>(P, in, vm, rc, x, okx, y, oky); break;
+            }
+            const uint32_t both = okx & oky;
+            switch (in.op - O_BIN) {
+                case B_ADD_I64: apply<B_ADD_I64>(in, vm, rc, x, y, both); break;
+                case B_SUB_I64: apply<B_SUB_I64>(in, vm, rc, x, y, both); break;
+                case B_MUL_I64: apply<B_MUL_I64>(in, vm, rc, x, y, both); break;
+                case B_DIV_I64: apply<B_DIV_I64>(in, vm, rc, x, y, both); break;
+                case B_ADD_F64: apply<B_ADD_F64>(in, vm, rc, x, y, both); break;
+                case B_SUB_F64: apply<B_SUB_F64>(in, vm, rc, x, y, both); break;
+                case B_MUL_F64: apply<B_MUL_F64>(in, vm, rc, x, y, both); break;
+                case B_DIV_F64: apply<B_DIV_F64>(in, vm, rc, x, y, both); break;
+                case B_CMP_I64: apply<B_CMP_I64>(in, vm, rc, x, y, both); break;
+                default: apply<B_CMP_F64>(in, vm, rc, x, y, both); break;
+            }
+            continue;
+        }
         switch (in.op) {
-#define KQ_M(B, M) case O_BIN + B * NMODES + M: binop<B, M>(P, in, vm, rc); break;
-#define KQ_B(B) KQ_M(B, M_ACC_COL) KQ_M(B, M_ACC_LIT) KQ_M(B, M_COL_ACC) KQ_M(B, M_LIT_ACC) \
-                KQ_M(B, M_COL_COL) KQ_M(B, M_COL_LIT) KQ_M(B, M_LIT_COL) KQ_M(B, M_STK_ACC)
-            KQ_B(B_ADD_I64) KQ_B(B_SUB_I64) KQ_B(B_MUL_I64) KQ_B(B_DIV_I64)
-            KQ_B(B_ADD_F64) KQ_B(B_SUB_F64) KQ_B(B_MUL_F64) KQ_B(B_DIV_F64)
-            KQ_B(B_CMP_I64) KQ_B(B_CMP_F64)
-#undef KQ_B
-#undef KQ_M
             case O_LOAD:
                 switch (in.src) {
                     case S_COL64: load64(P.cols[in.a], rc, vm.acc, vm.aok); break;
