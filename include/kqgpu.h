@@ -186,6 +186,14 @@ KQ_API int kq_filter_project_host(kq_ctx* ctx, kq_expr* pred, kq_expr* const* ex
                                   void* const* out_data, uint8_t* const* out_validity,
                                   int64_t* out_rows);
 
+/* Diagnostics (EXPLAIN): the CUDA source of the query-specific part of the kernel kq_project /
+ * kq_filter_project would run for this query shape over a batch whose columns have the given types
+ * and nullability; with compile != 0 the full kernel is also compiled for sm_100a (no device
+ * needed). On failure `source` receives the error text. pred may be NULL (projection only). */
+KQ_API int kq_explain_filter_project(kq_expr* pred, kq_expr* const* exprs, int nexprs, int ncols,
+                                     const int* types, const int* nullable, int compile,
+                                     char* source, size_t source_cap);
+
 /* ---- hash aggregate ---------------------------------------------------------------------- */
 /* HashAggregateExec(input, groupExpr, aggregateExpr) (Main.kt:605-610). `pred` (nullable) fuses a
  * FilterExec below the aggregate; group/aggregate input expressions are evaluated in the same

@@ -1,0 +1,93 @@
+// kq_aggtable.cuh — the global aggregation table in HBM: record layout, hashing, find-or-insert and the
+// atomic accumulate step. Shared by the specialised aggregate kernel (kq_k_agg.cuh) and the table
+// maintenance kernels of kq_hashagg.cu (rehash, merge, collect, finalize).
+//
+// Open addressing with linear probing, one AoS record per group: [0] header {state:32, key
+// nullmask:32}, [1..K] key words, then per aggregate input: non-null count, sum, min, max (only the
+// words the query needs), padded to a multiple of four 64-bit words so that a probe and all
+// accumulator updates of a row touch one or two 32-byte sectors.
+#pragma once
+
+#ifndef __CUDACC_RTC__
+#include <cuda_runtime.h>
+#include <stdint.h>
+#endif
+#include "kq_args.h"
+
+namespace kq {
+
+constexpr uint64_t HDR_EMPTY = 0, HDR_BUSY = 1, HDR_FULL = 2;
+
+__host__ __device__ __forceinline__ uint64_t mix64(uint64_t z) {     // splitmix64 finaliser (same as kq_gen.h kq_mix64)
+    z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ULL;
+    z = (z ^ (z >> 27)) * 0x94D049BB133111EBULL;
+    return z ^ (z >> 31);
+}
+__device__ __forceinline__ uint64_t order_map(uint64_t bits, bool is_int) {
+    if (is_int) return bits ^ 0x8000000000000000ULL;
+    return bits ^ ((bits >> 63) ? ~0ULL : 0x8000000000000000ULL);
+}
+__host__ __device__ __forceinline__ uint64_t order_unmap(uint64_t u, bool is_int) {
+    if (is_int) return u ^ 0x8000000000000000ULL;
+    return u ^ ((u >> 63) ? 0x8000000000000000ULL : ~0ULL);
+}
+__device__ __forceinline__ uint64_t canon_nan(uint64_t bits) {
+    return ((bits & 0x7fffffffffffffffULL) > 0x7ff0000000000000ULL) ? 0x7ff8000000000000ULL : bits;
+}
+__device__ __forceinline__ uint64_t hash_key(const uint64_t (&kw)[MAX_KEYS], uint32_t nullmask, int nkeys) {
+    uint64_t h = 0x9E3779B97F4A7C15ULL + nullmask;
+#pragma unroll
+    for (int k = 0; k < MAX_KEYS; k++) if (k < nkeys) h = mix64(h ^ kw[k]) + 0xD1B54A32D192ED03ULL * (k + 1);
+    return mix64(h);
+}
+
+// Find the record of (kw, nullmask) in the global table, inserting it if absent. Claim protocol:
+// CAS header EMPTY -> BUSY|nullmask, write keys + accumulator identities, fence, publish FULL.
+// The table never fills up: the host sizes it so that ngroups stays below capacity/2 plus margin.
+__device__ __forceinline__ uint64_t* table_find_or_insert(const AggArgs& A, uint64_t h, const uint64_t (&kw)[MAX_KEYS], uint32_t nullmask) {
+    uint64_t slot = h & A.cap_mask;
+    const uint64_t full_hdr = HDR_FULL | ((uint64_t)nullmask << 32);
+    while (true) {
+        uint64_t* rec = A.table + slot * (uint64_t)A.stride;
+        uint64_t hdr = *reinterpret_cast<volatile uint64_t*>(rec);
+        uint32_t state = (uint32_t)hdr;
+        if (state == HDR_EMPTY) {
+            unsigned long long old = atomicCAS(reinterpret_cast<unsigned long long*>(rec), 0ULL, HDR_BUSY | ((uint64_t)nullmask << 32));
+            if (old == 0ULL) {
+                for (int w = 1 + A.nkeys; w < A.stride; w++) rec[w] = A.rec_init[w];
+#pragma unroll
+                for (int k = 0; k < MAX_KEYS; k++) if (k < A.nkeys) rec[1 + k] = kw[k];
+                __threadfence();
+                *reinterpret_cast<volatile uint64_t*>(rec) = full_hdr;
+                atomicAdd(A.ngroups, 1ULL);
+                return rec;
+            }
+            hdr = old; state = (uint32_t)hdr;
+        }
+        if (state == HDR_BUSY) continue;          // another thread is publishing this slot: re-read
+        if (hdr == full_hdr) {
+            bool eq = true;
+#pragma unroll
+            for (int k = 0; k < MAX_KEYS; k++) if (k < A.nkeys) eq &= (__ldcg(rec + 1 + k) == kw[k]);
+            if (eq) return rec;
+        }
+        slot = (slot + 1) & A.cap_mask;
+    }
+}
+
+__device__ __forceinline__ void global_accumulate(uint64_t* rec, const AggInput& d, uint64_t v) {
+    atomicAdd(reinterpret_cast<unsigned long long*>(rec + d.rec_nn), 1ULL);
+    const bool is_int = d.flags & F_INT;
+    if (d.flags & F_SUM) {
+        if (is_int) atomicAdd(reinterpret_cast<unsigned long long*>(rec + d.rec_sum), (unsigned long long)v);
+        else atomicAdd(reinterpret_cast<double*>(rec + d.rec_sum), __longlong_as_double((long long)v));
+    }
+    if (d.flags & (F_MIN | F_MAX)) {
+        uint64_t m = order_map(is_int ? v : canon_nan(v), is_int);
+        if ((d.flags & F_MIN) && m < __ldcg(rec + d.rec_min)) atomicMin(reinterpret_cast<unsigned long long*>(rec + d.rec_min), (unsigned long long)m);
+        if ((d.flags & F_MAX) && m > __ldcg(rec + d.rec_max)) atomicMax(reinterpret_cast<unsigned long long*>(rec + d.rec_max), (unsigned long long)m);
+    }
+}
+
+
+}  // namespace kq

@@ -1,0 +1,117 @@
+// kq_args.h — kernel argument blocks shared by the host library (nvcc) and the query kernels that
+// are specialised at run time (NVRTC, see kq_jit.cu). Fixed-width integers and raw pointers only;
+// the text of this header is embedded verbatim in every generated translation unit.
+#pragma once
+
+#ifndef __CUDACC_RTC__
+#include <stdint.h>
+#endif
+
+namespace kq {
+
+// kq_type values of include/kqgpu.h, usable in device code
+constexpr int KQT_F64 = 1, KQT_UTF8 = 2, KQT_I64 = 3, KQT_BOOL = 4, KQT_DATE32 = 5, KQT_I32 = 6;
+
+// comparison truth masks: bit0 = lt, bit1 = eq, bit2 = gt, bit3 = unordered (NaN)
+constexpr uint32_t CM_EQ = 0x2, CM_NE = 0xD, CM_LT = 0x1, CM_LE = 0x3, CM_GT = 0x4, CM_GE = 0x6;
+
+constexpr int MAX_COLS = 16;        // distinct input columns one kernel may touch
+constexpr int MAX_LIT = 32;         // literal slots (64-bit each)
+constexpr int LITPOOL = 256;        // bytes of Utf8 literal text
+constexpr int MAX_OUT = 8;          // computed output columns of one kernel
+constexpr int MAX_KEYS = 4;         // group-by expressions
+constexpr int MAX_INPUTS = 6;       // distinct aggregate input expressions
+constexpr int MAX_STAGE_BUFS = 24;
+constexpr int MAX_STAGES = 8;
+
+// One input column (an Arrow FieldVector triple resident in HBM).
+struct QCol {
+    const void* data;
+    const uint32_t* validity;       // NULL: all rows valid
+    const int32_t* offsets;         // Utf8 only
+};
+
+// Run-time operands of a specialised kernel. Everything that shapes the code (types, nullability,
+// operators, staging offsets) is compiled in; pointers and literal VALUES stay arguments so that
+// `a > 0.5` and `a > 0.7` share one kernel.
+struct QArgs {
+    QCol cols[MAX_COLS];
+    uint64_t lit[MAX_LIT];          // f64 bits / int64 / date32 (sign-extended) / Utf8: (pool offset << 32) | length
+    uint8_t pool[LITPOOL];
+};
+
+// Shared-memory stage plan: which column buffers the producer warp moves with TMA bulk copies.
+enum StageKind : int32_t { SK_W8 = 0, SK_W4 = 1, SK_W4_PLUS1 = 2, SK_BIT = 3, SK_BYTES = 4 };
+
+struct StageBuf {
+    const char* g;                  // global base of the buffer
+    int32_t soff;                   // byte offset inside a stage (128-byte aligned)
+    int32_t kind;                   // StageKind
+};
+
+struct StagePlan {
+    int32_t nbuf;
+    int32_t stage_bytes;            // multiple of 128
+    int32_t nstages;
+    int32_t _pad;
+    StageBuf buf[MAX_STAGE_BUFS];
+};
+
+struct DOut {
+    void* data;
+    uint32_t* validity;
+};
+
+// ProjectionExec / FilterExec kernels.
+struct OpArgs {
+    QArgs q;
+    int64_t n, ntiles;
+    DOut outs[MAX_OUT];
+    unsigned long long* tile_desc;  // decoupled look-back descriptors, one per tile
+    unsigned int* ticket;
+    unsigned long long* out_count;
+    int32_t* selvec;
+    uint32_t* err;
+    StagePlan sp;
+};
+
+
+// ---- HashAggregateExec -----------------------------------------------------------------------------------------
+constexpr int MAX_REC_WORDS = 32;
+constexpr int DIR_SLOTS = 256;
+constexpr int FE_MAX_GROUPS = 64;
+
+enum : int32_t { F_SUM = 1, F_MIN = 2, F_MAX = 4, F_INT = 8 };
+
+struct AggInput {
+    int32_t flags;
+    int32_t rec_nn, rec_sum, rec_min, rec_max;   // record word indices (-1 = absent)
+    int32_t fe_sum, fe_min, fe_max;              // front-end slot indices (-1 = absent); the count slot is the input index
+};
+
+struct AggArgs {
+    QArgs q;
+    int64_t n, ntiles, tile_begin;
+    int32_t nkeys, ninputs;
+    uint32_t key_f64_mask;                 // keys whose NaNs must be canonicalised (Double.equals, rule R7)
+    int32_t stride;                        // record stride in 64-bit words
+    AggInput in[MAX_INPUTS];
+    uint64_t rec_init[MAX_REC_WORDS];
+    uint64_t* table;
+    uint64_t cap_mask;
+    unsigned long long* ngroups;
+    unsigned long long stop_threshold;
+    unsigned int* ticket;
+    uint32_t* err;
+    // front end
+    int32_t fe_groups, fe_nsum, fe_nmm;
+    int32_t fe_sum_word[MAX_INPUTS];       // front-end sum slot -> record word
+    uint32_t fe_sum_int;                   // bit s: slot s is an integer sum
+    int32_t fe_mm_word[2 * MAX_INPUTS];    // front-end min/max slot -> record word
+    uint32_t fe_mm_ismin;
+    // shared-memory layout (byte offsets): [stage ring][front end]
+    int32_t off_fe, off_dirkeys, off_dirstate, off_gid2slot, off_gslot, off_mm, off_cnt, off_sum, smem_bytes;
+    StagePlan sp;
+};
+
+}  // namespace kq

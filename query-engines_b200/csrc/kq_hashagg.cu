@@ -1,372 +1,24 @@
-// kq_hashagg.cu — HashAggregateExec (Main.kt:605-660) and its accumulators (Main.kt:514-562).
-//
-// One kernel per input batch fuses: optional FilterExec predicate, the group-key and aggregate-input
-// expressions (fused ProjectionExec), and the accumulate step of the drain loop (Main.kt:620-632).
-//
-// Two tiers of state:
-//   * a GLOBAL open-addressing table in HBM (linear probing, one AoS record per group so that a probe
-//     and all accumulator updates of a row touch one or two 32-byte sectors), the source of truth;
-//   * a per-CTA FRONT END in shared memory for the first `fe_groups` distinct keys a CTA meets: a key
-//     directory shared by the CTA plus LANE-PRIVATE count/sum accumulators (one copy per lane per
-//     warp: no atomics, no bank conflicts) and a CTA-shared MIN/MAX table that is only touched when a
-//     value beats the current extreme. Front ends are merged into the global table once, at CTA exit.
-//     Low-cardinality GROUP BYs (BASELINE configs 3 and 5) run entirely in the front end; rows whose
-//     key does not fit go straight to the global table with atomics (config 4).
-//
-// Accumulator semantics (oracle: MaxAccumulator etc.): nulls are skipped; a group whose inputs were
-// all null yields null, except COUNT; MIN/MAX use a total order in which canonical NaN sorts above
-// +inf and -0.0 below +0.0 — where the reference is order-dependent (rule R9/E8) this is the one
-// deterministic choice; Float64 sums are reassociated (1e-9 relative tolerance, rule E6).
+// kq_hashagg.cu — host side of HashAggregateExec (Main.kt:605-660): record layout, table growth,
+// the per-batch launch of the specialised aggregate kernel (kq_k_agg.cuh via kq_codegen.cu / kq_jit.cu),
+// finalisation into the single output batch (Main.kt:635-650) and the table maintenance kernels.
 #include <algorithm>
 #include <cstring>
 
-#include "kq_compile.h"
-#include "kq_pipe.cuh"
+#include "kq_aggtable.cuh"
+#include "kq_codegen.h"
 #include "kq_scan.cuh"
 
 using namespace kq;
 
 namespace {
 
-// 7 consumer warps (the lane-private front end scales with the warp count) + 1 service warp (TMA producer)
-constexpr int WARPS = 7;
-constexpr int BLOCK = WARPS * 32;
-constexpr int TILE = WARPS * WARP_ROWS;     // 896 rows
-constexpr int SERVICE_WARP = WARPS;
-constexpr int THREADS = BLOCK + 32;
+// Tile geometry of the aggregate kernel (compiled in as KQ_R / KQ_WARPS).
+constexpr int AGG_R = 4;
+constexpr int AGG_WARPS = 7;
+constexpr int TILE = AGG_WARPS * 32 * AGG_R;     // 896 rows
+constexpr int THREADS = AGG_WARPS * 32 + 32;
+constexpr int WARPS = AGG_WARPS;
 constexpr int AGG_MAX_STAGES = 4;
-constexpr int MAX_REC_WORDS = 32;
-constexpr int DIR_SLOTS = 256;
-constexpr int FE_MAX_GROUPS = 64;
-constexpr uint32_t DIR_EMPTY = 0, DIR_BUSY = 1, DIR_GLOBAL = 0xFFFFFFFFu;   // FULL = gid + 2
-constexpr uint64_t HDR_EMPTY = 0, HDR_BUSY = 1, HDR_FULL = 2;
-
-enum : int32_t { F_SUM = 1, F_MIN = 2, F_MAX = 4, F_INT = 8 };
-
-struct AggInput {
-    int32_t flags;
-    int32_t rec_nn, rec_sum, rec_min, rec_max;   // record word indices (-1 = absent)
-    int32_t fe_sum, fe_min, fe_max;              // front-end slot indices (-1 = absent); the count slot is the input index
-};
-
-struct AggArgs {
-    Program prog;
-    int64_t n, ntiles, tile_begin;
-    int32_t nkeys, ninputs;
-    uint32_t key_f64_mask;                 // keys whose NaNs must be canonicalised (Double.equals, rule R7)
-    int32_t stride;                        // record stride in 64-bit words
-    AggInput in[MAX_INPUTS];
-    uint64_t rec_init[MAX_REC_WORDS];
-    uint64_t* table;
-    uint64_t cap_mask;
-    unsigned long long* ngroups;
-    unsigned long long stop_threshold;
-    unsigned int* ticket;
-    uint32_t* err;
-    // front end
-    int32_t fe_groups, fe_nsum, fe_nmm;
-    int32_t fe_sum_word[MAX_INPUTS];       // front-end sum slot -> record word
-    uint32_t fe_sum_int;                   // bit s: slot s is an integer sum
-    int32_t fe_mm_word[2 * MAX_INPUTS];    // front-end min/max slot -> record word
-    uint32_t fe_mm_ismin;
-    // shared-memory layout (byte offsets): [stage ring][front end]
-    int32_t off_fe, off_dirkeys, off_dirstate, off_gid2slot, off_gslot, off_mm, off_cnt, off_sum, smem_bytes;
-    StagePlan sp;
-};
-
-__device__ __forceinline__ uint64_t order_map(uint64_t bits, bool is_int) {
-    if (is_int) return bits ^ 0x8000000000000000ULL;
-    return bits ^ ((bits >> 63) ? ~0ULL : 0x8000000000000000ULL);
-}
-__host__ __device__ __forceinline__ uint64_t order_unmap(uint64_t u, bool is_int) {
-    if (is_int) return u ^ 0x8000000000000000ULL;
-    return u ^ ((u >> 63) ? 0x8000000000000000ULL : ~0ULL);
-}
-__device__ __forceinline__ uint64_t canon_nan(uint64_t bits) {
-    return ((bits & 0x7fffffffffffffffULL) > 0x7ff0000000000000ULL) ? 0x7ff8000000000000ULL : bits;
-}
-__device__ __forceinline__ uint64_t hash_key(const uint64_t (&kw)[MAX_KEYS], uint32_t nullmask, int nkeys) {
-    uint64_t h = 0x9E3779B97F4A7C15ULL + nullmask;
-#pragma unroll
-    for (int k = 0; k < MAX_KEYS; k++) if (k < nkeys) h = kq_mix64(h ^ kw[k]) + 0xD1B54A32D192ED03ULL * (k + 1);
-    return kq_mix64(h);
-}
-
-// Find the record of (kw, nullmask) in the global table, inserting it if absent. Claim protocol:
-// CAS header EMPTY -> BUSY|nullmask, write keys + accumulator identities, fence, publish FULL.
-// The table never fills up: the host sizes it so that ngroups stays below capacity/2 plus margin.
-__device__ __forceinline__ uint64_t* table_find_or_insert(const AggArgs& A, uint64_t h, const uint64_t (&kw)[MAX_KEYS], uint32_t nullmask) {
-    uint64_t slot = h & A.cap_mask;
-    const uint64_t full_hdr = HDR_FULL | ((uint64_t)nullmask << 32);
-    while (true) {
-        uint64_t* rec = A.table + slot * (uint64_t)A.stride;
-        uint64_t hdr = *reinterpret_cast<volatile uint64_t*>(rec);
-        uint32_t state = (uint32_t)hdr;
-        if (state == HDR_EMPTY) {
-            unsigned long long old = atomicCAS(reinterpret_cast<unsigned long long*>(rec), 0ULL, HDR_BUSY | ((uint64_t)nullmask << 32));
-            if (old == 0ULL) {
-                for (int w = 1 + A.nkeys; w < A.stride; w++) rec[w] = A.rec_init[w];
-#pragma unroll
-                for (int k = 0; k < MAX_KEYS; k++) if (k < A.nkeys) rec[1 + k] = kw[k];
-                __threadfence();
-                *reinterpret_cast<volatile uint64_t*>(rec) = full_hdr;
-                atomicAdd(A.ngroups, 1ULL);
-                return rec;
-            }
-            hdr = old; state = (uint32_t)hdr;
-        }
-        if (state == HDR_BUSY) continue;          // another thread is publishing this slot: re-read
-        if (hdr == full_hdr) {
-            bool eq = true;
-#pragma unroll
-            for (int k = 0; k < MAX_KEYS; k++) if (k < A.nkeys) eq &= (__ldcg(rec + 1 + k) == kw[k]);
-            if (eq) return rec;
-        }
-        slot = (slot + 1) & A.cap_mask;
-    }
-}
-
-__device__ __forceinline__ void global_accumulate(uint64_t* rec, const AggInput& d, uint64_t v) {
-    atomicAdd(reinterpret_cast<unsigned long long*>(rec + d.rec_nn), 1ULL);
-    const bool is_int = d.flags & F_INT;
-    if (d.flags & F_SUM) {
-        if (is_int) atomicAdd(reinterpret_cast<unsigned long long*>(rec + d.rec_sum), (unsigned long long)v);
-        else atomicAdd(reinterpret_cast<double*>(rec + d.rec_sum), __longlong_as_double((long long)v));
-    }
-    if (d.flags & (F_MIN | F_MAX)) {
-        uint64_t m = order_map(is_int ? v : canon_nan(v), is_int);
-        if ((d.flags & F_MIN) && m < __ldcg(rec + d.rec_min)) atomicMin(reinterpret_cast<unsigned long long*>(rec + d.rec_min), (unsigned long long)m);
-        if ((d.flags & F_MAX) && m > __ldcg(rec + d.rec_max)) atomicMax(reinterpret_cast<unsigned long long*>(rec + d.rec_max), (unsigned long long)m);
-    }
-}
-
-struct SinkBase {
-    __device__ __forceinline__ void emit(int, const uint64_t (&)[R], uint32_t, RowCtx&) {}
-};
-struct AggSink : SinkBase {
-    uint32_t sel;
-    uint64_t key[MAX_KEYS][R];
-    uint32_t keyok[MAX_KEYS];
-    uint64_t in[MAX_INPUTS][R];
-    uint32_t inok[MAX_INPUTS];
-    __device__ __forceinline__ void set_sel(const uint64_t (&v)[R], uint32_t ok, RowCtx& rc) {
-        sel = (uint32_t)v[0] & ok & rc.inr;        // Bool truth mask; TRUE only (null predicate drops the row, rule E3)
-        rc.active = sel;
-    }
-    __device__ __forceinline__ void set_key(int k, bool is_bool, const uint64_t (&v)[R], uint32_t ok, RowCtx&) {
-#pragma unroll
-        for (int kk = 0; kk < MAX_KEYS; kk++)
-            if (kk == k) {
-#pragma unroll
-                for (int r = 0; r < R; r++) key[kk][r] = is_bool ? ((v[0] >> r) & 1u) : v[r];
-                keyok[kk] = ok;
-            }
-    }
-    __device__ __forceinline__ void set_in(int i, bool is_bool, const uint64_t (&v)[R], uint32_t ok, RowCtx&) {
-#pragma unroll
-        for (int ii = 0; ii < MAX_INPUTS; ii++)
-            if (ii == i) {
-#pragma unroll
-                for (int r = 0; r < R; r++) in[ii][r] = is_bool ? ((v[0] >> r) & 1u) : v[r];
-                inok[ii] = ok;
-            }
-    }
-};
-
-// Look the key up in the CTA directory; returns the front-end group id or -1 (row goes global).
-__device__ __forceinline__ int dir_lookup(const AggArgs& A, uint64_t* dirkeys, uint32_t* dirstate, uint32_t* gid2slot,
-                                          uint32_t* dir_count, uint64_t h, const uint64_t (&kw)[MAX_KEYS], uint32_t nullmask) {
-    const int KW = A.nkeys + 1;
-    uint32_t slot = (uint32_t)(h >> 40) & (DIR_SLOTS - 1);
-#pragma unroll 1
-    for (int probe = 0; probe < 8; probe++) {
-        uint32_t st = *reinterpret_cast<volatile uint32_t*>(dirstate + slot);
-        if (st == DIR_EMPTY) {
-            uint32_t old = atomicCAS(dirstate + slot, DIR_EMPTY, DIR_BUSY);
-            if (old == DIR_EMPTY) {
-                uint32_t gid = atomicAdd(dir_count, 1u);
-                uint64_t* dk = dirkeys + slot * KW;
-                dk[0] = nullmask;
-#pragma unroll
-                for (int k = 0; k < MAX_KEYS; k++) if (k < A.nkeys) dk[1 + k] = kw[k];
-                bool fits = gid < (uint32_t)A.fe_groups;
-                if (fits) gid2slot[gid] = slot;
-                __threadfence_block();
-                *reinterpret_cast<volatile uint32_t*>(dirstate + slot) = fits ? gid + 2 : DIR_GLOBAL;
-                return fits ? (int)gid : -1;
-            }
-            st = old;
-        }
-        if (st == DIR_BUSY) return -1;             // being published: this row takes the global path
-        const uint64_t* dk = dirkeys + slot * KW;
-        bool eq = dk[0] == (uint64_t)nullmask;
-#pragma unroll
-        for (int k = 0; k < MAX_KEYS; k++) if (k < A.nkeys) eq &= dk[1 + k] == kw[k];
-        if (eq) return st == DIR_GLOBAL ? -1 : (int)(st - 2);
-        slot = (slot + 1) & (DIR_SLOTS - 1);
-    }
-    return -1;
-}
-
-__global__ void __launch_bounds__(THREADS, 1) k_hash_aggregate(const __grid_constant__ AggArgs A) {
-    extern __shared__ __align__(128) unsigned char smem[];
-    __shared__ uint64_t full[MAX_STAGES], empty[MAX_STAGES];
-    __shared__ long long tile_of[MAX_STAGES];
-    __shared__ uint32_t s_dir_count;
-    uint64_t* dirkeys = reinterpret_cast<uint64_t*>(smem + A.off_dirkeys);
-    uint32_t* dirstate = reinterpret_cast<uint32_t*>(smem + A.off_dirstate);
-    uint32_t* gid2slot = reinterpret_cast<uint32_t*>(smem + A.off_gid2slot);
-    uint64_t* gslot = reinterpret_cast<uint64_t*>(smem + A.off_gslot);
-    uint64_t* mm = reinterpret_cast<uint64_t*>(smem + A.off_mm);
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int NI = A.ninputs, NS = A.fe_nsum, NM = A.fe_nmm, FG = A.fe_groups;
-    const int S = A.sp.nstages;
-    // lane-private accumulators of this warp: cnt[(gid*NI + i)*32 + lane], sum[(gid*NS + s)*32 + lane]
-    uint32_t* cnt = reinterpret_cast<uint32_t*>(smem + A.off_cnt) + (size_t)(warp % WARPS) * FG * NI * 32;
-    uint64_t* sum = reinterpret_cast<uint64_t*>(smem + A.off_sum) + (size_t)(warp % WARPS) * FG * NS * 32;
-
-    for (int i = A.off_fe + threadIdx.x * 4; i < A.smem_bytes; i += THREADS * 4) *reinterpret_cast<uint32_t*>(smem + i) = 0;
-    if (threadIdx.x == 0) {
-        s_dir_count = 0;
-        for (int s = 0; s < S; s++) { mbar_init(&full[s], 1); mbar_init(&empty[s], WARPS); }
-        mbar_fence_init();
-    }
-    __syncthreads();
-    for (int i = threadIdx.x; i < FG * NM; i += THREADS) mm[i] = ((A.fe_mm_ismin >> (i % NM)) & 1u) ? ~0ULL : 0ULL;
-    __syncthreads();
-
-    if (warp == SERVICE_WARP) {
-        if (lane == 0) {
-            for (int k = 0;; k++) {
-                const int s = k % S;
-                mbar_wait(&empty[s], ((k / S) & 1) ^ 1);
-                // stop taking tiles once the global table is half full: every ticket taken is processed,
-                // so the rows consumed so far are always a prefix of the batch (the host grows and resumes)
-                const unsigned long long g = *reinterpret_cast<volatile unsigned long long*>(A.ngroups);
-                long long tile = -1;
-                if (g <= A.stop_threshold) tile = (long long)atomicAdd(A.ticket, 1u) + A.tile_begin;
-                if (tile < 0 || tile >= A.ntiles) { tile_of[s] = -1; mbar_arrive(&full[s]); break; }
-                tile_of[s] = tile;
-                stage_issue(A.sp, smem + (size_t)s * A.sp.stage_bytes, &full[s], tile, TILE, A.n);
-            }
-        }
-    } else {
-    AggSink sink;
-    Vm st;
-    bool bypass = FG == 0;
-    for (int k = 0;; k++) {
-        const int s = k % S;
-        mbar_wait(&full[s], (k / S) & 1);
-        const long long tile = tile_of[s];
-        if (tile < 0) break;
-        RowCtx rc;
-        rowctx_init(rc, tile, TILE, A.n, A.err, smem + (size_t)s * A.sp.stage_bytes);
-        sink.sel = rc.inr;
-        run(A.prog, 0, A.prog.ninsn, st, rc, sink);
-        __syncwarp();
-        if (lane == 0) mbar_arrive(&empty[s]);       // everything needed is in registers now
-
-        int fe_hits = 0, rows = 0;
-#pragma unroll
-        for (int r = 0; r < R; r++) {
-            if (!((sink.sel >> r) & 1u)) continue;
-            uint64_t kw[MAX_KEYS];
-            uint32_t nullmask = 0;
-#pragma unroll
-            for (int k2 = 0; k2 < MAX_KEYS; k2++) {
-                kw[k2] = 0;
-                if (k2 < A.nkeys) {
-                    if ((sink.keyok[k2] >> r) & 1u) kw[k2] = ((A.key_f64_mask >> k2) & 1u) ? canon_nan(sink.key[k2][r]) : sink.key[k2][r];
-                    else nullmask |= 1u << k2;
-                }
-            }
-            const uint64_t h = hash_key(kw, nullmask, A.nkeys);
-            int gid = -1;
-            if (!bypass) gid = dir_lookup(A, dirkeys, dirstate, gid2slot, &s_dir_count, h, kw, nullmask);
-            rows++;
-            if (gid >= 0) {
-                fe_hits++;
-#pragma unroll
-                for (int i = 0; i < MAX_INPUTS; i++) {
-                    if (i < NI && ((sink.inok[i] >> r) & 1u)) {
-                        const AggInput d = A.in[i];
-                        const uint64_t v = sink.in[i][r];
-                        cnt[(gid * NI + i) * 32 + lane] += 1u;
-                        if (d.flags & F_SUM) {
-                            uint64_t* p = sum + (gid * NS + d.fe_sum) * 32 + lane;
-                            if (d.flags & F_INT) *p += v;
-                            else *p = (uint64_t)__double_as_longlong(__dadd_rn(__longlong_as_double((long long)*p), __longlong_as_double((long long)v)));
-                        }
-                        if (d.flags & (F_MIN | F_MAX)) {
-                            const bool is_int = d.flags & F_INT;
-                            uint64_t m = order_map(is_int ? v : canon_nan(v), is_int);
-                            if (d.flags & F_MIN) { uint64_t* p = mm + gid * NM + d.fe_min; if (m < *reinterpret_cast<volatile uint64_t*>(p)) atomicMin(reinterpret_cast<unsigned long long*>(p), (unsigned long long)m); }
-                            if (d.flags & F_MAX) { uint64_t* p = mm + gid * NM + d.fe_max; if (m > *reinterpret_cast<volatile uint64_t*>(p)) atomicMax(reinterpret_cast<unsigned long long*>(p), (unsigned long long)m); }
-                        }
-                    }
-                }
-            } else {
-                uint64_t* rec = table_find_or_insert(A, h, kw, nullmask);
-#pragma unroll
-                for (int i = 0; i < MAX_INPUTS; i++)
-                    if (i < NI && ((sink.inok[i] >> r) & 1u)) global_accumulate(rec, A.in[i], sink.in[i][r]);
-            }
-        }
-        // once the directory is full and this warp mostly misses it, stop probing it (high cardinality)
-        if (!bypass) {
-            int hits = fe_hits, tot = rows;
-#pragma unroll
-            for (int o = 16; o; o >>= 1) { hits += __shfl_xor_sync(0xffffffffu, hits, o); tot += __shfl_xor_sync(0xffffffffu, tot, o); }
-            if (tot >= 64 && hits * 8 < tot && *reinterpret_cast<volatile uint32_t*>(&s_dir_count) >= (uint32_t)FG) bypass = true;
-        }
-    }
-    }
-
-    // ---- merge the front end into the global table ---------------------------------------------------
-    __syncthreads();
-    const int G = min((int)s_dir_count, FG);
-    for (int g = threadIdx.x; g < G; g += THREADS) {
-        const uint64_t* dk = dirkeys + gid2slot[g] * (A.nkeys + 1);
-        uint64_t kw[MAX_KEYS];
-#pragma unroll
-        for (int k = 0; k < MAX_KEYS; k++) kw[k] = k < A.nkeys ? dk[1 + k] : 0;
-        uint32_t nullmask = (uint32_t)dk[0];
-        uint64_t* rec = table_find_or_insert(A, hash_key(kw, nullmask, A.nkeys), kw, nullmask);
-        gslot[g] = (uint64_t)(rec - A.table);
-    }
-    __syncthreads();
-    for (int g = 0; g < G && warp < WARPS; g++) {
-        uint64_t* rec = A.table + gslot[g];
-        for (int i = 0; i < NI; i++) {
-            unsigned long long c = cnt[(g * NI + i) * 32 + lane];
-#pragma unroll
-            for (int o = 16; o; o >>= 1) c += __shfl_xor_sync(0xffffffffu, c, o);
-            if (c == 0) continue;                                   // this warp saw no non-null value of input i in group g
-            const AggInput d = A.in[i];
-            if (lane == 0) atomicAdd(reinterpret_cast<unsigned long long*>(rec + d.rec_nn), c);
-            if (d.flags & F_SUM) {
-                uint64_t x = sum[(g * NS + d.fe_sum) * 32 + lane];
-                if (d.flags & F_INT) {
-#pragma unroll
-                    for (int o = 16; o; o >>= 1) x += __shfl_xor_sync(0xffffffffu, x, o);
-                    if (lane == 0) atomicAdd(reinterpret_cast<unsigned long long*>(rec + d.rec_sum), (unsigned long long)x);
-                } else {
-                    double f = __longlong_as_double((long long)x);
-#pragma unroll
-                    for (int o = 16; o; o >>= 1) f = __dadd_rn(f, __shfl_xor_sync(0xffffffffu, f, o));
-                    if (lane == 0) atomicAdd(reinterpret_cast<double*>(rec + d.rec_sum), f);
-                }
-            }
-        }
-    }
-    for (int t = threadIdx.x; t < G * NM; t += THREADS) {
-        const int g = t / NM, m = t % NM;
-        const uint64_t v = mm[t];
-        uint64_t* p = A.table + gslot[g] + A.fe_mm_word[m];
-        if ((A.fe_mm_ismin >> m) & 1u) { if (v != ~0ULL) atomicMin(reinterpret_cast<unsigned long long*>(p), (unsigned long long)v); }
-        else if (v != 0ULL) atomicMax(reinterpret_cast<unsigned long long*>(p), (unsigned long long)v);
-    }
-}
 
 // ---- table maintenance ---------------------------------------------------------------------------------------
 __global__ void k_rehash(const uint64_t* __restrict__ old_table, uint64_t old_cap, uint64_t* table, uint64_t cap_mask, int stride, int nkeys) {
@@ -658,39 +310,43 @@ int kq_hashagg_update(kq_ctx* ctx, kq_hashagg* h, kq_batch* input) {
     int64_t n; KQ_RET(kq_batch_resolve_rows(ctx, input, &n));
     for (kq_col* c : input->cols) KQ_RET(kq_col_resolve_rows(ctx, c, nullptr));
 
-    // compile: [predicate, SET_SEL] keys..., inputs...
-    KqCompiler cc;
-    KQ_RET(cc.begin(ctx, input));
+    // generate: [predicate -> selection] keys..., inputs...
+    KqCodegen cg;
+    KQ_RET(cg.begin(ctx, input));
     if (h->pred) {
-        int t; bool nl;
-        KQ_RET(cc.value(h->pred, &t, &nl));
-        if (t != KQ_BOOL) return kq_fail(ctx, KQ_ERR_ILLEGAL_STATE, "filter predicate is not Bool");
-        KQ_RET(cc.sink(O_SET_SEL, 0));
+        KqVal p;
+        KQ_RET(cg.value(h->pred, &p));
+        if (p.type != KQ_BOOL) return kq_fail(ctx, KQ_ERR_ILLEGAL_STATE, "filter predicate is not Bool");
+        cg.line("sink.sel = " + p.v + (p.nullable() ? " & " + p.ok : std::string()) + " & rc.inr;");   // TRUE only (rule E3)
+        cg.line("rc.active = sink.sel;");
     }
     std::vector<int> kt, it;
     uint32_t key_f64_mask = 0;
     for (size_t k = 0; k < h->groups.size(); k++) {
-        int t; bool nl;
-        KQ_RET(cc.key_value(h->groups[k], &t, &nl));
-        KQ_RET(cc.sink(O_SET_KEY, (int)k, t));
-        if (t == KQ_F64) key_f64_mask |= 1u << k;
-        kt.push_back(t);
+        KqVal v;
+        KQ_RET(cg.key_value(h->groups[k], &v));
+        const KqVal a = cg.as_array(v);
+        cg.line("sink.template set_key<" + std::to_string(k) + ">(" + a.v + ", " + a.okx() + ");");
+        if (v.type == KQ_F64) key_f64_mask |= 1u << k;
+        kt.push_back(v.type);
     }
     for (size_t i = 0; i < h->inputs.size(); i++) {
         int t; bool nl;
-        KQ_RET(cc.infer(h->inputs[i], &t, &nl));
-        if (h->input_count_only[i]) KQ_RET(cc.validity_only(h->inputs[i]));
+        KQ_RET(cg.infer(h->inputs[i], &t, &nl));
+        KqVal v;
+        if (h->input_count_only[i]) KQ_RET(cg.validity_only(h->inputs[i], &v));
         else {
             int fl = h->in[i].flags;
             // MaxAccumulator throws UnsupportedOperationException for other types (Main.kt:548-550)
             if (t != KQ_F64 && t != KQ_I64 && !(t == KQ_DATE32 && !(fl & F_SUM)))
                 return kq_fail(ctx, KQ_ERR_UNSUPPORTED, "%s is not implemented for data type %d", (fl & F_SUM) ? "SUM" : "MIN/MAX", t);
-            int t2; bool n2;
-            KQ_RET(cc.value(h->inputs[i], &t2, &n2));
+            KQ_RET(cg.value(h->inputs[i], &v));
         }
-        KQ_RET(cc.sink(O_SET_IN, (int)i, h->input_count_only[i] ? 0 : t));
+        const KqVal a = cg.as_array(v);
+        cg.line("sink.template set_in<" + std::to_string(i) + ">(" + a.v + ", " + a.okx() + ");");
         it.push_back(t);
     }
+    const std::string eval_body = cg.take_body();
     if (!h->typed) { h->key_types = kt; h->input_types = it; h->typed = true; }
     else if (kt != h->key_types || it != h->input_types) return kq_fail(ctx, KQ_ERR_ILLEGAL_STATE, "batch schema differs from earlier batches");
     for (size_t i = 0; i < h->inputs.size(); i++) {
@@ -703,7 +359,6 @@ int kq_hashagg_update(kq_ctx* ctx, kq_hashagg* h, kq_batch* input) {
 
     AggArgs A;
     memset(&A, 0, sizeof A);
-    A.prog = cc.prog;
     A.n = n; A.ntiles = (n + TILE - 1) / TILE;
     A.key_f64_mask = key_f64_mask;
 
@@ -723,10 +378,10 @@ int kq_hashagg_update(kq_ctx* ctx, kq_hashagg* h, kq_batch* input) {
     int fixed = DIR_SLOTS * KW * 8 + DIR_SLOTS * 4 + FE_MAX_GROUPS * (4 + 8 + 8 * nm) + 64;
     int per_group = WARPS * 32 * (4 * NI + 8 * ns);
     // stage ring first (2..4 stages within ~64 KB, more only if two stages need it), front end gets the rest
-    cc.plan_stages(64 * 1024, 1, TILE, &A.sp);
-    if (A.sp.nstages < 2) cc.plan_stages(std::min(2 * A.sp.stage_bytes, 112 * 1024), 2, TILE, &A.sp);
+    std::string stage_defs = cg.plan_stages(64 * 1024, 1, TILE, &A.sp);
+    if (A.sp.nstages < 2) stage_defs = cg.plan_stages(std::min(2 * A.sp.stage_bytes, 112 * 1024), 2, TILE, &A.sp);
     A.sp.nstages = std::max(1, std::min(A.sp.nstages, AGG_MAX_STAGES));
-    A.prog = cc.prog;                  // plan_stages filled the staged offsets of the program columns
+    A.q = cg.args;
     const int ring = A.sp.nstages * A.sp.stage_bytes;
     int budget = ctx->max_smem_optin - 2048 - fixed - ring;
     int fg = per_group > 0 ? std::min(FE_MAX_GROUPS, budget / per_group) : FE_MAX_GROUPS;
@@ -742,11 +397,12 @@ int kq_hashagg_update(kq_ctx* ctx, kq_hashagg* h, kq_batch* input) {
     A.off_dirstate = off; off += DIR_SLOTS * 4;
     A.off_gid2slot = off; off += FE_MAX_GROUPS * 4;
     A.smem_bytes = (off + 15) / 16 * 16;
-    KQ_CUDA(ctx, cudaFuncSetAttribute(k_hash_aggregate, cudaFuncAttributeMaxDynamicSharedMemorySize, A.smem_bytes));
-    int bps = 1;
-    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&bps, k_hash_aggregate, THREADS, A.smem_bytes);
-    if (bps < 1) bps = 1;
-    int grid = (int)std::min<int64_t>(A.ntiles, (int64_t)ctx->sm_count * bps);
+    const std::string gen = "namespace kq {\n" + stage_defs + "struct Q {\n    template <class Sink> static __device__ __forceinline__ void eval(const QArgs& q, RowCtx& rc, Sink& sink) {\n" +
+                            eval_body + "    }\n};\n}  // namespace kq\n";
+    const std::string defines = "#define KQ_R " + std::to_string(AGG_R) + "\n#define KQ_WARPS " + std::to_string(AGG_WARPS) + "\n";
+    void* kernel = nullptr;
+    KQ_RET(kq_jit_kernel(ctx, defines, gen, KQ_SKEL_AGG, "kq_hash_aggregate", A.smem_bytes, &kernel));
+    int grid = (int)std::min<int64_t>(A.ntiles, (int64_t)ctx->sm_count);
     // rows that may still create groups after a block has decided to continue: one tile per resident
     // block plus its front end
     const uint64_t margin = (uint64_t)grid * ((uint64_t)A.sp.nstages * TILE + FE_MAX_GROUPS);
@@ -771,8 +427,9 @@ int kq_hashagg_update(kq_ctx* ctx, kq_hashagg* h, kq_batch* input) {
         A.tile_begin = tile_begin;
         A.stop_threshold = unthrottled ? ~0ULL : h->capacity / 2;
         KQ_CUDA(ctx, cudaMemsetAsync(h->d_counters + 1, 0, 8, ctx->stream));
-        k_hash_aggregate<<<grid, THREADS, A.smem_bytes, ctx->stream>>>(A);
-        KQ_RET(launch_check(ctx, "k_hash_aggregate"));
+        void* kargs[] = {&A};
+        KQ_CUDA(ctx, cudaLaunchKernel(kernel, dim3(grid), dim3(THREADS), kargs, (size_t)A.smem_bytes, ctx->stream));
+        ctx->launches++;
         uint64_t c[2];
         KQ_RET(kq_read_u64(ctx, h->d_counters, 2, c));
         h->ngroups_host = (int64_t)c[0];

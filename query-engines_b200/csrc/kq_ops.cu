@@ -1,354 +1,22 @@
-// kq_ops.cu — ProjectionExec, FilterExec and the fused filter+project kernel.
-//
-//   k_project         ProjectionExec.execute for one batch (Main.kt:589-594): every expression of the
-//                     projection evaluated in one pass, one 128-bit store per pair of output rows.
-//   k_filter_project  FilterExec (absent from the reference) fused with the
-//                     projection above it: predicate -> warp ballot/popc ranks -> ordered cross-block
-//                     prefix (decoupled look-back) -> compacted stores, all in a single pass over the
-//                     input (algorithmic bytes only: each input column read once, each output row
-//                     written once).
+// kq_ops.cu — host side of ProjectionExec, FilterExec and the fused filter+project operator, plus the
+// gather kernels for pass-through columns. The streaming kernels themselves live in kq_k_ops.cuh and
+// are specialised per query shape at run time (kq_codegen.cu -> kq_jit.cu).
 #include <algorithm>
 #include <cstring>
 
-#define KQ_R 4      // rows per thread in the streaming kernels
-#include "kq_compile.h"
-#include "kq_pipe.cuh"
+#include "kq_codegen.h"
 #include "kq_scan.cuh"
 
 using namespace kq;
 
 namespace {
 
-struct DOut {
-    void* data;
-    uint32_t* validity;
-    int32_t type;
-    int32_t _pad;
-};
-
-struct OpArgs {
-    Program prog;
-    int64_t n, ntiles;
-    int32_t sel_end;          // instructions [0, sel_end) evaluate the predicate and end in O_SET_SEL
-    int32_t nout;
-    DOut outs[MAX_OUT];
-    unsigned long long* tile_desc;
-    unsigned int* ticket;
-    unsigned long long* out_count;
-    int32_t* selvec;
-    uint32_t* err;
-    StagePlan sp;
-};
-
-// One CTA per SM: 15 consumer warps evaluate 4 rows per thread (thread-level parallelism keeps the
-// issue slots busy while each warp walks its dependent dispatch chain), one service warp streams
-// tiles in with TMA bulk copies (and, in the filter kernel, resolves the cross-block prefix).
-// 512 threads -> 128 registers each; bytes in flight come from the stage ring, not from occupancy.
-constexpr int WARPS = 15;
-constexpr int BLOCK = WARPS * 32;
-constexpr int TILE = WARPS * WARP_ROWS;     // 1920 rows
-constexpr int SERVICE_WARP = WARPS;
-constexpr int THREADS = BLOCK + 32;
-
-struct SinkBase {
-    __device__ __forceinline__ void set_sel(const uint64_t (&)[R], uint32_t, RowCtx&) {}
-    __device__ __forceinline__ void emit(int, const uint64_t (&)[R], uint32_t, RowCtx&) {}
-    __device__ __forceinline__ void set_key(int, bool, const uint64_t (&)[R], uint32_t, RowCtx&) {}
-    __device__ __forceinline__ void set_in(int, bool, const uint64_t (&)[R], uint32_t, RowCtx&) {}
-};
-
-// write the 64 row bits of chunk j (rows warp_base + 64j ...) of a bit-packed buffer
-__device__ __forceinline__ void store_chunk_bits(uint32_t* bits, const RowCtx& rc, int j, uint32_t m) {
-    uint32_t b0 = __ballot_sync(0xffffffffu, (m >> (2 * j)) & 1u);
-    uint32_t b1 = __ballot_sync(0xffffffffu, (m >> (2 * j + 1)) & 1u);
-    int64_t chunk_base = rc.warp_base + j * 64;
-    if (rc.lane == 0 && chunk_base < rc.n) {
-        uint2 w = interleave_ballots(b0, b1);
-        *reinterpret_cast<uint2*>(bits + (chunk_base >> 5)) = w;
-    }
-}
-
-struct ProjectSink : SinkBase {
-    const DOut* outs;
-    __device__ __forceinline__ void emit(int k, const uint64_t (&v)[R], uint32_t ok, RowCtx& rc) {
-        const DOut o = outs[k];
-        if (o.type == KQ_BOOL) {
-            const uint32_t m = (uint32_t)v[0] & rc.inr;      // Bool values are truth masks
-#pragma unroll
-            for (int j = 0; j < NCHUNK; j++) store_chunk_bits(reinterpret_cast<uint32_t*>(o.data), rc, j, m);
-        } else if (o.type == KQ_DATE32 || o.type == KQ_I32) {
-#pragma unroll
-            for (int j = 0; j < NCHUNK; j++) {
-                int64_t r0 = rc.row0(j);
-                if (rc.full || r0 < rc.n) stg_v2(reinterpret_cast<uint2*>(o.data) + (r0 >> 1), make_uint2((uint32_t)v[2 * j], (uint32_t)v[2 * j + 1]));
-            }
-        } else {
-#pragma unroll
-            for (int j = 0; j < NCHUNK; j++) {
-                int64_t r0 = rc.row0(j);
-                if (rc.full || r0 < rc.n)
-                    stg_v4(reinterpret_cast<uint4*>(o.data) + (r0 >> 1),
-                           make_uint4((uint32_t)v[2 * j], (uint32_t)(v[2 * j] >> 32), (uint32_t)v[2 * j + 1], (uint32_t)(v[2 * j + 1] >> 32)));
-            }
-        }
-        if (o.validity) {
-#pragma unroll
-            for (int j = 0; j < NCHUNK; j++) store_chunk_bits(o.validity, rc, j, ok & rc.inr);
-        }
-    }
-};
-
-struct CompactSink : SinkBase {
-    const DOut* outs;
-    uint32_t sel;
-    int rank[R];
-    long long base;
-    __device__ __forceinline__ void set_sel(const uint64_t (&v)[R], uint32_t ok, RowCtx& rc) {
-        sel = (uint32_t)v[0] & ok & rc.inr;        // truth mask; TRUE only: a null predicate drops the row (rule E3)
-    }
-    __device__ __forceinline__ void emit(int k, const uint64_t (&v)[R], uint32_t ok, RowCtx&) {
-        const DOut o = outs[k];
-#pragma unroll
-        for (int r = 0; r < R; r++) {
-            if ((sel >> r) & 1u) {
-                long long pos = base + rank[r];
-                if (o.type == KQ_BOOL) {
-                    if ((v[0] >> r) & 1u) atomicOr(reinterpret_cast<uint32_t*>(o.data) + (pos >> 5), 1u << (pos & 31));
-                } else if (o.type == KQ_DATE32 || o.type == KQ_I32) {
-                    reinterpret_cast<uint32_t*>(o.data)[pos] = (uint32_t)v[r];
-                } else {
-                    reinterpret_cast<uint64_t*>(o.data)[pos] = v[r];
-                }
-                if (o.validity && ((ok >> r) & 1u)) atomicOr(o.validity + (pos >> 5), 1u << (pos & 31));
-            }
-        }
-    }
-};
-
-// ProjectionExec for one batch (Main.kt:589-594).
-__global__ void __launch_bounds__(THREADS, 1) k_project(const __grid_constant__ OpArgs A) {
-    extern __shared__ __align__(128) unsigned char stages[];
-    __shared__ uint64_t full[MAX_STAGES], empty[MAX_STAGES];
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int S = A.sp.nstages;
-    if (threadIdx.x == 0) {
-        for (int s = 0; s < S; s++) { mbar_init(&full[s], 1); mbar_init(&empty[s], WARPS); }
-        mbar_fence_init();
-    }
-    __syncthreads();
-    if (warp == SERVICE_WARP) {
-        if (lane == 0) {
-            int k = 0;
-            for (int64_t tile = blockIdx.x; tile < A.ntiles; tile += gridDim.x, k++) {
-                const int s = k % S;
-                mbar_wait(&empty[s], ((k / S) & 1) ^ 1);
-                stage_issue(A.sp, stages + (size_t)s * A.sp.stage_bytes, &full[s], tile, TILE, A.n);
-            }
-        }
-        return;
-    }
-    ProjectSink sink;
-    sink.outs = A.outs;
-    Vm st;
-    int k = 0;
-    for (int64_t tile = blockIdx.x; tile < A.ntiles; tile += gridDim.x, k++) {
-        const int s = k % S;
-        mbar_wait(&full[s], (k / S) & 1);
-        RowCtx rc;
-        rowctx_init(rc, tile, TILE, A.n, A.err, stages + (size_t)s * A.sp.stage_bytes);
-        run(A.prog, 0, A.prog.ninsn, st, rc, sink);
-        __syncwarp();
-        if (lane == 0) mbar_arrive(&empty[s]);
-    }
-}
-
-// FilterExec + ProjectionExec, single pass. Per tile k the consumer warps run step A (predicate ->
-// selection mask, ballot/popc ranks, per-warp totals) one tile AHEAD of step B (cross-block prefix,
-// projection, compacted stores); the tile's columns wait in their shared-memory stage in between.
-// The service warp turns the per-warp totals of a tile into its global exclusive prefix (decoupled
-// look-back over tile descriptors in HBM) while the consumers are busy with step A of the next
-// tile, so the L2 round trips of the look-back stay off the critical path; in between it keeps the
-// stage ring full (tickets are taken in look-back order).
-__global__ void __launch_bounds__(THREADS, 1) k_filter_project(const __grid_constant__ OpArgs A) {
-    extern __shared__ __align__(128) unsigned char stages[];
-    __shared__ uint64_t full[MAX_STAGES], empty[MAX_STAGES], agg_ready[MAX_STAGES], prefix_ready[MAX_STAGES];
-    __shared__ long long tile_of[MAX_STAGES];
-    __shared__ unsigned long long prefix[MAX_STAGES];
-    __shared__ int wtot[MAX_STAGES][WARPS];
-    __shared__ int tot[MAX_STAGES], arrived[MAX_STAGES];
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int S = A.sp.nstages;
-    if (threadIdx.x == 0) {
-        for (int s = 0; s < S; s++) {
-            mbar_init(&full[s], 1); mbar_init(&empty[s], WARPS);
-            mbar_init(&agg_ready[s], 1); mbar_init(&prefix_ready[s], 1);
-            tot[s] = 0; arrived[s] = 0;
-        }
-        mbar_fence_init();
-    }
-    __syncthreads();
-
-    if (warp == SERVICE_WARP) {
-        int kp = 0, kl = 0;                    // next tile slot to produce / to resolve
-        bool prod_done = false, lb_done = false;
-        // the next ticket is always requested one step early: the L2 round trip of the atomic overlaps
-        // the TMA issue and the look-back of the current step (ticket order = look-back order)
-        long long next_ticket = 0;
-        if (lane == 0) next_ticket = (long long)atomicAdd(A.ticket, 1u);
-        while (!prod_done || !lb_done) {
-            bool did = false;
-            // (1) start the descriptor loads of the tile waiting for its prefix
-            bool lb_pending = false; long long lb_tile = 0; int lb_s = 0;
-            unsigned long long d[4] = {0, 0, 0, 0};
-            if (!lb_done) {
-                lb_s = kl % S;
-                int go = 0;
-                if (lane == 0) go = mbar_test(&agg_ready[lb_s], (kl / S) & 1) ? 1 : 0;
-                go = __shfl_sync(0xffffffffu, go, 0);
-                if (go) {
-                    lb_tile = tile_of[lb_s];
-                    if (lb_tile >= A.ntiles) { lb_done = true; kl++; did = true; }
-                    else { lb_pending = true; lb_load(A.tile_desc, lb_tile - 1, d); }
-                }
-            }
-            // (2) keep the stage ring full
-            if (!prod_done) {
-                const int s = kp % S;
-                int go = 0;
-                if (lane == 0) go = mbar_test(&empty[s], ((kp / S) & 1) ^ 1) ? 1 : 0;
-                go = __shfl_sync(0xffffffffu, go, 0);
-                if (go) {
-                    int end = 0;
-                    if (lane == 0) {
-                        const long long tile = next_ticket;
-                        tile_of[s] = tile;
-                        if (tile >= A.ntiles) { mbar_arrive(&full[s]); end = 1; }
-                        else {
-                            next_ticket = (long long)atomicAdd(A.ticket, 1u);
-                            stage_issue(A.sp, stages + (size_t)s * A.sp.stage_bytes, &full[s], tile, TILE, A.n);
-                        }
-                    }
-                    end = __shfl_sync(0xffffffffu, end, 0);
-                    if (end) prod_done = true;
-                    kp++; did = true;
-                }
-            }
-            // (3) fold the descriptors; publish the inclusive prefix and hand the exclusive one to step B
-            if (lb_pending) {
-                unsigned long long excl = 0;
-                if (lb_finish(A.tile_desc, lb_tile, d, &excl)) {
-                    if (lane == 0) {
-                        const unsigned long long t = (unsigned long long)tot[lb_s];
-                        if (lb_tile > 0) A.tile_desc[lb_tile] = LB_INCL | (excl + t);
-                        prefix[lb_s] = excl;
-                        if (lb_tile == A.ntiles - 1) *A.out_count = excl + t;
-                        tot[lb_s] = 0; arrived[lb_s] = 0;      // consumers are done with them until the stage is reused
-                        mbar_arrive(&prefix_ready[lb_s]);
-                    }
-                    kl++; did = true;
-                }
-            }
-            if (!did) __nanosleep(40);
-        }
-        return;
-    }
-
-    CompactSink sink;
-    sink.outs = A.outs;
-    Vm st;
-    const uint32_t lt = (1u << lane) - 1u;
-    // ranks in row order (chunk, lane, pair element) from a selection mask: ballot + popc
-    auto ranks_of = [&](uint32_t sel, int (&rank)[R]) -> int {
-        int wt = 0;
-#pragma unroll
-        for (int j = 0; j < NCHUNK; j++) {
-            const uint32_t s0 = (sel >> (2 * j)) & 1u, s1 = (sel >> (2 * j + 1)) & 1u;
-            const uint32_t b0 = __ballot_sync(0xffffffffu, s0), b1 = __ballot_sync(0xffffffffu, s1);
-            const int below = __popc(b0 & lt) + __popc(b1 & lt);
-            rank[2 * j] = wt + below;
-            rank[2 * j + 1] = wt + below + (int)s0;
-            wt += __popc(b0) + __popc(b1);
-        }
-        return wt;
-    };
-    // Step A runs up to LOOKAHEAD tiles ahead of step B; a pending tile is remembered by its selection
-    // mask only (ranks are recomputed with ballots), so the look-back latency of tile k hides behind
-    // the predicate work of tiles k+1..k+LOOKAHEAD.
-    constexpr int LOOKAHEAD = 3;
-    uint32_t q_sel[LOOKAHEAD]; long long q_tile[LOOKAHEAD];
-#pragma unroll
-    for (int i = 0; i < LOOKAHEAD; i++) { q_sel[i] = 0; q_tile[i] = -1; }
-    const int D = min(LOOKAHEAD, S - 1);           // tiles in flight between A and B (S >= 2)
-    auto step_b = [&](int kb, uint32_t p_sel, long long p_tile) {
-        const int p_s = kb % S;
-        RowCtx rc;
-        rowctx_init(rc, p_tile, TILE, A.n, A.err, stages + (size_t)p_s * A.sp.stage_bytes);
-        rc.active = p_sel;        // projection errors only count on surviving rows (FilterExec runs first)
-        sink.sel = p_sel;
-        ranks_of(p_sel, sink.rank);
-        mbar_wait(&prefix_ready[p_s], (kb / S) & 1);
-        int woff = 0;
-#pragma unroll
-        for (int w = 0; w < WARPS; w++) { int x = wtot[p_s][w]; if (w < warp) woff += x; }
-        sink.base = (long long)prefix[p_s] + woff;
-        if (A.selvec) {
-#pragma unroll
-            for (int r = 0; r < R; r++)
-                if ((p_sel >> r) & 1u) A.selvec[sink.base + sink.rank[r]] = (int32_t)(rc.row0(r >> 1) + (r & 1));
-        }
-        run(A.prog, A.sel_end, A.prog.ninsn, st, rc, sink);
-        __syncwarp();
-        if (lane == 0) mbar_arrive(&empty[p_s]);
-    };
-    int k = 0;
-    for (;; k++) {
-        const int s = k % S;
-        mbar_wait(&full[s], (k / S) & 1);
-        const long long tile = tile_of[s];
-        if (tile >= A.ntiles) {
-            if (warp == 0 && lane == 0) mbar_arrive(&agg_ready[s]);     // end sentinel: wake the service warp
-            break;
-        }
-        // ---- step A(k): predicate -> selection mask -> warp total -> tile aggregate
-        RowCtx rc;
-        rowctx_init(rc, tile, TILE, A.n, A.err, stages + (size_t)s * A.sp.stage_bytes);
-        sink.sel = 0;
-        run(A.prog, 0, A.sel_end, st, rc, sink);
-        const uint32_t c_sel = sink.sel;
-        int wt = __popc(c_sel);
-#pragma unroll
-        for (int o = 16; o; o >>= 1) wt += __shfl_xor_sync(0xffffffffu, wt, o);
-        if (lane == 0) {
-            wtot[s][warp] = wt;
-            atomicAdd(&tot[s], wt);
-            __threadfence_block();
-            if (atomicAdd(&arrived[s], 1) == WARPS - 1) {
-                // last warp of the tile: publish the aggregate right away so that no other block's
-                // look-back ever waits on this block's service warp
-                __threadfence_block();
-                const unsigned long long t = (unsigned long long)atomicAdd(&tot[s], 0);
-                A.tile_desc[tile] = (tile == 0 ? LB_INCL : LB_PART) | t;
-                mbar_arrive(&agg_ready[s]);
-            }
-        }
-        __syncwarp();
-        // ---- step B(k - D) if that tile exists; then remember tile k in the queue slot k % LOOKAHEAD
-        if (k >= D) {
-#pragma unroll
-            for (int i = 0; i < LOOKAHEAD; i++)
-                if (i == (k - D) % LOOKAHEAD) step_b(k - D, q_sel[i], q_tile[i]);
-        }
-#pragma unroll
-        for (int i = 0; i < LOOKAHEAD; i++)
-            if (i == k % LOOKAHEAD) { q_sel[i] = c_sel; q_tile[i] = tile; }
-    }
-    // drain: tiles k-D .. k-1 still owe their step B
-    for (int kb = max(0, k - D); kb < k; kb++) {
-#pragma unroll
-        for (int i = 0; i < LOOKAHEAD; i++)
-            if (i == kb % LOOKAHEAD) step_b(kb, q_sel[i], q_tile[i]);
-    }
-}
+// Tile geometry of the streaming kernels (compiled into the specialised kernels as KQ_R / KQ_WARPS):
+// 15 consumer warps x 32 lanes x 4 rows = 1920 rows per tile, plus one service warp.
+constexpr int OPS_R = 4;
+constexpr int OPS_WARPS = 15;
+constexpr int TILE = OPS_WARPS * 32 * OPS_R;
+constexpr int THREADS = OPS_WARPS * 32 + 32;
 
 // ---- gathers by selection vector (Utf8 pass-through columns and kq_filter) --------------------------------------
 template <typename T>
@@ -394,12 +62,6 @@ __global__ void k_utf8_gather_bytes(const int32_t* __restrict__ in_off, const ui
 int stage_budget(kq_ctx* ctx, int ctas) {
     return (ctx->max_smem_optin + 1024) / ctas - 1024 - 2048;   // 1 KB/CTA reserved by the driver, 2 KB static
 }
-int blocks_per_sm(const void* fn, int threads, int smem) {
-    int nb = 1;
-    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, fn, threads, smem) != cudaSuccess || nb < 1) nb = 1;
-    return nb;
-}
-
 int launch_check(kq_ctx* ctx, const char* what) {
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) return kq_cuda_fail(ctx, e, what);
@@ -458,6 +120,69 @@ int gather_column(kq_ctx* ctx, kq_col* in, const int32_t* sel, kq_lazy_count* la
     return KQ_OK;
 }
 
+// Everything about an operator launch that depends on the query SHAPE only: how each output is produced,
+// the generated source and the stage plan. No CUDA calls (kq_explain_* runs it without a device).
+struct OpsPlan {
+    std::vector<int> mode;            // per output: 0 = fused kernel output, 1 = alias (rule R4), 2 = gather by selection vector
+    std::vector<int> out_type;
+    std::vector<char> out_nullable;
+    int nvm = 0;
+    std::string defines, gen;
+    const char* entry = "";
+    StagePlan sp;
+    int smem = 0;
+};
+
+int plan_ops(kq_ctx* ctx, KqCodegen& cg, kq_expr* pred, const std::vector<kq_expr*>& ex, int smem_optin, OpsPlan* P) {
+    std::string pred_body, proj_body;
+    int st;
+    if (pred) {
+        KqVal p;
+        KQ_RET(cg.value(pred, &p));
+        if (p.type != KQ_BOOL) return kq_fail(ctx, KQ_ERR_ILLEGAL_STATE, "filter predicate is not Bool");
+        cg.line("return " + p.v + (p.nullable() ? " & " + p.ok : std::string()) + ";");     // TRUE only (rule E3)
+        pred_body = cg.take_body();
+    }
+    // classify outputs: gather (Utf8 pass-through below a filter, or any column of kq_filter with
+    // too many fused outputs), alias (bare column without a filter, rule R4), or fused kernel output.
+    P->mode.assign(ex.size(), 0); P->out_type.assign(ex.size(), 0); P->out_nullable.assign(ex.size(), 0);
+    int nvm = 0;
+    for (size_t k = 0; k < ex.size(); k++) {
+        int bc = KqCodegen::bare_column(ex[k]);
+        int t; bool nl;
+        KQ_RET(cg.infer(ex[k], &t, &nl));
+        P->out_type[k] = t; P->out_nullable[k] = nl;
+        if (bc >= 0 && !pred) P->mode[k] = 1;
+        else if (bc >= 0 && (t == KQ_UTF8 || nvm >= MAX_OUT)) P->mode[k] = 2;
+        else {
+            if (t == KQ_UTF8) return kq_fail(ctx, KQ_ERR_UNSUPPORTED, "expressions cannot produce Utf8 values (only column pass-through)");
+            if (nvm >= MAX_OUT) return kq_fail(ctx, KQ_ERR_UNSUPPORTED, "more than %d computed outputs in one kernel", MAX_OUT);
+            KqVal v;
+            if ((st = cg.value(ex[k], &v)) != KQ_OK) return st;
+            P->out_type[k] = v.type; P->out_nullable[k] = v.nullable();
+            const std::string nul = v.nullable() ? "true" : "false";
+            if (v.type == KQ_BOOL) cg.line("sink.emit_bool(" + std::to_string(nvm) + ", " + v.v + ", " + v.okx() + ", " + nul + ", rc);");
+            else {
+                const KqVal a = cg.as_array(v);
+                cg.line("sink.template emit<" + std::to_string(v.type) + ">(" + std::to_string(nvm) + ", " + a.v + ", " + a.okx() + ", " + nul + ", rc);");
+            }
+            nvm++;
+        }
+    }
+    proj_body = cg.take_body();
+    P->nvm = nvm;
+    const std::string stage_defs = cg.plan_stages((smem_optin + 1024) - 1024 - 2048, pred ? 3 : 2, TILE, &P->sp);   // 1 KB/CTA driver-reserved, 2 KB static
+    P->smem = P->sp.nstages * P->sp.stage_bytes;
+    P->gen = "namespace kq {\n" + stage_defs + "struct Q {\n";
+    if (pred) P->gen += "    static __device__ __forceinline__ uint32_t pred(const QArgs& q, const RowCtx& rc) {\n" + pred_body + "    }\n";
+    P->gen += "    template <class Sink> static __device__ __forceinline__ void project(const QArgs& q, const RowCtx& rc, const Sink& sink) {\n" + proj_body + "    }\n";
+    P->gen += "};\n}  // namespace kq\n";
+    P->defines = "#define KQ_R " + std::to_string(OPS_R) + "\n#define KQ_WARPS " + std::to_string(OPS_WARPS) + "\n" +
+                 (pred ? "#define KQ_KERNEL_FILTER\n" : "#define KQ_KERNEL_PROJECT\n");
+    P->entry = pred ? "kq_filter_project" : "kq_project";
+    return KQ_OK;
+}
+
 // Shared implementation of kq_project / kq_filter_project / kq_filter / kq_expr_evaluate.
 int run_operator(kq_ctx* ctx, kq_expr* pred, kq_expr* const* exprs, int nexprs, kq_batch* input, bool all_columns,
                  kq_batch** out, kq_col** selection) {
@@ -472,103 +197,87 @@ int run_operator(kq_ctx* ctx, kq_expr* pred, kq_expr* const* exprs, int nexprs, 
     if (all_columns) for (int i = 0; i < (int)input->cols.size(); i++) { owned.push_back(kq_expr_column(i)); ex.push_back(owned.back()); }
     auto cleanup = [&]() { for (kq_expr* e : owned) kq_expr_free(e); };
 
-    KqCompiler cc;
-    int st = cc.begin(ctx, input);
+    KqCodegen cg;
+    OpsPlan P;
+    int st = cg.begin(ctx, input);
+    if (st == KQ_OK) st = plan_ops(ctx, cg, pred, ex, ctx->max_smem_optin, &P);
     std::vector<kq_col*> outs(ex.size(), nullptr);
-    auto fail = [&](int s) { for (kq_col* c : outs) kq_column_free(c); cleanup(); return s; };
+    kq_lazy_count* lazy = nullptr;
+    kq_col* selcol = nullptr;
+    auto fail = [&](int s) {
+        for (kq_col* c : outs) kq_column_free(c);
+        kq_column_free(selcol);
+        if (lazy) kq_lazy_release(ctx, lazy);
+        cleanup();
+        return s;
+    };
     if (st != KQ_OK) return fail(st);
 
     OpArgs A;
     memset(&A, 0, sizeof A);
     A.n = n; A.ntiles = (n + TILE - 1) / TILE; A.err = ctx->d_err;
-    kq_lazy_count* lazy = nullptr;
+    A.q = cg.args; A.sp = P.sp;
     if (pred) {
-        int t; bool nl;
-        if ((st = cc.value(pred, &t, &nl)) != KQ_OK) return fail(st);
-        if (t != KQ_BOOL) return fail(kq_fail(ctx, KQ_ERR_ILLEGAL_STATE, "filter predicate is not Bool"));
-        if ((st = cc.sink(O_SET_SEL, 0)) != KQ_OK) return fail(st);
-        A.sel_end = cc.pc();
         lazy = kq_lazy_new(ctx);
         if (!lazy) return fail(kq_fail(ctx, KQ_ERR_OUT_OF_MEMORY, "lazy count"));
     }
-    auto fail2 = [&](int s) { if (lazy) kq_lazy_release(ctx, lazy); return fail(s); };
-
-    // classify outputs: gather (Utf8 pass-through below a filter, or any column of kq_filter with
-    // too many fused outputs), alias (bare column without a filter, rule R4), or fused VM output.
-    std::vector<int> mode(ex.size(), 0);   // 0 = VM, 1 = alias, 2 = gather by selection vector
     int nvm = 0;
     for (size_t k = 0; k < ex.size(); k++) {
-        int bc = KqCompiler::bare_column(ex[k]);
-        int t; bool nl;
-        if ((st = cc.infer(ex[k], &t, &nl)) != KQ_OK) return fail2(st);
-        if (bc >= 0 && !pred) mode[k] = 1;
-        else if (bc >= 0 && (t == KQ_UTF8 || nvm >= MAX_OUT)) mode[k] = 2;
-        else {
-            if (t == KQ_UTF8) return fail2(kq_fail(ctx, KQ_ERR_UNSUPPORTED, "expressions cannot produce Utf8 values (only column pass-through)"));
-            if (nvm >= MAX_OUT) return fail2(kq_fail(ctx, KQ_ERR_UNSUPPORTED, "more than %d computed outputs in one kernel", MAX_OUT));
-            mode[k] = 0;
-            int t2; bool n2;
-            if ((st = cc.value(ex[k], &t2, &n2)) != KQ_OK) return fail2(st);
-            kq_col* c = nullptr;
-            if ((st = kq_col_new(ctx, t2, n, n2, 0, &c)) != KQ_OK) return fail2(st);
-            outs[k] = c;
-            if (pred) {
-                c->n = -1; c->lazy = lazy; lazy->rc.fetch_add(1);
-                if (c->validity) cudaMemsetAsync(c->validity, 0, (size_t)((n + 63) / 64) * 8, ctx->stream);
-                if (t2 == KQ_BOOL) cudaMemsetAsync(c->data, 0, (size_t)((n + 63) / 64) * 8, ctx->stream);
-            }
-            A.outs[nvm].data = c->data; A.outs[nvm].validity = c->validity; A.outs[nvm].type = t2;
-            if ((st = cc.sink(O_EMIT, nvm)) != KQ_OK) return fail2(st);
-            nvm++;
+        if (P.mode[k] != 0) continue;
+        kq_col* c = nullptr;
+        if ((st = kq_col_new(ctx, P.out_type[k], n, P.out_nullable[k], 0, &c)) != KQ_OK) return fail(st);
+        outs[k] = c;
+        if (pred) {
+            c->n = -1; c->lazy = lazy; lazy->rc.fetch_add(1);
+            if (c->validity) cudaMemsetAsync(c->validity, 0, (size_t)((n + 63) / 64) * 8, ctx->stream);
+            if (P.out_type[k] == KQ_BOOL) cudaMemsetAsync(c->data, 0, (size_t)((n + 63) / 64) * 8, ctx->stream);
         }
+        A.outs[nvm].data = c->data; A.outs[nvm].validity = c->validity;
+        nvm++;
     }
-    A.nout = nvm;
-    cc.plan_stages(stage_budget(ctx, 1), pred ? 3 : 2, TILE, &A.sp);
-    A.prog = cc.prog;
-    const int smem = A.sp.nstages * A.sp.stage_bytes;
 
     bool need_sel = selection != nullptr;
-    for (int m : mode) need_sel |= (m == 2);
-    kq_col* selcol = nullptr;
+    for (int m : P.mode) need_sel |= (m == 2);
     if (pred && need_sel) {
-        if ((st = kq_col_new(ctx, KQ_I32, n, false, 0, &selcol)) != KQ_OK) return fail2(st);
+        if ((st = kq_col_new(ctx, KQ_I32, n, false, 0, &selcol)) != KQ_OK) return fail(st);
         selcol->n = -1; selcol->lazy = lazy; lazy->rc.fetch_add(1);
         A.selvec = (int32_t*)selcol->data;
     }
-    auto fail3 = [&](int s) { kq_column_free(selcol); return fail2(s); };
+
+    const bool launch = n > 0 && (pred || P.nvm > 0);
+    void* kernel = nullptr;
+    if (launch && (st = kq_jit_kernel(ctx, P.defines, P.gen, KQ_SKEL_OPS, P.entry, P.smem, &kernel)) != KQ_OK) return fail(st);
+    void* kargs[] = {&A};
+    const int grid = (int)std::min<int64_t>(A.ntiles, (int64_t)ctx->sm_count);
 
     if (pred) {
         unsigned long long* scratch = nullptr;     // [0]: ticket, [2..]: tile descriptors
-        if ((st = kq_dev_alloc(ctx, (size_t)(A.ntiles + 2) * 8, (void**)&scratch)) != KQ_OK) return fail3(st);
+        if ((st = kq_dev_alloc(ctx, (size_t)(A.ntiles + 2) * 8, (void**)&scratch)) != KQ_OK) return fail(st);
         cudaMemsetAsync(scratch, 0, (size_t)(A.ntiles + 2) * 8, ctx->stream);
         A.ticket = (unsigned int*)scratch;
         A.tile_desc = scratch + 2;
         A.out_count = lazy->d_slot;
-        if (n > 0) {
-            cudaFuncSetAttribute(k_filter_project, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
-            int bps = blocks_per_sm((const void*)k_filter_project, THREADS, smem);
-            int grid = (int)std::min<int64_t>(A.ntiles, (int64_t)ctx->sm_count * bps);
-            k_filter_project<<<grid, THREADS, smem, ctx->stream>>>(A);
-            if ((st = launch_check(ctx, "k_filter_project")) != KQ_OK) { kq_dev_free(ctx, scratch); return fail3(st); }
+        if (launch) {
+            cudaError_t e = cudaLaunchKernel(kernel, dim3(grid), dim3(THREADS), kargs, (size_t)P.smem, ctx->stream);
+            if (e != cudaSuccess) { kq_dev_free(ctx, scratch); return fail(kq_cuda_fail(ctx, e, "kq_filter_project")); }
+            ctx->launches++;
         }
         kq_dev_free(ctx, scratch);
         for (size_t k = 0; k < ex.size(); k++) {
-            if (mode[k] != 2) continue;
-            kq_col* in = input->cols[(size_t)KqCompiler::bare_column(ex[k])];
-            if ((st = gather_column(ctx, in, (const int32_t*)selcol->data, lazy, n, &outs[k])) != KQ_OK) return fail3(st);
+            if (P.mode[k] != 2) continue;
+            kq_col* in = input->cols[(size_t)KqCodegen::bare_column(ex[k])];
+            if ((st = gather_column(ctx, in, (const int32_t*)selcol->data, lazy, n, &outs[k])) != KQ_OK) return fail(st);
         }
         // the row count travels back asynchronously; it is only waited for when somebody asks
         cudaMemcpyAsync(lazy->h_slot, lazy->d_slot, 8, cudaMemcpyDeviceToHost, ctx->stream);
         cudaEventRecord(lazy->ev, ctx->stream);
     } else {
         for (size_t k = 0; k < ex.size(); k++)
-            if (mode[k] == 1) { outs[k] = input->cols[(size_t)KqCompiler::bare_column(ex[k])]; outs[k]->rc.fetch_add(1); }
-        if (nvm > 0 && n > 0) {
-            cudaFuncSetAttribute(k_project, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
-            int bps = blocks_per_sm((const void*)k_project, THREADS, smem);
-            int grid = (int)std::min<int64_t>(A.ntiles, (int64_t)ctx->sm_count * bps);
-            k_project<<<grid, THREADS, smem, ctx->stream>>>(A);
-            if ((st = launch_check(ctx, "k_project")) != KQ_OK) return fail3(st);
+            if (P.mode[k] == 1) { outs[k] = input->cols[(size_t)KqCodegen::bare_column(ex[k])]; outs[k]->rc.fetch_add(1); }
+        if (launch) {
+            cudaError_t e = cudaLaunchKernel(kernel, dim3(grid), dim3(THREADS), kargs, (size_t)P.smem, ctx->stream);
+            if (e != cudaSuccess) return fail(kq_cuda_fail(ctx, e, "kq_project"));
+            ctx->launches++;
         }
     }
 
@@ -580,6 +289,26 @@ int run_operator(kq_ctx* ctx, kq_expr* pred, kq_expr* const* exprs, int nexprs, 
     if (selection) *selection = selcol; else kq_column_free(selcol);
     cleanup();
     return KQ_OK;
+}
+
+// A batch of columns that exist as a schema only (types + nullability), for kq_explain_*.
+struct SchemaBatch {
+    kq_batch batch;
+    std::vector<kq_col> cols;
+    SchemaBatch(int ncols, const int* types, const int* nullable) : cols((size_t)ncols) {
+        for (int i = 0; i < ncols; i++) {
+            cols[(size_t)i].type = types[i];
+            cols[(size_t)i].validity = (nullable && nullable[i]) ? reinterpret_cast<uint32_t*>(0x100) : nullptr;   // never dereferenced
+            batch.cols.push_back(&cols[(size_t)i]);
+        }
+    }
+};
+
+void copy_out(const std::string& s, char* dst, size_t cap) {
+    if (!dst || cap == 0) return;
+    size_t m = std::min(cap - 1, s.size());
+    memcpy(dst, s.data(), m);
+    dst[m] = 0;
 }
 
 }  // namespace
@@ -609,6 +338,21 @@ int kq_expr_evaluate(kq_ctx* ctx, kq_expr* e, kq_batch* input, kq_col** out) {
     (*out)->rc.fetch_add(1);
     kq_batch_free(b);
     return KQ_OK;
+}
+
+int kq_explain_filter_project(kq_expr* pred, kq_expr* const* exprs, int nexprs, int ncols, const int* types, const int* nullable,
+                              int compile, char* source, size_t source_cap) {
+    if (ncols < 0 || nexprs < 0 || (ncols > 0 && !types)) return KQ_ERR_ILLEGAL_ARGUMENT;
+    kq_ctx fake;
+    SchemaBatch sb(ncols, types, nullable);
+    KqCodegen cg;
+    OpsPlan P;
+    std::vector<kq_expr*> ex(exprs, exprs + nexprs);
+    int st = cg.begin(&fake, &sb.batch);
+    if (st == KQ_OK) st = plan_ops(&fake, cg, pred, ex, 232448, &P);
+    if (st == KQ_OK && compile) st = kq_jit_compile_only(&fake, P.defines, P.gen, KQ_SKEL_OPS);
+    copy_out(st == KQ_OK ? P.defines + P.gen : fake.last_error, source, source_cap);
+    return st;
 }
 
 int kq_filter_project_host(kq_ctx* ctx, kq_expr* pred, kq_expr* const* exprs, int nexprs, int ncols, const int* types,

@@ -8,29 +8,13 @@
 // this is what lets an HBM-bound integer/byte path approach the copy roofline on B200.
 #pragma once
 
+#ifndef __CUDACC_RTC__
 #include <cuda_runtime.h>
 #include <stdint.h>
+#endif
+#include "kq_args.h"
 
 namespace kq {
-
-constexpr int MAX_STAGE_BUFS = 24;
-constexpr int MAX_STAGES = 8;
-
-enum StageKind : int32_t { SK_W8 = 0, SK_W4 = 1, SK_W4_PLUS1 = 2, SK_BIT = 3 };
-
-struct StageBuf {
-    const char* g;        // global base of the buffer
-    int32_t soff;         // byte offset inside a stage (128-byte aligned)
-    int32_t kind;         // StageKind
-};
-
-struct StagePlan {
-    int32_t nbuf;
-    int32_t stage_bytes;  // multiple of 128
-    int32_t nstages;
-    int32_t _pad;
-    StageBuf buf[MAX_STAGE_BUFS];
-};
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 

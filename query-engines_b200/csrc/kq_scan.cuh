@@ -5,8 +5,10 @@
 // is already running: the look-back spin cannot deadlock regardless of residency.
 #pragma once
 
+#ifndef __CUDACC_RTC__
 #include <cuda_runtime.h>
 #include <stdint.h>
+#endif
 
 namespace kq {
 

@@ -96,6 +96,8 @@ SYMBOLS = {
     "kq_filter_project": (C.c_int, [_P, _P, _PP, C.c_int, _P, _PP]),
     "kq_filter_project_host": (C.c_int, [_P, _P, _PP, C.c_int, C.c_int, C.POINTER(C.c_int), _PP, _PP, C.c_int64,
                                           _PP, _PP, _I64P]),
+    "kq_explain_filter_project": (C.c_int, [_P, _PP, C.c_int, C.c_int, C.POINTER(C.c_int), C.POINTER(C.c_int), C.c_int,
+                                             C.c_char_p, C.c_size_t]),
     "kq_hashagg_create": (C.c_int, [_P, _P, _PP, C.c_int, C.POINTER(C.c_int), _PP, C.c_int, C.c_int64, _PP]),
     "kq_hashagg_update": (C.c_int, [_P, _P, _P]),
     "kq_hashagg_finalize": (C.c_int, [_P, _P, _PP]),
@@ -375,7 +377,41 @@ def make_specs(specs):
     return arr, keep
 
 
-class Engine:
+class Exprs:
+    """Expression factory (pure host objects: works without a device). Mirrors the reference's physical
+    expressions: col = ColumnExpression (Main.kt:452-460), cast = CastExpression (Main.kt:772-805),
+    lit_* / binary = the Literal/Binary extensions."""
+
+    # expressions
+    def col(self, i): return Expr(self, lib().kq_expr_column(i))
+    def lit_f64(self, v): return Expr(self, lib().kq_expr_literal_f64(float(v)))
+    def lit_i64(self, v): return Expr(self, lib().kq_expr_literal_i64(int(v)))
+    def lit_bool(self, v): return Expr(self, lib().kq_expr_literal_bool(int(bool(v))))
+    def lit_date32(self, v): return Expr(self, lib().kq_expr_literal_date32(int(v)))
+
+    def lit_utf8(self, s):
+        b = s.encode("utf-8") if isinstance(s, str) else bytes(s)
+        return Expr(self, lib().kq_expr_literal_utf8(b, len(b)))
+
+    def lit_null(self, t): return Expr(self, lib().kq_expr_literal_null(t))
+    def binary(self, op, l, r): return Expr(self, lib().kq_expr_binary(OPS[op], l.h, r.h), (l, r))
+    def cast(self, e, t): return Expr(self, lib().kq_expr_cast(e.h, t), (e,))
+
+    def explain_filter_project(self, pred, exprs, types, nullable=None, compile=True) -> str:
+        """CUDA source of the query-specific part of the kernel for this shape (kq_explain_filter_project)."""
+        n = len(types)
+        t = (C.c_int * n)(*types)
+        nl = (C.c_int * n)(*(nullable or [0] * n))
+        buf = C.create_string_buffer(1 << 18)
+        st = lib().kq_explain_filter_project(pred.h if pred is not None else None, _expr_array(exprs), len(exprs), n, t, nl,
+                                             int(bool(compile)), buf, len(buf))
+        text = buf.value.decode("utf-8", "replace")
+        if st != 0:
+            raise KqError(st, text)
+        return text
+
+
+class Engine(Exprs):
     """The operator vocabulary bound to one Context (same method names as oracle/oracle.py)."""
 
     OPS, AGGS = OPS, AGGS
@@ -396,21 +432,6 @@ class Engine:
 
         self.RecordBatch = _RB
         self.KqError = KqError
-
-    # expressions
-    def col(self, i): return Expr(self, lib().kq_expr_column(i))
-    def lit_f64(self, v): return Expr(self, lib().kq_expr_literal_f64(float(v)))
-    def lit_i64(self, v): return Expr(self, lib().kq_expr_literal_i64(int(v)))
-    def lit_bool(self, v): return Expr(self, lib().kq_expr_literal_bool(int(bool(v))))
-    def lit_date32(self, v): return Expr(self, lib().kq_expr_literal_date32(int(v)))
-
-    def lit_utf8(self, s):
-        b = s.encode("utf-8") if isinstance(s, str) else bytes(s)
-        return Expr(self, lib().kq_expr_literal_utf8(b, len(b)))
-
-    def lit_null(self, t): return Expr(self, lib().kq_expr_literal_null(t))
-    def binary(self, op, l, r): return Expr(self, lib().kq_expr_binary(OPS[op], l.h, r.h), (l, r))
-    def cast(self, e, t): return Expr(self, lib().kq_expr_cast(e.h, t), (e,))
 
     # operators
     def project(self, exprs, batch: RecordBatch) -> RecordBatch:
