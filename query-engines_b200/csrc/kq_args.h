@@ -71,6 +71,7 @@ struct OpArgs {
     unsigned int* ticket;
     unsigned long long* out_count;
     int32_t* selvec;
+    unsigned long long* trace;      // debugging (KQ_TRACE builds): 8 timestamps per tile
     uint32_t* err;
     StagePlan sp;
 };

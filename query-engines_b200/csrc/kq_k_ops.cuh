@@ -22,8 +22,23 @@ namespace kq {
 constexpr int WARPS = KQ_WARPS;
 constexpr int BLOCK = WARPS * 32;
 constexpr int TILE = WARPS * WARP_ROWS;
-constexpr int SERVICE_WARP = WARPS;
-constexpr int THREADS = BLOCK + 32;
+// Service warps come FIRST in the CTA: the SM's warp arbiter favours high warp ids, so polling service
+// warps never take issue slots from the consumer warps that share their scheduler.
+constexpr int PRODUCER_WARP = 0;             // TMA producer
+#ifdef KQ_KERNEL_FILTER
+constexpr int LOOKBACK_WARP = 1;             // cross-block prefix resolver
+constexpr int NSERVICE = 2;
+#else
+constexpr int NSERVICE = 1;
+#endif
+constexpr int THREADS = BLOCK + 32 * NSERVICE;
+
+#ifdef KQ_TRACE
+__device__ __forceinline__ unsigned long long gtime() { unsigned long long t; asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t)); return t; }
+#define KQ_TR(tile, slot) do { if (A.trace) A.trace[(tile) * 8 + (slot)] = gtime(); } while (0)
+#else
+#define KQ_TR(tile, slot) do { } while (0)
+#endif
 
 // ---- sinks: where the generated projection code hands its results --------------------------------------------------
 struct ProjectSink {
@@ -62,50 +77,93 @@ struct ProjectSink {
     }
 };
 
-struct CompactSink {
-    const DOut* outs;
+#ifdef KQ_KERNEL_FILTER
+// FilterExec: the projection of the surviving rows of a tile is parked, already compacted, in a
+// warp-private shared-memory ring until the tile's global output offset is known. A tile takes only
+// as many ring rows as it has survivors, so at low selectivity many tiles can be pending.
+constexpr int CAP = KQ_STASH_ROWS;            // ring capacity in rows (power of two, >= WARP_ROWS)
+struct StashSink {
+    uint64_t* val;            // this warp's ring: [NOUT][CAP] values
+    uint8_t* flag;            //                   [NOUT][CAP] validity flags (only if some output is nullable)
     uint32_t sel;
+    uint32_t head;            // ring position of the tile's first surviving row
     int rank[R];
-    long long base;
     template <int TYPE>
     __device__ __forceinline__ void emit(int k, const uint64_t (&v)[R], uint32_t ok, bool nullable, const RowCtx&) const {
-        const DOut o = outs[k];
 #pragma unroll
         for (int r = 0; r < R; r++) {
             if ((sel >> r) & 1u) {
-                const long long pos = base + rank[r];
-                if constexpr (TYPE == KQT_DATE32 || TYPE == KQT_I32) reinterpret_cast<uint32_t*>(o.data)[pos] = (uint32_t)v[r];
-                else reinterpret_cast<uint64_t*>(o.data)[pos] = v[r];
-                if (nullable && ((ok >> r) & 1u)) atomicOr(o.validity + (pos >> 5), 1u << (pos & 31));
+                const uint32_t at = k * CAP + ((head + rank[r]) & (CAP - 1));
+                val[at] = v[r];
+                if (nullable) flag[at] = (uint8_t)((ok >> r) & 1u);
             }
         }
     }
     __device__ __forceinline__ void emit_bool(int k, uint32_t truth, uint32_t ok, bool nullable, const RowCtx&) const {
-        const DOut o = outs[k];
 #pragma unroll
         for (int r = 0; r < R; r++) {
             if ((sel >> r) & 1u) {
-                const long long pos = base + rank[r];
-                if ((truth >> r) & 1u) atomicOr(reinterpret_cast<uint32_t*>(o.data) + (pos >> 5), 1u << (pos & 31));
-                if (nullable && ((ok >> r) & 1u)) atomicOr(o.validity + (pos >> 5), 1u << (pos & 31));
+                const uint32_t at = k * CAP + ((head + rank[r]) & (CAP - 1));
+                val[at] = (truth >> r) & 1u;
+                if (nullable) flag[at] = (uint8_t)((ok >> r) & 1u);
             }
         }
     }
 };
 
+// OR `bits` (32 consecutive output rows starting at bit position pos) into a pre-zeroed bitmap
+__device__ __forceinline__ void or_bits_at(uint32_t* bitmap, long long pos, uint32_t bits) {
+    if (!bits) return;
+    const int sh = (int)(pos & 31);
+    atomicOr(bitmap + (pos >> 5), bits << sh);
+    if (sh && (bits >> (32 - sh))) atomicOr(bitmap + (pos >> 5) + 1, bits >> (32 - sh));
+}
+
+// Copy output K of one tile from the warp's ring (rows tail .. tail+cnt) to rows [base, base + cnt) of the output column.
+template <int K>
+__device__ __forceinline__ void stash_copy_out(const DOut* outs, const uint64_t* val, const uint8_t* flag, uint32_t tail, long long base, int cnt, int lane) {
+    if constexpr (K < Q::NOUT) {
+        constexpr int TYPE = Q::OUT_TYPE[K];
+        constexpr bool NULLABLE = Q::OUT_NULLABLE[K];
+        const DOut o = outs[K];
+        for (int i0 = 0; i0 < cnt; i0 += 32) {
+            const int i = i0 + lane;
+            const bool in = i < cnt;
+            const uint32_t at = K * CAP + ((tail + i) & (CAP - 1));
+            uint64_t v = 0;
+            if (in) v = val[at];
+            if constexpr (TYPE == KQT_BOOL) {
+                const uint32_t bits = __ballot_sync(0xffffffffu, in && (v & 1u));
+                if (lane == 0) or_bits_at(reinterpret_cast<uint32_t*>(o.data), base + i0, bits);
+            } else if constexpr (TYPE == KQT_DATE32 || TYPE == KQT_I32) {
+                if (in) reinterpret_cast<uint32_t*>(o.data)[base + i] = (uint32_t)v;
+            } else {
+                if (in) reinterpret_cast<uint64_t*>(o.data)[base + i] = v;
+            }
+            if constexpr (NULLABLE) {
+                const uint32_t bits = __ballot_sync(0xffffffffu, in && flag[at]);
+                if (lane == 0) or_bits_at(o.validity, base + i0, bits);
+            }
+        }
+        stash_copy_out<K + 1>(outs, val, flag, tail, base, cnt, lane);
+    }
+}
+#endif  // KQ_KERNEL_FILTER
+
 #ifdef KQ_KERNEL_PROJECT
 // ProjectionExec for one batch (Main.kt:589-594).
 extern "C" __global__ void __launch_bounds__(THREADS, 1) kq_project(const __grid_constant__ OpArgs A) {
+    constexpr int S = KQ_STAGES;
     extern __shared__ __align__(128) unsigned char stages[];
-    __shared__ uint64_t full[MAX_STAGES], empty[MAX_STAGES];
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int S = A.sp.nstages;
+    __shared__ uint64_t full[S], empty[S];
+    const int wid = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int warp = wid - NSERVICE;         // consumer warp index
     if (threadIdx.x == 0) {
         for (int s = 0; s < S; s++) { mbar_init(&full[s], 1); mbar_init(&empty[s], WARPS); }
         mbar_fence_init();
     }
     __syncthreads();
-    if (warp == SERVICE_WARP) {
+    if (wid == PRODUCER_WARP) {
         if (lane == 0) {
             int k = 0;
             for (int64_t tile = blockIdx.x; tile < A.ntiles; tile += gridDim.x, k++) {
@@ -132,189 +190,172 @@ extern "C" __global__ void __launch_bounds__(THREADS, 1) kq_project(const __grid
 #endif  // KQ_KERNEL_PROJECT
 
 #ifdef KQ_KERNEL_FILTER
-// FilterExec + ProjectionExec, single pass. Per tile k the consumer warps run step A (predicate ->
-// selection mask, per-warp totals) ahead of step B (cross-block prefix, projection, compacted
-// stores); the tile's columns wait in their shared-memory stage in between. The service warp turns
-// the per-warp totals of a tile into its global exclusive prefix (decoupled look-back over tile
-// descriptors in HBM) while the consumers are busy with step A of the next tiles, so the L2 round
-// trips of the look-back stay off the critical path; in between it keeps the stage ring full
-// (tickets are taken in look-back order).
+// FilterExec + ProjectionExec, single pass over the input.
+//
+// Consumer warps, per tile k (tiles are dealt round-robin: CTA b owns tiles b, b+G, b+2G, ...):
+//   step A(k)  predicate -> selection mask -> ballot/popc ranks; the warp total goes to the tile's
+//              metadata slot (the last warp to arrive publishes the tile aggregate for other CTAs);
+//              the projection of the surviving rows is evaluated right away and parked, compacted, in
+//              the warp's private stash ring; the input stage goes back to the TMA producer at once,
+//              so the whole stage ring is prefetch depth.
+//   step B(j)  for every older tile j whose exclusive prefix has arrived meanwhile: copy its rows from
+//              the stash to their final position with coalesced stores. A warp only BLOCKS on a prefix
+//              when its stash ring or the metadata ring is full, so CTAs can drift apart by many tiles
+//              (at 25 % selectivity ~12) before anybody waits.
+// The look-back warp turns tile aggregates into exclusive prefixes (decoupled look-back over per-tile
+// descriptors in HBM) and hands every consumer warp its own output base.
+//
+// Ring sizes: S input stages; M metadata slots; a warp keeps at most DMAX = M-S-1 tiles pending — a
+// warp can run at most S tiles ahead of the slowest one (stage reuse), so a slot is never rewritten
+// while another warp still reads it.
 extern "C" __global__ void __launch_bounds__(THREADS, 1) kq_filter_project(const __grid_constant__ OpArgs A) {
-    extern __shared__ __align__(128) unsigned char stages[];
-    __shared__ uint64_t full[MAX_STAGES], empty[MAX_STAGES], agg_ready[MAX_STAGES], prefix_ready[MAX_STAGES];
-    __shared__ long long tile_of[MAX_STAGES];
-    __shared__ unsigned long long prefix[MAX_STAGES];
-    __shared__ int wtot[MAX_STAGES][WARPS];
-    __shared__ int tot[MAX_STAGES], arrived[MAX_STAGES];
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int S = A.sp.nstages;
+    constexpr int S = KQ_STAGES, M = KQ_META, DMAX = M - S - 1;
+    constexpr int STASH_WARP = CAP * (8 * Q::NOUT + (Q::ANY_NULLABLE ? Q::NOUT : 0) + (KQ_SELVEC ? 4 : 0));   // bytes per warp
+    extern __shared__ __align__(128) unsigned char smem[];      // [S input stages][WARPS stash rings]
+    __shared__ uint64_t full[S], empty[S], agg_ready[M], prefix_ready[M];
+    __shared__ long long tile_of[S];
+    __shared__ long long wbase[M][WARPS];        // per tile: output row of each warp's first survivor
+    __shared__ int wtot[M][WARPS];
+    __shared__ int tot[M], arrived[M];
+    const int wid = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int warp = wid - NSERVICE;         // consumer warp index
     if (threadIdx.x == 0) {
-        for (int s = 0; s < S; s++) {
-            mbar_init(&full[s], 1); mbar_init(&empty[s], WARPS);
-            mbar_init(&agg_ready[s], 1); mbar_init(&prefix_ready[s], 1);
-            tot[s] = 0; arrived[s] = 0;
-        }
+        for (int s = 0; s < S; s++) { mbar_init(&full[s], 1); mbar_init(&empty[s], WARPS); }
+        for (int m = 0; m < M; m++) { mbar_init(&agg_ready[m], 1); mbar_init(&prefix_ready[m], 1); tot[m] = 0; arrived[m] = 0; }
         mbar_fence_init();
     }
     __syncthreads();
 
-    if (warp == SERVICE_WARP) {
-        int kp = 0, kl = 0;                    // next tile slot to produce / to resolve
-        bool prod_done = false, lb_done = false;
-        // the next ticket is always requested one step early: the L2 round trip of the atomic overlaps
-        // the TMA issue and the look-back of the current step (ticket order = look-back order)
-        long long next_ticket = 0;
-        if (lane == 0) next_ticket = (long long)atomicAdd(A.ticket, 1u);
-        while (!prod_done || !lb_done) {
-            bool did = false;
-            // (1) start the descriptor loads of the tile waiting for its prefix
-            bool lb_pending = false; long long lb_tile = 0; int lb_s = 0;
-            unsigned long long d[4] = {0, 0, 0, 0};
-            if (!lb_done) {
-                lb_s = kl % S;
-                int go = 0;
-                if (lane == 0) go = mbar_test(&agg_ready[lb_s], (kl / S) & 1) ? 1 : 0;
-                go = __shfl_sync(0xffffffffu, go, 0);
-                if (go) {
-                    lb_tile = tile_of[lb_s];
-                    if (lb_tile >= A.ntiles) { lb_done = true; kl++; did = true; }
-                    else { lb_pending = true; lb_load(A.tile_desc, lb_tile - 1, d); }
-                }
-            }
-            // (2) keep the stage ring full
-            if (!prod_done) {
+    if (wid == PRODUCER_WARP) {
+        // ---- TMA producer: keeps the stage ring full. All CTAs move through the table as one wavefront:
+        // the predecessors a look-back needs are always tiles the other CTAs process at the same time.
+        // (Handing tiles out by an atomic ticket at load-issue time lets fast CTAs bind far-ahead tiles
+        // early and scrambles the order in which aggregates appear: measured 3x slower.) The launch is
+        // cooperative, so every CTA a look-back may wait for is resident.
+        if (lane == 0) {
+            int kp = 0;
+            for (long long tile = blockIdx.x; tile < A.ntiles; tile += gridDim.x, kp++) {
                 const int s = kp % S;
-                int go = 0;
-                if (lane == 0) go = mbar_test(&empty[s], ((kp / S) & 1) ^ 1) ? 1 : 0;
-                go = __shfl_sync(0xffffffffu, go, 0);
-                if (go) {
-                    int end = 0;
-                    if (lane == 0) {
-                        const long long tile = next_ticket;
-                        tile_of[s] = tile;
-                        if (tile >= A.ntiles) { mbar_arrive(&full[s]); end = 1; }
-                        else {
-                            next_ticket = (long long)atomicAdd(A.ticket, 1u);
-                            stage_issue(A.sp, stages + (size_t)s * A.sp.stage_bytes, &full[s], tile, TILE, A.n);
-                        }
-                    }
-                    end = __shfl_sync(0xffffffffu, end, 0);
-                    if (end) prod_done = true;
-                    kp++; did = true;
-                }
+                mbar_wait(&empty[s], ((kp / S) & 1) ^ 1);
+                tile_of[s] = tile;
+                KQ_TR(tile, 0);
+                stage_issue(A.sp, smem + (size_t)s * A.sp.stage_bytes, &full[s], tile, TILE, A.n);
             }
-            // (3) fold the descriptors; publish the inclusive prefix and hand the exclusive one to step B
-            if (lb_pending) {
-                unsigned long long excl = 0;
-                if (lb_finish(A.tile_desc, lb_tile, d, &excl)) {
-                    if (lane == 0) {
-                        const unsigned long long t = (unsigned long long)tot[lb_s];
-                        if (lb_tile > 0) A.tile_desc[lb_tile] = LB_INCL | (excl + t);
-                        prefix[lb_s] = excl;
-                        if (lb_tile == A.ntiles - 1) *A.out_count = excl + t;
-                        tot[lb_s] = 0; arrived[lb_s] = 0;      // consumers are done with them until the stage is reused
-                        mbar_arrive(&prefix_ready[lb_s]);
-                    }
-                    kl++; did = true;
-                }
+            const int s = kp % S;
+            mbar_wait(&empty[s], ((kp / S) & 1) ^ 1);
+            tile_of[s] = -1;
+            mbar_arrive(&full[s]);
+        }
+        return;
+    }
+    if (wid == LOOKBACK_WARP) {
+        // ---- look-back: tile aggregate -> exclusive prefix -> per-warp output bases, one local tile after the other
+        int kl = 0;
+        for (long long tile = blockIdx.x; tile < A.ntiles; tile += gridDim.x, kl++) {
+            const int m = kl % M;
+            mbar_wait(&agg_ready[m], (kl / M) & 1);
+            if (lane == 0) KQ_TR(tile, 3);
+            const unsigned long long excl = lb_resolve(A.tile_desc, tile);
+            int x = lane < WARPS ? wtot[m][lane] : 0, incl = x;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) { const int y = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= o) incl += y; }
+            if (lane < WARPS) wbase[m][lane] = (long long)excl + incl - x;
+            const unsigned long long t = (unsigned long long)__shfl_sync(0xffffffffu, incl, 31);
+            __syncwarp();
+            if (lane == 0) {
+                KQ_TR(tile, 4);
+                if (tile > 0) A.tile_desc[tile] = LB_INCL | (excl + t);
+                if (tile == A.ntiles - 1) *A.out_count = excl + t;
+                tot[m] = 0; arrived[m] = 0;      // consumers are done with them until the slot is reused
+                mbar_arrive(&prefix_ready[m]);
             }
-            if (!did) __nanosleep(40);
+            __syncwarp();
         }
         return;
     }
 
-    CompactSink sink;
-    sink.outs = A.outs;
+    unsigned char* const ring = smem + (size_t)S * A.sp.stage_bytes + (size_t)warp * STASH_WARP;
+    StashSink sink;
+    sink.val = reinterpret_cast<uint64_t*>(ring);
+    sink.flag = ring + CAP * 8 * Q::NOUT;
+    int32_t* const selring = reinterpret_cast<int32_t*>(ring + CAP * (8 * Q::NOUT + (Q::ANY_NULLABLE ? Q::NOUT : 0)));
     const uint32_t lt = (1u << lane) - 1u;
-    // ranks in row order (chunk, lane, pair element) from a selection mask: ballot + popc
-    auto ranks_of = [&](uint32_t sel, int (&rank)[R]) -> int {
+    uint32_t head = 0, tail = 0;             // stash ring positions (rows, monotonic)
+    int kb = 0;                              // oldest tile whose rows are still in the stash
+    // step B of local tile kb; `block` = wait for its prefix, otherwise only if it has already arrived
+    auto step_b = [&](bool block) -> bool {
+        const int m = kb % M;
+        if (block) mbar_wait(&prefix_ready[m], (kb / M) & 1);
+        else {
+            int go = 0;
+            if (lane == 0) go = mbar_test(&prefix_ready[m], (kb / M) & 1) ? 1 : 0;
+            if (!__shfl_sync(0xffffffffu, go, 0)) return false;
+        }
+        const int cnt = wtot[m][warp];
+        const long long base = wbase[m][warp];
+        stash_copy_out<0>(A.outs, sink.val, sink.flag, tail, base, cnt, lane);
+        if constexpr (KQ_SELVEC) {
+            for (int i = lane; i < cnt; i += 32) A.selvec[base + i] = selring[(tail + i) & (CAP - 1)];
+        }
+        tail += cnt;
+        kb++;
+        return true;
+    };
+    int k = 0;
+    for (;; k++) {
+        const int s = k % S, m = k % M;
+        // make room: one tile's worth of stash rows and a free metadata distance
+        while (k - kb >= DMAX || head - tail + WARP_ROWS > CAP) step_b(true);
+        mbar_wait(&full[s], (k / S) & 1);
+        const long long tile = tile_of[s];
+        if (tile < 0) break;
+        if (warp == 0 && lane == 0) KQ_TR(tile, 1);
+        // ---- step A(k)
+        RowCtx rc;
+        rowctx_init(rc, warp, tile, TILE, A.n, A.err, smem + (size_t)s * A.sp.stage_bytes);
+        const uint32_t sel = Q::pred(A.q, rc) & rc.inr;       // TRUE only: a null predicate drops the row (rule E3)
+        // ranks in row order (chunk, lane, pair element): ballot + popc
         int wt = 0;
 #pragma unroll
         for (int j = 0; j < NCHUNK; j++) {
             const uint32_t s0 = (sel >> (2 * j)) & 1u, s1 = (sel >> (2 * j + 1)) & 1u;
             const uint32_t b0 = __ballot_sync(0xffffffffu, s0), b1 = __ballot_sync(0xffffffffu, s1);
             const int below = __popc(b0 & lt) + __popc(b1 & lt);
-            rank[2 * j] = wt + below;
-            rank[2 * j + 1] = wt + below + (int)s0;
+            sink.rank[2 * j] = wt + below;
+            sink.rank[2 * j + 1] = wt + below + (int)s0;
             wt += __popc(b0) + __popc(b1);
         }
-        return wt;
-    };
-    // Step A runs up to LOOKAHEAD tiles ahead of step B; a pending tile is remembered by its selection
-    // mask only (ranks are recomputed with ballots), so the look-back latency of tile k hides behind
-    // the predicate work of tiles k+1..k+LOOKAHEAD.
-    constexpr int LOOKAHEAD = 3;
-    uint32_t q_sel[LOOKAHEAD]; long long q_tile[LOOKAHEAD];
-#pragma unroll
-    for (int i = 0; i < LOOKAHEAD; i++) { q_sel[i] = 0; q_tile[i] = -1; }
-    const int D = min(LOOKAHEAD, S - 1);           // tiles in flight between A and B (S >= 2)
-    auto step_b = [&](int kb, uint32_t p_sel, long long p_tile) {
-        const int p_s = kb % S;
-        RowCtx rc;
-        rowctx_init(rc, warp, p_tile, TILE, A.n, A.err, stages + (size_t)p_s * A.sp.stage_bytes);
-        rc.active = p_sel;        // projection errors only count on surviving rows (FilterExec runs first)
-        sink.sel = p_sel;
-        ranks_of(p_sel, sink.rank);
-        mbar_wait(&prefix_ready[p_s], (kb / S) & 1);
-        int woff = 0;
-#pragma unroll
-        for (int w = 0; w < WARPS; w++) { int x = wtot[p_s][w]; if (w < warp) woff += x; }
-        sink.base = (long long)prefix[p_s] + woff;
-        if (A.selvec) {
-#pragma unroll
-            for (int r = 0; r < R; r++)
-                if ((p_sel >> r) & 1u) A.selvec[sink.base + sink.rank[r]] = (int32_t)(rc.row0(r >> 1) + (r & 1));
-        }
-        Q::project(A.q, rc, sink);
-        __syncwarp();
-        if (lane == 0) mbar_arrive(&empty[p_s]);
-    };
-    int k = 0;
-    for (;; k++) {
-        const int s = k % S;
-        mbar_wait(&full[s], (k / S) & 1);
-        const long long tile = tile_of[s];
-        if (tile >= A.ntiles) {
-            if (warp == 0 && lane == 0) mbar_arrive(&agg_ready[s]);     // end sentinel: wake the service warp
-            break;
-        }
-        // ---- step A(k): predicate -> selection mask -> warp total -> tile aggregate
-        RowCtx rc;
-        rowctx_init(rc, warp, tile, TILE, A.n, A.err, stages + (size_t)s * A.sp.stage_bytes);
-        const uint32_t c_sel = Q::pred(A.q, rc) & rc.inr;     // TRUE only: a null predicate drops the row (rule E3)
-        int wt = __popc(c_sel);
-#pragma unroll
-        for (int o = 16; o; o >>= 1) wt += __shfl_xor_sync(0xffffffffu, wt, o);
         if (lane == 0) {
-            wtot[s][warp] = wt;
-            atomicAdd(&tot[s], wt);
+            wtot[m][warp] = wt;
+            atomicAdd(&tot[m], wt);
             __threadfence_block();
-            if (atomicAdd(&arrived[s], 1) == WARPS - 1) {
+            if (atomicAdd(&arrived[m], 1) == WARPS - 1) {
                 // last warp of the tile: publish the aggregate right away so that no other block's
-                // look-back ever waits on this block's service warp
+                // look-back ever waits on this block's look-back warp
                 __threadfence_block();
-                const unsigned long long t = (unsigned long long)atomicAdd(&tot[s], 0);
+                const unsigned long long t = (unsigned long long)atomicAdd(&tot[m], 0);
                 A.tile_desc[tile] = (tile == 0 ? LB_INCL : LB_PART) | t;
-                mbar_arrive(&agg_ready[s]);
+                KQ_TR(tile, 2);
+                mbar_arrive(&agg_ready[m]);
             }
         }
-        __syncwarp();
-        // ---- step B(k - D) if that tile exists; then remember tile k in the queue slot k % LOOKAHEAD
-        if (k >= D) {
+        // projection of the surviving rows -> stash (errors only count on surviving rows: FilterExec runs first)
+        sink.sel = sel;
+        sink.head = head;
+        rc.active = sel;
+        Q::project(A.q, rc, sink);
+        if constexpr (KQ_SELVEC) {
 #pragma unroll
-            for (int i = 0; i < LOOKAHEAD; i++)
-                if (i == (k - D) % LOOKAHEAD) step_b(k - D, q_sel[i], q_tile[i]);
+            for (int r = 0; r < R; r++)
+                if ((sel >> r) & 1u) selring[(head + sink.rank[r]) & (CAP - 1)] = (int32_t)(rc.row0(r >> 1) + (r & 1));
         }
-#pragma unroll
-        for (int i = 0; i < LOOKAHEAD; i++)
-            if (i == k % LOOKAHEAD) { q_sel[i] = c_sel; q_tile[i] = tile; }
+        head += wt;
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&empty[s]);       // the input stage is free again
+        // ---- step B for every pending tile whose prefix has arrived
+        while (kb <= k && step_b(false)) {}
     }
-    // drain: tiles k-D .. k-1 still owe their step B
-    for (int kb = max(0, k - D); kb < k; kb++) {
-#pragma unroll
-        for (int i = 0; i < LOOKAHEAD; i++)
-            if (i == kb % LOOKAHEAD) step_b(kb, q_sel[i], q_tile[i]);
-    }
+    while (kb < k) step_b(true);
 }
 #endif  // KQ_KERNEL_FILTER
 

@@ -2,6 +2,8 @@
 // gather kernels for pass-through columns. The streaming kernels themselves live in kq_k_ops.cuh and
 // are specialised per query shape at run time (kq_codegen.cu -> kq_jit.cu).
 #include <algorithm>
+#include <cstdio>
+#include <cstdlib>
 #include <cstring>
 
 #include "kq_codegen.h"
@@ -16,7 +18,8 @@ namespace {
 constexpr int OPS_R = 4;
 constexpr int OPS_WARPS = 15;
 constexpr int TILE = OPS_WARPS * 32 * OPS_R;
-constexpr int THREADS = OPS_WARPS * 32 + 32;
+constexpr int THREADS_PROJECT = OPS_WARPS * 32 + 32;     // + TMA producer warp
+constexpr int THREADS_FILTER = OPS_WARPS * 32 + 64;      // + TMA producer warp + look-back warp
 
 // ---- gathers by selection vector (Utf8 pass-through columns and kq_filter) --------------------------------------
 template <typename T>
@@ -120,22 +123,21 @@ int gather_column(kq_ctx* ctx, kq_col* in, const int32_t* sel, kq_lazy_count* la
     return KQ_OK;
 }
 
-// Everything about an operator launch that depends on the query SHAPE only: how each output is produced,
-// the generated source and the stage plan. No CUDA calls (kq_explain_* runs it without a device).
+// Everything about one kernel launch that depends on the query SHAPE only: the generated source, the
+// stage plan and the shared-memory budget. No CUDA calls (kq_explain_* runs it without a device).
 struct OpsPlan {
-    std::vector<int> mode;            // per output: 0 = fused kernel output, 1 = alias (rule R4), 2 = gather by selection vector
-    std::vector<int> out_type;
+    std::vector<int> out_type;        // per fused output
     std::vector<char> out_nullable;
-    int nvm = 0;
     std::string defines, gen;
     const char* entry = "";
     StagePlan sp;
     int smem = 0;
+    bool fits = true;                 // false: too many fused outputs for the stash, split the launch
 };
 
-int plan_ops(kq_ctx* ctx, KqCodegen& cg, kq_expr* pred, const std::vector<kq_expr*>& ex, int smem_optin, OpsPlan* P) {
+// `ex`: the expressions this launch computes (at most MAX_OUT); `selvec`: also emit the selection vector.
+int plan_ops(kq_ctx* ctx, KqCodegen& cg, kq_expr* pred, const std::vector<kq_expr*>& ex, bool selvec, int smem_optin, OpsPlan* P) {
     std::string pred_body, proj_body;
-    int st;
     if (pred) {
         KqVal p;
         KQ_RET(cg.value(pred, &p));
@@ -143,42 +145,62 @@ int plan_ops(kq_ctx* ctx, KqCodegen& cg, kq_expr* pred, const std::vector<kq_exp
         cg.line("return " + p.v + (p.nullable() ? " & " + p.ok : std::string()) + ";");     // TRUE only (rule E3)
         pred_body = cg.take_body();
     }
-    // classify outputs: gather (Utf8 pass-through below a filter, or any column of kq_filter with
-    // too many fused outputs), alias (bare column without a filter, rule R4), or fused kernel output.
-    P->mode.assign(ex.size(), 0); P->out_type.assign(ex.size(), 0); P->out_nullable.assign(ex.size(), 0);
-    int nvm = 0;
+    if ((int)ex.size() > MAX_OUT) return kq_fail(ctx, KQ_ERR_UNSUPPORTED, "more than %d computed outputs in one kernel", MAX_OUT);
+    bool any_nullable = false;
+    std::string types, nulls;
     for (size_t k = 0; k < ex.size(); k++) {
-        int bc = KqCodegen::bare_column(ex[k]);
-        int t; bool nl;
-        KQ_RET(cg.infer(ex[k], &t, &nl));
-        P->out_type[k] = t; P->out_nullable[k] = nl;
-        if (bc >= 0 && !pred) P->mode[k] = 1;
-        else if (bc >= 0 && (t == KQ_UTF8 || nvm >= MAX_OUT)) P->mode[k] = 2;
+        KqVal v;
+        KQ_RET(cg.value(ex[k], &v));
+        if (v.type == KQ_UTF8) return kq_fail(ctx, KQ_ERR_UNSUPPORTED, "expressions cannot produce Utf8 values (only column pass-through)");
+        P->out_type.push_back(v.type); P->out_nullable.push_back(v.nullable());
+        any_nullable |= v.nullable();
+        const std::string nul = v.nullable() ? "true" : "false";
+        types += (k ? ", " : "") + std::to_string(v.type); nulls += (k ? ", " : "") + nul;
+        if (v.type == KQ_BOOL) cg.line("sink.emit_bool(" + std::to_string(k) + ", " + v.v + ", " + v.okx() + ", " + nul + ", rc);");
         else {
-            if (t == KQ_UTF8) return kq_fail(ctx, KQ_ERR_UNSUPPORTED, "expressions cannot produce Utf8 values (only column pass-through)");
-            if (nvm >= MAX_OUT) return kq_fail(ctx, KQ_ERR_UNSUPPORTED, "more than %d computed outputs in one kernel", MAX_OUT);
-            KqVal v;
-            if ((st = cg.value(ex[k], &v)) != KQ_OK) return st;
-            P->out_type[k] = v.type; P->out_nullable[k] = v.nullable();
-            const std::string nul = v.nullable() ? "true" : "false";
-            if (v.type == KQ_BOOL) cg.line("sink.emit_bool(" + std::to_string(nvm) + ", " + v.v + ", " + v.okx() + ", " + nul + ", rc);");
-            else {
-                const KqVal a = cg.as_array(v);
-                cg.line("sink.template emit<" + std::to_string(v.type) + ">(" + std::to_string(nvm) + ", " + a.v + ", " + a.okx() + ", " + nul + ", rc);");
-            }
-            nvm++;
+            const KqVal a = cg.as_array(v);
+            cg.line("sink.template emit<" + std::to_string(v.type) + ">(" + std::to_string(k) + ", " + a.v + ", " + a.okx() + ", " + nul + ", rc);");
         }
     }
     proj_body = cg.take_body();
-    P->nvm = nvm;
-    const std::string stage_defs = cg.plan_stages((smem_optin + 1024) - 1024 - 2048, pred ? 3 : 2, TILE, &P->sp);   // 1 KB/CTA driver-reserved, 2 KB static
-    P->smem = P->sp.nstages * P->sp.stage_bytes;
+    if (ex.empty()) { types = "0"; nulls = "false"; }
+
+    // shared memory: [stage ring][per-warp stash rings (filter only)]; 1 KB/CTA is reserved by the driver,
+    // up to 7 KB static (barriers, per-tile metadata)
+    const int avail = smem_optin - 8192;
+    const int nout = (int)ex.size();
+    int cap = 32 * OPS_R, stash_total = 0;
+    std::string stage_defs;
+    if (pred) {
+        const int row_bytes = 8 * nout + (any_nullable ? nout : 0) + (selvec ? 4 : 0);
+        cg.plan_stages(1 << 30, 1, TILE, &P->sp);
+        const int stage_all = P->sp.stage_bytes;           // one stage with every referenced buffer staged
+        // the largest stash ring (rows per warp, power of two) that leaves three input stages, else two
+        bool found = false;
+        for (int want = 3; want >= 2 && !found; want--)
+            for (int c = 8 * 32 * OPS_R; c >= 32 * OPS_R; c >>= 1)
+                if (OPS_WARPS * c * row_bytes + want * stage_all <= avail) { cap = c; found = true; break; }
+        if (!found) {
+            cap = 32 * OPS_R;
+            if (nout > 1 || OPS_WARPS * cap * row_bytes + 16 * 1024 > avail) { P->fits = false; return KQ_OK; }
+        }
+        stash_total = (OPS_WARPS * cap * row_bytes + 127) / 128 * 128;
+    }
+    stage_defs = cg.plan_stages(avail - stash_total, 2, TILE, &P->sp);
+    P->smem = P->sp.nstages * P->sp.stage_bytes + stash_total;
     P->gen = "namespace kq {\n" + stage_defs + "struct Q {\n";
+    P->gen += "    static constexpr int NOUT = " + std::to_string(nout) + ";\n";
+    P->gen += "    static constexpr int OUT_TYPE[" + std::to_string(std::max(nout, 1)) + "] = {" + types + "};\n";
+    P->gen += "    static constexpr bool OUT_NULLABLE[" + std::to_string(std::max(nout, 1)) + "] = {" + nulls + "};\n";
+    P->gen += std::string("    static constexpr bool ANY_NULLABLE = ") + (any_nullable ? "true" : "false") + ";\n";
     if (pred) P->gen += "    static __device__ __forceinline__ uint32_t pred(const QArgs& q, const RowCtx& rc) {\n" + pred_body + "    }\n";
     P->gen += "    template <class Sink> static __device__ __forceinline__ void project(const QArgs& q, const RowCtx& rc, const Sink& sink) {\n" + proj_body + "    }\n";
     P->gen += "};\n}  // namespace kq\n";
-    P->defines = "#define KQ_R " + std::to_string(OPS_R) + "\n#define KQ_WARPS " + std::to_string(OPS_WARPS) + "\n" +
-                 (pred ? "#define KQ_KERNEL_FILTER\n" : "#define KQ_KERNEL_PROJECT\n");
+    P->defines = "#define KQ_R " + std::to_string(OPS_R) + "\n#define KQ_WARPS " + std::to_string(OPS_WARPS) + "\n#define KQ_STAGES " +
+                 std::to_string(P->sp.nstages) + "\n";
+    if (getenv("KQ_TRACE_FILE")) P->defines += "#define KQ_TRACE 1\n";
+    if (pred) P->defines += "#define KQ_KERNEL_FILTER\n#define KQ_STASH_ROWS " + std::to_string(cap) + "\n#define KQ_META 24\n#define KQ_SELVEC " + (selvec ? "1" : "0") + "\n";
+    else P->defines += "#define KQ_KERNEL_PROJECT\n";
     P->entry = pred ? "kq_filter_project" : "kq_project";
     return KQ_OK;
 }
@@ -195,12 +217,7 @@ int run_operator(kq_ctx* ctx, kq_expr* pred, kq_expr* const* exprs, int nexprs, 
     std::vector<kq_expr*> owned;
     std::vector<kq_expr*> ex(exprs, exprs + nexprs);
     if (all_columns) for (int i = 0; i < (int)input->cols.size(); i++) { owned.push_back(kq_expr_column(i)); ex.push_back(owned.back()); }
-    auto cleanup = [&]() { for (kq_expr* e : owned) kq_expr_free(e); };
 
-    KqCodegen cg;
-    OpsPlan P;
-    int st = cg.begin(ctx, input);
-    if (st == KQ_OK) st = plan_ops(ctx, cg, pred, ex, ctx->max_smem_optin, &P);
     std::vector<kq_col*> outs(ex.size(), nullptr);
     kq_lazy_count* lazy = nullptr;
     kq_col* selcol = nullptr;
@@ -208,77 +225,123 @@ int run_operator(kq_ctx* ctx, kq_expr* pred, kq_expr* const* exprs, int nexprs, 
         for (kq_col* c : outs) kq_column_free(c);
         kq_column_free(selcol);
         if (lazy) kq_lazy_release(ctx, lazy);
-        cleanup();
+        for (kq_expr* e : owned) kq_expr_free(e);
         return s;
     };
-    if (st != KQ_OK) return fail(st);
 
-    OpArgs A;
-    memset(&A, 0, sizeof A);
-    A.n = n; A.ntiles = (n + TILE - 1) / TILE; A.err = ctx->d_err;
-    A.q = cg.args; A.sp = P.sp;
+    // classify outputs: alias (bare column without a filter, rule R4), gather by selection vector (Utf8
+    // pass-through below a filter), or computed by the fused kernel
+    std::vector<int> mode(ex.size(), 0);   // 0 = fused, 1 = alias, 2 = gather
+    std::vector<size_t> fused;
+    bool need_sel = selection != nullptr;
+    {
+        KqCodegen probe;
+        int st = probe.begin(ctx, input);
+        if (st != KQ_OK) return fail(st);
+        if (pred) { int t; bool nl; if ((st = probe.infer(pred, &t, &nl)) != KQ_OK) return fail(st); }
+        for (size_t k = 0; k < ex.size(); k++) {
+            int bc = KqCodegen::bare_column(ex[k]);
+            int t; bool nl;
+            if ((st = probe.infer(ex[k], &t, &nl)) != KQ_OK) return fail(st);
+            if (bc >= 0 && !pred) mode[k] = 1;
+            else if (bc >= 0 && t == KQ_UTF8) { mode[k] = 2; need_sel = true; }
+            else fused.push_back(k);
+        }
+    }
     if (pred) {
         lazy = kq_lazy_new(ctx);
         if (!lazy) return fail(kq_fail(ctx, KQ_ERR_OUT_OF_MEMORY, "lazy count"));
-    }
-    int nvm = 0;
-    for (size_t k = 0; k < ex.size(); k++) {
-        if (P.mode[k] != 0) continue;
-        kq_col* c = nullptr;
-        if ((st = kq_col_new(ctx, P.out_type[k], n, P.out_nullable[k], 0, &c)) != KQ_OK) return fail(st);
-        outs[k] = c;
-        if (pred) {
-            c->n = -1; c->lazy = lazy; lazy->rc.fetch_add(1);
-            if (c->validity) cudaMemsetAsync(c->validity, 0, (size_t)((n + 63) / 64) * 8, ctx->stream);
-            if (P.out_type[k] == KQ_BOOL) cudaMemsetAsync(c->data, 0, (size_t)((n + 63) / 64) * 8, ctx->stream);
+        if (need_sel) {
+            int st = kq_col_new(ctx, KQ_I32, n, false, 0, &selcol);
+            if (st != KQ_OK) return fail(st);
+            selcol->n = -1; selcol->lazy = lazy; lazy->rc.fetch_add(1);
         }
-        A.outs[nvm].data = c->data; A.outs[nvm].validity = c->validity;
-        nvm++;
     }
 
-    bool need_sel = selection != nullptr;
-    for (int m : P.mode) need_sel |= (m == 2);
-    if (pred && need_sel) {
-        if ((st = kq_col_new(ctx, KQ_I32, n, false, 0, &selcol)) != KQ_OK) return fail(st);
-        selcol->n = -1; selcol->lazy = lazy; lazy->rc.fetch_add(1);
-        A.selvec = (int32_t*)selcol->data;
+    // One launch computes a chunk of the fused outputs; a filter whose outputs do not fit the stash is
+    // split into several launches that repeat the predicate.
+    std::vector<std::vector<size_t>> chunks;
+    if (!fused.empty() || pred) chunks.push_back(fused);
+    for (size_t ci = 0; ci < chunks.size(); ci++) {
+        const bool first = ci == 0;
+        std::vector<kq_expr*> cex;
+        for (size_t k : chunks[ci]) cex.push_back(ex[k]);
+        KqCodegen cg;
+        OpsPlan P;
+        int st = cg.begin(ctx, input);
+        if (st == KQ_OK && !pred && cex.size() > (size_t)MAX_OUT) P.fits = false;
+        else if (st == KQ_OK) st = plan_ops(ctx, cg, pred, cex, first && need_sel, ctx->max_smem_optin, &P);
+        if (st != KQ_OK) return fail(st);
+        if (!P.fits) {
+            if (chunks[ci].size() < 2) return fail(kq_fail(ctx, KQ_ERR_UNSUPPORTED, "projection does not fit the shared-memory budget"));
+            std::vector<size_t> lo(chunks[ci].begin(), chunks[ci].begin() + chunks[ci].size() / 2), hi(chunks[ci].begin() + chunks[ci].size() / 2, chunks[ci].end());
+            chunks[ci] = lo;
+            chunks.insert(chunks.begin() + (long)ci + 1, hi);
+            ci--;
+            continue;
+        }
+        OpArgs A;
+        memset(&A, 0, sizeof A);
+        A.n = n; A.ntiles = (n + TILE - 1) / TILE; A.err = ctx->d_err;
+        A.q = cg.args; A.sp = P.sp;
+        for (size_t j = 0; j < chunks[ci].size(); j++) {
+            const size_t k = chunks[ci][j];
+            kq_col* c = nullptr;
+            if ((st = kq_col_new(ctx, P.out_type[j], n, P.out_nullable[j], 0, &c)) != KQ_OK) return fail(st);
+            outs[k] = c;
+            if (pred) {
+                c->n = -1; c->lazy = lazy; lazy->rc.fetch_add(1);
+                if (c->validity) cudaMemsetAsync(c->validity, 0, (size_t)((n + 63) / 64) * 8, ctx->stream);
+                if (P.out_type[j] == KQ_BOOL) cudaMemsetAsync(c->data, 0, (size_t)((n + 63) / 64) * 8, ctx->stream);
+            }
+            A.outs[j].data = c->data; A.outs[j].validity = c->validity;
+        }
+        if (n == 0) continue;
+        void* kernel = nullptr;
+        if ((st = kq_jit_kernel(ctx, P.defines, P.gen, KQ_SKEL_OPS, P.entry, P.smem, &kernel)) != KQ_OK) return fail(st);
+        void* kargs[] = {&A};
+        const int grid = (int)std::min<int64_t>(A.ntiles, (int64_t)ctx->sm_count);
+        unsigned long long* scratch = nullptr;     // [0]: ticket, [2..]: tile descriptors
+        if (pred) {
+            if ((st = kq_dev_alloc(ctx, (size_t)(A.ntiles + 2) * 8, (void**)&scratch)) != KQ_OK) return fail(st);
+            cudaMemsetAsync(scratch, 0, (size_t)(A.ntiles + 2) * 8, ctx->stream);
+            A.ticket = (unsigned int*)scratch;
+            A.tile_desc = scratch + 2;
+            A.out_count = lazy->d_slot;
+            if (first && need_sel) A.selvec = (int32_t*)selcol->data;
+            if (getenv("KQ_TRACE_FILE")) {       // debugging aid: per-tile timestamps of the pipeline (needs a KQ_TRACE build)
+                kq_dev_alloc(ctx, (size_t)A.ntiles * 64, (void**)&A.trace);
+                cudaMemsetAsync(A.trace, 0, (size_t)A.ntiles * 64, ctx->stream);
+            }
+        }
+        // the filter kernel's CTAs wait for one another (cross-block prefix): cooperative launch = all resident
+        cudaError_t e = pred ? cudaLaunchCooperativeKernel(kernel, dim3(grid), dim3(THREADS_FILTER), kargs, (size_t)P.smem, ctx->stream)
+                             : cudaLaunchKernel(kernel, dim3(grid), dim3(THREADS_PROJECT), kargs, (size_t)P.smem, ctx->stream);
+        kq_dev_free(ctx, scratch);
+        if (A.trace) {
+            std::vector<unsigned long long> h((size_t)A.ntiles * 8);
+            cudaMemcpyAsync(h.data(), A.trace, h.size() * 8, cudaMemcpyDeviceToHost, ctx->stream);
+            cudaStreamSynchronize(ctx->stream);
+            if (FILE* f = fopen(getenv("KQ_TRACE_FILE"), "wb")) { fwrite(h.data(), 8, h.size(), f); fclose(f); }
+            kq_dev_free(ctx, A.trace);
+        }
+        if (e != cudaSuccess) return fail(kq_cuda_fail(ctx, e, P.entry));
+        ctx->launches++;
     }
-
-    const bool launch = n > 0 && (pred || P.nvm > 0);
-    void* kernel = nullptr;
-    if (launch && (st = kq_jit_kernel(ctx, P.defines, P.gen, KQ_SKEL_OPS, P.entry, P.smem, &kernel)) != KQ_OK) return fail(st);
-    void* kargs[] = {&A};
-    const int grid = (int)std::min<int64_t>(A.ntiles, (int64_t)ctx->sm_count);
 
     if (pred) {
-        unsigned long long* scratch = nullptr;     // [0]: ticket, [2..]: tile descriptors
-        if ((st = kq_dev_alloc(ctx, (size_t)(A.ntiles + 2) * 8, (void**)&scratch)) != KQ_OK) return fail(st);
-        cudaMemsetAsync(scratch, 0, (size_t)(A.ntiles + 2) * 8, ctx->stream);
-        A.ticket = (unsigned int*)scratch;
-        A.tile_desc = scratch + 2;
-        A.out_count = lazy->d_slot;
-        if (launch) {
-            cudaError_t e = cudaLaunchKernel(kernel, dim3(grid), dim3(THREADS), kargs, (size_t)P.smem, ctx->stream);
-            if (e != cudaSuccess) { kq_dev_free(ctx, scratch); return fail(kq_cuda_fail(ctx, e, "kq_filter_project")); }
-            ctx->launches++;
-        }
-        kq_dev_free(ctx, scratch);
         for (size_t k = 0; k < ex.size(); k++) {
-            if (P.mode[k] != 2) continue;
+            if (mode[k] != 2) continue;
             kq_col* in = input->cols[(size_t)KqCodegen::bare_column(ex[k])];
-            if ((st = gather_column(ctx, in, (const int32_t*)selcol->data, lazy, n, &outs[k])) != KQ_OK) return fail(st);
+            int st = gather_column(ctx, in, (const int32_t*)selcol->data, lazy, n, &outs[k]);
+            if (st != KQ_OK) return fail(st);
         }
         // the row count travels back asynchronously; it is only waited for when somebody asks
         cudaMemcpyAsync(lazy->h_slot, lazy->d_slot, 8, cudaMemcpyDeviceToHost, ctx->stream);
         cudaEventRecord(lazy->ev, ctx->stream);
     } else {
         for (size_t k = 0; k < ex.size(); k++)
-            if (P.mode[k] == 1) { outs[k] = input->cols[(size_t)KqCodegen::bare_column(ex[k])]; outs[k]->rc.fetch_add(1); }
-        if (launch) {
-            cudaError_t e = cudaLaunchKernel(kernel, dim3(grid), dim3(THREADS), kargs, (size_t)P.smem, ctx->stream);
-            if (e != cudaSuccess) return fail(kq_cuda_fail(ctx, e, "kq_project"));
-            ctx->launches++;
-        }
+            if (mode[k] == 1) { outs[k] = input->cols[(size_t)KqCodegen::bare_column(ex[k])]; outs[k]->rc.fetch_add(1); }
     }
 
     kq_batch* b = new kq_batch();
@@ -287,7 +350,7 @@ int run_operator(kq_ctx* ctx, kq_expr* pred, kq_expr* const* exprs, int nexprs, 
     if (pred) { b->n = -1; b->lazy = lazy; } else b->n = n;
     *out = b;
     if (selection) *selection = selcol; else kq_column_free(selcol);
-    cleanup();
+    for (kq_expr* e : owned) kq_expr_free(e);
     return KQ_OK;
 }
 
@@ -349,7 +412,8 @@ int kq_explain_filter_project(kq_expr* pred, kq_expr* const* exprs, int nexprs, 
     OpsPlan P;
     std::vector<kq_expr*> ex(exprs, exprs + nexprs);
     int st = cg.begin(&fake, &sb.batch);
-    if (st == KQ_OK) st = plan_ops(&fake, cg, pred, ex, 232448, &P);
+    if (st == KQ_OK) st = plan_ops(&fake, cg, pred, ex, false, 232448, &P);
+    if (st == KQ_OK && !P.fits) st = kq_fail(&fake, KQ_ERR_UNSUPPORTED, "outputs do not fit one launch (the operator would split them)");
     if (st == KQ_OK && compile) st = kq_jit_compile_only(&fake, P.defines, P.gen, KQ_SKEL_OPS);
     copy_out(st == KQ_OK ? P.defines + P.gen : fake.last_error, source, source_cap);
     return st;

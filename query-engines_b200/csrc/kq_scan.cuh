@@ -81,6 +81,42 @@ __device__ __forceinline__ bool lb_finish(const volatile unsigned long long* des
     }
 }
 
+// Blocking variant for a dedicated look-back warp. The tile's own aggregate has already been published
+// (LB_PART) by the consumer warps; reads the 128 predecessor descriptors at once (4 per lane, one L2
+// round trip), each lane spinning only on descriptors that are not published yet, and walks further
+// back if no inclusive prefix was among them. Returns the exclusive prefix (same value in every lane).
+__device__ __forceinline__ unsigned long long lb_resolve(const volatile unsigned long long* desc, long long tile) {
+    const int lane = threadIdx.x & 31;
+    unsigned long long excl = 0;
+    long long base = tile - 1;
+    while (base >= 0) {
+        unsigned long long d[4];
+#pragma unroll
+        for (int j = 0; j < 4; j++) {
+            const long long idx = base - lane - 32 * j;
+            d[j] = LB_INCL;                    // out of range: an inclusive zero
+            if (idx >= 0) d[j] = desc[idx];
+        }
+        bool done = false;
+#pragma unroll
+        for (int j = 0; j < 4; j++) {
+            if (done) continue;
+            const long long idx = base - lane - 32 * j;
+            while ((d[j] >> 62) == 0) { __nanosleep(40); d[j] = desc[idx]; }
+            const unsigned incl = __ballot_sync(0xffffffffu, (d[j] >> 62) == 2);
+            unsigned long long val = d[j] & LB_VMASK;
+            if (incl) { const int first = __ffs(incl) - 1; if (lane > first) val = 0; }
+#pragma unroll
+            for (int o = 16; o; o >>= 1) val += __shfl_xor_sync(0xffffffffu, val, o);
+            excl += val;
+            if (incl) done = true;
+        }
+        if (done) break;
+        base -= 128;
+    }
+    return excl;
+}
+
 // Device-wide exclusive prefix over item lengths -> Arrow int32 offsets. `f(i)` returns the byte
 // length of output item i (and may do side effects such as setting its validity bit). The item
 // count is device-resident (*d_count) so no host round trip is needed after a filter.
