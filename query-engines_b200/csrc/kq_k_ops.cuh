@@ -26,8 +26,9 @@ constexpr int TILE = WARPS * WARP_ROWS;
 // warps never take issue slots from the consumer warps that share their scheduler.
 constexpr int PRODUCER_WARP = 0;             // TMA producer
 #ifdef KQ_KERNEL_FILTER
-constexpr int LOOKBACK_WARP = 1;             // cross-block prefix resolver
-constexpr int NSERVICE = 2;
+constexpr int LOOKBACK_WARP = 1;             // first of NLB cross-block prefix resolvers (local tile kl -> warp kl % NLB)
+constexpr int NLB = 2;
+constexpr int NSERVICE = 1 + NLB;
 #else
 constexpr int NSERVICE = 1;
 #endif
@@ -248,10 +249,11 @@ extern "C" __global__ void __launch_bounds__(THREADS, 1) kq_filter_project(const
         }
         return;
     }
-    if (wid == LOOKBACK_WARP) {
-        // ---- look-back: tile aggregate -> exclusive prefix -> per-warp output bases, one local tile after the other
-        int kl = 0;
-        for (long long tile = blockIdx.x; tile < A.ntiles; tile += gridDim.x, kl++) {
+    if (wid >= LOOKBACK_WARP && wid < LOOKBACK_WARP + NLB) {
+        // ---- look-back: tile aggregate -> exclusive prefix -> per-warp output bases. Look-backs of
+        // different tiles are independent, so the NLB warps take the CTA's tiles in turn.
+        int kl = wid - LOOKBACK_WARP;
+        for (long long tile = blockIdx.x + (long long)kl * gridDim.x; tile < A.ntiles; tile += (long long)NLB * gridDim.x, kl += NLB) {
             const int m = kl % M;
             mbar_wait(&agg_ready[m], (kl / M) & 1);
             if (lane == 0) KQ_TR(tile, 3);

@@ -14,12 +14,13 @@ using namespace kq;
 namespace {
 
 // Tile geometry of the streaming kernels (compiled into the specialised kernels as KQ_R / KQ_WARPS):
-// 15 consumer warps x 32 lanes x 4 rows = 1920 rows per tile, plus one service warp.
+// 16 consumer warps x 32 lanes x 4 rows = 2048 rows per tile, plus the service warps (measured sweep: R x warps of
+// 2x28, 4x12, 4x15, 4x16, 6x10, 8x8 all land within 10 % of each other; 4x16 was best).
 constexpr int OPS_R = 4;
-constexpr int OPS_WARPS = 15;
+constexpr int OPS_WARPS = 16;
 constexpr int TILE = OPS_WARPS * 32 * OPS_R;
 constexpr int THREADS_PROJECT = OPS_WARPS * 32 + 32;     // + TMA producer warp
-constexpr int THREADS_FILTER = OPS_WARPS * 32 + 64;      // + TMA producer warp + look-back warp
+constexpr int THREADS_FILTER = OPS_WARPS * 32 + 96;      // + TMA producer warp + 2 look-back warps
 
 // ---- gathers by selection vector (Utf8 pass-through columns and kq_filter) --------------------------------------
 template <typename T>
@@ -166,8 +167,8 @@ int plan_ops(kq_ctx* ctx, KqCodegen& cg, kq_expr* pred, const std::vector<kq_exp
     if (ex.empty()) { types = "0"; nulls = "false"; }
 
     // shared memory: [stage ring][per-warp stash rings (filter only)]; 1 KB/CTA is reserved by the driver,
-    // up to 7 KB static (barriers, per-tile metadata)
-    const int avail = smem_optin - 8192;
+    // up to 9 KB static (barriers, per-tile metadata)
+    const int avail = smem_optin - 10240;
     const int nout = (int)ex.size();
     int cap = 32 * OPS_R, stash_total = 0;
     std::string stage_defs;
@@ -184,6 +185,7 @@ int plan_ops(kq_ctx* ctx, KqCodegen& cg, kq_expr* pred, const std::vector<kq_exp
             cap = 32 * OPS_R;
             if (nout > 1 || OPS_WARPS * cap * row_bytes + 16 * 1024 > avail) { P->fits = false; return KQ_OK; }
         }
+        if (const char* e = getenv("KQ_OPS_CAP")) cap = std::max(32 * OPS_R, std::min(cap, atoi(e)));     // tuning experiments
         stash_total = (OPS_WARPS * cap * row_bytes + 127) / 128 * 128;
     }
     stage_defs = cg.plan_stages(avail - stash_total, 2, TILE, &P->sp);
@@ -199,7 +201,7 @@ int plan_ops(kq_ctx* ctx, KqCodegen& cg, kq_expr* pred, const std::vector<kq_exp
     P->defines = "#define KQ_R " + std::to_string(OPS_R) + "\n#define KQ_WARPS " + std::to_string(OPS_WARPS) + "\n#define KQ_STAGES " +
                  std::to_string(P->sp.nstages) + "\n";
     if (getenv("KQ_TRACE_FILE")) P->defines += "#define KQ_TRACE 1\n";
-    if (pred) P->defines += "#define KQ_KERNEL_FILTER\n#define KQ_STASH_ROWS " + std::to_string(cap) + "\n#define KQ_META 24\n#define KQ_SELVEC " + (selvec ? "1" : "0") + "\n";
+    if (pred) P->defines += "#define KQ_KERNEL_FILTER\n#define KQ_STASH_ROWS " + std::to_string(cap) + "\n#define KQ_META 32\n#define KQ_SELVEC " + (selvec ? "1" : "0") + "\n";
     else P->defines += "#define KQ_KERNEL_PROJECT\n";
     P->entry = pred ? "kq_filter_project" : "kq_project";
     return KQ_OK;

@@ -82,9 +82,10 @@ __device__ __forceinline__ bool lb_finish(const volatile unsigned long long* des
 }
 
 // Blocking variant for a dedicated look-back warp. The tile's own aggregate has already been published
-// (LB_PART) by the consumer warps; reads the 128 predecessor descriptors at once (4 per lane, one L2
-// round trip), each lane spinning only on descriptors that are not published yet, and walks further
-// back if no inclusive prefix was among them. Returns the exclusive prefix (same value in every lane).
+// (LB_PART) by the consumer warps. Reads the 128 predecessor descriptors at once (4 per lane, one L2
+// round trip), each lane spinning only on descriptors that are not published yet; everything up to
+// and including the nearest inclusive prefix is summed with a single butterfly; walks further back
+// if no inclusive prefix was among the 128. Returns the exclusive prefix (same value in every lane).
 __device__ __forceinline__ unsigned long long lb_resolve(const volatile unsigned long long* desc, long long tile) {
     const int lane = threadIdx.x & 31;
     unsigned long long excl = 0;
@@ -97,21 +98,24 @@ __device__ __forceinline__ unsigned long long lb_resolve(const volatile unsigned
             d[j] = LB_INCL;                    // out of range: an inclusive zero
             if (idx >= 0) d[j] = desc[idx];
         }
-        bool done = false;
+        // nearest inclusive prefix among the published ones (distance = 32 j + lane); lanes spin only on
+        // descriptors that lie in front of it
+        int stop = 4 * 32;                     // distance of the nearest inclusive descriptor found so far
 #pragma unroll
         for (int j = 0; j < 4; j++) {
-            if (done) continue;
+            if (stop < 4 * 32) break;
             const long long idx = base - lane - 32 * j;
             while ((d[j] >> 62) == 0) { __nanosleep(40); d[j] = desc[idx]; }
             const unsigned incl = __ballot_sync(0xffffffffu, (d[j] >> 62) == 2);
-            unsigned long long val = d[j] & LB_VMASK;
-            if (incl) { const int first = __ffs(incl) - 1; if (lane > first) val = 0; }
-#pragma unroll
-            for (int o = 16; o; o >>= 1) val += __shfl_xor_sync(0xffffffffu, val, o);
-            excl += val;
-            if (incl) done = true;
+            if (incl) stop = 32 * j + __ffs(incl) - 1;
         }
-        if (done) break;
+        unsigned long long val = 0;
+#pragma unroll
+        for (int j = 0; j < 4; j++) if (32 * j + lane <= stop) val += d[j] & LB_VMASK;
+#pragma unroll
+        for (int o = 16; o; o >>= 1) val += __shfl_xor_sync(0xffffffffu, val, o);
+        excl += val;
+        if (stop < 4 * 32) break;
         base -= 128;
     }
     return excl;
