@@ -209,6 +209,12 @@ KQ_API int kq_hashagg_finalize(kq_ctx* ctx, kq_hashagg* agg, kq_batch** out);
 KQ_API int kq_hashagg_num_groups(kq_ctx* ctx, kq_hashagg* agg, int64_t* n);
 KQ_API int kq_hashagg_free(kq_hashagg* agg);
 
+/* EXPLAIN for the aggregate kernel (see kq_explain_filter_project). */
+KQ_API int kq_explain_hashagg(kq_expr* pred, kq_expr* const* group_exprs, int ngroup,
+                              const int* agg_kinds, kq_expr* const* agg_inputs, int nagg,
+                              int ncols, const int* types, const int* nullable, int compile,
+                              char* source, size_t source_cap);
+
 /* ---- multi-GPU merge (partial -> merge of main(), Main.kt:1309-1325) ----------------------- */
 #define KQ_COMM_ID_BYTES 128
 /* Rank 0 creates the id, the caller distributes it (any channel), all ranks call init. */

@@ -4,6 +4,7 @@
 // source becomes a kernel.
 #pragma once
 
+#include <cstring>
 #include <string>
 #include <vector>
 
@@ -64,6 +65,25 @@ struct KqCodegen {
     int lit_value(const kq_expr* e, KqVal* out);
     int bin_value(const kq_expr* e, KqVal* out);
 };
+
+// A batch that exists as a schema only (types + nullability), for kq_explain_*.
+struct KqSchemaBatch {
+    kq_batch batch;
+    std::vector<kq_col> cols;
+    KqSchemaBatch(int ncols, const int* types, const int* nullable) : cols((size_t)ncols) {
+        for (int i = 0; i < ncols; i++) {
+            cols[(size_t)i].type = types[i];
+            cols[(size_t)i].validity = (nullable && nullable[i]) ? reinterpret_cast<uint32_t*>(0x100) : nullptr;   // never dereferenced
+            batch.cols.push_back(&cols[(size_t)i]);
+        }
+    }
+};
+inline void kq_copy_text(const std::string& s, char* dst, size_t cap) {
+    if (!dst || cap == 0) return;
+    size_t m = s.size() < cap - 1 ? s.size() : cap - 1;
+    memcpy(dst, s.data(), m);
+    dst[m] = 0;
+}
 
 // ---- kq_jit.cu ----------------------------------------------------------------------------------------------------
 // Compile (or fetch from the process-wide cache) the kernel `entry` of: prelude + `generated` + skeleton.

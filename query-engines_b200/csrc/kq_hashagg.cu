@@ -232,16 +232,22 @@ static void fill_common_args(kq_hashagg* h, AggArgs& A) {
     A.stop_threshold = ~0ULL;
 }
 
+static void hashagg_delete_host(kq_hashagg* h) {
+    kq_expr_free(h->pred);
+    for (kq_expr* e : h->groups) kq_expr_free(e);
+    for (kq_expr* e : h->inputs) kq_expr_free(e);
+    delete h;
+}
+
 extern "C" {
 
-int kq_hashagg_create(kq_ctx* ctx, kq_expr* pred, kq_expr* const* group_exprs, int ngroup, const int* agg_kinds,
-                      kq_expr* const* agg_inputs, int nagg, int64_t expected_groups, kq_hashagg** out) {
-    if (!ctx || !out || ngroup < 0 || nagg < 0) return KQ_ERR_ILLEGAL_ARGUMENT;
+// Host-only part of construction: expression bookkeeping and the record layout (no CUDA calls).
+static int hashagg_new(kq_ctx* ctx, kq_expr* pred, kq_expr* const* group_exprs, int ngroup, const int* agg_kinds,
+                       kq_expr* const* agg_inputs, int nagg, int64_t expected_groups, kq_hashagg** out) {
     if (ngroup > MAX_KEYS) return kq_fail(ctx, KQ_ERR_UNSUPPORTED, "more than %d group expressions", MAX_KEYS);
     for (int i = 0; i < nagg; i++)
         if (agg_kinds[i] < KQ_AGG_MAX || agg_kinds[i] > KQ_AGG_COUNT)
             return kq_fail(ctx, KQ_ERR_ILLEGAL_STATE, "Unsupported aggregate function: %d", agg_kinds[i]);   // Main.kt:696
-    cudaSetDevice(ctx->device);
     kq_hashagg* h = new kq_hashagg();
     h->ctx = ctx;
     h->expected_groups = expected_groups;
@@ -252,7 +258,7 @@ int kq_hashagg_create(kq_ctx* ctx, kq_expr* pred, kq_expr* const* group_exprs, i
         int idx = -1;
         for (size_t j = 0; j < h->inputs.size(); j++) if (expr_equal(h->inputs[j], agg_inputs[i])) { idx = (int)j; break; }
         if (idx < 0) {
-            if (h->inputs.size() >= (size_t)MAX_INPUTS) { kq_hashagg_free(h); return kq_fail(ctx, KQ_ERR_UNSUPPORTED, "more than %d distinct aggregate inputs", MAX_INPUTS); }
+            if (h->inputs.size() >= (size_t)MAX_INPUTS) { hashagg_delete_host(h); return kq_fail(ctx, KQ_ERR_UNSUPPORTED, "more than %d distinct aggregate inputs", MAX_INPUTS); }
             agg_inputs[i]->rc.fetch_add(1);
             h->inputs.push_back(agg_inputs[i]);
             idx = (int)h->inputs.size() - 1;
@@ -278,7 +284,17 @@ int kq_hashagg_create(kq_ctx* ctx, kq_expr* pred, kq_expr* const* group_exprs, i
         h->input_count_only.push_back(flags[i] == 0);
     }
     h->stride = (w + 3) / 4 * 4;
-    if (h->stride > MAX_REC_WORDS) { kq_hashagg_free(h); return kq_fail(ctx, KQ_ERR_UNSUPPORTED, "aggregate record too wide"); }
+    if (h->stride > MAX_REC_WORDS) { hashagg_delete_host(h); return kq_fail(ctx, KQ_ERR_UNSUPPORTED, "aggregate record too wide"); }
+    *out = h;
+    return KQ_OK;
+}
+
+int kq_hashagg_create(kq_ctx* ctx, kq_expr* pred, kq_expr* const* group_exprs, int ngroup, const int* agg_kinds,
+                      kq_expr* const* agg_inputs, int nagg, int64_t expected_groups, kq_hashagg** out) {
+    if (!ctx || !out || ngroup < 0 || nagg < 0) return KQ_ERR_ILLEGAL_ARGUMENT;
+    cudaSetDevice(ctx->device);
+    kq_hashagg* h = nullptr;
+    KQ_RET(hashagg_new(ctx, pred, group_exprs, ngroup, agg_kinds, agg_inputs, nagg, expected_groups, &h));
     cudaError_t e = cudaMalloc(&h->d_counters, 64);
     if (e == cudaSuccess) e = cudaMemsetAsync(h->d_counters, 0, 64, ctx->stream);
     if (e != cudaSuccess) { kq_hashagg_free(h); return kq_cuda_fail(ctx, e, "cudaMalloc"); }
@@ -304,12 +320,11 @@ int kq_hashagg_free(kq_hashagg* h) {
     return KQ_OK;
 }
 
-int kq_hashagg_update(kq_ctx* ctx, kq_hashagg* h, kq_batch* input) {
-    if (!ctx || !h || !input) return KQ_ERR_ILLEGAL_ARGUMENT;
-    cudaSetDevice(ctx->device);
-    int64_t n; KQ_RET(kq_batch_resolve_rows(ctx, input, &n));
-    for (kq_col* c : input->cols) KQ_RET(kq_col_resolve_rows(ctx, c, nullptr));
+}  // extern "C"
 
+// Everything about an aggregate launch that depends on the query SHAPE only: generated source, stage
+// plan, front-end layout. Fills the shape-dependent fields of A. No CUDA calls (kq_explain_hashagg).
+static int plan_agg(kq_ctx* ctx, kq_hashagg* h, kq_batch* input, int smem_optin, AggArgs& A, std::string* defines_out, std::string* gen_out) {
     // generate: [predicate -> selection] keys..., inputs...
     KqCodegen cg;
     KQ_RET(cg.begin(ctx, input));
@@ -330,6 +345,9 @@ int kq_hashagg_update(kq_ctx* ctx, kq_hashagg* h, kq_batch* input) {
         if (v.type == KQ_F64) key_f64_mask |= 1u << k;
         kt.push_back(v.type);
     }
+    std::vector<int> in_cnt;            // front-end count slot per input: 0 = "every selected row" (input statically non-null)
+    int ncnt = 1;
+    bool cnt0_used = false;
     for (size_t i = 0; i < h->inputs.size(); i++) {
         int t; bool nl;
         KQ_RET(cg.infer(h->inputs[i], &t, &nl));
@@ -345,61 +363,89 @@ int kq_hashagg_update(kq_ctx* ctx, kq_hashagg* h, kq_batch* input) {
         const KqVal a = cg.as_array(v);
         cg.line("sink.template set_in<" + std::to_string(i) + ">(" + a.v + ", " + a.okx() + ");");
         it.push_back(t);
+        if (a.nullable()) in_cnt.push_back(ncnt++); else { in_cnt.push_back(0); cnt0_used = true; }
     }
     const std::string eval_body = cg.take_body();
     if (!h->typed) { h->key_types = kt; h->input_types = it; h->typed = true; }
     else if (kt != h->key_types || it != h->input_types) return kq_fail(ctx, KQ_ERR_ILLEGAL_STATE, "batch schema differs from earlier batches");
     for (size_t i = 0; i < h->inputs.size(); i++) {
         if (it[i] != KQ_F64) h->in[i].flags |= F_INT; else h->in[i].flags &= ~F_INT;
-        bool is_int = h->in[i].flags & F_INT;
         if (h->in[i].rec_max >= 0) h->rec_init[h->in[i].rec_max] = 0ULL;
-        (void)is_int;
     }
-    if (n == 0) return KQ_OK;
-
-    AggArgs A;
-    memset(&A, 0, sizeof A);
-    A.n = n; A.ntiles = (n + TILE - 1) / TILE;
     A.key_f64_mask = key_f64_mask;
 
-    // front-end layout
-    int NI = (int)h->inputs.size(), ns = 0, nm = 0;
+    // front-end layout (compile-time constants of the specialised kernel)
+    const int NI = (int)h->inputs.size(), NK = (int)h->groups.size();
+    int ns = 0, nm = 0;
+    uint32_t mm_ismin = 0;
+    std::vector<int> mm_word;
     for (int i = 0; i < NI; i++) {
         AggInput& d = h->in[i];
         d.fe_sum = (d.flags & F_SUM) ? ns++ : -1;
         d.fe_min = (d.flags & F_MIN) ? nm++ : -1;
         d.fe_max = (d.flags & F_MAX) ? nm++ : -1;
-        if (d.fe_sum >= 0) { A.fe_sum_word[d.fe_sum] = d.rec_sum; if (d.flags & F_INT) A.fe_sum_int |= 1u << d.fe_sum; }
-        if (d.fe_min >= 0) { A.fe_mm_word[d.fe_min] = d.rec_min; A.fe_mm_ismin |= 1u << d.fe_min; }
-        if (d.fe_max >= 0) A.fe_mm_word[d.fe_max] = d.rec_max;
+        if (d.fe_min >= 0) { mm_word.push_back(d.rec_min); mm_ismin |= 1u << d.fe_min; }
+        if (d.fe_max >= 0) mm_word.push_back(d.rec_max);
     }
-    A.fe_nsum = ns; A.fe_nmm = nm;
-    int KW = (int)h->groups.size() + 1;
-    int fixed = DIR_SLOTS * KW * 8 + DIR_SLOTS * 4 + FE_MAX_GROUPS * (4 + 8 + 8 * nm) + 64;
-    int per_group = WARPS * 32 * (4 * NI + 8 * ns);
     // stage ring first (2..4 stages within ~64 KB, more only if two stages need it), front end gets the rest
     std::string stage_defs = cg.plan_stages(64 * 1024, 1, TILE, &A.sp);
     if (A.sp.nstages < 2) stage_defs = cg.plan_stages(std::min(2 * A.sp.stage_bytes, 112 * 1024), 2, TILE, &A.sp);
     A.sp.nstages = std::max(1, std::min(A.sp.nstages, AGG_MAX_STAGES));
     A.q = cg.args;
     const int ring = A.sp.nstages * A.sp.stage_bytes;
-    int budget = ctx->max_smem_optin - 2048 - fixed - ring;
-    int fg = per_group > 0 ? std::min(FE_MAX_GROUPS, budget / per_group) : FE_MAX_GROUPS;
+    const int entry_words = (NK + 2) / 2 * 2;
+    const int per_group = WARPS * 32 * (4 * ncnt + 8 * ns) + 8 + 4 + 8 * nm;
+    int dir_slots = 1024;
+    int budget = smem_optin - 3072 - ring;
+    while (dir_slots > 256 && dir_slots * entry_words * 8 + 16 * per_group > budget) dir_slots >>= 1;
+    budget -= dir_slots * entry_words * 8 + 64;
+    int fg = std::min(FE_MAX_GROUPS, budget / per_group);
     if (fg < 1) fg = 0;
     A.fe_groups = fg;
-    int off = ring;
-    A.off_fe = off;
-    A.off_dirkeys = off; off += DIR_SLOTS * KW * 8;
-    A.off_gslot = off; off += FE_MAX_GROUPS * 8;
-    A.off_mm = off; off += FE_MAX_GROUPS * 8 * nm;
-    A.off_sum = off; off += WARPS * fg * ns * 32 * 8;
-    A.off_cnt = off; off += WARPS * fg * NI * 32 * 4;
-    A.off_dirstate = off; off += DIR_SLOTS * 4;
-    A.off_gid2slot = off; off += FE_MAX_GROUPS * 4;
-    A.smem_bytes = (off + 15) / 16 * 16;
-    const std::string gen = "namespace kq {\n" + stage_defs + "struct Q {\n    template <class Sink> static __device__ __forceinline__ void eval(const QArgs& q, RowCtx& rc, Sink& sink) {\n" +
+    A.smem_bytes = ring + dir_slots * entry_words * 8 + std::max(fg, 1) * 12 + fg * nm * 8 + WARPS * fg * 32 * (8 * ns + 4 * ncnt);
+    A.smem_bytes = (A.smem_bytes + 127) / 128 * 128;
+
+    auto arr = [&](const char* type, const char* name, int nelem, auto get) {
+        std::string s = std::string("    static constexpr ") + type + " " + name + "[" + std::to_string(std::max(nelem, 1)) + "] = {";
+        for (int i = 0; i < std::max(nelem, 1); i++) s += (i ? ", " : "") + std::to_string(i < nelem ? get(i) : 0);
+        return s + "};\n";
+    };
+    std::string consts;
+    consts += "    static constexpr int NKEYS = " + std::to_string(NK) + ", NIN = " + std::to_string(NI) + ", NCNT = " + std::to_string(ncnt) +
+              ", NSUM = " + std::to_string(ns) + ", NMM = " + std::to_string(nm) + ";\n";
+    consts += std::string("    static constexpr bool CNT0_USED = ") + (cnt0_used ? "true" : "false") + ";\n";
+    consts += "    static constexpr uint32_t KEY_F64_MASK = " + std::to_string(key_f64_mask) + "u, MM_ISMIN = " + std::to_string(mm_ismin) + "u;\n";
+    consts += arr("int", "IN_FLAGS", NI, [&](int i) { return h->in[i].flags; });
+    consts += arr("int", "IN_CNT", NI, [&](int i) { return in_cnt[(size_t)i]; });
+    consts += arr("int", "REC_NN", NI, [&](int i) { return h->in[i].rec_nn; });
+    consts += arr("int", "REC_SUM", NI, [&](int i) { return h->in[i].rec_sum; });
+    consts += arr("int", "FE_SUM", NI, [&](int i) { return h->in[i].fe_sum; });
+    consts += arr("int", "FE_MIN", NI, [&](int i) { return h->in[i].fe_min; });
+    consts += arr("int", "FE_MAX", NI, [&](int i) { return h->in[i].fe_max; });
+    consts += arr("int", "MM_WORD", nm, [&](int i) { return mm_word[(size_t)i]; });
+    *gen_out = "namespace kq {\n" + stage_defs + "struct Q {\n" + consts +
+                            "    template <class Sink> static __device__ __forceinline__ void eval(const QArgs& q, RowCtx& rc, Sink& sink) {\n" +
                             eval_body + "    }\n};\n}  // namespace kq\n";
-    const std::string defines = "#define KQ_R " + std::to_string(AGG_R) + "\n#define KQ_WARPS " + std::to_string(AGG_WARPS) + "\n";
+    *defines_out = "#define KQ_R " + std::to_string(AGG_R) + "\n#define KQ_WARPS " + std::to_string(AGG_WARPS) + "\n#define KQ_STAGES " +
+                                std::to_string(A.sp.nstages) + "\n#define KQ_FE_GROUPS " + std::to_string(fg) + "\n#define KQ_DIR_SLOTS " +
+                                std::to_string(dir_slots) + "\n";
+    return KQ_OK;
+}
+
+extern "C" {
+
+int kq_hashagg_update(kq_ctx* ctx, kq_hashagg* h, kq_batch* input) {
+    if (!ctx || !h || !input) return KQ_ERR_ILLEGAL_ARGUMENT;
+    cudaSetDevice(ctx->device);
+    int64_t n; KQ_RET(kq_batch_resolve_rows(ctx, input, &n));
+    for (kq_col* c : input->cols) KQ_RET(kq_col_resolve_rows(ctx, c, nullptr));
+
+    AggArgs A;
+    memset(&A, 0, sizeof A);
+    std::string defines, gen;
+    KQ_RET(plan_agg(ctx, h, input, ctx->max_smem_optin, A, &defines, &gen));
+    if (n == 0) return KQ_OK;
+    A.n = n; A.ntiles = (n + TILE - 1) / TILE;
     void* kernel = nullptr;
     KQ_RET(kq_jit_kernel(ctx, defines, gen, KQ_SKEL_AGG, "kq_hash_aggregate", A.smem_bytes, &kernel));
     int grid = (int)std::min<int64_t>(A.ntiles, (int64_t)ctx->sm_count);
@@ -441,6 +487,23 @@ int kq_hashagg_update(kq_ctx* ctx, kq_hashagg* h, kq_batch* input) {
         }
     }
     return KQ_OK;
+}
+
+int kq_explain_hashagg(kq_expr* pred, kq_expr* const* group_exprs, int ngroup, const int* agg_kinds, kq_expr* const* agg_inputs, int nagg,
+                       int ncols, const int* types, const int* nullable, int compile, char* source, size_t source_cap) {
+    if (ncols < 0 || ngroup < 0 || nagg < 0 || (ncols > 0 && !types)) return KQ_ERR_ILLEGAL_ARGUMENT;
+    kq_ctx fake;
+    KqSchemaBatch sb(ncols, types, nullable);
+    kq_hashagg* h = nullptr;
+    int st = hashagg_new(&fake, pred, group_exprs, ngroup, agg_kinds, agg_inputs, nagg, 0, &h);
+    AggArgs A;
+    memset(&A, 0, sizeof A);
+    std::string defines, gen;
+    if (st == KQ_OK) st = plan_agg(&fake, h, &sb.batch, 232448, A, &defines, &gen);
+    if (st == KQ_OK && compile) st = kq_jit_compile_only(&fake, defines, gen, KQ_SKEL_AGG);
+    kq_copy_text(st == KQ_OK ? defines + gen : fake.last_error, source, source_cap);
+    if (h) hashagg_delete_host(h);
+    return st;
 }
 
 int kq_hashagg_num_groups(kq_ctx* ctx, kq_hashagg* h, int64_t* n) {

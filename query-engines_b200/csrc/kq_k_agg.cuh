@@ -1,17 +1,17 @@
 // kq_k_agg.cuh — kernel skeleton of HashAggregateExec (Main.kt:605-660) and its accumulators
 // (Main.kt:514-562), specialised per query: the generated `struct Q` evaluates the optional FilterExec
 // predicate, the group-key and the aggregate-input expressions (fused ProjectionExec) for R rows per
-// thread and hands them to the sink; the skeleton runs the accumulate step of the drain loop
-// (Main.kt:620-632).
+// thread and hands them to the sink; it also carries the aggregate layout as compile-time constants.
+// The skeleton runs the accumulate step of the drain loop (Main.kt:620-632).
 //
 // Two tiers of state:
 //   * a GLOBAL open-addressing table in HBM (kq_aggtable.cuh), the source of truth;
-//   * a per-CTA FRONT END in shared memory for the first `fe_groups` distinct keys a CTA meets: a key
-//     directory shared by the CTA plus LANE-PRIVATE count/sum accumulators (one copy per lane per
-//     warp: no atomics, no bank conflicts) and a CTA-shared MIN/MAX table that is only touched when a
-//     value beats the current extreme. Front ends are merged into the global table once, at CTA exit.
-//     Low-cardinality GROUP BYs (BASELINE configs 3 and 5) run entirely in the front end; rows whose
-//     key does not fit go straight to the global table with atomics (config 4).
+//   * a per-CTA FRONT END in shared memory for the first FG distinct keys a CTA meets: a key directory
+//     shared by the CTA plus LANE-PRIVATE count/sum accumulators (one copy per lane per warp: plain
+//     read-modify-write, no atomics, no bank conflicts) and a CTA-shared MIN/MAX table that is only
+//     written when a value beats the current extreme. Front ends are merged into the global table
+//     once, at CTA exit. Low-cardinality GROUP BYs (BASELINE configs 3 and 5) run entirely in the
+//     front end; rows whose key does not fit go straight to the global table with atomics (config 4).
 //
 // Accumulator semantics (oracle: MaxAccumulator etc.): nulls are skipped; a group whose inputs were
 // all null yields null, except COUNT; MIN/MAX use a total order in which canonical NaN sorts above
@@ -24,21 +24,24 @@
 
 namespace kq {
 
-// KQ_WARPS consumer warps (the lane-private front end scales with the warp count) + 1 service warp (TMA producer)
-constexpr int WARPS = KQ_WARPS;
-constexpr int BLOCK = WARPS * 32;
+// Service warp first (the warp arbiter favours high warp ids: a polling producer must not starve consumers).
+constexpr int WARPS = KQ_WARPS;              // consumer warps (the lane-private front end scales with them)
+constexpr int PRODUCER_WARP = 0;
+constexpr int THREADS = WARPS * 32 + 32;
 constexpr int TILE = WARPS * WARP_ROWS;
-constexpr int SERVICE_WARP = WARPS;
-constexpr int THREADS = BLOCK + 32;
-constexpr uint32_t DIR_EMPTY = 0, DIR_BUSY = 1, DIR_GLOBAL = 0xFFFFFFFFu;   // FULL = gid + 2
+constexpr int S = KQ_STAGES;
+constexpr int FG = KQ_FE_GROUPS;             // front-end capacity in groups (0: no front end)
+constexpr int DIR = KQ_DIR_SLOTS;            // directory slots (power of two)
+constexpr int ENTRY_WORDS = (Q::NKEYS + 2) / 2 * 2;      // [0] = {state:32, key nullmask:32}, [1..NKEYS] = key words; 16-byte multiple
+constexpr uint32_t DIR_EMPTY = 0, DIR_BUSY = 1, DIR_GLOBAL = 0xFFFFFFFFu;   // else gid + 2
 
 // What the generated code fills per tile: selection, key words and aggregate inputs of the R owned rows.
 struct AggSink {
     uint32_t sel;
-    uint64_t key[MAX_KEYS][R];
-    uint32_t keyok[MAX_KEYS];
-    uint64_t in[MAX_INPUTS][R];
-    uint32_t inok[MAX_INPUTS];
+    uint64_t key[Q::NKEYS > 0 ? Q::NKEYS : 1][R];
+    uint32_t keyok[Q::NKEYS > 0 ? Q::NKEYS : 1];
+    uint64_t in[Q::NIN > 0 ? Q::NIN : 1][R];
+    uint32_t inok[Q::NIN > 0 ? Q::NIN : 1];
     template <int K>
     __device__ __forceinline__ void set_key(const uint64_t (&v)[R], uint32_t ok) {
 #pragma unroll
@@ -53,69 +56,159 @@ struct AggSink {
     }
 };
 
-// Look the key up in the CTA directory; returns the front-end group id or -1 (row goes global).
-__device__ __forceinline__ int dir_lookup(const AggArgs& A, uint64_t* dirkeys, uint32_t* dirstate, uint32_t* gid2slot,
-                                          uint32_t* dir_count, uint64_t h, const uint64_t (&kw)[MAX_KEYS], uint32_t nullmask) {
-    const int KW = A.nkeys + 1;
-    uint32_t slot = (uint32_t)(h >> 40) & (DIR_SLOTS - 1);
+struct FrontEnd {
+    uint64_t* dir;            // [DIR][ENTRY_WORDS]
+    uint32_t* dir_count;
+    uint32_t* gid2slot;       // [FG]
+    uint64_t* mm;             // [FG][NMM]  CTA-shared MIN/MAX in order-mapped form
+    uint32_t* cnt;            // this warp: [FG][NCNT][32]
+    uint64_t* sum;            // this warp: [FG][NSUM][32]
+};
+
+// Group id of a key in the CTA directory, inserting it while there is room; -1 = the row goes to the global table.
+__device__ __forceinline__ int dir_lookup(const FrontEnd& fe, uint64_t h, const uint64_t (&kw)[MAX_KEYS], uint32_t nullmask) {
+    uint32_t slot = (uint32_t)(h >> 40) & (DIR - 1);
 #pragma unroll 1
     for (int probe = 0; probe < 8; probe++) {
-        uint32_t st = *reinterpret_cast<volatile uint32_t*>(dirstate + slot);
+        uint64_t* e = fe.dir + (size_t)slot * ENTRY_WORDS;
+        const uint4 q = lds_v4(e);
+        uint32_t st = q.x;
         if (st == DIR_EMPTY) {
-            uint32_t old = atomicCAS(dirstate + slot, DIR_EMPTY, DIR_BUSY);
+            const uint32_t old = atomicCAS(reinterpret_cast<uint32_t*>(e), DIR_EMPTY, DIR_BUSY);
             if (old == DIR_EMPTY) {
-                uint32_t gid = atomicAdd(dir_count, 1u);
-                uint64_t* dk = dirkeys + slot * KW;
-                dk[0] = nullmask;
+                const uint32_t gid = atomicAdd(fe.dir_count, 1u);
+                reinterpret_cast<uint32_t*>(e)[1] = nullmask;
 #pragma unroll
-                for (int k = 0; k < MAX_KEYS; k++) if (k < A.nkeys) dk[1 + k] = kw[k];
-                bool fits = gid < (uint32_t)A.fe_groups;
-                if (fits) gid2slot[gid] = slot;
+                for (int k = 0; k < Q::NKEYS; k++) e[1 + k] = kw[k];
+                const bool fits = gid < (uint32_t)FG;
+                if (fits) fe.gid2slot[gid] = slot;
                 __threadfence_block();
-                *reinterpret_cast<volatile uint32_t*>(dirstate + slot) = fits ? gid + 2 : DIR_GLOBAL;
+                *reinterpret_cast<volatile uint32_t*>(e) = fits ? gid + 2 : DIR_GLOBAL;
                 return fits ? (int)gid : -1;
             }
             st = old;
+            if (st == DIR_BUSY) return -1;
+            // published by somebody else in the meantime: fall through and compare (re-read below)
         }
         if (st == DIR_BUSY) return -1;             // being published: this row takes the global path
-        const uint64_t* dk = dirkeys + slot * KW;
-        bool eq = dk[0] == (uint64_t)nullmask;
+        uint32_t e_nm = q.y;
+        uint64_t e_k0 = (uint64_t)q.z | ((uint64_t)q.w << 32);
+        if (st != q.x) {                           // the entry was published between our load and our CAS: read it again
+            e_nm = reinterpret_cast<volatile uint32_t*>(e)[1];
+            e_k0 = *reinterpret_cast<volatile uint64_t*>(e + 1);
+        }
+        bool eq = e_nm == nullmask;
+        if constexpr (Q::NKEYS >= 1) eq &= e_k0 == kw[0];
 #pragma unroll
-        for (int k = 0; k < MAX_KEYS; k++) if (k < A.nkeys) eq &= dk[1 + k] == kw[k];
+        for (int k = 1; k < Q::NKEYS; k++) eq &= *reinterpret_cast<volatile uint64_t*>(e + 1 + k) == kw[k];
         if (eq) return st == DIR_GLOBAL ? -1 : (int)(st - 2);
-        slot = (slot + 1) & (DIR_SLOTS - 1);
+        slot = (slot + 1) & (DIR - 1);
     }
     return -1;
 }
 
-extern "C" __global__ void __launch_bounds__(THREADS, 1) kq_hash_aggregate(const __grid_constant__ AggArgs A) {
-    extern __shared__ __align__(128) unsigned char smem[];
-    __shared__ uint64_t full[MAX_STAGES], empty[MAX_STAGES];
-    __shared__ long long tile_of[MAX_STAGES];
-    __shared__ uint32_t s_dir_count;
-    uint64_t* dirkeys = reinterpret_cast<uint64_t*>(smem + A.off_dirkeys);
-    uint32_t* dirstate = reinterpret_cast<uint32_t*>(smem + A.off_dirstate);
-    uint32_t* gid2slot = reinterpret_cast<uint32_t*>(smem + A.off_gid2slot);
-    uint64_t* gslot = reinterpret_cast<uint64_t*>(smem + A.off_gslot);
-    uint64_t* mm = reinterpret_cast<uint64_t*>(smem + A.off_mm);
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int NI = A.ninputs, NS = A.fe_nsum, NM = A.fe_nmm, FG = A.fe_groups;
-    const int S = A.sp.nstages;
-    // lane-private accumulators of this warp: cnt[(gid*NI + i)*32 + lane], sum[(gid*NS + s)*32 + lane]
-    uint32_t* cnt = reinterpret_cast<uint32_t*>(smem + A.off_cnt) + (size_t)(warp % WARPS) * FG * NI * 32;
-    uint64_t* sum = reinterpret_cast<uint64_t*>(smem + A.off_sum) + (size_t)(warp % WARPS) * FG * NS * 32;
+// Front-end accumulate of input I for one row (lane-private slots: plain read-modify-write).
+template <int I>
+__device__ __forceinline__ void fe_accumulate(const FrontEnd& fe, int gid, int lane, const AggSink& sink, int r) {
+    if constexpr (I < Q::NIN) {
+        constexpr int FL = Q::IN_FLAGS[I];
+        const bool valid = (sink.inok[I] >> r) & 1u;
+        if (Q::IN_CNT[I] > 0 && valid) fe.cnt[((gid * Q::NCNT + Q::IN_CNT[I]) << 5) + lane] += 1u;     // slot 0 (all rows) is counted by the caller
+        if constexpr ((FL & (F_SUM | F_MIN | F_MAX)) != 0) {
+            if (valid) {
+                const uint64_t v = sink.in[I][r];
+                if constexpr ((FL & F_SUM) != 0) {
+                    uint64_t* p = fe.sum + ((gid * Q::NSUM + Q::FE_SUM[I]) << 5) + lane;
+                    if constexpr ((FL & F_INT) != 0) *p += v;
+                    else *p = as_u64(__dadd_rn(as_f64(*p), as_f64(v)));
+                }
+                if constexpr ((FL & (F_MIN | F_MAX)) != 0) {
+                    constexpr bool is_int = (FL & F_INT) != 0;
+                    const uint64_t m = order_map(is_int ? v : canon_nan(v), is_int);
+                    if constexpr ((FL & F_MIN) != 0) {
+                        uint64_t* p = fe.mm + gid * Q::NMM + Q::FE_MIN[I];
+                        if (m < *reinterpret_cast<volatile uint64_t*>(p)) atomicMin(reinterpret_cast<unsigned long long*>(p), (unsigned long long)m);
+                    }
+                    if constexpr ((FL & F_MAX) != 0) {
+                        uint64_t* p = fe.mm + gid * Q::NMM + Q::FE_MAX[I];
+                        if (m > *reinterpret_cast<volatile uint64_t*>(p)) atomicMax(reinterpret_cast<unsigned long long*>(p), (unsigned long long)m);
+                    }
+                }
+            }
+        }
+        fe_accumulate<I + 1>(fe, gid, lane, sink, r);
+    }
+}
 
-    for (int i = A.off_fe + threadIdx.x * 4; i < A.smem_bytes; i += THREADS * 4) *reinterpret_cast<uint32_t*>(smem + i) = 0;
+// Accumulate one row straight into its record of the global table.
+template <int I>
+__device__ __forceinline__ void global_accumulate_all(const AggArgs& A, uint64_t* rec, const AggSink& sink, int r) {
+    if constexpr (I < Q::NIN) {
+        if ((sink.inok[I] >> r) & 1u) global_accumulate(rec, A.in[I], sink.in[I][r]);
+        global_accumulate_all<I + 1>(A, rec, sink, r);
+    }
+}
+
+// Merge the lane-private slots of front-end group g (this warp's copy) into its global record.
+template <int I>
+__device__ __forceinline__ void fe_merge_input(const FrontEnd& fe, uint64_t* rec, int g, int lane, const unsigned long long (&c)[Q::NCNT]) {
+    if constexpr (I < Q::NIN) {
+        constexpr int FL = Q::IN_FLAGS[I];
+        const unsigned long long n = c[Q::IN_CNT[I]];
+        if (n != 0) {                                       // this warp saw no non-null value of input I in group g otherwise
+            if (lane == 0) atomicAdd(reinterpret_cast<unsigned long long*>(rec + Q::REC_NN[I]), n);
+            if constexpr ((FL & F_SUM) != 0) {
+                uint64_t x = fe.sum[((g * Q::NSUM + Q::FE_SUM[I]) << 5) + lane];
+                if constexpr ((FL & F_INT) != 0) {
+#pragma unroll
+                    for (int o = 16; o; o >>= 1) x += __shfl_xor_sync(0xffffffffu, x, o);
+                    if (lane == 0) atomicAdd(reinterpret_cast<unsigned long long*>(rec + Q::REC_SUM[I]), (unsigned long long)x);
+                } else {
+                    double f = as_f64(x);
+#pragma unroll
+                    for (int o = 16; o; o >>= 1) f = __dadd_rn(f, __shfl_xor_sync(0xffffffffu, f, o));
+                    if (lane == 0) atomicAdd(reinterpret_cast<double*>(rec + Q::REC_SUM[I]), f);
+                }
+            }
+        }
+        fe_merge_input<I + 1>(fe, rec, g, lane, c);
+    }
+}
+
+extern "C" __global__ void __launch_bounds__(THREADS, 1) kq_hash_aggregate(const __grid_constant__ AggArgs A) {
+    // shared memory: [S stages][directory][gslot][gid2slot][mm][per-warp sums][per-warp counts]
+    extern __shared__ __align__(128) unsigned char smem[];
+    __shared__ uint64_t full[S], empty[S];
+    __shared__ long long tile_of[S];
+    __shared__ uint32_t s_dir_count;
+    const int wid = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int warp = wid - 1;                 // consumer warp index
+    constexpr int NCNT = Q::NCNT, NSUM = Q::NSUM, NMM = Q::NMM;
+    unsigned char* p0 = smem + (size_t)S * A.sp.stage_bytes;
+    const size_t fe_begin = (size_t)(p0 - smem);
+    FrontEnd fe;
+    fe.dir = reinterpret_cast<uint64_t*>(p0);            p0 += (size_t)DIR * ENTRY_WORDS * 8;
+    uint64_t* gslot = reinterpret_cast<uint64_t*>(p0);   p0 += (size_t)(FG > 0 ? FG : 1) * 8;
+    fe.mm = reinterpret_cast<uint64_t*>(p0);             p0 += (size_t)FG * NMM * 8;
+    uint64_t* sum0 = reinterpret_cast<uint64_t*>(p0);    p0 += (size_t)WARPS * FG * NSUM * 32 * 8;
+    uint32_t* cnt0 = reinterpret_cast<uint32_t*>(p0);    p0 += (size_t)WARPS * FG * NCNT * 32 * 4;
+    fe.gid2slot = reinterpret_cast<uint32_t*>(p0);       p0 += (size_t)(FG > 0 ? FG : 1) * 4;
+    const size_t fe_end = (size_t)(p0 - smem);
+    fe.dir_count = &s_dir_count;
+    fe.sum = sum0 + (size_t)(warp < 0 ? 0 : warp) * FG * NSUM * 32;
+    fe.cnt = cnt0 + (size_t)(warp < 0 ? 0 : warp) * FG * NCNT * 32;
+
+    for (size_t i = fe_begin + threadIdx.x * 4; i < fe_end; i += THREADS * 4) *reinterpret_cast<uint32_t*>(smem + i) = 0;
     if (threadIdx.x == 0) {
         s_dir_count = 0;
         for (int s = 0; s < S; s++) { mbar_init(&full[s], 1); mbar_init(&empty[s], WARPS); }
         mbar_fence_init();
     }
     __syncthreads();
-    for (int i = threadIdx.x; i < FG * NM; i += THREADS) mm[i] = ((A.fe_mm_ismin >> (i % NM)) & 1u) ? ~0ULL : 0ULL;
+    for (int i = threadIdx.x; i < FG * NMM; i += THREADS) fe.mm[i] = ((Q::MM_ISMIN >> (i % (NMM > 0 ? NMM : 1))) & 1u) ? ~0ULL : 0ULL;
     __syncthreads();
 
-    if (warp == SERVICE_WARP) {
+    if (wid == PRODUCER_WARP) {
         if (lane == 0) {
             for (int k = 0;; k++) {
                 const int s = k % S;
@@ -131,121 +224,104 @@ extern "C" __global__ void __launch_bounds__(THREADS, 1) kq_hash_aggregate(const
             }
         }
     } else {
-    AggSink sink;
-    bool bypass = FG == 0;
-    for (int k = 0;; k++) {
-        const int s = k % S;
-        mbar_wait(&full[s], (k / S) & 1);
-        const long long tile = tile_of[s];
-        if (tile < 0) break;
-        RowCtx rc;
-        rowctx_init(rc, warp, tile, TILE, A.n, A.err, smem + (size_t)s * A.sp.stage_bytes);
-        sink.sel = rc.inr;
-        Q::eval(A.q, rc, sink);
-        __syncwarp();
-        if (lane == 0) mbar_arrive(&empty[s]);       // everything needed is in registers now
+        AggSink sink;
+        bool bypass = FG == 0;
+        for (int k = 0;; k++) {
+            const int s = k % S;
+            mbar_wait(&full[s], (k / S) & 1);
+            const long long tile = tile_of[s];
+            if (tile < 0) break;
+            RowCtx rc;
+            rowctx_init(rc, warp, tile, TILE, A.n, A.err, smem + (size_t)s * A.sp.stage_bytes);
+            sink.sel = rc.inr;
+            Q::eval(A.q, rc, sink);
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&empty[s]);       // everything needed is in registers now
 
-        int fe_hits = 0, rows = 0;
+            // pass 1: key -> hash -> front-end group id for the R owned rows (independent chains)
+            uint64_t hh[R];
+            uint32_t nm[R];
+            int gid[R];
 #pragma unroll
-        for (int r = 0; r < R; r++) {
-            if (!((sink.sel >> r) & 1u)) continue;
-            uint64_t kw[MAX_KEYS];
-            uint32_t nullmask = 0;
+            for (int r = 0; r < R; r++) {
+                uint64_t kw[MAX_KEYS];
+                uint32_t nullmask = 0;
 #pragma unroll
-            for (int k2 = 0; k2 < MAX_KEYS; k2++) {
-                kw[k2] = 0;
-                if (k2 < A.nkeys) {
-                    if ((sink.keyok[k2] >> r) & 1u) kw[k2] = ((A.key_f64_mask >> k2) & 1u) ? canon_nan(sink.key[k2][r]) : sink.key[k2][r];
-                    else nullmask |= 1u << k2;
-                }
-            }
-            const uint64_t h = hash_key(kw, nullmask, A.nkeys);
-            int gid = -1;
-            if (!bypass) gid = dir_lookup(A, dirkeys, dirstate, gid2slot, &s_dir_count, h, kw, nullmask);
-            rows++;
-            if (gid >= 0) {
-                fe_hits++;
-#pragma unroll
-                for (int i = 0; i < MAX_INPUTS; i++) {
-                    if (i < NI && ((sink.inok[i] >> r) & 1u)) {
-                        const AggInput d = A.in[i];
-                        const uint64_t v = sink.in[i][r];
-                        cnt[(gid * NI + i) * 32 + lane] += 1u;
-                        if (d.flags & F_SUM) {
-                            uint64_t* p = sum + (gid * NS + d.fe_sum) * 32 + lane;
-                            if (d.flags & F_INT) *p += v;
-                            else *p = (uint64_t)__double_as_longlong(__dadd_rn(__longlong_as_double((long long)*p), __longlong_as_double((long long)v)));
-                        }
-                        if (d.flags & (F_MIN | F_MAX)) {
-                            const bool is_int = d.flags & F_INT;
-                            uint64_t m = order_map(is_int ? v : canon_nan(v), is_int);
-                            if (d.flags & F_MIN) { uint64_t* p = mm + gid * NM + d.fe_min; if (m < *reinterpret_cast<volatile uint64_t*>(p)) atomicMin(reinterpret_cast<unsigned long long*>(p), (unsigned long long)m); }
-                            if (d.flags & F_MAX) { uint64_t* p = mm + gid * NM + d.fe_max; if (m > *reinterpret_cast<volatile uint64_t*>(p)) atomicMax(reinterpret_cast<unsigned long long*>(p), (unsigned long long)m); }
-                        }
+                for (int k2 = 0; k2 < MAX_KEYS; k2++) {
+                    kw[k2] = 0;
+                    if (k2 < Q::NKEYS) {
+                        if ((sink.keyok[k2] >> r) & 1u) kw[k2] = ((Q::KEY_F64_MASK >> k2) & 1u) ? canon_nan(sink.key[k2][r]) : sink.key[k2][r];
+                        else nullmask |= 1u << k2;
+                        sink.key[k2][r] = kw[k2];
                     }
                 }
-            } else {
-                uint64_t* rec = table_find_or_insert(A, h, kw, nullmask);
+                nm[r] = nullmask;
+                hh[r] = hash_key(kw, nullmask, Q::NKEYS);
+                gid[r] = -1;
+                if (!bypass && ((sink.sel >> r) & 1u)) gid[r] = dir_lookup(fe, hh[r], kw, nullmask);
+            }
+            // pass 2: accumulate
+            int fe_hits = 0, rows = 0;
 #pragma unroll
-                for (int i = 0; i < MAX_INPUTS; i++)
-                    if (i < NI && ((sink.inok[i] >> r) & 1u)) global_accumulate(rec, A.in[i], sink.in[i][r]);
+            for (int r = 0; r < R; r++) {
+                if (!((sink.sel >> r) & 1u)) continue;
+                rows++;
+                if (gid[r] >= 0) {
+                    fe_hits++;
+                    if constexpr (Q::CNT0_USED) fe.cnt[((gid[r] * NCNT) << 5) + lane] += 1u;
+                    fe_accumulate<0>(fe, gid[r], lane, sink, r);
+                } else {
+                    uint64_t kw[MAX_KEYS];
+#pragma unroll
+                    for (int k2 = 0; k2 < MAX_KEYS; k2++) kw[k2] = k2 < Q::NKEYS ? sink.key[k2][r] : 0;
+                    uint64_t* rec = table_find_or_insert(A, hh[r], kw, nm[r]);
+                    global_accumulate_all<0>(A, rec, sink, r);
+                }
+            }
+            // once the directory is full and this warp mostly misses it, stop probing it (high cardinality)
+            if (!bypass) {
+                int hits = fe_hits, tot = rows;
+#pragma unroll
+                for (int o = 16; o; o >>= 1) { hits += __shfl_xor_sync(0xffffffffu, hits, o); tot += __shfl_xor_sync(0xffffffffu, tot, o); }
+                if (tot >= 64 && hits * 8 < tot && *reinterpret_cast<volatile uint32_t*>(&s_dir_count) >= (uint32_t)FG) bypass = true;
             }
         }
-        // once the directory is full and this warp mostly misses it, stop probing it (high cardinality)
-        if (!bypass) {
-            int hits = fe_hits, tot = rows;
-#pragma unroll
-            for (int o = 16; o; o >>= 1) { hits += __shfl_xor_sync(0xffffffffu, hits, o); tot += __shfl_xor_sync(0xffffffffu, tot, o); }
-            if (tot >= 64 && hits * 8 < tot && *reinterpret_cast<volatile uint32_t*>(&s_dir_count) >= (uint32_t)FG) bypass = true;
-        }
-    }
     }
 
     // ---- merge the front end into the global table ---------------------------------------------------
     __syncthreads();
     const int G = min((int)s_dir_count, FG);
     for (int g = threadIdx.x; g < G; g += THREADS) {
-        const uint64_t* dk = dirkeys + gid2slot[g] * (A.nkeys + 1);
+        const uint64_t* e = fe.dir + (size_t)fe.gid2slot[g] * ENTRY_WORDS;
         uint64_t kw[MAX_KEYS];
 #pragma unroll
-        for (int k = 0; k < MAX_KEYS; k++) kw[k] = k < A.nkeys ? dk[1 + k] : 0;
-        uint32_t nullmask = (uint32_t)dk[0];
-        uint64_t* rec = table_find_or_insert(A, hash_key(kw, nullmask, A.nkeys), kw, nullmask);
+        for (int k = 0; k < MAX_KEYS; k++) kw[k] = k < Q::NKEYS ? e[1 + k] : 0;
+        const uint32_t nullmask = (uint32_t)(e[0] >> 32);
+        uint64_t* rec = table_find_or_insert(A, hash_key(kw, nullmask, Q::NKEYS), kw, nullmask);
         gslot[g] = (uint64_t)(rec - A.table);
     }
     __syncthreads();
-    for (int g = 0; g < G && warp < WARPS; g++) {
-        uint64_t* rec = A.table + gslot[g];
-        for (int i = 0; i < NI; i++) {
-            unsigned long long c = cnt[(g * NI + i) * 32 + lane];
+    if (warp >= 0) {
+        for (int g = 0; g < G; g++) {
+            uint64_t* rec = A.table + gslot[g];
+            unsigned long long c[NCNT];
 #pragma unroll
-            for (int o = 16; o; o >>= 1) c += __shfl_xor_sync(0xffffffffu, c, o);
-            if (c == 0) continue;                                   // this warp saw no non-null value of input i in group g
-            const AggInput d = A.in[i];
-            if (lane == 0) atomicAdd(reinterpret_cast<unsigned long long*>(rec + d.rec_nn), c);
-            if (d.flags & F_SUM) {
-                uint64_t x = sum[(g * NS + d.fe_sum) * 32 + lane];
-                if (d.flags & F_INT) {
+            for (int j = 0; j < NCNT; j++) {
+                unsigned long long x = fe.cnt[((g * NCNT + j) << 5) + lane];
 #pragma unroll
-                    for (int o = 16; o; o >>= 1) x += __shfl_xor_sync(0xffffffffu, x, o);
-                    if (lane == 0) atomicAdd(reinterpret_cast<unsigned long long*>(rec + d.rec_sum), (unsigned long long)x);
-                } else {
-                    double f = __longlong_as_double((long long)x);
-#pragma unroll
-                    for (int o = 16; o; o >>= 1) f = __dadd_rn(f, __shfl_xor_sync(0xffffffffu, f, o));
-                    if (lane == 0) atomicAdd(reinterpret_cast<double*>(rec + d.rec_sum), f);
-                }
+                for (int o = 16; o; o >>= 1) x += __shfl_xor_sync(0xffffffffu, x, o);
+                c[j] = x;
             }
+            fe_merge_input<0>(fe, rec, g, lane, c);
         }
     }
-    for (int t = threadIdx.x; t < G * NM; t += THREADS) {
-        const int g = t / NM, m = t % NM;
-        const uint64_t v = mm[t];
-        uint64_t* p = A.table + gslot[g] + A.fe_mm_word[m];
-        if ((A.fe_mm_ismin >> m) & 1u) { if (v != ~0ULL) atomicMin(reinterpret_cast<unsigned long long*>(p), (unsigned long long)v); }
+    for (int t = threadIdx.x; t < G * NMM; t += THREADS) {
+        const int g = t / (NMM > 0 ? NMM : 1), m = t % (NMM > 0 ? NMM : 1);
+        const uint64_t v = fe.mm[t];
+        uint64_t* p = A.table + gslot[g] + Q::MM_WORD[m];
+        if ((Q::MM_ISMIN >> m) & 1u) { if (v != ~0ULL) atomicMin(reinterpret_cast<unsigned long long*>(p), (unsigned long long)v); }
         else if (v != 0ULL) atomicMax(reinterpret_cast<unsigned long long*>(p), (unsigned long long)v);
     }
 }
-
 
 }  // namespace kq

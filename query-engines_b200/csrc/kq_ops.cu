@@ -356,25 +356,6 @@ int run_operator(kq_ctx* ctx, kq_expr* pred, kq_expr* const* exprs, int nexprs, 
     return KQ_OK;
 }
 
-// A batch of columns that exist as a schema only (types + nullability), for kq_explain_*.
-struct SchemaBatch {
-    kq_batch batch;
-    std::vector<kq_col> cols;
-    SchemaBatch(int ncols, const int* types, const int* nullable) : cols((size_t)ncols) {
-        for (int i = 0; i < ncols; i++) {
-            cols[(size_t)i].type = types[i];
-            cols[(size_t)i].validity = (nullable && nullable[i]) ? reinterpret_cast<uint32_t*>(0x100) : nullptr;   // never dereferenced
-            batch.cols.push_back(&cols[(size_t)i]);
-        }
-    }
-};
-
-void copy_out(const std::string& s, char* dst, size_t cap) {
-    if (!dst || cap == 0) return;
-    size_t m = std::min(cap - 1, s.size());
-    memcpy(dst, s.data(), m);
-    dst[m] = 0;
-}
 
 }  // namespace
 
@@ -409,7 +390,7 @@ int kq_explain_filter_project(kq_expr* pred, kq_expr* const* exprs, int nexprs, 
                               int compile, char* source, size_t source_cap) {
     if (ncols < 0 || nexprs < 0 || (ncols > 0 && !types)) return KQ_ERR_ILLEGAL_ARGUMENT;
     kq_ctx fake;
-    SchemaBatch sb(ncols, types, nullable);
+    KqSchemaBatch sb(ncols, types, nullable);
     KqCodegen cg;
     OpsPlan P;
     std::vector<kq_expr*> ex(exprs, exprs + nexprs);
@@ -417,7 +398,7 @@ int kq_explain_filter_project(kq_expr* pred, kq_expr* const* exprs, int nexprs, 
     if (st == KQ_OK) st = plan_ops(&fake, cg, pred, ex, false, 232448, &P);
     if (st == KQ_OK && !P.fits) st = kq_fail(&fake, KQ_ERR_UNSUPPORTED, "outputs do not fit one launch (the operator would split them)");
     if (st == KQ_OK && compile) st = kq_jit_compile_only(&fake, P.defines, P.gen, KQ_SKEL_OPS);
-    copy_out(st == KQ_OK ? P.defines + P.gen : fake.last_error, source, source_cap);
+    kq_copy_text(st == KQ_OK ? P.defines + P.gen : fake.last_error, source, source_cap);
     return st;
 }
 

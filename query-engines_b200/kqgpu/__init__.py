@@ -98,6 +98,8 @@ SYMBOLS = {
                                           _PP, _PP, _I64P]),
     "kq_explain_filter_project": (C.c_int, [_P, _PP, C.c_int, C.c_int, C.POINTER(C.c_int), C.POINTER(C.c_int), C.c_int,
                                              C.c_char_p, C.c_size_t]),
+    "kq_explain_hashagg": (C.c_int, [_P, _PP, C.c_int, C.POINTER(C.c_int), _PP, C.c_int, C.c_int, C.POINTER(C.c_int),
+                                      C.POINTER(C.c_int), C.c_int, C.c_char_p, C.c_size_t]),
     "kq_hashagg_create": (C.c_int, [_P, _P, _PP, C.c_int, C.POINTER(C.c_int), _PP, C.c_int, C.c_int64, _PP]),
     "kq_hashagg_update": (C.c_int, [_P, _P, _P]),
     "kq_hashagg_finalize": (C.c_int, [_P, _P, _PP]),
@@ -409,6 +411,23 @@ class Exprs:
         if st != 0:
             raise KqError(st, text)
         return text
+
+
+def _explain_hashagg(group_exprs, aggs, types, nullable=None, pred=None, compile=True) -> str:
+    n = len(types)
+    t = (C.c_int * n)(*types)
+    nl = (C.c_int * n)(*(nullable or [0] * n))
+    kinds = (C.c_int * max(len(aggs), 1))(*[AGGS[k] for k, _ in aggs])
+    buf = C.create_string_buffer(1 << 18)
+    st = lib().kq_explain_hashagg(pred.h if pred is not None else None, _expr_array(group_exprs), len(group_exprs), kinds,
+                                  _expr_array([e for _, e in aggs]), len(aggs), n, t, nl, int(bool(compile)), buf, len(buf))
+    text = buf.value.decode("utf-8", "replace")
+    if st != 0:
+        raise KqError(st, text)
+    return text
+
+
+Exprs.explain_hashagg = staticmethod(_explain_hashagg)
 
 
 class Engine(Exprs):
