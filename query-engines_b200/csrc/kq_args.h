@@ -47,6 +47,8 @@ struct StageBuf {
     const char* g;                  // global base of the buffer
     int32_t soff;                   // byte offset inside a stage (128-byte aligned)
     int32_t kind;                   // StageKind
+    int32_t aux;                    // SK_BYTES: index of the StageBuf holding this column's offsets; column slot in the high half
+    int32_t cap;                    // SK_BYTES: bytes reserved per stage
 };
 
 struct StagePlan {

@@ -51,6 +51,7 @@ int KqCodegen::begin(kq_ctx* c, kq_batch* b) {
     ctx = c; batch = b; ncols = 0; nlit = 0; pool_used = 0; ntmp = 0;
     memset(&args, 0, sizeof args);
     for (int& x : colmap) x = -1;
+    for (bool& x : col_bytes_used) x = false;
     body.clear();
     begin_body();
     if (b->cols.size() > 256) return kq_fail(ctx, KQ_ERR_UNSUPPORTED, "batches wider than 256 columns are not supported");
@@ -365,20 +366,21 @@ int KqCodegen::key_value(const kq_expr* e, KqVal* out) {
         int bc = bare_column(e);
         if (bc < 0) return kq_fail(ctx, KQ_ERR_UNSUPPORTED, "Utf8 group keys must be columns");
         int slot; KQ_RET(use_col(bc, &slot));
+        col_bytes_used[slot] = true;
         const std::string ok = col_valid(slot), tt = tmp();
-        line("uint64_t " + tt + "[R]; utf8_pack<SO" + S(slot) + ">(q.cols[" + S(slot) + "], " + (ok.empty() ? std::string("rc.inr") : ok) + ", rc, " + tt + ");");
+        line("uint64_t " + tt + "[R]; utf8_pack<SO" + S(slot) + ", SB" + S(slot) + ", " + S(slot) + ">(q.cols[" + S(slot) + "], " + (ok.empty() ? std::string("rc.inr") : ok) + ", rc, " + tt + ");");
         out->v = tt; out->ok = ok; out->type = KQ_UTF8; out->scalar = false;
         return KQ_OK;
     }
     return value(e, out);
 }
 
-std::string KqCodegen::plan_stages(int budget, int min_stages, int tile_rows, StagePlan* sp) {
+std::string KqCodegen::plan_stages(int budget, int min_stages, int tile_rows, StagePlan* sp, bool stage_bytes) {
     const int TILE = tile_rows;
     memset(sp, 0, sizeof *sp);
     int off = 0;
     auto add = [&](int kind, const void* g) -> int {
-        int bytes = kind == SK_W8 ? TILE * 8 : (kind == SK_W4 ? TILE * 4 : (kind == SK_W4_PLUS1 ? TILE * 4 + 16 : TILE / 8));
+        int bytes = kind == SK_W8 ? TILE * 8 : (kind == SK_W4 ? TILE * 4 : (kind == SK_W4_PLUS1 ? TILE * 4 + 16 : (kind == SK_BYTES ? TILE * 4 + 64 : TILE / 8)));
         bytes = (bytes + 127) / 128 * 128;
         if (sp->nbuf >= MAX_STAGE_BUFS || (off + bytes) * min_stages > budget) return -1;   // stays on the direct global path
         sp->buf[sp->nbuf].g = (const char*)g; sp->buf[sp->nbuf].soff = off; sp->buf[sp->nbuf].kind = kind;
@@ -390,15 +392,23 @@ std::string KqCodegen::plan_stages(int budget, int min_stages, int tile_rows, St
     std::string defs;
     for (int i = 0; i < ncols; i++) {
         kq_col* c = batch->cols[(size_t)slot_col[i]];
-        int sd = -1, sv = -1, so = -1;
+        int sd = -1, sv = -1, so = -1, sb = -1;
         switch (c->type) {
             case KQ_F64: case KQ_I64: sd = add(SK_W8, c->data); break;
             case KQ_DATE32: case KQ_I32: sd = add(SK_W4, c->data); break;
             case KQ_BOOL: sd = add(SK_BIT, c->data); break;
-            case KQ_UTF8: so = add(SK_W4_PLUS1, c->offsets); break;   // string bytes stay in global memory
+            case KQ_UTF8:
+                so = add(SK_W4_PLUS1, c->offsets);
+                // string bytes: a second-phase copy of the range the tile's offsets span (up to 4 bytes/row on average; longer tiles fall back to global loads)
+                if (stage_bytes && so >= 0 && col_bytes_used[i]) {
+                    const int obuf = sp->nbuf - 1;
+                    sb = add(SK_BYTES, c->data);
+                    if (sb >= 0) { sp->buf[sp->nbuf - 1].aux = obuf | (i << 16); sp->buf[sp->nbuf - 1].cap = TILE * 4 + 64; }
+                }
+                break;
         }
         if (c->validity) sv = add(SK_BIT, c->validity);
-        defs += "constexpr int SD" + S(i) + " = " + S(sd) + ", SV" + S(i) + " = " + S(sv) + ", SO" + S(i) + " = " + S(so) + ";\n";
+        defs += "constexpr int SD" + S(i) + " = " + S(sd) + ", SV" + S(i) + " = " + S(sv) + ", SO" + S(i) + " = " + S(so) + ", SB" + S(i) + " = " + S(sb) + ";\n";
     }
     sp->stage_bytes = off > 0 ? off : 128;
     int ns = budget / sp->stage_bytes;

@@ -49,7 +49,8 @@ struct KqCodegen {
 
     // Decide which column buffers are staged through the shared-memory tile pipeline (kq_pipe.cuh)
     // and return the `constexpr int SD<i>, SV<i>, SO<i>` definitions the generated code refers to.
-    std::string plan_stages(int budget, int min_stages, int tile_rows, kq::StagePlan* sp);
+    std::string plan_stages(int budget, int min_stages, int tile_rows, kq::StagePlan* sp, bool stage_bytes = false);
+    bool col_bytes_used[kq::MAX_COLS];   // Utf8 column slots whose string bytes the generated code can read from the stage
 
     static int bare_column(const kq_expr* e) { return e && e->kind == KQ_EX_COL ? e->col : -1; }
 

@@ -388,10 +388,12 @@ static int plan_agg(kq_ctx* ctx, kq_hashagg* h, kq_batch* input, int smem_optin,
         if (d.fe_max >= 0) mm_word.push_back(d.rec_max);
     }
     // stage ring first (2..4 stages within ~64 KB, more only if two stages need it), front end gets the rest
-    std::string stage_defs = cg.plan_stages(64 * 1024, 1, TILE, &A.sp);
-    if (A.sp.nstages < 2) stage_defs = cg.plan_stages(std::min(2 * A.sp.stage_bytes, 112 * 1024), 2, TILE, &A.sp);
+    std::string stage_defs = cg.plan_stages(64 * 1024, 1, TILE, &A.sp, true);
+    if (A.sp.nstages < 2) stage_defs = cg.plan_stages(std::min(2 * A.sp.stage_bytes, 112 * 1024), 2, TILE, &A.sp, true);
     A.sp.nstages = std::max(1, std::min(A.sp.nstages, AGG_MAX_STAGES));
     A.q = cg.args;
+    bool has_bytes = false;
+    for (int b = 0; b < A.sp.nbuf; b++) has_bytes |= A.sp.buf[b].kind == SK_BYTES;
     const int ring = A.sp.nstages * A.sp.stage_bytes;
     const int entry_words = (NK + 2) / 2 * 2;
     const int per_group = WARPS * 32 * (4 * ncnt + 8 * ns) + 8 + 4 + 8 * nm;
@@ -428,7 +430,7 @@ static int plan_agg(kq_ctx* ctx, kq_hashagg* h, kq_batch* input, int smem_optin,
                             eval_body + "    }\n};\n}  // namespace kq\n";
     *defines_out = "#define KQ_R " + std::to_string(AGG_R) + "\n#define KQ_WARPS " + std::to_string(AGG_WARPS) + "\n#define KQ_STAGES " +
                                 std::to_string(A.sp.nstages) + "\n#define KQ_FE_GROUPS " + std::to_string(fg) + "\n#define KQ_DIR_SLOTS " +
-                                std::to_string(dir_slots) + "\n";
+                                std::to_string(dir_slots) + "\n#define KQ_STAGE_BYTES " + (has_bytes ? "1" : "0") + "\n";
     return KQ_OK;
 }
 

@@ -66,8 +66,16 @@ struct FrontEnd {
 };
 
 // Group id of a key in the CTA directory, inserting it while there is room; -1 = the row goes to the global table.
-__device__ __forceinline__ int dir_lookup(const FrontEnd& fe, uint64_t h, const uint64_t (&kw)[MAX_KEYS], uint32_t nullmask) {
-    uint32_t slot = (uint32_t)(h >> 40) & (DIR - 1);
+// cheap 32-bit multiplicative hash for the CTA directory (the 64-bit hash of the global table is only
+// computed for rows that actually go there)
+__device__ __forceinline__ uint32_t dir_hash(const uint64_t (&kw)[MAX_KEYS], uint32_t nullmask) {
+    uint32_t h = nullmask * 0x9E3779B1u;
+#pragma unroll
+    for (int k = 0; k < Q::NKEYS; k++) h = (h ^ (uint32_t)kw[k] ^ ((uint32_t)(kw[k] >> 32) * 0x85EBCA6Bu)) * 0x9E3779B1u;
+    return (h ^ (h >> 15)) & (DIR - 1);
+}
+
+__device__ __forceinline__ int dir_lookup(const FrontEnd& fe, uint32_t slot, const uint64_t (&kw)[MAX_KEYS], uint32_t nullmask) {
 #pragma unroll 1
     for (int probe = 0; probe < 8; probe++) {
         uint64_t* e = fe.dir + (size_t)slot * ENTRY_WORDS;
@@ -178,8 +186,9 @@ __device__ __forceinline__ void fe_merge_input(const FrontEnd& fe, uint64_t* rec
 extern "C" __global__ void __launch_bounds__(THREADS, 1) kq_hash_aggregate(const __grid_constant__ AggArgs A) {
     // shared memory: [S stages][directory][gslot][gid2slot][mm][per-warp sums][per-warp counts]
     extern __shared__ __align__(128) unsigned char smem[];
-    __shared__ uint64_t full[S], empty[S];
+    __shared__ uint64_t full[S], empty[S], full2[S];     // full2: second-phase copies (Utf8 string bytes)
     __shared__ long long tile_of[S];
+    __shared__ long long bbase[S][MAX_COLS];
     __shared__ uint32_t s_dir_count;
     const int wid = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int warp = wid - 1;                 // consumer warp index
@@ -201,7 +210,7 @@ extern "C" __global__ void __launch_bounds__(THREADS, 1) kq_hash_aggregate(const
     for (size_t i = fe_begin + threadIdx.x * 4; i < fe_end; i += THREADS * 4) *reinterpret_cast<uint32_t*>(smem + i) = 0;
     if (threadIdx.x == 0) {
         s_dir_count = 0;
-        for (int s = 0; s < S; s++) { mbar_init(&full[s], 1); mbar_init(&empty[s], WARPS); }
+        for (int s = 0; s < S; s++) { mbar_init(&full[s], 1); mbar_init(&empty[s], WARPS); mbar_init(&full2[s], 1); }
         mbar_fence_init();
     }
     __syncthreads();
@@ -210,6 +219,13 @@ extern "C" __global__ void __launch_bounds__(THREADS, 1) kq_hash_aggregate(const
 
     if (wid == PRODUCER_WARP) {
         if (lane == 0) {
+            // Utf8 string bytes are copied in a second phase, one step behind: the byte range of a tile is
+            // only known once its offsets have landed in the stage
+            auto phase2 = [&](int kk) {
+                const int sp = kk % S;
+                mbar_wait(&full[sp], (kk / S) & 1);
+                stage_issue_bytes(A.sp, smem + (size_t)sp * A.sp.stage_bytes, &full2[sp], tile_of[sp], TILE, A.n, bbase[sp]);
+            };
             for (int k = 0;; k++) {
                 const int s = k % S;
                 mbar_wait(&empty[s], ((k / S) & 1) ^ 1);
@@ -218,9 +234,14 @@ extern "C" __global__ void __launch_bounds__(THREADS, 1) kq_hash_aggregate(const
                 const unsigned long long g = *reinterpret_cast<volatile unsigned long long*>(A.ngroups);
                 long long tile = -1;
                 if (g <= A.stop_threshold) tile = (long long)atomicAdd(A.ticket, 1u) + A.tile_begin;
-                if (tile < 0 || tile >= A.ntiles) { tile_of[s] = -1; mbar_arrive(&full[s]); break; }
+                if (tile < 0 || tile >= A.ntiles) {
+                    if (KQ_STAGE_BYTES && k >= 1) phase2(k - 1);
+                    tile_of[s] = -1; mbar_arrive(&full[s]);
+                    break;
+                }
                 tile_of[s] = tile;
                 stage_issue(A.sp, smem + (size_t)s * A.sp.stage_bytes, &full[s], tile, TILE, A.n);
+                if (KQ_STAGE_BYTES && k >= 1) phase2(k - 1);
             }
         }
     } else {
@@ -231,15 +252,16 @@ extern "C" __global__ void __launch_bounds__(THREADS, 1) kq_hash_aggregate(const
             mbar_wait(&full[s], (k / S) & 1);
             const long long tile = tile_of[s];
             if (tile < 0) break;
+            if (KQ_STAGE_BYTES) mbar_wait(&full2[s], (k / S) & 1);
             RowCtx rc;
             rowctx_init(rc, warp, tile, TILE, A.n, A.err, smem + (size_t)s * A.sp.stage_bytes);
+            rc.bbase = bbase[s];
             sink.sel = rc.inr;
             Q::eval(A.q, rc, sink);
             __syncwarp();
             if (lane == 0) mbar_arrive(&empty[s]);       // everything needed is in registers now
 
             // pass 1: key -> hash -> front-end group id for the R owned rows (independent chains)
-            uint64_t hh[R];
             uint32_t nm[R];
             int gid[R];
 #pragma unroll
@@ -256,9 +278,8 @@ extern "C" __global__ void __launch_bounds__(THREADS, 1) kq_hash_aggregate(const
                     }
                 }
                 nm[r] = nullmask;
-                hh[r] = hash_key(kw, nullmask, Q::NKEYS);
                 gid[r] = -1;
-                if (!bypass && ((sink.sel >> r) & 1u)) gid[r] = dir_lookup(fe, hh[r], kw, nullmask);
+                if (!bypass && ((sink.sel >> r) & 1u)) gid[r] = dir_lookup(fe, dir_hash(kw, nullmask), kw, nullmask);
             }
             // pass 2: accumulate
             int fe_hits = 0, rows = 0;
@@ -274,7 +295,7 @@ extern "C" __global__ void __launch_bounds__(THREADS, 1) kq_hash_aggregate(const
                     uint64_t kw[MAX_KEYS];
 #pragma unroll
                     for (int k2 = 0; k2 < MAX_KEYS; k2++) kw[k2] = k2 < Q::NKEYS ? sink.key[k2][r] : 0;
-                    uint64_t* rec = table_find_or_insert(A, hh[r], kw, nm[r]);
+                    uint64_t* rec = table_find_or_insert(A, hash_key(kw, nm[r], Q::NKEYS), kw, nm[r]);
                     global_accumulate_all<0>(A, rec, sink, r);
                 }
             }

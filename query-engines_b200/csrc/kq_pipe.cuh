@@ -71,6 +71,7 @@ __device__ __forceinline__ void stage_issue(const StagePlan& sp, unsigned char* 
 #pragma unroll 1
     for (int b = 0; b < sp.nbuf; b++) {
         const int kind = sp.buf[b].kind;
+        if (kind == SK_BYTES) continue;     // second phase (stage_issue_bytes): needs the staged offsets
         uint32_t bytes = kind == SK_W8 ? rows * 8 : (kind == SK_W4 ? rows * 4 : (kind == SK_W4_PLUS1 ? (rows + 1) * 4 : (rows + 7) / 8));
         total += (bytes + 15u) & ~15u;
     }
@@ -78,6 +79,7 @@ __device__ __forceinline__ void stage_issue(const StagePlan& sp, unsigned char* 
 #pragma unroll 1
     for (int b = 0; b < sp.nbuf; b++) {
         const StageBuf sb = sp.buf[b];
+        if (sb.kind == SK_BYTES) continue;
         uint32_t bytes; int64_t goff;
         if (sb.kind == SK_W8) { bytes = rows * 8; goff = row0 * 8; }
         else if (sb.kind == SK_W4) { bytes = rows * 4; goff = row0 * 4; }
@@ -85,6 +87,39 @@ __device__ __forceinline__ void stage_issue(const StagePlan& sp, unsigned char* 
         else { bytes = (rows + 7) / 8; goff = row0 / 8; }
         bytes = (bytes + 15u) & ~15u;       // device buffers are padded (KQ_PAD), whole vectors past the end are readable
         bulk_g2s(stage + sb.soff, sb.g + goff, bytes, full);
+    }
+}
+
+// Second phase for Utf8 columns: once the tile's offsets have landed in the stage, copy the byte range
+// they span. bbase[column slot] receives the data-buffer offset the staged bytes start at (16-byte
+// aligned), or -1 when the range does not fit the stage (consumers then read those bytes from global
+// memory). Called by one thread after waiting for the first-phase barrier.
+__device__ __forceinline__ void stage_issue_bytes(const StagePlan& sp, unsigned char* stage, uint64_t* full2, int64_t tile,
+                                                  int tile_rows, int64_t n, long long* bbase) {
+    const int64_t row0 = tile * tile_rows;
+    const int rows = (int)((n - row0) < tile_rows ? (n - row0) : tile_rows);
+    uint32_t total = 0;
+    long long start[4]; uint32_t len[4]; int nb = 0;
+#pragma unroll 1
+    for (int b = 0; b < sp.nbuf && nb < 4; b++) {
+        const StageBuf sb = sp.buf[b];
+        if (sb.kind != SK_BYTES) continue;
+        const int32_t* off = reinterpret_cast<const int32_t*>(stage + sp.buf[sb.aux & 0xffff].soff);
+        const long long lo = (long long)off[0] & ~15LL, hi = ((long long)off[rows] + 15LL) & ~15LL;
+        const bool fits = hi - lo + 16 <= (long long)sb.cap;
+        start[nb] = fits ? lo : -1; len[nb] = fits ? (uint32_t)(hi - lo + 16) : 0u;     // +16: consumers read whole 8-byte words past the end (buffers are padded)
+        bbase[sb.aux >> 16] = start[nb];
+        total += len[nb];
+        nb++;
+    }
+    mbar_arrive_expect_tx(full2, total);
+    nb = 0;
+#pragma unroll 1
+    for (int b = 0; b < sp.nbuf && nb < 4; b++) {
+        const StageBuf sb = sp.buf[b];
+        if (sb.kind != SK_BYTES) continue;
+        if (len[nb]) bulk_g2s(stage + sb.soff, sb.g + start[nb], len[nb], full2);
+        nb++;
     }
 }
 

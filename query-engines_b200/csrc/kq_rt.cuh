@@ -47,6 +47,7 @@ struct RowCtx {
     uint32_t active;                 // rows whose errors count (in range and selected)
     uint32_t* err;
     const unsigned char* stage;      // shared-memory stage holding this tile's staged buffers
+    const long long* bbase;          // per column slot: data-buffer offset its staged string bytes start at (-1: not staged)
     int wrow;                        // first row of this warp inside the tile
     __device__ __forceinline__ int64_t row0(int j) const { return warp_base + j * 64 + lane * 2; }
     __device__ __forceinline__ int trow0(int j) const { return wrow + j * 64 + lane * 2; }
@@ -74,6 +75,7 @@ __device__ __forceinline__ void rowctx_init(RowCtx& rc, int warp, int64_t tile, 
     rc.inr = m;
     rc.active = m;
     rc.err = err;
+    rc.bbase = nullptr;
 }
 
 __device__ __forceinline__ uint4 ldg_nc_v4(const void* p) {
@@ -226,10 +228,21 @@ __device__ __forceinline__ uint32_t utf8_cmp_col(const QCol& c, const QCol& d, u
         }
     return m;
 }
-// short string (<= 7 bytes) -> packed u64 group key: bytes little-endian, length in the top byte
-template <int SOFF_OFF>
+// the 8 bytes at (unaligned) shared-memory address p, little-endian: two aligned 64-bit loads + funnel shift
+__device__ __forceinline__ uint64_t lds_u64_unaligned(const unsigned char* p) {
+    const uint32_t addr = smem_u32(p), al = addr & ~7u, sh = (addr & 7u) * 8u;
+    uint64_t lo, hi;
+    asm volatile("ld.shared.u64 %0, [%1];" : "=l"(lo) : "r"(al));
+    asm volatile("ld.shared.u64 %0, [%1];" : "=l"(hi) : "r"(al + 8u));
+    return sh ? ((lo >> sh) | (hi << (64u - sh))) : lo;
+}
+// short string (<= 7 bytes) -> packed u64 group key: bytes little-endian, length in the top byte.
+// SB >= 0: the tile's string bytes are staged at byte offset SB of the stage (when they fit: rc.bbase[SLOT] >= 0).
+template <int SOFF_OFF, int SB, int SLOT>
 __device__ __forceinline__ void utf8_pack(const QCol& c, uint32_t ok, const RowCtx& rc, uint64_t (&out)[R]) {
     const uint8_t* bytes = reinterpret_cast<const uint8_t*>(c.data);
+    long long base = -1;
+    if constexpr (SB >= 0) base = rc.bbase[SLOT];
 #pragma unroll
     for (int r = 0; r < R; r++) {
         uint64_t key = 0;
@@ -237,7 +250,8 @@ __device__ __forceinline__ void utf8_pack(const QCol& c, uint32_t ok, const RowC
             int a, b; utf8_bounds<SOFF_OFF>(c.offsets, rc, r, a, b);
             int len = b - a;
             if (len > 7) { if ((rc.active >> r) & 1u) atomicOr(rc.err, ERR_LONG_KEY); len = 7; }
-            for (int i = 0; i < len; i++) key |= (uint64_t)__ldg(bytes + a + i) << (8 * i);
+            if (SB >= 0 && base >= 0) key = lds_u64_unaligned(rc.stage + SB + (int)((long long)a - base)) & ((1ULL << (8 * len)) - 1ULL);
+            else for (int i = 0; i < len; i++) key |= (uint64_t)__ldg(bytes + a + i) << (8 * i);
             key |= (uint64_t)len << 56;
         }
         out[r] = key;
