@@ -6,18 +6,22 @@
 
 #include "kq_aggtable.cuh"
 #include "kq_codegen.h"
+#include "kq_comm.h"
 #include "kq_scan.cuh"
 
 using namespace kq;
 
 namespace {
 
-// Tile geometry of the aggregate kernel (compiled in as KQ_R / KQ_WARPS).
-constexpr int AGG_R = 4;
-constexpr int AGG_WARPS = 7;
-constexpr int TILE = AGG_WARPS * 32 * AGG_R;     // 896 rows
-constexpr int THREADS = AGG_WARPS * 32 + 32;
-constexpr int WARPS = AGG_WARPS;
+// Tile geometry of the aggregate kernel (compiled in as KQ_R / KQ_WARPS), chosen per query shape from a
+// measured sweep: the lane-private front end costs shared memory per consumer warp, so narrow rows (one
+// or two aggregate inputs) run best with 7 warps x 4 rows, wide rows (TPC-H Q1 shape) with 6 warps x 8 rows.
+struct AggGeometry {
+    int r, warps;
+    int tile() const { return warps * 32 * r; }
+    int threads() const { return warps * 32 + 32; }
+};
+static AggGeometry agg_geometry(int ninputs) { return ninputs >= 3 ? AggGeometry{8, 6} : AggGeometry{4, 7}; }
 constexpr int AGG_MAX_STAGES = 4;
 
 // ---- table maintenance ---------------------------------------------------------------------------------------
@@ -66,22 +70,83 @@ __global__ void k_merge_records(const AggArgs A, const uint64_t* __restrict__ re
     }
 }
 
-// Compact FULL records into a dense array (for exchange between ranks); optional hash partitioning.
-__global__ void k_collect_records(const uint64_t* __restrict__ table, uint64_t cap, int stride, int nkeys, uint64_t* out,
-                                  unsigned long long* counters, int nparts, uint64_t part_capacity) {
+// ---- kernels of the multi-GPU merges -----------------------------------------------------------------------------
+__device__ __forceinline__ int record_part(const uint64_t* src, int nkeys, int nparts) {
+    if (nparts <= 1) return 0;
+    uint64_t kw[MAX_KEYS];
+#pragma unroll
+    for (int k = 0; k < MAX_KEYS; k++) kw[k] = k < nkeys ? src[1 + k] : 0;
+    return (int)((hash_key(kw, (uint32_t)(src[0] >> 32), nkeys) >> 20) % (uint64_t)nparts);
+}
+// records per destination rank (hash partitioning of the group keys)
+__global__ void k_count_parts(const uint64_t* __restrict__ table, uint64_t cap, int stride, int nkeys, int nparts, unsigned long long* counts) {
     for (uint64_t s = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; s < cap; s += (uint64_t)gridDim.x * blockDim.x) {
         const uint64_t* src = table + s * stride;
         if ((uint32_t)src[0] != HDR_FULL) continue;
-        int part = 0;
-        if (nparts > 1) {
-            uint64_t kw[MAX_KEYS];
-#pragma unroll
-            for (int k = 0; k < MAX_KEYS; k++) kw[k] = k < nkeys ? src[1 + k] : 0;
-            part = (int)((hash_key(kw, (uint32_t)(src[0] >> 32), nkeys) >> 20) % (uint64_t)nparts);
-        }
-        unsigned long long pos = atomicAdd(counters + part, 1ULL);
-        uint64_t* dst = out + ((uint64_t)part * part_capacity + pos) * stride;
+        atomicAdd(counts + record_part(src, nkeys, nparts), 1ULL);
+    }
+}
+// Compact FULL records into a dense array, partition p starting at record base[p].
+__global__ void k_collect_records(const uint64_t* __restrict__ table, uint64_t cap, int stride, int nkeys, uint64_t* out,
+                                  unsigned long long* cursors, int nparts, const unsigned long long* __restrict__ base) {
+    for (uint64_t s = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; s < cap; s += (uint64_t)gridDim.x * blockDim.x) {
+        const uint64_t* src = table + s * stride;
+        if ((uint32_t)src[0] != HDR_FULL) continue;
+        const int part = record_part(src, nkeys, nparts);
+        const unsigned long long pos = base[part] + atomicAdd(cursors + part, 1ULL);
+        uint64_t* dst = out + pos * stride;
         for (int w = 0; w < stride; w++) dst[w] = src[w];
+    }
+}
+
+// Union dictionary of the gathered partial records of all ranks: key -> position of its FIRST occurrence in
+// the gathered buffer. The buffer is identical on every rank, so every rank derives the same dense index
+// without any further exchange. D is a scratch table whose records are {header, keys..., position}.
+__global__ void k_dict_build(const AggArgs D, const uint64_t* __restrict__ all, uint64_t nrecs, int stride) {
+    const int posw = 1 + D.nkeys;
+    for (uint64_t j = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; j < nrecs; j += (uint64_t)gridDim.x * blockDim.x) {
+        const uint64_t* src = all + j * stride;
+        if ((uint32_t)src[0] != HDR_FULL) continue;
+        uint64_t kw[MAX_KEYS];
+#pragma unroll
+        for (int k = 0; k < MAX_KEYS; k++) kw[k] = k < D.nkeys ? src[1 + k] : 0;
+        const uint32_t nullmask = (uint32_t)(src[0] >> 32);
+        uint64_t* rec = table_find_or_insert(D, hash_key(kw, nullmask, D.nkeys), kw, nullmask);
+        atomicMin(reinterpret_cast<unsigned long long*>(rec + posw), (unsigned long long)j);
+    }
+}
+__global__ void k_dense_init(uint64_t* dense, uint64_t T, int stride, const AggArgs A) {
+    for (uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; i < T * (uint64_t)stride; i += (uint64_t)gridDim.x * blockDim.x)
+        dense[i] = A.rec_init[i / T];          // identity of each accumulator word (0; ~0 for MIN)
+}
+// own partial records -> dense arrays [word][position]
+__global__ void k_dense_scatter(const AggArgs D, const uint64_t* __restrict__ all, uint64_t first, uint64_t count, int stride, uint64_t* dense, uint64_t T) {
+    const int posw = 1 + D.nkeys;
+    for (uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; i < count; i += (uint64_t)gridDim.x * blockDim.x) {
+        const uint64_t* src = all + (first + i) * stride;
+        if ((uint32_t)src[0] != HDR_FULL) continue;
+        uint64_t kw[MAX_KEYS];
+#pragma unroll
+        for (int k = 0; k < MAX_KEYS; k++) kw[k] = k < D.nkeys ? src[1 + k] : 0;
+        const uint32_t nullmask = (uint32_t)(src[0] >> 32);
+        const uint64_t p = table_find_or_insert(D, hash_key(kw, nullmask, D.nkeys), kw, nullmask)[posw];
+        for (int w = 1 + D.nkeys; w < stride; w++) dense[(uint64_t)w * T + p] = src[w];
+    }
+}
+// reduced dense arrays -> this rank's table (every rank ends up with the full merged result)
+__global__ void k_dense_writeback(const AggArgs A, const AggArgs D, const uint64_t* __restrict__ all, uint64_t T, const uint64_t* __restrict__ dense) {
+    const int posw = 1 + D.nkeys;
+    for (uint64_t j = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; j < T; j += (uint64_t)gridDim.x * blockDim.x) {
+        const uint64_t* src = all + j * A.stride;
+        if ((uint32_t)src[0] != HDR_FULL) continue;
+        uint64_t kw[MAX_KEYS];
+#pragma unroll
+        for (int k = 0; k < MAX_KEYS; k++) kw[k] = k < A.nkeys ? src[1 + k] : 0;
+        const uint32_t nullmask = (uint32_t)(src[0] >> 32);
+        const uint64_t h = hash_key(kw, nullmask, A.nkeys);
+        if (table_find_or_insert(D, h, kw, nullmask)[posw] != j) continue;       // not the first occurrence of this key
+        uint64_t* rec = table_find_or_insert(A, h, kw, nullmask);
+        for (int w = 1 + A.nkeys; w < A.stride; w++) rec[w] = dense[(uint64_t)w * T + j];
     }
 }
 
@@ -325,6 +390,8 @@ int kq_hashagg_free(kq_hashagg* h) {
 // Everything about an aggregate launch that depends on the query SHAPE only: generated source, stage
 // plan, front-end layout. Fills the shape-dependent fields of A. No CUDA calls (kq_explain_hashagg).
 static int plan_agg(kq_ctx* ctx, kq_hashagg* h, kq_batch* input, int smem_optin, AggArgs& A, std::string* defines_out, std::string* gen_out) {
+    const AggGeometry geo = agg_geometry((int)h->inputs.size());
+    const int TILE = geo.tile(), WARPS = geo.warps;
     // generate: [predicate -> selection] keys..., inputs...
     KqCodegen cg;
     KQ_RET(cg.begin(ctx, input));
@@ -428,7 +495,7 @@ static int plan_agg(kq_ctx* ctx, kq_hashagg* h, kq_batch* input, int smem_optin,
     *gen_out = "namespace kq {\n" + stage_defs + "struct Q {\n" + consts +
                             "    template <class Sink> static __device__ __forceinline__ void eval(const QArgs& q, RowCtx& rc, Sink& sink) {\n" +
                             eval_body + "    }\n};\n}  // namespace kq\n";
-    *defines_out = "#define KQ_R " + std::to_string(AGG_R) + "\n#define KQ_WARPS " + std::to_string(AGG_WARPS) + "\n#define KQ_STAGES " +
+    *defines_out = "#define KQ_R " + std::to_string(geo.r) + "\n#define KQ_WARPS " + std::to_string(geo.warps) + "\n#define KQ_STAGES " +
                                 std::to_string(A.sp.nstages) + "\n#define KQ_FE_GROUPS " + std::to_string(fg) + "\n#define KQ_DIR_SLOTS " +
                                 std::to_string(dir_slots) + "\n#define KQ_STAGE_BYTES " + (has_bytes ? "1" : "0") + "\n";
     return KQ_OK;
@@ -447,6 +514,8 @@ int kq_hashagg_update(kq_ctx* ctx, kq_hashagg* h, kq_batch* input) {
     std::string defines, gen;
     KQ_RET(plan_agg(ctx, h, input, ctx->max_smem_optin, A, &defines, &gen));
     if (n == 0) return KQ_OK;
+    const AggGeometry geo = agg_geometry((int)h->inputs.size());
+    const int TILE = geo.tile(), THREADS = geo.threads();
     A.n = n; A.ntiles = (n + TILE - 1) / TILE;
     void* kernel = nullptr;
     KQ_RET(kq_jit_kernel(ctx, defines, gen, KQ_SKEL_AGG, "kq_hash_aggregate", A.smem_bytes, &kernel));
@@ -590,6 +659,204 @@ int kq_hashagg_finalize(kq_ctx* ctx, kq_hashagg* h, kq_batch** out) {
     for (kq_col* c : cols) kq_column_free(c);
     cols.clear();
     return st;
+}
+
+// ---- multi-GPU merge (partial -> merge of main(), Main.kt:1309-1325) --------------------------------------------------
+// Word class of a record word: which reduction merges it.
+enum { WC_SKIP = 0, WC_SUM_U64, WC_SUM_F64, WC_MIN, WC_MAX };
+static void word_classes(kq_hashagg* h, int* cls) {
+    for (int w = 0; w < h->stride; w++) cls[w] = WC_SKIP;
+    for (size_t i = 0; i < h->inputs.size(); i++) {
+        const AggInput& d = h->in[i];
+        cls[d.rec_nn] = WC_SUM_U64;
+        if (d.rec_sum >= 0) cls[d.rec_sum] = (d.flags & F_INT) ? WC_SUM_U64 : WC_SUM_F64;
+        if (d.rec_min >= 0) cls[d.rec_min] = WC_MIN;
+        if (d.rec_max >= 0) cls[d.rec_max] = WC_MAX;
+    }
+}
+
+static int refresh_group_count(kq_ctx* ctx, kq_hashagg* h) {
+    uint64_t c; KQ_RET(kq_read_u64(ctx, h->d_counters, 1, &c));
+    h->ngroups_host = (int64_t)c;
+    return KQ_OK;
+}
+
+int kq_hashagg_merge_allreduce(kq_ctx* ctx, kq_hashagg* h) {
+    if (!ctx || !h) return KQ_ERR_ILLEGAL_ARGUMENT;
+    if (!ctx->comm || ctx->nranks <= 1) return KQ_OK;
+    KqNccl* N = kq_nccl(ctx);
+    if (!N) return KQ_ERR_NCCL;
+    cudaSetDevice(ctx->device);
+    ncclComm_t comm = (ncclComm_t)ctx->comm;
+    const int nr = ctx->nranks, me = ctx->rank, stride = h->stride, nkeys = (int)h->groups.size();
+    KQ_RET(kq_check_device_errors(ctx));
+    KQ_RET(refresh_group_count(ctx, h));
+    const uint64_t G = (uint64_t)h->ngroups_host;
+
+    // 1. how many partial groups does every rank hold?
+    unsigned long long* d_cnt = nullptr;
+    KQ_RET(kq_dev_alloc(ctx, (size_t)nr * 8, (void**)&d_cnt));
+    cudaMemcpyAsync(d_cnt + me, &G, 8, cudaMemcpyHostToDevice, ctx->stream);
+    ncclResult_t r = N->AllGather(d_cnt + me, d_cnt, 1, ncclUint64, comm, ctx->stream);
+    uint64_t cnt[64];
+    int st = r == ncclSuccess ? (nr <= 64 ? kq_read_u64(ctx, d_cnt, nr, cnt) : kq_fail(ctx, KQ_ERR_UNSUPPORTED, "more than 64 ranks")) : kq_nccl_fail(ctx, r, "ncclAllGather");
+    kq_dev_free(ctx, d_cnt);
+    KQ_RET(st);
+    uint64_t maxn = 0;
+    for (int i = 0; i < nr; i++) maxn = std::max(maxn, cnt[i]);
+    if (maxn == 0) return KQ_OK;
+    const uint64_t T = maxn * (uint64_t)nr;
+
+    // 2. all-gather the partial records themselves (padded to the largest rank; a zero header is skipped)
+    uint64_t *mine = nullptr, *all = nullptr;
+    unsigned long long* d_cur = nullptr;
+    KQ_RET(kq_dev_alloc(ctx, (size_t)maxn * stride * 8, (void**)&mine));
+    if ((st = kq_dev_alloc(ctx, (size_t)T * stride * 8, (void**)&all)) != KQ_OK) { kq_dev_free(ctx, mine); return st; }
+    if ((st = kq_dev_alloc(ctx, 16, (void**)&d_cur)) != KQ_OK) { kq_dev_free(ctx, mine); kq_dev_free(ctx, all); return st; }
+    auto cleanup = [&](int s) { kq_dev_free(ctx, mine); kq_dev_free(ctx, all); kq_dev_free(ctx, d_cur); return s; };
+    cudaMemsetAsync(mine, 0, (size_t)maxn * stride * 8, ctx->stream);
+    cudaMemsetAsync(d_cur, 0, 16, ctx->stream);      // [0] cursor, [1] base = 0
+    k_collect_records<<<small_grid(ctx, h->capacity), 256, 0, ctx->stream>>>(h->table, h->capacity, stride, nkeys, mine, d_cur, 1, d_cur + 1);
+    if ((st = launch_check(ctx, "k_collect_records")) != KQ_OK) return cleanup(st);
+    if ((r = N->AllGather(mine, all, (size_t)maxn * stride, ncclUint64, comm, ctx->stream)) != ncclSuccess) return cleanup(kq_nccl_fail(ctx, r, "ncclAllGather"));
+
+    // make room for the union of all ranks' keys
+    uint64_t need = h->capacity;
+    while (need / 2 < T + G) need <<= 1;
+    if (need != h->capacity && (st = table_grow(ctx, h, need)) != KQ_OK) return cleanup(st);
+    AggArgs A;
+    memset(&A, 0, sizeof A);
+    fill_common_args(h, A);
+
+    if (T > (1ULL << 20)) {
+        // too many groups for dense arrays to pay off: merge the other ranks' gathered partials locally
+        for (int s = 0; s < nr && st == KQ_OK; s++) {
+            if (s == me || cnt[s] == 0) continue;
+            k_merge_records<<<small_grid(ctx, cnt[s]), 256, 0, ctx->stream>>>(A, all + (uint64_t)s * maxn * stride, cnt[s]);
+            st = launch_check(ctx, "k_merge_records");
+        }
+        if (st == KQ_OK) st = refresh_group_count(ctx, h);
+        return cleanup(st);
+    }
+
+    // 3. union dictionary: key -> first position in the gathered buffer (same on every rank)
+    AggArgs D;
+    memset(&D, 0, sizeof D);
+    uint64_t dcap = 1024;
+    while (dcap < 2 * T) dcap <<= 1;
+    D.nkeys = nkeys; D.stride = (1 + nkeys + 1 + 3) / 4 * 4; D.cap_mask = dcap - 1;
+    D.rec_init[1 + nkeys] = ~0ULL;
+    uint64_t *dict = nullptr, *dense = nullptr;
+    if ((st = kq_dev_alloc(ctx, (size_t)dcap * D.stride * 8 + 64, (void**)&dict)) != KQ_OK) return cleanup(st);
+    if ((st = kq_dev_alloc(ctx, (size_t)T * stride * 8, (void**)&dense)) != KQ_OK) { kq_dev_free(ctx, dict); return cleanup(st); }
+    auto cleanup2 = [&](int s) { kq_dev_free(ctx, dict); kq_dev_free(ctx, dense); return cleanup(s); };
+    cudaMemsetAsync(dict, 0, (size_t)dcap * D.stride * 8 + 64, ctx->stream);
+    D.table = dict; D.ngroups = (unsigned long long*)(dict + dcap * D.stride);
+    k_dict_build<<<small_grid(ctx, T), 256, 0, ctx->stream>>>(D, all, T, stride);
+    if ((st = launch_check(ctx, "k_dict_build")) != KQ_OK) return cleanup2(st);
+    // 4. dense arrays [word][position]: identities everywhere, own partials scattered in, one all-reduce per word
+    k_dense_init<<<small_grid(ctx, T * stride), 256, 0, ctx->stream>>>(dense, T, stride, A);
+    if ((st = launch_check(ctx, "k_dense_init")) != KQ_OK) return cleanup2(st);
+    k_dense_scatter<<<small_grid(ctx, maxn), 256, 0, ctx->stream>>>(D, all, (uint64_t)me * maxn, maxn, stride, dense, T);
+    if ((st = launch_check(ctx, "k_dense_scatter")) != KQ_OK) return cleanup2(st);
+    int cls[MAX_REC_WORDS];
+    word_classes(h, cls);
+    if ((r = N->GroupStart()) != ncclSuccess) return cleanup2(kq_nccl_fail(ctx, r, "ncclGroupStart"));
+    for (int w = 1 + nkeys; w < stride && r == ncclSuccess; w++) {
+        uint64_t* p = dense + (uint64_t)w * T;
+        switch (cls[w]) {
+            case WC_SUM_U64: r = N->AllReduce(p, p, T, ncclUint64, ncclSum, comm, ctx->stream); break;
+            case WC_SUM_F64: r = N->AllReduce(p, p, T, ncclFloat64, ncclSum, comm, ctx->stream); break;
+            case WC_MIN: r = N->AllReduce(p, p, T, ncclUint64, ncclMin, comm, ctx->stream); break;     // order-mapped values
+            case WC_MAX: r = N->AllReduce(p, p, T, ncclUint64, ncclMax, comm, ctx->stream); break;
+            default: break;
+        }
+    }
+    ncclResult_t r2 = N->GroupEnd();
+    if (r != ncclSuccess || r2 != ncclSuccess) return cleanup2(kq_nccl_fail(ctx, r != ncclSuccess ? r : r2, "ncclAllReduce"));
+    // 5. write the reduced values into this rank's table
+    k_dense_writeback<<<small_grid(ctx, T), 256, 0, ctx->stream>>>(A, D, all, T, dense);
+    if ((st = launch_check(ctx, "k_dense_writeback")) != KQ_OK) return cleanup2(st);
+    st = refresh_group_count(ctx, h);
+    return cleanup2(st);
+}
+
+int kq_hashagg_repartition_alltoall(kq_ctx* ctx, kq_hashagg* h) {
+    if (!ctx || !h) return KQ_ERR_ILLEGAL_ARGUMENT;
+    if (!ctx->comm || ctx->nranks <= 1) return KQ_OK;
+    KqNccl* N = kq_nccl(ctx);
+    if (!N) return KQ_ERR_NCCL;
+    cudaSetDevice(ctx->device);
+    ncclComm_t comm = (ncclComm_t)ctx->comm;
+    const int nr = ctx->nranks, me = ctx->rank, stride = h->stride, nkeys = (int)h->groups.size();
+    if (nr > 64) return kq_fail(ctx, KQ_ERR_UNSUPPORTED, "more than 64 ranks");
+    KQ_RET(kq_check_device_errors(ctx));
+    KQ_RET(refresh_group_count(ctx, h));
+    const uint64_t G = (uint64_t)h->ngroups_host;
+
+    // 1. bucket the partial records by hash(key) % nranks: count, then scatter into contiguous buckets
+    unsigned long long* d_meta = nullptr;     // [0..nr) counts, [nr..2nr) bases, [2nr..3nr) cursors, [3nr..3nr+nr*nr) count matrix
+    KQ_RET(kq_dev_alloc(ctx, (size_t)(3 * nr + nr * nr) * 8, (void**)&d_meta));
+    uint64_t* sendbuf = nullptr; uint64_t* recvbuf = nullptr; uint64_t* newtab = nullptr;
+    auto cleanup = [&](int s) { kq_dev_free(ctx, d_meta); kq_dev_free(ctx, sendbuf); kq_dev_free(ctx, recvbuf); if (s != KQ_OK) kq_dev_free(ctx, newtab); return s; };
+    cudaMemsetAsync(d_meta, 0, (size_t)(3 * nr + nr * nr) * 8, ctx->stream);
+    k_count_parts<<<small_grid(ctx, h->capacity), 256, 0, ctx->stream>>>(h->table, h->capacity, stride, nkeys, nr, d_meta);
+    int st = launch_check(ctx, "k_count_parts");
+    if (st != KQ_OK) return cleanup(st);
+    uint64_t cnt[64], base[64];
+    if ((st = kq_read_u64(ctx, d_meta, nr, cnt)) != KQ_OK) return cleanup(st);
+    uint64_t acc = 0;
+    for (int p = 0; p < nr; p++) { base[p] = acc; acc += cnt[p]; }
+    cudaMemcpyAsync(d_meta + nr, base, (size_t)nr * 8, cudaMemcpyHostToDevice, ctx->stream);
+    if ((st = kq_dev_alloc(ctx, (size_t)std::max<uint64_t>(G, 1) * stride * 8, (void**)&sendbuf)) != KQ_OK) return cleanup(st);
+    k_collect_records<<<small_grid(ctx, h->capacity), 256, 0, ctx->stream>>>(h->table, h->capacity, stride, nkeys, sendbuf, d_meta + 2 * nr, nr, d_meta + nr);
+    if ((st = launch_check(ctx, "k_collect_records")) != KQ_OK) return cleanup(st);
+
+    // 2. everybody learns everybody's bucket sizes
+    unsigned long long* d_mat = d_meta + 3 * nr;
+    cudaMemcpyAsync(d_mat + (size_t)me * nr, d_meta, (size_t)nr * 8, cudaMemcpyDeviceToDevice, ctx->stream);
+    ncclResult_t r = N->AllGather(d_mat + (size_t)me * nr, d_mat, (size_t)nr, ncclUint64, comm, ctx->stream);
+    if (r != ncclSuccess) return cleanup(kq_nccl_fail(ctx, r, "ncclAllGather"));
+    std::vector<uint64_t> mat((size_t)nr * nr);
+    for (int s = 0; s < nr; s++)       // kq_read_u64 moves at most 64 words at a time
+        if ((st = kq_read_u64(ctx, d_mat + (size_t)s * nr, nr, mat.data() + (size_t)s * nr)) != KQ_OK) return cleanup(st);
+    uint64_t R = 0, roff[64];
+    for (int s = 0; s < nr; s++) { roff[s] = R; if (s != me) R += mat[(size_t)s * nr + me]; }
+
+    // 3. one-shot all-to-all over NVSwitch: grouped send/recv of the buckets
+    if ((st = kq_dev_alloc(ctx, (size_t)std::max<uint64_t>(R, 1) * stride * 8, (void**)&recvbuf)) != KQ_OK) return cleanup(st);
+    if ((r = N->GroupStart()) != ncclSuccess) return cleanup(kq_nccl_fail(ctx, r, "ncclGroupStart"));
+    for (int p = 0; p < nr && r == ncclSuccess; p++) {
+        if (p == me) continue;
+        if (cnt[p]) r = N->Send(sendbuf + base[p] * stride, (size_t)cnt[p] * stride, ncclUint64, p, comm, ctx->stream);
+        const uint64_t rc = mat[(size_t)p * nr + me];
+        if (r == ncclSuccess && rc) r = N->Recv(recvbuf + roff[p] * stride, (size_t)rc * stride, ncclUint64, p, comm, ctx->stream);
+    }
+    ncclResult_t r2 = N->GroupEnd();
+    if (r != ncclSuccess || r2 != ncclSuccess) return cleanup(kq_nccl_fail(ctx, r != ncclSuccess ? r : r2, "ncclSend/ncclRecv"));
+
+    // 4. this rank's final table: its own bucket merged with the buckets it received
+    uint64_t cap = 1ULL << 16;
+    while (cap / 2 < cnt[me] + R) cap <<= 1;
+    if ((st = kq_dev_alloc(ctx, (size_t)cap * stride * 8, (void**)&newtab)) != KQ_OK) return cleanup(st);
+    cudaMemsetAsync(newtab, 0, (size_t)cap * stride * 8, ctx->stream);
+    cudaMemsetAsync(h->d_counters, 0, 8, ctx->stream);
+    kq_dev_free(ctx, h->table);
+    h->table = newtab; h->capacity = cap;
+    AggArgs A;
+    memset(&A, 0, sizeof A);
+    fill_common_args(h, A);
+    if (cnt[me]) {
+        k_merge_records<<<small_grid(ctx, cnt[me]), 256, 0, ctx->stream>>>(A, sendbuf + base[me] * stride, cnt[me]);
+        if ((st = launch_check(ctx, "k_merge_records")) != KQ_OK) { newtab = nullptr; return cleanup(st); }
+    }
+    if (R) {
+        k_merge_records<<<small_grid(ctx, R), 256, 0, ctx->stream>>>(A, recvbuf, R);
+        if ((st = launch_check(ctx, "k_merge_records")) != KQ_OK) { newtab = nullptr; return cleanup(st); }
+    }
+    st = refresh_group_count(ctx, h);
+    newtab = nullptr;      // owned by h now
+    return cleanup(st);
 }
 
 }  // extern "C"

@@ -300,11 +300,11 @@ extern "C" __global__ void __launch_bounds__(THREADS, 1) kq_hash_aggregate(const
                 }
             }
             // once the directory is full and this warp mostly misses it, stop probing it (high cardinality)
-            if (!bypass) {
+            if (!bypass && *reinterpret_cast<volatile uint32_t*>(&s_dir_count) >= (uint32_t)FG) {
                 int hits = fe_hits, tot = rows;
 #pragma unroll
                 for (int o = 16; o; o >>= 1) { hits += __shfl_xor_sync(0xffffffffu, hits, o); tot += __shfl_xor_sync(0xffffffffu, tot, o); }
-                if (tot >= 64 && hits * 8 < tot && *reinterpret_cast<volatile uint32_t*>(&s_dir_count) >= (uint32_t)FG) bypass = true;
+                if (tot >= 64 && hits * 8 < tot) bypass = true;
             }
         }
     }
