@@ -49,7 +49,9 @@ struct StageBuf {
     int32_t kind;                   // StageKind
     int32_t aux;                    // SK_BYTES: index of the StageBuf holding this column's offsets; column slot in the high half
     int32_t cap;                    // SK_BYTES: bytes reserved per stage
+    int32_t slot, role;             // which QArgs column buffer this is: role 0 = data, 1 = validity, 2 = offsets
 };
+
 
 struct StagePlan {
     int32_t nbuf;
@@ -58,6 +60,14 @@ struct StagePlan {
     int32_t _pad;
     StageBuf buf[MAX_STAGE_BUFS];
 };
+
+// (re)bind the global bases of a stage plan to the column pointers of q
+__host__ __device__ inline void stage_plan_bind(StagePlan& sp, const QArgs& q) {
+    for (int b = 0; b < sp.nbuf; b++) {
+        const QCol& c = q.cols[sp.buf[b].slot];
+        sp.buf[b].g = (const char*)(sp.buf[b].role == 0 ? c.data : (sp.buf[b].role == 1 ? (const void*)c.validity : (const void*)c.offsets));
+    }
+}
 
 struct DOut {
     void* data;
@@ -68,6 +78,7 @@ struct DOut {
 struct OpArgs {
     QArgs q;
     int64_t n, ntiles;
+    int64_t tile_begin, tile_end;   // this launch covers tiles [tile_begin, tile_end) of the batch (host-streamed input is launched chunk by chunk)
     DOut outs[MAX_OUT];
     unsigned long long* tile_desc;  // decoupled look-back descriptors, one per tile
     unsigned int* ticket;

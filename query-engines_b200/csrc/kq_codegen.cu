@@ -379,11 +379,13 @@ std::string KqCodegen::plan_stages(int budget, int min_stages, int tile_rows, St
     const int TILE = tile_rows;
     memset(sp, 0, sizeof *sp);
     int off = 0;
-    auto add = [&](int kind, const void* g) -> int {
+    int cur_slot = 0;
+    auto add = [&](int kind, const void* g, int role) -> int {
         int bytes = kind == SK_W8 ? TILE * 8 : (kind == SK_W4 ? TILE * 4 : (kind == SK_W4_PLUS1 ? TILE * 4 + 16 : (kind == SK_BYTES ? TILE * 4 + 64 : TILE / 8)));
         bytes = (bytes + 127) / 128 * 128;
         if (sp->nbuf >= MAX_STAGE_BUFS || (off + bytes) * min_stages > budget) return -1;   // stays on the direct global path
-        sp->buf[sp->nbuf].g = (const char*)g; sp->buf[sp->nbuf].soff = off; sp->buf[sp->nbuf].kind = kind;
+        StageBuf& sb = sp->buf[sp->nbuf];
+        sb.g = (const char*)g; sb.soff = off; sb.kind = kind; sb.slot = cur_slot; sb.role = role;
         sp->nbuf++;
         const int at = off;
         off += bytes;
@@ -393,21 +395,22 @@ std::string KqCodegen::plan_stages(int budget, int min_stages, int tile_rows, St
     for (int i = 0; i < ncols; i++) {
         kq_col* c = batch->cols[(size_t)slot_col[i]];
         int sd = -1, sv = -1, so = -1, sb = -1;
+        cur_slot = i;
         switch (c->type) {
-            case KQ_F64: case KQ_I64: sd = add(SK_W8, c->data); break;
-            case KQ_DATE32: case KQ_I32: sd = add(SK_W4, c->data); break;
-            case KQ_BOOL: sd = add(SK_BIT, c->data); break;
+            case KQ_F64: case KQ_I64: sd = add(SK_W8, c->data, 0); break;
+            case KQ_DATE32: case KQ_I32: sd = add(SK_W4, c->data, 0); break;
+            case KQ_BOOL: sd = add(SK_BIT, c->data, 0); break;
             case KQ_UTF8:
-                so = add(SK_W4_PLUS1, c->offsets);
+                so = add(SK_W4_PLUS1, c->offsets, 2);
                 // string bytes: a second-phase copy of the range the tile's offsets span (up to 4 bytes/row on average; longer tiles fall back to global loads)
                 if (stage_bytes && so >= 0 && col_bytes_used[i]) {
                     const int obuf = sp->nbuf - 1;
-                    sb = add(SK_BYTES, c->data);
+                    sb = add(SK_BYTES, c->data, 0);
                     if (sb >= 0) { sp->buf[sp->nbuf - 1].aux = obuf | (i << 16); sp->buf[sp->nbuf - 1].cap = TILE * 4 + 64; }
                 }
                 break;
         }
-        if (c->validity) sv = add(SK_BIT, c->validity);
+        if (c->validity) sv = add(SK_BIT, c->validity, 1);
         defs += "constexpr int SD" + S(i) + " = " + S(sd) + ", SV" + S(i) + " = " + S(sv) + ", SO" + S(i) + " = " + S(so) + ", SB" + S(i) + " = " + S(sb) + ";\n";
     }
     sp->stage_bytes = off > 0 ? off : 128;

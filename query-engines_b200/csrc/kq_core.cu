@@ -84,6 +84,8 @@ int kq_ctx_destroy(kq_ctx* ctx) {
     if (!ctx) return KQ_OK;
     cudaSetDevice(ctx->device);
     cudaStreamSynchronize(ctx->stream);
+    for (kq_lazy_count* l : ctx->pending_lazy) { cudaEventDestroy(l->ev); delete l; }
+    ctx->pending_lazy.clear();
     if (ctx->d_flush) cudaFree(ctx->d_flush);
     for (auto& kv : ctx->block_size) cudaFree(kv.first);
     for (cudaEvent_t ev : ctx->free_events) cudaEventDestroy(ev);
@@ -224,7 +226,30 @@ int kq_col_new(kq_ctx* ctx, int type, int64_t n, bool with_validity, int64_t utf
     return KQ_OK;
 }
 
+// Slots whose owner went away before the asynchronous count copy landed are parked here and recycled
+// once their event has fired, so dropping an unread filter result never blocks the host.
+static void lazy_recycle(kq_ctx* ctx, kq_lazy_count* l) {
+    ctx->free_events.push_back(l->ev);
+    ctx->free_slots.push_back(l->slot);
+    kq_dev_free(ctx, l->d_slot);
+    delete l;
+}
+static void lazy_reap(kq_ctx* ctx, bool wait_for_one) {
+    for (size_t i = 0; i < ctx->pending_lazy.size();) {
+        kq_lazy_count* l = ctx->pending_lazy[i];
+        if (cudaEventQuery(l->ev) == cudaSuccess) { lazy_recycle(ctx, l); ctx->pending_lazy.erase(ctx->pending_lazy.begin() + (long)i); }
+        else i++;
+    }
+    if (wait_for_one && ctx->free_slots.empty() && !ctx->pending_lazy.empty()) {
+        kq_lazy_count* l = ctx->pending_lazy.front();
+        cudaEventSynchronize(l->ev);
+        lazy_recycle(ctx, l);
+        ctx->pending_lazy.erase(ctx->pending_lazy.begin());
+    }
+}
+
 kq_lazy_count* kq_lazy_new(kq_ctx* ctx) {
+    if (!ctx->pending_lazy.empty()) lazy_reap(ctx, true);
     kq_lazy_count* l = new kq_lazy_count();
     if (ctx->free_slots.empty()) { delete l; return nullptr; }
     l->slot = ctx->free_slots.back(); ctx->free_slots.pop_back();
@@ -238,11 +263,9 @@ kq_lazy_count* kq_lazy_new(kq_ctx* ctx) {
 void kq_lazy_release(kq_ctx* ctx, kq_lazy_count* l) {
     if (!l) return;
     if (l->rc.fetch_sub(1) == 1) {
-        if (!l->resolved) cudaEventSynchronize(l->ev);   // the async D2H into the pinned slot must have landed
-        ctx->free_events.push_back(l->ev);
-        ctx->free_slots.push_back(l->slot);
-        kq_dev_free(ctx, l->d_slot);
-        delete l;
+        // the async D2H into the pinned slot must have landed before the slot is reused
+        if (!l->resolved && cudaEventQuery(l->ev) != cudaSuccess) ctx->pending_lazy.push_back(l);
+        else lazy_recycle(ctx, l);
     }
 }
 static int kq_lazy_resolve(kq_ctx* ctx, kq_lazy_count* l, int64_t* n) {

@@ -50,6 +50,7 @@ struct kq_ctx {
     uint64_t* pinned_slots = nullptr;
     std::vector<int> free_slots;
     std::vector<cudaEvent_t> free_events;
+    std::vector<struct kq_lazy_count*> pending_lazy;   // released before their count arrived (kq_lazy_release)
 };
 
 struct kq_lazy_count;

@@ -167,7 +167,7 @@ extern "C" __global__ void __launch_bounds__(THREADS, 1) kq_project(const __grid
     if (wid == PRODUCER_WARP) {
         if (lane == 0) {
             int k = 0;
-            for (int64_t tile = blockIdx.x; tile < A.ntiles; tile += gridDim.x, k++) {
+            for (int64_t tile = A.tile_begin + blockIdx.x; tile < A.tile_end; tile += gridDim.x, k++) {
                 const int s = k % S;
                 mbar_wait(&empty[s], ((k / S) & 1) ^ 1);
                 stage_issue(A.sp, stages + (size_t)s * A.sp.stage_bytes, &full[s], tile, TILE, A.n);
@@ -178,7 +178,7 @@ extern "C" __global__ void __launch_bounds__(THREADS, 1) kq_project(const __grid
     ProjectSink sink;
     sink.outs = A.outs;
     int k = 0;
-    for (int64_t tile = blockIdx.x; tile < A.ntiles; tile += gridDim.x, k++) {
+    for (int64_t tile = A.tile_begin + blockIdx.x; tile < A.tile_end; tile += gridDim.x, k++) {
         const int s = k % S;
         mbar_wait(&full[s], (k / S) & 1);
         RowCtx rc;
@@ -235,7 +235,7 @@ extern "C" __global__ void __launch_bounds__(THREADS, 1) kq_filter_project(const
         // cooperative, so every CTA a look-back may wait for is resident.
         if (lane == 0) {
             int kp = 0;
-            for (long long tile = blockIdx.x; tile < A.ntiles; tile += gridDim.x, kp++) {
+            for (long long tile = A.tile_begin + blockIdx.x; tile < A.tile_end; tile += gridDim.x, kp++) {
                 const int s = kp % S;
                 mbar_wait(&empty[s], ((kp / S) & 1) ^ 1);
                 tile_of[s] = tile;
@@ -253,7 +253,7 @@ extern "C" __global__ void __launch_bounds__(THREADS, 1) kq_filter_project(const
         // ---- look-back: tile aggregate -> exclusive prefix -> per-warp output bases. Look-backs of
         // different tiles are independent, so the NLB warps take the CTA's tiles in turn.
         int kl = wid - LOOKBACK_WARP;
-        for (long long tile = blockIdx.x + (long long)kl * gridDim.x; tile < A.ntiles; tile += (long long)NLB * gridDim.x, kl += NLB) {
+        for (long long tile = A.tile_begin + blockIdx.x + (long long)kl * gridDim.x; tile < A.tile_end; tile += (long long)NLB * gridDim.x, kl += NLB) {
             const int m = kl % M;
             mbar_wait(&agg_ready[m], (kl / M) & 1);
             if (lane == 0) KQ_TR(tile, 3);

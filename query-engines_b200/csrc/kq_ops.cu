@@ -285,6 +285,7 @@ int run_operator(kq_ctx* ctx, kq_expr* pred, kq_expr* const* exprs, int nexprs, 
         OpArgs A;
         memset(&A, 0, sizeof A);
         A.n = n; A.ntiles = (n + TILE - 1) / TILE; A.err = ctx->d_err;
+        A.tile_begin = 0; A.tile_end = A.ntiles;
         A.q = cg.args; A.sp = P.sp;
         for (size_t j = 0; j < chunks[ci].size(); j++) {
             const size_t k = chunks[ci][j];
@@ -402,28 +403,156 @@ int kq_explain_filter_project(kq_expr* pred, kq_expr* const* exprs, int nexprs, 
     return st;
 }
 
+// FilterExec + ProjectionExec end to end from HOST Arrow buffers to HOST result buffers. The input is
+// streamed chunk by chunk: pinned H2D copies on one side stream (double-buffered device chunks), the
+// fused kernel on the compute stream over the chunk's tile range of ONE logical batch (the cross-block
+// prefix simply continues from the previous launch, so the compacted output stays globally ordered),
+// D2H of the rows each chunk produced on a second side stream. PCIe is full duplex, so the step costs
+// about max(H2D, D2H) instead of their sum plus the kernel.
 int kq_filter_project_host(kq_ctx* ctx, kq_expr* pred, kq_expr* const* exprs, int nexprs, int ncols, const int* types,
                            const uint8_t* const* validity, const void* const* data, int64_t n, void* const* out_data,
                            uint8_t* const* out_validity, int64_t* out_rows) {
-    // v1: upload -> fused kernel -> download, sequential (chunked overlap is a later optimisation)
-    if (!ctx || ncols < 0) return KQ_ERR_ILLEGAL_ARGUMENT;
-    std::vector<kq_col*> cols((size_t)ncols, nullptr);
-    int st = KQ_OK;
-    for (int i = 0; i < ncols && st == KQ_OK; i++) {
-        if (types[i] == KQ_UTF8) st = kq_fail(ctx, KQ_ERR_UNSUPPORTED, "kq_filter_project_host: Utf8 columns not supported");
-        else st = kq_column_upload(ctx, types[i], n, validity ? validity[i] : nullptr, nullptr, data[i], 0, &cols[(size_t)i]);
+    if (!ctx || ncols < 0 || nexprs < 0 || n < 0 || (ncols > 0 && (!types || !data))) return KQ_ERR_ILLEGAL_ARGUMENT;
+    if (!pred) return kq_fail(ctx, KQ_ERR_ILLEGAL_ARGUMENT, "kq_filter_project_host needs a predicate");
+    if (n > 2147483647LL) return kq_fail(ctx, KQ_ERR_ILLEGAL_ARGUMENT, "batch larger than 2^31-1 rows");
+    cudaSetDevice(ctx->device);
+    std::vector<int> nullable((size_t)ncols, 0);
+    for (int i = 0; i < ncols; i++) {
+        if (types[i] == KQ_UTF8) return kq_fail(ctx, KQ_ERR_UNSUPPORTED, "kq_filter_project_host: Utf8 columns are not supported");
+        nullable[(size_t)i] = validity && validity[i];
     }
-    kq_batch *in = nullptr, *res = nullptr;
-    if (st == KQ_OK) st = kq_batch_create(ctx, cols.data(), ncols, n, &in);
-    if (st == KQ_OK) st = kq_filter_project(ctx, pred, exprs, nexprs, in, &res);
-    int64_t m = 0;
-    if (st == KQ_OK) st = kq_batch_num_rows(ctx, res, &m);
-    for (int k = 0; k < nexprs && st == KQ_OK; k++)
-        st = kq_column_download(ctx, res->cols[(size_t)k], out_validity ? out_validity[k] : nullptr, nullptr, out_data[k]);
-    if (st == KQ_OK && out_rows) *out_rows = m;
-    kq_batch_free(res); kq_batch_free(in);
-    for (kq_col* c : cols) kq_column_free(c);
-    return st;
+    // plan + kernel (schema only)
+    KqSchemaBatch sb(ncols, types, nullable.data());
+    KqCodegen cg;
+    OpsPlan P;
+    std::vector<kq_expr*> ex(exprs, exprs + nexprs);
+    KQ_RET(cg.begin(ctx, &sb.batch));
+    KQ_RET(plan_ops(ctx, cg, pred, ex, false, ctx->max_smem_optin, &P));
+    if (!P.fits) return kq_fail(ctx, KQ_ERR_UNSUPPORTED, "kq_filter_project_host: too many outputs for one launch");
+    if (out_rows) *out_rows = 0;
+    if (n == 0) return KQ_OK;
+    void* kernel = nullptr;
+    KQ_RET(kq_jit_kernel(ctx, P.defines, P.gen, KQ_SKEL_OPS, P.entry, P.smem, &kernel));
+
+    const int64_t CH = (int64_t)TILE * 2048;          // rows per chunk (4 Mi): a multiple of the tile and of 64 (bitmap words)
+    const int64_t nchunks = (n + CH - 1) / CH, ntiles = (n + TILE - 1) / TILE;
+    auto width = [](int t) { return t == KQ_DATE32 || t == KQ_I32 ? 4 : 8; };
+
+    // device memory: double-buffered input chunks, full-size outputs, look-back descriptors
+    std::vector<void*> allocs;
+    cudaEvent_t h2d_done[2] = {nullptr, nullptr}, k_done[2] = {nullptr, nullptr}, cnt_ev[2] = {nullptr, nullptr};
+    uint64_t* h_cnt = nullptr;
+    auto cleanup = [&](int s) {
+        cudaStreamSynchronize(ctx->copy_stream[0]); cudaStreamSynchronize(ctx->copy_stream[1]); cudaStreamSynchronize(ctx->stream);
+        for (void* p : allocs) kq_dev_free(ctx, p);
+        for (int i = 0; i < 2; i++) { if (h2d_done[i]) cudaEventDestroy(h2d_done[i]); if (k_done[i]) cudaEventDestroy(k_done[i]); if (cnt_ev[i]) cudaEventDestroy(cnt_ev[i]); }
+        if (h_cnt) cudaFreeHost(h_cnt);
+        return s;
+    };
+    auto dalloc = [&](size_t bytes, void** p) { int s = kq_dev_alloc(ctx, bytes, p); if (s == KQ_OK) allocs.push_back(*p); return s; };
+    int st = KQ_OK;
+    std::vector<void*> in_d[2], in_v[2];
+    for (int s = 0; s < 2 && st == KQ_OK; s++) {
+        in_d[s].assign((size_t)ncols, nullptr); in_v[s].assign((size_t)ncols, nullptr);
+        for (int c = 0; c < ncols && st == KQ_OK; c++) {
+            st = dalloc(types[c] == KQ_BOOL ? (size_t)CH / 8 : (size_t)CH * width(types[c]), &in_d[s][(size_t)c]);
+            if (st == KQ_OK && nullable[(size_t)c]) st = dalloc((size_t)CH / 8, &in_v[s][(size_t)c]);
+        }
+    }
+    std::vector<void*> o_d((size_t)nexprs, nullptr), o_v((size_t)nexprs, nullptr);
+    for (int k = 0; k < nexprs && st == KQ_OK; k++) {
+        const size_t bytes = P.out_type[(size_t)k] == KQ_BOOL ? (size_t)((n + 63) / 64) * 8 : (size_t)n * width(P.out_type[(size_t)k]);
+        st = dalloc(bytes, &o_d[(size_t)k]);
+        if (st == KQ_OK && P.out_type[(size_t)k] == KQ_BOOL) cudaMemsetAsync(o_d[(size_t)k], 0, bytes, ctx->stream);
+        if (st == KQ_OK && P.out_nullable[(size_t)k]) {
+            st = dalloc((size_t)((n + 63) / 64) * 8, &o_v[(size_t)k]);
+            if (st == KQ_OK) cudaMemsetAsync(o_v[(size_t)k], 0, (size_t)((n + 63) / 64) * 8, ctx->stream);
+        }
+    }
+    unsigned long long* scratch = nullptr;     // [0]: out_count, [2..]: tile descriptors
+    if (st == KQ_OK) st = dalloc((size_t)(ntiles + 2) * 8, (void**)&scratch);
+    if (st != KQ_OK) return cleanup(st);
+    cudaMemsetAsync(scratch, 0, (size_t)(ntiles + 2) * 8, ctx->stream);
+    for (int i = 0; i < 2; i++) {
+        cudaEventCreateWithFlags(&h2d_done[i], cudaEventDisableTiming); cudaEventCreateWithFlags(&k_done[i], cudaEventDisableTiming);
+        cudaEventCreateWithFlags(&cnt_ev[i], cudaEventDisableTiming);
+    }
+    if (cudaMallocHost(&h_cnt, 2 * sizeof(uint64_t)) != cudaSuccess) return cleanup(kq_fail(ctx, KQ_ERR_OUT_OF_MEMORY, "pinned count slots"));
+    // the side streams start after everything queued so far on the compute stream (allocator order, memsets)
+    cudaEventRecord(ctx->copy_done, ctx->stream);
+    cudaStreamWaitEvent(ctx->copy_stream[0], ctx->copy_done, 0);
+    cudaStreamWaitEvent(ctx->copy_stream[1], ctx->copy_done, 0);
+
+    OpArgs A;
+    memset(&A, 0, sizeof A);
+    A.n = n; A.ntiles = ntiles; A.err = ctx->d_err; A.sp = P.sp;
+    A.q = cg.args;
+    A.tile_desc = scratch + 2; A.out_count = scratch; A.ticket = (unsigned int*)(scratch + 1);
+    for (int k = 0; k < nexprs; k++) { A.outs[k].data = o_d[(size_t)k]; A.outs[k].validity = (uint32_t*)o_v[(size_t)k]; }
+    void* kargs[] = {&A};
+
+    // D2H of output rows [from, to) (bit-packed buffers move whole 32-bit words: boundary words are rewritten by later chunks)
+    auto download = [&](int64_t from, int64_t to) {
+        if (to <= from) return;
+        for (int k = 0; k < nexprs; k++) {
+            const int t = P.out_type[(size_t)k];
+            const int64_t w0 = from / 32, w1 = (to + 31) / 32;
+            if (t == KQ_BOOL) cudaMemcpyAsync((char*)out_data[k] + w0 * 4, (char*)o_d[(size_t)k] + w0 * 4, (size_t)(w1 - w0) * 4, cudaMemcpyDeviceToHost, ctx->copy_stream[1]);
+            else cudaMemcpyAsync((char*)out_data[k] + from * width(t), (char*)o_d[(size_t)k] + from * width(t), (size_t)(to - from) * width(t), cudaMemcpyDeviceToHost, ctx->copy_stream[1]);
+            if (out_validity && out_validity[k]) {
+                if (o_v[(size_t)k]) cudaMemcpyAsync(out_validity[k] + w0 * 4, (char*)o_v[(size_t)k] + w0 * 4, (size_t)(w1 - w0) * 4, cudaMemcpyDeviceToHost, ctx->copy_stream[1]);
+                else memset(out_validity[k] + from / 8, 0xFF, (size_t)((to + 7) / 8 - from / 8));       // no nulls: all-ones (kq_column_download convention)
+            }
+        }
+    };
+
+    int64_t done_rows = 0;          // output rows already handed to the D2H stream
+    for (int64_t i = 0; i <= nchunks; i++) {
+        if (i < nchunks) {
+            const int s = (int)(i & 1);
+            const int64_t row0 = i * CH, rows = std::min(CH, n - row0);
+            if (i >= 2) cudaStreamWaitEvent(ctx->copy_stream[0], k_done[s], 0);       // the chunk buffer is free once its last kernel ran
+            for (int c = 0; c < ncols; c++) {
+                const size_t bytes = types[c] == KQ_BOOL ? (size_t)((rows + 7) / 8) : (size_t)rows * width(types[c]);
+                const size_t off = types[c] == KQ_BOOL ? (size_t)(row0 / 8) : (size_t)row0 * width(types[c]);
+                cudaMemcpyAsync(in_d[s][(size_t)c], (const char*)data[c] + off, bytes, cudaMemcpyHostToDevice, ctx->copy_stream[0]);
+                if (nullable[(size_t)c]) cudaMemcpyAsync(in_v[s][(size_t)c], validity[c] + row0 / 8, (size_t)((rows + 7) / 8), cudaMemcpyHostToDevice, ctx->copy_stream[0]);
+            }
+            cudaEventRecord(h2d_done[s], ctx->copy_stream[0]);
+            cudaStreamWaitEvent(ctx->stream, h2d_done[s], 0);
+            // the kernel indexes rows of the whole batch: bias the chunk pointers back by the chunk's first row
+            for (int q = 0; q < cg.ncols; q++) {
+                const int c = cg.slot_col[q];
+                const size_t off = types[c] == KQ_BOOL ? (size_t)(row0 / 8) : (size_t)row0 * width(types[c]);
+                A.q.cols[q].data = (const char*)in_d[s][(size_t)c] - off;
+                A.q.cols[q].validity = nullable[(size_t)c] ? (const uint32_t*)((const char*)in_v[s][(size_t)c] - row0 / 8) : nullptr;
+            }
+            stage_plan_bind(A.sp, A.q);          // the TMA producer reads through the same biased bases
+            A.tile_begin = row0 / TILE; A.tile_end = (row0 + rows + TILE - 1) / TILE;
+            const int grid = (int)std::min<int64_t>(A.tile_end - A.tile_begin, (int64_t)ctx->sm_count);
+            cudaError_t e = cudaLaunchCooperativeKernel(kernel, dim3(grid), dim3(THREADS_FILTER), kargs, (size_t)P.smem, ctx->stream);
+            if (e != cudaSuccess) return cleanup(kq_cuda_fail(ctx, e, "kq_filter_project"));
+            ctx->launches++;
+            cudaEventRecord(k_done[s], ctx->stream);
+            // running total = inclusive prefix of the chunk's last tile
+            cudaMemcpyAsync(&h_cnt[s], A.tile_desc + (A.tile_end - 1), 8, cudaMemcpyDeviceToHost, ctx->stream);
+            cudaEventRecord(cnt_ev[s], ctx->stream);
+        }
+        if (i >= 1) {       // results of chunk i-1: its kernel is queued behind nothing but chunk i's copies
+            const int s = (int)((i - 1) & 1);
+            cudaError_t e = cudaEventSynchronize(cnt_ev[s]);
+            if (e != cudaSuccess) return cleanup(kq_cuda_fail(ctx, e, "cudaEventSynchronize"));
+            const int64_t total = (int64_t)(h_cnt[s] & ((1ULL << 62) - 1ULL));
+            cudaStreamWaitEvent(ctx->copy_stream[1], k_done[s], 0);
+            download(done_rows, total);
+            done_rows = total;
+        }
+    }
+    cudaError_t e = cudaStreamSynchronize(ctx->copy_stream[1]);
+    if (e != cudaSuccess) return cleanup(kq_cuda_fail(ctx, e, "D2H"));
+    if (out_rows) *out_rows = done_rows;
+    st = kq_check_device_errors(ctx);
+    return cleanup(st);
 }
 
 }  // extern "C"

@@ -451,6 +451,7 @@ class Engine(Exprs):
 
         self.RecordBatch = _RB
         self.KqError = KqError
+        self.type_of = _type_of
 
     # operators
     def project(self, exprs, batch: RecordBatch) -> RecordBatch:
@@ -469,6 +470,23 @@ class Engine(Exprs):
         out = C.c_void_p()
         self.ctx.check(lib().kq_filter_project(self.ctx.h, pred.h, _expr_array(exprs), len(exprs), batch.h, C.byref(out)))
         return RecordBatch(self.ctx, out)
+
+    def filter_project_host(self, pred, exprs, cols, n, outs) -> int:
+        """kq_filter_project_host: host Arrow buffers in, host result buffers out, streamed in chunks with
+        H2D / kernel / D2H overlapped. cols = [(kq_type, validity_address or None, data_address)];
+        outs = [(data_address, validity_address or None)] with room for n rows each. Returns the row count."""
+        nc, no = len(cols), len(outs)
+        types = (C.c_int * max(nc, 1))(*[c[0] for c in cols])
+        val = (C.c_void_p * max(nc, 1))(*[c[1] for c in cols])
+        dat = (C.c_void_p * max(nc, 1))(*[c[2] for c in cols])
+        od = (C.c_void_p * max(no, 1))(*[o[0] for o in outs])
+        ov = (C.c_void_p * max(no, 1))(*[o[1] for o in outs])
+        rows = C.c_int64(0)
+        has_v = any(c[1] for c in cols)
+        self.ctx.check(lib().kq_filter_project_host(self.ctx.h, pred.h, _expr_array(exprs), len(exprs), nc, types,
+                                                    val if has_v else None, dat, n, od, ov if any(o[1] for o in outs) else None,
+                                                    C.byref(rows)))
+        return rows.value
 
     def HashAggregate(self, group_exprs, aggs, pred=None, expected_groups=0):
         return HashAggregate(self, group_exprs, aggs, pred, expected_groups)
