@@ -138,6 +138,13 @@ WORKLOADS = {
 }
 
 
+def shard_range(rank, rows_per_gpu):
+    """Rows [begin, end) of the global table that `rank` owns: contiguous, equal-sized shards (weak scaling:
+    the global table has world * rows_per_gpu rows). The generator is keyed by the global row index, so the
+    union of all shards is the same table at every GPU count."""
+    return rank * rows_per_gpu, (rank + 1) * rows_per_gpu
+
+
 # ---------------------------------------------------------------------------------------------------
 class ClockSampler:
     """nvidia-smi clocks/throttle reasons sampled DURING the timed region (B200_PROFILING.md)."""
@@ -304,8 +311,8 @@ def main():
 
     # each rank owns rows [rank*R, (rank+1)*R) of the same global table (weak scaling)
     n = wl.rows
-    row0 = rank * n
-    batch = E.generate(wl.specs(), 42, row0, row0 + n)
+    row0, row1 = shard_range(rank, n)
+    batch = E.generate(wl.specs(), 42, row0, row1)
     ctx.sync()
 
     def barrier():
