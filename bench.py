@@ -50,7 +50,7 @@ class Workload:
 
 
 class FilterProject(Workload):
-    kernel = "k_filter_project"
+    kernel = "kq_filter_project"
 
     def __init__(self, name, rows, flt):
         super().__init__(name, rows, "f64" if flt else "int64")
@@ -80,7 +80,7 @@ class FilterProject(Workload):
 
 
 class GroupBy(Workload):
-    kernel = "k_hash_aggregate"
+    kernel = "kq_hash_aggregate"
 
     def __init__(self, name, rows, kind):
         super().__init__(name, rows, "f64")

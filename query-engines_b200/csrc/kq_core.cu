@@ -322,8 +322,7 @@ __global__ void k_popcount_valid(const uint32_t* __restrict__ bits, int64_t n, u
 __global__ void k_fill_ones(uint32_t* bits, int64_t nwords) {
     for (int64_t w = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; w < nwords; w += (int64_t)gridDim.x * blockDim.x) bits[w] = 0xffffffffu;
 }
-__global__ void k_rebase_offsets(int32_t* off, int64_t n1, const int32_t* first) {
-    int32_t base = *first;
+__global__ void k_rebase_offsets(int32_t* off, int64_t n1, int32_t base) {
     for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n1; i += (int64_t)gridDim.x * blockDim.x) off[i] -= base;
 }
 
@@ -371,7 +370,7 @@ int kq_column_upload(kq_ctx* ctx, int type, int64_t n, const uint8_t* validity, 
     if (e == cudaSuccess) e = cudaStreamSynchronize(cs);
     if (e != cudaSuccess) { kq_column_free(c); return kq_cuda_fail(ctx, e, "column upload"); }
     if (type == KQ_UTF8 && n > 0 && payload_off != 0) {
-        k_rebase_offsets<<<grid_for(ctx, n + 1, 256), 256, 0, ctx->stream>>>(c->offsets, n + 1, c->offsets);
+        k_rebase_offsets<<<grid_for(ctx, n + 1, 256), 256, 0, ctx->stream>>>(c->offsets, n + 1, (int32_t)payload_off);
         ctx->launches++;
     }
     *out = c;

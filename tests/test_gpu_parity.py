@@ -218,6 +218,18 @@ def test_filter_project_host_pipeline(G, oracle, n, null_frac):
         same(a, w)
 
 
+def test_upload_of_a_sliced_utf8_vector_rebases_offsets(gpu, gctx):
+    """Arrow slices keep the parent's data buffer and a window of its offsets (offsets[0] != 0)."""
+    import ctypes as C
+    n = 300_000
+    whole = pa.array([("s%d" % (i % 977)) for i in range(n)], type=pa.string())
+    _, off, data = whole.buffers()
+    for lo, hi in [(0, n), (1, 100), (123_457, n), (299_999, n)]:
+        out = C.c_void_p()
+        gctx.check(gpu.lib().kq_column_upload(gctx.h, UTF8, hi - lo, None, off.address + 4 * lo, data.address, data.size, C.byref(out)))
+        same(gpu.Column(gctx, out).to_arrow(), pa.concat_arrays([whole.slice(lo, hi - lo)]))
+
+
 def test_filter_gathers_every_column_in_order(G, oracle):
     rng = np.random.default_rng(11)
     arrs = rand_table(rng, 50001, 0.1)
