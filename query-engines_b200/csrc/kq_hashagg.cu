@@ -463,15 +463,15 @@ static int plan_agg(kq_ctx* ctx, kq_hashagg* h, kq_batch* input, int smem_optin,
     for (int b = 0; b < A.sp.nbuf; b++) has_bytes |= A.sp.buf[b].kind == SK_BYTES;
     const int ring = A.sp.nstages * A.sp.stage_bytes;
     const int entry_words = (NK + 2) / 2 * 2;
-    const int per_group = WARPS * 32 * (4 * ncnt + 8 * ns) + 8 + 4 + 8 * nm;
+    const int per_group = WARPS * 32 * (4 * ncnt + 8 * ns) + 8 + 4 + 8 * nm;     // the kernel adds one trash group (fg + 1)
     int dir_slots = 1024;
     int budget = smem_optin - 3072 - ring;
     while (dir_slots > 256 && dir_slots * entry_words * 8 + 16 * per_group > budget) dir_slots >>= 1;
     budget -= dir_slots * entry_words * 8 + 64;
-    int fg = std::min(FE_MAX_GROUPS, budget / per_group);
+    int fg = std::min(FE_MAX_GROUPS, budget / per_group - 1);
     if (fg < 1) fg = 0;
     A.fe_groups = fg;
-    A.smem_bytes = ring + dir_slots * entry_words * 8 + std::max(fg, 1) * 12 + fg * nm * 8 + WARPS * fg * 32 * (8 * ns + 4 * ncnt);
+    A.smem_bytes = ring + dir_slots * entry_words * 8 + std::max(fg, 1) * 12 + (fg + 1) * nm * 8 + WARPS * (fg + 1) * 32 * (8 * ns + 4 * ncnt);
     A.smem_bytes = (A.smem_bytes + 127) / 128 * 128;
 
     auto arr = [&](const char* type, const char* name, int nelem, auto get) {

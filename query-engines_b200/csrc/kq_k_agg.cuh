@@ -148,6 +148,53 @@ __device__ __forceinline__ void fe_accumulate(const FrontEnd& fe, int gid, int l
     }
 }
 
+// ---- explicit shared-space accessors (32-bit addresses: no generic-pointer arithmetic on the hot path) -------------
+__device__ __forceinline__ uint32_t lds_u32(uint32_t a) { uint32_t v; asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(a) : "memory"); return v; }
+__device__ __forceinline__ uint64_t lds_u64(uint32_t a) { uint64_t v; asm volatile("ld.shared.u64 %0, [%1];" : "=l"(v) : "r"(a) : "memory"); return v; }
+__device__ __forceinline__ uint4 lds_u128(uint32_t a) { uint4 r; asm volatile("ld.shared.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w) : "r"(a) : "memory"); return r; }
+__device__ __forceinline__ void sts_u32(uint32_t a, uint32_t v) { asm volatile("st.shared.u32 [%0], %1;" ::"r"(a), "r"(v) : "memory"); }
+__device__ __forceinline__ void sts_u64(uint32_t a, uint64_t v) { asm volatile("st.shared.u64 [%0], %1;" ::"r"(a), "l"(v) : "memory"); }
+// CTA-shared MIN/MAX slot: a predicated reduction, no branch (the slot is only written when the value beats it)
+__device__ __forceinline__ void smem_min_u64(uint32_t a, uint64_t m) {
+    asm volatile("{\n\t.reg .pred p;\n\t.reg .u64 c;\n\tld.volatile.shared.u64 c, [%0];\n\tsetp.lt.u64 p, %1, c;\n\t@p red.shared.min.u64 [%0], %1;\n\t}"
+                 ::"r"(a), "l"(m) : "memory");
+}
+__device__ __forceinline__ void smem_max_u64(uint32_t a, uint64_t m) {
+    asm volatile("{\n\t.reg .pred p;\n\t.reg .u64 c;\n\tld.volatile.shared.u64 c, [%0];\n\tsetp.gt.u64 p, %1, c;\n\t@p red.shared.max.u64 [%0], %1;\n\t}"
+                 ::"r"(a), "l"(m) : "memory");
+}
+
+// Branch-free front-end accumulate of input I for one row. g = the row's group, or FG (a trash group
+// nobody reads) when the row is filtered out / takes the slow path; an invalid (null) input goes to the
+// trash group as well, so every read-modify-write is unconditional.
+template <int I>
+__device__ __forceinline__ void fe_accumulate_fast(uint32_t a_cnt, uint32_t a_sum, uint32_t a_mm, int g, int lane, const AggSink& sink, int r) {
+    if constexpr (I < Q::NIN) {
+        constexpr int FL = Q::IN_FLAGS[I];
+        const bool valid = (sink.inok[I] >> r) & 1u;
+        const int gi = (Q::IN_CNT[I] > 0 && !valid) ? FG : g;           // statically non-null inputs: always valid
+        if constexpr (Q::IN_CNT[I] > 0) {
+            const uint32_t a = a_cnt + ((((uint32_t)gi * Q::NCNT + Q::IN_CNT[I]) << 5) + lane) * 4u;
+            sts_u32(a, lds_u32(a) + 1u);
+        }
+        if constexpr ((FL & (F_SUM | F_MIN | F_MAX)) != 0) {
+            const uint64_t v = sink.in[I][r];
+            if constexpr ((FL & F_SUM) != 0) {
+                const uint32_t a = a_sum + ((((uint32_t)gi * Q::NSUM + Q::FE_SUM[I]) << 5) + lane) * 8u;
+                if constexpr ((FL & F_INT) != 0) sts_u64(a, lds_u64(a) + v);
+                else sts_u64(a, as_u64(__dadd_rn(as_f64(lds_u64(a)), as_f64(v))));
+            }
+            if constexpr ((FL & (F_MIN | F_MAX)) != 0) {
+                constexpr bool is_int = (FL & F_INT) != 0;
+                const uint64_t m = order_map(is_int ? v : canon_nan(v), is_int);
+                if constexpr ((FL & F_MIN) != 0) smem_min_u64(a_mm + ((uint32_t)gi * Q::NMM + Q::FE_MIN[I]) * 8u, m);
+                if constexpr ((FL & F_MAX) != 0) smem_max_u64(a_mm + ((uint32_t)gi * Q::NMM + Q::FE_MAX[I]) * 8u, m);
+            }
+        }
+        fe_accumulate_fast<I + 1>(a_cnt, a_sum, a_mm, g, lane, sink, r);
+    }
+}
+
 // Accumulate one row straight into its record of the global table.
 template <int I>
 __device__ __forceinline__ void global_accumulate_all(const AggArgs& A, uint64_t* rec, const AggSink& sink, int r) {
@@ -198,14 +245,15 @@ extern "C" __global__ void __launch_bounds__(THREADS, 1) kq_hash_aggregate(const
     FrontEnd fe;
     fe.dir = reinterpret_cast<uint64_t*>(p0);            p0 += (size_t)DIR * ENTRY_WORDS * 8;
     uint64_t* gslot = reinterpret_cast<uint64_t*>(p0);   p0 += (size_t)(FG > 0 ? FG : 1) * 8;
-    fe.mm = reinterpret_cast<uint64_t*>(p0);             p0 += (size_t)FG * NMM * 8;
-    uint64_t* sum0 = reinterpret_cast<uint64_t*>(p0);    p0 += (size_t)WARPS * FG * NSUM * 32 * 8;
-    uint32_t* cnt0 = reinterpret_cast<uint32_t*>(p0);    p0 += (size_t)WARPS * FG * NCNT * 32 * 4;
+    constexpr int FG1 = FG + 1;               // + one trash group: the branch-free path parks filtered-out / slow-path rows there
+    fe.mm = reinterpret_cast<uint64_t*>(p0);             p0 += (size_t)FG1 * NMM * 8;
+    uint64_t* sum0 = reinterpret_cast<uint64_t*>(p0);    p0 += (size_t)WARPS * FG1 * NSUM * 32 * 8;
+    uint32_t* cnt0 = reinterpret_cast<uint32_t*>(p0);    p0 += (size_t)WARPS * FG1 * NCNT * 32 * 4;
     fe.gid2slot = reinterpret_cast<uint32_t*>(p0);       p0 += (size_t)(FG > 0 ? FG : 1) * 4;
     const size_t fe_end = (size_t)(p0 - smem);
     fe.dir_count = &s_dir_count;
-    fe.sum = sum0 + (size_t)(warp < 0 ? 0 : warp) * FG * NSUM * 32;
-    fe.cnt = cnt0 + (size_t)(warp < 0 ? 0 : warp) * FG * NCNT * 32;
+    fe.sum = sum0 + (size_t)(warp < 0 ? 0 : warp) * FG1 * NSUM * 32;
+    fe.cnt = cnt0 + (size_t)(warp < 0 ? 0 : warp) * FG1 * NCNT * 32;
 
     for (size_t i = fe_begin + threadIdx.x * 4; i < fe_end; i += THREADS * 4) *reinterpret_cast<uint32_t*>(smem + i) = 0;
     if (threadIdx.x == 0) {
@@ -214,7 +262,7 @@ extern "C" __global__ void __launch_bounds__(THREADS, 1) kq_hash_aggregate(const
         mbar_fence_init();
     }
     __syncthreads();
-    for (int i = threadIdx.x; i < FG * NMM; i += THREADS) fe.mm[i] = ((Q::MM_ISMIN >> (i % (NMM > 0 ? NMM : 1))) & 1u) ? ~0ULL : 0ULL;
+    for (int i = threadIdx.x; i < FG1 * NMM; i += THREADS) fe.mm[i] = ((Q::MM_ISMIN >> (i % (NMM > 0 ? NMM : 1))) & 1u) ? ~0ULL : 0ULL;
     __syncthreads();
 
     if (wid == PRODUCER_WARP) {
@@ -247,6 +295,7 @@ extern "C" __global__ void __launch_bounds__(THREADS, 1) kq_hash_aggregate(const
     } else {
         AggSink sink;
         bool bypass = FG == 0;
+        const uint32_t a_dir = smem_u32(fe.dir), a_cnt = smem_u32(fe.cnt), a_sum = smem_u32(fe.sum), a_mm = smem_u32(fe.mm);
         for (int k = 0;; k++) {
             const int s = k % S;
             mbar_wait(&full[s], (k / S) & 1);
@@ -261,42 +310,68 @@ extern "C" __global__ void __launch_bounds__(THREADS, 1) kq_hash_aggregate(const
             __syncwarp();
             if (lane == 0) mbar_arrive(&empty[s]);       // everything needed is in registers now
 
-            // pass 1: key -> hash -> front-end group id for the R owned rows (independent chains)
+            // canonical key words + null masks of the R owned rows
             uint32_t nm[R];
-            int gid[R];
 #pragma unroll
             for (int r = 0; r < R; r++) {
-                uint64_t kw[MAX_KEYS];
                 uint32_t nullmask = 0;
 #pragma unroll
-                for (int k2 = 0; k2 < MAX_KEYS; k2++) {
-                    kw[k2] = 0;
-                    if (k2 < Q::NKEYS) {
-                        if ((sink.keyok[k2] >> r) & 1u) kw[k2] = ((Q::KEY_F64_MASK >> k2) & 1u) ? canon_nan(sink.key[k2][r]) : sink.key[k2][r];
-                        else nullmask |= 1u << k2;
-                        sink.key[k2][r] = kw[k2];
-                    }
+                for (int k2 = 0; k2 < Q::NKEYS; k2++) {
+                    uint64_t w = 0;
+                    if ((sink.keyok[k2] >> r) & 1u) w = ((Q::KEY_F64_MASK >> k2) & 1u) ? canon_nan(sink.key[k2][r]) : sink.key[k2][r];
+                    else nullmask |= 1u << k2;
+                    sink.key[k2][r] = w;
                 }
                 nm[r] = nullmask;
-                gid[r] = -1;
-                if (!bypass && ((sink.sel >> r) & 1u)) gid[r] = dir_lookup(fe, dir_hash(kw, nullmask), kw, nullmask);
             }
-            // pass 2: accumulate
-            int fe_hits = 0, rows = 0;
+            uint32_t slow = sink.sel;             // rows that still need the general path
+            int fe_hits = 0;
+            if (!bypass) {
+                // pass 1 (branch-free): one directory probe per row; a first-probe hit yields the group id
+                int gid[R];
+                slow = 0;
 #pragma unroll
-            for (int r = 0; r < R; r++) {
-                if (!((sink.sel >> r) & 1u)) continue;
-                rows++;
-                if (gid[r] >= 0) {
-                    fe_hits++;
-                    if constexpr (Q::CNT0_USED) fe.cnt[((gid[r] * NCNT) << 5) + lane] += 1u;
-                    fe_accumulate<0>(fe, gid[r], lane, sink, r);
-                } else {
+                for (int r = 0; r < R; r++) {
                     uint64_t kw[MAX_KEYS];
 #pragma unroll
                     for (int k2 = 0; k2 < MAX_KEYS; k2++) kw[k2] = k2 < Q::NKEYS ? sink.key[k2][r] : 0;
-                    uint64_t* rec = table_find_or_insert(A, hash_key(kw, nm[r], Q::NKEYS), kw, nm[r]);
-                    global_accumulate_all<0>(A, rec, sink, r);
+                    const uint32_t e = a_dir + dir_hash(kw, nm[r]) * (ENTRY_WORDS * 8u);
+                    const uint4 q = lds_u128(e);
+                    bool hit = q.x >= 2u && q.x != DIR_GLOBAL && q.y == nm[r];
+                    if constexpr (Q::NKEYS >= 1) hit &= ((uint64_t)q.z | ((uint64_t)q.w << 32)) == kw[0];
+#pragma unroll
+                    for (int k2 = 1; k2 < Q::NKEYS; k2++) hit &= lds_u64(e + 8u + 8u * k2) == kw[k2];
+                    const bool on = (sink.sel >> r) & 1u;
+                    gid[r] = (on && hit) ? (int)(q.x - 2u) : FG;
+                    slow |= (uint32_t)(on && !hit) << r;
+                }
+                // pass 2 (branch-free): unconditional read-modify-write of the lane-private slots
+#pragma unroll
+                for (int r = 0; r < R; r++) {
+                    if constexpr (Q::CNT0_USED) { const uint32_t a = a_cnt + ((((uint32_t)gid[r] * NCNT) << 5) + lane) * 4u; sts_u32(a, lds_u32(a) + 1u); }
+                    fe_accumulate_fast<0>(a_cnt, a_sum, a_mm, gid[r], lane, sink, r);
+                }
+                fe_hits = __popc(sink.sel & ~slow);
+            }
+            // general path for the rest: directory probing with insertion, else the global table
+            int rows = __popc(sink.sel);
+            if (slow) {
+#pragma unroll
+                for (int r = 0; r < R; r++) {
+                    if (!((slow >> r) & 1u)) continue;
+                    uint64_t kw[MAX_KEYS];
+#pragma unroll
+                    for (int k2 = 0; k2 < MAX_KEYS; k2++) kw[k2] = k2 < Q::NKEYS ? sink.key[k2][r] : 0;
+                    int g = -1;
+                    if (!bypass) g = dir_lookup(fe, dir_hash(kw, nm[r]), kw, nm[r]);
+                    if (g >= 0) {
+                        fe_hits++;
+                        if constexpr (Q::CNT0_USED) fe.cnt[((g * NCNT) << 5) + lane] += 1u;
+                        fe_accumulate<0>(fe, g, lane, sink, r);
+                    } else {
+                        uint64_t* rec = table_find_or_insert(A, hash_key(kw, nm[r], Q::NKEYS), kw, nm[r]);
+                        global_accumulate_all<0>(A, rec, sink, r);
+                    }
                 }
             }
             // once the directory is full and this warp mostly misses it, stop probing it (high cardinality)

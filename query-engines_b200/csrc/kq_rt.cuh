@@ -237,25 +237,49 @@ __device__ __forceinline__ uint64_t lds_u64_unaligned(const unsigned char* p) {
     return sh ? ((lo >> sh) | (hi << (64u - sh))) : lo;
 }
 // short string (<= 7 bytes) -> packed u64 group key: bytes little-endian, length in the top byte.
-// SB >= 0: the tile's string bytes are staged at byte offset SB of the stage (when they fit: rc.bbase[SLOT] >= 0).
+// SB >= 0: the tile's string bytes are staged at byte offset SB of the stage (when they fit: rc.bbase[SLOT] >= 0);
+// that path is branch-free per row (one uniform branch per tile).
 template <int SOFF_OFF, int SB, int SLOT>
 __device__ __forceinline__ void utf8_pack(const QCol& c, uint32_t ok, const RowCtx& rc, uint64_t (&out)[R]) {
-    const uint8_t* bytes = reinterpret_cast<const uint8_t*>(c.data);
     long long base = -1;
-    if constexpr (SB >= 0) base = rc.bbase[SLOT];
+    if constexpr (SB >= 0 && SOFF_OFF >= 0) base = rc.bbase[SLOT];
+    uint32_t too_long = 0;
+    if (base >= 0) {
+        const unsigned char* sb = rc.stage + SB - base;
+        const int32_t* so = reinterpret_cast<const int32_t*>(rc.stage + SOFF_OFF);
 #pragma unroll
-    for (int r = 0; r < R; r++) {
-        uint64_t key = 0;
-        if ((ok >> r) & 1u) {
-            int a, b; utf8_bounds<SOFF_OFF>(c.offsets, rc, r, a, b);
-            int len = b - a;
-            if (len > 7) { if ((rc.active >> r) & 1u) atomicOr(rc.err, ERR_LONG_KEY); len = 7; }
-            if (SB >= 0 && base >= 0) key = lds_u64_unaligned(rc.stage + SB + (int)((long long)a - base)) & ((1ULL << (8 * len)) - 1ULL);
-            else for (int i = 0; i < len; i++) key |= (uint64_t)__ldg(bytes + a + i) << (8 * i);
-            key |= (uint64_t)len << 56;
+        for (int j = 0; j < NCHUNK; j++) {
+            // the lane's two adjacent rows share their middle offset: o[2l], o[2l+1], o[2l+2]
+            const int t0 = rc.trow0(j);
+            const int2 o01 = *reinterpret_cast<const int2*>(so + t0);
+            const int o2 = so[t0 + 2];
+            // rows past the end of the batch have no offsets (stale shared memory): give them an empty, in-range string
+            const bool in0 = (rc.inr >> (2 * j)) & 1u, in1 = (rc.inr >> (2 * j + 1)) & 1u;
+            const int a0 = in0 ? o01.x : (int)base, a1 = in1 ? o01.y : (int)base;
+            const int len0 = in0 ? o01.y - o01.x : 0, len1 = in1 ? o2 - o01.y : 0;
+            too_long |= (uint32_t)(len0 > 7) << (2 * j) | (uint32_t)(len1 > 7) << (2 * j + 1);
+            const int l0 = len0 > 7 ? 7 : len0, l1 = len1 > 7 ? 7 : len1;
+            const uint64_t k0 = (lds_u64_unaligned(sb + a0) & ((1ULL << (8 * l0)) - 1ULL)) | ((uint64_t)l0 << 56);
+            const uint64_t k1 = (lds_u64_unaligned(sb + a1) & ((1ULL << (8 * l1)) - 1ULL)) | ((uint64_t)l1 << 56);
+            out[2 * j] = ((ok >> (2 * j)) & 1u) ? k0 : 0ULL;
+            out[2 * j + 1] = ((ok >> (2 * j + 1)) & 1u) ? k1 : 0ULL;
         }
-        out[r] = key;
+    } else {
+        const uint8_t* bytes = reinterpret_cast<const uint8_t*>(c.data);
+#pragma unroll
+        for (int r = 0; r < R; r++) {
+            uint64_t key = 0;
+            if ((ok >> r) & 1u) {
+                int a, b; utf8_bounds<SOFF_OFF>(c.offsets, rc, r, a, b);
+                int len = b - a;
+                if (len > 7) { too_long |= 1u << r; len = 7; }
+                for (int i = 0; i < len; i++) key |= (uint64_t)__ldg(bytes + a + i) << (8 * i);
+                key |= (uint64_t)len << 56;
+            }
+            out[r] = key;
+        }
     }
+    if (too_long & ok & rc.active) atomicOr(rc.err, ERR_LONG_KEY);
 }
 
 // CastExpression Utf8 -> Float64: Java Double.parseDouble grammar (rule R5). Decimal inputs with at
