@@ -106,8 +106,9 @@ class GroupBy(Workload):
             charge = E.binary("MUL", disc_price, E.binary("ADD", one, E.col(6)))
             pred = E.binary("LE", E.col(0), E.lit_date32(10471))
             return E.HashAggregate([E.col(1), E.col(2)], [("SUM", E.col(3)), ("SUM", E.col(4)), ("SUM", disc_price),
-                                                        ("SUM", charge), ("COUNT", E.lit_i64(1))], pred=pred)
-        hint = 10_000_000 if self.kind == "high" else 0
+                                                        ("SUM", charge), ("COUNT", E.lit_i64(1))], pred=pred, expected_groups=6)
+        # the planner's cardinality estimate (dictionary sizes of the synthetic table): a sizing hint, not a limit
+        hint = 10_000_000 if self.kind == "high" else 50
         v = E.col(1)
         return E.HashAggregate([E.col(0)], [("SUM", v), ("MIN", v), ("MAX", v), ("COUNT", v)], expected_groups=hint)
 

@@ -2,6 +2,8 @@
 // the per-batch launch of the specialised aggregate kernel (kq_k_agg.cuh via kq_codegen.cu / kq_jit.cu),
 // finalisation into the single output batch (Main.kt:635-650) and the table maintenance kernels.
 #include <algorithm>
+#include <cstdio>
+#include <cstdlib>
 #include <cstring>
 
 #include "kq_aggtable.cuh"
@@ -21,7 +23,13 @@ struct AggGeometry {
     int tile() const { return warps * 32 * r; }
     int threads() const { return warps * 32 + 32; }
 };
-static AggGeometry agg_geometry(int ninputs) { return ninputs >= 3 ? AggGeometry{8, 6} : AggGeometry{4, 7}; }
+static AggGeometry agg_geometry(int ninputs) {
+    if (const char* e = getenv("KQ_AGG_GEOM")) {       // tuning experiments: "rows,warps"
+        int r = 0, w = 0;
+        if (sscanf(e, "%d,%d", &r, &w) == 2 && r >= 2 && r <= 16 && r % 2 == 0 && w >= 1 && w <= 24) return AggGeometry{r, w};
+    }
+    return ninputs >= 3 ? AggGeometry{8, 6} : AggGeometry{4, 7};
+}
 constexpr int AGG_MAX_STAGES = 4;
 
 // ---- table maintenance ---------------------------------------------------------------------------------------
@@ -390,8 +398,6 @@ int kq_hashagg_free(kq_hashagg* h) {
 // Everything about an aggregate launch that depends on the query SHAPE only: generated source, stage
 // plan, front-end layout. Fills the shape-dependent fields of A. No CUDA calls (kq_explain_hashagg).
 static int plan_agg(kq_ctx* ctx, kq_hashagg* h, kq_batch* input, int smem_optin, AggArgs& A, std::string* defines_out, std::string* gen_out) {
-    const AggGeometry geo = agg_geometry((int)h->inputs.size());
-    const int TILE = geo.tile(), WARPS = geo.warps;
     // generate: [predicate -> selection] keys..., inputs...
     KqCodegen cg;
     KQ_RET(cg.begin(ctx, input));
@@ -454,23 +460,45 @@ static int plan_agg(kq_ctx* ctx, kq_hashagg* h, kq_batch* input, int smem_optin,
         if (d.fe_min >= 0) { mm_word.push_back(d.rec_min); mm_ismin |= 1u << d.fe_min; }
         if (d.fe_max >= 0) mm_word.push_back(d.rec_max);
     }
-    // stage ring first (2..4 stages within ~64 KB, more only if two stages need it), front end gets the rest
-    std::string stage_defs = cg.plan_stages(64 * 1024, 1, TILE, &A.sp, true);
-    if (A.sp.nstages < 2) stage_defs = cg.plan_stages(std::min(2 * A.sp.stage_bytes, 112 * 1024), 2, TILE, &A.sp, true);
-    A.sp.nstages = std::max(1, std::min(A.sp.nstages, AGG_MAX_STAGES));
-    A.q = cg.args;
+    // Geometry + shared-memory split. Candidates in order of measured speed (more rows per thread = more
+    // independent work per warp; the lane-private front end costs shared memory per consumer warp); take the
+    // first one whose front end holds the expected number of groups (64 when unknown), else the roomiest.
+    static const AggGeometry CANDIDATES[] = {{10, 7}, {8, 7}, {8, 6}, {6, 6}, {4, 7}, {4, 4}};
+    const int need_groups = (int)std::min<int64_t>(FE_MAX_GROUPS, h->expected_groups > 0 ? h->expected_groups : FE_MAX_GROUPS);
+    const int entry_words = (NK + 2) / 2 * 2;
+    AggGeometry geo = CANDIDATES[0];
+    std::string stage_defs;
+    int fg = -1, dir_slots = 1024;
     bool has_bytes = false;
+    auto try_geometry = [&](const AggGeometry& g, StagePlan* sp, std::string* defs, int* dir_out) {
+        // stage ring first (2..4 stages within ~64 KB, more only if two stages need it), front end gets the rest
+        *defs = cg.plan_stages(64 * 1024, 1, g.tile(), sp, true);
+        if (sp->nstages < 2) *defs = cg.plan_stages(std::min(2 * sp->stage_bytes, 112 * 1024), 2, g.tile(), sp, true);
+        sp->nstages = std::max(1, std::min(sp->nstages, AGG_MAX_STAGES));
+        const int ring = sp->nstages * sp->stage_bytes;
+        const int per_group = g.warps * 32 * (4 * ncnt + 8 * ns) + 8 + 4 + 8 * nm;     // the kernel adds one trash group (fg + 1)
+        int dir = 1024;
+        int budget = smem_optin - 3072 - ring;
+        while (dir > 256 && dir * entry_words * 8 + (need_groups + 1) * per_group > budget) dir >>= 1;
+        budget -= dir * entry_words * 8 + 64;
+        *dir_out = dir;
+        return std::max(0, std::min(FE_MAX_GROUPS, budget / per_group - 1));
+    };
+    const char* forced = getenv("KQ_AGG_GEOM");
+    for (const AggGeometry& g : CANDIDATES) {
+        const AggGeometry cand = forced ? agg_geometry(NI) : g;
+        StagePlan sp; std::string defs; int dir;
+        const int f = try_geometry(cand, &sp, &defs, &dir);
+        if (f > fg) { fg = f; geo = cand; A.sp = sp; stage_defs = defs; dir_slots = dir; }
+        if (f >= need_groups || forced) break;
+    }
+    const int TILE = geo.tile(), WARPS = geo.warps;
+    (void)TILE;
+    A.q = cg.args;
     for (int b = 0; b < A.sp.nbuf; b++) has_bytes |= A.sp.buf[b].kind == SK_BYTES;
     const int ring = A.sp.nstages * A.sp.stage_bytes;
-    const int entry_words = (NK + 2) / 2 * 2;
-    const int per_group = WARPS * 32 * (4 * ncnt + 8 * ns) + 8 + 4 + 8 * nm;     // the kernel adds one trash group (fg + 1)
-    int dir_slots = 1024;
-    int budget = smem_optin - 3072 - ring;
-    while (dir_slots > 256 && dir_slots * entry_words * 8 + 16 * per_group > budget) dir_slots >>= 1;
-    budget -= dir_slots * entry_words * 8 + 64;
-    int fg = std::min(FE_MAX_GROUPS, budget / per_group - 1);
-    if (fg < 1) fg = 0;
     A.fe_groups = fg;
+    A.geo_r = geo.r; A.geo_warps = geo.warps;
     A.smem_bytes = ring + dir_slots * entry_words * 8 + std::max(fg, 1) * 12 + (fg + 1) * nm * 8 + WARPS * (fg + 1) * 32 * (8 * ns + 4 * ncnt);
     A.smem_bytes = (A.smem_bytes + 127) / 128 * 128;
 
@@ -514,7 +542,7 @@ int kq_hashagg_update(kq_ctx* ctx, kq_hashagg* h, kq_batch* input) {
     std::string defines, gen;
     KQ_RET(plan_agg(ctx, h, input, ctx->max_smem_optin, A, &defines, &gen));
     if (n == 0) return KQ_OK;
-    const AggGeometry geo = agg_geometry((int)h->inputs.size());
+    const AggGeometry geo{A.geo_r, A.geo_warps};
     const int TILE = geo.tile(), THREADS = geo.threads();
     A.n = n; A.ntiles = (n + TILE - 1) / TILE;
     void* kernel = nullptr;
@@ -522,7 +550,7 @@ int kq_hashagg_update(kq_ctx* ctx, kq_hashagg* h, kq_batch* input) {
     int grid = (int)std::min<int64_t>(A.ntiles, (int64_t)ctx->sm_count);
     // rows that may still create groups after a block has decided to continue: one tile per resident
     // block plus its front end
-    const uint64_t margin = (uint64_t)grid * ((uint64_t)A.sp.nstages * TILE + FE_MAX_GROUPS);
+    const uint64_t margin = (uint64_t)grid * ((uint64_t)(A.sp.nstages + 1) * TILE + FE_MAX_GROUPS);     // + the ticket requested one step early
 
     int64_t tile_begin = 0;
     while (tile_begin < A.ntiles) {

@@ -267,29 +267,47 @@ extern "C" __global__ void __launch_bounds__(THREADS, 1) kq_hash_aggregate(const
 
     if (wid == PRODUCER_WARP) {
         if (lane == 0) {
-            // Utf8 string bytes are copied in a second phase, one step behind: the byte range of a tile is
-            // only known once its offsets have landed in the stage
-            auto phase2 = [&](int kk) {
-                const int sp = kk % S;
-                mbar_wait(&full[sp], (kk / S) & 1);
-                stage_issue_bytes(A.sp, smem + (size_t)sp * A.sp.stage_bytes, &full2[sp], tile_of[sp], TILE, A.n, bbase[sp]);
-            };
-            for (int k = 0;; k++) {
-                const int s = k % S;
-                mbar_wait(&empty[s], ((k / S) & 1) ^ 1);
+            // Two cursors over the CTA's tiles: kp = next tile whose fixed-size buffers (phase 1) are issued,
+            // kb = next tile whose Utf8 string bytes (phase 2) are issued — the byte range of a tile is only
+            // known once its offsets have landed in the stage. Neither waits for the other: the loop polls.
+            // The next ticket is always requested one step early so that the L2 round trip of the atomic
+            // overlaps the wait for a free stage.
+            int kp = 0, kb = 0;
+            bool done = false;
+            auto take = [&]() -> long long {
                 // stop taking tiles once the global table is half full: every ticket taken is processed,
                 // so the rows consumed so far are always a prefix of the batch (the host grows and resumes)
                 const unsigned long long g = *reinterpret_cast<volatile unsigned long long*>(A.ngroups);
-                long long tile = -1;
-                if (g <= A.stop_threshold) tile = (long long)atomicAdd(A.ticket, 1u) + A.tile_begin;
-                if (tile < 0 || tile >= A.ntiles) {
-                    if (KQ_STAGE_BYTES && k >= 1) phase2(k - 1);
-                    tile_of[s] = -1; mbar_arrive(&full[s]);
-                    break;
+                if (g > A.stop_threshold) return -1;
+                const long long t = (long long)atomicAdd(A.ticket, 1u) + A.tile_begin;
+                return t < A.ntiles ? t : -1;
+            };
+            long long next = take();
+            while (!done || kb < kp) {
+                bool did = false;
+                if (KQ_STAGE_BYTES && kb < kp) {
+                    const int sb = kb % S;
+                    if (mbar_test(&full[sb], (kb / S) & 1)) {
+                        stage_issue_bytes(A.sp, smem + (size_t)sb * A.sp.stage_bytes, &full2[sb], tile_of[sb], TILE, A.n, bbase[sb]);
+                        kb++; did = true;
+                    }
                 }
-                tile_of[s] = tile;
-                stage_issue(A.sp, smem + (size_t)s * A.sp.stage_bytes, &full[s], tile, TILE, A.n);
-                if (KQ_STAGE_BYTES && k >= 1) phase2(k - 1);
+                if (!done) {
+                    const int s = kp % S;
+                    if (mbar_test(&empty[s], ((kp / S) & 1) ^ 1)) {
+                        const long long tile = next;
+                        if (tile < 0) { tile_of[s] = -1; mbar_arrive(&full[s]); done = true; }
+                        else {
+                            tile_of[s] = tile;
+                            stage_issue(A.sp, smem + (size_t)s * A.sp.stage_bytes, &full[s], tile, TILE, A.n);
+                            next = take();
+                            kp++;
+                        }
+                        did = true;
+                    }
+                }
+                if (!KQ_STAGE_BYTES) kb = kp;
+                if (!did) __nanosleep(20);
             }
         }
     } else {
