@@ -525,7 +525,8 @@ static int plan_agg(kq_ctx* ctx, kq_hashagg* h, kq_batch* input, int smem_optin,
                             eval_body + "    }\n};\n}  // namespace kq\n";
     *defines_out = "#define KQ_R " + std::to_string(geo.r) + "\n#define KQ_WARPS " + std::to_string(geo.warps) + "\n#define KQ_STAGES " +
                                 std::to_string(A.sp.nstages) + "\n#define KQ_FE_GROUPS " + std::to_string(fg) + "\n#define KQ_DIR_SLOTS " +
-                                std::to_string(dir_slots) + "\n#define KQ_STAGE_BYTES " + (has_bytes ? "1" : "0") + "\n";
+                                std::to_string(dir_slots) + (getenv("KQ_L2_PREFETCH") ? "\n#define KQ_L2_PREFETCH " + std::to_string(atoi(getenv("KQ_L2_PREFETCH"))) : std::string()) +
+                                "\n#define KQ_STAGE_BYTES " + (has_bytes ? "1" : "0") + "\n";
     return KQ_OK;
 }
 

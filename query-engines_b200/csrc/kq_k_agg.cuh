@@ -25,6 +25,9 @@
 namespace kq {
 
 // Service warp first (the warp arbiter favours high warp ids: a polling producer must not starve consumers).
+#ifndef KQ_L2_PREFETCH
+#define KQ_L2_PREFETCH 0          // measured: no effect here (consumers, not HBM latency, bound this kernel)
+#endif
 constexpr int WARPS = KQ_WARPS;              // consumer warps (the lane-private front end scales with them)
 constexpr int PRODUCER_WARP = 0;
 constexpr int THREADS = WARPS * 32 + 32;
@@ -301,6 +304,7 @@ extern "C" __global__ void __launch_bounds__(THREADS, 1) kq_hash_aggregate(const
                             tile_of[s] = tile;
                             stage_issue(A.sp, smem + (size_t)s * A.sp.stage_bytes, &full[s], tile, TILE, A.n);
                             next = take();
+                            if (KQ_L2_PREFETCH > 0 && next >= 0) stage_prefetch_l2(A.sp, next, TILE, A.n);     // staged one step from now
                             kp++;
                         }
                         did = true;

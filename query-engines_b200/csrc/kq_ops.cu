@@ -201,6 +201,7 @@ int plan_ops(kq_ctx* ctx, KqCodegen& cg, kq_expr* pred, const std::vector<kq_exp
     P->defines = "#define KQ_R " + std::to_string(OPS_R) + "\n#define KQ_WARPS " + std::to_string(OPS_WARPS) + "\n#define KQ_STAGES " +
                  std::to_string(P->sp.nstages) + "\n";
     if (getenv("KQ_TRACE_FILE")) P->defines += "#define KQ_TRACE 1\n";
+    if (const char* e = getenv("KQ_L2_PREFETCH")) P->defines += "#define KQ_L2_PREFETCH " + std::to_string(atoi(e)) + "\n";     // tuning experiments
     if (pred) P->defines += "#define KQ_KERNEL_FILTER\n#define KQ_STASH_ROWS " + std::to_string(cap) + "\n#define KQ_META 32\n#define KQ_SELVEC " + (selvec ? "1" : "0") + "\n";
     else P->defines += "#define KQ_KERNEL_PROJECT\n";
     P->entry = pred ? "kq_filter_project" : "kq_project";

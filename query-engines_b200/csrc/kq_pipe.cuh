@@ -90,6 +90,27 @@ __device__ __forceinline__ void stage_issue(const StagePlan& sp, unsigned char* 
     }
 }
 
+// Ask the L2 to fetch the fixed-size buffers of a tile that will be staged a few iterations from now: the
+// later bulk copy then sees L2 latency instead of HBM latency, so the shared-memory ring has to cover far
+// fewer bytes in flight. Called by one thread.
+__device__ __forceinline__ void stage_prefetch_l2(const StagePlan& sp, int64_t tile, int tile_rows, int64_t n) {
+    const int64_t row0 = tile * tile_rows;
+    if (row0 >= n) return;
+    const int rows = (int)((n - row0) < tile_rows ? (n - row0) : tile_rows);
+#pragma unroll 1
+    for (int b = 0; b < sp.nbuf; b++) {
+        const StageBuf sb = sp.buf[b];
+        if (sb.kind == SK_BYTES) continue;
+        uint32_t bytes; int64_t goff;
+        if (sb.kind == SK_W8) { bytes = rows * 8; goff = row0 * 8; }
+        else if (sb.kind == SK_W4) { bytes = rows * 4; goff = row0 * 4; }
+        else if (sb.kind == SK_W4_PLUS1) { bytes = (rows + 1) * 4; goff = row0 * 4; }
+        else { bytes = (rows + 7) / 8; goff = row0 / 8; }
+        bytes = (bytes + 15u) & ~15u;
+        bulk_prefetch_l2(sb.g + goff, bytes);
+    }
+}
+
 // Second phase for Utf8 columns: once the tile's offsets have landed in the stage, copy the byte range
 // they span. bbase[column slot] receives the data-buffer offset the staged bytes start at (16-byte
 // aligned), or -1 when the range does not fit the stage (consumers then read those bytes from global
