@@ -75,7 +75,9 @@ __device__ __forceinline__ uint32_t dir_hash(const uint64_t (&kw)[MAX_KEYS], uin
     uint32_t h = nullmask * 0x9E3779B1u;
 #pragma unroll
     for (int k = 0; k < Q::NKEYS; k++) h = (h ^ (uint32_t)kw[k] ^ ((uint32_t)(kw[k] >> 32) * 0x85EBCA6Bu)) * 0x9E3779B1u;
-    return (h ^ (h >> 15)) & (DIR - 1);
+    // murmur3 finaliser: small integers and short strings must not share low bits
+    h ^= h >> 16; h *= 0x85EBCA6Bu; h ^= h >> 13; h *= 0xC2B2AE35u; h ^= h >> 16;
+    return h & (DIR - 1);
 }
 
 __device__ __forceinline__ int dir_lookup(const FrontEnd& fe, uint32_t slot, const uint64_t (&kw)[MAX_KEYS], uint32_t nullmask) {
@@ -357,12 +359,19 @@ extern "C" __global__ void __launch_bounds__(THREADS, 1) kq_hash_aggregate(const
                     uint64_t kw[MAX_KEYS];
 #pragma unroll
                     for (int k2 = 0; k2 < MAX_KEYS; k2++) kw[k2] = k2 < Q::NKEYS ? sink.key[k2][r] : 0;
-                    const uint32_t e = a_dir + dir_hash(kw, nm[r]) * (ENTRY_WORDS * 8u);
-                    const uint4 q = lds_u128(e);
-                    bool hit = q.x >= 2u && q.x != DIR_GLOBAL && q.y == nm[r];
-                    if constexpr (Q::NKEYS >= 1) hit &= ((uint64_t)q.z | ((uint64_t)q.w << 32)) == kw[0];
+                    // the key's home slot and its neighbour (linear probing rarely displaces a key further)
+                    const uint32_t s0 = dir_hash(kw, nm[r]);
+                    const uint32_t e0 = a_dir + s0 * (ENTRY_WORDS * 8u), e1 = a_dir + ((s0 + 1) & (DIR - 1)) * (ENTRY_WORDS * 8u);
+                    const uint4 q0 = lds_u128(e0), q1 = lds_u128(e1);
+                    bool h0 = q0.x >= 2u && q0.x != DIR_GLOBAL && q0.y == nm[r], h1 = q1.x >= 2u && q1.x != DIR_GLOBAL && q1.y == nm[r];
+                    if constexpr (Q::NKEYS >= 1) {
+                        h0 &= ((uint64_t)q0.z | ((uint64_t)q0.w << 32)) == kw[0];
+                        h1 &= ((uint64_t)q1.z | ((uint64_t)q1.w << 32)) == kw[0];
+                    }
 #pragma unroll
-                    for (int k2 = 1; k2 < Q::NKEYS; k2++) hit &= lds_u64(e + 8u + 8u * k2) == kw[k2];
+                    for (int k2 = 1; k2 < Q::NKEYS; k2++) { h0 &= lds_u64(e0 + 8u + 8u * k2) == kw[k2]; h1 &= lds_u64(e1 + 8u + 8u * k2) == kw[k2]; }
+                    const bool hit = h0 | h1;
+                    const uint4 q = h0 ? q0 : q1;
                     const bool on = (sink.sel >> r) & 1u;
                     gid[r] = (on && hit) ? (int)(q.x - 2u) : FG;
                     slow |= (uint32_t)(on && !hit) << r;
