@@ -146,7 +146,7 @@ int plan_ops(kq_ctx* ctx, KqCodegen& cg, kq_expr* pred, const std::vector<kq_exp
         cg.line("return " + p.v + (p.nullable() ? " & " + p.ok : std::string()) + ";");     // TRUE only (rule E3)
         pred_body = cg.take_body();
     }
-    if ((int)ex.size() > MAX_OUT) return kq_fail(ctx, KQ_ERR_UNSUPPORTED, "more than %d computed outputs in one kernel", MAX_OUT);
+    if ((int)ex.size() > MAX_OUT) { P->fits = false; return KQ_OK; }       // the caller splits the projection into several launches
     bool any_nullable = false;
     std::string types, nulls;
     for (size_t k = 0; k < ex.size(); k++) {

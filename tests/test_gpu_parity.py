@@ -230,6 +230,22 @@ def test_upload_of_a_sliced_utf8_vector_rebases_offsets(gpu, gctx):
         same(gpu.Column(gctx, out).to_arrow(), pa.concat_arrays([whole.slice(lo, hi - lo)]))
 
 
+@pytest.mark.parametrize("threshold", [-1.0, 0.37, 2.0])         # keeps every row / some rows / no row
+def test_filter_selectivity_extremes_and_wide_projection(G, oracle, threshold):
+    """A projection wider than one launch's stash is split into several launches that repeat the predicate;
+    the outputs must still line up row by row."""
+    rng = np.random.default_rng(3)
+    n = 150_001
+    arrs = [pa.array(rng.random(n)), pa.array(rng.integers(-9, 9, n), mask=rng.random(n) < 0.1), pa.array(rng.random(n) < 0.5)]
+    pred = b("GT", col(0), lit("f64", threshold))
+    proj = [b("ADD", col(0), lit("f64", float(i))) for i in range(7)] + [b("MUL", col(1), lit("i64", i + 2)) for i in range(5)] + [col(2), b("LT", col(0), lit("f64", 0.5))]
+    want = oracle.filter_project(build(oracle, pred), [build(oracle, p) for p in proj], oracle.RecordBatch.from_arrow(arrs))
+    got = G.filter_project(build(G, pred), [build(G, p) for p in proj], G.RecordBatch.from_arrow(arrs))
+    assert got.row_count() == want.row_count() == (n if threshold < 0 else (0 if threshold > 1 else want.row_count()))
+    for a, w in zip(got.to_arrow(), want.to_arrow()):
+        same(a, w)
+
+
 def test_filter_gathers_every_column_in_order(G, oracle):
     rng = np.random.default_rng(11)
     arrs = rand_table(rng, 50001, 0.1)
