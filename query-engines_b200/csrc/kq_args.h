@@ -23,6 +23,7 @@ constexpr int MAX_KEYS = 4;         // group-by expressions
 constexpr int MAX_INPUTS = 6;       // distinct aggregate input expressions
 constexpr int MAX_STAGE_BUFS = 24;
 constexpr int MAX_STAGES = 8;
+constexpr int MAX_BYTES_BUFS = 4;  // Utf8 byte ranges staged per tile
 
 // One input column (an Arrow FieldVector triple resident in HBM).
 struct QCol {
@@ -57,7 +58,8 @@ struct StagePlan {
     int32_t nbuf;
     int32_t stage_bytes;            // multiple of 128
     int32_t nstages;
-    int32_t _pad;
+    int32_t nbytes;                 // SK_BYTES buffers (at most MAX_BYTES_BUFS are staged)
+    int32_t bytes_buf[4];           // their indices in buf[]
     StageBuf buf[MAX_STAGE_BUFS];
 };
 

@@ -384,6 +384,7 @@ std::string KqCodegen::plan_stages(int budget, int min_stages, int tile_rows, St
         int bytes = kind == SK_W8 ? TILE * 8 : (kind == SK_W4 ? TILE * 4 : (kind == SK_W4_PLUS1 ? TILE * 4 + 16 : (kind == SK_BYTES ? TILE * 4 + 64 : TILE / 8)));
         bytes = (bytes + 127) / 128 * 128;
         if (sp->nbuf >= MAX_STAGE_BUFS || (off + bytes) * min_stages > budget) return -1;   // stays on the direct global path
+        if (kind == SK_BIT && TILE % 128 != 0) return -1;                                   // a tile's bit range must start 16-byte aligned for the bulk copy
         StageBuf& sb = sp->buf[sp->nbuf];
         sb.g = (const char*)g; sb.soff = off; sb.kind = kind; sb.slot = cur_slot; sb.role = role;
         sp->nbuf++;
@@ -403,10 +404,10 @@ std::string KqCodegen::plan_stages(int budget, int min_stages, int tile_rows, St
             case KQ_UTF8:
                 so = add(SK_W4_PLUS1, c->offsets, 2);
                 // string bytes: a second-phase copy of the range the tile's offsets span (up to 4 bytes/row on average; longer tiles fall back to global loads)
-                if (stage_bytes && so >= 0 && col_bytes_used[i]) {
+                if (stage_bytes && so >= 0 && col_bytes_used[i] && sp->nbytes < MAX_BYTES_BUFS) {
                     const int obuf = sp->nbuf - 1;
                     sb = add(SK_BYTES, c->data, 0);
-                    if (sb >= 0) { sp->buf[sp->nbuf - 1].aux = obuf | (i << 16); sp->buf[sp->nbuf - 1].cap = TILE * 4 + 64; }
+                    if (sb >= 0) { sp->buf[sp->nbuf - 1].aux = obuf | (i << 16); sp->buf[sp->nbuf - 1].cap = TILE * 4 + 64; sp->bytes_buf[sp->nbytes++] = sp->nbuf - 1; }
                 }
                 break;
         }

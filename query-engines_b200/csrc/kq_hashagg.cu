@@ -520,6 +520,9 @@ static int plan_agg(kq_ctx* ctx, kq_hashagg* h, kq_batch* input, int smem_optin,
     consts += arr("int", "FE_MIN", NI, [&](int i) { return h->in[i].fe_min; });
     consts += arr("int", "FE_MAX", NI, [&](int i) { return h->in[i].fe_max; });
     consts += arr("int", "MM_WORD", nm, [&](int i) { return mm_word[(size_t)i]; });
+    // one input with both MIN and MAX in adjacent, 16-byte aligned record words: the global path reads them with one load
+    const bool mm_paired = NI == 1 && nm == 2 && mm_word[1] == mm_word[0] + 1 && mm_word[0] % 2 == 0 && h->in[0].fe_min == 0;
+    consts += std::string("    static constexpr bool MM_PAIRED = ") + (mm_paired ? "true" : "false") + ";\n";
     *gen_out = "namespace kq {\n" + stage_defs + "struct Q {\n" + consts +
                             "    template <class Sink> static __device__ __forceinline__ void eval(const QArgs& q, RowCtx& rc, Sink& sink) {\n" +
                             eval_body + "    }\n};\n}  // namespace kq\n";

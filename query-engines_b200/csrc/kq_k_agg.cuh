@@ -169,34 +169,73 @@ __device__ __forceinline__ void smem_max_u64(uint32_t a, uint64_t m) {
                  ::"r"(a), "l"(m) : "memory");
 }
 
-// Branch-free front-end accumulate of input I for one row. g = the row's group, or FG (a trash group
-// nobody reads) when the row is filtered out / takes the slow path; an invalid (null) input goes to the
-// trash group as well, so every read-modify-write is unconditional.
-template <int I>
-__device__ __forceinline__ void fe_accumulate_fast(uint32_t a_cnt, uint32_t a_sum, uint32_t a_mm, int g, int lane, const AggSink& sink, int r) {
-    if constexpr (I < Q::NIN) {
-        constexpr int FL = Q::IN_FLAGS[I];
-        const bool valid = (sink.inok[I] >> r) & 1u;
-        const int gi = (Q::IN_CNT[I] > 0 && !valid) ? FG : g;           // statically non-null inputs: always valid
-        if constexpr (Q::IN_CNT[I] > 0) {
-            const uint32_t a = a_cnt + ((((uint32_t)gi * Q::NCNT + Q::IN_CNT[I]) << 5) + lane) * 4u;
-            sts_u32(a, lds_u32(a) + 1u);
+// Branch-free front-end accumulate of the adjacent row pair (r0, r0 + 1), groups g0 / g1 (FG = trash).
+// Every lane-private load of BOTH rows is issued before the first dependent add, so a pair exposes one
+// shared-memory latency instead of one per slot. When both rows fall in the same group the second row's add
+// chains on the first row's result rather than on the (stale) value it loaded, and its store lands last.
+// MIN/MAX: the CTA-shared extremes are pre-checked on the HIGH WORD of the order-mapped value only (two
+// instructions to map, one 32-bit load per slot); the exact 64-bit compare + reduction runs in a rarely
+// taken branch (value's high word ties or beats the current extreme, or the value is a NaN).
+__device__ __forceinline__ void fe_accumulate_pair(uint32_t a_cnt, uint32_t a_sum, uint32_t a_mm, int g0, int g1, int lane, const AggSink& sink, int r0) {
+    constexpr int NI = Q::NIN > 0 ? Q::NIN : 1;
+    const int r1 = r0 + 1;
+    const uint32_t l4 = (uint32_t)lane * 4u, l8 = (uint32_t)lane * 8u;
+    uint32_t c0a[2] = {0, 0}, c0v[2] = {0, 0};
+    if constexpr (Q::CNT0_USED) {
+        c0a[0] = a_cnt + (uint32_t)g0 * (Q::NCNT * 128u) + l4; c0a[1] = a_cnt + (uint32_t)g1 * (Q::NCNT * 128u) + l4;
+        c0v[0] = lds_u32(c0a[0]); c0v[1] = lds_u32(c0a[1]);
+    }
+    uint32_t gi[NI][2], ca[NI][2], cv[NI][2], sa[NI][2], mna[NI][2], mxa[NI][2], mnh[NI][2], mxh[NI][2];
+    uint64_t sv[NI][2];
+#pragma unroll
+    for (int i = 0; i < Q::NIN; i++) {
+        const int FL = Q::IN_FLAGS[i];
+#pragma unroll
+        for (int k = 0; k < 2; k++) {
+            const bool valid = (sink.inok[i] >> (r0 + k)) & 1u;
+            gi[i][k] = (Q::IN_CNT[i] > 0 && !valid) ? (uint32_t)FG : (uint32_t)(k ? g1 : g0);      // statically non-null inputs: always valid
+            if (Q::IN_CNT[i] > 0) { ca[i][k] = a_cnt + (gi[i][k] * Q::NCNT + Q::IN_CNT[i]) * 128u + l4; cv[i][k] = lds_u32(ca[i][k]); }
+            if (FL & F_SUM) { sa[i][k] = a_sum + (gi[i][k] * Q::NSUM + Q::FE_SUM[i]) * 256u + l8; sv[i][k] = lds_u64(sa[i][k]); }
+            if (FL & F_MIN) { mna[i][k] = a_mm + (gi[i][k] * Q::NMM + Q::FE_MIN[i]) * 8u; mnh[i][k] = lds_u32(mna[i][k] + 4u); }
+            if (FL & F_MAX) { mxa[i][k] = a_mm + (gi[i][k] * Q::NMM + Q::FE_MAX[i]) * 8u; mxh[i][k] = lds_u32(mxa[i][k] + 4u); }
         }
-        if constexpr ((FL & (F_SUM | F_MIN | F_MAX)) != 0) {
-            const uint64_t v = sink.in[I][r];
-            if constexpr ((FL & F_SUM) != 0) {
-                const uint32_t a = a_sum + ((((uint32_t)gi * Q::NSUM + Q::FE_SUM[I]) << 5) + lane) * 8u;
-                if constexpr ((FL & F_INT) != 0) sts_u64(a, lds_u64(a) + v);
-                else sts_u64(a, as_u64(__dadd_rn(as_f64(lds_u64(a)), as_f64(v))));
-            }
-            if constexpr ((FL & (F_MIN | F_MAX)) != 0) {
-                constexpr bool is_int = (FL & F_INT) != 0;
-                const uint64_t m = order_map(is_int ? v : canon_nan(v), is_int);
-                if constexpr ((FL & F_MIN) != 0) smem_min_u64(a_mm + ((uint32_t)gi * Q::NMM + Q::FE_MIN[I]) * 8u, m);
-                if constexpr ((FL & F_MAX) != 0) smem_max_u64(a_mm + ((uint32_t)gi * Q::NMM + Q::FE_MAX[I]) * 8u, m);
+    }
+    if constexpr (Q::CNT0_USED) {
+        const uint32_t y0 = c0v[0] + 1u, y1 = (g0 == g1 ? y0 : c0v[1]) + 1u;
+        sts_u32(c0a[0], y0); sts_u32(c0a[1], y1);
+    }
+#pragma unroll
+    for (int i = 0; i < Q::NIN; i++) {
+        const int FL = Q::IN_FLAGS[i];
+        const bool same = gi[i][0] == gi[i][1];
+        if (Q::IN_CNT[i] > 0) {
+            const uint32_t y0 = cv[i][0] + 1u, y1 = (same ? y0 : cv[i][1]) + 1u;
+            sts_u32(ca[i][0], y0); sts_u32(ca[i][1], y1);
+        }
+        if (FL & F_SUM) {
+            const uint64_t x0 = sink.in[i][r0], x1 = sink.in[i][r1];
+            uint64_t y0, y1;
+            if (FL & F_INT) { y0 = sv[i][0] + x0; y1 = (same ? y0 : sv[i][1]) + x1; }
+            else { y0 = as_u64(__dadd_rn(as_f64(sv[i][0]), as_f64(x0))); y1 = as_u64(__dadd_rn(as_f64(same ? y0 : sv[i][1]), as_f64(x1))); }
+            sts_u64(sa[i][0], y0); sts_u64(sa[i][1], y1);
+        }
+        if (FL & (F_MIN | F_MAX)) {
+            const bool is_int = (FL & F_INT) != 0;
+#pragma unroll
+            for (int k = 0; k < 2; k++) {
+                const uint64_t v = sink.in[i][r0 + k];
+                const uint32_t hi = (uint32_t)(v >> 32);
+                const uint32_t mh = is_int ? hi ^ 0x80000000u : hi ^ ((uint32_t)((int32_t)hi >> 31) | 0x80000000u);     // high word of order_map(v)
+                bool exact = !is_int && as_f64(v) != as_f64(v);                                                            // NaNs are canonicalised below
+                if (FL & F_MIN) exact |= mh <= mnh[i][k];
+                if (FL & F_MAX) exact |= mh >= mxh[i][k];
+                if (exact) {
+                    const uint64_t m = order_map(is_int ? v : canon_nan(v), is_int);
+                    if (FL & F_MIN) smem_min_u64(mna[i][k], m);
+                    if (FL & F_MAX) smem_max_u64(mxa[i][k], m);
+                }
             }
         }
-        fe_accumulate_fast<I + 1>(a_cnt, a_sum, a_mm, g, lane, sink, r);
     }
 }
 
@@ -235,10 +274,102 @@ __device__ __forceinline__ void fe_merge_input(const FrontEnd& fe, uint64_t* rec
     }
 }
 
+// ---- high-cardinality path: every row goes to the global table ------------------------------------------------------
+// A thread's R rows are looked up TOGETHER: each probing round first issues the header+key loads of all
+// rows that are still unresolved (R independent L2/HBM round trips in flight per thread instead of one),
+// then examines them; accumulation is a second batch of fire-and-forget reductions. Latency-bound random
+// access is what limits this path, so memory-level parallelism per thread is what buys throughput.
+template <int I>
+__device__ __forceinline__ void global_accumulate_batched(uint64_t* const (&rec)[R], const ulonglong2 (&mmv)[R], const AggSink& sink, uint32_t rows) {
+    if constexpr (I < Q::NIN) {
+        constexpr int FL = Q::IN_FLAGS[I];
+#pragma unroll
+        for (int r = 0; r < R; r++) {
+            if (!((rows >> r) & 1u) || !((sink.inok[I] >> r) & 1u)) continue;
+            uint64_t* p = rec[r];
+            atomicAdd(reinterpret_cast<unsigned long long*>(p + Q::REC_NN[I]), 1ULL);
+            if constexpr ((FL & (F_SUM | F_MIN | F_MAX)) != 0) {
+                const uint64_t v = sink.in[I][r];
+                if constexpr ((FL & F_SUM) != 0) {
+                    if constexpr ((FL & F_INT) != 0) atomicAdd(reinterpret_cast<unsigned long long*>(p + Q::REC_SUM[I]), (unsigned long long)v);
+                    else atomicAdd(reinterpret_cast<double*>(p + Q::REC_SUM[I]), as_f64(v));
+                }
+                if constexpr ((FL & (F_MIN | F_MAX)) != 0) {
+                    constexpr bool is_int = (FL & F_INT) != 0;
+                    const uint64_t m = order_map(is_int ? v : canon_nan(v), is_int);
+                    // pre-check against a (possibly stale) copy: MIN only falls and MAX only rises, so a stale value errs on the safe side
+                    if constexpr ((FL & F_MIN) != 0) {
+                        const uint64_t cur = (Q::NIN == 1 && Q::MM_PAIRED) ? mmv[r].x : __ldcg(p + Q::MM_WORD[Q::FE_MIN[I]]);
+                        if (m < cur) atomicMin(reinterpret_cast<unsigned long long*>(p + Q::MM_WORD[Q::FE_MIN[I]]), (unsigned long long)m);
+                    }
+                    if constexpr ((FL & F_MAX) != 0) {
+                        const uint64_t cur = (Q::NIN == 1 && Q::MM_PAIRED) ? mmv[r].y : __ldcg(p + Q::MM_WORD[Q::FE_MAX[I]]);
+                        if (m > cur) atomicMax(reinterpret_cast<unsigned long long*>(p + Q::MM_WORD[Q::FE_MAX[I]]), (unsigned long long)m);
+                    }
+                }
+            }
+        }
+        global_accumulate_batched<I + 1>(rec, mmv, sink, rows);
+    }
+}
+
+__device__ __forceinline__ void global_path_batched(const AggArgs& A, const AggSink& sink, const uint32_t (&nm)[R], uint32_t rows) {
+    uint64_t* rec[R];                 // record under examination, then the row's record
+    uint64_t* const tab_end = A.table + (A.cap_mask + 1) * (uint64_t)A.stride;
+#pragma unroll
+    for (int r = 0; r < R; r++) {
+        uint64_t kw[MAX_KEYS];
+#pragma unroll
+        for (int k2 = 0; k2 < MAX_KEYS; k2++) kw[k2] = k2 < Q::NKEYS ? sink.key[k2][r] : 0;
+        rec[r] = A.table + (hash_key(kw, nm[r], Q::NKEYS) & A.cap_mask) * (uint64_t)A.stride;
+    }
+    constexpr bool PAIRED = Q::NIN == 1 && Q::MM_PAIRED;
+    ulonglong2 mmv[R];
+    uint32_t pending = rows;
+    while (pending) {
+        ulonglong2 hk[R];
+#pragma unroll
+        for (int r = 0; r < R; r++)
+            if ((pending >> r) & 1u) {
+                hk[r] = __ldcg(reinterpret_cast<const ulonglong2*>(rec[r]));                                   // {header, key 0}
+                if constexpr (PAIRED) mmv[r] = __ldcg(reinterpret_cast<const ulonglong2*>(rec[r] + Q::MM_WORD[0]));   // {min, max}: same round trip
+            }
+#pragma unroll
+        for (int r = 0; r < R; r++) {
+            if (!((pending >> r) & 1u)) continue;
+            uint64_t* p = rec[r];
+            const uint64_t hdr = hk[r].x, full_hdr = HDR_FULL | ((uint64_t)nm[r] << 32);
+            const uint32_t st = (uint32_t)hdr;
+            if (st == HDR_EMPTY) {
+                const unsigned long long old = atomicCAS(reinterpret_cast<unsigned long long*>(p), 0ULL, HDR_BUSY | ((uint64_t)nm[r] << 32));
+                if (old == 0ULL) {
+                    for (int w = 1 + Q::NKEYS; w < A.stride; w++) p[w] = A.rec_init[w];
+#pragma unroll
+                    for (int k2 = 0; k2 < Q::NKEYS; k2++) p[1 + k2] = sink.key[k2][r];
+                    __threadfence();
+                    *reinterpret_cast<volatile uint64_t*>(p) = full_hdr;
+                    atomicAdd(A.ngroups, 1ULL);
+                    if constexpr (PAIRED) mmv[r] = make_ulonglong2(~0ULL, 0ULL);      // identities of a fresh record
+                    pending &= ~(1u << r);
+                }
+                // lost the race: look at the same slot again next round
+            } else if (st != HDR_BUSY) {        // BUSY: being published, look again next round
+                bool eq = hdr == full_hdr;
+                if constexpr (Q::NKEYS >= 1) eq &= hk[r].y == sink.key[0][r];
+#pragma unroll
+                for (int k2 = 1; k2 < Q::NKEYS; k2++) eq &= __ldcg(p + 1 + k2) == sink.key[k2][r];
+                if (eq) pending &= ~(1u << r);
+                else { p += A.stride; rec[r] = p == tab_end ? A.table : p; }
+            }
+        }
+    }
+    global_accumulate_batched<0>(rec, mmv, sink, rows);
+}
+
 extern "C" __global__ void __launch_bounds__(THREADS, 1) kq_hash_aggregate(const __grid_constant__ AggArgs A) {
     // shared memory: [S stages][directory][gslot][gid2slot][mm][per-warp sums][per-warp counts]
     extern __shared__ __align__(128) unsigned char smem[];
-    __shared__ uint64_t full[S], empty[S], full2[S];     // full2: second-phase copies (Utf8 string bytes)
+    __shared__ uint64_t full[S], empty[S];
     __shared__ long long tile_of[S];
     __shared__ long long bbase[S][MAX_COLS];
     __shared__ uint32_t s_dir_count;
@@ -263,7 +394,7 @@ extern "C" __global__ void __launch_bounds__(THREADS, 1) kq_hash_aggregate(const
     for (size_t i = fe_begin + threadIdx.x * 4; i < fe_end; i += THREADS * 4) *reinterpret_cast<uint32_t*>(smem + i) = 0;
     if (threadIdx.x == 0) {
         s_dir_count = 0;
-        for (int s = 0; s < S; s++) { mbar_init(&full[s], 1); mbar_init(&empty[s], WARPS); mbar_init(&full2[s], 1); }
+        for (int s = 0; s < S; s++) { mbar_init(&full[s], 1); mbar_init(&empty[s], WARPS); }
         mbar_fence_init();
     }
     __syncthreads();
@@ -272,48 +403,30 @@ extern "C" __global__ void __launch_bounds__(THREADS, 1) kq_hash_aggregate(const
 
     if (wid == PRODUCER_WARP) {
         if (lane == 0) {
-            // Two cursors over the CTA's tiles: kp = next tile whose fixed-size buffers (phase 1) are issued,
-            // kb = next tile whose Utf8 string bytes (phase 2) are issued — the byte range of a tile is only
-            // known once its offsets have landed in the stage. Neither waits for the other: the loop polls.
-            // The next ticket is always requested one step early so that the L2 round trip of the atomic
-            // overlaps the wait for a free stage.
-            int kp = 0, kb = 0;
-            bool done = false;
+            // The next ticket is always requested one step early: the L2 round trip of the atomic and the HBM
+            // reads of the tile's Utf8 boundary offsets (stage_bounds_fetch) overlap the wait for a free stage,
+            // so string bytes and fixed-size buffers of a tile are issued together on one barrier.
+            TileBounds tb = {};
             auto take = [&]() -> long long {
                 // stop taking tiles once the global table is half full: every ticket taken is processed,
                 // so the rows consumed so far are always a prefix of the batch (the host grows and resumes)
                 const unsigned long long g = *reinterpret_cast<volatile unsigned long long*>(A.ngroups);
                 if (g > A.stop_threshold) return -1;
                 const long long t = (long long)atomicAdd(A.ticket, 1u) + A.tile_begin;
-                return t < A.ntiles ? t : -1;
+                if (t >= A.ntiles) return -1;
+                if (KQ_STAGE_BYTES) stage_bounds_fetch(A.sp, t, TILE, A.n, tb);
+                return t;
             };
             long long next = take();
-            while (!done || kb < kp) {
-                bool did = false;
-                if (KQ_STAGE_BYTES && kb < kp) {
-                    const int sb = kb % S;
-                    if (mbar_test(&full[sb], (kb / S) & 1)) {
-                        stage_issue_bytes(A.sp, smem + (size_t)sb * A.sp.stage_bytes, &full2[sb], tile_of[sb], TILE, A.n, bbase[sb]);
-                        kb++; did = true;
-                    }
-                }
-                if (!done) {
-                    const int s = kp % S;
-                    if (mbar_test(&empty[s], ((kp / S) & 1) ^ 1)) {
-                        const long long tile = next;
-                        if (tile < 0) { tile_of[s] = -1; mbar_arrive(&full[s]); done = true; }
-                        else {
-                            tile_of[s] = tile;
-                            stage_issue(A.sp, smem + (size_t)s * A.sp.stage_bytes, &full[s], tile, TILE, A.n);
-                            next = take();
-                            if (KQ_L2_PREFETCH > 0 && next >= 0) stage_prefetch_l2(A.sp, next, TILE, A.n);     // staged one step from now
-                            kp++;
-                        }
-                        did = true;
-                    }
-                }
-                if (!KQ_STAGE_BYTES) kb = kp;
-                if (!did) __nanosleep(20);
+            for (int kp = 0;; kp++) {
+                const int s = kp % S;
+                mbar_wait(&empty[s], ((kp / S) & 1) ^ 1);
+                const long long tile = next;
+                tile_of[s] = tile;
+                if (tile < 0) { mbar_arrive(&full[s]); break; }
+                stage_issue_all(A.sp, smem + (size_t)s * A.sp.stage_bytes, &full[s], tile, TILE, A.n, tb, bbase[s]);
+                next = take();
+                if (KQ_L2_PREFETCH > 0 && next >= 0) stage_prefetch_l2(A.sp, next, TILE, A.n);     // staged one step from now
             }
         }
     } else {
@@ -325,7 +438,6 @@ extern "C" __global__ void __launch_bounds__(THREADS, 1) kq_hash_aggregate(const
             mbar_wait(&full[s], (k / S) & 1);
             const long long tile = tile_of[s];
             if (tile < 0) break;
-            if (KQ_STAGE_BYTES) mbar_wait(&full2[s], (k / S) & 1);
             RowCtx rc;
             rowctx_init(rc, warp, tile, TILE, A.n, A.err, smem + (size_t)s * A.sp.stage_bytes);
             rc.bbase = bbase[s];
@@ -376,17 +488,16 @@ extern "C" __global__ void __launch_bounds__(THREADS, 1) kq_hash_aggregate(const
                     gid[r] = (on && hit) ? (int)(q.x - 2u) : FG;
                     slow |= (uint32_t)(on && !hit) << r;
                 }
-                // pass 2 (branch-free): unconditional read-modify-write of the lane-private slots
+                // pass 2 (branch-free): unconditional read-modify-write of the lane-private slots, a row pair at a time
 #pragma unroll
-                for (int r = 0; r < R; r++) {
-                    if constexpr (Q::CNT0_USED) { const uint32_t a = a_cnt + ((((uint32_t)gid[r] * NCNT) << 5) + lane) * 4u; sts_u32(a, lds_u32(a) + 1u); }
-                    fe_accumulate_fast<0>(a_cnt, a_sum, a_mm, gid[r], lane, sink, r);
-                }
+                for (int j = 0; j < NCHUNK; j++) fe_accumulate_pair(a_cnt, a_sum, a_mm, gid[2 * j], gid[2 * j + 1], lane, sink, 2 * j);
                 fe_hits = __popc(sink.sel & ~slow);
             }
             // general path for the rest: directory probing with insertion, else the global table
             int rows = __popc(sink.sel);
-            if (slow) {
+            if (bypass) {
+                if (slow) global_path_batched(A, sink, nm, slow);
+            } else if (slow) {
 #pragma unroll
                 for (int r = 0; r < R; r++) {
                     if (!((slow >> r) & 1u)) continue;

@@ -111,6 +111,70 @@ __device__ __forceinline__ void stage_prefetch_l2(const StagePlan& sp, int64_t t
     }
 }
 
+// Boundary offsets of a tile's staged Utf8 columns, read straight from HBM by the producer lane as soon as it
+// holds the tile's ticket (one step before the tile gets a stage): with them in registers, the string bytes are
+// issued together with the fixed-size buffers (stage_issue_all) instead of a dependent second round trip.
+struct TileBounds { int32_t lo[MAX_BYTES_BUFS], hi[MAX_BYTES_BUFS]; };
+__device__ __forceinline__ void stage_bounds_fetch(const StagePlan& sp, int64_t tile, int tile_rows, int64_t n, TileBounds& tb) {
+    const int64_t row0 = tile * tile_rows;
+    const int rows = (int)((n - row0) < tile_rows ? (n - row0) : tile_rows);
+#pragma unroll
+    for (int i = 0; i < MAX_BYTES_BUFS; i++) {
+        tb.lo[i] = tb.hi[i] = 0;
+        if (i < sp.nbytes) {
+            const int32_t* off = reinterpret_cast<const int32_t*>(sp.buf[sp.buf[sp.bytes_buf[i]].aux & 0xffff].g) + row0;
+            asm volatile("ld.global.nc.L1::no_allocate.s32 %0, [%1];" : "=r"(tb.lo[i]) : "l"(off));
+            asm volatile("ld.global.nc.L1::no_allocate.s32 %0, [%1];" : "=r"(tb.hi[i]) : "l"(off + rows));
+        }
+    }
+}
+
+// Issue every bulk copy of a tile — fixed-size buffers and the Utf8 byte ranges given by `tb` — on ONE barrier.
+// bbase[column slot] receives the data-buffer offset the staged bytes start at (16-byte aligned), or -1 when the
+// range does not fit the stage (consumers then read those bytes from global memory). Called by one thread.
+__device__ __forceinline__ void stage_issue_all(const StagePlan& sp, unsigned char* stage, uint64_t* full, int64_t tile,
+                                                int tile_rows, int64_t n, const TileBounds& tb, long long* bbase) {
+    const int64_t row0 = tile * tile_rows;
+    const int rows = (int)((n - row0) < tile_rows ? (n - row0) : tile_rows);
+    uint32_t total = 0;
+#pragma unroll 1
+    for (int b = 0; b < sp.nbuf; b++) {
+        const int kind = sp.buf[b].kind;
+        if (kind == SK_BYTES) continue;
+        uint32_t bytes = kind == SK_W8 ? rows * 8 : (kind == SK_W4 ? rows * 4 : (kind == SK_W4_PLUS1 ? (rows + 1) * 4 : (rows + 7) / 8));
+        total += (bytes + 15u) & ~15u;
+    }
+    long long start[MAX_BYTES_BUFS]; uint32_t len[MAX_BYTES_BUFS];
+#pragma unroll
+    for (int i = 0; i < MAX_BYTES_BUFS; i++) {
+        start[i] = -1; len[i] = 0;
+        if (i < sp.nbytes) {
+            const StageBuf& sb = sp.buf[sp.bytes_buf[i]];
+            const long long lo = (long long)tb.lo[i] & ~15LL, hi = ((long long)tb.hi[i] + 15LL) & ~15LL;
+            const bool fits = hi - lo + 16 <= (long long)sb.cap;
+            if (fits) { start[i] = lo; len[i] = (uint32_t)(hi - lo + 16); }     // +16: consumers read whole 8-byte words past the end (buffers are padded)
+            bbase[sb.aux >> 16] = start[i];
+            total += len[i];
+        }
+    }
+    mbar_arrive_expect_tx(full, total);
+#pragma unroll 1
+    for (int b = 0; b < sp.nbuf; b++) {
+        const StageBuf sb = sp.buf[b];
+        if (sb.kind == SK_BYTES) continue;
+        uint32_t bytes; int64_t goff;
+        if (sb.kind == SK_W8) { bytes = rows * 8; goff = row0 * 8; }
+        else if (sb.kind == SK_W4) { bytes = rows * 4; goff = row0 * 4; }
+        else if (sb.kind == SK_W4_PLUS1) { bytes = (rows + 1) * 4; goff = row0 * 4; }
+        else { bytes = (rows + 7) / 8; goff = row0 / 8; }
+        bytes = (bytes + 15u) & ~15u;
+        bulk_g2s(stage + sb.soff, sb.g + goff, bytes, full);
+    }
+#pragma unroll
+    for (int i = 0; i < MAX_BYTES_BUFS; i++)
+        if (i < sp.nbytes && len[i]) { const StageBuf& sb = sp.buf[sp.bytes_buf[i]]; bulk_g2s(stage + sb.soff, sb.g + start[i], len[i], full); }
+}
+
 // Second phase for Utf8 columns: once the tile's offsets have landed in the stage, copy the byte range
 // they span. bbase[column slot] receives the data-buffer offset the staged bytes start at (16-byte
 // aligned), or -1 when the range does not fit the stage (consumers then read those bytes from global
