@@ -44,7 +44,10 @@ __device__ __forceinline__ uint64_t hash_key(const uint64_t (&kw)[MAX_KEYS], uin
 // Find the record of (kw, nullmask) in the global table, inserting it if absent. Claim protocol:
 // CAS header EMPTY -> BUSY|nullmask, write keys + accumulator identities, fence, publish FULL.
 // The table never fills up: the host sizes it so that ngroups stays below capacity/2 plus margin.
-__device__ __forceinline__ uint64_t* table_find_or_insert(const AggArgs& A, uint64_t h, const uint64_t (&kw)[MAX_KEYS], uint32_t nullmask) {
+// `inserted` (optional): count new groups there instead of in A.ngroups — one counter for every insert of the whole
+// grid serialises in the L2 (10 M inserts cost milliseconds); callers add their tally to A.ngroups in bulk.
+__device__ __forceinline__ uint64_t* table_find_or_insert(const AggArgs& A, uint64_t h, const uint64_t (&kw)[MAX_KEYS], uint32_t nullmask,
+                                                          uint32_t* inserted = nullptr) {
     uint64_t slot = h & A.cap_mask;
     const uint64_t full_hdr = HDR_FULL | ((uint64_t)nullmask << 32);
     while (true) {
@@ -59,7 +62,7 @@ __device__ __forceinline__ uint64_t* table_find_or_insert(const AggArgs& A, uint
                 for (int k = 0; k < MAX_KEYS; k++) if (k < A.nkeys) rec[1 + k] = kw[k];
                 __threadfence();
                 *reinterpret_cast<volatile uint64_t*>(rec) = full_hdr;
-                atomicAdd(A.ngroups, 1ULL);
+                if (inserted) ++*inserted; else atomicAdd(A.ngroups, 1ULL);
                 return rec;
             }
             hdr = old; state = (uint32_t)hdr;

@@ -126,6 +126,13 @@ struct AggArgs {
     uint32_t fe_sum_int;                   // bit s: slot s is an integer sum
     int32_t fe_mm_word[2 * MAX_INPUTS];    // front-end min/max slot -> record word
     uint32_t fe_mm_ismin;
+    // partitioned path (high cardinality): pass 1 scatters the evaluated rows into per-(partition, CTA) buckets of
+    // HBM scratch, pass 2 reduces one partition at a time in a shared-memory table and merges it into `table`
+    uint64_t* part_scratch;                // [nparts][part_ncta][part_cap] tuples
+    uint32_t* part_counts;                 // [nparts][part_ncta] tuples per bucket
+    int32_t nparts, part_ncta, part_cap, part_begin;
+    int32_t part_log2, _pad_part;          // nparts = 1 << part_log2
+    int32_t part_slots, part_tw;           // shared-memory table slots of pass 2 (power of two); 64-bit words per tuple
     // shared-memory layout (byte offsets): [stage ring][front end]
     int32_t off_fe, off_dirkeys, off_dirstate, off_gid2slot, off_gslot, off_mm, off_cnt, off_sum, smem_bytes;
     StagePlan sp;

@@ -2,6 +2,7 @@
 // the per-batch launch of the specialised aggregate kernel (kq_k_agg.cuh via kq_codegen.cu / kq_jit.cu),
 // finalisation into the single output batch (Main.kt:635-650) and the table maintenance kernels.
 #include <algorithm>
+#include <cmath>
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
@@ -168,41 +169,53 @@ struct FinArgs {
     unsigned long long* pos;
 };
 
+// Output positions are reserved once per warp and chunk of 1024 table slots (one counter bumped by every warp
+// for every 32 slots serialises in the L2 when the table has tens of millions of slots).
 __global__ void k_finalize(const __grid_constant__ FinArgs F) {
     const int lane = threadIdx.x & 31;
-    uint64_t total = (F.cap + 31) / 32 * 32;
-    for (uint64_t s = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; s < total; s += (uint64_t)gridDim.x * blockDim.x) {
-        const uint64_t* rec = F.table + s * F.stride;
-        bool full = s < F.cap && (uint32_t)rec[0] == HDR_FULL;
-        uint32_t b = __ballot_sync(0xffffffffu, full);
-        if (!b) continue;
-        unsigned long long base = 0;
-        if (lane == __ffs(b) - 1) base = atomicAdd(F.pos, (unsigned long long)__popc(b));
-        base = __shfl_sync(0xffffffffu, base, __ffs(b) - 1);
-        if (!full) continue;
-        const uint64_t row = base + __popc(b & ((1u << lane) - 1u));
-        const uint32_t nullmask = (uint32_t)(rec[0] >> 32);
-        for (int k = 0; k < F.nkeys; k++) {
-            const FinKey o = F.keys[k];
-            const uint64_t v = rec[1 + k];
-            const bool valid = !((nullmask >> k) & 1u);
-            if (o.validity && valid) atomicOr(o.validity + (row >> 5), 1u << (row & 31));
-            switch (o.type) {
-                case KQ_F64: case KQ_I64: case KQ_UTF8: reinterpret_cast<uint64_t*>(o.data)[row] = v; break;   // UTF8: packed, expanded later
-                case KQ_DATE32: case KQ_I32: reinterpret_cast<uint32_t*>(o.data)[row] = (uint32_t)v; break;
-                case KQ_BOOL: if (v & 1u) atomicOr(reinterpret_cast<uint32_t*>(o.data) + (row >> 5), 1u << (row & 31)); break;
-            }
+    constexpr int CH = 32;                      // slots per lane and chunk
+    const uint64_t warp0 = (blockIdx.x * (uint64_t)blockDim.x + threadIdx.x) >> 5, nwarps = ((uint64_t)gridDim.x * blockDim.x) >> 5;
+    for (uint64_t c0 = warp0 * (32 * CH); c0 < F.cap; c0 += nwarps * (32 * CH)) {
+        uint32_t mine = 0;
+#pragma unroll 8
+        for (int j = 0; j < CH; j++) {
+            const uint64_t s = c0 + (uint64_t)j * 32 + lane;
+            if (s < F.cap && (uint32_t)F.table[s * F.stride] == HDR_FULL) mine |= 1u << j;
         }
-        for (int a = 0; a < F.naggs; a++) {
-            const FinAgg o = F.aggs[a];
-            const uint64_t nn = rec[o.nn_word];
-            if (o.kind == KQ_AGG_COUNT) { reinterpret_cast<uint64_t*>(o.data)[row] = nn; continue; }   // Int64, never null (rule E7)
-            if (nn == 0) continue;                                                                    // all-null group => null (R9)
-            atomicOr(o.validity + (row >> 5), 1u << (row & 31));
-            uint64_t v = rec[o.word];
-            if (o.kind != KQ_AGG_SUM) v = order_unmap(v, o.is_int);
-            if (o.out_type == KQ_DATE32) reinterpret_cast<uint32_t*>(o.data)[row] = (uint32_t)v;
-            else reinterpret_cast<uint64_t*>(o.data)[row] = v;
+        uint32_t incl = __popc(mine);
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) { const uint32_t y = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= o) incl += y; }
+        const uint32_t total = __shfl_sync(0xffffffffu, incl, 31);
+        if (!total) continue;
+        unsigned long long base = 0;
+        if (lane == 0) base = atomicAdd(F.pos, (unsigned long long)total);
+        base = __shfl_sync(0xffffffffu, base, 0);
+        uint64_t row = base + incl - __popc(mine);
+        for (; mine; mine &= mine - 1, row++) {
+            const uint64_t* rec = F.table + (c0 + (uint64_t)(__ffs(mine) - 1) * 32 + lane) * F.stride;
+            const uint32_t nullmask = (uint32_t)(rec[0] >> 32);
+            for (int k = 0; k < F.nkeys; k++) {
+                const FinKey o = F.keys[k];
+                const uint64_t v = rec[1 + k];
+                const bool valid = !((nullmask >> k) & 1u);
+                if (o.validity && valid) atomicOr(o.validity + (row >> 5), 1u << (row & 31));
+                switch (o.type) {
+                    case KQ_F64: case KQ_I64: case KQ_UTF8: reinterpret_cast<uint64_t*>(o.data)[row] = v; break;   // UTF8: packed, expanded later
+                    case KQ_DATE32: case KQ_I32: reinterpret_cast<uint32_t*>(o.data)[row] = (uint32_t)v; break;
+                    case KQ_BOOL: if (v & 1u) atomicOr(reinterpret_cast<uint32_t*>(o.data) + (row >> 5), 1u << (row & 31)); break;
+                }
+            }
+            for (int a = 0; a < F.naggs; a++) {
+                const FinAgg o = F.aggs[a];
+                const uint64_t nn = rec[o.nn_word];
+                if (o.kind == KQ_AGG_COUNT) { reinterpret_cast<uint64_t*>(o.data)[row] = nn; continue; }   // Int64, never null (rule E7)
+                if (nn == 0) continue;                                                                    // all-null group => null (R9)
+                atomicOr(o.validity + (row >> 5), 1u << (row & 31));
+                uint64_t v = rec[o.word];
+                if (o.kind != KQ_AGG_SUM) v = order_unmap(v, o.is_int);
+                if (o.out_type == KQ_DATE32) reinterpret_cast<uint32_t*>(o.data)[row] = (uint32_t)v;
+                else reinterpret_cast<uint64_t*>(o.data)[row] = v;
+            }
         }
     }
 }
@@ -397,7 +410,11 @@ int kq_hashagg_free(kq_hashagg* h) {
 
 // Everything about an aggregate launch that depends on the query SHAPE only: generated source, stage
 // plan, front-end layout. Fills the shape-dependent fields of A. No CUDA calls (kq_explain_hashagg).
-static int plan_agg(kq_ctx* ctx, kq_hashagg* h, kq_batch* input, int smem_optin, AggArgs& A, std::string* defines_out, std::string* gen_out) {
+// mode 0: front end + global table. mode 1: pass 1 of the partitioned path (no front end; `nparts` cursors in shared
+// memory) — the same translation unit also holds pass 2 (kq_agg_partition_reduce), whose table geometry is returned in
+// A.part_slots / *reduce_smem.
+static int plan_agg(kq_ctx* ctx, kq_hashagg* h, kq_batch* input, int smem_optin, AggArgs& A, std::string* defines_out, std::string* gen_out,
+                    int mode = 0, int nparts = 0, int* reduce_smem = nullptr) {
     // generate: [predicate -> selection] keys..., inputs...
     KqCodegen cg;
     KQ_RET(cg.begin(ctx, input));
@@ -410,12 +427,14 @@ static int plan_agg(kq_ctx* ctx, kq_hashagg* h, kq_batch* input, int smem_optin,
     }
     std::vector<int> kt, it;
     uint32_t key_f64_mask = 0;
+    bool keys_nullable = false;         // statically non-null keys: no null-mask hashing / comparing in the front end
     for (size_t k = 0; k < h->groups.size(); k++) {
         KqVal v;
         KQ_RET(cg.key_value(h->groups[k], &v));
         const KqVal a = cg.as_array(v);
         cg.line("sink.template set_key<" + std::to_string(k) + ">(" + a.v + ", " + a.okx() + ");");
         if (v.type == KQ_F64) key_f64_mask |= 1u << k;
+        keys_nullable |= a.nullable();
         kt.push_back(v.type);
     }
     std::vector<int> in_cnt;            // front-end count slot per input: 0 = "every selected row" (input statically non-null)
@@ -485,7 +504,16 @@ static int plan_agg(kq_ctx* ctx, kq_hashagg* h, kq_batch* input, int smem_optin,
         return std::max(0, std::min(FE_MAX_GROUPS, budget / per_group - 1));
     };
     const char* forced = getenv("KQ_AGG_GEOM");
+    if (mode == 1) {
+        // pass 1 of the partitioned path: no lane-private state, so many warps (latency of the shared-memory cursor
+        // atomics and of the scattered stores is hidden by occupancy) and a deep stage ring
+        geo = forced ? agg_geometry(NI) : AggGeometry{4, 15};
+        stage_defs = cg.plan_stages(96 * 1024, 1, geo.tile(), &A.sp, true);
+        A.sp.nstages = std::max(1, std::min(A.sp.nstages, AGG_MAX_STAGES));
+        fg = 0; dir_slots = 4;
+    }
     for (const AggGeometry& g : CANDIDATES) {
+        if (mode == 1) break;
         const AggGeometry cand = forced ? agg_geometry(NI) : g;
         StagePlan sp; std::string defs; int dir;
         const int f = try_geometry(cand, &sp, &defs, &dir);
@@ -500,7 +528,18 @@ static int plan_agg(kq_ctx* ctx, kq_hashagg* h, kq_batch* input, int smem_optin,
     A.fe_groups = fg;
     A.geo_r = geo.r; A.geo_warps = geo.warps;
     A.smem_bytes = ring + dir_slots * entry_words * 8 + std::max(fg, 1) * 12 + (fg + 1) * nm * 8 + WARPS * (fg + 1) * 32 * (8 * ns + 4 * ncnt);
+    if (mode == 1) A.smem_bytes += 16 + nparts * 4;
     A.smem_bytes = (A.smem_bytes + 127) / 128 * 128;
+    {   // pass-2 table: as many power-of-two slots as fit in shared memory
+        const int slot_bytes = 8 * (NK + ns + nm) + 4 * (ncnt + 1);
+        int sl = 256;
+        while (sl < 8192 && sl * 2 * slot_bytes <= smem_optin - 2048) sl <<= 1;
+        A.part_slots = sl;
+        if (reduce_smem) *reduce_smem = sl * slot_bytes;
+        int tw = NK + ((keys_nullable || ncnt > 1) ? 1 : 0);
+        for (int i = 0; i < NI; i++) if (h->in[i].flags & (F_SUM | F_MIN | F_MAX)) tw++;
+        A.part_tw = std::max(1, tw);
+    }
 
     auto arr = [&](const char* type, const char* name, int nelem, auto get) {
         std::string s = std::string("    static constexpr ") + type + " " + name + "[" + std::to_string(std::max(nelem, 1)) + "] = {";
@@ -510,7 +549,7 @@ static int plan_agg(kq_ctx* ctx, kq_hashagg* h, kq_batch* input, int smem_optin,
     std::string consts;
     consts += "    static constexpr int NKEYS = " + std::to_string(NK) + ", NIN = " + std::to_string(NI) + ", NCNT = " + std::to_string(ncnt) +
               ", NSUM = " + std::to_string(ns) + ", NMM = " + std::to_string(nm) + ";\n";
-    consts += std::string("    static constexpr bool CNT0_USED = ") + (cnt0_used ? "true" : "false") + ";\n";
+    consts += std::string("    static constexpr bool CNT0_USED = ") + (cnt0_used ? "true" : "false") + ", KEYS_NULLABLE = " + (keys_nullable ? "true" : "false") + ";\n";
     consts += "    static constexpr uint32_t KEY_F64_MASK = " + std::to_string(key_f64_mask) + "u, MM_ISMIN = " + std::to_string(mm_ismin) + "u;\n";
     consts += arr("int", "IN_FLAGS", NI, [&](int i) { return h->in[i].flags; });
     consts += arr("int", "IN_CNT", NI, [&](int i) { return in_cnt[(size_t)i]; });
@@ -529,8 +568,113 @@ static int plan_agg(kq_ctx* ctx, kq_hashagg* h, kq_batch* input, int smem_optin,
     *defines_out = "#define KQ_R " + std::to_string(geo.r) + "\n#define KQ_WARPS " + std::to_string(geo.warps) + "\n#define KQ_STAGES " +
                                 std::to_string(A.sp.nstages) + "\n#define KQ_FE_GROUPS " + std::to_string(fg) + "\n#define KQ_DIR_SLOTS " +
                                 std::to_string(dir_slots) + (getenv("KQ_L2_PREFETCH") ? "\n#define KQ_L2_PREFETCH " + std::to_string(atoi(getenv("KQ_L2_PREFETCH"))) : std::string()) +
-                                "\n#define KQ_STAGE_BYTES " + (has_bytes ? "1" : "0") + "\n";
+                                "\n#define KQ_STAGE_BYTES " + (has_bytes ? "1" : "0") + "\n#define KQ_AGG_MODE " + std::to_string(mode) + "\n" +
+                                (getenv("KQ_GLOBAL_BATCHED") ? "#define KQ_GLOBAL_BATCHED " + std::to_string(atoi(getenv("KQ_GLOBAL_BATCHED"))) + "\n" : std::string());
     return KQ_OK;
+}
+
+// ---- the partitioned path (kq_k_agg.cuh, KQ_AGG_MODE 1) ------------------------------------------------------------------
+constexpr int64_t PART_MIN_GROUPS = 16384;          // below this the plain path's global table stays L2-resident
+constexpr int64_t PART_MIN_ROWS = 1 << 20;          // small batches do not amortise the bucket scratch
+constexpr int64_t PART_CHUNK_ROWS = 1LL << 28;      // rows per pass-1 launch (bounds the scratch: ~1.3 tuples per row)
+
+// largest bucket fill of a pass-1 launch (bounds the groups one pass-2 block can add)
+__global__ void k_max_u32(const uint32_t* __restrict__ v, uint64_t n, unsigned long long* out) {
+    uint32_t m = 0;
+    for (uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; i < n; i += (uint64_t)gridDim.x * blockDim.x) m = max(m, v[i]);
+#pragma unroll
+    for (int o = 16; o; o >>= 1) m = max(m, __shfl_xor_sync(0xffffffffu, m, o));
+    if ((threadIdx.x & 31) == 0) atomicMax(out, (unsigned long long)m);
+}
+
+static int hashagg_update_partitioned(kq_ctx* ctx, kq_hashagg* h, kq_batch* input, int64_t n, int64_t g_est) {
+    AggArgs A;
+    memset(&A, 0, sizeof A);
+    std::string defines, gen;
+    // shape first (table slots of pass 2 decide the partition count), then the real plan
+    int reduce_smem = 0;
+    KQ_RET(plan_agg(ctx, h, input, ctx->max_smem_optin, A, &defines, &gen, 1, 512, &reduce_smem));
+    int nparts = 512;
+    while (nparts < 4096 && (int64_t)nparts * A.part_slots * 6 / 10 < g_est) nparts <<= 1;
+    if (const char* e = getenv("KQ_PARTS")) { int v = atoi(e); if (v >= 16 && v <= 8192 && (v & (v - 1)) == 0) nparts = v; }
+    memset(&A, 0, sizeof A);
+    KQ_RET(plan_agg(ctx, h, input, ctx->max_smem_optin, A, &defines, &gen, 1, nparts, &reduce_smem));
+    const AggGeometry geo{A.geo_r, A.geo_warps};
+    const int TILE = geo.tile(), THREADS = geo.threads();
+    const int64_t ntiles = (n + TILE - 1) / TILE;
+    void *k_scatter = nullptr, *k_reduce = nullptr;
+    KQ_RET(kq_jit_kernel(ctx, defines, gen, KQ_SKEL_AGG, "kq_hash_aggregate", A.smem_bytes, &k_scatter));
+    KQ_RET(kq_jit_kernel(ctx, defines, gen, KQ_SKEL_AGG, "kq_agg_partition_reduce", reduce_smem, &k_reduce));
+    int grid = (int)std::min<int64_t>(ntiles, (int64_t)ctx->sm_count);
+    if (const char* e = getenv("KQ_PART_GRID")) { int v = atoi(e); if (v >= 1 && v <= grid) grid = v; }      // tuning experiments
+    const int64_t chunk_tiles = std::max<int64_t>(1, PART_CHUNK_ROWS / TILE);
+    const int64_t chunk_rows = std::min<int64_t>(n, chunk_tiles * TILE);
+    // bucket capacity: the mean fill of a (partition, block) bucket plus slack for hash and scheduling imbalance; a
+    // bucket that overflows anyway (skewed keys) spills its rows to the plain global path inside pass 1
+    const double mean = (double)chunk_rows / ((double)nparts * grid);
+    const int part_cap = (int)(mean * 1.25 + 4.0 * sqrt(mean) + 16.0);
+    const int tw = A.part_tw;           // tuple words (plan_agg; the kernel derives the same number from the compiled-in layout)
+    uint64_t* scratch = nullptr; uint32_t* counts = nullptr;
+    const size_t buckets = (size_t)nparts * grid;
+    KQ_RET(kq_dev_alloc(ctx, buckets * (size_t)part_cap * tw * 8, (void**)&scratch));
+    int st = kq_dev_alloc(ctx, buckets * 4 + 64, (void**)&counts);
+    if (st != KQ_OK) { kq_dev_free(ctx, scratch); return st; }
+    auto done = [&](int s) { kq_dev_free(ctx, scratch); kq_dev_free(ctx, counts); return s; };
+    unsigned long long* d_max = h->d_counters + 3;
+
+    // pass 2 needs room for every group a partition in flight may add; keep a floor under the table size
+    const uint64_t margin1 = (uint64_t)grid * ((uint64_t)(A.sp.nstages + 1) * TILE);
+    int64_t tile_begin = 0;
+    while (tile_begin < ntiles) {
+        const int64_t tile_end = std::min(ntiles, tile_begin + chunk_tiles);
+        // ---- pass 1: scatter tiles [tile_begin, tile_end) (rows of full buckets go to the global table directly)
+        {
+            const uint64_t rows_here = (uint64_t)(std::min<int64_t>(n, tile_end * TILE) - tile_begin * TILE);
+            uint64_t cap = h->capacity;
+            while (cap / 4 < std::min(margin1, rows_here) || (uint64_t)h->ngroups_host >= cap / 2) cap <<= 1;
+            if (cap != h->capacity && (st = table_grow(ctx, h, cap)) != KQ_OK) return done(st);
+        }
+        fill_common_args(h, A);
+        A.n = n; A.ntiles = tile_end; A.tile_begin = tile_begin;
+        A.stop_threshold = h->capacity / 2;
+        A.part_scratch = scratch; A.part_counts = counts; A.nparts = nparts; A.part_ncta = grid; A.part_cap = part_cap; A.part_begin = 0;
+        A.part_log2 = 0; while ((1 << A.part_log2) < nparts) A.part_log2++;
+        if (cudaMemsetAsync(h->d_counters + 1, 0, 8, ctx->stream) != cudaSuccess || cudaMemsetAsync(counts, 0, buckets * 4, ctx->stream) != cudaSuccess)
+            return done(kq_cuda_fail(ctx, cudaGetLastError(), "cudaMemsetAsync"));
+        void* kargs[] = {&A};
+        cudaError_t ce = cudaLaunchKernel(k_scatter, dim3(grid), dim3(THREADS), kargs, (size_t)A.smem_bytes, ctx->stream);
+        if (ce != cudaSuccess) return done(kq_cuda_fail(ctx, ce, "cudaLaunchKernel(kq_hash_aggregate, partition scatter)"));
+        ctx->launches++;
+        cudaMemsetAsync(d_max, 0, 8, ctx->stream);
+        k_max_u32<<<small_grid(ctx, buckets), 256, 0, ctx->stream>>>(counts, buckets, d_max);
+        if ((st = launch_check(ctx, "k_max_u32")) != KQ_OK) return done(st);
+        uint64_t c[4];
+        if ((st = kq_read_u64(ctx, h->d_counters, 4, c)) != KQ_OK) return done(st);
+        h->ngroups_host = (int64_t)c[0];
+        const int64_t taken = std::min<int64_t>((int64_t)(uint32_t)c[1], tile_end - tile_begin);
+        const uint64_t max_bucket = c[3];
+        // ---- pass 2: reduce the partitions; a block in flight may add up to one partition's rows as new groups
+        const uint64_t margin2 = (uint64_t)std::min<int64_t>(grid, nparts) * std::max<uint64_t>(1, max_bucket * (uint64_t)grid);
+        int part_begin = 0;
+        while (part_begin < nparts) {
+            uint64_t cap = h->capacity;
+            while (cap / 4 < margin2 || (uint64_t)h->ngroups_host >= cap / 2) cap <<= 1;
+            if (cap != h->capacity && (st = table_grow(ctx, h, cap)) != KQ_OK) return done(st);
+            fill_common_args(h, A);
+            A.stop_threshold = h->capacity / 2;
+            A.part_begin = part_begin;
+            if (cudaMemsetAsync(h->d_counters + 1, 0, 8, ctx->stream) != cudaSuccess) return done(kq_cuda_fail(ctx, cudaGetLastError(), "cudaMemsetAsync"));
+            ce = cudaLaunchKernel(k_reduce, dim3(std::min(nparts - part_begin, ctx->sm_count)), dim3(512), kargs, (size_t)reduce_smem, ctx->stream);
+            if (ce != cudaSuccess) return done(kq_cuda_fail(ctx, ce, "cudaLaunchKernel(kq_agg_partition_reduce)"));
+            ctx->launches++;
+            if ((st = kq_read_u64(ctx, h->d_counters, 2, c)) != KQ_OK) return done(st);
+            h->ngroups_host = (int64_t)c[0];
+            part_begin += (int)std::min<int64_t>((int64_t)(uint32_t)c[1], nparts - part_begin);
+        }
+        tile_begin += taken;
+        if (taken == 0 && (st = table_grow(ctx, h, h->capacity * 2)) != KQ_OK) return done(st);   // pass 1 could not start (table at its threshold)
+    }
+    return done(KQ_OK);
 }
 
 extern "C" {
@@ -544,6 +688,9 @@ int kq_hashagg_update(kq_ctx* ctx, kq_hashagg* h, kq_batch* input) {
     AggArgs A;
     memset(&A, 0, sizeof A);
     std::string defines, gen;
+    // High cardinality (planner hint, or learnt from earlier batches): the partitioned path.
+    const int64_t g_est = std::max<int64_t>(h->expected_groups, h->ngroups_host);
+    if (g_est >= PART_MIN_GROUPS && n >= PART_MIN_ROWS && !getenv("KQ_NO_PARTITION")) return hashagg_update_partitioned(ctx, h, input, n, g_est);
     KQ_RET(plan_agg(ctx, h, input, ctx->max_smem_optin, A, &defines, &gen));
     if (n == 0) return KQ_OK;
     const AggGeometry geo{A.geo_r, A.geo_warps};
@@ -598,11 +745,13 @@ int kq_explain_hashagg(kq_expr* pred, kq_expr* const* group_exprs, int ngroup, c
     kq_ctx fake;
     KqSchemaBatch sb(ncols, types, nullable);
     kq_hashagg* h = nullptr;
-    int st = hashagg_new(&fake, pred, group_exprs, ngroup, agg_kinds, agg_inputs, nagg, 0, &h);
+    const char* eg = getenv("KQ_EXPLAIN_GROUPS");        // tuning aid: the cardinality hint shapes the geometry
+    int st = hashagg_new(&fake, pred, group_exprs, ngroup, agg_kinds, agg_inputs, nagg, eg ? atoll(eg) : 0, &h);
     AggArgs A;
     memset(&A, 0, sizeof A);
     std::string defines, gen;
-    if (st == KQ_OK) st = plan_agg(&fake, h, &sb.batch, 232448, A, &defines, &gen);
+    const char* ep = getenv("KQ_EXPLAIN_PARTS");          // tuning aid: compile the partitioned path's kernels instead
+    if (st == KQ_OK) st = plan_agg(&fake, h, &sb.batch, 232448, A, &defines, &gen, ep ? 1 : 0, ep ? atoi(ep) : 0);
     if (st == KQ_OK && compile) st = kq_jit_compile_only(&fake, defines, gen, KQ_SKEL_AGG);
     kq_copy_text(st == KQ_OK ? defines + gen : fake.last_error, source, source_cap);
     if (h) hashagg_delete_host(h);

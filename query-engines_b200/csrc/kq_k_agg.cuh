@@ -68,18 +68,19 @@ struct FrontEnd {
     uint64_t* sum;            // this warp: [FG][NSUM][32]
 };
 
-// Group id of a key in the CTA directory, inserting it while there is room; -1 = the row goes to the global table.
-// cheap 32-bit multiplicative hash for the CTA directory (the 64-bit hash of the global table is only
-// computed for rows that actually go there)
+// Home slot of a key in the CTA directory. Multiplicative (Fibonacci) hashing: the HIGH bits of the product are
+// the well-mixed ones, so small integers and short strings spread without a finaliser (the 64-bit hash of the
+// global table is only computed for rows that actually go there). The home is an EVEN slot — a two-slot bucket,
+// probed linearly from there — so the branch-free first probe reads slots home and home + 1 without wrapping.
+__host__ __device__ constexpr int ilog2c(int x) { return x <= 1 ? 0 : 1 + ilog2c(x >> 1); }
 __device__ __forceinline__ uint32_t dir_hash(const uint64_t (&kw)[MAX_KEYS], uint32_t nullmask) {
-    uint32_t h = nullmask * 0x9E3779B1u;
+    uint32_t h = Q::KEYS_NULLABLE ? nullmask * 0x9E3779B1u : 0u;
 #pragma unroll
     for (int k = 0; k < Q::NKEYS; k++) h = (h ^ (uint32_t)kw[k] ^ ((uint32_t)(kw[k] >> 32) * 0x85EBCA6Bu)) * 0x9E3779B1u;
-    // murmur3 finaliser: small integers and short strings must not share low bits
-    h ^= h >> 16; h *= 0x85EBCA6Bu; h ^= h >> 13; h *= 0xC2B2AE35u; h ^= h >> 16;
-    return h & (DIR - 1);
+    return (h >> (33 - ilog2c(DIR))) << 1;
 }
 
+// Group id of a key in the CTA directory, inserting it while there is room; -1 = the row goes to the global table.
 __device__ __forceinline__ int dir_lookup(const FrontEnd& fe, uint32_t slot, const uint64_t (&kw)[MAX_KEYS], uint32_t nullmask) {
 #pragma unroll 1
     for (int probe = 0; probe < 8; probe++) {
@@ -299,7 +300,9 @@ __device__ __forceinline__ void global_accumulate_batched(uint64_t* const (&rec)
                     const uint64_t m = order_map(is_int ? v : canon_nan(v), is_int);
                     // pre-check against a (possibly stale) copy: MIN only falls and MAX only rises, so a stale value errs on the safe side
                     if constexpr ((FL & F_MIN) != 0) {
-                        const uint64_t cur = (Q::NIN == 1 && Q::MM_PAIRED) ? mmv[r].x : __ldcg(p + Q::MM_WORD[Q::FE_MIN[I]]);
+                        // the paired copy was loaded alongside the header, not after it: it may predate the record's
+                        // initialisation (all-zero words). 0 is never a safe stale MIN, so it only means "unknown"
+                        const uint64_t cur = (Q::NIN == 1 && Q::MM_PAIRED) ? (mmv[r].x ? mmv[r].x : ~0ULL) : __ldcg(p + Q::MM_WORD[Q::FE_MIN[I]]);
                         if (m < cur) atomicMin(reinterpret_cast<unsigned long long*>(p + Q::MM_WORD[Q::FE_MIN[I]]), (unsigned long long)m);
                     }
                     if constexpr ((FL & F_MAX) != 0) {
@@ -313,7 +316,7 @@ __device__ __forceinline__ void global_accumulate_batched(uint64_t* const (&rec)
     }
 }
 
-__device__ __forceinline__ void global_path_batched(const AggArgs& A, const AggSink& sink, const uint32_t (&nm)[R], uint32_t rows) {
+__device__ __forceinline__ void global_path_batched(const AggArgs& A, const AggSink& sink, const uint32_t (&nm)[R], uint32_t rows, uint32_t& new_groups) {
     uint64_t* rec[R];                 // record under examination, then the row's record
     uint64_t* const tab_end = A.table + (A.cap_mask + 1) * (uint64_t)A.stride;
 #pragma unroll
@@ -348,7 +351,7 @@ __device__ __forceinline__ void global_path_batched(const AggArgs& A, const AggS
                     for (int k2 = 0; k2 < Q::NKEYS; k2++) p[1 + k2] = sink.key[k2][r];
                     __threadfence();
                     *reinterpret_cast<volatile uint64_t*>(p) = full_hdr;
-                    atomicAdd(A.ngroups, 1ULL);
+                    new_groups++;
                     if constexpr (PAIRED) mmv[r] = make_ulonglong2(~0ULL, 0ULL);      // identities of a fresh record
                     pending &= ~(1u << r);
                 }
@@ -364,6 +367,88 @@ __device__ __forceinline__ void global_path_batched(const AggArgs& A, const AggS
         }
     }
     global_accumulate_batched<0>(rec, mmv, sink, rows);
+}
+
+// ---- partitioned path (high cardinality) ------------------------------------------------------------------------------
+// With millions of groups every row of the plain path is a random read-modify-write in HBM/L2 (latency- and
+// atomic-bound, a few G rows/s). Instead: PASS 1 (this kernel, KQ_AGG_MODE 1) evaluates the query's expressions
+// and scatters one TUPLE per selected row into HBM scratch, bucketed by (hash partition, CTA) — a CTA appends to
+// its own buckets through shared-memory cursors, so there are no global atomics and the L2 merges the appends
+// into full lines; PASS 2 (kq_agg_partition_reduce) reduces one partition at a time in a shared-memory hash
+// table — a partition holds a few thousand distinct keys — and merges the table into the global one, once per
+// distinct key instead of once per row. Rows that do not fit (bucket or table full: skewed keys) take the plain
+// global path, so the result never depends on the partition geometry.
+// Tuple: [key words][meta word if anything is nullable: key null mask | input validity bits << 8][one word per
+// input that carries a value (inputs used by COUNT only carry none)].
+#ifndef KQ_AGG_MODE
+#define KQ_AGG_MODE 0
+#endif
+#ifndef KQ_GLOBAL_BATCHED
+#define KQ_GLOBAL_BATCHED 0          // 1: global_path_batched (R lookups in flight per thread) — EXPERIMENTAL, misattributes a few rows per million at 10 M groups (tools/part_debug.py); off until understood
+#endif
+constexpr bool TUPLE_META = Q::KEYS_NULLABLE || Q::NCNT > 1;
+__host__ __device__ constexpr int tuple_in_word(int i) {
+    int w = Q::NKEYS + (TUPLE_META ? 1 : 0);
+    for (int j = 0; j < i; j++) if (Q::IN_FLAGS[j] & (F_SUM | F_MIN | F_MAX)) w++;
+    return w;
+}
+constexpr int TW = tuple_in_word(Q::NIN) > 0 ? tuple_in_word(Q::NIN) : 1;
+// 32-bit multiplicative hash of a key: its TOP bits choose the partition (pass 1); pass 2 runs it through a
+// bijective finaliser for the shared-memory slot, so keys that share a partition still spread over the table.
+// (The 64-bit hash_key of the global table is only computed per distinct key, at merge time.)
+__device__ __forceinline__ uint32_t part_hash(const uint64_t (&kw)[MAX_KEYS], uint32_t nullmask) {
+    uint32_t h = Q::KEYS_NULLABLE ? nullmask * 0xC2B2AE35u : 0u;
+#pragma unroll
+    for (int k = 0; k < Q::NKEYS; k++) h = (h ^ (uint32_t)kw[k] ^ ((uint32_t)(kw[k] >> 32) * 0x85EBCA6Bu)) * 0x9E3779B1u;
+    return h;
+}
+
+__device__ __forceinline__ uint32_t atoms_inc(uint32_t addr) {
+    uint32_t old;
+    asm volatile("atom.shared.add.u32 %0, [%1], 1;" : "=r"(old) : "r"(addr) : "memory");
+    return old;
+}
+
+// Scatter the selected rows of this thread into the CTA's buckets; returns the rows whose bucket is full.
+__device__ __forceinline__ uint32_t partition_scatter(const AggArgs& A, uint32_t a_cursor, const AggSink& sink, const uint32_t (&nm)[R], uint32_t rows) {
+    uint32_t part[R], pos[R];
+#pragma unroll
+    for (int r = 0; r < R; r++) {
+        part[r] = 0; pos[r] = 0xFFFFFFFFu;
+        if ((rows >> r) & 1u) {
+            uint64_t kw[MAX_KEYS];
+#pragma unroll
+            for (int k2 = 0; k2 < MAX_KEYS; k2++) kw[k2] = k2 < Q::NKEYS ? sink.key[k2][r] : 0;
+            part[r] = part_hash(kw, nm[r]) >> (32 - A.part_log2);
+            pos[r] = atoms_inc(a_cursor + part[r] * 4u);
+        }
+    }
+    uint32_t overflow = 0;
+#pragma unroll
+    for (int r = 0; r < R; r++) {
+        if (!((rows >> r) & 1u)) continue;
+        if (pos[r] >= (uint32_t)A.part_cap) { overflow |= 1u << r; continue; }
+        uint64_t* t = A.part_scratch + (((uint64_t)part[r] * (uint32_t)A.part_ncta + blockIdx.x) * (uint32_t)A.part_cap + pos[r]) * TW;
+        uint64_t w[TW];
+#pragma unroll
+        for (int k2 = 0; k2 < Q::NKEYS; k2++) w[k2] = sink.key[k2][r];
+        if constexpr (TUPLE_META) {
+            uint32_t meta = nm[r];
+#pragma unroll
+            for (int i = 0; i < Q::NIN; i++) meta |= ((sink.inok[i] >> r) & 1u) << (8 + i);
+            w[Q::NKEYS] = meta;
+        }
+#pragma unroll
+        for (int i = 0; i < Q::NIN; i++) if (Q::IN_FLAGS[i] & (F_SUM | F_MIN | F_MAX)) w[tuple_in_word(i)] = sink.in[i][r];
+        if constexpr (TW % 2 == 0) {
+#pragma unroll
+            for (int j = 0; j < TW; j += 2) *reinterpret_cast<ulonglong2*>(t + j) = make_ulonglong2(w[j], w[j + 1]);
+        } else {
+#pragma unroll
+            for (int j = 0; j < TW; j++) t[j] = w[j];
+        }
+    }
+    return overflow;
 }
 
 extern "C" __global__ void __launch_bounds__(THREADS, 1) kq_hash_aggregate(const __grid_constant__ AggArgs A) {
@@ -386,6 +471,9 @@ extern "C" __global__ void __launch_bounds__(THREADS, 1) kq_hash_aggregate(const
     uint64_t* sum0 = reinterpret_cast<uint64_t*>(p0);    p0 += (size_t)WARPS * FG1 * NSUM * 32 * 8;
     uint32_t* cnt0 = reinterpret_cast<uint32_t*>(p0);    p0 += (size_t)WARPS * FG1 * NCNT * 32 * 4;
     fe.gid2slot = reinterpret_cast<uint32_t*>(p0);       p0 += (size_t)(FG > 0 ? FG : 1) * 4;
+    p0 = smem + (((size_t)(p0 - smem) + 15) & ~(size_t)15);
+    uint32_t* part_cursor = reinterpret_cast<uint32_t*>(p0);   // pass 1 of the partitioned path: tuples appended per partition
+    if (KQ_AGG_MODE == 1) p0 += (size_t)A.nparts * 4;
     const size_t fe_end = (size_t)(p0 - smem);
     fe.dir_count = &s_dir_count;
     fe.sum = sum0 + (size_t)(warp < 0 ? 0 : warp) * FG1 * NSUM * 32;
@@ -420,7 +508,7 @@ extern "C" __global__ void __launch_bounds__(THREADS, 1) kq_hash_aggregate(const
             long long next = take();
             for (int kp = 0;; kp++) {
                 const int s = kp % S;
-                mbar_wait(&empty[s], ((kp / S) & 1) ^ 1);
+                while (!mbar_test(&empty[s], ((kp / S) & 1) ^ 1)) __nanosleep(64);      // a spinning producer would take issue slots from the consumer warp on its scheduler
                 const long long tile = next;
                 tile_of[s] = tile;
                 if (tile < 0) { mbar_arrive(&full[s]); break; }
@@ -454,13 +542,14 @@ extern "C" __global__ void __launch_bounds__(THREADS, 1) kq_hash_aggregate(const
 #pragma unroll
                 for (int k2 = 0; k2 < Q::NKEYS; k2++) {
                     uint64_t w = 0;
-                    if ((sink.keyok[k2] >> r) & 1u) w = ((Q::KEY_F64_MASK >> k2) & 1u) ? canon_nan(sink.key[k2][r]) : sink.key[k2][r];
+                    if (!Q::KEYS_NULLABLE || ((sink.keyok[k2] >> r) & 1u)) w = ((Q::KEY_F64_MASK >> k2) & 1u) ? canon_nan(sink.key[k2][r]) : sink.key[k2][r];
                     else nullmask |= 1u << k2;
                     sink.key[k2][r] = w;
                 }
                 nm[r] = nullmask;
             }
             uint32_t slow = sink.sel;             // rows that still need the general path
+            uint32_t new_groups = 0;              // groups this thread adds to the global table in this tile
             int fe_hits = 0;
             if (!bypass) {
                 // pass 1 (branch-free): one directory probe per row; a first-probe hit yields the group id
@@ -471,11 +560,12 @@ extern "C" __global__ void __launch_bounds__(THREADS, 1) kq_hash_aggregate(const
                     uint64_t kw[MAX_KEYS];
 #pragma unroll
                     for (int k2 = 0; k2 < MAX_KEYS; k2++) kw[k2] = k2 < Q::NKEYS ? sink.key[k2][r] : 0;
-                    // the key's home slot and its neighbour (linear probing rarely displaces a key further)
-                    const uint32_t s0 = dir_hash(kw, nm[r]);
-                    const uint32_t e0 = a_dir + s0 * (ENTRY_WORDS * 8u), e1 = a_dir + ((s0 + 1) & (DIR - 1)) * (ENTRY_WORDS * 8u);
+                    // the key's home bucket: slots s0 (even) and s0 + 1 (linear probing rarely displaces a key further)
+                    const uint32_t e0 = a_dir + dir_hash(kw, nm[r]) * (ENTRY_WORDS * 8u), e1 = e0 + ENTRY_WORDS * 8u;
                     const uint4 q0 = lds_u128(e0), q1 = lds_u128(e1);
-                    bool h0 = q0.x >= 2u && q0.x != DIR_GLOBAL && q0.y == nm[r], h1 = q1.x >= 2u && q1.x != DIR_GLOBAL && q1.y == nm[r];
+                    // state word: gid + 2 for a published front-end group (EMPTY, BUSY and GLOBAL all fail the unsigned test)
+                    bool h0 = q0.x - 2u < (uint32_t)FG, h1 = q1.x - 2u < (uint32_t)FG;
+                    if constexpr (Q::KEYS_NULLABLE) { h0 &= q0.y == nm[r]; h1 &= q1.y == nm[r]; }
                     if constexpr (Q::NKEYS >= 1) {
                         h0 &= ((uint64_t)q0.z | ((uint64_t)q0.w << 32)) == kw[0];
                         h1 &= ((uint64_t)q1.z | ((uint64_t)q1.w << 32)) == kw[0];
@@ -495,8 +585,11 @@ extern "C" __global__ void __launch_bounds__(THREADS, 1) kq_hash_aggregate(const
             }
             // general path for the rest: directory probing with insertion, else the global table
             int rows = __popc(sink.sel);
-            if (bypass) {
-                if (slow) global_path_batched(A, sink, nm, slow);
+            if (KQ_AGG_MODE == 1) {
+                if (slow) slow = partition_scatter(A, smem_u32(part_cursor), sink, nm, slow);
+                if (slow) global_path_batched(A, sink, nm, slow, new_groups);          // bucket full (skewed keys)
+            } else if (bypass && KQ_GLOBAL_BATCHED) {
+                if (slow) global_path_batched(A, sink, nm, slow, new_groups);
             } else if (slow) {
 #pragma unroll
                 for (int r = 0; r < R; r++) {
@@ -511,13 +604,18 @@ extern "C" __global__ void __launch_bounds__(THREADS, 1) kq_hash_aggregate(const
                         if constexpr (Q::CNT0_USED) fe.cnt[((g * NCNT) << 5) + lane] += 1u;
                         fe_accumulate<0>(fe, g, lane, sink, r);
                     } else {
-                        uint64_t* rec = table_find_or_insert(A, hash_key(kw, nm[r], Q::NKEYS), kw, nm[r]);
+                        uint64_t* rec = table_find_or_insert(A, hash_key(kw, nm[r], Q::NKEYS), kw, nm[r], &new_groups);
                         global_accumulate_all<0>(A, rec, sink, r);
                     }
                 }
             }
+            // one update of the global group count per warp and tile (a single counter bumped by every insert serialises in the L2)
+            if (__any_sync(0xffffffffu, new_groups != 0)) {
+                const uint32_t tot = __reduce_add_sync(0xffffffffu, new_groups);
+                if (lane == 0) atomicAdd(A.ngroups, (unsigned long long)tot);
+            }
             // once the directory is full and this warp mostly misses it, stop probing it (high cardinality)
-            if (!bypass && *reinterpret_cast<volatile uint32_t*>(&s_dir_count) >= (uint32_t)FG) {
+            if (!bypass && __any_sync(0xffffffffu, fe_hits < rows) && *reinterpret_cast<volatile uint32_t*>(&s_dir_count) >= (uint32_t)FG) {
                 int hits = fe_hits, tot = rows;
 #pragma unroll
                 for (int o = 16; o; o >>= 1) { hits += __shfl_xor_sync(0xffffffffu, hits, o); tot += __shfl_xor_sync(0xffffffffu, tot, o); }
@@ -528,6 +626,10 @@ extern "C" __global__ void __launch_bounds__(THREADS, 1) kq_hash_aggregate(const
 
     // ---- merge the front end into the global table ---------------------------------------------------
     __syncthreads();
+    if (KQ_AGG_MODE == 1) {
+        for (int p = threadIdx.x; p < A.nparts; p += THREADS)
+            A.part_counts[(size_t)p * A.part_ncta + blockIdx.x] = min(part_cursor[p], (uint32_t)A.part_cap);
+    }
     const int G = min((int)s_dir_count, FG);
     for (int g = threadIdx.x; g < G; g += THREADS) {
         const uint64_t* e = fe.dir + (size_t)fe.gid2slot[g] * ENTRY_WORDS;
@@ -561,5 +663,220 @@ extern "C" __global__ void __launch_bounds__(THREADS, 1) kq_hash_aggregate(const
         else if (v != 0ULL) atomicMax(reinterpret_cast<unsigned long long*>(p), (unsigned long long)v);
     }
 }
+
+#if KQ_AGG_MODE == 1
+// ---- pass 2 of the partitioned path ------------------------------------------------------------------------------------
+constexpr int PR_THREADS = 512, PR_WARPS = PR_THREADS / 32, PR_UNROLL = 4;
+
+struct PartTable {            // struct-of-arrays hash table in shared memory, SL slots
+    uint64_t* key;            // [NKEYS][SL]
+    uint64_t* sum;            // [NSUM][SL]
+    uint64_t* mm;             // [NMM][SL]  order-mapped MIN/MAX
+    uint32_t* cnt;            // [NCNT][SL] slot 0: rows (statically non-null inputs), else one per nullable input
+    uint32_t* state;          // [SL] 0 empty, 1 being published, 2 | key null mask << 8 full
+    uint32_t* nfull;
+    int SL;
+    uint32_t limit;           // stop inserting at this fill (the rest goes to the global table)
+};
+
+template <int I>
+__device__ __forceinline__ void part_accumulate_input(const PartTable& T, uint32_t slot, uint32_t meta, const uint64_t (&w)[TW]) {
+    if constexpr (I < Q::NIN) {
+        constexpr int FL = Q::IN_FLAGS[I];
+        const bool valid = Q::IN_CNT[I] > 0 ? ((meta >> (8 + I)) & 1u) != 0 : true;
+        if (valid) {
+            if constexpr (Q::IN_CNT[I] > 0) atomicAdd(T.cnt + (size_t)Q::IN_CNT[I] * T.SL + slot, 1u);
+            if constexpr ((FL & (F_SUM | F_MIN | F_MAX)) != 0) {
+                const uint64_t v = w[tuple_in_word(I)];
+                if constexpr ((FL & F_SUM) != 0) {
+                    uint64_t* p = T.sum + (size_t)Q::FE_SUM[I] * T.SL + slot;
+                    if constexpr ((FL & F_INT) != 0) atomicAdd(reinterpret_cast<unsigned long long*>(p), (unsigned long long)v);
+                    else atomicAdd(reinterpret_cast<double*>(p), as_f64(v));
+                }
+                if constexpr ((FL & (F_MIN | F_MAX)) != 0) {
+                    constexpr bool is_int = (FL & F_INT) != 0;
+                    const uint64_t m = order_map(is_int ? v : canon_nan(v), is_int);
+                    if constexpr ((FL & F_MIN) != 0) {
+                        uint64_t* p = T.mm + (size_t)Q::FE_MIN[I] * T.SL + slot;
+                        if (m < *reinterpret_cast<volatile uint64_t*>(p)) atomicMin(reinterpret_cast<unsigned long long*>(p), (unsigned long long)m);
+                    }
+                    if constexpr ((FL & F_MAX) != 0) {
+                        uint64_t* p = T.mm + (size_t)Q::FE_MAX[I] * T.SL + slot;
+                        if (m > *reinterpret_cast<volatile uint64_t*>(p)) atomicMax(reinterpret_cast<unsigned long long*>(p), (unsigned long long)m);
+                    }
+                }
+            }
+        }
+        part_accumulate_input<I + 1>(T, slot, meta, w);
+    }
+}
+template <int I>
+__device__ __forceinline__ void part_overflow_input(const AggArgs& A, uint64_t* rec, uint32_t meta, const uint64_t (&w)[TW]) {
+    if constexpr (I < Q::NIN) {
+        const bool valid = Q::IN_CNT[I] > 0 ? ((meta >> (8 + I)) & 1u) != 0 : true;
+        if (valid) global_accumulate(rec, A.in[I], (Q::IN_FLAGS[I] & (F_SUM | F_MIN | F_MAX)) ? w[tuple_in_word(I)] : 0ULL);
+        part_overflow_input<I + 1>(A, rec, meta, w);
+    }
+}
+template <int I>
+__device__ __forceinline__ void part_merge_input(const PartTable& T, uint32_t slot, uint64_t* rec) {
+    if constexpr (I < Q::NIN) {
+        constexpr int FL = Q::IN_FLAGS[I];
+        const uint32_t n = T.cnt[(size_t)Q::IN_CNT[I] * T.SL + slot];
+        if (n) {
+            atomicAdd(reinterpret_cast<unsigned long long*>(rec + Q::REC_NN[I]), (unsigned long long)n);
+            if constexpr ((FL & F_SUM) != 0) {
+                const uint64_t x = T.sum[(size_t)Q::FE_SUM[I] * T.SL + slot];
+                if constexpr ((FL & F_INT) != 0) atomicAdd(reinterpret_cast<unsigned long long*>(rec + Q::REC_SUM[I]), (unsigned long long)x);
+                else atomicAdd(reinterpret_cast<double*>(rec + Q::REC_SUM[I]), as_f64(x));
+            }
+            if constexpr ((FL & F_MIN) != 0) {
+                const uint64_t x = T.mm[(size_t)Q::FE_MIN[I] * T.SL + slot];
+                if (x != ~0ULL) atomicMin(reinterpret_cast<unsigned long long*>(rec + Q::MM_WORD[Q::FE_MIN[I]]), (unsigned long long)x);
+            }
+            if constexpr ((FL & F_MAX) != 0) {
+                const uint64_t x = T.mm[(size_t)Q::FE_MAX[I] * T.SL + slot];
+                if (x != 0ULL) atomicMax(reinterpret_cast<unsigned long long*>(rec + Q::MM_WORD[Q::FE_MAX[I]]), (unsigned long long)x);
+            }
+        }
+        part_merge_input<I + 1>(T, slot, rec);
+    }
+}
+
+// One tuple into the partition's shared-memory table (find or insert, then shared-memory atomics).
+__device__ __forceinline__ void part_accumulate(const AggArgs& A, const PartTable& T, const uint64_t (&w)[TW]) {
+    uint64_t kw[MAX_KEYS];
+#pragma unroll
+    for (int k = 0; k < MAX_KEYS; k++) kw[k] = k < Q::NKEYS ? w[k] : 0;
+    const uint32_t meta = TUPLE_META ? (uint32_t)w[Q::NKEYS] : 0u;
+    const uint32_t nm = meta & 0xffu;
+    // slot hash: the partition hash (its top bits are equal for all keys here) through a bijective finaliser
+    uint32_t h = part_hash(kw, nm);
+    h ^= h >> 16; h *= 0x85EBCA6Bu; h ^= h >> 13; h *= 0xC2B2AE35u; h ^= h >> 16;
+    uint32_t slot = h & (uint32_t)(T.SL - 1);
+    const uint32_t full = 2u | (nm << 8);
+    bool found = false;
+    int spins = 0;
+    for (int probe = 0; probe < 128;) {
+        uint32_t st = *reinterpret_cast<volatile uint32_t*>(T.state + slot);
+        if (st == 0u) {
+            if (*reinterpret_cast<volatile uint32_t*>(T.nfull) >= T.limit) break;
+            const uint32_t old = atomicCAS(T.state + slot, 0u, 1u);
+            if (old == 0u) {
+#pragma unroll
+                for (int k = 0; k < Q::NKEYS; k++) T.key[(size_t)k * T.SL + slot] = kw[k];
+                __threadfence_block();
+                *reinterpret_cast<volatile uint32_t*>(T.state + slot) = full;
+                atomicAdd(T.nfull, 1u);
+                found = true;
+                break;
+            }
+            st = old;
+        }
+        if (st == 1u) {
+            // being published. The publisher may be a lane of THIS warp (two first occurrences of a key side by side):
+            // a bare spin would keep the warp on this path and starve it, so sleep (yields to the other path) and,
+            // if that does not help quickly, send the row to the global table instead
+            if (++spins > 8) break;
+            __nanosleep(40);
+            continue;
+        }
+        if (st == full) {
+            bool eq = true;
+#pragma unroll
+            for (int k = 0; k < Q::NKEYS; k++) eq &= *reinterpret_cast<volatile uint64_t*>(T.key + (size_t)k * T.SL + slot) == kw[k];
+            if (eq) { found = true; break; }
+        }
+        slot = (slot + 1) & (uint32_t)(T.SL - 1);
+        probe++;
+    }
+    if (found) {
+        if constexpr (Q::CNT0_USED) atomicAdd(T.cnt + slot, 1u);
+        part_accumulate_input<0>(T, slot, meta, w);
+    } else {
+        uint64_t* rec = table_find_or_insert(A, hash_key(kw, nm, Q::NKEYS), kw, nm);
+        part_overflow_input<0>(A, rec, meta, w);
+    }
+}
+
+extern "C" __global__ void __launch_bounds__(PR_THREADS, 1) kq_agg_partition_reduce(const __grid_constant__ AggArgs A) {
+    extern __shared__ __align__(128) unsigned char smem[];
+    __shared__ int s_part;
+    __shared__ uint32_t s_nfull, s_new;
+    const int SL = A.part_slots;
+    PartTable T;
+    T.SL = SL; T.limit = (uint32_t)(SL - SL / 8); T.nfull = &s_nfull;
+    T.key = reinterpret_cast<uint64_t*>(smem);
+    T.sum = T.key + (size_t)Q::NKEYS * SL;
+    T.mm = T.sum + (size_t)Q::NSUM * SL;
+    T.cnt = reinterpret_cast<uint32_t*>(T.mm + (size_t)Q::NMM * SL);
+    T.state = T.cnt + (size_t)Q::NCNT * SL;
+    const size_t table_bytes = (size_t)SL * (8 * (Q::NKEYS + Q::NSUM + Q::NMM) + 4 * (Q::NCNT + 1));
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    for (;;) {
+        __syncthreads();                                    // the previous partition is merged
+        if (tid == 0) {
+            // same protocol as the tiles of the plain path: partitions are taken in order, and none is taken once the
+            // global table is half full (the host grows it and resumes with the next partition)
+            int p = -1;
+            if (*reinterpret_cast<volatile unsigned long long*>(A.ngroups) <= A.stop_threshold) {
+                const long long t = (long long)atomicAdd(A.ticket, 1u) + A.part_begin;
+                if (t < A.nparts) p = (int)t;
+            }
+            s_part = p; s_nfull = 0; s_new = 0;
+        }
+        for (size_t i = (size_t)tid * 16; i < table_bytes; i += (size_t)PR_THREADS * 16) *reinterpret_cast<uint4*>(smem + i) = make_uint4(0, 0, 0, 0);
+        __syncthreads();
+        const int p = s_part;
+        if (p < 0) break;
+        for (int i = tid; i < Q::NMM * SL; i += PR_THREADS) if ((Q::MM_ISMIN >> (i / SL)) & 1u) T.mm[i] = ~0ULL;
+        __syncthreads();
+        // the partition's buckets, one warp per bucket; PR_UNROLL tuples per lane in flight
+        for (int seg = warp; seg < A.part_ncta; seg += PR_WARPS) {
+            const uint32_t n = A.part_counts[(size_t)p * A.part_ncta + seg];
+            const uint64_t* base = A.part_scratch + ((uint64_t)p * (uint32_t)A.part_ncta + (uint32_t)seg) * (uint32_t)A.part_cap * TW;
+            for (uint32_t b0 = 0; b0 < n; b0 += 32 * PR_UNROLL) {       // warp-uniform trip count
+                const uint32_t i0 = b0 + lane;
+                uint64_t w[PR_UNROLL][TW];
+#pragma unroll
+                for (int u = 0; u < PR_UNROLL; u++) {
+                    const uint32_t i = i0 + 32u * u;
+                    if (i < n) {
+                        const uint64_t* t = base + (uint64_t)i * TW;
+                        if constexpr (TW % 2 == 0) {
+#pragma unroll
+                            for (int j = 0; j < TW; j += 2) { const ulonglong2 q = __ldcs(reinterpret_cast<const ulonglong2*>(t + j)); w[u][j] = q.x; w[u][j + 1] = q.y; }
+                        } else {
+#pragma unroll
+                            for (int j = 0; j < TW; j++) w[u][j] = __ldcs(t + j);
+                        }
+                    }
+                }
+#pragma unroll
+                for (int u = 0; u < PR_UNROLL; u++) {
+                    if (i0 + 32u * u < n) part_accumulate(A, T, w[u]);
+                    __syncwarp();           // the probe / CAS loops diverge: reconverge before the next tuple (measured: without
+                }                           // this the lanes of a warp drift apart for good, 4 active lanes per instruction)
+            }
+        }
+        __syncthreads();
+        // merge the table into the global one: once per distinct key of the partition
+        uint32_t fresh = 0;
+        for (int slot = tid; slot < SL; slot += PR_THREADS) {
+            const uint32_t st = T.state[slot];
+            if ((st & 0xffu) != 2u) continue;
+            uint64_t kw[MAX_KEYS];
+#pragma unroll
+            for (int k = 0; k < MAX_KEYS; k++) kw[k] = k < Q::NKEYS ? T.key[(size_t)k * SL + slot] : 0;
+            const uint32_t nm = st >> 8;
+            uint64_t* rec = table_find_or_insert(A, hash_key(kw, nm, Q::NKEYS), kw, nm, &fresh);
+            part_merge_input<0>(T, (uint32_t)slot, rec);
+        }
+        if (fresh) atomicAdd(&s_new, fresh);
+        __syncthreads();
+        if (tid == 0 && s_new) atomicAdd(A.ngroups, (unsigned long long)s_new);       // one update per partition, not per group
+    }
+}
+#endif  // KQ_AGG_MODE == 1
 
 }  // namespace kq

@@ -228,42 +228,83 @@ __device__ __forceinline__ uint32_t utf8_cmp_col(const QCol& c, const QCol& d, u
         }
     return m;
 }
-// the 8 bytes at (unaligned) shared-memory address p, little-endian: two aligned 64-bit loads + funnel shift
-__device__ __forceinline__ uint64_t lds_u64_unaligned(const unsigned char* p) {
-    const uint32_t addr = smem_u32(p), al = addr & ~7u, sh = (addr & 7u) * 8u;
-    uint64_t lo, hi;
-    asm volatile("ld.shared.u64 %0, [%1];" : "=l"(lo) : "r"(al));
-    asm volatile("ld.shared.u64 %0, [%1];" : "=l"(hi) : "r"(al + 8u));
-    return sh ? ((lo >> sh) | (hi << (64u - sh))) : lo;
+// 64-bit shifts with PTX semantics (an amount >= 64 yields 0; C++ leaves it undefined)
+__device__ __forceinline__ uint64_t shl64c(uint64_t x, uint32_t n) { uint64_t r; asm("shl.b64 %0, %1, %2;" : "=l"(r) : "l"(x), "r"(n)); return r; }
+__device__ __forceinline__ uint64_t shr64c(uint64_t x, uint32_t n) { uint64_t r; asm("shr.u64 %0, %1, %2;" : "=l"(r) : "l"(x), "r"(n)); return r; }
+// the 8 bytes at (unaligned) shared-memory address `addr`, little-endian: three aligned 32-bit loads + two funnel shifts
+__device__ __forceinline__ uint64_t lds_window64(uint32_t addr) {
+    const uint32_t al = addr & ~3u, sh = addr << 3;          // the funnel shift takes sh mod 32 = (addr & 3) * 8
+    uint32_t w0, w1, w2;
+    asm volatile("ld.shared.u32 %0, [%1];" : "=r"(w0) : "r"(al));
+    asm volatile("ld.shared.u32 %0, [%1+4];" : "=r"(w1) : "r"(al));
+    asm volatile("ld.shared.u32 %0, [%1+8];" : "=r"(w2) : "r"(al));
+    return (uint64_t)__funnelshift_r(w0, w1, sh) | ((uint64_t)__funnelshift_r(w1, w2, sh) << 32);
+}
+// first `len` bytes of window w, length in the top byte (len <= 7; longer strings raise ERR_LONG_KEY, their key is unused)
+__device__ __forceinline__ uint64_t pack_key(uint64_t w, int len) {
+    const uint32_t drop = 64u - 8u * (uint32_t)len;
+    return shr64c(shl64c(w, drop), drop) | ((uint64_t)(uint32_t)len << 56);
+}
+// Staged fast path of utf8_pack. FULL: the whole tile is inside the batch (no per-row range handling).
+// A lane's two adjacent rows are adjacent strings: one 8-byte window at the first string's start yields both
+// keys whenever the two fit in it; pairs that do not (long keys) are redone in a rarely taken second loop.
+template <int SOFF_OFF, int SB, bool FULL>
+__device__ __forceinline__ uint32_t utf8_pack_staged(long long base, uint32_t ok, const RowCtx& rc, uint64_t (&out)[R]) {
+    const uint32_t sb32 = smem_u32(rc.stage) + (uint32_t)SB - (uint32_t)base;      // shared address of data-buffer offset 0 (mod 2^32)
+    const uint32_t so32 = smem_u32(rc.stage) + (uint32_t)SOFF_OFF;
+    int mxlen = 0;
+    uint32_t need2 = 0;
+    // offsets of the lane's row pair in chunk j: o[2l], o[2l+1], o[2l+2]; rows past the end of the batch have
+    // none (stale shared memory): give them an empty, in-range string
+    auto bounds = [&](int j, int& a0, int& len0, int& len1) {
+        const uint32_t oa = so32 + (uint32_t)rc.trow0(j) * 4u;
+        int o0, o1, o2;
+        asm volatile("ld.shared.v2.s32 {%0,%1}, [%2];" : "=r"(o0), "=r"(o1) : "r"(oa));
+        asm volatile("ld.shared.s32 %0, [%1+8];" : "=r"(o2) : "r"(oa));
+        a0 = o0; len0 = o1 - o0; len1 = o2 - o1;
+        if constexpr (!FULL) {
+            const bool in0 = (rc.inr >> (2 * j)) & 1u, in1 = (rc.inr >> (2 * j + 1)) & 1u;
+            a0 = in0 ? a0 : (int)base; len0 = in0 ? len0 : 0; len1 = in1 ? len1 : 0;
+        }
+    };
+#pragma unroll
+    for (int j = 0; j < NCHUNK; j++) {
+        int a0, len0, len1;
+        bounds(j, a0, len0, len1);
+        mxlen = max(mxlen, max(len0, len1));
+        need2 |= (uint32_t)(len0 + len1 > 8) << j;
+        const uint64_t w0 = lds_window64(sb32 + (uint32_t)a0);
+        const uint64_t k0 = pack_key(w0, len0), k1 = pack_key(shr64c(w0, 8u * (uint32_t)len0), len1);
+        out[2 * j] = ((ok >> (2 * j)) & 1u) ? k0 : 0ULL;
+        out[2 * j + 1] = ((ok >> (2 * j + 1)) & 1u) ? k1 : 0ULL;
+    }
+    uint32_t too_long = 0;
+    if (need2 | (uint32_t)(mxlen > 7)) {
+#pragma unroll 1
+        for (int j = 0; j < NCHUNK; j++) {
+            int a0, len0, len1;
+            bounds(j, a0, len0, len1);
+            too_long |= (uint32_t)(len0 > 7) << (2 * j) | (uint32_t)(len1 > 7) << (2 * j + 1);
+            if ((need2 >> j) & 1u) {
+                const uint64_t k1 = pack_key(lds_window64(sb32 + (uint32_t)(a0 + len0)), len1);
+#pragma unroll
+                for (int jj = 0; jj < NCHUNK; jj++) if (jj == j) out[2 * jj + 1] = ((ok >> (2 * jj + 1)) & 1u) ? k1 : 0ULL;
+            }
+        }
+    }
+    return too_long;
 }
 // short string (<= 7 bytes) -> packed u64 group key: bytes little-endian, length in the top byte.
 // SB >= 0: the tile's string bytes are staged at byte offset SB of the stage (when they fit: rc.bbase[SLOT] >= 0);
-// that path is branch-free per row (one uniform branch per tile).
+// that path is branch-free per row (uniform branches per tile only).
 template <int SOFF_OFF, int SB, int SLOT>
 __device__ __forceinline__ void utf8_pack(const QCol& c, uint32_t ok, const RowCtx& rc, uint64_t (&out)[R]) {
     long long base = -1;
     if constexpr (SB >= 0 && SOFF_OFF >= 0) base = rc.bbase[SLOT];
     uint32_t too_long = 0;
     if (base >= 0) {
-        const unsigned char* sb = rc.stage + SB - base;
-        const int32_t* so = reinterpret_cast<const int32_t*>(rc.stage + SOFF_OFF);
-#pragma unroll
-        for (int j = 0; j < NCHUNK; j++) {
-            // the lane's two adjacent rows share their middle offset: o[2l], o[2l+1], o[2l+2]
-            const int t0 = rc.trow0(j);
-            const int2 o01 = *reinterpret_cast<const int2*>(so + t0);
-            const int o2 = so[t0 + 2];
-            // rows past the end of the batch have no offsets (stale shared memory): give them an empty, in-range string
-            const bool in0 = (rc.inr >> (2 * j)) & 1u, in1 = (rc.inr >> (2 * j + 1)) & 1u;
-            const int a0 = in0 ? o01.x : (int)base, a1 = in1 ? o01.y : (int)base;
-            const int len0 = in0 ? o01.y - o01.x : 0, len1 = in1 ? o2 - o01.y : 0;
-            too_long |= (uint32_t)(len0 > 7) << (2 * j) | (uint32_t)(len1 > 7) << (2 * j + 1);
-            const int l0 = len0 > 7 ? 7 : len0, l1 = len1 > 7 ? 7 : len1;
-            const uint64_t k0 = (lds_u64_unaligned(sb + a0) & ((1ULL << (8 * l0)) - 1ULL)) | ((uint64_t)l0 << 56);
-            const uint64_t k1 = (lds_u64_unaligned(sb + a1) & ((1ULL << (8 * l1)) - 1ULL)) | ((uint64_t)l1 << 56);
-            out[2 * j] = ((ok >> (2 * j)) & 1u) ? k0 : 0ULL;
-            out[2 * j + 1] = ((ok >> (2 * j + 1)) & 1u) ? k1 : 0ULL;
-        }
+        if (rc.full) too_long = utf8_pack_staged<SOFF_OFF, SB, true>(base, ok, rc, out);
+        else too_long = utf8_pack_staged<SOFF_OFF, SB, false>(base, ok, rc, out);
     } else {
         const uint8_t* bytes = reinterpret_cast<const uint8_t*>(c.data);
 #pragma unroll

@@ -345,6 +345,38 @@ def test_high_cardinality_aggregate_grows_the_table(G, oracle):
     assert run(G) == run(oracle)
 
 
+@pytest.mark.parametrize("null_frac", [0.0, 0.05])
+@pytest.mark.parametrize("keys", [[0], [0, 7], [3]])
+def test_partitioned_path_matches_oracle(G, oracle, keys, null_frac):
+    """High-cardinality hint + a batch above the row threshold: the partitioned path (scatter into hash
+    partitions, reduce each in shared memory). Int64 / Int64+Bool / Float64 keys, nullable keys and inputs."""
+    rng = np.random.default_rng(77)
+    n = 1_300_000
+    arrs = rand_table(rng, n, null_frac)
+    def run(E, **kw):
+        agg = E.HashAggregate([E.col(k) for k in keys], [(kind, E.col(c)) for kind, c in AGGS], **kw)
+        agg.update(E.RecordBatch.from_arrow(arrs))
+        agg.update(E.RecordBatch.from_arrow([a.slice(0, 1_100_000) for a in arrs]))     # a second batch merges into the same table
+        return agg.finalize()
+    got, want = run(G, expected_groups=700_000), run(oracle)
+    assert got.row_count() == want.row_count()
+    assert sort_rows(got.to_arrow(), len(keys)) == sort_rows(want.to_arrow(), len(keys))
+
+
+def test_partitioned_path_survives_skewed_keys(G, oracle):
+    """Nine rows in ten share one key: its buckets overflow and the surplus rows take the plain global path."""
+    rng = np.random.default_rng(78)
+    n = 1_500_000
+    k = rng.integers(0, 400_000, n)
+    k[rng.random(n) < 0.9] = 123456789
+    arrs = [pa.array(k), pa.array(np.floor(rng.random(n) * 1000))]
+    def run(E, **kw):
+        agg = E.HashAggregate([E.col(0)], [("SUM", E.col(1)), ("MIN", E.col(1)), ("MAX", E.col(1)), ("COUNT", E.col(1))], **kw)
+        agg.update(E.RecordBatch.from_arrow(arrs))
+        return sort_rows(agg.finalize().to_arrow(), 1)
+    assert run(G, expected_groups=400_000) == run(oracle)
+
+
 def test_fused_filter_project_aggregate_q1_shape(G, oracle):
     """TPC-H Q1 shape (BASELINE config 5) on a small seeded lineitem."""
     specs = q1_specs()
