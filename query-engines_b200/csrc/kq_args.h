@@ -131,8 +131,8 @@ struct AggArgs {
     uint64_t* part_scratch;                // [nparts][part_ncta][part_cap] tuples
     uint32_t* part_counts;                 // [nparts][part_ncta] tuples per bucket
     int32_t nparts, part_ncta, part_cap, part_begin;
-    int32_t part_log2, _pad_part;          // nparts = 1 << part_log2
-    int32_t part_slots, part_tw;           // shared-memory table slots of pass 2 (power of two); 64-bit words per tuple
+    int32_t part_log2, part_groups;        // nparts = 1 << part_log2; accumulator rows of the pass-2 table (distinct keys it can hold)
+    int32_t part_slots, part_tw;           // lookup slots of the pass-2 table (power of two); 64-bit words per tuple
     // shared-memory layout (byte offsets): [stage ring][front end]
     int32_t off_fe, off_dirkeys, off_dirstate, off_gid2slot, off_gslot, off_mm, off_cnt, off_sum, smem_bytes;
     StagePlan sp;

@@ -530,12 +530,15 @@ static int plan_agg(kq_ctx* ctx, kq_hashagg* h, kq_batch* input, int smem_optin,
     A.smem_bytes = ring + dir_slots * entry_words * 8 + std::max(fg, 1) * 12 + (fg + 1) * nm * 8 + WARPS * (fg + 1) * 32 * (8 * ns + 4 * ncnt);
     if (mode == 1) A.smem_bytes += 16 + nparts * 4;
     A.smem_bytes = (A.smem_bytes + 127) / 128 * 128;
-    {   // pass-2 table: as many power-of-two slots as fit in shared memory
-        const int slot_bytes = 8 * (NK + ns + nm) + 4 * (ncnt + 1);
-        int sl = 256;
-        while (sl < 8192 && sl * 2 * slot_bytes <= smem_optin - 2048) sl <<= 1;
+    {   // pass-2 table: a sparse LOOKUP part (state + key words per slot, power-of-two slots, <= 45 % full so that probe
+        // sequences stay short) pointing into a dense ACCUMULATOR part (one row of counts / sums / extremes per distinct key)
+        const int lookup_bytes = 4 + 8 * NK, acc_bytes = 4 * ncnt + 8 * ns + 8 * nm;
+        int sl = 512;
+        auto bytes_for = [&](int slots) { return slots * lookup_bytes + (slots * 45 / 100 / 4 * 4) * acc_bytes; };
+        while (sl < 16384 && bytes_for(sl * 2) <= smem_optin - 4096) sl <<= 1;
         A.part_slots = sl;
-        if (reduce_smem) *reduce_smem = sl * slot_bytes;
+        A.part_groups = sl * 45 / 100 / 4 * 4;
+        if (reduce_smem) *reduce_smem = (bytes_for(sl) + 15) / 16 * 16;
         int tw = NK + ((keys_nullable || ncnt > 1) ? 1 : 0);
         for (int i = 0; i < NI; i++) if (h->in[i].flags & (F_SUM | F_MIN | F_MAX)) tw++;
         A.part_tw = std::max(1, tw);
@@ -595,7 +598,7 @@ static int hashagg_update_partitioned(kq_ctx* ctx, kq_hashagg* h, kq_batch* inpu
     int reduce_smem = 0;
     KQ_RET(plan_agg(ctx, h, input, ctx->max_smem_optin, A, &defines, &gen, 1, 512, &reduce_smem));
     int nparts = 512;
-    while (nparts < 4096 && (int64_t)nparts * A.part_slots * 6 / 10 < g_est) nparts <<= 1;
+    while (nparts < 4096 && (int64_t)nparts * A.part_groups * 7 / 10 < g_est) nparts <<= 1;       // partitions ~70 % of what a table holds
     if (const char* e = getenv("KQ_PARTS")) { int v = atoi(e); if (v >= 16 && v <= 8192 && (v & (v - 1)) == 0) nparts = v; }
     memset(&A, 0, sizeof A);
     KQ_RET(plan_agg(ctx, h, input, ctx->max_smem_optin, A, &defines, &gen, 1, nparts, &reduce_smem));

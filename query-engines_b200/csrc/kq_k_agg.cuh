@@ -668,15 +668,15 @@ extern "C" __global__ void __launch_bounds__(THREADS, 1) kq_hash_aggregate(const
 // ---- pass 2 of the partitioned path ------------------------------------------------------------------------------------
 constexpr int PR_THREADS = 512, PR_WARPS = PR_THREADS / 32, PR_UNROLL = 4;
 
-struct PartTable {            // struct-of-arrays hash table in shared memory, SL slots
+struct PartTable {            // hash table in shared memory: sparse lookup part (SL slots) -> dense accumulator rows (AC)
+    uint32_t* state;          // [SL] 0 empty, 1 being published, else (accumulator row + 2) | key null mask << 24
     uint64_t* key;            // [NKEYS][SL]
-    uint64_t* sum;            // [NSUM][SL]
-    uint64_t* mm;             // [NMM][SL]  order-mapped MIN/MAX
-    uint32_t* cnt;            // [NCNT][SL] slot 0: rows (statically non-null inputs), else one per nullable input
-    uint32_t* state;          // [SL] 0 empty, 1 being published, 2 | key null mask << 8 full
-    uint32_t* nfull;
-    int SL;
-    uint32_t limit;           // stop inserting at this fill (the rest goes to the global table)
+    uint64_t* sum;            // [NSUM][AC]
+    uint64_t* mm;             // [NMM][AC]  order-mapped MIN/MAX
+    uint32_t* cnt;            // [NCNT][AC] row 0: rows (statically non-null inputs), else one per nullable input
+    uint32_t* nfull;          // accumulator rows handed out
+    int SL, AC;
+    uint32_t limit;           // stop inserting at this many rows (every thread may have one insert in flight)
 };
 
 template <int I>
@@ -685,11 +685,11 @@ __device__ __forceinline__ void part_accumulate_input(const PartTable& T, uint32
         constexpr int FL = Q::IN_FLAGS[I];
         const bool valid = Q::IN_CNT[I] > 0 ? ((meta >> (8 + I)) & 1u) != 0 : true;
         if (valid) {
-            if constexpr (Q::IN_CNT[I] > 0) atomicAdd(T.cnt + (size_t)Q::IN_CNT[I] * T.SL + slot, 1u);
+            if constexpr (Q::IN_CNT[I] > 0) atomicAdd(T.cnt + (size_t)Q::IN_CNT[I] * T.AC + slot, 1u);
             if constexpr ((FL & (F_SUM | F_MIN | F_MAX)) != 0) {
                 const uint64_t v = w[tuple_in_word(I)];
                 if constexpr ((FL & F_SUM) != 0) {
-                    uint64_t* p = T.sum + (size_t)Q::FE_SUM[I] * T.SL + slot;
+                    uint64_t* p = T.sum + (size_t)Q::FE_SUM[I] * T.AC + slot;
                     if constexpr ((FL & F_INT) != 0) atomicAdd(reinterpret_cast<unsigned long long*>(p), (unsigned long long)v);
                     else atomicAdd(reinterpret_cast<double*>(p), as_f64(v));
                 }
@@ -697,11 +697,11 @@ __device__ __forceinline__ void part_accumulate_input(const PartTable& T, uint32
                     constexpr bool is_int = (FL & F_INT) != 0;
                     const uint64_t m = order_map(is_int ? v : canon_nan(v), is_int);
                     if constexpr ((FL & F_MIN) != 0) {
-                        uint64_t* p = T.mm + (size_t)Q::FE_MIN[I] * T.SL + slot;
+                        uint64_t* p = T.mm + (size_t)Q::FE_MIN[I] * T.AC + slot;
                         if (m < *reinterpret_cast<volatile uint64_t*>(p)) atomicMin(reinterpret_cast<unsigned long long*>(p), (unsigned long long)m);
                     }
                     if constexpr ((FL & F_MAX) != 0) {
-                        uint64_t* p = T.mm + (size_t)Q::FE_MAX[I] * T.SL + slot;
+                        uint64_t* p = T.mm + (size_t)Q::FE_MAX[I] * T.AC + slot;
                         if (m > *reinterpret_cast<volatile uint64_t*>(p)) atomicMax(reinterpret_cast<unsigned long long*>(p), (unsigned long long)m);
                     }
                 }
@@ -722,20 +722,20 @@ template <int I>
 __device__ __forceinline__ void part_merge_input(const PartTable& T, uint32_t slot, uint64_t* rec) {
     if constexpr (I < Q::NIN) {
         constexpr int FL = Q::IN_FLAGS[I];
-        const uint32_t n = T.cnt[(size_t)Q::IN_CNT[I] * T.SL + slot];
+        const uint32_t n = T.cnt[(size_t)Q::IN_CNT[I] * T.AC + slot];
         if (n) {
             atomicAdd(reinterpret_cast<unsigned long long*>(rec + Q::REC_NN[I]), (unsigned long long)n);
             if constexpr ((FL & F_SUM) != 0) {
-                const uint64_t x = T.sum[(size_t)Q::FE_SUM[I] * T.SL + slot];
+                const uint64_t x = T.sum[(size_t)Q::FE_SUM[I] * T.AC + slot];
                 if constexpr ((FL & F_INT) != 0) atomicAdd(reinterpret_cast<unsigned long long*>(rec + Q::REC_SUM[I]), (unsigned long long)x);
                 else atomicAdd(reinterpret_cast<double*>(rec + Q::REC_SUM[I]), as_f64(x));
             }
             if constexpr ((FL & F_MIN) != 0) {
-                const uint64_t x = T.mm[(size_t)Q::FE_MIN[I] * T.SL + slot];
+                const uint64_t x = T.mm[(size_t)Q::FE_MIN[I] * T.AC + slot];
                 if (x != ~0ULL) atomicMin(reinterpret_cast<unsigned long long*>(rec + Q::MM_WORD[Q::FE_MIN[I]]), (unsigned long long)x);
             }
             if constexpr ((FL & F_MAX) != 0) {
-                const uint64_t x = T.mm[(size_t)Q::FE_MAX[I] * T.SL + slot];
+                const uint64_t x = T.mm[(size_t)Q::FE_MAX[I] * T.AC + slot];
                 if (x != 0ULL) atomicMax(reinterpret_cast<unsigned long long*>(rec + Q::MM_WORD[Q::FE_MAX[I]]), (unsigned long long)x);
             }
         }
@@ -743,8 +743,14 @@ __device__ __forceinline__ void part_merge_input(const PartTable& T, uint32_t sl
     }
 }
 
-// One tuple into the partition's shared-memory table (find or insert, then shared-memory atomics).
-__device__ __forceinline__ void part_accumulate(const AggArgs& A, const PartTable& T, const uint64_t (&w)[TW]) {
+// One tuple per lane into the partition's shared-memory table (find or insert, then shared-memory atomics).
+// Called by ALL 32 lanes (`valid` = the lane has a tuple). The probe runs in LOCKSTEP: every unresolved lane takes
+// one probe step per iteration and the warp leaves the loop together. Two reasons: (1) a lane that meets a slot being
+// published by another lane of its own warp simply looks again next iteration (by then the publisher, which runs
+// in the same iteration, is done) — a free-running spin could starve the publisher; (2) with free-running loops
+// the compiler emits no reconvergence point and the lanes of a warp drift apart for good (measured: 4 active lanes
+// per instruction). The warp pays for its slowest lane, hence the sparse lookup part (probe sequences of 1-4 slots).
+__device__ __forceinline__ void part_accumulate(const AggArgs& A, const PartTable& T, const uint64_t (&w)[TW], bool valid) {
     uint64_t kw[MAX_KEYS];
 #pragma unroll
     for (int k = 0; k < MAX_KEYS; k++) kw[k] = k < Q::NKEYS ? w[k] : 0;
@@ -754,46 +760,38 @@ __device__ __forceinline__ void part_accumulate(const AggArgs& A, const PartTabl
     uint32_t h = part_hash(kw, nm);
     h ^= h >> 16; h *= 0x85EBCA6Bu; h ^= h >> 13; h *= 0xC2B2AE35u; h ^= h >> 16;
     uint32_t slot = h & (uint32_t)(T.SL - 1);
-    const uint32_t full = 2u | (nm << 8);
-    bool found = false;
-    int spins = 0;
-    for (int probe = 0; probe < 128;) {
-        uint32_t st = *reinterpret_cast<volatile uint32_t*>(T.state + slot);
-        if (st == 0u) {
-            if (*reinterpret_cast<volatile uint32_t*>(T.nfull) >= T.limit) break;
-            const uint32_t old = atomicCAS(T.state + slot, 0u, 1u);
-            if (old == 0u) {
+    uint32_t row = 0xFFFFFFFFu;                 // accumulator row once found
+    bool probing = valid;
+    while (__any_sync(0xffffffffu, probing)) {
+        if (probing) {
+            uint32_t st = *reinterpret_cast<volatile uint32_t*>(T.state + slot);
+            if (st == 0u) {
+                if (*reinterpret_cast<volatile uint32_t*>(T.nfull) >= T.limit) probing = false;       // accumulator rows nearly used up: global path
+                else {
+                    st = atomicCAS(T.state + slot, 0u, 1u);
+                    if (st == 0u) {
+                        row = atomicAdd(T.nfull, 1u);
 #pragma unroll
-                for (int k = 0; k < Q::NKEYS; k++) T.key[(size_t)k * T.SL + slot] = kw[k];
-                __threadfence_block();
-                *reinterpret_cast<volatile uint32_t*>(T.state + slot) = full;
-                atomicAdd(T.nfull, 1u);
-                found = true;
-                break;
+                        for (int k = 0; k < Q::NKEYS; k++) T.key[(size_t)k * T.SL + slot] = kw[k];
+                        __threadfence_block();
+                        *reinterpret_cast<volatile uint32_t*>(T.state + slot) = (row + 2u) | (nm << 24);
+                        probing = false;
+                    }
+                }
             }
-            st = old;
-        }
-        if (st == 1u) {
-            // being published. The publisher may be a lane of THIS warp (two first occurrences of a key side by side):
-            // a bare spin would keep the warp on this path and starve it, so sleep (yields to the other path) and,
-            // if that does not help quickly, send the row to the global table instead
-            if (++spins > 8) break;
-            __nanosleep(40);
-            continue;
-        }
-        if (st == full) {
-            bool eq = true;
+            if (probing && st > 1u) {           // st == 1: being published, look at the same slot again next iteration
+                bool eq = (st >> 24) == nm;
 #pragma unroll
-            for (int k = 0; k < Q::NKEYS; k++) eq &= *reinterpret_cast<volatile uint64_t*>(T.key + (size_t)k * T.SL + slot) == kw[k];
-            if (eq) { found = true; break; }
+                for (int k = 0; k < Q::NKEYS; k++) eq &= *reinterpret_cast<volatile uint64_t*>(T.key + (size_t)k * T.SL + slot) == kw[k];
+                if (eq) { row = (st & 0xFFFFFFu) - 2u; probing = false; }
+                else slot = (slot + 1) & (uint32_t)(T.SL - 1);
+            }
         }
-        slot = (slot + 1) & (uint32_t)(T.SL - 1);
-        probe++;
     }
-    if (found) {
-        if constexpr (Q::CNT0_USED) atomicAdd(T.cnt + slot, 1u);
-        part_accumulate_input<0>(T, slot, meta, w);
-    } else {
+    if (row != 0xFFFFFFFFu) {
+        if constexpr (Q::CNT0_USED) atomicAdd(T.cnt + row, 1u);
+        part_accumulate_input<0>(T, row, meta, w);
+    } else if (valid) {
         uint64_t* rec = table_find_or_insert(A, hash_key(kw, nm, Q::NKEYS), kw, nm);
         part_overflow_input<0>(A, rec, meta, w);
     }
@@ -803,15 +801,16 @@ extern "C" __global__ void __launch_bounds__(PR_THREADS, 1) kq_agg_partition_red
     extern __shared__ __align__(128) unsigned char smem[];
     __shared__ int s_part;
     __shared__ uint32_t s_nfull, s_new;
-    const int SL = A.part_slots;
+    const int SL = A.part_slots, AC = A.part_groups;
     PartTable T;
-    T.SL = SL; T.limit = (uint32_t)(SL - SL / 8); T.nfull = &s_nfull;
+    T.SL = SL; T.AC = AC; T.nfull = &s_nfull;
+    T.limit = AC > PR_THREADS ? (uint32_t)(AC - PR_THREADS) : 0u;      // every thread may have one insert in flight past the check
     T.key = reinterpret_cast<uint64_t*>(smem);
     T.sum = T.key + (size_t)Q::NKEYS * SL;
-    T.mm = T.sum + (size_t)Q::NSUM * SL;
-    T.cnt = reinterpret_cast<uint32_t*>(T.mm + (size_t)Q::NMM * SL);
-    T.state = T.cnt + (size_t)Q::NCNT * SL;
-    const size_t table_bytes = (size_t)SL * (8 * (Q::NKEYS + Q::NSUM + Q::NMM) + 4 * (Q::NCNT + 1));
+    T.mm = T.sum + (size_t)Q::NSUM * AC;
+    T.cnt = reinterpret_cast<uint32_t*>(T.mm + (size_t)Q::NMM * AC);
+    T.state = T.cnt + (size_t)Q::NCNT * AC;
+    const size_t table_bytes = ((size_t)SL * (8 * Q::NKEYS + 4) + (size_t)AC * (8 * (Q::NSUM + Q::NMM) + 4 * Q::NCNT) + 15) / 16 * 16;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     for (;;) {
         __syncthreads();                                    // the previous partition is merged
@@ -829,7 +828,7 @@ extern "C" __global__ void __launch_bounds__(PR_THREADS, 1) kq_agg_partition_red
         __syncthreads();
         const int p = s_part;
         if (p < 0) break;
-        for (int i = tid; i < Q::NMM * SL; i += PR_THREADS) if ((Q::MM_ISMIN >> (i / SL)) & 1u) T.mm[i] = ~0ULL;
+        for (int i = tid; i < Q::NMM * AC; i += PR_THREADS) if ((Q::MM_ISMIN >> (i / AC)) & 1u) T.mm[i] = ~0ULL;
         __syncthreads();
         // the partition's buckets, one warp per bucket; PR_UNROLL tuples per lane in flight
         for (int seg = warp; seg < A.part_ncta; seg += PR_WARPS) {
@@ -841,6 +840,8 @@ extern "C" __global__ void __launch_bounds__(PR_THREADS, 1) kq_agg_partition_red
 #pragma unroll
                 for (int u = 0; u < PR_UNROLL; u++) {
                     const uint32_t i = i0 + 32u * u;
+#pragma unroll
+                    for (int j = 0; j < TW; j++) w[u][j] = 0;
                     if (i < n) {
                         const uint64_t* t = base + (uint64_t)i * TW;
                         if constexpr (TW % 2 == 0) {
@@ -854,9 +855,10 @@ extern "C" __global__ void __launch_bounds__(PR_THREADS, 1) kq_agg_partition_red
                 }
 #pragma unroll
                 for (int u = 0; u < PR_UNROLL; u++) {
-                    if (i0 + 32u * u < n) part_accumulate(A, T, w[u]);
-                    __syncwarp();           // the probe / CAS loops diverge: reconverge before the next tuple (measured: without
-                }                           // this the lanes of a warp drift apart for good, 4 active lanes per instruction)
+                    if (b0 + 32u * u >= n) break;                          // warp-uniform
+                    part_accumulate(A, T, w[u], i0 + 32u * u < n);
+                    __syncwarp();
+                }
             }
         }
         __syncthreads();
@@ -864,13 +866,13 @@ extern "C" __global__ void __launch_bounds__(PR_THREADS, 1) kq_agg_partition_red
         uint32_t fresh = 0;
         for (int slot = tid; slot < SL; slot += PR_THREADS) {
             const uint32_t st = T.state[slot];
-            if ((st & 0xffu) != 2u) continue;
+            if (st < 2u) continue;
             uint64_t kw[MAX_KEYS];
 #pragma unroll
             for (int k = 0; k < MAX_KEYS; k++) kw[k] = k < Q::NKEYS ? T.key[(size_t)k * SL + slot] : 0;
-            const uint32_t nm = st >> 8;
+            const uint32_t nm = st >> 24;
             uint64_t* rec = table_find_or_insert(A, hash_key(kw, nm, Q::NKEYS), kw, nm, &fresh);
-            part_merge_input<0>(T, (uint32_t)slot, rec);
+            part_merge_input<0>(T, (st & 0xFFFFFFu) - 2u, rec);
         }
         if (fresh) atomicAdd(&s_new, fresh);
         __syncthreads();
