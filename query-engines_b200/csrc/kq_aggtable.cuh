@@ -41,6 +41,11 @@ __device__ __forceinline__ uint64_t hash_key(const uint64_t (&kw)[MAX_KEYS], uin
     return mix64(h);
 }
 
+// Home slot of a hash: its TOP bits. The partitioned path (kq_k_agg.cuh) partitions rows by the top bits of the same
+// hash, so the groups of one partition live in one contiguous region of the table (plus what linear probing spills
+// into the next): its merge works on an L2-resident slice instead of random HBM lines.
+__device__ __forceinline__ uint64_t table_home(uint64_t h, uint64_t cap_mask) { return h >> __clzll((long long)cap_mask); }
+
 // Find the record of (kw, nullmask) in the global table, inserting it if absent. Claim protocol:
 // CAS header EMPTY -> BUSY|nullmask, write keys + accumulator identities, fence, publish FULL.
 // The table never fills up: the host sizes it so that ngroups stays below capacity/2 plus margin.
@@ -48,7 +53,7 @@ __device__ __forceinline__ uint64_t hash_key(const uint64_t (&kw)[MAX_KEYS], uin
 // grid serialises in the L2 (10 M inserts cost milliseconds); callers add their tally to A.ngroups in bulk.
 __device__ __forceinline__ uint64_t* table_find_or_insert(const AggArgs& A, uint64_t h, const uint64_t (&kw)[MAX_KEYS], uint32_t nullmask,
                                                           uint32_t* inserted = nullptr) {
-    uint64_t slot = h & A.cap_mask;
+    uint64_t slot = table_home(h, A.cap_mask);
     const uint64_t full_hdr = HDR_FULL | ((uint64_t)nullmask << 32);
     while (true) {
         uint64_t* rec = A.table + slot * (uint64_t)A.stride;
@@ -60,7 +65,7 @@ __device__ __forceinline__ uint64_t* table_find_or_insert(const AggArgs& A, uint
                 for (int w = 1 + A.nkeys; w < A.stride; w++) rec[w] = A.rec_init[w];
 #pragma unroll
                 for (int k = 0; k < MAX_KEYS; k++) if (k < A.nkeys) rec[1 + k] = kw[k];
-                __threadfence();
+                asm volatile("fence.acq_rel.gpu;" ::: "memory");      // release: keys and identities before the header (a full fence.sc costs more)
                 *reinterpret_cast<volatile uint64_t*>(rec) = full_hdr;
                 if (inserted) ++*inserted; else atomicAdd(A.ngroups, 1ULL);
                 return rec;

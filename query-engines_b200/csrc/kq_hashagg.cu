@@ -41,7 +41,7 @@ __global__ void k_rehash(const uint64_t* __restrict__ old_table, uint64_t old_ca
         uint64_t kw[MAX_KEYS];
 #pragma unroll
         for (int k = 0; k < MAX_KEYS; k++) kw[k] = k < nkeys ? src[1 + k] : 0;
-        uint64_t slot = hash_key(kw, (uint32_t)(src[0] >> 32), nkeys) & cap_mask;
+        uint64_t slot = table_home(hash_key(kw, (uint32_t)(src[0] >> 32), nkeys), cap_mask);
         while (true) {
             uint64_t* rec = table + slot * stride;
             if (atomicCAS(reinterpret_cast<unsigned long long*>(rec), 0ULL, (unsigned long long)src[0]) == 0ULL) {
@@ -504,6 +504,13 @@ static int plan_agg(kq_ctx* ctx, kq_hashagg* h, kq_batch* input, int smem_optin,
         return std::max(0, std::min(FE_MAX_GROUPS, budget / per_group - 1));
     };
     const char* forced = getenv("KQ_AGG_GEOM");
+    if (mode == 2) {
+        // mid cardinality: block-shared table; many warps hide the latency of its shared-memory atomics
+        geo = forced ? agg_geometry(NI) : AggGeometry{4, 15};
+        stage_defs = cg.plan_stages(64 * 1024, 1, geo.tile(), &A.sp, true);
+        A.sp.nstages = std::max(1, std::min(A.sp.nstages, AGG_MAX_STAGES));
+        fg = 0; dir_slots = 4;
+    }
     if (mode == 1) {
         // pass 1 of the partitioned path: no lane-private state, so many warps (latency of the shared-memory cursor
         // atomics and of the scattered stores is hidden by occupancy) and a deep stage ring
@@ -513,7 +520,7 @@ static int plan_agg(kq_ctx* ctx, kq_hashagg* h, kq_batch* input, int smem_optin,
         fg = 0; dir_slots = 4;
     }
     for (const AggGeometry& g : CANDIDATES) {
-        if (mode == 1) break;
+        if (mode != 0) break;
         const AggGeometry cand = forced ? agg_geometry(NI) : g;
         StagePlan sp; std::string defs; int dir;
         const int f = try_geometry(cand, &sp, &defs, &dir);
@@ -533,12 +540,17 @@ static int plan_agg(kq_ctx* ctx, kq_hashagg* h, kq_batch* input, int smem_optin,
     {   // pass-2 table: a sparse LOOKUP part (state + key words per slot, power-of-two slots, <= 45 % full so that probe
         // sequences stay short) pointing into a dense ACCUMULATOR part (one row of counts / sums / extremes per distinct key)
         const int lookup_bytes = 4 + 8 * NK, acc_bytes = 4 * ncnt + 8 * ns + 8 * nm;
-        int sl = 512;
-        auto bytes_for = [&](int slots) { return slots * lookup_bytes + (slots * 45 / 100 / 4 * 4) * acc_bytes; };
-        while (sl < 16384 && bytes_for(sl * 2) <= smem_optin - 4096) sl <<= 1;
+        // mode 2: the table shares the block's shared memory with the stage ring and the (empty) front end
+        const int avail = mode == 2 ? smem_optin - 2048 - A.smem_bytes : smem_optin - 4096;
+        int sl = 256;
+        while (sl < 16384 && sl * 2 * lookup_bytes <= avail * 62 / 100) sl <<= 1;
+        const int ac = std::min(sl / 2, (avail - sl * lookup_bytes) / acc_bytes) / 4 * 4;       // accumulator rows: lookup part at most half full
+        if (ac < 64) { if (mode == 2) return kq_fail(ctx, KQ_ERR_UNSUPPORTED, "aggregate record too wide for the shared-memory table"); }
         A.part_slots = sl;
-        A.part_groups = sl * 45 / 100 / 4 * 4;
-        if (reduce_smem) *reduce_smem = (bytes_for(sl) + 15) / 16 * 16;
+        A.part_groups = std::max(ac, 0);
+        const int table_bytes = (sl * lookup_bytes + std::max(ac, 0) * acc_bytes + 15) / 16 * 16;
+        if (reduce_smem) *reduce_smem = table_bytes;
+        if (mode == 2) A.smem_bytes = (A.smem_bytes + 32 + table_bytes + 127) / 128 * 128;
         int tw = NK + ((keys_nullable || ncnt > 1) ? 1 : 0);
         for (int i = 0; i < NI; i++) if (h->in[i].flags & (F_SUM | F_MIN | F_MAX)) tw++;
         A.part_tw = std::max(1, tw);
@@ -598,7 +610,7 @@ static int hashagg_update_partitioned(kq_ctx* ctx, kq_hashagg* h, kq_batch* inpu
     int reduce_smem = 0;
     KQ_RET(plan_agg(ctx, h, input, ctx->max_smem_optin, A, &defines, &gen, 1, 512, &reduce_smem));
     int nparts = 512;
-    while (nparts < 4096 && (int64_t)nparts * A.part_groups * 7 / 10 < g_est) nparts <<= 1;       // partitions ~70 % of what a table holds
+    while (nparts < 4096 && (int64_t)nparts * (A.part_groups - 512) * 7 / 10 < g_est) nparts <<= 1;       // partitions ~70 % of what a table holds
     if (const char* e = getenv("KQ_PARTS")) { int v = atoi(e); if (v >= 16 && v <= 8192 && (v & (v - 1)) == 0) nparts = v; }
     memset(&A, 0, sizeof A);
     KQ_RET(plan_agg(ctx, h, input, ctx->max_smem_optin, A, &defines, &gen, 1, nparts, &reduce_smem));
@@ -657,7 +669,7 @@ static int hashagg_update_partitioned(kq_ctx* ctx, kq_hashagg* h, kq_batch* inpu
         const int64_t taken = std::min<int64_t>((int64_t)(uint32_t)c[1], tile_end - tile_begin);
         const uint64_t max_bucket = c[3];
         // ---- pass 2: reduce the partitions; a block in flight may add up to one partition's rows as new groups
-        const uint64_t margin2 = (uint64_t)std::min<int64_t>(grid, nparts) * std::max<uint64_t>(1, max_bucket * (uint64_t)grid);
+        const uint64_t margin2 = (uint64_t)std::min<int64_t>(ctx->sm_count, nparts) * std::max<uint64_t>(1, max_bucket * (uint64_t)grid);
         int part_begin = 0;
         while (part_begin < nparts) {
             uint64_t cap = h->capacity;
@@ -693,8 +705,17 @@ int kq_hashagg_update(kq_ctx* ctx, kq_hashagg* h, kq_batch* input) {
     std::string defines, gen;
     // High cardinality (planner hint, or learnt from earlier batches): the partitioned path.
     const int64_t g_est = std::max<int64_t>(h->expected_groups, h->ngroups_host);
-    if (g_est >= PART_MIN_GROUPS && n >= PART_MIN_ROWS && !getenv("KQ_NO_PARTITION")) return hashagg_update_partitioned(ctx, h, input, n, g_est);
-    KQ_RET(plan_agg(ctx, h, input, ctx->max_smem_optin, A, &defines, &gen));
+    const int64_t part_min_groups = getenv("KQ_PART_MIN_GROUPS") ? atoll(getenv("KQ_PART_MIN_GROUPS")) : PART_MIN_GROUPS;      // tuning experiments
+    if (g_est >= part_min_groups && n >= PART_MIN_ROWS && !getenv("KQ_NO_PARTITION")) return hashagg_update_partitioned(ctx, h, input, n, g_est);
+    // Mid cardinality (more groups than the lane-private front end holds, few enough for one shared-memory table per block)
+    int mode = 0;
+    if (g_est > FE_MAX_GROUPS && !getenv("KQ_NO_SHARED_TABLE")) {
+        AggArgs P;
+        memset(&P, 0, sizeof P);
+        std::string d2, g2;
+        if (plan_agg(ctx, h, input, ctx->max_smem_optin, P, &d2, &g2, 2) == KQ_OK && g_est <= (int64_t)(P.part_groups - 32 * (P.geo_warps + 1)) * 9 / 10) mode = 2;
+    }
+    KQ_RET(plan_agg(ctx, h, input, ctx->max_smem_optin, A, &defines, &gen, mode));
     if (n == 0) return KQ_OK;
     const AggGeometry geo{A.geo_r, A.geo_warps};
     const int TILE = geo.tile(), THREADS = geo.threads();
@@ -753,8 +774,8 @@ int kq_explain_hashagg(kq_expr* pred, kq_expr* const* group_exprs, int ngroup, c
     AggArgs A;
     memset(&A, 0, sizeof A);
     std::string defines, gen;
-    const char* ep = getenv("KQ_EXPLAIN_PARTS");          // tuning aid: compile the partitioned path's kernels instead
-    if (st == KQ_OK) st = plan_agg(&fake, h, &sb.batch, 232448, A, &defines, &gen, ep ? 1 : 0, ep ? atoi(ep) : 0);
+    const char* ep = getenv("KQ_EXPLAIN_PARTS");          // tuning aid: compile the partitioned path's kernels instead (0: the block-shared table mode)
+    if (st == KQ_OK) st = plan_agg(&fake, h, &sb.batch, 232448, A, &defines, &gen, ep ? (atoi(ep) > 0 ? 1 : 2) : 0, ep ? atoi(ep) : 0);
     if (st == KQ_OK && compile) st = kq_jit_compile_only(&fake, defines, gen, KQ_SKEL_AGG);
     kq_copy_text(st == KQ_OK ? defines + gen : fake.last_error, source, source_cap);
     if (h) hashagg_delete_host(h);

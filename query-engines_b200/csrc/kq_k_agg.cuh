@@ -324,7 +324,7 @@ __device__ __forceinline__ void global_path_batched(const AggArgs& A, const AggS
         uint64_t kw[MAX_KEYS];
 #pragma unroll
         for (int k2 = 0; k2 < MAX_KEYS; k2++) kw[k2] = k2 < Q::NKEYS ? sink.key[k2][r] : 0;
-        rec[r] = A.table + (hash_key(kw, nm[r], Q::NKEYS) & A.cap_mask) * (uint64_t)A.stride;
+        rec[r] = A.table + table_home(hash_key(kw, nm[r], Q::NKEYS), A.cap_mask) * (uint64_t)A.stride;
     }
     constexpr bool PAIRED = Q::NIN == 1 && Q::MM_PAIRED;
     ulonglong2 mmv[R];
@@ -393,9 +393,8 @@ __host__ __device__ constexpr int tuple_in_word(int i) {
     return w;
 }
 constexpr int TW = tuple_in_word(Q::NIN) > 0 ? tuple_in_word(Q::NIN) : 1;
-// 32-bit multiplicative hash of a key: its TOP bits choose the partition (pass 1); pass 2 runs it through a
-// bijective finaliser for the shared-memory slot, so keys that share a partition still spread over the table.
-// (The 64-bit hash_key of the global table is only computed per distinct key, at merge time.)
+// 32-bit multiplicative hash of a key for the shared-memory table of pass 2 / of the block-shared front end: a different
+// function from hash_key, whose top bits are equal for all keys of a partition.
 __device__ __forceinline__ uint32_t part_hash(const uint64_t (&kw)[MAX_KEYS], uint32_t nullmask) {
     uint32_t h = Q::KEYS_NULLABLE ? nullmask * 0xC2B2AE35u : 0u;
 #pragma unroll
@@ -419,7 +418,7 @@ __device__ __forceinline__ uint32_t partition_scatter(const AggArgs& A, uint32_t
             uint64_t kw[MAX_KEYS];
 #pragma unroll
             for (int k2 = 0; k2 < MAX_KEYS; k2++) kw[k2] = k2 < Q::NKEYS ? sink.key[k2][r] : 0;
-            part[r] = part_hash(kw, nm[r]) >> (32 - A.part_log2);
+            part[r] = (uint32_t)(hash_key(kw, nm[r], Q::NKEYS) >> (64 - A.part_log2));      // = top bits of the key's home slot in the global table
             pos[r] = atoms_inc(a_cursor + part[r] * 4u);
         }
     }
@@ -451,6 +450,240 @@ __device__ __forceinline__ uint32_t partition_scatter(const AggArgs& A, uint32_t
     return overflow;
 }
 
+#if KQ_AGG_MODE >= 1
+struct PartTable {            // hash table in shared memory: sparse lookup part (SL slots) -> dense accumulator rows (AC)
+    uint32_t* state;          // [SL] 0 empty, 1 being published, else (accumulator row + 2) | key null mask << 24
+    uint64_t* key;            // [NKEYS][SL]
+    uint64_t* sum;            // [NSUM][AC]
+    uint64_t* mm;             // [NMM][AC]  order-mapped MIN/MAX
+    uint32_t* cnt;            // [NCNT][AC] row 0: rows (statically non-null inputs), else one per nullable input
+    uint32_t* nfull;          // accumulator rows handed out
+    int SL, AC;
+    uint32_t limit;           // stop inserting at this many rows (every thread may have one insert in flight)
+};
+
+template <int I>
+__device__ __forceinline__ void part_accumulate_input(const PartTable& T, uint32_t slot, uint32_t meta, const uint64_t (&w)[TW]) {
+    if constexpr (I < Q::NIN) {
+        constexpr int FL = Q::IN_FLAGS[I];
+        const bool valid = Q::IN_CNT[I] > 0 ? ((meta >> (8 + I)) & 1u) != 0 : true;
+        if (valid) {
+            if constexpr (Q::IN_CNT[I] > 0) atomicAdd(T.cnt + (size_t)Q::IN_CNT[I] * T.AC + slot, 1u);
+            if constexpr ((FL & (F_SUM | F_MIN | F_MAX)) != 0) {
+                const uint64_t v = w[tuple_in_word(I)];
+                if constexpr ((FL & F_SUM) != 0) {
+                    uint64_t* p = T.sum + (size_t)Q::FE_SUM[I] * T.AC + slot;
+                    if constexpr ((FL & F_INT) != 0) atomicAdd(reinterpret_cast<unsigned long long*>(p), (unsigned long long)v);
+                    else atomicAdd(reinterpret_cast<double*>(p), as_f64(v));
+                }
+                if constexpr ((FL & (F_MIN | F_MAX)) != 0) {
+                    constexpr bool is_int = (FL & F_INT) != 0;
+                    const uint64_t m = order_map(is_int ? v : canon_nan(v), is_int);
+                    if constexpr ((FL & F_MIN) != 0) {
+                        uint64_t* p = T.mm + (size_t)Q::FE_MIN[I] * T.AC + slot;
+                        if (m < *reinterpret_cast<volatile uint64_t*>(p)) atomicMin(reinterpret_cast<unsigned long long*>(p), (unsigned long long)m);
+                    }
+                    if constexpr ((FL & F_MAX) != 0) {
+                        uint64_t* p = T.mm + (size_t)Q::FE_MAX[I] * T.AC + slot;
+                        if (m > *reinterpret_cast<volatile uint64_t*>(p)) atomicMax(reinterpret_cast<unsigned long long*>(p), (unsigned long long)m);
+                    }
+                }
+            }
+        }
+        part_accumulate_input<I + 1>(T, slot, meta, w);
+    }
+}
+template <int I>
+__device__ __forceinline__ void part_overflow_input(const AggArgs& A, uint64_t* rec, uint32_t meta, const uint64_t (&w)[TW]) {
+    if constexpr (I < Q::NIN) {
+        const bool valid = Q::IN_CNT[I] > 0 ? ((meta >> (8 + I)) & 1u) != 0 : true;
+        if (valid) global_accumulate(rec, A.in[I], (Q::IN_FLAGS[I] & (F_SUM | F_MIN | F_MAX)) ? w[tuple_in_word(I)] : 0ULL);
+        part_overflow_input<I + 1>(A, rec, meta, w);
+    }
+}
+// OWNED: the record was claimed by this thread and is not published yet — plain stores instead of atomics.
+template <int I, bool OWNED = false>
+__device__ __forceinline__ void part_merge_input(const PartTable& T, uint32_t slot, uint64_t* rec) {
+    if constexpr (I < Q::NIN) {
+        constexpr int FL = Q::IN_FLAGS[I];
+        const uint32_t n = T.cnt[(size_t)Q::IN_CNT[I] * T.AC + slot];
+        if constexpr (OWNED) {
+            rec[Q::REC_NN[I]] = n;
+            if constexpr ((FL & F_SUM) != 0) rec[Q::REC_SUM[I]] = n ? T.sum[(size_t)Q::FE_SUM[I] * T.AC + slot] : 0ULL;
+            if constexpr ((FL & F_MIN) != 0) rec[Q::MM_WORD[Q::FE_MIN[I]]] = T.mm[(size_t)Q::FE_MIN[I] * T.AC + slot];      // identity ~0 when no value was seen
+            if constexpr ((FL & F_MAX) != 0) rec[Q::MM_WORD[Q::FE_MAX[I]]] = T.mm[(size_t)Q::FE_MAX[I] * T.AC + slot];      // identity 0
+        } else if (n) {
+            atomicAdd(reinterpret_cast<unsigned long long*>(rec + Q::REC_NN[I]), (unsigned long long)n);
+            if constexpr ((FL & F_SUM) != 0) {
+                const uint64_t x = T.sum[(size_t)Q::FE_SUM[I] * T.AC + slot];
+                if constexpr ((FL & F_INT) != 0) atomicAdd(reinterpret_cast<unsigned long long*>(rec + Q::REC_SUM[I]), (unsigned long long)x);
+                else atomicAdd(reinterpret_cast<double*>(rec + Q::REC_SUM[I]), as_f64(x));
+            }
+            if constexpr ((FL & F_MIN) != 0) {
+                const uint64_t x = T.mm[(size_t)Q::FE_MIN[I] * T.AC + slot];
+                if (x != ~0ULL) atomicMin(reinterpret_cast<unsigned long long*>(rec + Q::MM_WORD[Q::FE_MIN[I]]), (unsigned long long)x);
+            }
+            if constexpr ((FL & F_MAX) != 0) {
+                const uint64_t x = T.mm[(size_t)Q::FE_MAX[I] * T.AC + slot];
+                if (x != 0ULL) atomicMax(reinterpret_cast<unsigned long long*>(rec + Q::MM_WORD[Q::FE_MAX[I]]), (unsigned long long)x);
+            }
+        }
+        part_merge_input<I + 1, OWNED>(T, slot, rec);
+    }
+}
+
+// One tuple per lane into the partition's shared-memory table (find or insert, then shared-memory atomics).
+// Called by ALL 32 lanes (`valid` = the lane has a tuple). The probe runs in LOCKSTEP: every unresolved lane takes
+// one probe step per iteration and the warp leaves the loop together. Two reasons: (1) a lane that meets a slot being
+// published by another lane of its own warp simply looks again next iteration (by then the publisher, which runs
+// in the same iteration, is done) — a free-running spin could starve the publisher; (2) with free-running loops
+// the compiler emits no reconvergence point and the lanes of a warp drift apart for good (measured: 4 active lanes
+// per instruction). The warp pays for its slowest lane, hence the sparse lookup part (probe sequences of 1-4 slots).
+__device__ __forceinline__ void part_accumulate(const AggArgs& A, const PartTable& T, const uint64_t (&w)[TW], bool valid) {
+    uint64_t kw[MAX_KEYS];
+#pragma unroll
+    for (int k = 0; k < MAX_KEYS; k++) kw[k] = k < Q::NKEYS ? w[k] : 0;
+    const uint32_t meta = TUPLE_META ? (uint32_t)w[Q::NKEYS] : 0u;
+    const uint32_t nm = meta & 0xffu;
+    // slot hash: independent of the partition bits (top bits of hash_key); finaliser so that low bits are well mixed
+    uint32_t h = part_hash(kw, nm);
+    h ^= h >> 16; h *= 0x85EBCA6Bu; h ^= h >> 13; h *= 0xC2B2AE35u; h ^= h >> 16;
+    uint32_t slot = h & (uint32_t)(T.SL - 1);
+    uint32_t row = 0xFFFFFFFFu;                 // accumulator row once found
+    bool probing = valid;
+    while (__any_sync(0xffffffffu, probing)) {
+        if (probing) {
+            uint32_t st = *reinterpret_cast<volatile uint32_t*>(T.state + slot);
+            if (st == 0u) {
+                if (*reinterpret_cast<volatile uint32_t*>(T.nfull) >= T.limit) probing = false;       // accumulator rows nearly used up: global path
+                else {
+                    st = atomicCAS(T.state + slot, 0u, 1u);
+                    if (st == 0u) {
+                        row = atomicAdd(T.nfull, 1u);
+#pragma unroll
+                        for (int k = 0; k < Q::NKEYS; k++) T.key[(size_t)k * T.SL + slot] = kw[k];
+                        __threadfence_block();
+                        *reinterpret_cast<volatile uint32_t*>(T.state + slot) = (row + 2u) | (nm << 24);
+                        probing = false;
+                    }
+                }
+            }
+            if (probing && st > 1u) {           // st == 1: being published, look at the same slot again next iteration
+                bool eq = (st >> 24) == nm;
+#pragma unroll
+                for (int k = 0; k < Q::NKEYS; k++) eq &= *reinterpret_cast<volatile uint64_t*>(T.key + (size_t)k * T.SL + slot) == kw[k];
+                if (eq) { row = (st & 0xFFFFFFu) - 2u; probing = false; }
+                else slot = (slot + 1) & (uint32_t)(T.SL - 1);
+            }
+        }
+    }
+    if (row != 0xFFFFFFFFu) {
+        if constexpr (Q::CNT0_USED) atomicAdd(T.cnt + row, 1u);
+        part_accumulate_input<0>(T, row, meta, w);
+    } else if (valid) {
+        uint64_t* rec = table_find_or_insert(A, hash_key(kw, nm, Q::NKEYS), kw, nm);
+        part_overflow_input<0>(A, rec, meta, w);
+    }
+}
+
+// Merge the shared-memory table into the global one: once per distinct key. `fresh` counts the groups this thread added.
+// Up to MK table entries per thread are merged TOGETHER: the header loads, the claiming CAS and the accumulator atomics
+// of all of them are in flight at once (one entry at a time is a chain of four dependent L2/HBM round trips), and one
+// fence covers all the records the thread publishes.
+// ONLY for pass 2 of the partitioned path: there a partition's keys belong to one block, so no other thread inserts the
+// SAME key while this runs and a slot that is BUSY (being published, necessarily with another key) is treated like any
+// occupied slot — nobody waits while holding a claim, which is what makes several claims per thread deadlock-free.
+template <int MK>
+__device__ __forceinline__ void part_merge_table_batched(const AggArgs& A, const PartTable& T, int tid, int nthreads, uint32_t& fresh) {
+    constexpr int NK1 = Q::NKEYS > 0 ? Q::NKEYS : 1;
+    uint64_t* const tab_end = A.table + (A.cap_mask + 1) * (uint64_t)A.stride;
+    for (int base = 0; base < T.SL; base += nthreads * MK) {
+        uint64_t* rec[MK];
+        uint64_t key[MK][NK1];
+        uint32_t row[MK], nmv[MK];
+        uint32_t have = 0;
+#pragma unroll
+        for (int j = 0; j < MK; j++) {
+            const int slot = base + j * nthreads + tid;
+            const uint32_t st = slot < T.SL ? T.state[slot] : 0u;
+            row[j] = 0; nmv[j] = 0; rec[j] = A.table;
+#pragma unroll
+            for (int k = 0; k < NK1; k++) key[j][k] = 0;
+            if (st >= 2u) {
+                have |= 1u << j;
+                uint64_t kw[MAX_KEYS];
+#pragma unroll
+                for (int k = 0; k < MAX_KEYS; k++) kw[k] = k < Q::NKEYS ? T.key[(size_t)k * T.SL + slot] : 0;
+#pragma unroll
+                for (int k = 0; k < Q::NKEYS; k++) key[j][k] = kw[k];
+                nmv[j] = st >> 24; row[j] = (st & 0xFFFFFFu) - 2u;
+                rec[j] = A.table + table_home(hash_key(kw, nmv[j], Q::NKEYS), A.cap_mask) * (uint64_t)A.stride;
+            }
+        }
+        // Every probe is ONE atomic round trip: CAS(EMPTY -> BUSY) either claims the slot or returns the header that is there
+        // (a separate load first would double the latency of the common case, an empty home slot).
+        uint32_t pend = have, mine = 0;
+        while (pend) {
+            uint64_t hdr[MK];
+#pragma unroll
+            for (int j = 0; j < MK; j++)        // all CAS in flight before the first result is looked at
+                if ((pend >> j) & 1u) hdr[j] = atomicCAS(reinterpret_cast<unsigned long long*>(rec[j]), 0ULL, HDR_BUSY | ((uint64_t)nmv[j] << 32));
+#pragma unroll
+            for (int j = 0; j < MK; j++) {
+                if (!((pend >> j) & 1u)) continue;
+                if (hdr[j] == 0ULL) { mine |= 1u << j; pend &= ~(1u << j); continue; }            // claimed: ours to fill in
+                bool eq = hdr[j] == (HDR_FULL | ((uint64_t)nmv[j] << 32));
+                if (eq) {
+#pragma unroll
+                    for (int k = 0; k < Q::NKEYS; k++) eq &= __ldcg(rec[j] + 1 + k) == key[j][k];
+                }
+                if (eq) pend &= ~(1u << j);                                                       // the group exists already
+                else { uint64_t* p = rec[j] + A.stride; rec[j] = p == tab_end ? A.table : p; }    // another key, or one being published
+            }
+        }
+        // claimed records: keys and the final accumulator values with plain stores, ONE fence, then the headers
+#pragma unroll
+        for (int j = 0; j < MK; j++) {
+            if (!((mine >> j) & 1u)) continue;
+            for (int w = 1 + Q::NKEYS; w < A.stride; w++) rec[j][w] = A.rec_init[w];
+#pragma unroll
+            for (int k = 0; k < Q::NKEYS; k++) rec[j][1 + k] = key[j][k];
+            part_merge_input<0, true>(T, row[j], rec[j]);
+        }
+        if (mine) asm volatile("fence.acq_rel.gpu;" ::: "memory");
+#pragma unroll
+        for (int j = 0; j < MK; j++)
+            if ((mine >> j) & 1u) { *reinterpret_cast<volatile uint64_t*>(rec[j]) = HDR_FULL | ((uint64_t)nmv[j] << 32); fresh++; }
+#pragma unroll
+        for (int j = 0; j < MK; j++) if (((have & ~mine) >> j) & 1u) part_merge_input<0>(T, row[j], rec[j]);
+    }
+}
+__device__ __forceinline__ void part_merge_table(const AggArgs& A, const PartTable& T, int tid, int nthreads, uint32_t& fresh) {
+    for (int slot = tid; slot < T.SL; slot += nthreads) {
+        const uint32_t st = T.state[slot];
+        if (st < 2u) continue;
+        uint64_t kw[MAX_KEYS];
+#pragma unroll
+        for (int k = 0; k < MAX_KEYS; k++) kw[k] = k < Q::NKEYS ? T.key[(size_t)k * T.SL + slot] : 0;
+        const uint32_t nm = st >> 24;
+        uint64_t* rec = table_find_or_insert(A, hash_key(kw, nm, Q::NKEYS), kw, nm, &fresh);
+        part_merge_input<0>(T, (st & 0xFFFFFFu) - 2u, rec);
+    }
+}
+// Carve the table out of shared memory at p (16-byte aligned); returns its size in bytes (multiple of 16).
+__device__ __forceinline__ size_t part_table_place(PartTable& T, unsigned char* p, int SL, int AC, int nthreads, uint32_t* nfull) {
+    T.SL = SL; T.AC = AC; T.nfull = nfull;
+    T.limit = AC > nthreads ? (uint32_t)(AC - nthreads) : 0u;      // every thread may have one insert in flight past the check
+    T.key = reinterpret_cast<uint64_t*>(p);
+    T.sum = T.key + (size_t)Q::NKEYS * SL;
+    T.mm = T.sum + (size_t)Q::NSUM * AC;
+    T.cnt = reinterpret_cast<uint32_t*>(T.mm + (size_t)Q::NMM * AC);
+    T.state = T.cnt + (size_t)Q::NCNT * AC;
+    return ((size_t)SL * (8 * Q::NKEYS + 4) + (size_t)AC * (8 * (Q::NSUM + Q::NMM) + 4 * Q::NCNT) + 15) / 16 * 16;
+}
+
+#endif  // KQ_AGG_MODE >= 1
+
 extern "C" __global__ void __launch_bounds__(THREADS, 1) kq_hash_aggregate(const __grid_constant__ AggArgs A) {
     // shared memory: [S stages][directory][gslot][gid2slot][mm][per-warp sums][per-warp counts]
     extern __shared__ __align__(128) unsigned char smem[];
@@ -474,6 +707,14 @@ extern "C" __global__ void __launch_bounds__(THREADS, 1) kq_hash_aggregate(const
     p0 = smem + (((size_t)(p0 - smem) + 15) & ~(size_t)15);
     uint32_t* part_cursor = reinterpret_cast<uint32_t*>(p0);   // pass 1 of the partitioned path: tuples appended per partition
     if (KQ_AGG_MODE == 1) p0 += (size_t)A.nparts * 4;
+#if KQ_AGG_MODE == 2
+    // mid cardinality: ONE block-shared table (sparse lookup part + accumulator rows, shared-memory atomics) instead of
+    // the lane-private front end, which only holds a few dozen groups; merged into the global table at block exit
+    __shared__ uint32_t s_tab_nfull;
+    PartTable T2;
+    p0 += part_table_place(T2, p0, A.part_slots, A.part_groups, THREADS, &s_tab_nfull);
+    if (threadIdx.x == 0) s_tab_nfull = 0;
+#endif
     const size_t fe_end = (size_t)(p0 - smem);
     fe.dir_count = &s_dir_count;
     fe.sum = sum0 + (size_t)(warp < 0 ? 0 : warp) * FG1 * NSUM * 32;
@@ -487,6 +728,9 @@ extern "C" __global__ void __launch_bounds__(THREADS, 1) kq_hash_aggregate(const
     }
     __syncthreads();
     for (int i = threadIdx.x; i < FG1 * NMM; i += THREADS) fe.mm[i] = ((Q::MM_ISMIN >> (i % (NMM > 0 ? NMM : 1))) & 1u) ? ~0ULL : 0ULL;
+#if KQ_AGG_MODE == 2
+    for (int i = threadIdx.x; i < NMM * T2.AC; i += THREADS) if ((Q::MM_ISMIN >> (i / T2.AC)) & 1u) T2.mm[i] = ~0ULL;
+#endif
     __syncthreads();
 
     if (wid == PRODUCER_WARP) {
@@ -588,7 +832,30 @@ extern "C" __global__ void __launch_bounds__(THREADS, 1) kq_hash_aggregate(const
             if (KQ_AGG_MODE == 1) {
                 if (slow) slow = partition_scatter(A, smem_u32(part_cursor), sink, nm, slow);
                 if (slow) global_path_batched(A, sink, nm, slow, new_groups);          // bucket full (skewed keys)
-            } else if (bypass && KQ_GLOBAL_BATCHED) {
+            }
+#if KQ_AGG_MODE == 2
+            else if (true) {
+#pragma unroll
+                for (int r = 0; r < R; r++) {           // all 32 lanes: the table probe runs in lockstep
+                    uint64_t w[TW];
+#pragma unroll
+                    for (int j = 0; j < TW; j++) w[j] = 0;
+#pragma unroll
+                    for (int k2 = 0; k2 < Q::NKEYS; k2++) w[k2] = sink.key[k2][r];
+                    if constexpr (TUPLE_META) {
+                        uint32_t meta = nm[r];
+#pragma unroll
+                        for (int i = 0; i < Q::NIN; i++) meta |= ((sink.inok[i] >> r) & 1u) << (8 + i);
+                        w[Q::NKEYS] = meta;
+                    }
+#pragma unroll
+                    for (int i = 0; i < Q::NIN; i++) if (Q::IN_FLAGS[i] & (F_SUM | F_MIN | F_MAX)) w[tuple_in_word(i)] = sink.in[i][r];
+                    part_accumulate(A, T2, w, (slow >> r) & 1u);
+                    __syncwarp();
+                }
+            }
+#endif
+            else if (bypass && KQ_GLOBAL_BATCHED) {
                 if (slow) global_path_batched(A, sink, nm, slow, new_groups);
             } else if (slow) {
 #pragma unroll
@@ -630,6 +897,14 @@ extern "C" __global__ void __launch_bounds__(THREADS, 1) kq_hash_aggregate(const
         for (int p = threadIdx.x; p < A.nparts; p += THREADS)
             A.part_counts[(size_t)p * A.part_ncta + blockIdx.x] = min(part_cursor[p], (uint32_t)A.part_cap);
     }
+#if KQ_AGG_MODE == 2
+    {
+        uint32_t fresh = 0;
+        part_merge_table(A, T2, threadIdx.x, THREADS, fresh);
+        const uint32_t tot = __reduce_add_sync(0xffffffffu, fresh);
+        if (lane == 0 && tot) atomicAdd(A.ngroups, (unsigned long long)tot);
+    }
+#endif
     const int G = min((int)s_dir_count, FG);
     for (int g = threadIdx.x; g < G; g += THREADS) {
         const uint64_t* e = fe.dir + (size_t)fe.gid2slot[g] * ENTRY_WORDS;
@@ -668,161 +943,25 @@ extern "C" __global__ void __launch_bounds__(THREADS, 1) kq_hash_aggregate(const
 // ---- pass 2 of the partitioned path ------------------------------------------------------------------------------------
 constexpr int PR_THREADS = 512, PR_WARPS = PR_THREADS / 32, PR_UNROLL = 4;
 
-struct PartTable {            // hash table in shared memory: sparse lookup part (SL slots) -> dense accumulator rows (AC)
-    uint32_t* state;          // [SL] 0 empty, 1 being published, else (accumulator row + 2) | key null mask << 24
-    uint64_t* key;            // [NKEYS][SL]
-    uint64_t* sum;            // [NSUM][AC]
-    uint64_t* mm;             // [NMM][AC]  order-mapped MIN/MAX
-    uint32_t* cnt;            // [NCNT][AC] row 0: rows (statically non-null inputs), else one per nullable input
-    uint32_t* nfull;          // accumulator rows handed out
-    int SL, AC;
-    uint32_t limit;           // stop inserting at this many rows (every thread may have one insert in flight)
-};
-
-template <int I>
-__device__ __forceinline__ void part_accumulate_input(const PartTable& T, uint32_t slot, uint32_t meta, const uint64_t (&w)[TW]) {
-    if constexpr (I < Q::NIN) {
-        constexpr int FL = Q::IN_FLAGS[I];
-        const bool valid = Q::IN_CNT[I] > 0 ? ((meta >> (8 + I)) & 1u) != 0 : true;
-        if (valid) {
-            if constexpr (Q::IN_CNT[I] > 0) atomicAdd(T.cnt + (size_t)Q::IN_CNT[I] * T.AC + slot, 1u);
-            if constexpr ((FL & (F_SUM | F_MIN | F_MAX)) != 0) {
-                const uint64_t v = w[tuple_in_word(I)];
-                if constexpr ((FL & F_SUM) != 0) {
-                    uint64_t* p = T.sum + (size_t)Q::FE_SUM[I] * T.AC + slot;
-                    if constexpr ((FL & F_INT) != 0) atomicAdd(reinterpret_cast<unsigned long long*>(p), (unsigned long long)v);
-                    else atomicAdd(reinterpret_cast<double*>(p), as_f64(v));
-                }
-                if constexpr ((FL & (F_MIN | F_MAX)) != 0) {
-                    constexpr bool is_int = (FL & F_INT) != 0;
-                    const uint64_t m = order_map(is_int ? v : canon_nan(v), is_int);
-                    if constexpr ((FL & F_MIN) != 0) {
-                        uint64_t* p = T.mm + (size_t)Q::FE_MIN[I] * T.AC + slot;
-                        if (m < *reinterpret_cast<volatile uint64_t*>(p)) atomicMin(reinterpret_cast<unsigned long long*>(p), (unsigned long long)m);
-                    }
-                    if constexpr ((FL & F_MAX) != 0) {
-                        uint64_t* p = T.mm + (size_t)Q::FE_MAX[I] * T.AC + slot;
-                        if (m > *reinterpret_cast<volatile uint64_t*>(p)) atomicMax(reinterpret_cast<unsigned long long*>(p), (unsigned long long)m);
-                    }
-                }
-            }
-        }
-        part_accumulate_input<I + 1>(T, slot, meta, w);
-    }
-}
-template <int I>
-__device__ __forceinline__ void part_overflow_input(const AggArgs& A, uint64_t* rec, uint32_t meta, const uint64_t (&w)[TW]) {
-    if constexpr (I < Q::NIN) {
-        const bool valid = Q::IN_CNT[I] > 0 ? ((meta >> (8 + I)) & 1u) != 0 : true;
-        if (valid) global_accumulate(rec, A.in[I], (Q::IN_FLAGS[I] & (F_SUM | F_MIN | F_MAX)) ? w[tuple_in_word(I)] : 0ULL);
-        part_overflow_input<I + 1>(A, rec, meta, w);
-    }
-}
-template <int I>
-__device__ __forceinline__ void part_merge_input(const PartTable& T, uint32_t slot, uint64_t* rec) {
-    if constexpr (I < Q::NIN) {
-        constexpr int FL = Q::IN_FLAGS[I];
-        const uint32_t n = T.cnt[(size_t)Q::IN_CNT[I] * T.AC + slot];
-        if (n) {
-            atomicAdd(reinterpret_cast<unsigned long long*>(rec + Q::REC_NN[I]), (unsigned long long)n);
-            if constexpr ((FL & F_SUM) != 0) {
-                const uint64_t x = T.sum[(size_t)Q::FE_SUM[I] * T.AC + slot];
-                if constexpr ((FL & F_INT) != 0) atomicAdd(reinterpret_cast<unsigned long long*>(rec + Q::REC_SUM[I]), (unsigned long long)x);
-                else atomicAdd(reinterpret_cast<double*>(rec + Q::REC_SUM[I]), as_f64(x));
-            }
-            if constexpr ((FL & F_MIN) != 0) {
-                const uint64_t x = T.mm[(size_t)Q::FE_MIN[I] * T.AC + slot];
-                if (x != ~0ULL) atomicMin(reinterpret_cast<unsigned long long*>(rec + Q::MM_WORD[Q::FE_MIN[I]]), (unsigned long long)x);
-            }
-            if constexpr ((FL & F_MAX) != 0) {
-                const uint64_t x = T.mm[(size_t)Q::FE_MAX[I] * T.AC + slot];
-                if (x != 0ULL) atomicMax(reinterpret_cast<unsigned long long*>(rec + Q::MM_WORD[Q::FE_MAX[I]]), (unsigned long long)x);
-            }
-        }
-        part_merge_input<I + 1>(T, slot, rec);
-    }
-}
-
-// One tuple per lane into the partition's shared-memory table (find or insert, then shared-memory atomics).
-// Called by ALL 32 lanes (`valid` = the lane has a tuple). The probe runs in LOCKSTEP: every unresolved lane takes
-// one probe step per iteration and the warp leaves the loop together. Two reasons: (1) a lane that meets a slot being
-// published by another lane of its own warp simply looks again next iteration (by then the publisher, which runs
-// in the same iteration, is done) — a free-running spin could starve the publisher; (2) with free-running loops
-// the compiler emits no reconvergence point and the lanes of a warp drift apart for good (measured: 4 active lanes
-// per instruction). The warp pays for its slowest lane, hence the sparse lookup part (probe sequences of 1-4 slots).
-__device__ __forceinline__ void part_accumulate(const AggArgs& A, const PartTable& T, const uint64_t (&w)[TW], bool valid) {
-    uint64_t kw[MAX_KEYS];
-#pragma unroll
-    for (int k = 0; k < MAX_KEYS; k++) kw[k] = k < Q::NKEYS ? w[k] : 0;
-    const uint32_t meta = TUPLE_META ? (uint32_t)w[Q::NKEYS] : 0u;
-    const uint32_t nm = meta & 0xffu;
-    // slot hash: the partition hash (its top bits are equal for all keys here) through a bijective finaliser
-    uint32_t h = part_hash(kw, nm);
-    h ^= h >> 16; h *= 0x85EBCA6Bu; h ^= h >> 13; h *= 0xC2B2AE35u; h ^= h >> 16;
-    uint32_t slot = h & (uint32_t)(T.SL - 1);
-    uint32_t row = 0xFFFFFFFFu;                 // accumulator row once found
-    bool probing = valid;
-    while (__any_sync(0xffffffffu, probing)) {
-        if (probing) {
-            uint32_t st = *reinterpret_cast<volatile uint32_t*>(T.state + slot);
-            if (st == 0u) {
-                if (*reinterpret_cast<volatile uint32_t*>(T.nfull) >= T.limit) probing = false;       // accumulator rows nearly used up: global path
-                else {
-                    st = atomicCAS(T.state + slot, 0u, 1u);
-                    if (st == 0u) {
-                        row = atomicAdd(T.nfull, 1u);
-#pragma unroll
-                        for (int k = 0; k < Q::NKEYS; k++) T.key[(size_t)k * T.SL + slot] = kw[k];
-                        __threadfence_block();
-                        *reinterpret_cast<volatile uint32_t*>(T.state + slot) = (row + 2u) | (nm << 24);
-                        probing = false;
-                    }
-                }
-            }
-            if (probing && st > 1u) {           // st == 1: being published, look at the same slot again next iteration
-                bool eq = (st >> 24) == nm;
-#pragma unroll
-                for (int k = 0; k < Q::NKEYS; k++) eq &= *reinterpret_cast<volatile uint64_t*>(T.key + (size_t)k * T.SL + slot) == kw[k];
-                if (eq) { row = (st & 0xFFFFFFu) - 2u; probing = false; }
-                else slot = (slot + 1) & (uint32_t)(T.SL - 1);
-            }
-        }
-    }
-    if (row != 0xFFFFFFFFu) {
-        if constexpr (Q::CNT0_USED) atomicAdd(T.cnt + row, 1u);
-        part_accumulate_input<0>(T, row, meta, w);
-    } else if (valid) {
-        uint64_t* rec = table_find_or_insert(A, hash_key(kw, nm, Q::NKEYS), kw, nm);
-        part_overflow_input<0>(A, rec, meta, w);
-    }
-}
-
 extern "C" __global__ void __launch_bounds__(PR_THREADS, 1) kq_agg_partition_reduce(const __grid_constant__ AggArgs A) {
     extern __shared__ __align__(128) unsigned char smem[];
     __shared__ int s_part;
     __shared__ uint32_t s_nfull, s_new;
     const int SL = A.part_slots, AC = A.part_groups;
     PartTable T;
-    T.SL = SL; T.AC = AC; T.nfull = &s_nfull;
-    T.limit = AC > PR_THREADS ? (uint32_t)(AC - PR_THREADS) : 0u;      // every thread may have one insert in flight past the check
-    T.key = reinterpret_cast<uint64_t*>(smem);
-    T.sum = T.key + (size_t)Q::NKEYS * SL;
-    T.mm = T.sum + (size_t)Q::NSUM * AC;
-    T.cnt = reinterpret_cast<uint32_t*>(T.mm + (size_t)Q::NMM * AC);
-    T.state = T.cnt + (size_t)Q::NCNT * AC;
-    const size_t table_bytes = ((size_t)SL * (8 * Q::NKEYS + 4) + (size_t)AC * (8 * (Q::NSUM + Q::NMM) + 4 * Q::NCNT) + 15) / 16 * 16;
+    const size_t table_bytes = part_table_place(T, smem, SL, AC, PR_THREADS, &s_nfull);
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    auto take_part = [&]() -> int {
+        if (*reinterpret_cast<volatile unsigned long long*>(A.ngroups) > A.stop_threshold) return -1;
+        const long long t = (long long)atomicAdd(A.ticket, 1u) + A.part_begin;
+        return t < A.nparts ? (int)t : -1;
+    };
     for (;;) {
         __syncthreads();                                    // the previous partition is merged
         if (tid == 0) {
             // same protocol as the tiles of the plain path: partitions are taken in order, and none is taken once the
             // global table is half full (the host grows it and resumes with the next partition)
-            int p = -1;
-            if (*reinterpret_cast<volatile unsigned long long*>(A.ngroups) <= A.stop_threshold) {
-                const long long t = (long long)atomicAdd(A.ticket, 1u) + A.part_begin;
-                if (t < A.nparts) p = (int)t;
-            }
-            s_part = p; s_nfull = 0; s_new = 0;
+            s_part = take_part(); s_nfull = 0; s_new = 0;
         }
         for (size_t i = (size_t)tid * 16; i < table_bytes; i += (size_t)PR_THREADS * 16) *reinterpret_cast<uint4*>(smem + i) = make_uint4(0, 0, 0, 0);
         __syncthreads();
@@ -830,16 +969,18 @@ extern "C" __global__ void __launch_bounds__(PR_THREADS, 1) kq_agg_partition_red
         if (p < 0) break;
         for (int i = tid; i < Q::NMM * AC; i += PR_THREADS) if ((Q::MM_ISMIN >> (i / AC)) & 1u) T.mm[i] = ~0ULL;
         __syncthreads();
-        // the partition's buckets, one warp per bucket; PR_UNROLL tuples per lane in flight
-        for (int seg = warp; seg < A.part_ncta; seg += PR_WARPS) {
-            const uint32_t n = A.part_counts[(size_t)p * A.part_ncta + seg];
-            const uint64_t* base = A.part_scratch + ((uint64_t)p * (uint32_t)A.part_ncta + (uint32_t)seg) * (uint32_t)A.part_cap * TW;
-            for (uint32_t b0 = 0; b0 < n; b0 += 32 * PR_UNROLL) {       // warp-uniform trip count
-                const uint32_t i0 = b0 + lane;
-                uint64_t w[PR_UNROLL][TW];
+        // The partition's buckets, one warp per bucket, in batches of 32 * PR_UNROLL tuples. The loads of the NEXT batch
+        // (possibly of the warp's next bucket: the fill counts of all its buckets are fetched up front, one per lane)
+        // are in flight while the current batch goes through the table.
+        {
+            const int my_seg = warp + PR_WARPS * lane;                  // lane l looks after the warp's l-th bucket
+            const uint32_t my_n = my_seg < A.part_ncta ? A.part_counts[(size_t)p * A.part_ncta + my_seg] : 0u;
+            const int nseg = (A.part_ncta - warp + PR_WARPS - 1) / PR_WARPS;     // buckets of this warp (<= 32: part_ncta <= 512)
+            auto load_batch = [&](int si, uint32_t b0, uint32_t n, uint64_t (&w)[PR_UNROLL][TW]) {
+                const uint64_t* base = A.part_scratch + ((uint64_t)p * (uint32_t)A.part_ncta + (uint32_t)(warp + PR_WARPS * si)) * (uint32_t)A.part_cap * TW;
 #pragma unroll
                 for (int u = 0; u < PR_UNROLL; u++) {
-                    const uint32_t i = i0 + 32u * u;
+                    const uint32_t i = b0 + lane + 32u * u;
 #pragma unroll
                     for (int j = 0; j < TW; j++) w[u][j] = 0;
                     if (i < n) {
@@ -853,27 +994,42 @@ extern "C" __global__ void __launch_bounds__(PR_THREADS, 1) kq_agg_partition_red
                         }
                     }
                 }
+            };
+            // cursor over (bucket, batch): warp-uniform
+            int si = 0; uint32_t b0 = 0, n = 0;
+            auto seek = [&]() {         // move (si, b0) to the next non-empty batch at or after the current position; false at the end
+                while (si < nseg) {
+                    n = __shfl_sync(0xffffffffu, my_n, si);
+                    if (b0 < n) return true;
+                    si++; b0 = 0;
+                }
+                return false;
+            };
+            uint64_t cur[PR_UNROLL][TW], nxt[PR_UNROLL][TW];
+            bool have = seek();
+            if (have) load_batch(si, b0, n, cur);
+            while (have) {
+                const uint32_t cb0 = b0, cn = n;
+                b0 += 32 * PR_UNROLL;
+                const bool more = seek();
+                if (more) load_batch(si, b0, n, nxt);
 #pragma unroll
                 for (int u = 0; u < PR_UNROLL; u++) {
-                    if (b0 + 32u * u >= n) break;                          // warp-uniform
-                    part_accumulate(A, T, w[u], i0 + 32u * u < n);
+                    if (cb0 + 32u * u >= cn) break;                        // warp-uniform
+                    part_accumulate(A, T, cur[u], cb0 + lane + 32u * u < cn);
                     __syncwarp();
                 }
+#pragma unroll
+                for (int u = 0; u < PR_UNROLL; u++)
+#pragma unroll
+                    for (int j = 0; j < TW; j++) cur[u][j] = nxt[u][j];
+                have = more;
             }
         }
         __syncthreads();
         // merge the table into the global one: once per distinct key of the partition
         uint32_t fresh = 0;
-        for (int slot = tid; slot < SL; slot += PR_THREADS) {
-            const uint32_t st = T.state[slot];
-            if (st < 2u) continue;
-            uint64_t kw[MAX_KEYS];
-#pragma unroll
-            for (int k = 0; k < MAX_KEYS; k++) kw[k] = k < Q::NKEYS ? T.key[(size_t)k * SL + slot] : 0;
-            const uint32_t nm = st >> 24;
-            uint64_t* rec = table_find_or_insert(A, hash_key(kw, nm, Q::NKEYS), kw, nm, &fresh);
-            part_merge_input<0>(T, (st & 0xFFFFFFu) - 2u, rec);
-        }
+        part_merge_table_batched<4>(A, T, tid, PR_THREADS, fresh);
         if (fresh) atomicAdd(&s_new, fresh);
         __syncthreads();
         if (tid == 0 && s_new) atomicAdd(A.ngroups, (unsigned long long)s_new);       // one update per partition, not per group

@@ -363,6 +363,25 @@ def test_partitioned_path_matches_oracle(G, oracle, keys, null_frac):
     assert sort_rows(got.to_arrow(), len(keys)) == sort_rows(want.to_arrow(), len(keys))
 
 
+@pytest.mark.parametrize("null_frac", [0.0, 0.1])
+@pytest.mark.parametrize("ngroups,hint", [(700, 700), (5000, 900)])     # fits the block-shared table / overflows it (rows spill to the global table)
+def test_mid_cardinality_shared_table_matches_oracle(G, oracle, ngroups, hint, null_frac):
+    rng = np.random.default_rng(5)
+    n = 150_000
+    arrs = rand_table(rng, n, null_frac)
+    k = rng.integers(0, ngroups, n)
+    arrs[0] = pa.array(k, type=pa.int64(), mask=rng.random(n) < null_frac) if null_frac else pa.array(k, type=pa.int64())
+    for keys in ([0], [0, 7]):
+        def run(E, **kw):
+            agg = E.HashAggregate([E.col(c) for c in keys], [(kind, E.col(c)) for kind, c in AGGS], **kw)
+            agg.update(E.RecordBatch.from_arrow(arrs))
+            agg.update(E.RecordBatch.from_arrow([a.slice(11, 40_000) for a in arrs]))
+            return agg.finalize()
+        got, want = run(G, expected_groups=hint), run(oracle)
+        assert got.row_count() == want.row_count()
+        assert sort_rows(got.to_arrow(), len(keys)) == sort_rows(want.to_arrow(), len(keys))
+
+
 def test_partitioned_path_survives_skewed_keys(G, oracle):
     """Nine rows in ten share one key: its buckets overflow and the surplus rows take the plain global path."""
     rng = np.random.default_rng(78)
