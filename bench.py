@@ -80,7 +80,6 @@ class FilterProject(Workload):
 
 
 class GroupBy(Workload):
-    kernel = "kq_hash_aggregate"
 
     def __init__(self, name, rows, kind):
         super().__init__(name, rows, "f64")
@@ -88,6 +87,11 @@ class GroupBy(Workload):
         self.describe = {"low": "GROUP BY 50-value Utf8 key: SUM/MIN/MAX/COUNT(Float64)",
                          "high": "GROUP BY Int64 key (10M distinct): SUM/MIN/MAX/COUNT(Float64)",
                          "q1": "TPC-H Q1 shape: date filter, derived projections, 2-key grouped SUMs + COUNT"}[kind]
+
+    @property
+    def kernel(self):
+        # high cardinality runs the partitioned path: scatter (kq_hash_aggregate, KQ_AGG_MODE 1) + kq_agg_partition_reduce
+        return "kq_hash_aggregate+kq_agg_partition_reduce" if self.kind == "high" else "kq_hash_aggregate"
 
     def specs(self):
         if self.kind == "low":

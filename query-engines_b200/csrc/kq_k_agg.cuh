@@ -383,6 +383,9 @@ __device__ __forceinline__ void global_path_batched(const AggArgs& A, const AggS
 #ifndef KQ_AGG_MODE
 #define KQ_AGG_MODE 0
 #endif
+#ifndef KQ_PART_L2_HINTS
+#define KQ_PART_L2_HINTS 1           // measured: pass 1 2.61 -> 2.44 ms per 100 M rows (fewer partially filled bucket lines evicted)
+#endif
 #ifndef KQ_GLOBAL_BATCHED
 #define KQ_GLOBAL_BATCHED 0          // 1: global_path_batched (R lookups in flight per thread) — EXPERIMENTAL, misattributes a few rows per million at 10 M groups (tools/part_debug.py); off until understood
 #endif
@@ -423,6 +426,7 @@ __device__ __forceinline__ uint32_t partition_scatter(const AggArgs& A, uint32_t
         }
     }
     uint32_t overflow = 0;
+    const uint64_t st_policy = KQ_PART_L2_HINTS ? l2_policy_evict_last() : 0ULL;
 #pragma unroll
     for (int r = 0; r < R; r++) {
         if (!((rows >> r) & 1u)) continue;
@@ -441,7 +445,10 @@ __device__ __forceinline__ uint32_t partition_scatter(const AggArgs& A, uint32_t
         for (int i = 0; i < Q::NIN; i++) if (Q::IN_FLAGS[i] & (F_SUM | F_MIN | F_MAX)) w[tuple_in_word(i)] = sink.in[i][r];
         if constexpr (TW % 2 == 0) {
 #pragma unroll
-            for (int j = 0; j < TW; j += 2) *reinterpret_cast<ulonglong2*>(t + j) = make_ulonglong2(w[j], w[j + 1]);
+            for (int j = 0; j < TW; j += 2) {
+                if (KQ_PART_L2_HINTS) asm volatile("st.global.L2::cache_hint.v2.u64 [%0], {%1, %2}, %3;" ::"l"(t + j), "l"(w[j]), "l"(w[j + 1]), "l"(st_policy) : "memory");
+                else *reinterpret_cast<ulonglong2*>(t + j) = make_ulonglong2(w[j], w[j + 1]);
+            }
         } else {
 #pragma unroll
             for (int j = 0; j < TW; j++) t[j] = w[j];
@@ -739,6 +746,9 @@ extern "C" __global__ void __launch_bounds__(THREADS, 1) kq_hash_aggregate(const
             // reads of the tile's Utf8 boundary offsets (stage_bounds_fetch) overlap the wait for a free stage,
             // so string bytes and fixed-size buffers of a tile are issued together on one barrier.
             TileBounds tb = {};
+            // partition scatter: the input streams through once (evict first) while the partially filled lines of the
+            // buckets should stay in the L2 until they are complete (the stores below ask for evict last)
+            const uint64_t in_policy = (KQ_AGG_MODE == 1 && KQ_PART_L2_HINTS) ? l2_policy_evict_first() : 0ULL;
             auto take = [&]() -> long long {
                 // stop taking tiles once the global table is half full: every ticket taken is processed,
                 // so the rows consumed so far are always a prefix of the batch (the host grows and resumes)
@@ -756,7 +766,7 @@ extern "C" __global__ void __launch_bounds__(THREADS, 1) kq_hash_aggregate(const
                 const long long tile = next;
                 tile_of[s] = tile;
                 if (tile < 0) { mbar_arrive(&full[s]); break; }
-                stage_issue_all(A.sp, smem + (size_t)s * A.sp.stage_bytes, &full[s], tile, TILE, A.n, tb, bbase[s]);
+                stage_issue_all(A.sp, smem + (size_t)s * A.sp.stage_bytes, &full[s], tile, TILE, A.n, tb, bbase[s], in_policy);
                 next = take();
                 if (KQ_L2_PREFETCH > 0 && next >= 0) stage_prefetch_l2(A.sp, next, TILE, A.n);     // staged one step from now
             }

@@ -55,6 +55,14 @@ __device__ __forceinline__ void bulk_g2s(void* dst_smem, const void* src, uint32
     asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
                  ::"r"(smem_u32(dst_smem)), "l"(src), "r"(bytes), "r"(smem_u32(bar)) : "memory");
 }
+// the same with an L2 eviction policy (createpolicy): streaming inputs that must not displace lines another part of the
+// kernel wants to keep in the L2
+__device__ __forceinline__ void bulk_g2s_policy(void* dst_smem, const void* src, uint32_t bytes, uint64_t* bar, uint64_t policy) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1], %2, [%3], %4;"
+                 ::"r"(smem_u32(dst_smem)), "l"(src), "r"(bytes), "r"(smem_u32(bar)), "l"(policy) : "memory");
+}
+__device__ __forceinline__ uint64_t l2_policy_evict_first() { uint64_t p; asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(p)); return p; }
+__device__ __forceinline__ uint64_t l2_policy_evict_last() { uint64_t p; asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(p)); return p; }
 __device__ __forceinline__ void bulk_prefetch_l2(const void* src, uint32_t bytes) {
     asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(src), "r"(bytes) : "memory");
 }
@@ -133,7 +141,7 @@ __device__ __forceinline__ void stage_bounds_fetch(const StagePlan& sp, int64_t 
 // bbase[column slot] receives the data-buffer offset the staged bytes start at (16-byte aligned), or -1 when the
 // range does not fit the stage (consumers then read those bytes from global memory). Called by one thread.
 __device__ __forceinline__ void stage_issue_all(const StagePlan& sp, unsigned char* stage, uint64_t* full, int64_t tile,
-                                                int tile_rows, int64_t n, const TileBounds& tb, long long* bbase) {
+                                                int tile_rows, int64_t n, const TileBounds& tb, long long* bbase, uint64_t policy = 0) {
     const int64_t row0 = tile * tile_rows;
     const int rows = (int)((n - row0) < tile_rows ? (n - row0) : tile_rows);
     uint32_t total = 0;
@@ -168,11 +176,14 @@ __device__ __forceinline__ void stage_issue_all(const StagePlan& sp, unsigned ch
         else if (sb.kind == SK_W4_PLUS1) { bytes = (rows + 1) * 4; goff = row0 * 4; }
         else { bytes = (rows + 7) / 8; goff = row0 / 8; }
         bytes = (bytes + 15u) & ~15u;
-        bulk_g2s(stage + sb.soff, sb.g + goff, bytes, full);
+        if (policy) bulk_g2s_policy(stage + sb.soff, sb.g + goff, bytes, full, policy); else bulk_g2s(stage + sb.soff, sb.g + goff, bytes, full);
     }
 #pragma unroll
     for (int i = 0; i < MAX_BYTES_BUFS; i++)
-        if (i < sp.nbytes && len[i]) { const StageBuf& sb = sp.buf[sp.bytes_buf[i]]; bulk_g2s(stage + sb.soff, sb.g + start[i], len[i], full); }
+        if (i < sp.nbytes && len[i]) {
+            const StageBuf& sb = sp.buf[sp.bytes_buf[i]];
+            if (policy) bulk_g2s_policy(stage + sb.soff, sb.g + start[i], len[i], full, policy); else bulk_g2s(stage + sb.soff, sb.g + start[i], len[i], full);
+        }
 }
 
 // Second phase for Utf8 columns: once the tile's offsets have landed in the stage, copy the byte range
