@@ -491,7 +491,8 @@ static int plan_agg(kq_ctx* ctx, kq_hashagg* h, kq_batch* input, int smem_optin,
     bool has_bytes = false;
     auto try_geometry = [&](const AggGeometry& g, StagePlan* sp, std::string* defs, int* dir_out) {
         // stage ring first (2..4 stages within ~64 KB, more only if two stages need it), front end gets the rest
-        *defs = cg.plan_stages(64 * 1024, 1, g.tile(), sp, true);
+        const int ring_budget = getenv("KQ_AGG_RING_KB") ? atoi(getenv("KQ_AGG_RING_KB")) * 1024 : 64 * 1024;      // tuning experiments
+        *defs = cg.plan_stages(ring_budget, 1, g.tile(), sp, true);
         if (sp->nstages < 2) *defs = cg.plan_stages(std::min(2 * sp->stage_bytes, 112 * 1024), 2, g.tile(), sp, true);
         sp->nstages = std::max(1, std::min(sp->nstages, AGG_MAX_STAGES));
         const int ring = sp->nstages * sp->stage_bytes;
@@ -580,8 +581,7 @@ static int plan_agg(kq_ctx* ctx, kq_hashagg* h, kq_batch* input, int smem_optin,
     *gen_out = "namespace kq {\n" + stage_defs + "struct Q {\n" + consts +
                             "    template <class Sink> static __device__ __forceinline__ void eval(const QArgs& q, RowCtx& rc, Sink& sink) {\n" +
                             eval_body + "    }\n};\n}  // namespace kq\n";
-    *defines_out = "#define KQ_R " + std::to_string(geo.r) + "\n#define KQ_WARPS " + std::to_string(geo.warps) + "\n#define KQ_STAGES " +
-                                std::to_string(A.sp.nstages) + "\n#define KQ_FE_GROUPS " + std::to_string(fg) + "\n#define KQ_DIR_SLOTS " +
+    *defines_out = "#define KQ_R " + std::to_string(geo.r) + "\n#define KQ_WARPS " + std::to_string(geo.warps) + "\n#define KQ_STAGES " + std::to_string(A.sp.nstages) + "\n#define KQ_FE_GROUPS " + std::to_string(fg) + "\n#define KQ_DIR_SLOTS " +
                                 std::to_string(dir_slots) + (getenv("KQ_L2_PREFETCH") ? "\n#define KQ_L2_PREFETCH " + std::to_string(atoi(getenv("KQ_L2_PREFETCH"))) : std::string()) +
                                 "\n#define KQ_STAGE_BYTES " + (has_bytes ? "1" : "0") + "\n#define KQ_AGG_MODE " + std::to_string(mode) + "\n" +
                                 (getenv("KQ_PART_L2_HINTS") ? "#define KQ_PART_L2_HINTS " + std::to_string(atoi(getenv("KQ_PART_L2_HINTS"))) + "\n" : std::string()) +

@@ -26,7 +26,7 @@ namespace kq {
 
 // Service warp first (the warp arbiter favours high warp ids: a polling producer must not starve consumers).
 #ifndef KQ_L2_PREFETCH
-#define KQ_L2_PREFETCH 0          // measured: no effect here (consumers, not HBM latency, bound this kernel)
+#define KQ_L2_PREFETCH 0          // measured: no effect one step ahead; several grid rounds ahead: 20 % slower
 #endif
 constexpr int WARPS = KQ_WARPS;              // consumer warps (the lane-private front end scales with them)
 constexpr int PRODUCER_WARP = 0;
@@ -64,6 +64,7 @@ struct FrontEnd {
     uint32_t* dir_count;
     uint32_t* gid2slot;       // [FG]
     uint64_t* mm;             // [FG][NMM]  CTA-shared MIN/MAX in order-mapped form
+    unsigned long long* mm_bound;   // [NMM] {insert epoch : 32 | bound on the high word over all front-end groups : 32}
     uint32_t* cnt;            // this warp: [FG][NCNT][32]
     uint64_t* sum;            // this warp: [FG][NSUM][32]
 };
@@ -95,7 +96,14 @@ __device__ __forceinline__ int dir_lookup(const FrontEnd& fe, uint32_t slot, con
 #pragma unroll
                 for (int k = 0; k < Q::NKEYS; k++) e[1 + k] = kw[k];
                 const bool fits = gid < (uint32_t)FG;
-                if (fits) fe.gid2slot[gid] = slot;
+                if (fits) {
+                    fe.gid2slot[gid] = slot;
+                    // a new group's extremes are the identities: no bound holds any more. The epoch makes a concurrent
+                    // recomputation (mm_bound_refresh), which cannot have seen this group, lose its compare-and-swap.
+#pragma unroll
+                    for (int m = 0; m < Q::NMM; m++)
+                        atomicExch(fe.mm_bound + m, ((unsigned long long)(gid + 1u) << 32) | (((Q::MM_ISMIN >> m) & 1u) ? 0xFFFFFFFFull : 0ull));
+                }
                 __threadfence_block();
                 *reinterpret_cast<volatile uint32_t*>(e) = fits ? gid + 2 : DIR_GLOBAL;
                 return fits ? (int)gid : -1;
@@ -170,14 +178,36 @@ __device__ __forceinline__ void smem_max_u64(uint32_t a, uint64_t m) {
                  ::"r"(a), "l"(m) : "memory");
 }
 
+// Recompute the all-groups bounds from the CTA-shared extremes (one warp, every few tiles). Extremes only tighten, so a
+// bound computed from older values stays valid; a group inserted meanwhile changes the epoch and the swap fails.
+__device__ __forceinline__ void mm_bound_refresh(const FrontEnd& fe, int lane) {
+    if constexpr (Q::NMM > 0 && FG > 0) {
+#pragma unroll
+        for (int m = 0; m < Q::NMM; m++) {
+            const bool ismin = (Q::MM_ISMIN >> m) & 1u;
+            const unsigned long long old = *reinterpret_cast<volatile unsigned long long*>(fe.mm_bound + m);
+            const int cnt = min((int)*reinterpret_cast<volatile uint32_t*>(fe.dir_count), FG);      // read AFTER the epoch
+            uint32_t x = ismin ? 0u : 0xFFFFFFFFu;
+            for (int g = lane; g < cnt; g += 32) {
+                const uint32_t hi = (uint32_t)(*reinterpret_cast<volatile uint64_t*>(fe.mm + g * Q::NMM + m) >> 32);
+                x = ismin ? max(x, hi) : min(x, hi);
+            }
+            x = ismin ? __reduce_max_sync(0xffffffffu, x) : __reduce_min_sync(0xffffffffu, x);
+            if (lane == 0 && cnt > 0) atomicCAS(fe.mm_bound + m, old, (old & 0xFFFFFFFF00000000ull) | x);
+        }
+    }
+}
+
 // Branch-free front-end accumulate of the adjacent row pair (r0, r0 + 1), groups g0 / g1 (FG = trash).
 // Every lane-private load of BOTH rows is issued before the first dependent add, so a pair exposes one
 // shared-memory latency instead of one per slot. When both rows fall in the same group the second row's add
 // chains on the first row's result rather than on the (stale) value it loaded, and its store lands last.
-// MIN/MAX: the CTA-shared extremes are pre-checked on the HIGH WORD of the order-mapped value only (two
-// instructions to map, one 32-bit load per slot); the exact 64-bit compare + reduction runs in a rarely
-// taken branch (value's high word ties or beats the current extreme, or the value is a NaN).
-__device__ __forceinline__ void fe_accumulate_pair(uint32_t a_cnt, uint32_t a_sum, uint32_t a_mm, int g0, int g1, int lane, const AggSink& sink, int r0) {
+// MIN/MAX: a value is first compared, on the HIGH WORD of its order-mapped form, with a bound that holds for EVERY
+// front-end group (mmb: the largest of the groups' minima / the smallest of their maxima, see fe.mm_bound) — two
+// register compares per row, no shared-memory access; only a value that beats the bound (or ties, or is a NaN)
+// takes the rarely executed branch with the exact 64-bit compare + reduction on its own group's slot.
+__device__ __forceinline__ void fe_accumulate_pair(uint32_t a_cnt, uint32_t a_sum, uint32_t a_mm, int g0, int g1, int lane, const AggSink& sink, int r0,
+                                                   const uint32_t (&mmb)[Q::NMM > 0 ? Q::NMM : 1]) {
     constexpr int NI = Q::NIN > 0 ? Q::NIN : 1;
     const int r1 = r0 + 1;
     const uint32_t l4 = (uint32_t)lane * 4u, l8 = (uint32_t)lane * 8u;
@@ -186,7 +216,7 @@ __device__ __forceinline__ void fe_accumulate_pair(uint32_t a_cnt, uint32_t a_su
         c0a[0] = a_cnt + (uint32_t)g0 * (Q::NCNT * 128u) + l4; c0a[1] = a_cnt + (uint32_t)g1 * (Q::NCNT * 128u) + l4;
         c0v[0] = lds_u32(c0a[0]); c0v[1] = lds_u32(c0a[1]);
     }
-    uint32_t gi[NI][2], ca[NI][2], cv[NI][2], sa[NI][2], mna[NI][2], mxa[NI][2], mnh[NI][2], mxh[NI][2];
+    uint32_t gi[NI][2], ca[NI][2], cv[NI][2], sa[NI][2];
     uint64_t sv[NI][2];
 #pragma unroll
     for (int i = 0; i < Q::NIN; i++) {
@@ -197,8 +227,6 @@ __device__ __forceinline__ void fe_accumulate_pair(uint32_t a_cnt, uint32_t a_su
             gi[i][k] = (Q::IN_CNT[i] > 0 && !valid) ? (uint32_t)FG : (uint32_t)(k ? g1 : g0);      // statically non-null inputs: always valid
             if (Q::IN_CNT[i] > 0) { ca[i][k] = a_cnt + (gi[i][k] * Q::NCNT + Q::IN_CNT[i]) * 128u + l4; cv[i][k] = lds_u32(ca[i][k]); }
             if (FL & F_SUM) { sa[i][k] = a_sum + (gi[i][k] * Q::NSUM + Q::FE_SUM[i]) * 256u + l8; sv[i][k] = lds_u64(sa[i][k]); }
-            if (FL & F_MIN) { mna[i][k] = a_mm + (gi[i][k] * Q::NMM + Q::FE_MIN[i]) * 8u; mnh[i][k] = lds_u32(mna[i][k] + 4u); }
-            if (FL & F_MAX) { mxa[i][k] = a_mm + (gi[i][k] * Q::NMM + Q::FE_MAX[i]) * 8u; mxh[i][k] = lds_u32(mxa[i][k] + 4u); }
         }
     }
     if constexpr (Q::CNT0_USED) {
@@ -228,12 +256,12 @@ __device__ __forceinline__ void fe_accumulate_pair(uint32_t a_cnt, uint32_t a_su
                 const uint32_t hi = (uint32_t)(v >> 32);
                 const uint32_t mh = is_int ? hi ^ 0x80000000u : hi ^ ((uint32_t)((int32_t)hi >> 31) | 0x80000000u);     // high word of order_map(v)
                 bool exact = !is_int && as_f64(v) != as_f64(v);                                                            // NaNs are canonicalised below
-                if (FL & F_MIN) exact |= mh <= mnh[i][k];
-                if (FL & F_MAX) exact |= mh >= mxh[i][k];
+                if (FL & F_MIN) exact |= mh <= mmb[Q::FE_MIN[i] < 0 ? 0 : Q::FE_MIN[i]];
+                if (FL & F_MAX) exact |= mh >= mmb[Q::FE_MAX[i] < 0 ? 0 : Q::FE_MAX[i]];
                 if (exact) {
                     const uint64_t m = order_map(is_int ? v : canon_nan(v), is_int);
-                    if (FL & F_MIN) smem_min_u64(mna[i][k], m);
-                    if (FL & F_MAX) smem_max_u64(mxa[i][k], m);
+                    if (FL & F_MIN) smem_min_u64(a_mm + (gi[i][k] * Q::NMM + Q::FE_MIN[i]) * 8u, m);
+                    if (FL & F_MAX) smem_max_u64(a_mm + (gi[i][k] * Q::NMM + Q::FE_MAX[i]) * 8u, m);
                 }
             }
         }
@@ -698,6 +726,7 @@ extern "C" __global__ void __launch_bounds__(THREADS, 1) kq_hash_aggregate(const
     __shared__ long long tile_of[S];
     __shared__ long long bbase[S][MAX_COLS];
     __shared__ uint32_t s_dir_count;
+    __shared__ unsigned long long s_mm_bound[Q::NMM > 0 ? Q::NMM : 1];
     const int wid = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int warp = wid - 1;                 // consumer warp index
     constexpr int NCNT = Q::NCNT, NSUM = Q::NSUM, NMM = Q::NMM;
@@ -724,12 +753,14 @@ extern "C" __global__ void __launch_bounds__(THREADS, 1) kq_hash_aggregate(const
 #endif
     const size_t fe_end = (size_t)(p0 - smem);
     fe.dir_count = &s_dir_count;
+    fe.mm_bound = s_mm_bound;
     fe.sum = sum0 + (size_t)(warp < 0 ? 0 : warp) * FG1 * NSUM * 32;
     fe.cnt = cnt0 + (size_t)(warp < 0 ? 0 : warp) * FG1 * NCNT * 32;
 
     for (size_t i = fe_begin + threadIdx.x * 4; i < fe_end; i += THREADS * 4) *reinterpret_cast<uint32_t*>(smem + i) = 0;
     if (threadIdx.x == 0) {
         s_dir_count = 0;
+        for (int m = 0; m < Q::NMM; m++) s_mm_bound[m] = ((Q::MM_ISMIN >> m) & 1u) ? 0xFFFFFFFFull : 0ull;
         for (int s = 0; s < S; s++) { mbar_init(&full[s], 1); mbar_init(&empty[s], WARPS); }
         mbar_fence_init();
     }
@@ -774,6 +805,7 @@ extern "C" __global__ void __launch_bounds__(THREADS, 1) kq_hash_aggregate(const
     } else {
         AggSink sink;
         bool bypass = FG == 0;
+        int low_tiles = 0;                        // consecutive tiles in which this warp mostly missed a full directory
         const uint32_t a_dir = smem_u32(fe.dir), a_cnt = smem_u32(fe.cnt), a_sum = smem_u32(fe.sum), a_mm = smem_u32(fe.mm);
         for (int k = 0;; k++) {
             const int s = k % S;
@@ -833,8 +865,36 @@ extern "C" __global__ void __launch_bounds__(THREADS, 1) kq_hash_aggregate(const
                     slow |= (uint32_t)(on && !hit) << r;
                 }
                 // pass 2 (branch-free): unconditional read-modify-write of the lane-private slots, a row pair at a time
+                // second chance, only when some lane missed: the NEXT bucket (slots home + 2, home + 3), which is where linear
+                // probing puts a key whose home bucket was taken. Without it ONE displaced key among 50 sends half of all
+                // warp-rows through the serial general path below (measured: 1.8 -> 0.45 TB/s on BASELINE config 3).
+                if (__any_sync(0xffffffffu, slow != 0)) {
 #pragma unroll
-                for (int j = 0; j < NCHUNK; j++) fe_accumulate_pair(a_cnt, a_sum, a_mm, gid[2 * j], gid[2 * j + 1], lane, sink, 2 * j);
+                    for (int r = 0; r < R; r++) {
+                        if (!((slow >> r) & 1u)) continue;
+                        uint64_t kw[MAX_KEYS];
+#pragma unroll
+                        for (int k2 = 0; k2 < MAX_KEYS; k2++) kw[k2] = k2 < Q::NKEYS ? sink.key[k2][r] : 0;
+                        const uint32_t e0 = a_dir + ((dir_hash(kw, nm[r]) + 2u) & (uint32_t)(DIR - 1)) * (ENTRY_WORDS * 8u), e1 = e0 + ENTRY_WORDS * 8u;
+                        const uint4 q0 = lds_u128(e0), q1 = lds_u128(e1);
+                        bool h0 = q0.x - 2u < (uint32_t)FG, h1 = q1.x - 2u < (uint32_t)FG;
+                        if constexpr (Q::KEYS_NULLABLE) { h0 &= q0.y == nm[r]; h1 &= q1.y == nm[r]; }
+                        if constexpr (Q::NKEYS >= 1) {
+                            h0 &= ((uint64_t)q0.z | ((uint64_t)q0.w << 32)) == kw[0];
+                            h1 &= ((uint64_t)q1.z | ((uint64_t)q1.w << 32)) == kw[0];
+                        }
+#pragma unroll
+                        for (int k2 = 1; k2 < Q::NKEYS; k2++) { h0 &= lds_u64(e0 + 8u + 8u * k2) == kw[k2]; h1 &= lds_u64(e1 + 8u + 8u * k2) == kw[k2]; }
+                        if (h0 | h1) { gid[r] = (int)((h0 ? q0.x : q1.x) - 2u); slow &= ~(1u << r); }
+                    }
+                }
+                // bounds on the extremes of all groups: read AFTER the probes (a group this warp has seen is covered)
+                uint32_t mmb[Q::NMM > 0 ? Q::NMM : 1];
+#pragma unroll
+                for (int m = 0; m < Q::NMM; m++) mmb[m] = (uint32_t)*reinterpret_cast<volatile unsigned long long*>(s_mm_bound + m);
+#pragma unroll
+                for (int j = 0; j < NCHUNK; j++) fe_accumulate_pair(a_cnt, a_sum, a_mm, gid[2 * j], gid[2 * j + 1], lane, sink, 2 * j, mmb);
+                if (Q::NMM > 0 && ((k + warp) & 3) == 0) mm_bound_refresh(fe, lane);
                 fe_hits = __popc(sink.sel & ~slow);
             }
             // general path for the rest: directory probing with insertion, else the global table
@@ -892,12 +952,15 @@ extern "C" __global__ void __launch_bounds__(THREADS, 1) kq_hash_aggregate(const
                 if (lane == 0) atomicAdd(A.ngroups, (unsigned long long)tot);
             }
             // once the directory is full and this warp mostly misses it, stop probing it (high cardinality)
+            // (two tiles in a row: while the blocks' first tiles race to fill the directory most rows find their key's slot
+            // busy and miss, also when every key ends up fitting — measured as a 10x cliff when FG equals the group count)
             if (!bypass && __any_sync(0xffffffffu, fe_hits < rows) && *reinterpret_cast<volatile uint32_t*>(&s_dir_count) >= (uint32_t)FG) {
                 int hits = fe_hits, tot = rows;
 #pragma unroll
                 for (int o = 16; o; o >>= 1) { hits += __shfl_xor_sync(0xffffffffu, hits, o); tot += __shfl_xor_sync(0xffffffffu, tot, o); }
-                if (tot >= 64 && hits * 8 < tot) bypass = true;
-            }
+                if (tot >= 64 && hits * 8 < tot) { if (++low_tiles >= 2) bypass = true; }
+                else low_tiles = 0;
+            } else low_tiles = 0;
         }
     }
 
