@@ -79,6 +79,12 @@ __global__ void k_merge_records(const AggArgs A, const uint64_t* __restrict__ re
     }
 }
 
+// every `pitch`-th word of `src` (the per-rank counts at the head of the gathered blocks of the small merge)
+__global__ void k_gather_words(const uint64_t* __restrict__ src, uint64_t pitch, int n, unsigned long long* out) {
+    for (int i = threadIdx.x; i < n; i += blockDim.x) out[i] = src[(uint64_t)i * pitch];
+}
+constexpr uint64_t SMALL_MERGE_MAX = 1024;      // partial groups per rank up to which kq_hashagg_merge_allreduce takes the one-shot path
+
 // ---- kernels of the multi-GPU merges -----------------------------------------------------------------------------
 __device__ __forceinline__ int record_part(const uint64_t* src, int nkeys, int nparts) {
     if (nparts <= 1) return 0;
@@ -898,6 +904,57 @@ int kq_hashagg_merge_allreduce(kq_ctx* ctx, kq_hashagg* h) {
     KQ_RET(kq_check_device_errors(ctx));
     KQ_RET(refresh_group_count(ctx, h));
     const uint64_t G = (uint64_t)h->ngroups_host;
+
+    // 0. Small unions (BASELINE configs 3 and 5: tens of groups) are latency-bound, so the all-reduce is done the
+    //    latency-optimal way: ONE fixed-size all-gather carrying every rank's group count and, when it has at most
+    //    SMALL_MERGE_MAX groups, its partial records; then every rank rebuilds its table by merging the gathered
+    //    partials rank by rank (a key occurs at most once per rank, so the order of every Float64 addition is fixed
+    //    and all ranks end with bit-identical results). One host synchronisation, no dictionary, no dense arrays.
+    {
+        const uint64_t blockw = 8 + SMALL_MERGE_MAX * (uint64_t)stride;          // words per rank: [0] count, [1] cursor, [2] base, [8..] records
+        uint64_t *mine = nullptr, *all = nullptr;
+        unsigned long long* d_cnt = nullptr;
+        KQ_RET(kq_dev_alloc(ctx, (size_t)blockw * 8, (void**)&mine));
+        int st = kq_dev_alloc(ctx, (size_t)blockw * 8 * nr, (void**)&all);
+        if (st == KQ_OK) st = kq_dev_alloc(ctx, (size_t)nr * 8, (void**)&d_cnt);
+        auto cleanup = [&](int s2) { kq_dev_free(ctx, mine); kq_dev_free(ctx, all); kq_dev_free(ctx, d_cnt); return s2; };
+        if (st != KQ_OK) return cleanup(st);
+        cudaMemsetAsync(mine, 0, (size_t)blockw * 8, ctx->stream);
+        cudaMemcpyAsync(mine, &G, 8, cudaMemcpyHostToDevice, ctx->stream);
+        if (G > 0 && G <= SMALL_MERGE_MAX) {
+            k_collect_records<<<small_grid(ctx, h->capacity), 256, 0, ctx->stream>>>(h->table, h->capacity, stride, nkeys, mine + 8,
+                                                                                   (unsigned long long*)mine + 1, 1, (unsigned long long*)mine + 2);
+            if ((st = launch_check(ctx, "k_collect_records")) != KQ_OK) return cleanup(st);
+        }
+        ncclResult_t r0 = N->AllGather(mine, all, (size_t)blockw, ncclUint64, comm, ctx->stream);
+        if (r0 != ncclSuccess) return cleanup(kq_nccl_fail(ctx, r0, "ncclAllGather"));
+        k_gather_words<<<1, 64, 0, ctx->stream>>>(all, blockw, nr, d_cnt);
+        if ((st = launch_check(ctx, "k_gather_words")) != KQ_OK) return cleanup(st);
+        uint64_t cnt[64];
+        if (nr > 64) return cleanup(kq_fail(ctx, KQ_ERR_UNSUPPORTED, "more than 64 ranks"));
+        if ((st = kq_read_u64(ctx, d_cnt, nr, cnt)) != KQ_OK) return cleanup(st);
+        uint64_t total = 0, maxn = 0;
+        for (int i = 0; i < nr; i++) { total += cnt[i]; maxn = std::max(maxn, cnt[i]); }
+        if (total == 0) return cleanup(KQ_OK);
+        if (maxn <= SMALL_MERGE_MAX && !getenv("KQ_NO_SMALL_MERGE")) {
+            uint64_t cap = 1024;
+            while (cap < 4 * total) cap <<= 1;
+            kq_dev_free(ctx, h->table);
+            h->table = nullptr;
+            if ((st = table_alloc(ctx, h, cap)) != KQ_OK) return cleanup(st);
+            cudaMemsetAsync(h->d_counters, 0, 8, ctx->stream);
+            AggArgs A;
+            memset(&A, 0, sizeof A);
+            fill_common_args(h, A);
+            for (int s2 = 0; s2 < nr; s2++) {
+                if (cnt[s2] == 0) continue;
+                k_merge_records<<<small_grid(ctx, cnt[s2]), 256, 0, ctx->stream>>>(A, all + (uint64_t)s2 * blockw + 8, cnt[s2]);
+                if ((st = launch_check(ctx, "k_merge_records")) != KQ_OK) return cleanup(st);
+            }
+            return cleanup(refresh_group_count(ctx, h));
+        }
+        cleanup(KQ_OK);           // some rank holds more: the general path below
+    }
 
     // 1. how many partial groups does every rank hold?
     unsigned long long* d_cnt = nullptr;

@@ -81,6 +81,33 @@ def test_low_cardinality_allreduce_merge(gpu, oracle, world):
     assert all(g == got[0] for g in got), "all-reduce must leave bit-identical results on every rank"
 
 
+@pytest.mark.parametrize("world", [2, 4])
+def test_mid_cardinality_allreduce_merge(gpu, oracle, world):
+    """More partial groups per rank than the one-shot small merge carries (1024): the union-dictionary + dense
+    ncclAllReduce path of kq_hashagg_merge_allreduce."""
+    if gpu.device_count() < world:
+        pytest.skip(f"needs {world} GPUs")
+    n = 200_000
+    specs = [dict(kind=3, col_id=0, ilo=0, ihi=3000), dict(kind=2, col_id=1, flo=-5.0, fhi=5.0, null_per_10k=500)]
+
+    def plan(E, batch):
+        a = E.HashAggregate([E.col(0)], [("SUM", E.col(1)), ("MIN", E.col(1)), ("MAX", E.col(1)), ("COUNT", E.col(1))])
+        a.update(batch)
+        return a
+
+    def body(r, ctx, E):
+        lo, hi = r * n // world, (r + 1) * n // world
+        a = plan(E, E.generate(specs, 11, lo, hi))
+        a.merge_allreduce()
+        return rows_of(a.finalize())
+
+    got = run_ranks(gpu, world, body)
+    want = rows_of(plan(oracle, oracle.generate(specs, 11, 0, n)).finalize())
+    for r in range(world):
+        close(got[r], want)
+    assert all(g == got[0] for g in got), "all-reduce must leave bit-identical results on every rank"
+
+
 @pytest.mark.parametrize("world", [2, 4, 8])
 def test_high_cardinality_alltoall_repartition(gpu, oracle, world):
     if gpu.device_count() < world:
