@@ -20,6 +20,8 @@
  *                                             (Main.kt:615-651); KQ_AGG_MAX = MaxAccumulator (Main.kt:538-562);
  *                                             SUM/MIN/COUNT are extensions (a12)
  *   kq_comm_*, kq_hashagg_merge_* ........... partition -> partial aggregate -> merge of main() (Main.kt:1306-1342)
+ *   kq_csv_header, kq_csv_scan .............. CsvDataSource.schema()/inferSchema and scan() + ReaderIterator.createBatch
+ *                                             (Main.kt:251-273, 276-357): CSV text -> one batch of Utf8 columns
  *   kq_generate ............................. bench-only synthetic tables (no reference counterpart)
  *
  * Conventions
@@ -230,6 +232,19 @@ KQ_API int kq_hashagg_merge_allreduce(kq_ctx* ctx, kq_hashagg* agg);
 /* High-cardinality merge: partials bucketed by hash(key) % nranks, exchanged with a grouped
  * ncclSend/ncclRecv all-to-all, merged locally. Afterwards each key lives on exactly one rank. */
 KQ_API int kq_hashagg_repartition_alltoall(kq_ctx* ctx, kq_hashagg* agg);
+
+/* ---- scan side: CsvDataSource (Main.kt:276-357) -------------------------------------------- */
+/* CsvDataSource.inferSchema (Main.kt:328-356), host only: detects the delimiter and line separator as the reference's
+ * parser settings ask (Main.kt:289-296) and reads the first record. `names` receives the column names, one per line
+ * ('\n'-terminated): the header fields if has_headers, else field_1.. (Main.kt:345-349). All columns are Utf8. */
+KQ_API int kq_csv_header(const uint8_t* text, int64_t nbytes, int has_headers, char* names, size_t names_cap,
+                         int* ncols, char* delimiter);
+/* CsvDataSource.scan(projection) (Main.kt:304-326) fused with ReaderIterator.createBatch (Main.kt:251-273): the
+ * whole text of a CSV file (HOST buffer, < 2 GiB) -> ONE batch of Utf8 columns in HBM, every value trimmed
+ * (Main.kt:263), never null. `projection`: file column indices in output order (NULL/0 = all columns); the caller
+ * maps names to indices as Schema.select does (Main.kt:47-52). Rules C1-C9: csrc/kq_csv.cu. */
+KQ_API int kq_csv_scan(kq_ctx* ctx, const uint8_t* text, int64_t nbytes, int has_headers, const int* projection,
+                       int nproj, kq_batch** out);
 
 /* ---- bench-only: device-side synthetic tables -------------------------------------------- */
 KQ_API int kq_generate(kq_ctx* ctx, const kq_gen_spec* specs, int ncols, uint64_t seed,

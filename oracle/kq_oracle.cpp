@@ -652,6 +652,81 @@ static RecordBatch sliceBatch(const RecordBatch& b, int64_t off, int64_t len) {
 struct ko_col { ColPtr c; };
 struct ko_batch { RecordBatch b; };
 struct ko_expr { ExprPtr e; };
+// ---- CsvDataSource.scan + ReaderIterator.createBatch (Main.kt:251-273, 276-357) -----------------------------
+// The reference hands tokenising to univocity-parsers (com.univocity:univocity-parsers, NOT under /root/reference, no
+// pinned version: PARITY UNPINNED) with delimiter/line-separator detection, skipEmptyLines and header extraction
+// (Main.kt:289-296, 322), then stores getValue(name, "").trim() of every field (Main.kt:262-264). Restated as rules
+// C1-C9 (query-engines_b200/csrc/kq_csv.cu header), here as a plain character-at-a-time tokenizer:
+//   C1 separator "\n" (CRLF: the CR goes with the terminator) or lone "\r" when the text has no "\n"; delimiter = most
+//      frequent of , ; TAB | outside quotes in the first record.   C2 '"' toggles quoting wherever it stands; a value
+//      whose first non-blank byte is '"' is unquoted ("" -> "), what follows its closing quote is dropped.
+//   C3 lines without a byte are skipped.  C4 header record names the columns.  C5 values are trimmed (<= 0x20).
+//   C6 all columns Utf8, never null; missing field = "".  C7 projection by file column index.  C8 surplus fields ignored.
+struct CsvText {
+    std::vector<std::vector<std::string>> records;
+    char delim = ',', term = '\n';
+};
+static std::string csv_trim(const std::string& v) {
+    size_t a = 0, b = v.size();
+    while (a < b && (unsigned char)v[a] <= 0x20) a++;
+    while (b > a && (unsigned char)v[b - 1] <= 0x20) b--;
+    return v.substr(a, b - a);
+}
+static std::string csv_field_value(const std::string& raw) {
+    std::string t = csv_trim(raw);
+    if (t.empty() || t[0] != '"') return t;
+    std::string v;
+    for (size_t i = 1; i < t.size(); i++) {
+        if (t[i] == '"') {
+            if (i + 1 < t.size() && t[i + 1] == '"') { v += '"'; i++; }
+            else break;                       // closing quote: the rest of the field is dropped
+        } else v += t[i];
+    }
+    return csv_trim(v);                       // String.trim() on the parsed value (Main.kt:263)
+}
+static CsvText csv_tokenize(const uint8_t* text, int64_t n) {
+    CsvText out;
+    std::string all((const char*)text, (size_t)n);
+    if (all.find('\n') == std::string::npos && all.find('\r') != std::string::npos) out.term = '\r';
+    // lines: split at terminators outside quotes
+    std::vector<std::string> lines;
+    {
+        std::string cur; bool inq = false;
+        for (char c : all) {
+            if (c == '"') inq = !inq;
+            if (c == out.term && !inq) { lines.push_back(cur); cur.clear(); }
+            else cur += c;
+        }
+        if (inq) throw KqError(E_ILLEGAL_STATE, "CSV text ends inside a quoted field");
+        if (!cur.empty()) lines.push_back(cur);
+    }
+    bool first = true;
+    for (std::string& line : lines) {
+        if (out.term == '\n' && !line.empty() && line.back() == '\r') line.pop_back();     // CRLF
+        if (line.empty()) continue;                                                        // skipEmptyLines (Main.kt:293)
+        if (first) {                            // delimiter detection on the first record (Main.kt:291)
+            first = false;
+            const char cand[4] = {',', ';', '\t', '|'};
+            long cnt[4] = {0, 0, 0, 0};
+            bool inq = false;
+            for (char c : line) { if (c == '"') inq = !inq; else if (!inq) for (int k = 0; k < 4; k++) cnt[k] += c == cand[k]; }
+            int best = 0;
+            for (int k = 1; k < 4; k++) if (cnt[k] > cnt[best]) best = k;
+            out.delim = cand[best];
+        }
+        std::vector<std::string> fields;
+        std::string cur; bool inq = false;
+        for (char c : line) {
+            if (c == '"') inq = !inq;
+            if (c == out.delim && !inq) { fields.push_back(csv_field_value(cur)); cur.clear(); }
+            else cur += c;
+        }
+        fields.push_back(csv_field_value(cur));
+        out.records.push_back(std::move(fields));
+    }
+    return out;
+}
+
 struct ko_hashagg { HashAggregateExec h; };
 
 #define KO_TRY(body) \
@@ -702,6 +777,48 @@ int ko_column_download(ko_col* col, uint8_t* validity, int32_t* offsets, void* d
     })
 }
 int ko_column_free(ko_col* c) { delete c; return OK; }
+
+// CsvDataSource.inferSchema (Main.kt:328-356): names separated by '\n'
+int ko_csv_header(const uint8_t* text, int64_t nbytes, int has_headers, char* names, size_t cap, int* ncols, char* delimiter) {
+    KO_TRY({
+        CsvText t = csv_tokenize(text, nbytes);
+        std::string all;
+        const size_t k = t.records.empty() ? 0 : t.records[0].size();
+        for (size_t i = 0; i < k; i++) all += (has_headers ? t.records[0][i] : "field_" + std::to_string(i + 1)) + "\n";
+        if (all.size() + 1 > cap) throw KqError(E_ILLEGAL_ARGUMENT, "names buffer too small");
+        std::memcpy(names, all.c_str(), all.size() + 1);
+        *ncols = (int)k;
+        if (delimiter) *delimiter = t.delim;
+    })
+}
+// CsvDataSource.scan (Main.kt:304-326) + createBatch (Main.kt:251-273), all records in one batch (rule C9)
+int ko_csv_scan(const uint8_t* text, int64_t nbytes, int has_headers, const int* projection, int nproj, ko_batch** out) {
+    KO_TRY({
+        CsvText t = csv_tokenize(text, nbytes);
+        const int file_cols = t.records.empty() ? 0 : (int)t.records[0].size();
+        std::vector<int> proj;
+        if (nproj) proj.assign(projection, projection + nproj);
+        else for (int i = 0; i < file_cols; i++) proj.push_back(i);
+        for (int c : proj) if (c < 0 || c >= file_cols) throw KqError(E_ILLEGAL_ARGUMENT, "projected CSV column out of range");
+        const size_t skip = has_headers && !t.records.empty() ? 1 : 0;
+        const int64_t rows = (int64_t)(t.records.size() - skip);
+        auto b = new ko_batch();
+        b->b.explicit_rows = rows;
+        for (int c : proj) {
+            auto col = std::make_shared<ArrowColumn>();
+            col->ty = T_UTF8; col->n = rows;
+            col->offsets.push_back(0);
+            for (size_t r = skip; r < t.records.size(); r++) {
+                const std::vector<std::string>& rec = t.records[r];
+                const std::string v = (size_t)c < rec.size() ? rec[(size_t)c] : std::string();     // getValue(name, "") (Main.kt:263)
+                col->data.insert(col->data.end(), v.begin(), v.end());
+                col->offsets.push_back((int32_t)col->data.size());
+            }
+            b->b.fields.push_back(col);
+        }
+        *out = b;
+    })
+}
 
 int ko_batch_create(ko_col* const* cols, int ncols, int64_t n_rows, ko_batch** out) {
     KO_TRY({

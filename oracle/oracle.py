@@ -97,6 +97,8 @@ def lib():
         L.ko_hashagg_finalize.argtypes = [C.c_void_p, C.POINTER(C.c_void_p)]
         L.ko_hashagg_free.argtypes = [C.c_void_p]
         L.ko_generate.argtypes = [C.POINTER(GenSpec), C.c_int, C.c_uint64, C.c_int64, C.c_int64, C.POINTER(C.c_void_p)]
+        L.ko_csv_header.argtypes = [C.c_char_p, C.c_int64, C.c_int, C.c_char_p, C.c_size_t, C.POINTER(C.c_int), C.c_char_p]
+        L.ko_csv_scan.argtypes = [C.c_char_p, C.c_int64, C.c_int, C.POINTER(C.c_int), C.c_int, C.POINTER(C.c_void_p)]
         L.ko_filter_project_mt.argtypes = [C.c_void_p, C.POINTER(C.c_void_p), C.c_int, C.c_void_p, C.c_int,
                                            C.POINTER(C.c_int64)]
         L.ko_hashagg_mt.argtypes = [C.c_void_p, C.POINTER(C.c_void_p), C.c_int, C.POINTER(C.c_int),
@@ -322,6 +324,29 @@ def generate(specs, seed, row_begin, row_end) -> RecordBatch:
     arr, keep = make_specs(specs)
     out = C.c_void_p()
     _check(lib().ko_generate(arr, len(specs), seed, row_begin, row_end, C.byref(out)))
+    return RecordBatch(out)
+
+
+def csv_header(text: bytes, has_headers=True):
+    """CsvDataSource.schema() (Main.kt:328-356): (column names, detected delimiter)."""
+    names = C.create_string_buffer(1 << 16)
+    n, d = C.c_int(), C.create_string_buffer(2)
+    _check(lib().ko_csv_header(text, len(text), int(bool(has_headers)), names, len(names), C.byref(n), d))
+    return names.value.decode("utf-8").split("\n")[:n.value], d.raw[:1].decode()
+
+
+def csv_scan(text: bytes, has_headers=True, projection=None) -> RecordBatch:
+    """CsvDataSource.scan(projection) (Main.kt:304-326) + createBatch (Main.kt:251-273); projection by column NAME."""
+    idx = []
+    if projection:
+        names, _ = csv_header(text, has_headers)
+        for p in projection:
+            if p not in names:
+                raise OracleError(3, f"Field {p} not found")        # E_ILLEGAL_ARGUMENT = IllegalArgumentException, Main.kt:49
+            idx.append(names.index(p))
+    arr = (C.c_int * max(len(idx), 1))(*idx)
+    out = C.c_void_p()
+    _check(lib().ko_csv_scan(text, len(text), int(bool(has_headers)), arr if idx else None, len(idx), C.byref(out)))
     return RecordBatch(out)
 
 

@@ -1,0 +1,430 @@
+// kq_csv.cu — CsvDataSource.scan (Main.kt:276-357) + ReaderIterator.createBatch (Main.kt:251-273) on the GPU:
+// the text of a CSV file -> one RecordBatch of Utf8 columns resident in HBM, ready for the operators.
+//
+// The reference delegates tokenising to univocity-parsers (absent from /root/reference, version unpinned) with
+// delimiter and line-separator detection, skipEmptyLines and header extraction (Main.kt:289-296, 322); every value
+// then goes through getValue(name, "").trim() into a VarCharVector (Main.kt:262-264). Rules restated here (C1-C9,
+// oracle: ko_csv_scan in oracle/kq_oracle.cpp; parity UNPINNED — see DESIGN.md):
+//   C1 line separator: "\n" (a preceding "\r" is whitespace and trimmed) or, when the text holds no "\n", "\r";
+//      delimiter: the most frequent of , ; TAB | outside quotes in the first record (ties: that order).
+//   C2 quote '"', escaped by doubling; a field whose first non-blank byte is a quote is quoted: delimiters and line
+//      separators inside are data; bytes between the closing quote and the next delimiter are dropped.
+//   C3 records without any byte are skipped (skipEmptyLines).   C4 has_headers: the first record names the columns.
+//   C5 each value is trimmed of leading/trailing bytes <= 0x20 (String.trim(), Main.kt:263), quoted or not.
+//   C6 every column is Utf8 and never null: a missing or empty field reads "" (getValue's default, Main.kt:263).
+//   C7 projection selects/reorders file columns (Main.kt:313-318).   C8 surplus fields of a record are ignored.
+//   C9 one output batch per call (the reference cuts 1000-row batches, Main.kt:396; results do not depend on it).
+//
+// Device pipeline (all HBM-bound byte work; no tensor cores):
+//   1. quote scan      : device-wide exclusive sum of '"' counts per 64-byte block -> quote parity at every block start
+//   2. record scan     : device-wide exclusive sum of record terminators outside quotes (non-empty records only)
+//   3. record ends     : position of every counted terminator
+//   4. field lengths   : one thread per record walks it once, trimmed/unescaped length of every projected field
+//   5. offsets         : one device-wide exclusive sum per projected column -> Arrow int32 offsets
+//   6. copy            : one thread per record walks it again and writes the field bytes
+#include <algorithm>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "kq_internal.h"
+#include "kq_scan.cuh"
+
+using namespace kq;
+
+namespace {
+
+constexpr int CSV_BLOCK = 64;            // bytes per scan item
+constexpr int CSV_MAX_COLS = 256;        // file columns
+
+struct CsvFormat { uint8_t delim, term; };
+
+__device__ __forceinline__ bool csv_blank(uint8_t c) { return c <= 0x20; }
+
+// number of '"' in block i
+struct QuoteCount {
+    const uint8_t* text; long long n;
+    __device__ __forceinline__ int operator()(long long i) const {
+        const long long b = i * CSV_BLOCK;
+        int k = 0;
+        if (b + CSV_BLOCK <= n) {
+            const uint4* p = reinterpret_cast<const uint4*>(text + b);
+#pragma unroll
+            for (int j = 0; j < CSV_BLOCK / 16; j++) {
+                const uint4 v = __ldg(p + j);
+                const uint32_t w[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+                for (int t = 0; t < 4; t++) {
+                    uint32_t x = w[t] ^ 0x22222222u;                            // zero byte where the text has a quote
+                    x = ~(((x & 0x7F7F7F7Fu) + 0x7F7F7F7Fu) | x) & 0x80808080u;  // 0x80 in every zero byte (exact)
+                    k += __popc(x);
+                }
+            }
+        } else {
+            for (long long j = b; j < n; j++) k += text[j] == '"';
+        }
+        return k;
+    }
+};
+
+// Is the terminator at position p the end of a NON-EMPTY record? (rule C3; p is outside quotes, so are the bytes before it
+// unless they are quotes themselves, which makes the record non-empty anyway)
+__device__ __forceinline__ bool csv_ends_record(const uint8_t* text, long long p, CsvFormat f) {
+    if (p == 0) return false;
+    const uint8_t a = text[p - 1];
+    if (a == f.term) return false;
+    if (f.term == '\n' && a == '\r') return !(p == 1 || text[p - 2] == '\n');
+    return true;
+}
+
+// record terminators (outside quotes, non-empty records) in block i; with `ends`, also their positions
+struct RecordCount {
+    const uint8_t* text; long long n; const int32_t* quotes_before; CsvFormat f;
+    long long* ends; const int32_t* recs_before;
+    __device__ __forceinline__ int operator()(long long i) const {
+        const long long b = i * CSV_BLOCK, e = b + CSV_BLOCK < n ? b + CSV_BLOCK : n;
+        uint32_t inq = (uint32_t)quotes_before[i] & 1u;
+        int k = 0;
+        for (long long p = b; p < e; p++) {
+            const uint8_t c = text[p];
+            if (c == '"') inq ^= 1u;
+            else if (c == f.term && !inq && csv_ends_record(text, p, f)) {
+                if (ends) ends[recs_before[i] + k] = p;
+                k++;
+            }
+        }
+        return k;
+    }
+};
+__global__ void k_csv_record_ends(RecordCount rc, long long nblocks) {
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < nblocks; i += (long long)gridDim.x * blockDim.x) rc(i);
+}
+
+// One record = bytes [b, e) (e = its terminator). Visit(col, first, last): raw field bytes [first, last) of file column col.
+template <class Visit>
+__device__ __forceinline__ void csv_walk_record(const uint8_t* text, long long b, long long e, CsvFormat f, Visit&& visit) {
+    // skipped empty records in front of this one consist of terminator bytes (and "\r") only
+    while (b < e && (text[b] == f.term || (f.term == '\n' && text[b] == '\r' && b + 1 < e && text[b + 1] == '\n'))) b++;
+    int col = 0;
+    long long first = b;
+    bool inq = false;
+    for (long long p = b; p <= e; p++) {
+        const uint8_t c = p < e ? text[p] : f.delim;
+        if (c == '"') inq = !inq;
+        else if ((c == f.delim && !inq) || p == e) {
+            visit(col, first, p);
+            col++;
+            first = p + 1;
+        }
+    }
+}
+// Trimmed, unquoted value of the raw field [first, last): returns its length; with `out`, also writes it.
+__device__ __forceinline__ int csv_value(const uint8_t* text, long long first, long long last, uint8_t* out) {
+    while (first < last && csv_blank(text[first])) first++;
+    while (last > first && csv_blank(text[last - 1])) last--;
+    if (first < last && text[first] == '"') {                  // quoted (rule C2): content up to the closing quote
+        long long p = first + 1, q = p;
+        // find the closing quote: a quote not followed by a quote
+        while (q < last && !(text[q] == '"' && !(q + 1 < last && text[q + 1] == '"'))) q += (text[q] == '"') ? 2 : 1;
+        if (q > last) q = last;
+        // trim the content (String.trim() runs on the parsed value, rule C5)
+        while (p < q && csv_blank(text[p])) p++;
+        while (q > p && csv_blank(text[q - 1])) q--;
+        int len = 0;
+        for (long long j = p; j < q; j++) {
+            if (out) out[len] = text[j];
+            len++;
+            if (text[j] == '"' && j + 1 < q && text[j + 1] == '"') j++;       // "" -> "
+        }
+        return len;
+    }
+    const int len = (int)(last - first);
+    if (out) for (int j = 0; j < len; j++) out[j] = text[first + j];
+    return len;
+}
+
+struct CsvCols {
+    int16_t out_of[CSV_MAX_COLS];       // file column -> output column, -1: not projected
+    int32_t* lens[CSV_MAX_COLS];        // per output column: lengths, later Arrow offsets (device)
+    uint8_t* data[CSV_MAX_COLS];
+    int nout;
+};
+
+// pass 4: lengths of the projected fields of every data record (missing fields: 0, rule C6)
+__global__ void k_csv_field_lengths(const uint8_t* __restrict__ text, const long long* __restrict__ ends, long long nrec, int skip,
+                                    CsvFormat f, const CsvCols* __restrict__ cols) {
+    for (long long r = blockIdx.x * (long long)blockDim.x + threadIdx.x; r + skip < nrec; r += (long long)gridDim.x * blockDim.x) {
+        const long long rec = r + skip;
+        for (int c = 0; c < cols->nout; c++) if (cols->lens[c]) cols->lens[c][r] = 0;       // (a column projected twice is materialised once)
+        csv_walk_record(text, rec ? ends[rec - 1] + 1 : 0, ends[rec], f, [&](int col, long long a, long long b) {
+            if (col < CSV_MAX_COLS && cols->out_of[col] >= 0) cols->lens[cols->out_of[col]][r] = csv_value(text, a, b, nullptr);
+        });
+    }
+}
+struct LenAt {
+    const int32_t* lens;
+    __device__ __forceinline__ int operator()(long long i) const { return lens[i]; }
+};
+// pass 6: the bytes
+__global__ void k_csv_copy(const uint8_t* __restrict__ text, const long long* __restrict__ ends, long long nrec, int skip, CsvFormat f,
+                           const CsvCols* __restrict__ cols) {
+    for (long long r = blockIdx.x * (long long)blockDim.x + threadIdx.x; r + skip < nrec; r += (long long)gridDim.x * blockDim.x) {
+        const long long rec = r + skip;
+        csv_walk_record(text, rec ? ends[rec - 1] + 1 : 0, ends[rec], f, [&](int col, long long a, long long b) {
+            if (col < CSV_MAX_COLS && cols->out_of[col] >= 0) {
+                const int oc = cols->out_of[col];
+                csv_value(text, a, b, cols->data[oc] + cols->lens[oc][r]);      // lens now holds the exclusive offsets
+            }
+        });
+    }
+}
+
+// ---- host side: format detection and the header record (rules C1, C4) ---------------------------------------------
+struct HostRecord { std::vector<std::string> fields; int64_t end = 0; };    // end: index just past the record's terminator
+
+static void host_trim(std::string& s) {
+    size_t a = 0, b = s.size();
+    while (a < b && (unsigned char)s[a] <= 0x20) a++;
+    while (b > a && (unsigned char)s[b - 1] <= 0x20) b--;
+    s = s.substr(a, b - a);
+}
+// First NON-EMPTY record (rule C3, the same test as csv_ends_record): [b, e) without its terminator; false if there is none.
+static bool host_first_line(const uint8_t* t, int64_t n, uint8_t term, int64_t* b, int64_t* e) {
+    int64_t start = 0;
+    bool inq = false;
+    for (int64_t p = 0; p <= n; p++) {
+        const bool at_end = p == n;
+        const uint8_t c = at_end ? term : t[p];
+        if (c == '"' && !at_end) inq = !inq;
+        else if (c == term && (!inq || at_end)) {
+            int64_t end = p;
+            const bool empty = end == start || (term == '\n' && end == start + 1 && t[start] == '\r');
+            if (!empty) { *b = start; *e = end; return true; }
+            start = p + 1;
+        }
+    }
+    return false;
+}
+static CsvFormat host_detect(const uint8_t* t, int64_t n) {
+    CsvFormat f{',', '\n'};
+    if (!memchr(t, '\n', (size_t)n) && memchr(t, '\r', (size_t)n)) f.term = '\r';
+    int64_t b, e;
+    if (!host_first_line(t, n, f.term, &b, &e)) return f;
+    int64_t cnt[4] = {0, 0, 0, 0};
+    const uint8_t cand[4] = {',', ';', '\t', '|'};
+    bool inq = false;
+    for (int64_t p = b; p < e; p++) {
+        const uint8_t c = t[p];
+        if (c == '"') inq = !inq;
+        else if (!inq) for (int k = 0; k < 4; k++) cnt[k] += c == cand[k];
+    }
+    int best = 0;
+    for (int k = 1; k < 4; k++) if (cnt[k] > cnt[best]) best = k;
+    f.delim = cand[best];
+    return f;
+}
+static HostRecord host_first_record(const uint8_t* t, int64_t n, CsvFormat f) {
+    HostRecord r;
+    int64_t b, e;
+    if (!host_first_line(t, n, f.term, &b, &e)) { r.end = n; return r; }
+    r.end = e;
+    int64_t first = b;
+    bool inq = false;
+    for (int64_t p = b; p <= e; p++) {
+        const uint8_t c = p < e ? t[p] : f.delim;
+        if (c == '"' && p < e) { inq = !inq; continue; }
+        if (p == e || (!inq && c == f.delim)) {
+            std::string raw((const char*)t + first, (size_t)(p - first));
+            host_trim(raw);
+            if (!raw.empty() && raw[0] == '"') {
+                std::string v;
+                size_t q = 1;
+                while (q < raw.size() && !(raw[q] == '"' && !(q + 1 < raw.size() && raw[q + 1] == '"'))) { v += raw[q]; q += raw[q] == '"' ? 2 : 1; }
+                host_trim(v);
+                raw = v;
+            }
+            r.fields.push_back(raw);
+            first = p + 1;
+        }
+    }
+    return r;
+}
+
+}  // namespace
+
+extern "C" {
+
+int kq_csv_header(const uint8_t* text, int64_t nbytes, int has_headers, char* names, size_t names_cap, int* ncols, char* delimiter) {
+    if (!text || nbytes < 0 || !ncols) return KQ_ERR_ILLEGAL_ARGUMENT;
+    const CsvFormat f = host_detect(text, nbytes);
+    const HostRecord h = host_first_record(text, nbytes, f);
+    *ncols = (int)h.fields.size();
+    if (delimiter) *delimiter = (char)f.delim;
+    if (names && names_cap) {
+        std::string all;
+        for (size_t i = 0; i < h.fields.size(); i++) {
+            all += has_headers ? h.fields[i] : "field_" + std::to_string(i + 1);      // Main.kt:345-349
+            all += '\n';
+        }
+        if (all.size() + 1 > names_cap) return KQ_ERR_ILLEGAL_ARGUMENT;
+        memcpy(names, all.c_str(), all.size() + 1);
+    }
+    return KQ_OK;
+}
+
+int kq_csv_scan(kq_ctx* ctx, const uint8_t* text, int64_t nbytes, int has_headers, const int* projection, int nproj, kq_batch** out) {
+    if (!ctx || !out || nbytes < 0 || (nbytes && !text) || nproj < 0 || (nproj && !projection)) return KQ_ERR_ILLEGAL_ARGUMENT;
+    if (nbytes >= (1LL << 31) - 2 * CSV_BLOCK) return kq_fail(ctx, KQ_ERR_UNSUPPORTED, "CSV text of 2 GiB or more: scan it in pieces (Arrow int32 offsets)");
+    cudaSetDevice(ctx->device);
+    const CsvFormat f = nbytes ? host_detect(text, nbytes) : CsvFormat{',', '\n'};
+    const HostRecord head = nbytes ? host_first_record(text, nbytes, f) : HostRecord();
+    const int file_cols = (int)head.fields.size();
+    if (file_cols > CSV_MAX_COLS) return kq_fail(ctx, KQ_ERR_UNSUPPORTED, "more than %d CSV columns", CSV_MAX_COLS);
+    std::vector<int> proj;
+    if (nproj) proj.assign(projection, projection + nproj);
+    else for (int i = 0; i < file_cols; i++) proj.push_back(i);
+    const int nout = (int)proj.size();
+    for (int c : proj)
+        if (c < 0 || c >= file_cols) return kq_fail(ctx, KQ_ERR_ILLEGAL_ARGUMENT, "projected CSV column %d out of range (file has %d)", c, file_cols);   // Schema.select, Main.kt:47-52
+
+    // the text on the device, terminated (a last record without a line separator still ends)
+    const bool add_term = nbytes > 0 && text[nbytes - 1] != f.term;
+    const long long n = nbytes + (add_term ? 1 : 0);
+    const long long nblocks = (n + CSV_BLOCK - 1) / CSV_BLOCK;
+    uint8_t* d_text = nullptr;
+    int32_t *d_q = nullptr, *d_r = nullptr;
+    unsigned long long* d_scratch = nullptr;        // [0] ticket, [1] total, [2] item count, [4..] tile descriptors
+    long long* d_ends = nullptr;
+    CsvCols* d_cols = nullptr;
+    std::vector<kq_col*> cols;
+    // tile descriptors of the device-wide scans: over 64-byte blocks (passes 1-2) and over records (pass 5; a record has at
+    // least two bytes, so nblocks * 32 bounds the record count)
+    const long long ntiles = (std::max<long long>(nblocks, 1) * (CSV_BLOCK / 2) + SCAN_TILE - 1) / SCAN_TILE + 2;
+    auto cleanup = [&](int st) {
+        kq_dev_free(ctx, d_text); kq_dev_free(ctx, d_q); kq_dev_free(ctx, d_r); kq_dev_free(ctx, d_scratch); kq_dev_free(ctx, d_ends); kq_dev_free(ctx, d_cols);
+        if (st != KQ_OK) for (kq_col* c : cols) kq_column_free(c);
+        return st;
+    };
+    auto make_batch = [&](int64_t rows) {
+        kq_batch* b = new kq_batch();
+        b->ctx = ctx; b->n = rows; b->cols = cols;
+        *out = b;
+        return KQ_OK;
+    };
+    int64_t nrec = 0;
+    int st = KQ_OK;
+    if (n > 0) {
+        if ((st = kq_dev_alloc(ctx, (size_t)n + 16, (void**)&d_text)) != KQ_OK) return cleanup(st);
+        if ((st = kq_dev_alloc(ctx, (size_t)(nblocks + 1) * 4, (void**)&d_q)) != KQ_OK) return cleanup(st);
+        if ((st = kq_dev_alloc(ctx, (size_t)(nblocks + 1) * 4, (void**)&d_r)) != KQ_OK) return cleanup(st);
+        if ((st = kq_dev_alloc(ctx, (size_t)(ntiles + 4) * 8, (void**)&d_scratch)) != KQ_OK) return cleanup(st);
+        if (cudaMemcpyAsync(d_text, text, (size_t)nbytes, cudaMemcpyHostToDevice, ctx->stream) != cudaSuccess) return cleanup(kq_cuda_fail(ctx, cudaGetLastError(), "cudaMemcpyAsync(csv text)"));
+        if (add_term) cudaMemsetAsync(d_text + nbytes, f.term, 1, ctx->stream);
+        const unsigned long long items = (unsigned long long)nblocks;
+        auto scan_begin = [&](unsigned long long count) {
+            cudaMemsetAsync(d_scratch, 0, (size_t)(ntiles + 4) * 8, ctx->stream);
+            cudaMemcpyAsync(d_scratch + 2, &count, 8, cudaMemcpyHostToDevice, ctx->stream);
+        };
+        const int sg = (int)std::max<long long>(1, std::min<long long>((nblocks + SCAN_TILE - 1) / SCAN_TILE, (long long)ctx->sm_count * 4));
+        // 1. quotes before every block
+        scan_begin(items);
+        k_exclusive_offsets<QuoteCount><<<sg, 256, 0, ctx->stream>>>(QuoteCount{d_text, n}, d_scratch + 2, d_q, d_scratch + 4, (unsigned int*)d_scratch, d_scratch + 1);
+        if (cudaGetLastError() != cudaSuccess) return cleanup(kq_cuda_fail(ctx, cudaGetLastError(), "k_exclusive_offsets(quotes)"));
+        ctx->launches++;
+        uint64_t total = 0;
+        if ((st = kq_read_u64(ctx, d_scratch + 1, 1, &total)) != KQ_OK) return cleanup(st);
+        if (total & 1) return cleanup(kq_fail(ctx, KQ_ERR_ILLEGAL_STATE, "CSV text ends inside a quoted field"));
+        // 2. records before every block
+        scan_begin(items);
+        k_exclusive_offsets<RecordCount><<<sg, 256, 0, ctx->stream>>>(RecordCount{d_text, n, d_q, f, nullptr, nullptr}, d_scratch + 2, d_r, d_scratch + 4,
+                                                                       (unsigned int*)d_scratch, d_scratch + 1);
+        if (cudaGetLastError() != cudaSuccess) return cleanup(kq_cuda_fail(ctx, cudaGetLastError(), "k_exclusive_offsets(records)"));
+        ctx->launches++;
+        if ((st = kq_read_u64(ctx, d_scratch + 1, 1, &total)) != KQ_OK) return cleanup(st);
+        nrec = (int64_t)total;
+    }
+    const int skip = has_headers && nrec > 0 ? 1 : 0;
+    const int64_t rows = nrec - skip;
+    if (rows <= 0 || nout == 0) {            // no data records: zero-row columns (Main.kt:245-247 yields no batch; one empty batch here, rule R10's shape)
+        for (int c = 0; c < nout; c++) {
+            kq_col* col = nullptr;
+            if ((st = kq_col_new(ctx, KQ_UTF8, 0, false, 0, &col)) != KQ_OK) return cleanup(st);
+            cudaMemsetAsync(col->offsets, 0, 4, ctx->stream);
+            cols.push_back(col);
+        }
+        make_batch(std::max<int64_t>(rows, 0));
+        return cleanup(KQ_OK);
+    }
+    // 3. record ends
+    if ((st = kq_dev_alloc(ctx, (size_t)nrec * 8, (void**)&d_ends)) != KQ_OK) return cleanup(st);
+    const int g = (int)std::max<long long>(1, std::min<long long>((nblocks + 255) / 256, (long long)ctx->sm_count * 8));
+    k_csv_record_ends<<<g, 256, 0, ctx->stream>>>(RecordCount{d_text, n, d_q, f, d_ends, d_r}, nblocks);
+    if (cudaGetLastError() != cudaSuccess) return cleanup(kq_cuda_fail(ctx, cudaGetLastError(), "k_csv_record_ends"));
+    ctx->launches++;
+    // 4. field lengths (into scratch arrays; the columns' offsets buffers are written by the scans below)
+    CsvCols hc;
+    memset(&hc, 0, sizeof hc);
+    for (int i = 0; i < CSV_MAX_COLS; i++) hc.out_of[i] = -1;
+    hc.nout = nout;
+    std::vector<int32_t*> d_len((size_t)nout, nullptr);
+    auto cleanup2 = [&](int s2) { for (int32_t* p : d_len) kq_dev_free(ctx, p); return cleanup(s2); };
+    // a file column projected twice is materialised once and shared (ColumnExpression aliasing, rule R4)
+    std::vector<int> first_out((size_t)file_cols, -1);
+    for (int c = 0; c < nout; c++) {
+        if (first_out[(size_t)proj[(size_t)c]] >= 0) continue;
+        first_out[(size_t)proj[(size_t)c]] = c;
+        hc.out_of[proj[(size_t)c]] = (int16_t)c;
+        if ((st = kq_dev_alloc(ctx, (size_t)(rows + 1) * 4, (void**)&d_len[(size_t)c])) != KQ_OK) return cleanup2(st);
+        hc.lens[c] = d_len[(size_t)c];
+    }
+    if ((st = kq_dev_alloc(ctx, sizeof hc, (void**)&d_cols)) != KQ_OK) return cleanup2(st);
+    cudaMemcpyAsync(d_cols, &hc, sizeof hc, cudaMemcpyHostToDevice, ctx->stream);
+    const int gr = (int)std::max<long long>(1, std::min<long long>((rows + 127) / 128, (long long)ctx->sm_count * 16));
+    k_csv_field_lengths<<<gr, 128, 0, ctx->stream>>>(d_text, d_ends, nrec, skip, f, d_cols);
+    if (cudaGetLastError() != cudaSuccess) return cleanup2(kq_cuda_fail(ctx, cudaGetLastError(), "k_csv_field_lengths"));
+    ctx->launches++;
+    // 5. offsets per materialised column, then the data buffers
+    std::vector<uint64_t> bytes((size_t)nout, 0);
+    std::vector<int32_t*> d_off((size_t)nout, nullptr);
+    auto cleanup3 = [&](int s2) { for (int32_t* p : d_off) kq_dev_free(ctx, p); return cleanup2(s2); };
+    const int sgr = (int)std::max<long long>(1, std::min<long long>((rows + SCAN_TILE - 1) / SCAN_TILE, (long long)ctx->sm_count * 4));
+    for (int c = 0; c < nout; c++) {
+        if (!d_len[(size_t)c]) continue;
+        if ((st = kq_dev_alloc(ctx, (size_t)(rows + 1) * 4, (void**)&d_off[(size_t)c])) != KQ_OK) return cleanup3(st);
+        cudaMemsetAsync(d_scratch, 0, (size_t)(ntiles + 4) * 8, ctx->stream);
+        const unsigned long long count = (unsigned long long)rows;
+        cudaMemcpyAsync(d_scratch + 2, &count, 8, cudaMemcpyHostToDevice, ctx->stream);
+        k_exclusive_offsets<LenAt><<<sgr, 256, 0, ctx->stream>>>(LenAt{d_len[(size_t)c]}, d_scratch + 2, d_off[(size_t)c], d_scratch + 4, (unsigned int*)d_scratch, d_scratch + 1);
+        if (cudaGetLastError() != cudaSuccess) return cleanup3(kq_cuda_fail(ctx, cudaGetLastError(), "k_exclusive_offsets(column)"));
+        ctx->launches++;
+        if ((st = kq_read_u64(ctx, d_scratch + 1, 1, &bytes[(size_t)c])) != KQ_OK) return cleanup3(st);
+        if (bytes[(size_t)c] >= (1ULL << 31)) return cleanup3(kq_fail(ctx, KQ_ERR_UNSUPPORTED, "CSV column of 2 GiB or more"));
+    }
+    cols.assign((size_t)nout, nullptr);
+    for (int c = 0; c < nout; c++) {
+        if (!d_len[(size_t)c]) continue;
+        kq_col* col = nullptr;
+        if ((st = kq_col_new(ctx, KQ_UTF8, rows, false, (int64_t)bytes[(size_t)c], &col)) != KQ_OK) { cols.erase(std::remove(cols.begin(), cols.end(), nullptr), cols.end()); return cleanup3(st); }
+        cudaMemcpyAsync(col->offsets, d_off[(size_t)c], (size_t)(rows + 1) * 4, cudaMemcpyDeviceToDevice, ctx->stream);
+        cols[(size_t)c] = col;
+        hc.lens[c] = col->offsets;
+        hc.data[c] = (uint8_t*)col->data;
+    }
+    for (int c = 0; c < nout; c++)
+        if (!cols[(size_t)c]) { kq_col* src = cols[(size_t)first_out[(size_t)proj[(size_t)c]]]; src->rc.fetch_add(1); cols[(size_t)c] = src; }
+    // 6. the bytes (the table of pointers changed: lens now = offsets)
+    CsvCols* d_cols2 = nullptr;
+    if ((st = kq_dev_alloc(ctx, sizeof hc, (void**)&d_cols2)) != KQ_OK) return cleanup3(st);
+    cudaMemcpyAsync(d_cols2, &hc, sizeof hc, cudaMemcpyHostToDevice, ctx->stream);
+    k_csv_copy<<<gr, 128, 0, ctx->stream>>>(d_text, d_ends, nrec, skip, f, d_cols2);
+    st = cudaGetLastError() != cudaSuccess ? kq_cuda_fail(ctx, cudaGetLastError(), "k_csv_copy") : KQ_OK;
+    ctx->launches++;
+    // hc lives on the host stack: the two pageable uploads above were staged synchronously by the runtime
+    if (st == KQ_OK) st = cudaStreamSynchronize(ctx->stream) == cudaSuccess ? KQ_OK : kq_cuda_fail(ctx, cudaGetLastError(), "cudaStreamSynchronize(csv)");
+    kq_dev_free(ctx, d_cols2);
+    if (st != KQ_OK) return cleanup3(st);
+    make_batch(rows);
+    return cleanup3(KQ_OK);
+}
+
+}  // extern "C"

@@ -113,6 +113,8 @@ SYMBOLS = {
     "kq_hashagg_merge_allreduce": (C.c_int, [_P, _P]),
     "kq_hashagg_repartition_alltoall": (C.c_int, [_P, _P]),
     "kq_generate": (C.c_int, [_P, C.POINTER(GenSpec), C.c_int, C.c_uint64, C.c_int64, C.c_int64, _PP]),
+    "kq_csv_header": (C.c_int, [C.c_char_p, C.c_int64, C.c_int, C.c_char_p, C.c_size_t, C.POINTER(C.c_int), C.c_char_p]),
+    "kq_csv_scan": (C.c_int, [_P, C.c_char_p, C.c_int64, C.c_int, C.POINTER(C.c_int), C.c_int, _PP]),
 }
 
 _lib = None
@@ -490,6 +492,31 @@ class Engine(Exprs):
 
     def HashAggregate(self, group_exprs, aggs, pred=None, expected_groups=0):
         return HashAggregate(self, group_exprs, aggs, pred, expected_groups)
+
+    @staticmethod
+    def csv_header(text: bytes, has_headers=True):
+        """CsvDataSource.schema() (Main.kt:328-356): (column names, detected delimiter); every column is Utf8."""
+        names = C.create_string_buffer(1 << 16)
+        n, d = C.c_int(), C.create_string_buffer(2)
+        st = lib().kq_csv_header(text, len(text), int(bool(has_headers)), names, len(names), C.byref(n), d)
+        if st != 0:
+            raise KqError(st, "kq_csv_header")
+        return names.value.decode("utf-8").split("\n")[:n.value], d.raw[:1].decode()
+
+    def csv_scan(self, text: bytes, has_headers=True, projection=None) -> RecordBatch:
+        """CsvDataSource.scan(projection) (Main.kt:304-326): the text of a CSV file -> one batch of Utf8 columns on the
+        device. `projection`: column NAMES in output order (Schema.select, Main.kt:47-52); None/[] = all columns."""
+        idx = []
+        if projection:
+            names, _ = self.csv_header(text, has_headers)
+            for p in projection:
+                if p not in names:
+                    raise KqError(3, f"Field {p} not found")        # KQ_ERR_ILLEGAL_ARGUMENT = IllegalArgumentException, Main.kt:49
+                idx.append(names.index(p))
+        arr = (C.c_int * max(len(idx), 1))(*idx)
+        out = C.c_void_p()
+        self.ctx.check(lib().kq_csv_scan(self.ctx.h, text, len(text), int(bool(has_headers)), arr if idx else None, len(idx), C.byref(out)))
+        return RecordBatch(self.ctx, out)
 
     def generate(self, specs, seed, row_begin, row_end) -> RecordBatch:
         arr, keep = make_specs(specs)

@@ -33,6 +33,8 @@ def where_state(val):
 
 golden = {
     "source": "kquerydiy/employee.csv (157 bytes) read with csv.reader + strip()",
+    # the fixture's bytes (data, not code), so that the CSV scan tests can run where /root/reference does not exist
+    "csv_text_hex": open(SRC, "rb").read().hex(),
     "schema": header,
     "columns": cols,
     "last_name_row3_utf8_hex": cols["last_name"][2].encode("utf-8").hex(),
