@@ -134,12 +134,61 @@ class GroupBy(Workload):
         return per_row * n + 40 * out_rows
 
 
+class CsvScan(Workload):
+    """CsvDataSource.scan (Main.kt:276-357) on the device — CSV text -> Utf8 columns."""
+
+    kernel = "k_csv_field_lengths+k_csv_copy"
+
+    def __init__(self, name, rows):
+        super().__init__(name, rows, "u8")
+        self.describe = "CsvDataSource.scan: CSV text (6 columns, ~39 B/record, quoted fields with delimiters/line breaks) -> 6 Utf8 columns"
+        self.text = None
+
+    def make_text(self, rows, seed=7):
+        """`rows` records: a 100k-record block of tests/csv_cases.synthetic repeated (ids repeat; synthetic data)."""
+        sys.path.insert(0, os.path.join(ROOT, "tests"))
+        from csv_cases import synthetic
+        blk_rows = min(rows, 100_000)
+        t = synthetic(blk_rows, seed=seed)
+        head, body = t.split(b"\n", 1)
+        # whole blocks only, so that every record is complete; the tail is cut from a fresh block at a record boundary
+        reps, rest = divmod(rows, blk_rows)
+        tail = b""
+        if rest:
+            tail = synthetic(rest, seed=seed).split(b"\n", 1)[1]
+        return head + b"\n" + body * reps + tail
+
+    def prepare(self, E, ctx, row0, row1):
+        """The file's bytes resident in HBM (uploaded as an Int64 column; padded with empty lines, which rule C3 skips)."""
+        import numpy as np
+        import pyarrow as pa
+        import kqgpu
+        self.text = self.make_text(row1 - row0)
+        pad = (-len(self.text)) % 8
+        self.dev = kqgpu.Column.from_arrow(ctx, pa.array(np.frombuffer(self.text + b"\n" * pad, dtype=np.int64)))
+        self.dev_ptr = self.dev.device_ptrs()[2]
+        self.nbytes = len(self.text) + pad
+        return self.dev
+
+    def run(self, E, batch, dist=None):
+        return E.csv_scan_ptr(self.dev_ptr, self.nbytes, True)
+
+    def result_rows(self, res):
+        sizes = [res.field(i).sizes() for i in range(res.num_columns())]
+        self.out_bytes = sum(nb + 4 * (n + 1) for n, nb, _ in sizes)           # Arrow data + offsets buffers written
+        return res.row_count()
+
+    def algo_bytes(self, n, out_rows):
+        return self.nbytes + getattr(self, "out_bytes", 0)         # the text read once + the Arrow buffers written once
+
+
 WORKLOADS = {
     "cfg2f": lambda rows: FilterProject("cfg2f", rows or 100_000_000, True),
     "cfg2i": lambda rows: FilterProject("cfg2i", rows or 100_000_000, False),
     "cfg3": lambda rows: GroupBy("cfg3", rows or 1_000_000_000, "low"),
     "cfg4": lambda rows: GroupBy("cfg4", rows or 1_000_000_000, "high"),
     "cfg5": lambda rows: GroupBy("cfg5", rows or 600_037_902, "q1"),
+    "csv": lambda rows: CsvScan("csv", rows or 10_000_000),
 }
 
 
@@ -214,6 +263,12 @@ def cpu_reference(wl, sample_rows, threads, seed=42):
     """Time the CPU oracle (port of the Kotlin operators) on `sample_rows` rows of the same workload."""
     from oracle import oracle as O
     O.build()
+    if isinstance(wl, CsvScan):                # single-threaded, like the reference's ReaderIterator (Main.kt:204-273)
+        text = wl.make_text(sample_rows)
+        t0 = time.perf_counter()
+        out_rows = O.csv_scan(text, True).row_count()
+        dt = time.perf_counter() - t0
+        return sample_rows / dt, dt, out_rows
     batch = O.generate(wl.specs(), seed, 0, sample_rows)
 
     t0 = time.perf_counter()
@@ -238,13 +293,13 @@ def cpu_reference(wl, sample_rows, threads, seed=42):
 
 def cpu_sample_rows(wl):
     # sized for roughly 10-20 s of single-thread-equivalent CPU work (the oracle is row-at-a-time and boxed)
-    return {"cfg2f": 24_000_000, "cfg2i": 24_000_000, "cfg3": 16_000_000, "cfg4": 8_000_000, "cfg5": 8_000_000}[wl.name]
+    return {"cfg2f": 24_000_000, "cfg2i": 24_000_000, "cfg3": 16_000_000, "cfg4": 8_000_000, "cfg5": 8_000_000, "csv": 4_000_000}[wl.name]
 
 
 def run_reference(args, wl, rank, world):
     if rank != 0:
         return
-    threads = os.cpu_count() or 1
+    threads = 1 if isinstance(wl, CsvScan) else (os.cpu_count() or 1)
     sample = cpu_sample_rows(wl) // 4
     for _ in range(args.warmup):
         cpu_reference(wl, max(sample // 8, 100_000), threads)
@@ -316,7 +371,7 @@ def main():
     # each rank owns rows [rank*R, (rank+1)*R) of the same global table (weak scaling)
     n = wl.rows
     row0, row1 = shard_range(rank, n)
-    batch = E.generate(wl.specs(), 42, row0, row1)
+    batch = wl.prepare(E, ctx, row0, row1) if hasattr(wl, "prepare") else E.generate(wl.specs(), 42, row0, row1)
     ctx.sync()
 
     def barrier():
@@ -368,7 +423,7 @@ def main():
 
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
-        threads = os.cpu_count() or 1
+        threads = 1 if isinstance(wl, CsvScan) else (os.cpu_count() or 1)      # the reference's CSV reader is one thread (Main.kt:204-273)
         sample = cpu_sample_rows(wl)
         v1, dt1, _ = cpu_reference(wl, sample // 8, 1)
         vn, dtn, _ = cpu_reference(wl, sample, threads)
@@ -400,6 +455,27 @@ def run_e2e(kqgpu, ctx, E, wl, batch, dist, steps, world):
     batch of 32 Mi rows, Main.kt:617-634), merge across ranks, finalize, result batch copied back."""
     import ctypes as C
     L = kqgpu.lib()
+    if isinstance(wl, CsvScan):
+        # the file's bytes in pinned host memory -> kq_csv_scan (H2D inside) -> row count and buffer sizes read back
+        nb = len(wl.text)
+        hp = ctx.host_alloc(nb)
+        C.memmove(hp, wl.text, nb)
+
+        def one_csv():
+            res = E.csv_scan_ptr(hp, nb, True)
+            sizes = [res.field(i).sizes() for i in range(res.num_columns())]      # the step's result read back: rows and bytes per column
+            return 8 + 24 * len(sizes), res.row_count()
+        d2h, _ = one_csv()
+        ctx.sync()
+        t0 = time.perf_counter()
+        for _ in range(steps):
+            d2h, _ = one_csv()
+        ctx.sync()
+        dt = time.perf_counter() - t0
+        ctx.host_free(hp)
+        return {"value": world * wl.rows * steps / dt, "unit": "rows/s", "h2d_bytes_per_step": nb, "d2h_bytes_per_step": d2h, "steps": steps,
+                "ms_per_step": dt / steps * 1e3,
+                "how": "CSV text in pinned host memory -> kq_csv_scan (H2D copy + scan kernels) -> row count and column sizes read back, wall clock around synchronised steps"}
     cols = [batch.field(i) for i in range(batch.num_columns())]
     host = []
     h2d = 0

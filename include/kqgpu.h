@@ -240,7 +240,7 @@ KQ_API int kq_hashagg_repartition_alltoall(kq_ctx* ctx, kq_hashagg* agg);
 KQ_API int kq_csv_header(const uint8_t* text, int64_t nbytes, int has_headers, char* names, size_t names_cap,
                          int* ncols, char* delimiter);
 /* CsvDataSource.scan(projection) (Main.kt:304-326) fused with ReaderIterator.createBatch (Main.kt:251-273): the
- * whole text of a CSV file (HOST buffer, < 2 GiB) -> ONE batch of Utf8 columns in HBM, every value trimmed
+ * whole text of a CSV file (< 2 GiB; a HOST buffer, or a DEVICE pointer when the file is already in HBM) -> ONE batch of Utf8 columns in HBM, every value trimmed
  * (Main.kt:263), never null. `projection`: file column indices in output order (NULL/0 = all columns); the caller
  * maps names to indices as Schema.select does (Main.kt:47-52). Rules C1-C9: csrc/kq_csv.cu. */
 KQ_API int kq_csv_scan(kq_ctx* ctx, const uint8_t* text, int64_t nbytes, int has_headers, const int* projection,

@@ -276,8 +276,29 @@ int kq_csv_scan(kq_ctx* ctx, const uint8_t* text, int64_t nbytes, int has_header
     if (!ctx || !out || nbytes < 0 || (nbytes && !text) || nproj < 0 || (nproj && !projection)) return KQ_ERR_ILLEGAL_ARGUMENT;
     if (nbytes >= (1LL << 31) - 2 * CSV_BLOCK) return kq_fail(ctx, KQ_ERR_UNSUPPORTED, "CSV text of 2 GiB or more: scan it in pieces (Arrow int32 offsets)");
     cudaSetDevice(ctx->device);
-    const CsvFormat f = nbytes ? host_detect(text, nbytes) : CsvFormat{',', '\n'};
-    const HostRecord head = nbytes ? host_first_record(text, nbytes, f) : HostRecord();
+    // `text` may also be a DEVICE pointer (a file already resident in HBM: bench.py's device-resident timing). Format
+    // detection and the header record then work on a copy of its first MiB (the first record must end inside it).
+    bool on_device = false;
+    {
+        cudaPointerAttributes at;
+        if (nbytes && cudaPointerGetAttributes(&at, text) == cudaSuccess) on_device = at.type == cudaMemoryTypeDevice;
+        else cudaGetLastError();
+    }
+    std::vector<uint8_t> prefix;
+    uint8_t last_byte = nbytes && !on_device ? text[nbytes - 1] : 0;
+    const uint8_t* htext = text;
+    int64_t hbytes = nbytes;
+    if (on_device) {
+        hbytes = std::min<int64_t>(nbytes, 1 << 20);
+        prefix.resize((size_t)hbytes);
+        KQ_CUDA(ctx, cudaMemcpyAsync(prefix.data(), text, (size_t)hbytes, cudaMemcpyDeviceToHost, ctx->stream));
+        KQ_CUDA(ctx, cudaMemcpyAsync(&last_byte, text + nbytes - 1, 1, cudaMemcpyDeviceToHost, ctx->stream));
+        KQ_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+        htext = prefix.data();
+    }
+    const CsvFormat f = nbytes ? host_detect(htext, hbytes) : CsvFormat{',', '\n'};
+    const HostRecord head = nbytes ? host_first_record(htext, hbytes, f) : HostRecord();
+    if (on_device && hbytes < nbytes && head.end >= hbytes) return kq_fail(ctx, KQ_ERR_UNSUPPORTED, "first CSV record longer than 1 MiB");
     const int file_cols = (int)head.fields.size();
     if (file_cols > CSV_MAX_COLS) return kq_fail(ctx, KQ_ERR_UNSUPPORTED, "more than %d CSV columns", CSV_MAX_COLS);
     std::vector<int> proj;
@@ -288,7 +309,7 @@ int kq_csv_scan(kq_ctx* ctx, const uint8_t* text, int64_t nbytes, int has_header
         if (c < 0 || c >= file_cols) return kq_fail(ctx, KQ_ERR_ILLEGAL_ARGUMENT, "projected CSV column %d out of range (file has %d)", c, file_cols);   // Schema.select, Main.kt:47-52
 
     // the text on the device, terminated (a last record without a line separator still ends)
-    const bool add_term = nbytes > 0 && text[nbytes - 1] != f.term;
+    const bool add_term = nbytes > 0 && last_byte != f.term;
     const long long n = nbytes + (add_term ? 1 : 0);
     const long long nblocks = (n + CSV_BLOCK - 1) / CSV_BLOCK;
     uint8_t* d_text = nullptr;
@@ -318,7 +339,7 @@ int kq_csv_scan(kq_ctx* ctx, const uint8_t* text, int64_t nbytes, int has_header
         if ((st = kq_dev_alloc(ctx, (size_t)(nblocks + 1) * 4, (void**)&d_q)) != KQ_OK) return cleanup(st);
         if ((st = kq_dev_alloc(ctx, (size_t)(nblocks + 1) * 4, (void**)&d_r)) != KQ_OK) return cleanup(st);
         if ((st = kq_dev_alloc(ctx, (size_t)(ntiles + 4) * 8, (void**)&d_scratch)) != KQ_OK) return cleanup(st);
-        if (cudaMemcpyAsync(d_text, text, (size_t)nbytes, cudaMemcpyHostToDevice, ctx->stream) != cudaSuccess) return cleanup(kq_cuda_fail(ctx, cudaGetLastError(), "cudaMemcpyAsync(csv text)"));
+        if (cudaMemcpyAsync(d_text, text, (size_t)nbytes, on_device ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice, ctx->stream) != cudaSuccess) return cleanup(kq_cuda_fail(ctx, cudaGetLastError(), "cudaMemcpyAsync(csv text)"));
         if (add_term) cudaMemsetAsync(d_text + nbytes, f.term, 1, ctx->stream);
         const unsigned long long items = (unsigned long long)nblocks;
         auto scan_begin = [&](unsigned long long count) {

@@ -518,6 +518,16 @@ class Engine(Exprs):
         self.ctx.check(lib().kq_csv_scan(self.ctx.h, text, len(text), int(bool(has_headers)), arr if idx else None, len(idx), C.byref(out)))
         return RecordBatch(self.ctx, out)
 
+    def csv_scan_ptr(self, ptr: int, nbytes: int, has_headers=True, columns=None) -> RecordBatch:
+        """kq_csv_scan on a raw buffer: pinned/pageable host memory or a device pointer (text already in HBM);
+        `columns`: file column indices in output order."""
+        idx = list(columns or [])
+        arr = (C.c_int * max(len(idx), 1))(*idx)
+        out = C.c_void_p()
+        self.ctx.check(lib().kq_csv_scan(self.ctx.h, C.cast(C.c_void_p(ptr), C.c_char_p), nbytes, int(bool(has_headers)),
+                                         arr if idx else None, len(idx), C.byref(out)))
+        return RecordBatch(self.ctx, out)
+
     def generate(self, specs, seed, row_begin, row_end) -> RecordBatch:
         arr, keep = make_specs(specs)
         out = C.c_void_p()
