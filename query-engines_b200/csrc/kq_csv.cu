@@ -85,6 +85,48 @@ struct RecordCount {
         const long long b = i * CSV_BLOCK, e = b + CSV_BLOCK < n ? b + CSV_BLOCK : n;
         uint32_t inq = (uint32_t)quotes_before[i] & 1u;
         int k = 0;
+        if (b + CSV_BLOCK <= n) {
+            // whole block: one bit per byte (SWAR zero-byte test + multiply-gather), quote state by prefix XOR, the
+            // emptiness test of csv_ends_record by shifted masks (carries: the two bytes in front of the block; the
+            // start of the text counts as a terminator at position -1)
+            uint64_t qm = 0, tm = 0, cm = 0;
+            const uint4* p4 = reinterpret_cast<const uint4*>(text + b);
+            const uint32_t tpat = f.term * 0x01010101u;
+#pragma unroll
+            for (int j = 0; j < CSV_BLOCK / 16; j++) {
+                const uint4 v = __ldg(p4 + j);
+                const uint32_t w[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+                for (int t = 0; t < 4; t++) {
+                    auto bits = [](uint32_t x) -> uint64_t {          // bit k = byte k of x is zero
+                        x = ~(((x & 0x7F7F7F7Fu) + 0x7F7F7F7Fu) | x) & 0x80808080u;
+                        return (uint64_t)((((x >> 7) * 0x00204081u) >> 21) & 0xFu);
+                    };
+                    const int sh = 16 * j + 4 * t;
+                    qm |= bits(w[t] ^ 0x22222222u) << sh;
+                    tm |= bits(w[t] ^ tpat) << sh;
+                    cm |= bits(w[t] ^ 0x0D0D0D0Du) << sh;
+                }
+            }
+            uint64_t x = qm;
+            x ^= x << 1; x ^= x << 2; x ^= x << 4; x ^= x << 8; x ^= x << 16; x ^= x << 32;
+            const uint64_t inside = inq ? ~x : x;                                        // in-quote state at every non-quote byte
+            const bool t1 = b == 0 || text[b - 1] == f.term, t2 = b <= 1 || text[b - 2] == f.term;
+            const uint64_t prev_t = (tm << 1) | (uint64_t)t1;
+            uint64_t empty = prev_t;
+            if (f.term == '\n') {
+                const uint64_t prev_c = (cm << 1) | (uint64_t)(b > 0 && text[b - 1] == '\r');
+                const uint64_t prev2_t = (tm << 2) | ((uint64_t)t1 << 1) | (uint64_t)t2;
+                empty |= prev_c & prev2_t;
+            }
+            uint64_t m = tm & ~inside & ~empty;
+            k = __popcll(m);
+            if (ends) {
+                long long* o = ends + recs_before[i];
+                while (m) { *o++ = b + (__ffsll((long long)m) - 1); m &= m - 1; }
+            }
+            return k;
+        }
         for (long long p = b; p < e; p++) {
             const uint8_t c = text[p];
             if (c == '"') inq ^= 1u;
