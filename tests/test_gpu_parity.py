@@ -489,3 +489,28 @@ def test_generator_matches_oracle_bit_for_bit(G, oracle):
         want = oracle.generate(specs, 42, lo, hi).to_arrow()
         for a, w in zip(got, want):
             same(a, w)
+
+
+# ---------------------------------------------------------------- front-end geometry corner cases
+@pytest.mark.parametrize("geom", ["8,8", "4,4", "12,7", "6,10"])
+def test_group_by_is_geometry_independent(G, oracle, geom, monkeypatch):
+    """The tile geometry of the aggregate kernel (KQ_AGG_GEOM, a tuning variable) changes the front end's capacity and the
+    directory size: "8,8" leaves room for exactly the 50 groups in a 256-slot directory (keys displaced from their home
+    bucket: the second-chance probe), "6,10" for fewer than 50 (the surplus keys live in the global table only)."""
+    states = "ALAKAZARCACOCTDEFLGAHIIDILINIAKSKYLAMEMDMAMIMNMSMOMTNENVNHNJNMNYNCNDOHOKORPARISCSDTNTXUTVTVAWAWVWIWY"
+    specs = [dict(kind=5, col_id=0, dict=states, dict_width=2), dict(kind=2, col_id=1, flo=0.0, fhi=1000.0, null_per_10k=100)]
+    n = 300_000
+
+    def run(E, batch):
+        v = E.col(1)
+        a = E.HashAggregate([E.col(0)], [("SUM", v), ("MIN", v), ("MAX", v), ("COUNT", v)], expected_groups=50) if E is G else \
+            E.HashAggregate([E.col(0)], [("SUM", v), ("MIN", v), ("MAX", v), ("COUNT", v)])
+        a.update(batch)
+        return sorted(zip(*[x.to_pylist() for x in a.finalize().to_arrow()]))
+
+    want = run(oracle, oracle.generate(specs, 5, 0, n))
+    monkeypatch.setenv("KQ_AGG_GEOM", geom)
+    got = run(G, G.generate(specs, 5, 0, n))
+    assert len(got) == len(want) == 50
+    for a, b in zip(got, want):
+        assert a[0] == b[0] and a[2:] == b[2:] and abs(a[1] - b[1]) <= 1e-9 * abs(b[1])
