@@ -137,7 +137,7 @@ class GroupBy(Workload):
 class CsvScan(Workload):
     """CsvDataSource.scan (Main.kt:276-357) on the device — CSV text -> Utf8 columns."""
 
-    kernel = "k_csv_field_lengths+k_csv_copy"
+    kernel = "k_csv_fields"
 
     def __init__(self, name, rows):
         super().__init__(name, rows, "u8")

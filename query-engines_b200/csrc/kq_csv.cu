@@ -15,13 +15,16 @@
 //   C7 projection selects/reorders file columns (Main.kt:313-318).   C8 surplus fields of a record are ignored.
 //   C9 one output batch per call (the reference cuts 1000-row batches, Main.kt:396; results do not depend on it).
 //
-// Device pipeline (all HBM-bound byte work; no tensor cores):
-//   1. quote scan      : device-wide exclusive sum of '"' counts per 64-byte block -> quote parity at every block start
-//   2. record scan     : device-wide exclusive sum of record terminators outside quotes (non-empty records only)
-//   3. record ends     : position of every counted terminator
-//   4. field lengths   : one thread per record walks it once, trimmed/unescaped length of every projected field
+// Device pipeline (all HBM-bound byte work; no tensor cores). Passes 1-3 see the text as one bit per byte (SWAR masks
+// over 64-byte blocks), so no pass runs a per-byte state machine:
+//   1. quote scan      : device-wide exclusive sum of '"' counts per block -> quote parity at every block start
+//   2. record scan,    : device-wide exclusive sums of (a) terminators outside quotes that end a non-empty record and
+//      separator scan    (b) field separators = those terminators + delimiters outside quotes
+//   3. separators      : the position of every separator in text order + each record's last separator index; field c of
+//                        a record is then the text between two consecutive separators — no re-parsing
+//   4. field lengths   : one thread per record, trimmed/unescaped length of every projected field
 //   5. offsets         : one device-wide exclusive sum per projected column -> Arrow int32 offsets
-//   6. copy            : one thread per record walks it again and writes the field bytes
+//   6. copy            : one thread per record writes the field bytes
 #include <algorithm>
 #include <cstring>
 #include <string>
@@ -77,89 +80,88 @@ __device__ __forceinline__ bool csv_ends_record(const uint8_t* text, long long p
     return true;
 }
 
-// record terminators (outside quotes, non-empty records) in block i; with `ends`, also their positions
-struct RecordCount {
-    const uint8_t* text; long long n; const int32_t* quotes_before; CsvFormat f;
-    long long* ends; const int32_t* recs_before;
-    __device__ __forceinline__ int operator()(long long i) const {
-        const long long b = i * CSV_BLOCK, e = b + CSV_BLOCK < n ? b + CSV_BLOCK : n;
-        uint32_t inq = (uint32_t)quotes_before[i] & 1u;
-        int k = 0;
-        if (b + CSV_BLOCK <= n) {
-            // whole block: one bit per byte (SWAR zero-byte test + multiply-gather), quote state by prefix XOR, the
-            // emptiness test of csv_ends_record by shifted masks (carries: the two bytes in front of the block; the
-            // start of the text counts as a terminator at position -1)
-            uint64_t qm = 0, tm = 0, cm = 0;
-            const uint4* p4 = reinterpret_cast<const uint4*>(text + b);
-            const uint32_t tpat = f.term * 0x01010101u;
-#pragma unroll
-            for (int j = 0; j < CSV_BLOCK / 16; j++) {
-                const uint4 v = __ldg(p4 + j);
-                const uint32_t w[4] = {v.x, v.y, v.z, v.w};
-#pragma unroll
-                for (int t = 0; t < 4; t++) {
-                    auto bits = [](uint32_t x) -> uint64_t {          // bit k = byte k of x is zero
-                        x = ~(((x & 0x7F7F7F7Fu) + 0x7F7F7F7Fu) | x) & 0x80808080u;
-                        return (uint64_t)((((x >> 7) * 0x00204081u) >> 21) & 0xFu);
-                    };
-                    const int sh = 16 * j + 4 * t;
-                    qm |= bits(w[t] ^ 0x22222222u) << sh;
-                    tm |= bits(w[t] ^ tpat) << sh;
-                    cm |= bits(w[t] ^ 0x0D0D0D0Du) << sh;
-                }
-            }
-            uint64_t x = qm;
-            x ^= x << 1; x ^= x << 2; x ^= x << 4; x ^= x << 8; x ^= x << 16; x ^= x << 32;
-            const uint64_t inside = inq ? ~x : x;                                        // in-quote state at every non-quote byte
-            const bool t1 = b == 0 || text[b - 1] == f.term, t2 = b <= 1 || text[b - 2] == f.term;
-            const uint64_t prev_t = (tm << 1) | (uint64_t)t1;
-            uint64_t empty = prev_t;
-            if (f.term == '\n') {
-                const uint64_t prev_c = (cm << 1) | (uint64_t)(b > 0 && text[b - 1] == '\r');
-                const uint64_t prev2_t = (tm << 2) | ((uint64_t)t1 << 1) | (uint64_t)t2;
-                empty |= prev_c & prev2_t;
-            }
-            uint64_t m = tm & ~inside & ~empty;
-            k = __popcll(m);
-            if (ends) {
-                long long* o = ends + recs_before[i];
-                while (m) { *o++ = b + (__ffsll((long long)m) - 1); m &= m - 1; }
-            }
-            return k;
-        }
-        for (long long p = b; p < e; p++) {
+// One bit per byte of block i: `rec` = terminators outside quotes that end a non-empty record, `delim` = delimiters
+// outside quotes. Whole blocks: SWAR zero-byte test + multiply-gather into 64-bit masks, quote state by prefix XOR, the
+// emptiness test of csv_ends_record by shifted masks (carries: the two bytes in front of the block; the start of the
+// text counts as a terminator at position -1). The last, partial block goes byte by byte.
+struct BlockMasks { uint64_t rec, delim; };
+__device__ __forceinline__ BlockMasks csv_block_masks(const uint8_t* __restrict__ text, long long n, long long i, const int32_t* __restrict__ quotes_before, CsvFormat f) {
+    const long long b = i * CSV_BLOCK;
+    const uint32_t inq = (uint32_t)quotes_before[i] & 1u;
+    BlockMasks m{0, 0};
+    if (b + CSV_BLOCK > n) {
+        uint32_t q = inq;
+        for (long long p = b; p < n; p++) {
             const uint8_t c = text[p];
-            if (c == '"') inq ^= 1u;
-            else if (c == f.term && !inq && csv_ends_record(text, p, f)) {
-                if (ends) ends[recs_before[i] + k] = p;
-                k++;
-            }
+            if (c == '"') q ^= 1u;
+            else if (!q && c == f.term) { if (csv_ends_record(text, p, f)) m.rec |= 1ULL << (p - b); }
+            else if (!q && c == f.delim) m.delim |= 1ULL << (p - b);
         }
-        return k;
+        return m;
+    }
+    uint64_t qm = 0, tm = 0, cm = 0, dm = 0;
+    const uint4* p4 = reinterpret_cast<const uint4*>(text + b);
+    const uint32_t tpat = f.term * 0x01010101u, dpat = f.delim * 0x01010101u;
+#pragma unroll
+    for (int j = 0; j < CSV_BLOCK / 16; j++) {
+        const uint4 v = __ldg(p4 + j);
+        const uint32_t w[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+        for (int t = 0; t < 4; t++) {
+            auto bits = [](uint32_t x) -> uint64_t {          // bit k = byte k of x is zero
+                x = ~(((x & 0x7F7F7F7Fu) + 0x7F7F7F7Fu) | x) & 0x80808080u;
+                return (uint64_t)((((x >> 7) * 0x00204081u) >> 21) & 0xFu);
+            };
+            const int sh = 16 * j + 4 * t;
+            qm |= bits(w[t] ^ 0x22222222u) << sh;
+            tm |= bits(w[t] ^ tpat) << sh;
+            cm |= bits(w[t] ^ 0x0D0D0D0Du) << sh;
+            dm |= bits(w[t] ^ dpat) << sh;
+        }
+    }
+    uint64_t x = qm;
+    x ^= x << 1; x ^= x << 2; x ^= x << 4; x ^= x << 8; x ^= x << 16; x ^= x << 32;
+    const uint64_t inside = inq ? ~x : x;                                        // in-quote state at every non-quote byte
+    const bool t1 = b == 0 || text[b - 1] == f.term, t2 = b <= 1 || text[b - 2] == f.term;
+    uint64_t empty = (tm << 1) | (uint64_t)t1;
+    if (f.term == '\n') {
+        const uint64_t prev_c = (cm << 1) | (uint64_t)(b > 0 && text[b - 1] == '\r');
+        const uint64_t prev2_t = (tm << 2) | ((uint64_t)t1 << 1) | (uint64_t)t2;
+        empty |= prev_c & prev2_t;
+    }
+    m.rec = tm & ~inside & ~empty;
+    m.delim = dm & ~inside;
+    return m;
+}
+struct RecordCount {          // records ending in block i
+    const uint8_t* text; long long n; const int32_t* quotes_before; CsvFormat f;
+    __device__ __forceinline__ int operator()(long long i) const { return __popcll(csv_block_masks(text, n, i, quotes_before, f).rec); }
+};
+struct SeparatorCount {       // field separators in block i: delimiters + record ends
+    const uint8_t* text; long long n; const int32_t* quotes_before; CsvFormat f;
+    __device__ __forceinline__ int operator()(long long i) const {
+        const BlockMasks m = csv_block_masks(text, n, i, quotes_before, f);
+        return __popcll(m.rec | m.delim);
     }
 };
-__global__ void k_csv_record_ends(RecordCount rc, long long nblocks) {
-    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < nblocks; i += (long long)gridDim.x * blockDim.x) rc(i);
-}
-
-// One record = bytes [b, e) (e = its terminator). Visit(col, first, last): raw field bytes [first, last) of file column col.
-template <class Visit>
-__device__ __forceinline__ void csv_walk_record(const uint8_t* text, long long b, long long e, CsvFormat f, Visit&& visit) {
-    // skipped empty records in front of this one consist of terminator bytes (and "\r") only
-    while (b < e && (text[b] == f.term || (f.term == '\n' && text[b] == '\r' && b + 1 < e && text[b + 1] == '\n'))) b++;
-    int col = 0;
-    long long first = b;
-    bool inq = false;
-    for (long long p = b; p <= e; p++) {
-        const uint8_t c = p < e ? text[p] : f.delim;
-        if (c == '"') inq = !inq;
-        else if ((c == f.delim && !inq) || p == e) {
-            visit(col, first, p);
-            col++;
-            first = p + 1;
+// pass 3: the position of every separator, in text order, and for every record the index of its LAST separator (its end):
+// field c of record r is the text between separators rec_last[r-1] + c and rec_last[r-1] + c + 1.
+__global__ void k_csv_separators(const uint8_t* __restrict__ text, long long n, long long nblocks, const int32_t* __restrict__ quotes_before, CsvFormat f,
+                                 const int32_t* __restrict__ recs_before, const int32_t* __restrict__ seps_before, int32_t* sep, int32_t* rec_last) {
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < nblocks; i += (long long)gridDim.x * blockDim.x) {
+        const BlockMasks m = csv_block_masks(text, n, i, quotes_before, f);
+        uint64_t all = m.rec | m.delim;
+        int32_t k = seps_before[i], r = recs_before[i];
+        while (all) {
+            const int j = __ffsll((long long)all) - 1;
+            sep[k] = (int32_t)(i * CSV_BLOCK + j);
+            if ((m.rec >> j) & 1ULL) rec_last[r++] = k;
+            k++;
+            all &= all - 1;
         }
     }
 }
+
 // Trimmed, unquoted value of the raw field [first, last): returns its length; with `out`, also writes it.
 __device__ __forceinline__ int csv_value(const uint8_t* text, long long first, long long last, uint8_t* out) {
     while (first < last && csv_blank(text[first])) first++;
@@ -186,40 +188,39 @@ __device__ __forceinline__ int csv_value(const uint8_t* text, long long first, l
 }
 
 struct CsvCols {
-    int16_t out_of[CSV_MAX_COLS];       // file column -> output column, -1: not projected
+    int16_t file_col[CSV_MAX_COLS];     // output column -> file column (materialised columns only; -1: shares another column's buffers)
     int32_t* lens[CSV_MAX_COLS];        // per output column: lengths, later Arrow offsets (device)
     uint8_t* data[CSV_MAX_COLS];
     int nout;
 };
 
-// pass 4: lengths of the projected fields of every data record (missing fields: 0, rule C6)
-__global__ void k_csv_field_lengths(const uint8_t* __restrict__ text, const long long* __restrict__ ends, long long nrec, int skip,
-                                    CsvFormat f, const CsvCols* __restrict__ cols) {
+// Raw bytes [a, b) of file column c of record `rec` (a missing field: a == b, rule C6)
+__device__ __forceinline__ void csv_field(const int32_t* __restrict__ sep, const int32_t* __restrict__ rec_last, long long rec, int c, long long& a, long long& b) {
+    const long long k0 = rec ? (long long)rec_last[rec - 1] + 1 : 0, k1 = rec_last[rec];      // the record's separators: k0 .. k1
+    a = b = 0;
+    if (k0 + c > k1) return;
+    a = k0 + c ? (long long)sep[k0 + c - 1] + 1 : 0;      // bytes of skipped empty lines in front of a record are blanks: trimmed with the value
+    b = sep[k0 + c];
+}
+// pass 4: lengths of the projected fields of every data record; pass 6 (COPY): the bytes, at the offsets pass 5 produced
+template <bool COPY>
+__global__ void k_csv_fields(const uint8_t* __restrict__ text, const int32_t* __restrict__ sep, const int32_t* __restrict__ rec_last, long long nrec, int skip,
+                             const CsvCols* __restrict__ cols) {
     for (long long r = blockIdx.x * (long long)blockDim.x + threadIdx.x; r + skip < nrec; r += (long long)gridDim.x * blockDim.x) {
-        const long long rec = r + skip;
-        for (int c = 0; c < cols->nout; c++) if (cols->lens[c]) cols->lens[c][r] = 0;       // (a column projected twice is materialised once)
-        csv_walk_record(text, rec ? ends[rec - 1] + 1 : 0, ends[rec], f, [&](int col, long long a, long long b) {
-            if (col < CSV_MAX_COLS && cols->out_of[col] >= 0) cols->lens[cols->out_of[col]][r] = csv_value(text, a, b, nullptr);
-        });
+        for (int oc = 0; oc < cols->nout; oc++) {
+            const int c = cols->file_col[oc];
+            if (c < 0) continue;
+            long long a, b;
+            csv_field(sep, rec_last, r + skip, c, a, b);
+            if (COPY) csv_value(text, a, b, cols->data[oc] + cols->lens[oc][r]);
+            else cols->lens[oc][r] = csv_value(text, a, b, nullptr);
+        }
     }
 }
 struct LenAt {
     const int32_t* lens;
     __device__ __forceinline__ int operator()(long long i) const { return lens[i]; }
 };
-// pass 6: the bytes
-__global__ void k_csv_copy(const uint8_t* __restrict__ text, const long long* __restrict__ ends, long long nrec, int skip, CsvFormat f,
-                           const CsvCols* __restrict__ cols) {
-    for (long long r = blockIdx.x * (long long)blockDim.x + threadIdx.x; r + skip < nrec; r += (long long)gridDim.x * blockDim.x) {
-        const long long rec = r + skip;
-        csv_walk_record(text, rec ? ends[rec - 1] + 1 : 0, ends[rec], f, [&](int col, long long a, long long b) {
-            if (col < CSV_MAX_COLS && cols->out_of[col] >= 0) {
-                const int oc = cols->out_of[col];
-                csv_value(text, a, b, cols->data[oc] + cols->lens[oc][r]);      // lens now holds the exclusive offsets
-            }
-        });
-    }
-}
 
 // ---- host side: format detection and the header record (rules C1, C4) ---------------------------------------------
 struct HostRecord { std::vector<std::string> fields; int64_t end = 0; };    // end: index just past the record's terminator
@@ -357,14 +358,14 @@ int kq_csv_scan(kq_ctx* ctx, const uint8_t* text, int64_t nbytes, int has_header
     uint8_t* d_text = nullptr;
     int32_t *d_q = nullptr, *d_r = nullptr;
     unsigned long long* d_scratch = nullptr;        // [0] ticket, [1] total, [2] item count, [4..] tile descriptors
-    long long* d_ends = nullptr;
+    int32_t *d_s = nullptr, *d_sep = nullptr, *d_last = nullptr;
     CsvCols* d_cols = nullptr;
     std::vector<kq_col*> cols;
     // tile descriptors of the device-wide scans: over 64-byte blocks (passes 1-2) and over records (pass 5; a record has at
     // least two bytes, so nblocks * 32 bounds the record count)
     const long long ntiles = (std::max<long long>(nblocks, 1) * (CSV_BLOCK / 2) + SCAN_TILE - 1) / SCAN_TILE + 2;
     auto cleanup = [&](int st) {
-        kq_dev_free(ctx, d_text); kq_dev_free(ctx, d_q); kq_dev_free(ctx, d_r); kq_dev_free(ctx, d_scratch); kq_dev_free(ctx, d_ends); kq_dev_free(ctx, d_cols);
+        kq_dev_free(ctx, d_text); kq_dev_free(ctx, d_q); kq_dev_free(ctx, d_r); kq_dev_free(ctx, d_scratch); kq_dev_free(ctx, d_s); kq_dev_free(ctx, d_sep); kq_dev_free(ctx, d_last); kq_dev_free(ctx, d_cols);
         if (st != KQ_OK) for (kq_col* c : cols) kq_column_free(c);
         return st;
     };
@@ -374,7 +375,7 @@ int kq_csv_scan(kq_ctx* ctx, const uint8_t* text, int64_t nbytes, int has_header
         *out = b;
         return KQ_OK;
     };
-    int64_t nrec = 0;
+    int64_t nrec = 0, nsep = 0;
     int st = KQ_OK;
     if (n > 0) {
         if ((st = kq_dev_alloc(ctx, (size_t)n + 16, (void**)&d_text)) != KQ_OK) return cleanup(st);
@@ -397,14 +398,22 @@ int kq_csv_scan(kq_ctx* ctx, const uint8_t* text, int64_t nbytes, int has_header
         uint64_t total = 0;
         if ((st = kq_read_u64(ctx, d_scratch + 1, 1, &total)) != KQ_OK) return cleanup(st);
         if (total & 1) return cleanup(kq_fail(ctx, KQ_ERR_ILLEGAL_STATE, "CSV text ends inside a quoted field"));
-        // 2. records before every block
+        // 2. records and separators before every block
         scan_begin(items);
-        k_exclusive_offsets<RecordCount><<<sg, 256, 0, ctx->stream>>>(RecordCount{d_text, n, d_q, f, nullptr, nullptr}, d_scratch + 2, d_r, d_scratch + 4,
+        k_exclusive_offsets<RecordCount><<<sg, 256, 0, ctx->stream>>>(RecordCount{d_text, n, d_q, f}, d_scratch + 2, d_r, d_scratch + 4,
                                                                        (unsigned int*)d_scratch, d_scratch + 1);
         if (cudaGetLastError() != cudaSuccess) return cleanup(kq_cuda_fail(ctx, cudaGetLastError(), "k_exclusive_offsets(records)"));
         ctx->launches++;
         if ((st = kq_read_u64(ctx, d_scratch + 1, 1, &total)) != KQ_OK) return cleanup(st);
         nrec = (int64_t)total;
+        if ((st = kq_dev_alloc(ctx, (size_t)(nblocks + 1) * 4, (void**)&d_s)) != KQ_OK) return cleanup(st);
+        scan_begin(items);
+        k_exclusive_offsets<SeparatorCount><<<sg, 256, 0, ctx->stream>>>(SeparatorCount{d_text, n, d_q, f}, d_scratch + 2, d_s, d_scratch + 4,
+                                                                          (unsigned int*)d_scratch, d_scratch + 1);
+        if (cudaGetLastError() != cudaSuccess) return cleanup(kq_cuda_fail(ctx, cudaGetLastError(), "k_exclusive_offsets(separators)"));
+        ctx->launches++;
+        if ((st = kq_read_u64(ctx, d_scratch + 1, 1, &total)) != KQ_OK) return cleanup(st);
+        nsep = (int64_t)total;
     }
     const int skip = has_headers && nrec > 0 ? 1 : 0;
     const int64_t rows = nrec - skip;
@@ -418,16 +427,17 @@ int kq_csv_scan(kq_ctx* ctx, const uint8_t* text, int64_t nbytes, int has_header
         make_batch(std::max<int64_t>(rows, 0));
         return cleanup(KQ_OK);
     }
-    // 3. record ends
-    if ((st = kq_dev_alloc(ctx, (size_t)nrec * 8, (void**)&d_ends)) != KQ_OK) return cleanup(st);
+    // 3. separator positions and each record's last separator
+    if ((st = kq_dev_alloc(ctx, (size_t)nsep * 4 + 16, (void**)&d_sep)) != KQ_OK) return cleanup(st);
+    if ((st = kq_dev_alloc(ctx, (size_t)nrec * 4 + 16, (void**)&d_last)) != KQ_OK) return cleanup(st);
     const int g = (int)std::max<long long>(1, std::min<long long>((nblocks + 255) / 256, (long long)ctx->sm_count * 8));
-    k_csv_record_ends<<<g, 256, 0, ctx->stream>>>(RecordCount{d_text, n, d_q, f, d_ends, d_r}, nblocks);
-    if (cudaGetLastError() != cudaSuccess) return cleanup(kq_cuda_fail(ctx, cudaGetLastError(), "k_csv_record_ends"));
+    k_csv_separators<<<g, 256, 0, ctx->stream>>>(d_text, n, nblocks, d_q, f, d_r, d_s, d_sep, d_last);
+    if (cudaGetLastError() != cudaSuccess) return cleanup(kq_cuda_fail(ctx, cudaGetLastError(), "k_csv_separators"));
     ctx->launches++;
     // 4. field lengths (into scratch arrays; the columns' offsets buffers are written by the scans below)
     CsvCols hc;
     memset(&hc, 0, sizeof hc);
-    for (int i = 0; i < CSV_MAX_COLS; i++) hc.out_of[i] = -1;
+    for (int i = 0; i < CSV_MAX_COLS; i++) hc.file_col[i] = -1;
     hc.nout = nout;
     std::vector<int32_t*> d_len((size_t)nout, nullptr);
     auto cleanup2 = [&](int s2) { for (int32_t* p : d_len) kq_dev_free(ctx, p); return cleanup(s2); };
@@ -436,33 +446,43 @@ int kq_csv_scan(kq_ctx* ctx, const uint8_t* text, int64_t nbytes, int has_header
     for (int c = 0; c < nout; c++) {
         if (first_out[(size_t)proj[(size_t)c]] >= 0) continue;
         first_out[(size_t)proj[(size_t)c]] = c;
-        hc.out_of[proj[(size_t)c]] = (int16_t)c;
+        hc.file_col[c] = (int16_t)proj[(size_t)c];
         if ((st = kq_dev_alloc(ctx, (size_t)(rows + 1) * 4, (void**)&d_len[(size_t)c])) != KQ_OK) return cleanup2(st);
         hc.lens[c] = d_len[(size_t)c];
     }
     if ((st = kq_dev_alloc(ctx, sizeof hc, (void**)&d_cols)) != KQ_OK) return cleanup2(st);
     cudaMemcpyAsync(d_cols, &hc, sizeof hc, cudaMemcpyHostToDevice, ctx->stream);
     const int gr = (int)std::max<long long>(1, std::min<long long>((rows + 127) / 128, (long long)ctx->sm_count * 16));
-    k_csv_field_lengths<<<gr, 128, 0, ctx->stream>>>(d_text, d_ends, nrec, skip, f, d_cols);
-    if (cudaGetLastError() != cudaSuccess) return cleanup2(kq_cuda_fail(ctx, cudaGetLastError(), "k_csv_field_lengths"));
+    k_csv_fields<false><<<gr, 128, 0, ctx->stream>>>(d_text, d_sep, d_last, nrec, skip, d_cols);
+    if (cudaGetLastError() != cudaSuccess) return cleanup2(kq_cuda_fail(ctx, cudaGetLastError(), "k_csv_fields(lengths)"));
     ctx->launches++;
     // 5. offsets per materialised column, then the data buffers
     std::vector<uint64_t> bytes((size_t)nout, 0);
     std::vector<int32_t*> d_off((size_t)nout, nullptr);
     auto cleanup3 = [&](int s2) { for (int32_t* p : d_off) kq_dev_free(ctx, p); return cleanup2(s2); };
     const int sgr = (int)std::max<long long>(1, std::min<long long>((rows + SCAN_TILE - 1) / SCAN_TILE, (long long)ctx->sm_count * 4));
+    // all column scans are queued back to back (each with its own ticket / total / tile descriptors), then the totals are read
+    const size_t scratch_words = (size_t)(ntiles + 4);
+    unsigned long long* d_scratch2 = nullptr;
+    if ((st = kq_dev_alloc(ctx, scratch_words * 8 * (size_t)nout, (void**)&d_scratch2)) != KQ_OK) return cleanup3(st);
+    auto cleanup4 = [&](int s2) { kq_dev_free(ctx, d_scratch2); return cleanup3(s2); };
+    cudaMemsetAsync(d_scratch2, 0, scratch_words * 8 * (size_t)nout, ctx->stream);
+    const unsigned long long count = (unsigned long long)rows;
     for (int c = 0; c < nout; c++) {
         if (!d_len[(size_t)c]) continue;
-        if ((st = kq_dev_alloc(ctx, (size_t)(rows + 1) * 4, (void**)&d_off[(size_t)c])) != KQ_OK) return cleanup3(st);
-        cudaMemsetAsync(d_scratch, 0, (size_t)(ntiles + 4) * 8, ctx->stream);
-        const unsigned long long count = (unsigned long long)rows;
-        cudaMemcpyAsync(d_scratch + 2, &count, 8, cudaMemcpyHostToDevice, ctx->stream);
-        k_exclusive_offsets<LenAt><<<sgr, 256, 0, ctx->stream>>>(LenAt{d_len[(size_t)c]}, d_scratch + 2, d_off[(size_t)c], d_scratch + 4, (unsigned int*)d_scratch, d_scratch + 1);
-        if (cudaGetLastError() != cudaSuccess) return cleanup3(kq_cuda_fail(ctx, cudaGetLastError(), "k_exclusive_offsets(column)"));
+        if ((st = kq_dev_alloc(ctx, (size_t)(rows + 1) * 4, (void**)&d_off[(size_t)c])) != KQ_OK) return cleanup4(st);
+        unsigned long long* sc = d_scratch2 + scratch_words * (size_t)c;
+        cudaMemcpyAsync(sc + 2, &count, 8, cudaMemcpyHostToDevice, ctx->stream);
+        k_exclusive_offsets<LenAt><<<sgr, 256, 0, ctx->stream>>>(LenAt{d_len[(size_t)c]}, sc + 2, d_off[(size_t)c], sc + 4, (unsigned int*)sc, sc + 1);
+        if (cudaGetLastError() != cudaSuccess) return cleanup4(kq_cuda_fail(ctx, cudaGetLastError(), "k_exclusive_offsets(column)"));
         ctx->launches++;
-        if ((st = kq_read_u64(ctx, d_scratch + 1, 1, &bytes[(size_t)c])) != KQ_OK) return cleanup3(st);
-        if (bytes[(size_t)c] >= (1ULL << 31)) return cleanup3(kq_fail(ctx, KQ_ERR_UNSUPPORTED, "CSV column of 2 GiB or more"));
     }
+    for (int c = 0; c < nout; c++) {
+        if (!d_len[(size_t)c]) continue;
+        if ((st = kq_read_u64(ctx, d_scratch2 + scratch_words * (size_t)c + 1, 1, &bytes[(size_t)c])) != KQ_OK) return cleanup4(st);
+        if (bytes[(size_t)c] >= (1ULL << 31)) return cleanup4(kq_fail(ctx, KQ_ERR_UNSUPPORTED, "CSV column of 2 GiB or more"));
+    }
+    kq_dev_free(ctx, d_scratch2);
     cols.assign((size_t)nout, nullptr);
     for (int c = 0; c < nout; c++) {
         if (!d_len[(size_t)c]) continue;
@@ -479,8 +499,8 @@ int kq_csv_scan(kq_ctx* ctx, const uint8_t* text, int64_t nbytes, int has_header
     CsvCols* d_cols2 = nullptr;
     if ((st = kq_dev_alloc(ctx, sizeof hc, (void**)&d_cols2)) != KQ_OK) return cleanup3(st);
     cudaMemcpyAsync(d_cols2, &hc, sizeof hc, cudaMemcpyHostToDevice, ctx->stream);
-    k_csv_copy<<<gr, 128, 0, ctx->stream>>>(d_text, d_ends, nrec, skip, f, d_cols2);
-    st = cudaGetLastError() != cudaSuccess ? kq_cuda_fail(ctx, cudaGetLastError(), "k_csv_copy") : KQ_OK;
+    k_csv_fields<true><<<gr, 128, 0, ctx->stream>>>(d_text, d_sep, d_last, nrec, skip, d_cols2);
+    st = cudaGetLastError() != cudaSuccess ? kq_cuda_fail(ctx, cudaGetLastError(), "k_csv_fields(copy)") : KQ_OK;
     ctx->launches++;
     // hc lives on the host stack: the two pageable uploads above were staged synchronously by the runtime
     if (st == KQ_OK) st = cudaStreamSynchronize(ctx->stream) == cudaSuccess ? KQ_OK : kq_cuda_fail(ctx, cudaGetLastError(), "cudaStreamSynchronize(csv)");
