@@ -48,3 +48,12 @@ def test_agrees_with_python_csv_module(oracle, crlf):
     rows = [r for r in csv.reader(io.StringIO(text.decode("utf-8"), newline="")) if r]
     want = [[(r[c] if c < len(r) else "").strip() for r in rows[1:]] for c in range(len(rows[0]))]
     assert columns(oracle.csv_scan(text, True)) == want
+
+
+@pytest.mark.parametrize("case", CASES, ids=[c[0] for c in CASES])
+def test_product_header_detection_matches_oracle(oracle, case):
+    """kq_csv_header is host code (format detection + first record): it runs without a GPU and must agree with the oracle."""
+    import kqgpu
+    _, text, hdr, names, _ = case
+    assert kqgpu.Engine.csv_header(text, hdr) == oracle.csv_header(text, hdr)
+    assert kqgpu.Engine.csv_header(text, hdr)[0] == names
