@@ -1,0 +1,128 @@
+"""A Python model of the DEVICE algorithm of kq_csv_scan (csrc/kq_csv.cu) — the same bit-mask formulas per 64-byte block,
+the separator array, field bounds and value extraction, with Python integers for the 64-bit masks — so that the
+algorithm (block-boundary carries, the shifted-mask test for empty records, quote state by prefix XOR) can be checked
+against the oracle on the CPU with generated inputs. It is a model for tests, not a fallback: nothing imports it but tests/."""
+M64 = (1 << 64) - 1
+BLOCK = 64
+
+
+def detect(text: bytes):
+    """host_detect + host_first_line of kq_csv.cu: (delimiter, terminator)."""
+    term = 0x0A
+    if b"\n" not in text and b"\r" in text:
+        term = 0x0D
+    start, inq, line = 0, False, None
+    for p in range(len(text) + 1):
+        at_end = p == len(text)
+        c = term if at_end else text[p]
+        if c == 0x22 and not at_end:
+            inq = not inq
+        elif c == term and (not inq or at_end):
+            empty = p == start or (term == 0x0A and p == start + 1 and text[start] == 0x0D)
+            if not empty:
+                line = text[start:p]
+                break
+            start = p + 1
+    delim = ord(",")
+    if line is not None:
+        cnt, inq = {}, False
+        for c in line:
+            if c == 0x22:
+                inq = not inq
+            elif not inq and c in b",;\t|":
+                cnt[c] = cnt.get(c, 0) + 1
+        best = 0
+        for cand in b",;\t|":
+            if cnt.get(cand, 0) > best:
+                best, delim = cnt[cand], cand
+    return delim, term
+
+
+def block_masks(text: bytes, n: int, i: int, quotes_before: int, delim: int, term: int):
+    """csv_block_masks: (rec, delim) bit masks of block i."""
+    b = i * BLOCK
+    blk = text[b:min(b + BLOCK, n)]
+    qm = tm = cm = dm = 0
+    for j, c in enumerate(blk):
+        qm |= (c == 0x22) << j
+        tm |= (c == term) << j
+        cm |= (c == 0x0D) << j
+        dm |= (c == delim) << j
+    x = qm
+    for sh in (1, 2, 4, 8, 16, 32):
+        x ^= (x << sh) & M64
+    inside = (~x & M64) if (quotes_before & 1) else x
+    t1 = b == 0 or text[b - 1] == term
+    t2 = b <= 1 or text[b - 2] == term
+    empty = ((tm << 1) & M64) | int(t1)
+    if term == 0x0A:
+        prev_c = ((cm << 1) & M64) | int(b > 0 and text[b - 1] == 0x0D)
+        prev2_t = ((tm << 2) & M64) | (int(t1) << 1) | int(t2)
+        empty |= prev_c & prev2_t
+    live = (1 << len(blk)) - 1
+    return tm & ~inside & ~empty & live, dm & ~inside & live
+
+
+def value(text: bytes, first: int, last: int) -> bytes:
+    """csv_value: trimmed, unquoted bytes of the raw field [first, last)."""
+    while first < last and text[first] <= 0x20:
+        first += 1
+    while last > first and text[last - 1] <= 0x20:
+        last -= 1
+    if first < last and text[first] == 0x22:
+        p = q = first + 1
+        while q < last and not (text[q] == 0x22 and not (q + 1 < last and text[q + 1] == 0x22)):
+            q += 2 if text[q] == 0x22 else 1
+        q = min(q, last)
+        while p < q and text[p] <= 0x20:
+            p += 1
+        while q > p and text[q - 1] <= 0x20:
+            q -= 1
+        out, j = bytearray(), p
+        while j < q:
+            out.append(text[j])
+            if text[j] == 0x22 and j + 1 < q and text[j + 1] == 0x22:
+                j += 1
+            j += 1
+        return bytes(out)
+    return text[first:last]
+
+
+def scan(text: bytes, has_headers=True):
+    """kq_csv_scan's passes 1-6 -> list of columns (lists of str), all file columns."""
+    if not text:
+        return []
+    delim, term = detect(text)
+    if text[-1] != term:
+        text = text + bytes([term])
+    n = len(text)
+    nblocks = (n + BLOCK - 1) // BLOCK
+    sep, rec_last, q = [], [], 0
+    for i in range(nblocks):
+        rec, dl = block_masks(text, n, i, q, delim, term)
+        allm = rec | dl
+        while allm:
+            j = (allm & -allm).bit_length() - 1
+            sep.append(i * BLOCK + j)
+            if (rec >> j) & 1:
+                rec_last.append(len(sep) - 1)
+            allm &= allm - 1
+        q += text[i * BLOCK:min((i + 1) * BLOCK, n)].count(b'"')
+    if q & 1:
+        raise ValueError("CSV text ends inside a quoted field")
+    nrec = len(rec_last)
+    if nrec == 0:
+        return []
+    ncols = rec_last[0] + 1                          # fields of the first record
+    skip = 1 if has_headers else 0
+    cols = [[] for _ in range(ncols)]
+    for rec in range(skip, nrec):
+        k0 = rec_last[rec - 1] + 1 if rec else 0
+        k1 = rec_last[rec]
+        for c in range(ncols):
+            if k0 + c > k1:
+                cols[c].append("")
+                continue
+            a = sep[k0 + c - 1] + 1 if k0 + c else 0
+            cols[c].append(value(text, a, sep[k0 + c]).decode("utf-8"))
+    return cols

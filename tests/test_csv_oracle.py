@@ -95,3 +95,34 @@ def test_roundtrip_of_random_tables(oracle, ncols, data, crlf):
     got = columns(oracle.csv_scan(text, True))
     want = [[_trim(r[c]) for r in rows] for c in range(ncols)]
     assert got == want
+
+
+# ---------------------------------------------------------------- the device algorithm, modelled in Python, against the oracle
+import csv_device_model as dm
+
+
+@pytest.mark.parametrize("case", CASES, ids=[c[0] for c in CASES])
+def test_device_model_on_cases(oracle, case):
+    _, text, hdr, names, want = case
+    assert dm.scan(text, hdr) == want
+    d, _ = dm.detect(text)
+    assert chr(d) == oracle.csv_header(text, hdr)[1]
+
+
+_LONG_FIELD = st.text(_ALPHABET, max_size=40)        # long enough for fields and records to straddle 64-byte blocks
+
+
+@settings(max_examples=400, deadline=None)
+@given(ncols=st.integers(2, 4), data=st.data(), crlf=st.booleans(), blanks=st.booleans())
+def test_device_model_agrees_with_oracle_on_random_tables(oracle, ncols, data, crlf, blanks):
+    rows = data.draw(st.lists(st.lists(_LONG_FIELD, min_size=ncols, max_size=ncols), max_size=8))
+    eol = "\r\n" if crlf else "\n"
+    buf = io.StringIO(newline="")
+    w = csv.writer(buf, lineterminator=eol, quoting=csv.QUOTE_MINIMAL)
+    w.writerow([f"h{i}" for i in range(ncols)])
+    for r in rows:
+        w.writerow(r)
+        if blanks:
+            buf.write(eol * data.draw(st.integers(0, 3)))       # empty lines between records (skipped, rule C3)
+    text = buf.getvalue().encode("utf-8")
+    assert dm.scan(text, True) == columns(oracle.csv_scan(text, True))
