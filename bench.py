@@ -1,21 +1,25 @@
 #!/usr/bin/env python
 """bench.py — the headline measurement (BASELINE.json metric: rows/s and achieved HBM GB/s per query).
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--workload cfg2f|cfg2i|cfg3|cfg4|cfg5]
-                    [--rows R] [--impl reference]
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--workload cfg3|cfg2f|cfg2i|cfg4|cfg5|csv]
+                    [--rows R] [--impl reference] [--no-sub]
 
 A "step" is one pass of the hot path over one batch of synthetic input that is already resident in
-HBM. Default workload (N=1): BASELINE.json configs[1], the fused filter (a > k AND b < m) +
-projection (a*b + c) over a 100 M-row Float64 table. With N > 1 (torchrun, one rank per GPU) every
-rank processes its own row range of the same global table (weak scaling); filter+project has no
-exchange step, the aggregate workloads merge partials over NCCL inside the timed region.
+HBM. The line's own workload is BASELINE.json configs[2] — the reference's hot loop,
+HashAggregateExec (Main.kt:615-651): GROUP BY a 50-value Utf8 key, SUM/MIN/MAX/COUNT over 1 B rows —
+STRONG-scaled: with N > 1 (torchrun, one rank per GPU) the 1 B rows are split N ways and the partial
+tables are merged over NCCL inside the timed region (partition -> partial -> merge, Main.kt:1309-1325).
+`sub` carries the same measurement for configs[1] (cfg2f, fused filter+project, 100 M rows per GPU, no
+exchange), configs[4] (cfg5, TPC-H Q1 shape, 600 M rows split N ways) and configs[3] (cfg4, 10 M groups
+over 1 B rows split N ways, NCCL all-to-all repartition), so all four are on the driver's clock.
 
 One JSON line on stdout (rank 0). `value` is device-resident throughput (CUDA events on the kernel
 stream, max over ranks); `e2e` is the same metric through the C ABI with HOST buffers (pinned
 host -> device copies in, result copied back, inside the timed region); `roofline` compares the
 dominant kernel's algorithmic bytes/launch with the measured HBM peak; `cpu_baseline` is the CPU
 oracle (a C++ restatement of the Kotlin operators — the reference itself cannot run here) timed on
-this box's host cores on a bounded sample.
+this box's host cores on a bounded sample; `check` is in-bench evidence that the timed step's result
+is right (sum of COUNTs = rows, group count, identical result on every rank).
 """
 from __future__ import annotations
 
@@ -296,6 +300,29 @@ def cpu_sample_rows(wl):
     return {"cfg2f": 24_000_000, "cfg2i": 24_000_000, "cfg3": 16_000_000, "cfg4": 8_000_000, "cfg5": 8_000_000, "csv": 4_000_000}[wl.name]
 
 
+def scaling_of(wl):
+    """Strong scaling (the BASELINE table split across the ranks) for the aggregate workloads, whose merge is the
+    exchange step of the path; filter+project and the CSV scan have no exchange and keep their per-GPU size (weak)."""
+    return "strong" if isinstance(wl, GroupBy) else "weak"
+
+
+def rows_per_rank(wl, rank, world):
+    """Row range [begin, end) of the global table that `rank` owns."""
+    if scaling_of(wl) == "weak":
+        return shard_range(rank, wl.rows)
+    per = (wl.rows + world - 1) // world
+    return min(wl.rows, rank * per), min(wl.rows, (rank + 1) * per)
+
+
+def config_of(wl, world):
+    rows_total = wl.rows if scaling_of(wl) == "strong" else wl.rows * world
+    par = f"row-sharded x{world}"
+    if world > 1 and isinstance(wl, GroupBy):
+        par += ", NCCL all-to-all repartition" if wl.kind == "high" else ", NCCL all-gather merge of the partial tables"
+    return {"workload": f"{wl.name}: {wl.describe}", "rows_total": rows_total, "rows_per_gpu": (rows_total + world - 1) // world,
+            "seed": 42, "scaling": scaling_of(wl), "l2": "inputs larger than L2 (no flush needed)", "parallelism": par}
+
+
 def run_reference(args, wl, rank, world):
     if rank != 0:
         return
@@ -309,16 +336,162 @@ def run_reference(args, wl, rank, world):
         rows += sample
         dt += d
     v = rows / dt
+    cfg = config_of(wl, args.gpus)
     line = {"impl": "reference", "metric": "rows/s", "value": v, "unit": "rows/s", "n_gpus": args.gpus, "steps": args.steps,
-            "warmup": args.warmup, "ms_per_step": dt / args.steps * 1e3, "higher_is_better": True, "scaling": "weak",
-            "vs_baseline": None, "dtype": wl.dtype, "data": "synthetic",
-            "config": {"workload": f"{wl.name}: {wl.describe}", "rows_per_gpu": wl.rows, "seed": 42},
+            "warmup": args.warmup, "ms_per_step": dt / args.steps * 1e3, "higher_is_better": True, "scaling": scaling_of(wl),
+            "vs_baseline": None, "dtype": wl.dtype, "data": "synthetic", "config": cfg,
             "cpu_baseline": {"value": v, "unit": "rows/s", "cores": threads, "kind": "port",
                              "sample": f"{sample} rows per step of the same seeded table, already resident in host memory when the clock starts; "
                                        f"partition->partial->merge on {threads} threads"},
             "e2e": {"value": v, "unit": "rows/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
-            "note": "CPU oracle = C++ restatement of the Kotlin operators (the Kotlin reference cannot be built here: no JVM)"}
+            "note": "CPU oracle = C++ restatement of the Kotlin operators (the Kotlin reference cannot be built here: no JVM); "
+                    "a rate measured on a bounded sample of the workload named in config"}
     print(json.dumps(line), flush=True)
+
+
+# ---------------------------------------------------------------------------------------------------
+def result_check(wl, E, batch, res, n_local, dist, world):
+    """In-bench correctness evidence for the timed step's result (the only multi-GPU check the driver's boxes see)."""
+    import hashlib
+    import numpy as np
+    chk = {}
+    if isinstance(wl, GroupBy):
+        arrs = res.to_arrow()
+        nk = 2 if wl.kind == "q1" else 1
+        cnt = np.asarray(arrs[-1].to_numpy(zero_copy_only=False), dtype=np.int64)          # COUNT is the last aggregate of every workload
+        chk["groups_rank0"] = int(len(cnt))
+        local_rows_counted = int(cnt.sum())
+        if wl.kind == "q1":
+            pred = E.binary("LE", E.col(0), E.lit_date32(10471))
+            expect_local = E.filter(pred, batch).row_count()                               # rows passing the filter, counted by another kernel
+        else:
+            expect_local = n_local
+        # canonical bytes of the result: rows sorted by key, every column's values
+        keys = [a.to_pylist() for a in arrs[:nk]]
+        order = sorted(range(len(cnt)), key=lambda i: tuple(k[i] for k in keys))
+        h = hashlib.sha256()
+        for a in arrs:
+            col = a.to_pylist()
+            h.update(repr([col[i] for i in order]).encode())
+        digest = h.hexdigest()[:16]
+        chk["result_sha256_16"] = digest
+        if dist is None:
+            chk["count_sum"] = local_rows_counted
+            chk["count_expected"] = int(expect_local)
+            chk["count_ok"] = local_rows_counted == expect_local
+        else:
+            torch, td = dist["torch"], dist["td"]
+            t = torch.tensor([expect_local, local_rows_counted, len(cnt)], device="cuda", dtype=torch.int64)
+            g = [torch.zeros_like(t) for _ in range(world)]
+            td.all_gather(g, t)
+            exp_total = int(sum(int(x[0]) for x in g))
+            if wl.kind == "high":           # repartitioned: every key lives on exactly one rank, concatenation = answer
+                chk["count_sum"] = int(sum(int(x[1]) for x in g))
+                chk["groups_total"] = int(sum(int(x[2]) for x in g))
+            else:                           # all-gather merge: every rank holds the full result
+                chk["count_sum"] = local_rows_counted
+                d8 = torch.tensor(list(bytes.fromhex(digest)), device="cuda", dtype=torch.uint8)
+                dg = [torch.zeros_like(d8) for _ in range(world)]
+                td.all_gather(dg, d8)
+                chk["all_ranks_identical"] = all(bool((x == d8).all()) for x in dg)
+            chk["count_expected"] = exp_total
+            chk["count_ok"] = chk["count_sum"] == exp_total
+        if wl.kind == "low":
+            chk["groups_ok"] = chk["groups_rank0"] == 50
+    elif isinstance(wl, FilterProject):
+        chk["rows_out_rank0"] = res.row_count()
+    return chk
+
+
+def measure(kqgpu, ctx, E, wl, args, dist, rank, world, steps, warmup, want_e2e, want_cpu):
+    """One workload: generate this rank's shard, warm up, time `steps` steps on the device, check the result."""
+    row0, row1 = rows_per_rank(wl, rank, world)
+    n = row1 - row0
+    batch = wl.prepare(E, ctx, row0, row1) if hasattr(wl, "prepare") else E.generate(wl.specs(), 42, row0, row1)
+    ctx.sync()
+
+    def barrier():
+        ctx.sync()
+        if dist:
+            dist["td"].barrier()
+            dist["torch"].cuda.synchronize()
+
+    out_rows = 0
+    keep = None
+    for _ in range(warmup):
+        keep = wl.run(E, batch, dist)      # same ownership pattern as the timed loop: the previous result lives until the next exists
+        out_rows = wl.result_rows(keep)
+    barrier()
+
+    sampler = ClockSampler(ctx.device) if rank == 0 else None
+    launches0 = ctx.launch_count()
+    t_wall0 = time.time()
+    ctx.timer_begin()
+    for _ in range(steps):
+        keep = wl.run(E, batch, dist)          # inputs (2.4-28 GB) are far larger than L2: no flush needed
+    ms = ctx.timer_end()
+    barrier()
+    launches = ctx.launch_count() - launches0
+    clocks = sampler.stop(t_wall0, time.time()) if sampler else None
+    out_rows = wl.result_rows(keep)
+    check = result_check(wl, E, batch, keep, n, dist, world)
+    del keep
+    if dist:
+        t = dist["torch"].tensor([ms], device="cuda")
+        dist["td"].all_reduce(t, op=dist["td"].ReduceOp.MAX)
+        ms = float(t.item())
+    ms_per_step = ms / steps
+    cfg = config_of(wl, world)
+    rows_total = cfg["rows_total"]
+    value = rows_total / (ms_per_step * 1e-3)
+
+    e2e = None
+    if want_e2e:
+        e2e = run_e2e(kqgpu, ctx, E, wl, batch, dist, min(steps, 5), world, n, rows_total)
+
+    peak, peak_src = measured_peak()
+    # roofline of the dominant kernel on THIS rank's shard (per launch), against the per-GPU peak
+    algo = wl.algo_bytes(n, out_rows)
+    achieved = algo / (ms_per_step * 1e-3) / 1e9
+    roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                "traffic": ncu_traffic(wl.name, wl.kernel), "kernel": wl.kernel, "algorithmic_bytes_per_launch": algo,
+                "peak_source": peak_src, "frac_of_8TBps": achieved / 8000.0,
+                "how": "algorithmic bytes of one rank's step / (CUDA-event time of the timed region / steps, max over ranks) on the kernel "
+                       "stream; at N>1 the step also holds the NCCL merge, so this is a lower bound for the kernel"}
+    cpu = None
+    if want_cpu and rank == 0 and world == 1:
+        threads = 1 if isinstance(wl, CsvScan) else (os.cpu_count() or 1)      # the reference's CSV reader is one thread (Main.kt:204-273)
+        sample = cpu_sample_rows(wl)
+        v1, dt1, _ = cpu_reference(wl, sample // 8, 1)
+        vn, dtn, _ = cpu_reference(wl, sample, threads)
+        cpu = {"value": vn, "unit": "rows/s", "cores": threads, "kind": "port",
+               "sample": f"{sample} rows of the same seeded table, partition->partial->merge on {threads} threads ({dtn:.1f} s); "
+                         f"1 thread on {sample // 8} rows: {v1:.3e} rows/s",
+               "value_1thread": v1,
+               "note": "C++ restatement of the Kotlin operators (boxed, row-at-a-time); the Kotlin reference cannot run here (no JVM)"}
+    del batch
+    return {"value": value, "output_rows_rank0": out_rows, "ms_per_step": ms_per_step, "scaling": scaling_of(wl), "dtype": wl.dtype, "config": cfg, "roofline": roofline,
+            "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": launches, "clocks": clocks, "check": check, "steps": steps, "warmup": warmup}
+
+
+def bind_to_gpu_numa(local_rank):
+    """Run this rank (and first-touch its pinned staging buffers) on the CPUs nearest to its GPU."""
+    try:
+        import pynvml
+        pynvml.nvmlInit()
+        h = pynvml.nvmlDeviceGetHandleByIndex(local_rank)
+        words = pynvml.nvmlDeviceGetCpuAffinity(h, (os.cpu_count() + 63) // 64)
+        cpus = {64 * i + b for i, w in enumerate(words) for b in range(64) if (w >> b) & 1}
+        cpus &= os.sched_getaffinity(0)
+        if cpus:
+            os.sched_setaffinity(0, cpus)
+            return f"{len(cpus)} CPUs nearest to GPU {local_rank}"
+    except Exception as e:       # no NVML / restricted container: leave the affinity alone
+        return f"unchanged ({type(e).__name__})"
+    return "unchanged"
+
+
+SUBS = {"cfg3": ["cfg2f", "cfg5", "cfg4"]}
 
 
 # ---------------------------------------------------------------------------------------------------
@@ -327,11 +500,12 @@ def main():
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
-    ap.add_argument("--workload", default="cfg2f", choices=sorted(WORKLOADS))
-    ap.add_argument("--rows", type=int, default=0, help="rows per GPU (default: the BASELINE config size)")
+    ap.add_argument("--workload", default="cfg3", choices=sorted(WORKLOADS))
+    ap.add_argument("--rows", type=int, default=0, help="rows of the table (strong-scaled workloads: in total; weak: per GPU); default: the BASELINE config size")
     ap.add_argument("--impl", default="kqgpu", choices=["kqgpu", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-sub", action="store_true", help="skip the secondary workloads reported under `sub`")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "kqgpu" else args.warmup
 
@@ -347,6 +521,7 @@ def main():
     import kqgpu
     if kqgpu.device_count() < 1:
         raise SystemExit("bench.py needs a CUDA device: there is no CPU fallback (use --impl reference for the CPU oracle)")
+    numa = bind_to_gpu_numa(local_rank)
 
     dist = None
     if world > 1:
@@ -358,7 +533,7 @@ def main():
 
     ctx = kqgpu.Context(local_rank)
     E = kqgpu.Engine(ctx)
-    if world > 1 and isinstance(wl, GroupBy):
+    if world > 1:
         import ctypes
         idbuf = ctypes.create_string_buffer(kqgpu.COMM_ID_BYTES)
         if rank == 0:
@@ -368,86 +543,27 @@ def main():
         idbytes = bytes(t.cpu().numpy().tobytes())
         ctx.check(kqgpu.lib().kq_comm_init(ctx.h, idbytes, rank, world))
 
-    # each rank owns rows [rank*R, (rank+1)*R) of the same global table (weak scaling)
-    n = wl.rows
-    row0, row1 = shard_range(rank, n)
-    batch = wl.prepare(E, ctx, row0, row1) if hasattr(wl, "prepare") else E.generate(wl.specs(), 42, row0, row1)
-    ctx.sync()
-
-    def barrier():
-        ctx.sync()
-        if dist:
-            dist["td"].barrier()
-            dist["torch"].cuda.synchronize()
-
-    # warm-up
-    out_rows = 0
-    keep = None
-    for _ in range(args.warmup):
-        keep = wl.run(E, batch, dist)      # same ownership pattern as the timed loop: the previous result lives until the next exists
-        out_rows = wl.result_rows(keep)
-    barrier()
-
-    sampler = ClockSampler(local_rank) if rank == 0 else None
-    launches0 = ctx.launch_count()
-    t_wall0 = time.time()
-    ctx.timer_begin()
-    for _ in range(args.steps):
-        keep = wl.run(E, batch, dist)          # inputs (2.4-28 GB) are far larger than L2: no flush needed
-    ms = ctx.timer_end()
-    barrier()
-    t_wall1 = time.time()
-    launches = ctx.launch_count() - launches0
-    out_rows = wl.result_rows(keep)
-    del keep
-    if dist:
-        t = dist["torch"].tensor([ms], device="cuda")
-        dist["td"].all_reduce(t, op=dist["td"].ReduceOp.MAX)
-        ms = float(t.item())
-    ms_per_step = ms / args.steps
-    value = world * n / (ms_per_step * 1e-3)
-
-    # end to end through the C ABI from host (pinned) buffers, result copied back
-    e2e = None
-    if not args.no_e2e:
-        e2e = run_e2e(kqgpu, ctx, E, wl, batch, dist, min(args.steps, 5), world)
-    clocks = sampler.stop(t_wall0, time.time()) if sampler else None
-
-    peak, peak_src = measured_peak()
-    algo = wl.algo_bytes(n, out_rows)
-    achieved = algo / (ms_per_step * 1e-3) / 1e9
-    roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                "traffic": ncu_traffic(wl.name, wl.kernel), "kernel": wl.kernel, "algorithmic_bytes_per_launch": algo,
-                "peak_source": peak_src, "frac_of_8TBps": achieved / 8000.0,
-                "how": "algorithmic bytes of one step / (CUDA-event time of the timed region / steps) on the kernel stream"}
-
-    cpu = None
-    if rank == 0 and world == 1 and not args.no_cpu_baseline:
-        threads = 1 if isinstance(wl, CsvScan) else (os.cpu_count() or 1)      # the reference's CSV reader is one thread (Main.kt:204-273)
-        sample = cpu_sample_rows(wl)
-        v1, dt1, _ = cpu_reference(wl, sample // 8, 1)
-        vn, dtn, _ = cpu_reference(wl, sample, threads)
-        cpu = {"value": vn, "unit": "rows/s", "cores": threads, "kind": "port",
-               "sample": f"{sample} rows of the same seeded table, partition->partial->merge on {threads} threads ({dtn:.1f} s); "
-                         f"1 thread on {sample // 8} rows: {v1:.3e} rows/s",
-               "value_1thread": v1,
-               "note": "C++ restatement of the Kotlin operators (boxed, row-at-a-time); the Kotlin reference cannot run here (no JVM)"}
+    m = measure(kqgpu, ctx, E, wl, args, dist, rank, world, args.steps, args.warmup, not args.no_e2e, not args.no_cpu_baseline)
+    sub = {}
+    if not args.no_sub and not args.rows:
+        for name in SUBS.get(args.workload, []):
+            swl = WORKLOADS[name](0)
+            r = measure(kqgpu, ctx, E, swl, args, dist, rank, world, max(3, min(args.steps, 10)), 3, not args.no_e2e, False)
+            sub[name] = {k: r[k] for k in ("value", "ms_per_step", "scaling", "dtype", "config", "roofline", "e2e", "gpu_launches", "check", "steps", "output_rows_rank0")}
+            sub[name]["unit"] = "rows/s"
 
     if rank == 0:
-        line = {"metric": "rows/s", "value": value, "unit": "rows/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
-                "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": wl.dtype,
-                "data": "synthetic",
-                "config": {"workload": f"{wl.name}: {wl.describe}", "rows_per_gpu": n, "rows_total": n * world, "seed": 42,
-                           "output_rows_rank0": out_rows, "l2": "inputs larger than L2 (no flush needed)",
-                           "parallelism": f"row-sharded x{world}" + ("" if world == 1 or isinstance(wl, FilterProject) else
-                                                                    (", NCCL all-to-all repartition" if wl.kind == "high" else ", NCCL allreduce merge"))},
-                "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": launches, "clocks": clocks}
+        line = {"metric": "rows/s", "value": m["value"], "unit": "rows/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+                "ms_per_step": m["ms_per_step"], "higher_is_better": True, "scaling": m["scaling"], "vs_baseline": None, "dtype": m["dtype"],
+                "data": "synthetic", "config": m["config"], "roofline": m["roofline"], "cpu_baseline": m["cpu_baseline"], "e2e": m["e2e"],
+                "gpu_launches": m["gpu_launches"], "clocks": m["clocks"], "check": m["check"], "output_rows_rank0": m["output_rows_rank0"],
+                "cpu_affinity": numa, "sub": sub}
         print(json.dumps(line), flush=True)
     if dist:
         dist["td"].destroy_process_group()
 
 
-def run_e2e(kqgpu, ctx, E, wl, batch, dist, steps, world):
+def run_e2e(kqgpu, ctx, E, wl, batch, dist, steps, world, n_local, rows_total):
     """Same step, but inputs start in pinned HOST memory and the result ends in host memory.
 
     filter+project: one kq_filter_project_host call (chunked H2D / kernel / D2H overlap inside the library).
@@ -473,7 +589,7 @@ def run_e2e(kqgpu, ctx, E, wl, batch, dist, steps, world):
         ctx.sync()
         dt = time.perf_counter() - t0
         ctx.host_free(hp)
-        return {"value": world * wl.rows * steps / dt, "unit": "rows/s", "h2d_bytes_per_step": nb, "d2h_bytes_per_step": d2h, "steps": steps,
+        return {"value": rows_total * steps / dt, "unit": "rows/s", "h2d_bytes_per_step": nb, "d2h_bytes_per_step": d2h, "steps": steps,
                 "ms_per_step": dt / steps * 1e3,
                 "how": "CSV text in pinned host memory -> kq_csv_scan (H2D copy + scan kernels) -> row count and column sizes read back, wall clock around synchronised steps"}
     cols = [batch.field(i) for i in range(batch.num_columns())]
@@ -489,7 +605,7 @@ def run_e2e(kqgpu, ctx, E, wl, batch, dist, steps, world):
                                        C.c_void_p(ptr_o) if ptr_o else None, C.c_void_p(ptr_d)))
         host.append((t, n, ptr_v, ptr_o, ptr_d, nb))
         h2d += nb + ((n + 1) * 4 if ptr_o else 0) + ((n + 7) // 8 if ptr_v else 0)
-    n = wl.rows
+    n = n_local
     outs = []
     if isinstance(wl, FilterProject):
         pred, proj = wl.exprs(E)
@@ -541,7 +657,7 @@ def run_e2e(kqgpu, ctx, E, wl, batch, dist, steps, world):
                 ctx.host_free(p)
     for (pd, pv) in outs:
         ctx.host_free(pd)
-    return {"value": world * wl.rows * steps / dt, "unit": "rows/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+    return {"value": rows_total * steps / dt, "unit": "rows/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
             "steps": steps, "ms_per_step": dt / steps * 1e3,
             "how": ("kq_filter_project_host: pinned host buffers -> chunked H2D / fused kernel / D2H overlap -> host result buffers"
                     if isinstance(wl, FilterProject) else

@@ -48,14 +48,22 @@ __device__ __forceinline__ uint64_t table_home(uint64_t h, uint64_t cap_mask) { 
 
 // Find the record of (kw, nullmask) in the global table, inserting it if absent. Claim protocol:
 // CAS header EMPTY -> BUSY|nullmask, write keys + accumulator identities, fence, publish FULL.
-// The table never fills up: the host sizes it so that ngroups stays below capacity/2 plus margin.
+// The host sizes the table so that ngroups stays below capacity/2 plus margin — except when it sized it OPTIMISTICALLY
+// from the planner's group-count hint (kq_hashagg.cu): then a probe sequence that has seen every slot raises
+// A.overflow and the caller gets the DUMMY record behind the last slot (the table is allocated with capacity + 1
+// records), so nothing spins and nothing faults; the host discards the launch, restores the table and grows it.
 // `inserted` (optional): count new groups there instead of in A.ngroups — one counter for every insert of the whole
 // grid serialises in the L2 (10 M inserts cost milliseconds); callers add their tally to A.ngroups in bulk.
 __device__ __forceinline__ uint64_t* table_find_or_insert(const AggArgs& A, uint64_t h, const uint64_t (&kw)[MAX_KEYS], uint32_t nullmask,
                                                           uint32_t* inserted = nullptr) {
     uint64_t slot = table_home(h, A.cap_mask);
     const uint64_t full_hdr = HDR_FULL | ((uint64_t)nullmask << 32);
+    uint64_t probes = 0;
     while (true) {
+        if (++probes > A.cap_mask + 1 || (A.overflow && (probes & 63u) == 0 && *reinterpret_cast<volatile unsigned int*>(A.overflow))) {
+            if (A.overflow) *reinterpret_cast<volatile unsigned int*>(A.overflow) = 1u;
+            return A.table + (A.cap_mask + 1) * (uint64_t)A.stride;
+        }
         uint64_t* rec = A.table + slot * (uint64_t)A.stride;
         uint64_t hdr = *reinterpret_cast<volatile uint64_t*>(rec);
         uint32_t state = (uint32_t)hdr;
@@ -72,7 +80,7 @@ __device__ __forceinline__ uint64_t* table_find_or_insert(const AggArgs& A, uint
             }
             hdr = old; state = (uint32_t)hdr;
         }
-        if (state == HDR_BUSY) continue;          // another thread is publishing this slot: re-read
+        if (state == HDR_BUSY) { probes--; continue; }          // another thread is publishing this slot: re-read
         if (hdr == full_hdr) {
             bool eq = true;
 #pragma unroll
@@ -90,8 +98,10 @@ __device__ __forceinline__ void global_accumulate(uint64_t* rec, const AggInput&
         if (is_int) atomicAdd(reinterpret_cast<unsigned long long*>(rec + d.rec_sum), (unsigned long long)v);
         else atomicAdd(reinterpret_cast<double*>(rec + d.rec_sum), __longlong_as_double((long long)v));
     }
-    if (d.flags & (F_MIN | F_MAX)) {
-        uint64_t m = order_map(is_int ? v : canon_nan(v), is_int);
+    // MIN/MAX compare like the reference's `value > this.value` (Main.kt:552): a NaN never replaces a held value. A group
+    // whose non-null values were all NaN keeps the identity, which k_finalize turns into NaN.
+    if ((d.flags & (F_MIN | F_MAX)) && (is_int || __longlong_as_double((long long)v) == __longlong_as_double((long long)v))) {
+        uint64_t m = order_map(v, is_int);
         if ((d.flags & F_MIN) && m < __ldcg(rec + d.rec_min)) atomicMin(reinterpret_cast<unsigned long long*>(rec + d.rec_min), (unsigned long long)m);
         if ((d.flags & F_MAX) && m > __ldcg(rec + d.rec_max)) atomicMax(reinterpret_cast<unsigned long long*>(rec + d.rec_max), (unsigned long long)m);
     }

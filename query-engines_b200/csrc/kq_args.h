@@ -119,6 +119,7 @@ struct AggArgs {
     unsigned long long stop_threshold;
     unsigned int* ticket;
     uint32_t* err;
+    unsigned int* overflow;                // set when an insert finds the table full (optimistically sized table: the host rolls back and grows)
     // front end
     int32_t fe_groups, fe_nsum, fe_nmm;
     int32_t geo_r, geo_warps;              // tile geometry the host chose for this launch (host-side bookkeeping)

@@ -89,7 +89,7 @@ inline void kq_copy_text(const std::string& s, char* dst, size_t cap) {
 // ---- kq_jit.cu ----------------------------------------------------------------------------------------------------
 // Compile (or fetch from the process-wide cache) the kernel `entry` of: prelude + `generated` + skeleton.
 // `defines` are `#define` lines placed before the prelude (KQ_R, KQ_WARPS, KQ_KERNEL_*).
-enum KqSkeleton { KQ_SKEL_OPS = 0, KQ_SKEL_AGG = 1 };
+enum KqSkeleton { KQ_SKEL_OPS = 0, KQ_SKEL_AGG = 1, KQ_SKEL_AGG_FE = 2 };
 KQ_HIDDEN int kq_jit_kernel(kq_ctx* ctx, const std::string& defines, const std::string& generated, int skeleton,
                             const char* entry, int dynamic_smem, void** kernel_out);
 KQ_HIDDEN int kq_jit_compile_only(kq_ctx* ctx, const std::string& defines, const std::string& generated, int skeleton);

@@ -150,6 +150,12 @@ int kq_check_device_errors(kq_ctx* ctx) {
     uint32_t e = *ctx->h_err;
     if (!e) return KQ_OK;
     KQ_CUDA(ctx, cudaMemsetAsync(ctx->d_err, 0, 4, ctx->stream));
+    return kq_device_error_status(ctx, e);
+}
+
+// kq_status (and message) for the error bits a kernel raised.
+int kq_device_error_status(kq_ctx* ctx, uint32_t e) {
+    if (!e) return KQ_OK;
     if (e & KQ_DEV_ERR_DIV0) return kq_fail(ctx, KQ_ERR_ARITHMETIC, "/ by zero");
     if (e & KQ_DEV_ERR_NUMBER_FORMAT) return kq_fail(ctx, KQ_ERR_NUMBER_FORMAT, "For input string: cannot parse as double");
     if (e & 8u) return kq_fail(ctx, KQ_ERR_UNSUPPORTED, "Utf8->Float64 cast: value outside the exact fast path (>19 digits, |exp10|>22 or hex float)");

@@ -79,11 +79,63 @@ __global__ void k_merge_records(const AggArgs A, const uint64_t* __restrict__ re
     }
 }
 
-// every `pitch`-th word of `src` (the per-rank counts at the head of the gathered blocks of the small merge)
-__global__ void k_gather_words(const uint64_t* __restrict__ src, uint64_t pitch, int n, unsigned long long* out) {
-    for (int i = threadIdx.x; i < n; i += blockDim.x) out[i] = src[(uint64_t)i * pitch];
-}
+// ---- the one-shot merge of small partial tables (BASELINE configs 3 and 5) ---------------------------------------------
+// Block of one rank in the all-gather: [0] FULL records in its table (may exceed the block's room), [1] its status
+// (device error bits of the aggregate), [2] cursor, [8..] up to `room` records.
 constexpr uint64_t SMALL_MERGE_MAX = 1024;      // partial groups per rank up to which kq_hashagg_merge_allreduce takes the one-shot path
+constexpr int MERGE_HDR = 8;
+__global__ void k_collect_small(const uint64_t* __restrict__ table, uint64_t cap, int stride, uint64_t* block, uint64_t room, const uint32_t* __restrict__ err) {
+    unsigned long long* cursor = reinterpret_cast<unsigned long long*>(block) + 2;
+    for (uint64_t s = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; s < cap; s += (uint64_t)gridDim.x * blockDim.x) {
+        const uint64_t* src = table + s * stride;
+        if ((uint32_t)src[0] != HDR_FULL) continue;
+        const unsigned long long pos = atomicAdd(cursor, 1ULL);
+        if (pos < room) { uint64_t* dst = block + MERGE_HDR + pos * stride; for (int w = 0; w < stride; w++) dst[w] = src[w]; }
+    }
+    if (blockIdx.x == 0 && threadIdx.x == 0) block[1] = *err;
+}
+__global__ void k_collect_small_done(uint64_t* block) { block[0] = block[2]; }
+// [count, status] of every rank's block -> out[2 * rank]
+__global__ void k_merge_heads(const uint64_t* __restrict__ all, uint64_t pitch, int n, unsigned long long* out) {
+    for (int i = threadIdx.x; i < n; i += blockDim.x) { out[2 * i] = all[(uint64_t)i * pitch]; out[2 * i + 1] = all[(uint64_t)i * pitch + 1]; }
+}
+// Rebuild this rank's table from the gathered partials, RANK BY RANK in one block: a key occurs at most once per rank,
+// so within a rank no two threads touch the same record, and the barrier between ranks fixes the order of every
+// Float64 addition — all ranks end with bit-identical tables.
+__global__ void __launch_bounds__(1024) k_merge_small(const AggArgs A, const uint64_t* __restrict__ all, uint64_t pitch, int nranks, uint64_t room) {
+    __shared__ unsigned int s_new;
+    if (threadIdx.x == 0) s_new = 0;
+    __syncthreads();
+    for (int r = 0; r < nranks; r++) {
+        const uint64_t* blk = all + (uint64_t)r * pitch;
+        const uint64_t n = blk[0] < room ? blk[0] : room;
+        for (uint64_t s = threadIdx.x; s < n; s += blockDim.x) {
+            const uint64_t* src = blk + MERGE_HDR + s * A.stride;
+            uint64_t kw[MAX_KEYS];
+#pragma unroll
+            for (int k = 0; k < MAX_KEYS; k++) kw[k] = k < A.nkeys ? src[1 + k] : 0;
+            const uint32_t nullmask = (uint32_t)(src[0] >> 32);
+            uint32_t fresh = 0;
+            uint64_t* rec = table_find_or_insert(A, hash_key(kw, nullmask, A.nkeys), kw, nullmask, &fresh);
+            if (fresh) atomicAdd(&s_new, 1u);
+            for (int i = 0; i < A.ninputs; i++) {
+                const AggInput d = A.in[i];
+                const uint64_t c = src[d.rec_nn];
+                if (!c) continue;
+                rec[d.rec_nn] += c;                     // plain read-modify-write: this thread is the only one on this record in this round
+                if (d.flags & F_SUM) {
+                    if (d.flags & F_INT) rec[d.rec_sum] += src[d.rec_sum];
+                    else rec[d.rec_sum] = (uint64_t)__double_as_longlong(__dadd_rn(__longlong_as_double((long long)rec[d.rec_sum]), __longlong_as_double((long long)src[d.rec_sum])));
+                }
+                if (d.flags & F_MIN) rec[d.rec_min] = src[d.rec_min] < rec[d.rec_min] ? src[d.rec_min] : rec[d.rec_min];
+                if (d.flags & F_MAX) rec[d.rec_max] = src[d.rec_max] > rec[d.rec_max] ? src[d.rec_max] : rec[d.rec_max];
+            }
+        }
+        __threadfence();
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) *A.ngroups = s_new;
+}
 
 // ---- kernels of the multi-GPU merges -----------------------------------------------------------------------------
 __device__ __forceinline__ int record_part(const uint64_t* src, int nkeys, int nparts) {
@@ -218,7 +270,12 @@ __global__ void k_finalize(const __grid_constant__ FinArgs F) {
                 if (nn == 0) continue;                                                                    // all-null group => null (R9)
                 atomicOr(o.validity + (row >> 5), 1u << (row & 31));
                 uint64_t v = rec[o.word];
-                if (o.kind != KQ_AGG_SUM) v = order_unmap(v, o.is_int);
+                if (o.kind != KQ_AGG_SUM) {
+                    v = order_unmap(v, o.is_int);
+                    // Float64 MIN/MAX whose identity survived: every non-null value of the group was a NaN (NaNs never replace a held
+                    // value) => NaN, as the reference yields when the first value is NaN and nothing compares greater (Main.kt:545-555)
+                    if (!o.is_int && (v & 0x7fffffffffffffffULL) > 0x7ff0000000000000ULL) v = 0x7ff8000000000000ULL;
+                }
                 if (o.out_type == KQ_DATE32) reinterpret_cast<uint32_t*>(o.data)[row] = (uint32_t)v;
                 else reinterpret_cast<uint64_t*>(o.data)[row] = v;
             }
@@ -233,7 +290,8 @@ struct PackedLen {
         return (int)(packed[i] >> 56);
     }
 };
-__global__ void k_unpack_utf8(const uint64_t* __restrict__ packed, const int32_t* __restrict__ off, uint64_t n, uint8_t* out) {
+__global__ void k_unpack_utf8(const uint64_t* __restrict__ packed, const int32_t* __restrict__ off, const unsigned long long* __restrict__ nrows, uint8_t* out) {
+    const uint64_t n = *nrows;
     for (uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; i < n; i += (uint64_t)gridDim.x * blockDim.x) {
         int len = off[i + 1] - off[i];
         uint64_t p = packed[i];
@@ -277,7 +335,27 @@ struct kq_hashagg {
     unsigned long long* d_counters = nullptr;   // [0] ngroups, [1] ticket (low 32 bits)
     int64_t ngroups_host = 0;
     int64_t expected_groups = 0;
+    bool pessimistic = false;               // an optimistically sized table overflowed once: size for the rows in flight from now on
+    uint64_t* snapshot = nullptr;           // copy of a small table taken before an optimistic launch (rollback on overflow)
+    uint64_t snapshot_cap = 0;
+    // Errors raised by this aggregate's kernels (Int64 / 0, malformed number in a cast) live in its OWN device word
+    // (d_counters[5]) and are sticky: once seen, every later update / merge / finalize of this aggregate fails with the
+    // same status — an unrelated call on the context can neither consume nor hide them.
+    uint32_t dev_err = 0;
+    bool groups_exact = true;               // ngroups_host is exact (after a merge it is an upper bound until finalize reads the count)
+    // merge buffers (kq_hashagg_merge_allreduce), allocated once per aggregate
+    uint64_t* merge_mine = nullptr; uint64_t* merge_all = nullptr; uint64_t merge_words = 0;
 };
+
+// d_counters layout (64-bit words): [0] groups in the table, [1] tile/partition tickets, [2] finalize cursor, [3] scratch max,
+// [4] table-overflow flag, [5] device error bits of this aggregate, [6] merge scratch, [8..] Utf8 byte totals at finalize
+static int sticky_error(kq_ctx* ctx, kq_hashagg* h) { return h->dev_err ? kq_device_error_status(ctx, h->dev_err) : KQ_OK; }
+// counters of a finished launch: remembers device errors (sticky), reports an overflow of a conservatively sized table
+static int read_counters(kq_ctx* ctx, kq_hashagg* h, uint64_t (&c)[6]) {
+    KQ_RET(kq_read_u64(ctx, h->d_counters, 6, c));
+    if ((uint32_t)c[5]) { h->dev_err |= (uint32_t)c[5]; return sticky_error(ctx, h); }
+    return KQ_OK;
+}
 
 static bool expr_equal(const kq_expr* a, const kq_expr* b) {
     if (a == b) return true;
@@ -292,7 +370,7 @@ static bool expr_equal(const kq_expr* a, const kq_expr* b) {
 }
 
 static int table_alloc(kq_ctx* ctx, kq_hashagg* h, uint64_t capacity) {
-    size_t bytes = (size_t)capacity * h->stride * 8;
+    size_t bytes = (size_t)(capacity + 1) * h->stride * 8;       // + the dummy record a full table hands out (kq_aggtable.cuh)
     KQ_RET(kq_dev_alloc(ctx, bytes, (void**)&h->table));
     KQ_CUDA(ctx, cudaMemsetAsync(h->table, 0, bytes, ctx->stream));
     h->capacity = capacity;
@@ -320,7 +398,8 @@ static void fill_common_args(kq_hashagg* h, AggArgs& A) {
     A.cap_mask = h->capacity - 1;
     A.ngroups = h->d_counters;
     A.ticket = (unsigned int*)(h->d_counters + 1);
-    A.err = h->ctx->d_err;
+    A.err = (uint32_t*)(h->d_counters + 5);
+    A.overflow = (unsigned int*)(h->d_counters + 4);
     A.stop_threshold = ~0ULL;
 }
 
@@ -387,12 +466,15 @@ int kq_hashagg_create(kq_ctx* ctx, kq_expr* pred, kq_expr* const* group_exprs, i
     cudaSetDevice(ctx->device);
     kq_hashagg* h = nullptr;
     KQ_RET(hashagg_new(ctx, pred, group_exprs, ngroup, agg_kinds, agg_inputs, nagg, expected_groups, &h));
-    cudaError_t e = cudaMalloc(&h->d_counters, 64);
-    if (e == cudaSuccess) e = cudaMemsetAsync(h->d_counters, 0, 64, ctx->stream);
-    if (e != cudaSuccess) { kq_hashagg_free(h); return kq_cuda_fail(ctx, e, "cudaMalloc"); }
-    uint64_t cap = 1ULL << 16;
+    // counters and table come from the ctx's caching allocator: creating an aggregate costs no cudaMalloc after the first query
+    int st = kq_dev_alloc(ctx, 256, (void**)&h->d_counters);
+    if (st != KQ_OK) { kq_hashagg_free(h); return st; }
+    cudaError_t e = cudaMemsetAsync(h->d_counters, 0, 256, ctx->stream);
+    if (e != cudaSuccess) { kq_hashagg_free(h); return kq_cuda_fail(ctx, e, "cudaMemsetAsync"); }
+    // sized from the planner's hint: a 50-group query gets a 1024-slot table (64 KB), not one sized for the rows in flight
+    uint64_t cap = 1024;
     while ((int64_t)cap < expected_groups * 2) cap <<= 1;
-    int st = table_alloc(ctx, h, cap);
+    st = table_alloc(ctx, h, cap);
     if (st != KQ_OK) { kq_hashagg_free(h); return st; }
     *out = h;
     return KQ_OK;
@@ -406,7 +488,10 @@ int kq_hashagg_free(kq_hashagg* h) {
         for (kq_expr* e : h->groups) kq_expr_free(e);
         for (kq_expr* e : h->inputs) kq_expr_free(e);
         kq_dev_free(h->ctx, h->table);
-        if (h->d_counters) { cudaStreamSynchronize(h->ctx->stream); cudaFree(h->d_counters); }
+        kq_dev_free(h->ctx, h->d_counters);
+        kq_dev_free(h->ctx, h->snapshot);
+        kq_dev_free(h->ctx, h->merge_mine);
+        kq_dev_free(h->ctx, h->merge_all);
         delete h;
     }
     return KQ_OK;
@@ -511,6 +596,49 @@ static int plan_agg(kq_ctx* ctx, kq_hashagg* h, kq_batch* input, int smem_optin,
         return std::max(0, std::min(FE_MAX_GROUPS, budget / per_group - 1));
     };
     const char* forced = getenv("KQ_AGG_GEOM");
+    int fe_smem = 0;
+    if (mode == 3) {
+        // kq_k_agg_fe.cuh: lane-private SUM/COUNT blocks per consumer warp (the shared-memory data path bounds this kernel,
+        // so the warp count only has to hide latency), a stage ring with at least ~48 KB in flight beyond the stage being
+        // consumed, and a directory sparse enough for perfect placement (>= 8 slots per group).
+        const int gs = ns * 256 + ncnt * 128, nmm1 = std::max(nm, 1), nkw = std::max(NK, 1);
+        int want = h->expected_groups > 0 ? (int)std::min<int64_t>(FE_MAX_GROUPS, h->expected_groups + 2) : FE_MAX_GROUPS;
+        want = std::max(want, 4);
+        auto fe_bytes = [&](int g, int warps, int dir) {
+            return dir * 4 + dir * nkw * 8 + g * nkw * 8 + (g + 1) * nmm1 * 8 + g * 8 + ((g + 3) & ~3) * 4 + warps * (g + 1) * gs;
+        };
+        const int budget = smem_optin - 1024;
+        struct Cand { int r, warps; };
+        static const Cand CAND[] = {{4, 8}, {4, 7}, {4, 6}, {2, 8}, {4, 5}, {2, 6}, {4, 4}, {2, 4}, {2, 2}};
+        int fr = 0, fw = 0, fs = 0;                                   // tuning experiments: KQ_AGG_GEOM="rows,warps[,stages]"
+        if (forced) sscanf(forced, "%d,%d,%d", &fr, &fw, &fs);
+        bool found = false;
+        // the first candidate (most consumer warps first) that holds `want` groups; a directory of fewer groups only if nothing does
+        for (int g = want; g >= 4 && !found; g = g * 3 / 4) {
+            for (const Cand& c : CAND) {
+                const int r = fr > 0 ? fr : c.r, w = fw > 0 ? fw : c.warps;
+                int dir = 256;
+                while (dir < 16 * g) dir <<= 1;
+                StagePlan sp;
+                const std::string defs = cg.plan_stages(1 << 30, 1, w * 32 * r, &sp, true);
+                int fe = fe_bytes(g, w, dir);
+                // three stages at least, and ~40 KB in flight beyond the stage being consumed (HBM latency x the SM's bandwidth share)
+                int ring_min = std::max(3 * sp.stage_bytes, sp.stage_bytes + 40 * 1024);
+                if (fr > 0) ring_min = 2 * sp.stage_bytes;
+                if (fe + ring_min > budget) { dir >>= 1; fe = fe_bytes(g, w, dir); }       // 8 slots per group still places within a few attempts
+                if (fe + ring_min <= budget) {
+                    int st = std::min((budget - fe) / sp.stage_bytes, 6);
+                    if (fs > 0) st = std::min(st, std::max(fs, 2));
+                    sp.nstages = st;
+                    geo = AggGeometry{r, w}; A.sp = sp; stage_defs = defs; fg = g; dir_slots = dir; fe_smem = fe;
+                    found = true;
+                    break;
+                }
+                if (fr > 0) break;
+            }
+        }
+        if (!found) return kq_fail(ctx, KQ_ERR_UNSUPPORTED, "aggregate too wide for the shared-memory front end");
+    }
     if (mode == 2) {
         // mid cardinality: block-shared table; many warps hide the latency of its shared-memory atomics
         geo = forced ? agg_geometry(NI) : AggGeometry{4, 15};
@@ -542,6 +670,7 @@ static int plan_agg(kq_ctx* ctx, kq_hashagg* h, kq_batch* input, int smem_optin,
     A.fe_groups = fg;
     A.geo_r = geo.r; A.geo_warps = geo.warps;
     A.smem_bytes = ring + dir_slots * entry_words * 8 + std::max(fg, 1) * 12 + (fg + 1) * nm * 8 + WARPS * (fg + 1) * 32 * (8 * ns + 4 * ncnt);
+    if (mode == 3) A.smem_bytes = ring + fe_smem;
     if (mode == 1) A.smem_bytes += 16 + nparts * 4;
     A.smem_bytes = (A.smem_bytes + 127) / 128 * 128;
     {   // pass-2 table: a sparse LOOKUP part (state + key words per slot, power-of-two slots, <= 45 % full so that probe
@@ -590,8 +719,7 @@ static int plan_agg(kq_ctx* ctx, kq_hashagg* h, kq_batch* input, int smem_optin,
     *defines_out = "#define KQ_R " + std::to_string(geo.r) + "\n#define KQ_WARPS " + std::to_string(geo.warps) + "\n#define KQ_STAGES " + std::to_string(A.sp.nstages) + "\n#define KQ_FE_GROUPS " + std::to_string(fg) + "\n#define KQ_DIR_SLOTS " +
                                 std::to_string(dir_slots) + (getenv("KQ_L2_PREFETCH") ? "\n#define KQ_L2_PREFETCH " + std::to_string(atoi(getenv("KQ_L2_PREFETCH"))) : std::string()) +
                                 "\n#define KQ_STAGE_BYTES " + (has_bytes ? "1" : "0") + "\n#define KQ_AGG_MODE " + std::to_string(mode) + "\n" +
-                                (getenv("KQ_PART_L2_HINTS") ? "#define KQ_PART_L2_HINTS " + std::to_string(atoi(getenv("KQ_PART_L2_HINTS"))) + "\n" : std::string()) +
-                                (getenv("KQ_GLOBAL_BATCHED") ? "#define KQ_GLOBAL_BATCHED " + std::to_string(atoi(getenv("KQ_GLOBAL_BATCHED"))) + "\n" : std::string());
+                                (getenv("KQ_PART_L2_HINTS") ? "#define KQ_PART_L2_HINTS " + std::to_string(atoi(getenv("KQ_PART_L2_HINTS"))) + "\n" : std::string());
     return KQ_OK;
 }
 
@@ -670,8 +798,9 @@ static int hashagg_update_partitioned(kq_ctx* ctx, kq_hashagg* h, kq_batch* inpu
         cudaMemsetAsync(d_max, 0, 8, ctx->stream);
         k_max_u32<<<small_grid(ctx, buckets), 256, 0, ctx->stream>>>(counts, buckets, d_max);
         if ((st = launch_check(ctx, "k_max_u32")) != KQ_OK) return done(st);
-        uint64_t c[4];
-        if ((st = kq_read_u64(ctx, h->d_counters, 4, c)) != KQ_OK) return done(st);
+        uint64_t c[6];
+        if ((st = read_counters(ctx, h, c)) != KQ_OK) return done(st);
+        if ((uint32_t)c[4] != 0) return done(kq_fail(ctx, KQ_ERR_ILLEGAL_STATE, "aggregation table overflow"));
         h->ngroups_host = (int64_t)c[0];
         const int64_t taken = std::min<int64_t>((int64_t)(uint32_t)c[1], tile_end - tile_begin);
         const uint64_t max_bucket = c[3];
@@ -689,7 +818,8 @@ static int hashagg_update_partitioned(kq_ctx* ctx, kq_hashagg* h, kq_batch* inpu
             ce = cudaLaunchKernel(k_reduce, dim3(std::min(nparts - part_begin, ctx->sm_count)), dim3(512), kargs, (size_t)reduce_smem, ctx->stream);
             if (ce != cudaSuccess) return done(kq_cuda_fail(ctx, ce, "cudaLaunchKernel(kq_agg_partition_reduce)"));
             ctx->launches++;
-            if ((st = kq_read_u64(ctx, h->d_counters, 2, c)) != KQ_OK) return done(st);
+            if ((st = read_counters(ctx, h, c)) != KQ_OK) return done(st);
+            if ((uint32_t)c[4] != 0) return done(kq_fail(ctx, KQ_ERR_ILLEGAL_STATE, "aggregation table overflow"));
             h->ngroups_host = (int64_t)c[0];
             part_begin += (int)std::min<int64_t>((int64_t)(uint32_t)c[1], nparts - part_begin);
         }
@@ -699,11 +829,90 @@ static int hashagg_update_partitioned(kq_ctx* ctx, kq_hashagg* h, kq_batch* inpu
     return done(KQ_OK);
 }
 
+// ---- the low-cardinality path (kq_k_agg_fe.cuh) ---------------------------------------------------------------------------
+// The global table is sized OPTIMISTICALLY from the planner's hint (a few KB for a 50-group query: nothing to zero, scan
+// or collect beyond the groups themselves). Should the hint be wrong by so much that the table fills up, the kernel
+// raises the overflow flag instead of spinning; the launch is discarded, the table restored from a snapshot taken
+// before it (only a non-empty table needs one) and the batch is redone with the conservative capacity rule.
+static int hashagg_update_fe(kq_ctx* ctx, kq_hashagg* h, kq_batch* input, int64_t n) {
+    AggArgs A;
+    memset(&A, 0, sizeof A);
+    std::string defines, gen;
+    KQ_RET(plan_agg(ctx, h, input, ctx->max_smem_optin, A, &defines, &gen, 3));
+    if (n == 0) return KQ_OK;
+    const AggGeometry geo{A.geo_r, A.geo_warps};
+    const int TILE = geo.tile(), THREADS = geo.threads();
+    A.n = n; A.ntiles = (n + TILE - 1) / TILE;
+    void* kernel = nullptr;
+    KQ_RET(kq_jit_kernel(ctx, defines, gen, KQ_SKEL_AGG_FE, "kq_group_aggregate", A.smem_bytes, &kernel));
+    const int grid = (int)std::min<int64_t>(A.ntiles, (int64_t)ctx->sm_count);
+    // rows that may still create groups after a block has decided to continue (conservative rule only)
+    const uint64_t margin = (uint64_t)grid * ((uint64_t)(A.sp.nstages + 1) * TILE + FE_MAX_GROUPS);
+
+    int64_t tile_begin = 0;
+    while (tile_begin < A.ntiles) {
+        const uint64_t remaining_rows = (uint64_t)(n - tile_begin * TILE);
+        uint64_t cap = h->capacity;
+        bool unthrottled = false;
+        const bool optimistic = !h->pessimistic;
+        if (optimistic) {
+            // room for 8x the groups known or promised; the kernel stops taking tiles past half full, overflow is caught
+            const uint64_t g = (uint64_t)std::max<int64_t>(std::max<int64_t>(h->expected_groups, h->ngroups_host), 64);
+            while (cap < 8 * g) cap <<= 1;
+        } else {
+            const uint64_t inflight = std::min(margin, remaining_rows);
+            while (true) {
+                if ((uint64_t)h->ngroups_host + remaining_rows <= cap / 4 * 3) { unthrottled = true; break; }
+                if (cap / 4 >= inflight && (uint64_t)h->ngroups_host < cap / 2) break;
+                cap <<= 1;
+            }
+        }
+        if (cap != h->capacity) KQ_RET(table_grow(ctx, h, cap));
+        const bool need_snapshot = optimistic && h->ngroups_host > 0;
+        if (need_snapshot) {
+            if (h->snapshot_cap != h->capacity) {
+                kq_dev_free(ctx, h->snapshot); h->snapshot = nullptr; h->snapshot_cap = 0;
+                KQ_RET(kq_dev_alloc(ctx, (size_t)(h->capacity + 1) * h->stride * 8, (void**)&h->snapshot));
+                h->snapshot_cap = h->capacity;
+            }
+            KQ_CUDA(ctx, cudaMemcpyAsync(h->snapshot, h->table, (size_t)h->capacity * h->stride * 8, cudaMemcpyDeviceToDevice, ctx->stream));
+        }
+        const int64_t groups_before = h->ngroups_host;
+        fill_common_args(h, A);
+        A.tile_begin = tile_begin;
+        A.stop_threshold = unthrottled ? ~0ULL : h->capacity / 2;
+        KQ_CUDA(ctx, cudaMemsetAsync(h->d_counters + 1, 0, 8, ctx->stream));
+        void* kargs[] = {&A};
+        KQ_CUDA(ctx, cudaLaunchKernel(kernel, dim3(grid), dim3(THREADS), kargs, (size_t)A.smem_bytes, ctx->stream));
+        ctx->launches++;
+        uint64_t c[6];
+        KQ_RET(read_counters(ctx, h, c));
+        if ((uint32_t)c[4] != 0) {
+            // the table filled up (the hint was far off): discard this launch and redo its tiles with a table sized for the rows in flight
+            if (!optimistic) return kq_fail(ctx, KQ_ERR_ILLEGAL_STATE, "aggregation table overflow");
+            if (need_snapshot) KQ_CUDA(ctx, cudaMemcpyAsync(h->table, h->snapshot, (size_t)h->capacity * h->stride * 8, cudaMemcpyDeviceToDevice, ctx->stream));
+            else KQ_CUDA(ctx, cudaMemsetAsync(h->table, 0, (size_t)(h->capacity + 1) * h->stride * 8, ctx->stream));
+            const unsigned long long restore[1] = {(unsigned long long)groups_before};
+            KQ_CUDA(ctx, cudaMemcpyAsync(h->d_counters, restore, 8, cudaMemcpyHostToDevice, ctx->stream));
+            KQ_CUDA(ctx, cudaMemsetAsync(h->d_counters + 4, 0, 8, ctx->stream));
+            KQ_CUDA(ctx, cudaStreamSynchronize(ctx->stream));          // `restore` lives on this stack frame
+            h->pessimistic = true;
+            continue;
+        }
+        h->ngroups_host = (int64_t)c[0];
+        const int64_t taken = (int64_t)(uint32_t)c[1];
+        tile_begin += std::min<int64_t>(taken, A.ntiles - tile_begin);
+        if (tile_begin < A.ntiles) KQ_RET(table_grow(ctx, h, h->capacity * 4));      // stopped early: the table crossed half full
+    }
+    return KQ_OK;
+}
+
 extern "C" {
 
 int kq_hashagg_update(kq_ctx* ctx, kq_hashagg* h, kq_batch* input) {
     if (!ctx || !h || !input) return KQ_ERR_ILLEGAL_ARGUMENT;
     cudaSetDevice(ctx->device);
+    KQ_RET(sticky_error(ctx, h));
     int64_t n; KQ_RET(kq_batch_resolve_rows(ctx, input, &n));
     for (kq_col* c : input->cols) KQ_RET(kq_col_resolve_rows(ctx, c, nullptr));
 
@@ -714,6 +923,8 @@ int kq_hashagg_update(kq_ctx* ctx, kq_hashagg* h, kq_batch* input) {
     const int64_t g_est = std::max<int64_t>(h->expected_groups, h->ngroups_host);
     const int64_t part_min_groups = getenv("KQ_PART_MIN_GROUPS") ? atoll(getenv("KQ_PART_MIN_GROUPS")) : PART_MIN_GROUPS;      // tuning experiments
     if (g_est >= part_min_groups && n >= PART_MIN_ROWS && !getenv("KQ_NO_PARTITION")) return hashagg_update_partitioned(ctx, h, input, n, g_est);
+    // Low cardinality (planner hint / what earlier batches showed fits the CTA directory, or nothing is known yet): kq_k_agg_fe.cuh
+    if (g_est <= FE_MAX_GROUPS && !getenv("KQ_NO_FE")) return hashagg_update_fe(ctx, h, input, n);
     // Mid cardinality (more groups than the lane-private front end holds, few enough for one shared-memory table per block)
     int mode = 0;
     if (g_est > FE_MAX_GROUPS && !getenv("KQ_NO_SHARED_TABLE")) {
@@ -757,8 +968,9 @@ int kq_hashagg_update(kq_ctx* ctx, kq_hashagg* h, kq_batch* input) {
         void* kargs[] = {&A};
         KQ_CUDA(ctx, cudaLaunchKernel(kernel, dim3(grid), dim3(THREADS), kargs, (size_t)A.smem_bytes, ctx->stream));
         ctx->launches++;
-        uint64_t c[2];
-        KQ_RET(kq_read_u64(ctx, h->d_counters, 2, c));
+        uint64_t c[6];
+        KQ_RET(read_counters(ctx, h, c));
+        if ((uint32_t)c[4] != 0) return kq_fail(ctx, KQ_ERR_ILLEGAL_STATE, "aggregation table overflow");      // cannot happen under the capacity rule above
         h->ngroups_host = (int64_t)c[0];
         int64_t taken = (int64_t)(uint32_t)c[1];
         tile_begin += std::min<int64_t>(taken, A.ntiles - tile_begin);
@@ -782,8 +994,11 @@ int kq_explain_hashagg(kq_expr* pred, kq_expr* const* group_exprs, int ngroup, c
     memset(&A, 0, sizeof A);
     std::string defines, gen;
     const char* ep = getenv("KQ_EXPLAIN_PARTS");          // tuning aid: compile the partitioned path's kernels instead (0: the block-shared table mode)
-    if (st == KQ_OK) st = plan_agg(&fake, h, &sb.batch, 232448, A, &defines, &gen, ep ? (atoi(ep) > 0 ? 1 : 2) : 0, ep ? atoi(ep) : 0);
-    if (st == KQ_OK && compile) st = kq_jit_compile_only(&fake, defines, gen, KQ_SKEL_AGG);
+    // default: what kq_hashagg_update would run for this hint — the low-cardinality kernel up to FE_MAX_GROUPS groups
+    const int64_t egv = eg ? atoll(eg) : 0;
+    const int mode = ep ? (atoi(ep) > 0 ? 1 : 2) : ((egv <= FE_MAX_GROUPS && !getenv("KQ_NO_FE")) ? 3 : 0);
+    if (st == KQ_OK) st = plan_agg(&fake, h, &sb.batch, 232448, A, &defines, &gen, mode, ep ? atoi(ep) : 0);
+    if (st == KQ_OK && compile) st = kq_jit_compile_only(&fake, defines, gen, mode == 3 ? KQ_SKEL_AGG_FE : KQ_SKEL_AGG);
     kq_copy_text(st == KQ_OK ? defines + gen : fake.last_error, source, source_cap);
     if (h) hashagg_delete_host(h);
     return st;
@@ -791,18 +1006,22 @@ int kq_explain_hashagg(kq_expr* pred, kq_expr* const* group_exprs, int ngroup, c
 
 int kq_hashagg_num_groups(kq_ctx* ctx, kq_hashagg* h, int64_t* n) {
     if (!ctx || !h || !n) return KQ_ERR_ILLEGAL_ARGUMENT;
-    uint64_t c; KQ_RET(kq_read_u64(ctx, h->d_counters, 1, &c));
-    h->ngroups_host = (int64_t)c;
-    *n = (int64_t)c;
+    KQ_RET(sticky_error(ctx, h));
+    uint64_t c[6]; KQ_RET(read_counters(ctx, h, c));
+    h->ngroups_host = (int64_t)c[0]; h->groups_exact = true;
+    *n = (int64_t)c[0];
     return KQ_OK;
 }
 
+// One output batch (Main.kt:635-650). ONE host synchronisation: the output columns are allocated for the group count the
+// host already knows (exact after an update, an upper bound after a merge), every kernel is queued, then the row count,
+// the Utf8 byte totals and this aggregate's error word come back in a single copy.
 int kq_hashagg_finalize(kq_ctx* ctx, kq_hashagg* h, kq_batch** out) {
     if (!ctx || !h || !out) return KQ_ERR_ILLEGAL_ARGUMENT;
     cudaSetDevice(ctx->device);
     if (!h->typed) return kq_fail(ctx, KQ_ERR_ILLEGAL_STATE, "finalize before any update: output types unknown");
-    KQ_RET(kq_check_device_errors(ctx));
-    int64_t G; KQ_RET(kq_hashagg_num_groups(ctx, h, &G));
+    KQ_RET(sticky_error(ctx, h));
+    const int64_t G = h->ngroups_host;             // rows to allocate (>= the rows that will be written)
     if (G > 2147483647LL) return kq_fail(ctx, KQ_ERR_UNSUPPORTED, "more than 2^31-1 groups in one output batch");
     FinArgs F;
     memset(&F, 0, sizeof F);
@@ -810,8 +1029,14 @@ int kq_hashagg_finalize(kq_ctx* ctx, kq_hashagg* h, kq_batch** out) {
     F.nkeys = (int)h->groups.size(); F.naggs = (int)h->agg_kinds.size();
     std::vector<kq_col*> cols;
     std::vector<uint64_t*> packed((size_t)F.nkeys, nullptr);
+    std::vector<unsigned long long*> scratches;
     int st = KQ_OK;
-    auto fail = [&](int s) { for (kq_col* c : cols) kq_column_free(c); for (uint64_t* p : packed) kq_dev_free(ctx, p); return s; };
+    auto fail = [&](int s) {
+        for (kq_col* c : cols) kq_column_free(c);
+        for (uint64_t* p : packed) kq_dev_free(ctx, p);
+        for (unsigned long long* p : scratches) kq_dev_free(ctx, p);
+        return s;
+    };
     for (int k = 0; k < F.nkeys; k++) {
         kq_col* c = nullptr;
         int t = h->key_types[(size_t)k];
@@ -821,7 +1046,7 @@ int kq_hashagg_finalize(kq_ctx* ctx, kq_hashagg* h, kq_batch** out) {
         if (t == KQ_BOOL) cudaMemsetAsync(c->data, 0, (size_t)((G + 63) / 64) * 8, ctx->stream);
         F.keys[k].validity = c->validity; F.keys[k].type = t;
         if (t == KQ_UTF8) {
-            if ((st = kq_dev_alloc(ctx, (size_t)G * 8, (void**)&packed[(size_t)k])) != KQ_OK) return fail(st);
+            if ((st = kq_dev_alloc(ctx, (size_t)std::max<int64_t>(G, 1) * 8, (void**)&packed[(size_t)k])) != KQ_OK) return fail(st);
             F.keys[k].data = packed[(size_t)k];
         } else F.keys[k].data = c->data;
     }
@@ -846,28 +1071,38 @@ int kq_hashagg_finalize(kq_ctx* ctx, kq_hashagg* h, kq_batch** out) {
         k_finalize<<<small_grid(ctx, h->capacity), 256, 0, ctx->stream>>>(F);
         if ((st = launch_check(ctx, "k_finalize")) != KQ_OK) return fail(st);
     }
+    // Utf8 keys: packed words -> offsets (device-wide scan over d_pos rows) + bytes; the byte total of key k lands in d_counters[8 + k]
     for (int k = 0; k < F.nkeys; k++) {
         if (h->key_types[(size_t)k] != KQ_UTF8) continue;
         kq_col* c = cols[(size_t)k];
         int64_t ntiles = (G + SCAN_TILE - 1) / SCAN_TILE + 1;
         unsigned long long* scratch = nullptr;
         if ((st = kq_dev_alloc(ctx, (size_t)(ntiles + 4) * 8, (void**)&scratch)) != KQ_OK) return fail(st);
+        scratches.push_back(scratch);
         cudaMemsetAsync(scratch, 0, (size_t)(ntiles + 4) * 8, ctx->stream);
         PackedLen pl{packed[(size_t)k], c->validity};
         int sg = (int)std::max<int64_t>(1, std::min<int64_t>(ntiles, (int64_t)ctx->sm_count * 4));
-        k_exclusive_offsets<PackedLen><<<sg, 256, 0, ctx->stream>>>(pl, h->d_counters, c->offsets, scratch + 4, (unsigned int*)scratch, scratch + 2);
-        if ((st = launch_check(ctx, "k_exclusive_offsets")) != KQ_OK) { kq_dev_free(ctx, scratch); return fail(st); }
+        k_exclusive_offsets<PackedLen><<<sg, 256, 0, ctx->stream>>>(pl, d_pos, c->offsets, scratch + 4, (unsigned int*)scratch, h->d_counters + 8 + k);
+        if ((st = launch_check(ctx, "k_exclusive_offsets")) != KQ_OK) return fail(st);
         if (G > 0) {
-            k_unpack_utf8<<<small_grid(ctx, (uint64_t)G), 256, 0, ctx->stream>>>(packed[(size_t)k], c->offsets, (uint64_t)G, (uint8_t*)c->data);
-            if ((st = launch_check(ctx, "k_unpack_utf8")) != KQ_OK) { kq_dev_free(ctx, scratch); return fail(st); }
+            k_unpack_utf8<<<small_grid(ctx, (uint64_t)G), 256, 0, ctx->stream>>>(packed[(size_t)k], c->offsets, d_pos, (uint8_t*)c->data);
+            if ((st = launch_check(ctx, "k_unpack_utf8")) != KQ_OK) return fail(st);
         }
-        uint64_t bytes;
-        if ((st = kq_read_u64(ctx, scratch + 2, 1, &bytes)) != KQ_OK) { kq_dev_free(ctx, scratch); return fail(st); }
-        c->data_bytes = (int64_t)bytes;
-        kq_dev_free(ctx, scratch);
     }
+    uint64_t c16[16];
+    if ((st = kq_read_u64(ctx, h->d_counters, 8 + MAX_KEYS, c16)) != KQ_OK) return fail(st);
+    if ((uint32_t)c16[5]) { h->dev_err |= (uint32_t)c16[5]; return fail(sticky_error(ctx, h)); }
+    const int64_t rows = (int64_t)c16[2];
+    h->ngroups_host = (int64_t)c16[0]; h->groups_exact = true;
+    for (int k = 0; k < F.nkeys; k++) {
+        kq_col* c = cols[(size_t)k];
+        c->n = rows;
+        if (h->key_types[(size_t)k] == KQ_UTF8) c->data_bytes = (int64_t)c16[8 + k];
+    }
+    for (size_t a = (size_t)F.nkeys; a < cols.size(); a++) cols[a]->n = rows;
     for (uint64_t*& p : packed) { kq_dev_free(ctx, p); p = nullptr; }
-    st = kq_batch_create(ctx, cols.data(), (int)cols.size(), G, out);
+    for (unsigned long long*& p : scratches) { kq_dev_free(ctx, p); p = nullptr; }
+    st = kq_batch_create(ctx, cols.data(), (int)cols.size(), rows, out);
     for (kq_col* c : cols) kq_column_free(c);
     cols.clear();
     return st;
@@ -901,130 +1136,169 @@ int kq_hashagg_merge_allreduce(kq_ctx* ctx, kq_hashagg* h) {
     cudaSetDevice(ctx->device);
     ncclComm_t comm = (ncclComm_t)ctx->comm;
     const int nr = ctx->nranks, me = ctx->rank, stride = h->stride, nkeys = (int)h->groups.size();
-    KQ_RET(kq_check_device_errors(ctx));
-    KQ_RET(refresh_group_count(ctx, h));
-    const uint64_t G = (uint64_t)h->ngroups_host;
+    // (a sticky error from an earlier call does not return here: the peers are, or will be, in the all-gather, so this
+    //  rank joins it and its status word — d_counters[5] still holds the bits — tells everybody)
 
     // 0. Small unions (BASELINE configs 3 and 5: tens of groups) are latency-bound, so the all-reduce is done the
-    //    latency-optimal way: ONE fixed-size all-gather carrying every rank's group count and, when it has at most
-    //    SMALL_MERGE_MAX groups, its partial records; then every rank rebuilds its table by merging the gathered
-    //    partials rank by rank (a key occurs at most once per rank, so the order of every Float64 addition is fixed
-    //    and all ranks end with bit-identical results). One host synchronisation, no dictionary, no dense arrays.
+    //    latency-optimal way: ONE fixed-size all-gather carrying every rank's group count, status and (when they fit) its
+    //    partial records; then every rank rebuilds its table from the gathered partials rank by rank (k_merge_small:
+    //    the order of every Float64 addition is fixed, all ranks end bit-identical). One host synchronisation — it also
+    //    is where all ranks agree, on the SAME gathered data, whether anybody failed and which path to take, so no rank
+    //    leaves while its peers wait in a collective. No allocation after the aggregate's first merge.
+    const uint64_t room = (h->expected_groups > 0 && h->expected_groups <= 96) ? 128 : SMALL_MERGE_MAX;       // same on every rank: the plan's hint
     {
-        const uint64_t blockw = 8 + SMALL_MERGE_MAX * (uint64_t)stride;          // words per rank: [0] count, [1] cursor, [2] base, [8..] records
-        uint64_t *mine = nullptr, *all = nullptr;
-        unsigned long long* d_cnt = nullptr;
-        KQ_RET(kq_dev_alloc(ctx, (size_t)blockw * 8, (void**)&mine));
-        int st = kq_dev_alloc(ctx, (size_t)blockw * 8 * nr, (void**)&all);
-        if (st == KQ_OK) st = kq_dev_alloc(ctx, (size_t)nr * 8, (void**)&d_cnt);
-        auto cleanup = [&](int s2) { kq_dev_free(ctx, mine); kq_dev_free(ctx, all); kq_dev_free(ctx, d_cnt); return s2; };
-        if (st != KQ_OK) return cleanup(st);
-        cudaMemsetAsync(mine, 0, (size_t)blockw * 8, ctx->stream);
-        cudaMemcpyAsync(mine, &G, 8, cudaMemcpyHostToDevice, ctx->stream);
-        if (G > 0 && G <= SMALL_MERGE_MAX) {
-            k_collect_records<<<small_grid(ctx, h->capacity), 256, 0, ctx->stream>>>(h->table, h->capacity, stride, nkeys, mine + 8,
-                                                                                   (unsigned long long*)mine + 1, 1, (unsigned long long*)mine + 2);
-            if ((st = launch_check(ctx, "k_collect_records")) != KQ_OK) return cleanup(st);
+        const uint64_t blockw = MERGE_HDR + room * (uint64_t)stride;
+        if (h->merge_words != blockw) {
+            kq_dev_free(ctx, h->merge_mine); kq_dev_free(ctx, h->merge_all);
+            h->merge_mine = h->merge_all = nullptr; h->merge_words = 0;
+            // an allocation failure here cannot be reported before the collective without leaving the peers hanging:
+            // nothing else has been allocated yet for this merge, so fail the rank hard (the job's launcher aborts the others)
+            int st0 = kq_dev_alloc(ctx, (size_t)blockw * 8, (void**)&h->merge_mine);
+            if (st0 == KQ_OK) st0 = kq_dev_alloc(ctx, (size_t)blockw * 8 * nr + 2 * 64 * 8, (void**)&h->merge_all);
+            if (st0 != KQ_OK) return st0;
+            h->merge_words = blockw;
         }
+        uint64_t* mine = h->merge_mine; uint64_t* all = h->merge_all;
+        unsigned long long* d_heads = reinterpret_cast<unsigned long long*>(all + blockw * nr);
+        if (nr > 64) return kq_fail(ctx, KQ_ERR_UNSUPPORTED, "more than 64 ranks");
+        cudaMemsetAsync(mine, 0, MERGE_HDR * 8, ctx->stream);
+        k_collect_small<<<small_grid(ctx, h->capacity), 256, 0, ctx->stream>>>(h->table, h->capacity, stride, mine, room, (const uint32_t*)(h->d_counters + 5));
+        k_collect_small_done<<<1, 1, 0, ctx->stream>>>(mine);
+        ctx->launches += 2;
         ncclResult_t r0 = N->AllGather(mine, all, (size_t)blockw, ncclUint64, comm, ctx->stream);
-        if (r0 != ncclSuccess) return cleanup(kq_nccl_fail(ctx, r0, "ncclAllGather"));
-        k_gather_words<<<1, 64, 0, ctx->stream>>>(all, blockw, nr, d_cnt);
-        if ((st = launch_check(ctx, "k_gather_words")) != KQ_OK) return cleanup(st);
-        uint64_t cnt[64];
-        if (nr > 64) return cleanup(kq_fail(ctx, KQ_ERR_UNSUPPORTED, "more than 64 ranks"));
-        if ((st = kq_read_u64(ctx, d_cnt, nr, cnt)) != KQ_OK) return cleanup(st);
-        uint64_t total = 0, maxn = 0;
-        for (int i = 0; i < nr; i++) { total += cnt[i]; maxn = std::max(maxn, cnt[i]); }
-        if (total == 0) return cleanup(KQ_OK);
-        if (maxn <= SMALL_MERGE_MAX && !getenv("KQ_NO_SMALL_MERGE")) {
+        if (r0 != ncclSuccess) return kq_nccl_fail(ctx, r0, "ncclAllGather");
+        k_merge_heads<<<1, 64, 0, ctx->stream>>>(all, blockw, nr, d_heads);
+        ctx->launches++;
+        uint64_t heads[128];
+        KQ_RET(kq_read_u64(ctx, d_heads, 2 * nr > 64 ? 64 : 2 * nr, heads));
+        if (2 * nr > 64) KQ_RET(kq_read_u64(ctx, d_heads + 64, 2 * nr - 64, heads + 64));
+        uint64_t total = 0, maxn = 0; uint32_t status = 0;
+        for (int i = 0; i < nr; i++) { total += heads[2 * i]; maxn = std::max(maxn, heads[2 * i]); status |= (uint32_t)heads[2 * i + 1]; }
+        if (status) { h->dev_err |= status; return sticky_error(ctx, h); }       // some rank's kernels raised an error: every rank reports it
+        if (total == 0) return KQ_OK;
+        if (maxn <= room && !getenv("KQ_NO_SMALL_MERGE")) {
             uint64_t cap = 1024;
             while (cap < 4 * total) cap <<= 1;
-            kq_dev_free(ctx, h->table);
-            h->table = nullptr;
-            if ((st = table_alloc(ctx, h, cap)) != KQ_OK) return cleanup(st);
-            cudaMemsetAsync(h->d_counters, 0, 8, ctx->stream);
+            if (cap > h->capacity) {
+                uint64_t* old = h->table; const uint64_t old_cap = h->capacity;
+                h->table = nullptr;
+                const int st1 = table_alloc(ctx, h, cap);              // the new table first: on failure the old one is still there
+                if (st1 != KQ_OK) { h->table = old; h->capacity = old_cap; return st1; }
+                kq_dev_free(ctx, old);
+            } else cudaMemsetAsync(h->table, 0, (size_t)(h->capacity + 1) * stride * 8, ctx->stream);
             AggArgs A;
             memset(&A, 0, sizeof A);
             fill_common_args(h, A);
-            for (int s2 = 0; s2 < nr; s2++) {
-                if (cnt[s2] == 0) continue;
-                k_merge_records<<<small_grid(ctx, cnt[s2]), 256, 0, ctx->stream>>>(A, all + (uint64_t)s2 * blockw + 8, cnt[s2]);
-                if ((st = launch_check(ctx, "k_merge_records")) != KQ_OK) return cleanup(st);
-            }
-            return cleanup(refresh_group_count(ctx, h));
+            k_merge_small<<<1, 1024, 0, ctx->stream>>>(A, all, blockw, nr, room);
+            KQ_RET(launch_check(ctx, "k_merge_small"));
+            h->ngroups_host = (int64_t)total; h->groups_exact = false;      // an upper bound; finalize reads the exact count
+            return KQ_OK;
         }
-        cleanup(KQ_OK);           // some rank holds more: the general path below
+        // some rank holds more: the general path below (every rank takes it: the decision was made on the same data)
     }
-
-    // 1. how many partial groups does every rank hold?
-    unsigned long long* d_cnt = nullptr;
-    KQ_RET(kq_dev_alloc(ctx, (size_t)nr * 8, (void**)&d_cnt));
-    cudaMemcpyAsync(d_cnt + me, &G, 8, cudaMemcpyHostToDevice, ctx->stream);
-    ncclResult_t r = N->AllGather(d_cnt + me, d_cnt, 1, ncclUint64, comm, ctx->stream);
+    // ---- general path: larger unions ---------------------------------------------------------------------------------------
+    // 1. every rank's group count is known from the heads above; everything this path needs is allocated NOW, and the
+    //    ranks agree on whether all of them succeeded before the first data collective (one word per rank, all-gathered):
+    //    a rank that cannot allocate must not leave its peers waiting in ncclAllGather.
     uint64_t cnt[64];
-    int st = r == ncclSuccess ? (nr <= 64 ? kq_read_u64(ctx, d_cnt, nr, cnt) : kq_fail(ctx, KQ_ERR_UNSUPPORTED, "more than 64 ranks")) : kq_nccl_fail(ctx, r, "ncclAllGather");
-    kq_dev_free(ctx, d_cnt);
-    KQ_RET(st);
+    {
+        uint64_t heads[128];
+        unsigned long long* d_heads = reinterpret_cast<unsigned long long*>(h->merge_all + h->merge_words * nr);
+        KQ_RET(kq_read_u64(ctx, d_heads, 2 * nr > 64 ? 64 : 2 * nr, heads));
+        if (2 * nr > 64) KQ_RET(kq_read_u64(ctx, d_heads + 64, 2 * nr - 64, heads + 64));
+        for (int i = 0; i < nr; i++) cnt[i] = heads[2 * i];
+    }
+    const uint64_t G = cnt[me];
     uint64_t maxn = 0;
     for (int i = 0; i < nr; i++) maxn = std::max(maxn, cnt[i]);
-    if (maxn == 0) return KQ_OK;
     const uint64_t T = maxn * (uint64_t)nr;
-
-    // 2. all-gather the partial records themselves (padded to the largest rank; a zero header is skipped)
-    uint64_t *mine = nullptr, *all = nullptr;
+    const bool dense_path = T <= (1ULL << 20);
+    uint64_t *mine = nullptr, *all = nullptr, *dict = nullptr, *dense = nullptr;
     unsigned long long* d_cur = nullptr;
-    KQ_RET(kq_dev_alloc(ctx, (size_t)maxn * stride * 8, (void**)&mine));
-    if ((st = kq_dev_alloc(ctx, (size_t)T * stride * 8, (void**)&all)) != KQ_OK) { kq_dev_free(ctx, mine); return st; }
-    if ((st = kq_dev_alloc(ctx, 16, (void**)&d_cur)) != KQ_OK) { kq_dev_free(ctx, mine); kq_dev_free(ctx, all); return st; }
-    auto cleanup = [&](int s) { kq_dev_free(ctx, mine); kq_dev_free(ctx, all); kq_dev_free(ctx, d_cur); return s; };
-    cudaMemsetAsync(mine, 0, (size_t)maxn * stride * 8, ctx->stream);
-    cudaMemsetAsync(d_cur, 0, 16, ctx->stream);      // [0] cursor, [1] base = 0
-    k_collect_records<<<small_grid(ctx, h->capacity), 256, 0, ctx->stream>>>(h->table, h->capacity, stride, nkeys, mine, d_cur, 1, d_cur + 1);
-    if ((st = launch_check(ctx, "k_collect_records")) != KQ_OK) return cleanup(st);
-    if ((r = N->AllGather(mine, all, (size_t)maxn * stride, ncclUint64, comm, ctx->stream)) != ncclSuccess) return cleanup(kq_nccl_fail(ctx, r, "ncclAllGather"));
-
-    // make room for the union of all ranks' keys
-    uint64_t need = h->capacity;
-    while (need / 2 < T + G) need <<= 1;
-    if (need != h->capacity && (st = table_grow(ctx, h, need)) != KQ_OK) return cleanup(st);
-    AggArgs A;
-    memset(&A, 0, sizeof A);
-    fill_common_args(h, A);
-
-    if (T > (1ULL << 20)) {
-        // too many groups for dense arrays to pay off: merge the other ranks' gathered partials locally
-        for (int s = 0; s < nr && st == KQ_OK; s++) {
-            if (s == me || cnt[s] == 0) continue;
-            k_merge_records<<<small_grid(ctx, cnt[s]), 256, 0, ctx->stream>>>(A, all + (uint64_t)s * maxn * stride, cnt[s]);
-            st = launch_check(ctx, "k_merge_records");
-        }
-        if (st == KQ_OK) st = refresh_group_count(ctx, h);
-        return cleanup(st);
-    }
-
-    // 3. union dictionary: key -> first position in the gathered buffer (same on every rank)
+    auto cleanup = [&](int s) { kq_dev_free(ctx, mine); kq_dev_free(ctx, all); kq_dev_free(ctx, d_cur); kq_dev_free(ctx, dict); kq_dev_free(ctx, dense); return s; };
     AggArgs D;
     memset(&D, 0, sizeof D);
     uint64_t dcap = 1024;
     while (dcap < 2 * T) dcap <<= 1;
     D.nkeys = nkeys; D.stride = (1 + nkeys + 1 + 3) / 4 * 4; D.cap_mask = dcap - 1;
     D.rec_init[1 + nkeys] = ~0ULL;
-    uint64_t *dict = nullptr, *dense = nullptr;
-    if ((st = kq_dev_alloc(ctx, (size_t)dcap * D.stride * 8 + 64, (void**)&dict)) != KQ_OK) return cleanup(st);
-    if ((st = kq_dev_alloc(ctx, (size_t)T * stride * 8, (void**)&dense)) != KQ_OK) { kq_dev_free(ctx, dict); return cleanup(st); }
-    auto cleanup2 = [&](int s) { kq_dev_free(ctx, dict); kq_dev_free(ctx, dense); return cleanup(s); };
-    cudaMemsetAsync(dict, 0, (size_t)dcap * D.stride * 8 + 64, ctx->stream);
-    D.table = dict; D.ngroups = (unsigned long long*)(dict + dcap * D.stride);
+    int st = kq_dev_alloc(ctx, (size_t)maxn * stride * 8, (void**)&mine);
+    if (st == KQ_OK) st = kq_dev_alloc(ctx, (size_t)T * stride * 8, (void**)&all);
+    if (st == KQ_OK) st = kq_dev_alloc(ctx, 16, (void**)&d_cur);
+    if (st == KQ_OK && dense_path) st = kq_dev_alloc(ctx, (size_t)(dcap + 1) * D.stride * 8 + 64, (void**)&dict);
+    if (st == KQ_OK && dense_path) st = kq_dev_alloc(ctx, (size_t)T * stride * 8, (void**)&dense);
+    uint64_t* newtab = nullptr;          // the merged table: room for the union of all ranks' keys
+    uint64_t need = 1024;
+    while (need / 2 < T) need <<= 1;
+    if (st == KQ_OK && !dense_path) st = kq_dev_alloc(ctx, (size_t)(need + 1) * stride * 8, (void**)&newtab);
+    if (st == KQ_OK && dense_path) {
+        // dense path: the reduced values are written back into this rank's table, which must hold the union of all ranks' keys
+        uint64_t want_cap = h->capacity;
+        while (want_cap / 2 < T + G) want_cap <<= 1;
+        if (want_cap != h->capacity) st = table_grow(ctx, h, want_cap);
+    }
+    {
+        const unsigned long long mystatus = st == KQ_OK ? 0ULL : 1ULL;
+        unsigned long long* d_st = reinterpret_cast<unsigned long long*>(h->merge_mine);
+        unsigned long long* d_all = reinterpret_cast<unsigned long long*>(h->merge_all);
+        cudaMemcpyAsync(d_st, &mystatus, 8, cudaMemcpyHostToDevice, ctx->stream);
+        ncclResult_t rs = N->AllGather(d_st, d_all, 1, ncclUint64, comm, ctx->stream);
+        uint64_t sts[64];
+        int st2 = rs == ncclSuccess ? kq_read_u64(ctx, d_all, nr, sts) : kq_nccl_fail(ctx, rs, "ncclAllGather");
+        bool peer_failed = false;
+        for (int i = 0; st2 == KQ_OK && i < nr; i++) peer_failed |= sts[i] != 0;
+        if (st != KQ_OK || st2 != KQ_OK || peer_failed) {
+            kq_dev_free(ctx, newtab);
+            if (st != KQ_OK) return cleanup(st);
+            if (st2 != KQ_OK) return cleanup(st2);
+            return cleanup(kq_fail(ctx, KQ_ERR_NCCL, "merge abandoned: another rank could not allocate its merge buffers"));
+        }
+    }
+
+    // 2. all-gather the partial records themselves (padded to the largest rank; a zero header is skipped)
+    ncclResult_t r;
+    cudaMemsetAsync(mine, 0, (size_t)maxn * stride * 8, ctx->stream);
+    cudaMemsetAsync(d_cur, 0, 16, ctx->stream);      // [0] cursor, [1] base = 0
+    k_collect_records<<<small_grid(ctx, h->capacity), 256, 0, ctx->stream>>>(h->table, h->capacity, stride, nkeys, mine, d_cur, 1, d_cur + 1);
+    if ((st = launch_check(ctx, "k_collect_records")) != KQ_OK) { kq_dev_free(ctx, newtab); return cleanup(st); }
+    if ((r = N->AllGather(mine, all, (size_t)maxn * stride, ncclUint64, comm, ctx->stream)) != ncclSuccess) { kq_dev_free(ctx, newtab); return cleanup(kq_nccl_fail(ctx, r, "ncclAllGather")); }
+
+    if (!dense_path) {
+        // too many groups for dense arrays to pay off: every rank rebuilds its table from ALL gathered partials, its own
+        // included, in rank order (a key occurs once per rank: the order of every Float64 addition is the same everywhere)
+        cudaMemsetAsync(newtab, 0, (size_t)(need + 1) * stride * 8, ctx->stream);
+        cudaMemsetAsync(h->d_counters, 0, 8, ctx->stream);
+        kq_dev_free(ctx, h->table);
+        h->table = newtab; h->capacity = need;
+        AggArgs A;
+        memset(&A, 0, sizeof A);
+        fill_common_args(h, A);
+        for (int s2 = 0; s2 < nr && st == KQ_OK; s2++) {
+            if (cnt[s2] == 0) continue;
+            k_merge_records<<<small_grid(ctx, cnt[s2]), 256, 0, ctx->stream>>>(A, all + (uint64_t)s2 * maxn * stride, cnt[s2]);
+            st = launch_check(ctx, "k_merge_records");
+        }
+        if (st == KQ_OK) st = refresh_group_count(ctx, h);
+        return cleanup(st);
+    }
+
+    AggArgs A;
+    memset(&A, 0, sizeof A);
+    fill_common_args(h, A);
+
+    // 3. union dictionary: key -> first position in the gathered buffer (same on every rank)
+    cudaMemsetAsync(dict, 0, (size_t)(dcap + 1) * D.stride * 8 + 64, ctx->stream);
+    D.table = dict; D.ngroups = (unsigned long long*)(dict + (dcap + 1) * D.stride);
     k_dict_build<<<small_grid(ctx, T), 256, 0, ctx->stream>>>(D, all, T, stride);
-    if ((st = launch_check(ctx, "k_dict_build")) != KQ_OK) return cleanup2(st);
+    st = launch_check(ctx, "k_dict_build");
     // 4. dense arrays [word][position]: identities everywhere, own partials scattered in, one all-reduce per word
     k_dense_init<<<small_grid(ctx, T * stride), 256, 0, ctx->stream>>>(dense, T, stride, A);
-    if ((st = launch_check(ctx, "k_dense_init")) != KQ_OK) return cleanup2(st);
+    if (st == KQ_OK) st = launch_check(ctx, "k_dense_init");
     k_dense_scatter<<<small_grid(ctx, maxn), 256, 0, ctx->stream>>>(D, all, (uint64_t)me * maxn, maxn, stride, dense, T);
-    if ((st = launch_check(ctx, "k_dense_scatter")) != KQ_OK) return cleanup2(st);
+    if (st == KQ_OK) st = launch_check(ctx, "k_dense_scatter");
     int cls[MAX_REC_WORDS];
     word_classes(h, cls);
-    if ((r = N->GroupStart()) != ncclSuccess) return cleanup2(kq_nccl_fail(ctx, r, "ncclGroupStart"));
+    if ((r = N->GroupStart()) != ncclSuccess) return cleanup(kq_nccl_fail(ctx, r, "ncclGroupStart"));
     for (int w = 1 + nkeys; w < stride && r == ncclSuccess; w++) {
         uint64_t* p = dense + (uint64_t)w * T;
         switch (cls[w]) {
@@ -1036,12 +1310,13 @@ int kq_hashagg_merge_allreduce(kq_ctx* ctx, kq_hashagg* h) {
         }
     }
     ncclResult_t r2 = N->GroupEnd();
-    if (r != ncclSuccess || r2 != ncclSuccess) return cleanup2(kq_nccl_fail(ctx, r != ncclSuccess ? r : r2, "ncclAllReduce"));
+    if (r != ncclSuccess || r2 != ncclSuccess) return cleanup(kq_nccl_fail(ctx, r != ncclSuccess ? r : r2, "ncclAllReduce"));
+    if (st != KQ_OK) return cleanup(st);
     // 5. write the reduced values into this rank's table
     k_dense_writeback<<<small_grid(ctx, T), 256, 0, ctx->stream>>>(A, D, all, T, dense);
-    if ((st = launch_check(ctx, "k_dense_writeback")) != KQ_OK) return cleanup2(st);
+    if ((st = launch_check(ctx, "k_dense_writeback")) != KQ_OK) return cleanup(st);
     st = refresh_group_count(ctx, h);
-    return cleanup2(st);
+    return cleanup(st);
 }
 
 int kq_hashagg_repartition_alltoall(kq_ctx* ctx, kq_hashagg* h) {
@@ -1101,8 +1376,8 @@ int kq_hashagg_repartition_alltoall(kq_ctx* ctx, kq_hashagg* h) {
     // 4. this rank's final table: its own bucket merged with the buckets it received
     uint64_t cap = 1ULL << 16;
     while (cap / 2 < cnt[me] + R) cap <<= 1;
-    if ((st = kq_dev_alloc(ctx, (size_t)cap * stride * 8, (void**)&newtab)) != KQ_OK) return cleanup(st);
-    cudaMemsetAsync(newtab, 0, (size_t)cap * stride * 8, ctx->stream);
+    if ((st = kq_dev_alloc(ctx, (size_t)(cap + 1) * stride * 8, (void**)&newtab)) != KQ_OK) return cleanup(st);
+    cudaMemsetAsync(newtab, 0, (size_t)(cap + 1) * stride * 8, ctx->stream);
     cudaMemsetAsync(h->d_counters, 0, 8, ctx->stream);
     kq_dev_free(ctx, h->table);
     h->table = newtab; h->capacity = cap;

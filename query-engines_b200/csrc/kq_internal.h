@@ -131,6 +131,7 @@ KQ_HIDDEN int kq_type_width(int type);   // bytes per row for fixed-width types 
 KQ_HIDDEN int kq_batch_resolve_rows(kq_ctx* ctx, kq_batch* b, int64_t* n);
 KQ_HIDDEN int kq_col_resolve_rows(kq_ctx* ctx, kq_col* c, int64_t* n);
 KQ_HIDDEN int kq_check_device_errors(kq_ctx* ctx);
+KQ_HIDDEN int kq_device_error_status(kq_ctx* ctx, uint32_t bits);   // kq_status for error bits raised by a kernel (0 -> KQ_OK)
 KQ_HIDDEN kq_lazy_count* kq_lazy_new(kq_ctx* ctx);
 KQ_HIDDEN void kq_lazy_release(kq_ctx* ctx, kq_lazy_count* l);
 KQ_HIDDEN int kq_read_u64(kq_ctx* ctx, const void* d_ptr, int count, uint64_t* out);  // sync small D2H

@@ -14,9 +14,10 @@
 //     front end; rows whose key does not fit go straight to the global table with atomics (config 4).
 //
 // Accumulator semantics (oracle: MaxAccumulator etc.): nulls are skipped; a group whose inputs were
-// all null yields null, except COUNT; MIN/MAX use a total order in which canonical NaN sorts above
-// +inf and -0.0 below +0.0 — where the reference is order-dependent (rule R9/E8) this is the one
-// deterministic choice; Float64 sums are reassociated (1e-9 relative tolerance, rule E6).
+// all null yields null, except COUNT; MIN/MAX compare like the reference's `value > this.value`
+// (Main.kt:552): a NaN never replaces a held value, and a group whose non-null values were all NaN
+// yields NaN (k_finalize); among equal-comparing zeros -0.0 orders below +0.0 (the reference keeps
+// the first seen, an order dependence); Float64 sums are reassociated (1e-9 relative, rule E6).
 #pragma once
 
 #include "kq_rt.cuh"
@@ -146,14 +147,15 @@ __device__ __forceinline__ void fe_accumulate(const FrontEnd& fe, int gid, int l
                 }
                 if constexpr ((FL & (F_MIN | F_MAX)) != 0) {
                     constexpr bool is_int = (FL & F_INT) != 0;
-                    const uint64_t m = order_map(is_int ? v : canon_nan(v), is_int);
+                    const uint64_t m = order_map(v, is_int);
+                    const bool cmp = is_int || as_f64(v) == as_f64(v);          // a NaN never replaces a held value (Main.kt:552)
                     if constexpr ((FL & F_MIN) != 0) {
                         uint64_t* p = fe.mm + gid * Q::NMM + Q::FE_MIN[I];
-                        if (m < *reinterpret_cast<volatile uint64_t*>(p)) atomicMin(reinterpret_cast<unsigned long long*>(p), (unsigned long long)m);
+                        if (cmp && m < *reinterpret_cast<volatile uint64_t*>(p)) atomicMin(reinterpret_cast<unsigned long long*>(p), (unsigned long long)m);
                     }
                     if constexpr ((FL & F_MAX) != 0) {
                         uint64_t* p = fe.mm + gid * Q::NMM + Q::FE_MAX[I];
-                        if (m > *reinterpret_cast<volatile uint64_t*>(p)) atomicMax(reinterpret_cast<unsigned long long*>(p), (unsigned long long)m);
+                        if (cmp && m > *reinterpret_cast<volatile uint64_t*>(p)) atomicMax(reinterpret_cast<unsigned long long*>(p), (unsigned long long)m);
                     }
                 }
             }
@@ -255,11 +257,11 @@ __device__ __forceinline__ void fe_accumulate_pair(uint32_t a_cnt, uint32_t a_su
                 const uint64_t v = sink.in[i][r0 + k];
                 const uint32_t hi = (uint32_t)(v >> 32);
                 const uint32_t mh = is_int ? hi ^ 0x80000000u : hi ^ ((uint32_t)((int32_t)hi >> 31) | 0x80000000u);     // high word of order_map(v)
-                bool exact = !is_int && as_f64(v) != as_f64(v);                                                            // NaNs are canonicalised below
+                bool exact = false;
                 if (FL & F_MIN) exact |= mh <= mmb[Q::FE_MIN[i] < 0 ? 0 : Q::FE_MIN[i]];
                 if (FL & F_MAX) exact |= mh >= mmb[Q::FE_MAX[i] < 0 ? 0 : Q::FE_MAX[i]];
-                if (exact) {
-                    const uint64_t m = order_map(is_int ? v : canon_nan(v), is_int);
+                if (exact && (is_int || as_f64(v) == as_f64(v))) {                                                        // a NaN never replaces a held value (Main.kt:552)
+                    const uint64_t m = order_map(v, is_int);
                     if (FL & F_MIN) smem_min_u64(a_mm + (gi[i][k] * Q::NMM + Q::FE_MIN[i]) * 8u, m);
                     if (FL & F_MAX) smem_max_u64(a_mm + (gi[i][k] * Q::NMM + Q::FE_MAX[i]) * 8u, m);
                 }
@@ -303,100 +305,6 @@ __device__ __forceinline__ void fe_merge_input(const FrontEnd& fe, uint64_t* rec
     }
 }
 
-// ---- high-cardinality path: every row goes to the global table ------------------------------------------------------
-// A thread's R rows are looked up TOGETHER: each probing round first issues the header+key loads of all
-// rows that are still unresolved (R independent L2/HBM round trips in flight per thread instead of one),
-// then examines them; accumulation is a second batch of fire-and-forget reductions. Latency-bound random
-// access is what limits this path, so memory-level parallelism per thread is what buys throughput.
-template <int I>
-__device__ __forceinline__ void global_accumulate_batched(uint64_t* const (&rec)[R], const ulonglong2 (&mmv)[R], const AggSink& sink, uint32_t rows) {
-    if constexpr (I < Q::NIN) {
-        constexpr int FL = Q::IN_FLAGS[I];
-#pragma unroll
-        for (int r = 0; r < R; r++) {
-            if (!((rows >> r) & 1u) || !((sink.inok[I] >> r) & 1u)) continue;
-            uint64_t* p = rec[r];
-            atomicAdd(reinterpret_cast<unsigned long long*>(p + Q::REC_NN[I]), 1ULL);
-            if constexpr ((FL & (F_SUM | F_MIN | F_MAX)) != 0) {
-                const uint64_t v = sink.in[I][r];
-                if constexpr ((FL & F_SUM) != 0) {
-                    if constexpr ((FL & F_INT) != 0) atomicAdd(reinterpret_cast<unsigned long long*>(p + Q::REC_SUM[I]), (unsigned long long)v);
-                    else atomicAdd(reinterpret_cast<double*>(p + Q::REC_SUM[I]), as_f64(v));
-                }
-                if constexpr ((FL & (F_MIN | F_MAX)) != 0) {
-                    constexpr bool is_int = (FL & F_INT) != 0;
-                    const uint64_t m = order_map(is_int ? v : canon_nan(v), is_int);
-                    // pre-check against a (possibly stale) copy: MIN only falls and MAX only rises, so a stale value errs on the safe side
-                    if constexpr ((FL & F_MIN) != 0) {
-                        // the paired copy was loaded alongside the header, not after it: it may predate the record's
-                        // initialisation (all-zero words). 0 is never a safe stale MIN, so it only means "unknown"
-                        const uint64_t cur = (Q::NIN == 1 && Q::MM_PAIRED) ? (mmv[r].x ? mmv[r].x : ~0ULL) : __ldcg(p + Q::MM_WORD[Q::FE_MIN[I]]);
-                        if (m < cur) atomicMin(reinterpret_cast<unsigned long long*>(p + Q::MM_WORD[Q::FE_MIN[I]]), (unsigned long long)m);
-                    }
-                    if constexpr ((FL & F_MAX) != 0) {
-                        const uint64_t cur = (Q::NIN == 1 && Q::MM_PAIRED) ? mmv[r].y : __ldcg(p + Q::MM_WORD[Q::FE_MAX[I]]);
-                        if (m > cur) atomicMax(reinterpret_cast<unsigned long long*>(p + Q::MM_WORD[Q::FE_MAX[I]]), (unsigned long long)m);
-                    }
-                }
-            }
-        }
-        global_accumulate_batched<I + 1>(rec, mmv, sink, rows);
-    }
-}
-
-__device__ __forceinline__ void global_path_batched(const AggArgs& A, const AggSink& sink, const uint32_t (&nm)[R], uint32_t rows, uint32_t& new_groups) {
-    uint64_t* rec[R];                 // record under examination, then the row's record
-    uint64_t* const tab_end = A.table + (A.cap_mask + 1) * (uint64_t)A.stride;
-#pragma unroll
-    for (int r = 0; r < R; r++) {
-        uint64_t kw[MAX_KEYS];
-#pragma unroll
-        for (int k2 = 0; k2 < MAX_KEYS; k2++) kw[k2] = k2 < Q::NKEYS ? sink.key[k2][r] : 0;
-        rec[r] = A.table + table_home(hash_key(kw, nm[r], Q::NKEYS), A.cap_mask) * (uint64_t)A.stride;
-    }
-    constexpr bool PAIRED = Q::NIN == 1 && Q::MM_PAIRED;
-    ulonglong2 mmv[R];
-    uint32_t pending = rows;
-    while (pending) {
-        ulonglong2 hk[R];
-#pragma unroll
-        for (int r = 0; r < R; r++)
-            if ((pending >> r) & 1u) {
-                hk[r] = __ldcg(reinterpret_cast<const ulonglong2*>(rec[r]));                                   // {header, key 0}
-                if constexpr (PAIRED) mmv[r] = __ldcg(reinterpret_cast<const ulonglong2*>(rec[r] + Q::MM_WORD[0]));   // {min, max}: same round trip
-            }
-#pragma unroll
-        for (int r = 0; r < R; r++) {
-            if (!((pending >> r) & 1u)) continue;
-            uint64_t* p = rec[r];
-            const uint64_t hdr = hk[r].x, full_hdr = HDR_FULL | ((uint64_t)nm[r] << 32);
-            const uint32_t st = (uint32_t)hdr;
-            if (st == HDR_EMPTY) {
-                const unsigned long long old = atomicCAS(reinterpret_cast<unsigned long long*>(p), 0ULL, HDR_BUSY | ((uint64_t)nm[r] << 32));
-                if (old == 0ULL) {
-                    for (int w = 1 + Q::NKEYS; w < A.stride; w++) p[w] = A.rec_init[w];
-#pragma unroll
-                    for (int k2 = 0; k2 < Q::NKEYS; k2++) p[1 + k2] = sink.key[k2][r];
-                    __threadfence();
-                    *reinterpret_cast<volatile uint64_t*>(p) = full_hdr;
-                    new_groups++;
-                    if constexpr (PAIRED) mmv[r] = make_ulonglong2(~0ULL, 0ULL);      // identities of a fresh record
-                    pending &= ~(1u << r);
-                }
-                // lost the race: look at the same slot again next round
-            } else if (st != HDR_BUSY) {        // BUSY: being published, look again next round
-                bool eq = hdr == full_hdr;
-                if constexpr (Q::NKEYS >= 1) eq &= hk[r].y == sink.key[0][r];
-#pragma unroll
-                for (int k2 = 1; k2 < Q::NKEYS; k2++) eq &= __ldcg(p + 1 + k2) == sink.key[k2][r];
-                if (eq) pending &= ~(1u << r);
-                else { p += A.stride; rec[r] = p == tab_end ? A.table : p; }
-            }
-        }
-    }
-    global_accumulate_batched<0>(rec, mmv, sink, rows);
-}
-
 // ---- partitioned path (high cardinality) ------------------------------------------------------------------------------
 // With millions of groups every row of the plain path is a random read-modify-write in HBM/L2 (latency- and
 // atomic-bound, a few G rows/s). Instead: PASS 1 (this kernel, KQ_AGG_MODE 1) evaluates the query's expressions
@@ -413,9 +321,6 @@ __device__ __forceinline__ void global_path_batched(const AggArgs& A, const AggS
 #endif
 #ifndef KQ_PART_L2_HINTS
 #define KQ_PART_L2_HINTS 1           // measured: pass 1 2.61 -> 2.44 ms per 100 M rows (fewer partially filled bucket lines evicted)
-#endif
-#ifndef KQ_GLOBAL_BATCHED
-#define KQ_GLOBAL_BATCHED 0          // 1: global_path_batched (R lookups in flight per thread) — EXPERIMENTAL, misattributes a few rows per million at 10 M groups (tools/part_debug.py); off until understood
 #endif
 constexpr bool TUPLE_META = Q::KEYS_NULLABLE || Q::NCNT > 1;
 __host__ __device__ constexpr int tuple_in_word(int i) {
@@ -513,14 +418,15 @@ __device__ __forceinline__ void part_accumulate_input(const PartTable& T, uint32
                 }
                 if constexpr ((FL & (F_MIN | F_MAX)) != 0) {
                     constexpr bool is_int = (FL & F_INT) != 0;
-                    const uint64_t m = order_map(is_int ? v : canon_nan(v), is_int);
+                    const uint64_t m = order_map(v, is_int);
+                    const bool cmp = is_int || as_f64(v) == as_f64(v);          // a NaN never replaces a held value (Main.kt:552)
                     if constexpr ((FL & F_MIN) != 0) {
                         uint64_t* p = T.mm + (size_t)Q::FE_MIN[I] * T.AC + slot;
-                        if (m < *reinterpret_cast<volatile uint64_t*>(p)) atomicMin(reinterpret_cast<unsigned long long*>(p), (unsigned long long)m);
+                        if (cmp && m < *reinterpret_cast<volatile uint64_t*>(p)) atomicMin(reinterpret_cast<unsigned long long*>(p), (unsigned long long)m);
                     }
                     if constexpr ((FL & F_MAX) != 0) {
                         uint64_t* p = T.mm + (size_t)Q::FE_MAX[I] * T.AC + slot;
-                        if (m > *reinterpret_cast<volatile uint64_t*>(p)) atomicMax(reinterpret_cast<unsigned long long*>(p), (unsigned long long)m);
+                        if (cmp && m > *reinterpret_cast<volatile uint64_t*>(p)) atomicMax(reinterpret_cast<unsigned long long*>(p), (unsigned long long)m);
                     }
                 }
             }
@@ -899,12 +805,11 @@ extern "C" __global__ void __launch_bounds__(THREADS, 1) kq_hash_aggregate(const
             }
             // general path for the rest: directory probing with insertion, else the global table
             int rows = __popc(sink.sel);
-            if (KQ_AGG_MODE == 1) {
-                if (slow) slow = partition_scatter(A, smem_u32(part_cursor), sink, nm, slow);
-                if (slow) global_path_batched(A, sink, nm, slow, new_groups);          // bucket full (skewed keys)
-            }
+            // pass 1 of the partitioned path: rows whose bucket is full (skewed keys) stay in `slow` and take the
+            // scalar global path below (table_find_or_insert + global_accumulate_all), like any other overflow row
+            if (KQ_AGG_MODE == 1 && slow) { slow = partition_scatter(A, smem_u32(part_cursor), sink, nm, slow); }
 #if KQ_AGG_MODE == 2
-            else if (true) {
+            if (true) {
 #pragma unroll
                 for (int r = 0; r < R; r++) {           // all 32 lanes: the table probe runs in lockstep
                     uint64_t w[TW];
@@ -924,10 +829,8 @@ extern "C" __global__ void __launch_bounds__(THREADS, 1) kq_hash_aggregate(const
                     __syncwarp();
                 }
             }
-#endif
-            else if (bypass && KQ_GLOBAL_BATCHED) {
-                if (slow) global_path_batched(A, sink, nm, slow, new_groups);
-            } else if (slow) {
+#else
+            if (slow) {
 #pragma unroll
                 for (int r = 0; r < R; r++) {
                     if (!((slow >> r) & 1u)) continue;
@@ -946,6 +849,7 @@ extern "C" __global__ void __launch_bounds__(THREADS, 1) kq_hash_aggregate(const
                     }
                 }
             }
+#endif
             // one update of the global group count per warp and tile (a single counter bumped by every insert serialises in the L2)
             if (__any_sync(0xffffffffu, new_groups != 0)) {
                 const uint32_t tot = __reduce_add_sync(0xffffffffu, new_groups);

@@ -1,0 +1,702 @@
+// kq_k_agg_fe.cuh — HashAggregateExec (Main.kt:605-660) for LOW-cardinality GROUP BYs (BASELINE configs 3 and 5): the
+// drain loop's per-row work (key list, HashMap.getOrPut, Accumulator.accumulate; Main.kt:620-632) with every group of a
+// CTA held in shared memory. Specialised per query like kq_k_agg.cuh (generated `struct Q`, same AggSink contract).
+//
+// What bounds this kernel is the shared-memory data path (one 128-byte wavefront per cycle and SM), not instruction
+// issue and not HBM: at the copy roofline a 14-byte row leaves ~90 bytes of shared-memory traffic per row. So the design
+// counts wavefronts:
+//   * KEY -> GROUP: a CTA directory with PERFECT placement. slot = (lo * s1 + hi * s2 ...) >> shift; whenever an insert
+//     collides with an occupied home slot the directory is rebuilt under new multipliers until every key sits in its
+//     home slot (a handful of attempts at <= 6 % load). A probe is therefore ONE 4-byte state load + one 8-byte load per
+//     key word, never a second slot; readers validate with a sequence number that rebuilds bump.
+//   * ACCUMULATE: lane-private SUM / COUNT slots (one copy per lane per warp: plain read-modify-write, no atomics — the
+//     shared-memory atomics of sm_100a are CAS loops for everything but 32-bit integers — and no bank conflicts by
+//     construction).
+//   * MIN / MAX: kept once per CTA; a row touches them only when its value beats a bound that holds for every group
+//     with a value (register compares per row), or when it is the first value its lane sees in that group.
+// Inserts, rebuilds, first values and bound refreshes are serialised by a CTA lock; they happen a few dozen times per
+// CTA, the per-row path takes no lock. Rows whose key does not fit the directory go to the global table of
+// kq_aggtable.cuh with atomics; the CTA's groups are merged into it once, at exit.
+//
+// Accumulator semantics (oracle: MaxAccumulator, Main.kt:538-562, and the E5-E7 extensions): nulls are skipped; MIN/MAX
+// use IEEE comparisons like the reference's `value > this.value`, so a NaN never replaces a held value; a group whose
+// non-null values were all NaN yields NaN (the identity survives, see k_finalize); Float64 sums are reassociated.
+#pragma once
+
+#include "kq_rt.cuh"
+#include "kq_aggtable.cuh"
+
+namespace kq {
+
+constexpr int WARPS = KQ_WARPS;              // consumer warps
+constexpr int PRODUCER_WARP = 0;             // service warp first: the warp arbiter favours high warp ids
+constexpr int THREADS = WARPS * 32 + 32;
+constexpr int TILE = WARPS * WARP_ROWS;
+constexpr int S = KQ_STAGES;
+constexpr int FG = KQ_FE_GROUPS;             // directory capacity in groups (<= 254)
+constexpr int DIR = KQ_DIR_SLOTS;            // directory slots (power of two, >= 8 * FG)
+__host__ __device__ constexpr int ilog2c(int x) { return x <= 1 ? 0 : 1 + ilog2c(x >> 1); }
+constexpr int DIR_SHIFT = 32 - ilog2c(DIR);
+constexpr int NKW = Q::NKEYS > 0 ? Q::NKEYS : 1;          // key words per group (a global aggregate has one constant word)
+constexpr int NMM1 = Q::NMM > 0 ? Q::NMM : 1;
+constexpr int GS = Q::NSUM * 256 + Q::NCNT * 128;         // lane-private bytes per group and warp: [NSUM][32] u64, [NCNT][32] u32
+constexpr int REBUILD_ATTEMPTS = 256;
+
+// What the generated code fills per tile: selection, key words and aggregate inputs of the R owned rows.
+struct AggSink {
+    uint32_t sel;
+    uint64_t key[NKW][R];
+    uint32_t keyok[NKW];
+    uint64_t in[Q::NIN > 0 ? Q::NIN : 1][R];
+    uint32_t inok[Q::NIN > 0 ? Q::NIN : 1];
+    template <int K>
+    __device__ __forceinline__ void set_key(const uint64_t (&v)[R], uint32_t ok) {
+#pragma unroll
+        for (int r = 0; r < R; r++) key[K][r] = v[r];
+        keyok[K] = ok;
+    }
+    template <int I>
+    __device__ __forceinline__ void set_in(const uint64_t (&v)[R], uint32_t ok) {
+#pragma unroll
+        for (int r = 0; r < R; r++) in[I][r] = v[r];
+        inok[I] = ok;
+    }
+};
+
+// Control block of the CTA directory (one 16-byte load per tile and warp).
+struct __align__(16) DirCtl {
+    uint32_t gen;            // sequence number: odd while a rebuild is in progress
+    uint32_t s1, s2;         // multipliers of the placement hash
+    uint32_t count;          // groups in the directory
+};
+
+struct Fe {                  // shared-memory addresses (32-bit) and pointers of the CTA front end
+    uint32_t a_ctl, a_meta, a_keys;     // DirCtl; [DIR] u32 state; [DIR][NKW] u64 key words
+    uint32_t a_mm;                      // [FG + 1][NMM] u64 order-mapped extremes (CTA-shared; row FG is a trash row)
+    uint32_t a_lane8, a_lane4;          // this warp's lane-private block + lane * 8 / + NSUM*256 + lane * 4
+    DirCtl* ctl;
+    uint32_t* meta;
+    uint64_t* keys;
+    uint64_t* gkeys;                    // [FG][NKW] dense list of the groups, in insertion order
+    uint32_t* gnm;                      // [FG] their key null masks
+    uint64_t* mm;
+    uint64_t* bound;                    // [NMM] bound on the extremes of all groups WITH a value, as the input's own bits
+    uint32_t* lock;
+    uint32_t* limit;                    // no more inserts at this many groups (FG, or fewer after a failed rebuild)
+};
+
+__device__ __forceinline__ uint32_t lds_u32(uint32_t a) { uint32_t v; asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(a)); return v; }
+__device__ __forceinline__ uint64_t lds_u64(uint32_t a) { uint64_t v; asm volatile("ld.shared.u64 %0, [%1];" : "=l"(v) : "r"(a)); return v; }
+__device__ __forceinline__ uint4 lds_u128(uint32_t a) { uint4 r; asm volatile("ld.shared.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w) : "r"(a)); return r; }
+
+// identities of the CTA-shared extremes, in order-mapped form (never produced by a non-NaN value)
+__device__ __forceinline__ constexpr uint64_t mm_identity(int m) { return ((Q::MM_ISMIN >> m) & 1u) ? ~0ULL : 0ULL; }
+// "no bound": every value takes the exact path
+__device__ __forceinline__ uint64_t bound_none(int m, bool is_int) {
+    const bool ismin = (Q::MM_ISMIN >> m) & 1u;
+    if (is_int) return ismin ? 0x7FFFFFFFFFFFFFFFULL : 0x8000000000000000ULL;       // = the identities: nothing is lost when they tie
+    return 0x7FF8000000000000ULL;                                                   // NaN: `!(v >= bound)` / `!(v <= bound)` hold for every v
+}
+__host__ __device__ constexpr bool mm_is_int(int m) {
+    for (int i = 0; i < Q::NIN; i++) if (Q::FE_MIN[i] == m || Q::FE_MAX[i] == m) return (Q::IN_FLAGS[i] & F_INT) != 0;
+    return false;
+}
+
+// Placement hash of a key under the multipliers (s1, s2): distinct keys are separated by SOME pair of multipliers.
+__device__ __forceinline__ uint32_t dir_slot(const uint64_t (&kw)[NKW], uint32_t nm, uint32_t s1, uint32_t s2) {
+    uint32_t h = Q::KEYS_NULLABLE ? nm * 0x9E3779B1u : 0u;
+#pragma unroll
+    for (int k = 0; k < NKW; k++) {
+        if (k > 0) h = h * 0x85EBCA6Bu + (h >> 15);
+        h += (uint32_t)kw[k] * s1 + (uint32_t)(kw[k] >> 32) * s2;
+    }
+    return h >> DIR_SHIFT;
+}
+
+// One lock-free probe of the home slot: group id, or -1. Valid only if ctl->gen did not move meanwhile (caller checks).
+__device__ __forceinline__ int dir_probe(const Fe& fe, const uint64_t (&kw)[NKW], uint32_t nm, uint32_t s1, uint32_t s2) {
+    const uint32_t slot = dir_slot(kw, nm, s1, s2);
+    const uint32_t m = lds_u32(fe.a_meta + slot * 4u);
+    bool hit = true;
+#pragma unroll
+    for (int k = 0; k < NKW; k++) hit &= lds_u64(fe.a_keys + slot * (8u * NKW) + 8u * k) == kw[k];
+    const uint32_t x = Q::KEYS_NULLABLE ? m ^ (nm << 8) : m;
+    const uint32_t g = x - 1u;                 // state: 0 = empty, else (gid + 1) | null mask << 8
+    return (hit && g < (uint32_t)FG) ? (int)g : -1;
+}
+
+__device__ __forceinline__ void fe_lock(const Fe& fe, int lane) {
+    if (lane == 0) { while (atomicCAS(fe.lock, 0u, 1u) != 0u) __nanosleep(64); }
+    __syncwarp();
+    __threadfence_block();
+}
+__device__ __forceinline__ void fe_unlock(const Fe& fe, int lane) {
+    __threadfence_block();
+    __syncwarp();
+    if (lane == 0) atomicExch(fe.lock, 0u);
+}
+
+// Place groups [0, n) under the multipliers (s1, s2). Whole warp, under the lock, gen odd. false on any collision.
+__device__ __forceinline__ bool dir_place_all(const Fe& fe, int n, uint32_t s1, uint32_t s2, int lane) {
+    for (int i = lane; i < DIR; i += 32) fe.meta[i] = 0u;
+    __syncwarp();
+    bool ok = true;
+    for (int g = lane; g < n; g += 32) {
+        uint64_t kw[NKW];
+#pragma unroll
+        for (int k = 0; k < NKW; k++) kw[k] = fe.gkeys[g * NKW + k];
+        const uint32_t nm = fe.gnm[g];
+        const uint32_t slot = dir_slot(kw, nm, s1, s2);
+        if (atomicCAS(fe.meta + slot, 0u, (uint32_t)(g + 1) | (nm << 8)) != 0u) ok = false;
+        else {
+#pragma unroll
+            for (int k = 0; k < NKW; k++) fe.keys[slot * NKW + k] = kw[k];
+        }
+    }
+    return __all_sync(0xffffffffu, ok);
+}
+
+// Group id of key (kw, nm), inserting it while there is room; -1: the directory cannot take it (the row goes to the
+// global table). Called by ALL lanes of a warp with the same key.
+__device__ __noinline__ int dir_find_or_insert(const Fe& fe, const uint64_t (&kw)[NKW], uint32_t nm, int lane) {
+    fe_lock(fe, lane);
+    volatile DirCtl* ctl = fe.ctl;
+    const int n = (int)ctl->count;
+    int found = -1;
+    for (int g = lane; g < n; g += 32) {
+        bool eq = *reinterpret_cast<volatile uint32_t*>(fe.gnm + g) == nm;
+#pragma unroll
+        for (int k = 0; k < NKW; k++) eq &= *reinterpret_cast<volatile uint64_t*>(fe.gkeys + g * NKW + k) == kw[k];
+        if (eq) found = g;
+    }
+    const uint32_t f = __ballot_sync(0xffffffffu, found >= 0);
+    int gid = f ? __shfl_sync(0xffffffffu, found, __ffs(f) - 1) : -1;
+    if (!f && n < (int)*reinterpret_cast<volatile uint32_t*>(fe.limit)) {
+        gid = n;
+        if (lane == 0) {
+#pragma unroll
+            for (int k = 0; k < NKW; k++) fe.gkeys[n * NKW + k] = kw[k];
+            fe.gnm[n] = nm;
+        }
+        __syncwarp();
+        uint32_t s1 = ctl->s1, s2 = ctl->s2;
+        const uint32_t slot = dir_slot(kw, nm, s1, s2);
+        if (*reinterpret_cast<volatile uint32_t*>(fe.meta + slot) == 0u) {
+            // the home slot is free: publish keys, then the state word (readers that miss meanwhile come here and find it)
+            if (lane == 0) {
+#pragma unroll
+                for (int k = 0; k < NKW; k++) fe.keys[slot * NKW + k] = kw[k];
+                __threadfence_block();
+                *reinterpret_cast<volatile uint32_t*>(fe.meta + slot) = (uint32_t)(n + 1) | (nm << 8);
+                ctl->count = (uint32_t)(n + 1);
+            }
+        } else {
+            // collision: new multipliers until every key of the directory sits in its home slot
+            if (lane == 0) ctl->gen = ctl->gen + 1u;          // odd: probes in flight are void
+            __threadfence_block();
+            __syncwarp();
+            bool placed = false;
+            uint32_t t1 = s1, t2 = s2;
+            for (int a = 0; a < REBUILD_ATTEMPTS && !placed; a++) {
+                t1 = (t1 * 0x2C1B3C6Du + 0x297A2D39u) | 1u;
+                t2 = ((t2 ^ (t1 >> 7)) * 0x9E3779B1u + 0x85EBCA6Bu) | 1u;
+                placed = dir_place_all(fe, n + 1, t1, t2, lane);
+                __syncwarp();
+            }
+            if (!placed) {
+                // two keys no multiplier separates (never seen; possible in principle): keep the old directory, which places
+                // its n keys, stop inserting, and send this key to the global table
+                dir_place_all(fe, n, s1, s2, lane);
+                t1 = s1; t2 = s2; gid = -1;
+                if (lane == 0) *reinterpret_cast<volatile uint32_t*>(fe.limit) = (uint32_t)n;
+            }
+            __threadfence_block();
+            __syncwarp();
+            if (lane == 0) { ctl->s1 = t1; ctl->s2 = t2; ctl->count = (uint32_t)(placed ? n + 1 : n); __threadfence_block(); ctl->gen = ctl->gen + 1u; }
+        }
+    }
+    fe_unlock(fe, lane);
+    return gid;
+}
+
+// Exact MIN/MAX update of the CTA-shared extreme (gid, slot m) with value bits v (not NaN for Float64).
+__device__ __noinline__ void mm_update(const Fe& fe, int gid, int m, uint64_t v, bool is_int) {
+    const uint64_t x = order_map(v, is_int);
+    unsigned long long* p = reinterpret_cast<unsigned long long*>(fe.mm + gid * NMM1 + m);
+    const bool ismin = (Q::MM_ISMIN >> m) & 1u;
+    const uint64_t cur = *reinterpret_cast<volatile unsigned long long*>(p);
+    if (cur == mm_identity(m)) {
+        // first value of this group CTA-wide: no bound computed so far covers the group. Reset the bound BEFORE the value
+        // becomes visible; both under the lock that bound refreshes take. The lock is per THREAD here and several lanes of a
+        // warp may want it at once: the critical section sits INSIDE the retry loop, so the lane that wins never waits at
+        // a reconvergence point for the lanes that lost (the SIMT spin-lock deadlock).
+        bool done = false;
+        while (!done) {
+            if (atomicCAS(fe.lock, 0u, 1u) == 0u) {
+                __threadfence_block();
+                *reinterpret_cast<volatile uint64_t*>(fe.bound + m) = bound_none(m, is_int);
+                __threadfence_block();
+                if (ismin) atomicMin(p, (unsigned long long)x); else atomicMax(p, (unsigned long long)x);
+                __threadfence_block();
+                atomicExch(fe.lock, 0u);
+                done = true;
+            } else __nanosleep(32);
+        }
+    } else if (ismin ? x < cur : x > cur) {
+        if (ismin) atomicMin(p, (unsigned long long)x); else atomicMax(p, (unsigned long long)x);
+    }
+}
+
+// A NaN met the identity: the group now "has a value" as far as first-value detection goes (its lanes' later rows are
+// not first rows any more), so mark it with a second NaN-patterned sentinel that any real value replaces. While a
+// group holds the sentinel the refreshed bound is a NaN, i.e. every row takes the exact path — correct, slow, and only
+// for as long as a group has seen nothing but NaNs.
+__device__ __noinline__ void mm_mark_nan(const Fe& fe, int gid, int m) {
+    unsigned long long* p = reinterpret_cast<unsigned long long*>(fe.mm + gid * NMM1 + m);
+    if (*reinterpret_cast<volatile unsigned long long*>(p) != mm_identity(m)) return;
+    const bool ismin = (Q::MM_ISMIN >> m) & 1u;
+    bool done = false;
+    while (!done) {                 // critical section inside the retry loop: see mm_update
+        if (atomicCAS(fe.lock, 0u, 1u) == 0u) {
+            __threadfence_block();
+            *reinterpret_cast<volatile uint64_t*>(fe.bound + m) = bound_none(m, false);
+            __threadfence_block();
+            atomicCAS(p, (unsigned long long)mm_identity(m), ismin ? ~0ULL - 1ULL : 1ULL);
+            __threadfence_block();
+            atomicExch(fe.lock, 0u);
+            done = true;
+        } else __nanosleep(32);
+    }
+}
+
+// Recompute the bounds from the extremes of all groups that have a value (one warp, every few tiles, under the lock).
+__device__ __noinline__ void mm_bound_refresh(const Fe& fe, int lane) {
+    if (lane == 0 && atomicCAS(fe.lock, 0u, 1u) != 0u) lane = -1;          // somebody is inserting: try again later
+    if (__shfl_sync(0xffffffffu, lane, 0) < 0) return;
+    __threadfence_block();
+    const int n = (int)*reinterpret_cast<volatile uint32_t*>(&fe.ctl->count);
+#pragma unroll
+    for (int m = 0; m < Q::NMM; m++) {
+        const bool ismin = (Q::MM_ISMIN >> m) & 1u, is_int = mm_is_int(m);
+        uint64_t b = ismin ? 0ULL : ~0ULL;               // MIN: the largest group minimum; MAX: the smallest group maximum (order-mapped)
+        bool any = false, none = false;
+        for (int g = lane; g < n; g += 32) {
+            const uint64_t x = *reinterpret_cast<volatile uint64_t*>(fe.mm + g * NMM1 + m);
+            if (x == mm_identity(m)) { if (is_int) none = true; continue; }      // Int64: the identity is also a value (kq_k_agg_fe.cuh header)
+            any = true;
+            b = ismin ? (x > b ? x : b) : (x < b ? x : b);
+        }
+#pragma unroll
+        for (int o = 16; o; o >>= 1) {
+            const uint64_t y = __shfl_xor_sync(0xffffffffu, b, o);
+            b = ismin ? (y > b ? y : b) : (y < b ? y : b);
+        }
+        any = __any_sync(0xffffffffu, any) && !__any_sync(0xffffffffu, none);
+        if (lane == 0) *reinterpret_cast<volatile uint64_t*>(fe.bound + m) = any ? order_unmap(b, is_int) : bound_none(m, is_int);
+    }
+    __threadfence_block();
+    __syncwarp();
+    if (lane == 0) atomicExch(fe.lock, 0u);
+}
+
+// Accumulate one row into the lane-private slots of group g (FG = trash) — the branch-free per-row path. All loads of
+// the row's slots are issued before the first store (the slots of one row never alias; the next row's may).
+// Returns true when the row needs the exact MIN/MAX path (beats a bound, or first value of this lane in the group).
+__device__ __forceinline__ bool fe_accumulate_row(const Fe& fe, uint32_t g, const AggSink& sink, int r, const uint64_t (&bnd)[NMM1]) {
+    constexpr int NI = Q::NIN > 0 ? Q::NIN : 1;
+    const uint32_t base = g * (uint32_t)GS;
+    const uint32_t a8 = fe.a_lane8 + base, a4 = fe.a_lane4 + base;
+    const uint32_t t8 = fe.a_lane8 + (uint32_t)(FG * GS), t4 = fe.a_lane4 + (uint32_t)(FG * GS);      // an invalid row of a nullable input: the trash group
+    uint32_t c0 = 0, ca[NI], cv[NI], sa[NI];
+    uint64_t sv[NI];
+    bool valid[NI];
+    if constexpr (Q::CNT0_USED) c0 = lds_u32(a4);
+#pragma unroll
+    for (int i = 0; i < Q::NIN; i++) {
+        const int FL = Q::IN_FLAGS[i];
+        const bool nullable = Q::IN_CNT[i] > 0;
+        valid[i] = nullable ? ((sink.inok[i] >> r) & 1u) != 0 : true;
+        if (nullable) { ca[i] = (valid[i] ? a4 : t4) + (uint32_t)Q::IN_CNT[i] * 128u; cv[i] = lds_u32(ca[i]); }
+        if (FL & F_SUM) { sa[i] = (nullable ? (valid[i] ? a8 : t8) : a8) + (uint32_t)Q::FE_SUM[i] * 256u; sv[i] = lds_u64(sa[i]); }
+    }
+    if constexpr (Q::CNT0_USED) asm volatile("st.shared.u32 [%0], %1;" ::"r"(a4), "r"(c0 + 1u) : "memory");
+    bool exact = false;
+#pragma unroll
+    for (int i = 0; i < Q::NIN; i++) {
+        const int FL = Q::IN_FLAGS[i];
+        const bool nullable = Q::IN_CNT[i] > 0;
+        bool first = c0 == 0u;
+        if (nullable) {
+            asm volatile("st.shared.u32 [%0], %1;" ::"r"(ca[i]), "r"(cv[i] + 1u) : "memory");
+            first = cv[i] == 0u;
+        }
+        const uint64_t v = sink.in[i][r];
+        if (FL & F_SUM) {
+            const uint64_t y = (FL & F_INT) ? sv[i] + v : as_u64(__dadd_rn(as_f64(sv[i]), as_f64(v)));
+            asm volatile("st.shared.u64 [%0], %1;" ::"r"(sa[i]), "l"(y) : "memory");
+        }
+        if (FL & (F_MIN | F_MAX)) {
+            bool e = first;
+            if (FL & F_INT) {
+                if (FL & F_MIN) e |= (long long)v < (long long)bnd[Q::FE_MIN[i] < 0 ? 0 : Q::FE_MIN[i]];
+                if (FL & F_MAX) e |= (long long)v > (long long)bnd[Q::FE_MAX[i] < 0 ? 0 : Q::FE_MAX[i]];
+            } else {
+                if (FL & F_MIN) e |= !(as_f64(v) >= as_f64(bnd[Q::FE_MIN[i] < 0 ? 0 : Q::FE_MIN[i]]));
+                if (FL & F_MAX) e |= !(as_f64(v) <= as_f64(bnd[Q::FE_MAX[i] < 0 ? 0 : Q::FE_MAX[i]]));
+            }
+            exact |= e && valid[i];
+        }
+    }
+    return exact;
+}
+
+// The exact MIN/MAX path of one row (rare).
+__device__ __forceinline__ void fe_exact_row(const Fe& fe, int gid, const AggSink& sink, int r) {
+#pragma unroll
+    for (int i = 0; i < Q::NIN; i++) {
+        const int FL = Q::IN_FLAGS[i];
+        if (!(FL & (F_MIN | F_MAX))) continue;
+        if (Q::IN_CNT[i] > 0 && !((sink.inok[i] >> r) & 1u)) continue;
+        const uint64_t v = sink.in[i][r];
+        const bool is_int = (FL & F_INT) != 0;
+        if (!is_int && as_f64(v) != as_f64(v)) {                    // NaN never replaces a held value (Main.kt:552: `value > this.value`)
+            if (FL & F_MIN) mm_mark_nan(fe, gid, Q::FE_MIN[i]);
+            if (FL & F_MAX) mm_mark_nan(fe, gid, Q::FE_MAX[i]);
+            continue;
+        }
+        if (FL & F_MIN) mm_update(fe, gid, Q::FE_MIN[i], v, is_int);
+        if (FL & F_MAX) mm_update(fe, gid, Q::FE_MAX[i], v, is_int);
+    }
+}
+
+template <int I>
+__device__ __forceinline__ void global_accumulate_all(const AggArgs& A, uint64_t* rec, const AggSink& sink, int r) {
+    if constexpr (I < Q::NIN) {
+        if ((sink.inok[I] >> r) & 1u) global_accumulate(rec, A.in[I], sink.in[I][r]);
+        global_accumulate_all<I + 1>(A, rec, sink, r);
+    }
+}
+
+// Merge the lane-private slots of group g (this warp's copy) into its global record.
+template <int I>
+__device__ __forceinline__ void fe_merge_input(uint32_t a_warp, uint64_t* rec, int g, int lane, const unsigned long long (&c)[Q::NCNT]) {
+    if constexpr (I < Q::NIN) {
+        constexpr int FL = Q::IN_FLAGS[I];
+        const unsigned long long n = c[Q::IN_CNT[I]];
+        if (n != 0) {                                       // this warp saw no non-null value of input I in group g otherwise
+            if (lane == 0) atomicAdd(reinterpret_cast<unsigned long long*>(rec + Q::REC_NN[I]), n);
+            if constexpr ((FL & F_SUM) != 0) {
+                uint64_t x = lds_u64(a_warp + (uint32_t)g * GS + (uint32_t)Q::FE_SUM[I] * 256u + (uint32_t)lane * 8u);
+                if constexpr ((FL & F_INT) != 0) {
+#pragma unroll
+                    for (int o = 16; o; o >>= 1) x += __shfl_xor_sync(0xffffffffu, x, o);
+                    if (lane == 0) atomicAdd(reinterpret_cast<unsigned long long*>(rec + Q::REC_SUM[I]), (unsigned long long)x);
+                } else {
+                    double f = as_f64(x);
+#pragma unroll
+                    for (int o = 16; o; o >>= 1) f = __dadd_rn(f, __shfl_xor_sync(0xffffffffu, f, o));
+                    if (lane == 0) atomicAdd(reinterpret_cast<double*>(rec + Q::REC_SUM[I]), f);
+                }
+            }
+        }
+        fe_merge_input<I + 1>(a_warp, rec, g, lane, c);
+    }
+}
+
+extern "C" __global__ void __launch_bounds__(THREADS, 1) kq_group_aggregate(const __grid_constant__ AggArgs A) {
+    // dynamic shared memory: [S stages][directory state][directory keys][dense keys][dense null masks][extremes][gslot]
+    //                        [per-warp lane-private blocks of FG + 1 groups]
+    extern __shared__ __align__(128) unsigned char smem[];
+    __shared__ uint64_t full[S], empty[S];
+    __shared__ long long tile_of[S];
+    __shared__ long long bbase[S][MAX_COLS];
+    __shared__ DirCtl s_ctl;
+    __shared__ uint32_t s_lock, s_limit;
+    __shared__ uint64_t s_bound[NMM1];
+    const int wid = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int warp = wid - 1;                 // consumer warp index
+    unsigned char* p0 = smem + (size_t)S * A.sp.stage_bytes;
+    const size_t fe_begin = (size_t)(p0 - smem);
+    Fe fe;
+    fe.meta = reinterpret_cast<uint32_t*>(p0);            p0 += (size_t)DIR * 4;
+    fe.keys = reinterpret_cast<uint64_t*>(p0);            p0 += (size_t)DIR * NKW * 8;
+    fe.gkeys = reinterpret_cast<uint64_t*>(p0);           p0 += (size_t)FG * NKW * 8;
+    fe.mm = reinterpret_cast<uint64_t*>(p0);              p0 += (size_t)(FG + 1) * NMM1 * 8;
+    uint64_t* gslot = reinterpret_cast<uint64_t*>(p0);    p0 += (size_t)FG * 8;
+    fe.gnm = reinterpret_cast<uint32_t*>(p0);             p0 += (size_t)((FG + 3) & ~3) * 4;
+    unsigned char* lane_blocks = p0;                      p0 += (size_t)WARPS * (FG + 1) * GS;
+    const size_t fe_end = (size_t)(p0 - smem);
+    fe.ctl = &s_ctl; fe.lock = &s_lock; fe.limit = &s_limit; fe.bound = s_bound;
+    fe.a_ctl = smem_u32(&s_ctl); fe.a_meta = smem_u32(fe.meta); fe.a_keys = smem_u32(fe.keys); fe.a_mm = smem_u32(fe.mm);
+    const uint32_t a_warp = smem_u32(lane_blocks) + (uint32_t)(warp < 0 ? 0 : warp) * (uint32_t)((FG + 1) * GS);
+    fe.a_lane8 = a_warp + (uint32_t)lane * 8u;
+    fe.a_lane4 = a_warp + (uint32_t)Q::NSUM * 256u + (uint32_t)lane * 4u;
+
+    for (size_t i = fe_begin + threadIdx.x * 4; i < fe_end; i += THREADS * 4) *reinterpret_cast<uint32_t*>(smem + i) = 0;
+    if (threadIdx.x == 0) {
+        s_ctl.gen = 0; s_ctl.s1 = 0x9E3779B1u; s_ctl.s2 = 0x85EBCA6Bu; s_ctl.count = 0;
+        s_lock = 0; s_limit = (uint32_t)FG;
+        for (int m = 0; m < Q::NMM; m++) s_bound[m] = bound_none(m, mm_is_int(m));
+        for (int s = 0; s < S; s++) { mbar_init(&full[s], 1); mbar_init(&empty[s], WARPS); }
+        mbar_fence_init();
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < (FG + 1) * Q::NMM; i += THREADS) fe.mm[i] = mm_identity(i % NMM1);
+    __syncthreads();
+
+    if (wid == PRODUCER_WARP) {
+        if (lane == 0) {
+            // The next ticket is always requested one step early: the L2 round trip of the atomic and the HBM reads of the
+            // tile's Utf8 boundary offsets (stage_bounds_fetch) overlap the wait for a free stage, so string bytes and
+            // fixed-size buffers of a tile are issued together on one barrier.
+            TileBounds tb = {};
+            auto take = [&]() -> long long {
+                // stop taking tiles once the global table is past its threshold: every ticket taken is processed, so the
+                // rows consumed so far are always a prefix of the batch (the host grows the table and resumes)
+                const unsigned long long g = *reinterpret_cast<volatile unsigned long long*>(A.ngroups);
+                if (g > A.stop_threshold) return -1;
+                const long long t = (long long)atomicAdd(A.ticket, 1u) + A.tile_begin;
+                if (t >= A.ntiles) return -1;
+                if (KQ_STAGE_BYTES) stage_bounds_fetch(A.sp, t, TILE, A.n, tb);
+                return t;
+            };
+            long long next = take();
+            for (int kp = 0;; kp++) {
+                const int s = kp % S;
+                while (!mbar_test(&empty[s], ((kp / S) & 1) ^ 1)) __nanosleep(32);
+                const long long tile = next;
+                tile_of[s] = tile;
+                if (tile < 0) { mbar_arrive(&full[s]); break; }
+                stage_issue_all(A.sp, smem + (size_t)s * A.sp.stage_bytes, &full[s], tile, TILE, A.n, tb, bbase[s], 0ULL);
+                next = take();
+            }
+        }
+    } else {
+        AggSink sink;
+        bool bypass = false;                      // high cardinality after all: stop probing a full directory that mostly misses
+        int low_tiles = 0;
+        for (int k = 0;; k++) {
+            const int s = k % S;
+            mbar_wait(&full[s], (k / S) & 1);
+            const long long tile = tile_of[s];
+            if (tile < 0) break;
+            RowCtx rc;
+            rowctx_init(rc, warp, tile, TILE, A.n, A.err, smem + (size_t)s * A.sp.stage_bytes);
+            rc.bbase = bbase[s];
+            sink.sel = rc.inr;
+            if constexpr (Q::NKEYS == 0) {
+#pragma unroll
+                for (int r = 0; r < R; r++) sink.key[0][r] = 0;
+                sink.keyok[0] = RMASK;
+            }
+            Q::eval(A.q, rc, sink);
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&empty[s]);       // everything needed is in registers now
+
+            // canonical key words + null masks of the R owned rows
+            uint32_t nm[R];
+#pragma unroll
+            for (int r = 0; r < R; r++) {
+                uint32_t nullmask = 0;
+#pragma unroll
+                for (int k2 = 0; k2 < Q::NKEYS; k2++) {
+                    uint64_t w = 0;
+                    if (!Q::KEYS_NULLABLE || ((sink.keyok[k2] >> r) & 1u)) w = ((Q::KEY_F64_MASK >> k2) & 1u) ? canon_nan(sink.key[k2][r]) : sink.key[k2][r];
+                    else nullmask |= 1u << k2;
+                    sink.key[k2][r] = w;
+                }
+                nm[r] = nullmask;
+            }
+
+            // ---- key -> group: one probe per row ------------------------------------------------------------------
+            uint32_t gsel[R];                         // group id, FG (trash) for rows that are filtered out or unresolved
+            uint32_t slow = sink.sel;                 // rows that still need the general path
+            if (!bypass) {
+                const uint4 c = lds_u128(fe.a_ctl);   // {gen, s1, s2, count}
+                uint32_t miss = 0;
+#pragma unroll
+                for (int r = 0; r < R; r++) {
+                    uint64_t kw[NKW];
+#pragma unroll
+                    for (int k2 = 0; k2 < NKW; k2++) kw[k2] = sink.key[k2][r];
+                    const int g = dir_probe(fe, kw, nm[r], c.y, c.z);
+                    const bool on = (sink.sel >> r) & 1u;
+                    gsel[r] = (on && g >= 0) ? (uint32_t)g : (uint32_t)FG;
+                    miss |= (uint32_t)(on && g < 0) << r;
+                }
+                const uint32_t gen2 = *reinterpret_cast<volatile uint32_t*>(&s_ctl.gen);
+                if (gen2 != c.x || (c.x & 1u)) {      // a rebuild ran meanwhile: nothing probed counts
+#pragma unroll
+                    for (int r = 0; r < R; r++) gsel[r] = (uint32_t)FG;
+                    miss = sink.sel;
+                }
+                slow = miss;
+            } else {
+#pragma unroll
+                for (int r = 0; r < R; r++) gsel[r] = (uint32_t)FG;
+            }
+
+            // ---- accumulate (branch-free); bounds are read AFTER the probes: they cover every group probed -----------
+            uint64_t bnd[NMM1];
+#pragma unroll
+            for (int m = 0; m < Q::NMM; m++) bnd[m] = *reinterpret_cast<volatile uint64_t*>(s_bound + m);
+            uint32_t exact = 0;
+            bool many_exact = false;
+            if (!bypass) {
+                uint32_t onmask = 0;
+#pragma unroll
+                for (int r = 0; r < R; r++) {
+                    const bool on = gsel[r] != (uint32_t)FG;
+                    onmask |= (uint32_t)on << r;
+                    exact |= (uint32_t)(fe_accumulate_row(fe, gsel[r], sink, r, bnd) && on) << r;
+                }
+                if (Q::NMM > 0 && __any_sync(0xffffffffu, exact != 0)) {
+                    // a lane that took the exact path may have met a group no bound covers yet (first value): the flags of its
+                    // other rows were computed against a possibly stale bound, so all its rows take the exact path
+                    if (exact) exact = onmask;
+                    many_exact = __popc(__ballot_sync(0xffffffffu, exact != 0)) >= 8;
+#pragma unroll
+                    for (int r = 0; r < R; r++)
+                        if ((exact >> r) & 1u) fe_exact_row(fe, (int)gsel[r], sink, r);
+                }
+            }
+
+            // ---- general path: keys that are not in the directory (yet) ------------------------------------------------
+            uint32_t new_groups = 0;
+            const int rows = __popc(sink.sel);
+            int fe_hits = rows - __popc(slow);
+            while (__any_sync(0xffffffffu, slow != 0)) {
+                bool full_dir = true;
+                if (!bypass) {
+                    // look again: another warp may have inserted the key meanwhile (no lock needed for that)
+                    const uint4 c = lds_u128(fe.a_ctl);
+                    int g2[R];
+#pragma unroll
+                    for (int r = 0; r < R; r++) {
+                        g2[r] = -1;
+                        if ((slow >> r) & 1u) {
+                            uint64_t kw[NKW];
+#pragma unroll
+                            for (int k2 = 0; k2 < NKW; k2++) kw[k2] = sink.key[k2][r];
+                            g2[r] = dir_probe(fe, kw, nm[r], c.y, c.z);
+                        }
+                    }
+                    const uint32_t gen2 = *reinterpret_cast<volatile uint32_t*>(&s_ctl.gen);
+                    const bool valid = gen2 == c.x && !(c.x & 1u);
+                    full_dir = valid && c.w >= *reinterpret_cast<volatile uint32_t*>(&s_limit);
+                    if (valid) {
+                        uint64_t nb[NMM1];
+#pragma unroll
+                        for (int m = 0; m < NMM1; m++) nb[m] = 0;
+#pragma unroll
+                        for (int r = 0; r < R; r++) {
+                            if (g2[r] < 0) continue;
+                            fe_accumulate_row(fe, (uint32_t)g2[r], sink, r, nb);
+                            if (Q::NMM > 0) fe_exact_row(fe, g2[r], sink, r);       // rare path: always the exact compare
+                            slow &= ~(1u << r);
+                            fe_hits++;
+                        }
+                    }
+                    if (!__any_sync(0xffffffffu, slow != 0)) break;
+                }
+                if (full_dir) {
+                    // the directory takes no more keys: the rest goes to the global table
+#pragma unroll
+                    for (int r = 0; r < R; r++) {
+                        if (!((slow >> r) & 1u)) continue;
+                        uint64_t kw[MAX_KEYS];
+#pragma unroll
+                        for (int k2 = 0; k2 < MAX_KEYS; k2++) kw[k2] = k2 < Q::NKEYS ? sink.key[k2][r] : 0;
+                        uint64_t* rec = table_find_or_insert(A, hash_key(kw, nm[r], Q::NKEYS), kw, nm[r], &new_groups);
+                        if (rec) global_accumulate_all<0>(A, rec, sink, r);
+                    }
+                    slow = 0;
+                    break;
+                }
+                // insert the first unresolved key of the first lane that has one (whole warp, under the CTA lock)
+                const uint32_t b = __ballot_sync(0xffffffffu, slow != 0);
+                const int leader = __ffs(b) - 1;
+                const int r0 = __ffs(slow) - 1;             // meaningful on the leader
+                uint64_t kw[NKW];
+                uint32_t knm = 0;
+#pragma unroll
+                for (int r = 0; r < R; r++)
+                    if (r == r0) {
+#pragma unroll
+                        for (int k2 = 0; k2 < NKW; k2++) kw[k2] = sink.key[k2][r];
+                        knm = nm[r];
+                    }
+#pragma unroll
+                for (int k2 = 0; k2 < NKW; k2++) kw[k2] = __shfl_sync(0xffffffffu, kw[k2], leader);
+                knm = __shfl_sync(0xffffffffu, knm, leader);
+                const int g = dir_find_or_insert(fe, kw, knm, lane);
+                if (g < 0 && lane == leader) {
+                    // not insertable (directory full or unplaceable): this row goes to the global table now
+                    uint64_t kg[MAX_KEYS];
+#pragma unroll
+                    for (int k2 = 0; k2 < MAX_KEYS; k2++) kg[k2] = k2 < Q::NKEYS ? kw[k2] : 0;
+                    uint64_t* rec = table_find_or_insert(A, hash_key(kg, knm, Q::NKEYS), kg, knm, &new_groups);
+#pragma unroll
+                    for (int r = 0; r < R; r++) if (r == r0 && rec) global_accumulate_all<0>(A, rec, sink, r);
+                    slow &= ~(1u << r0);
+                }
+                // g >= 0: the next round's probe finds the key (for every lane that waits for it)
+            }
+            // one update of the global group count per warp and tile (a single counter bumped by every insert serialises in the L2)
+            if (__any_sync(0xffffffffu, new_groups != 0)) {
+                const uint32_t tot = __reduce_add_sync(0xffffffffu, new_groups);
+                if (lane == 0) atomicAdd(A.ngroups, (unsigned long long)tot);
+            }
+            // refresh the bounds when they look stale (many rows took the exact path), and every 16 tiles to tighten them
+            if (Q::NMM > 0 && (many_exact || ((k + 2 * warp) & 15) == 0)) mm_bound_refresh(fe, lane);
+            // once the directory is full and this warp mostly misses it, stop probing it (the hint was wrong: high cardinality)
+            if (!bypass && __any_sync(0xffffffffu, fe_hits < rows) && *reinterpret_cast<volatile uint32_t*>(&s_ctl.count) >= *reinterpret_cast<volatile uint32_t*>(&s_limit)) {
+                int hits = fe_hits, tot = rows;
+#pragma unroll
+                for (int o = 16; o; o >>= 1) { hits += __shfl_xor_sync(0xffffffffu, hits, o); tot += __shfl_xor_sync(0xffffffffu, tot, o); }
+                if (tot >= 64 && hits * 8 < tot) { if (++low_tiles >= 2) bypass = true; }
+                else low_tiles = 0;
+            } else low_tiles = 0;
+        }
+    }
+
+    // ---- merge the CTA's groups into the global table ---------------------------------------------------------------
+    __syncthreads();
+    const int G = (int)s_ctl.count;
+    for (int g = threadIdx.x; g < G; g += THREADS) {
+        uint64_t kw[MAX_KEYS];
+#pragma unroll
+        for (int k = 0; k < MAX_KEYS; k++) kw[k] = k < Q::NKEYS ? fe.gkeys[g * NKW + k] : 0;
+        const uint32_t nullmask = fe.gnm[g];
+        uint32_t fresh = 0;
+        uint64_t* rec = table_find_or_insert(A, hash_key(kw, nullmask, Q::NKEYS), kw, nullmask, &fresh);
+        if (fresh) atomicAdd(A.ngroups, 1ULL);
+        gslot[g] = rec ? (uint64_t)(rec - A.table) : ~0ULL;
+    }
+    __syncthreads();
+    if (warp >= 0) {
+        for (int g = 0; g < G; g++) {
+            if (gslot[g] == ~0ULL) continue;
+            uint64_t* rec = A.table + gslot[g];
+            unsigned long long c[Q::NCNT];
+#pragma unroll
+            for (int j = 0; j < Q::NCNT; j++) {
+                unsigned long long x = lds_u32(a_warp + (uint32_t)g * GS + (uint32_t)Q::NSUM * 256u + (uint32_t)j * 128u + (uint32_t)lane * 4u);
+#pragma unroll
+                for (int o = 16; o; o >>= 1) x += __shfl_xor_sync(0xffffffffu, x, o);
+                c[j] = x;
+            }
+            fe_merge_input<0>(a_warp, rec, g, lane, c);
+        }
+    }
+    for (int t = threadIdx.x; t < G * Q::NMM; t += THREADS) {
+        const int g = t / NMM1, m = t % NMM1;
+        if (gslot[g] == ~0ULL) continue;
+        const uint64_t v = fe.mm[g * NMM1 + m];
+        uint64_t* p = A.table + gslot[g] + Q::MM_WORD[m];
+        if ((Q::MM_ISMIN >> m) & 1u) { if (v != ~0ULL) atomicMin(reinterpret_cast<unsigned long long*>(p), (unsigned long long)v); }
+        else if (v != 0ULL) atomicMax(reinterpret_cast<unsigned long long*>(p), (unsigned long long)v);
+    }
+}
+
+}  // namespace kq

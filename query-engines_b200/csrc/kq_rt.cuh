@@ -240,24 +240,31 @@ __device__ __forceinline__ uint64_t lds_window64(uint32_t addr) {
     asm volatile("ld.shared.u32 %0, [%1+8];" : "=r"(w2) : "r"(al));
     return (uint64_t)__funnelshift_r(w0, w1, sh) | ((uint64_t)__funnelshift_r(w1, w2, sh) << 32);
 }
-// first `len` bytes of window w, length in the top byte (len <= 7; longer strings raise ERR_LONG_KEY, their key is unused)
+// 32-bit shifts with PTX semantics (an amount >= 32 yields 0; C++ leaves it undefined, SASS would wrap)
+__device__ __forceinline__ uint32_t shl32c(uint32_t x, uint32_t n) { uint32_t r; asm("shl.b32 %0, %1, %2;" : "=r"(r) : "r"(x), "r"(n)); return r; }
+__device__ __forceinline__ uint32_t shr32c(uint32_t x, uint32_t n) { uint32_t r; asm("shr.u32 %0, %1, %2;" : "=r"(r) : "r"(x), "r"(n)); return r; }
+// first `len` bytes of window w, length in the top byte (len <= 7; longer strings raise ERR_LONG_KEY, their key is unused).
+// Masks instead of 64-bit shift pairs: low word keeps its low 8*len bits (all of them from len = 4), high word the low
+// 8*(len-4) bits (none up to len = 4) — seven 32-bit instructions.
 __device__ __forceinline__ uint64_t pack_key(uint64_t w, int len) {
-    const uint32_t drop = 64u - 8u * (uint32_t)len;
-    return shr64c(shl64c(w, drop), drop) | ((uint64_t)(uint32_t)len << 56);
+    const uint32_t nb = 8u * (uint32_t)len;
+    const uint32_t lo = (uint32_t)w & ~shl32c(0xFFFFFFFFu, nb);
+    const uint32_t hi = ((uint32_t)(w >> 32) & shr32c(0xFFFFFFFFu, 64u - nb)) | ((uint32_t)len << 24);
+    return (uint64_t)lo | ((uint64_t)hi << 32);
 }
-// Staged fast path of utf8_pack. FULL: the whole tile is inside the batch (no per-row range handling).
+// Staged fast path of utf8_pack. FULL: the whole tile is inside the batch (no per-row range handling). ALLOK: the column
+// has no nulls in range, so no key has to be blanked.
 // A lane's two adjacent rows are adjacent strings: one 8-byte window at the first string's start yields both
 // keys whenever the two fit in it; pairs that do not (long keys) are redone in a rarely taken second loop.
-template <int SOFF_OFF, int SB, bool FULL>
+template <int SOFF_OFF, int SB, bool FULL, bool ALLOK>
 __device__ __forceinline__ uint32_t utf8_pack_staged(long long base, uint32_t ok, const RowCtx& rc, uint64_t (&out)[R]) {
     const uint32_t sb32 = smem_u32(rc.stage) + (uint32_t)SB - (uint32_t)base;      // shared address of data-buffer offset 0 (mod 2^32)
-    const uint32_t so32 = smem_u32(rc.stage) + (uint32_t)SOFF_OFF;
-    int mxlen = 0;
-    uint32_t need2 = 0;
+    const uint32_t so32 = smem_u32(rc.stage) + (uint32_t)SOFF_OFF + (uint32_t)rc.trow0(0) * 4u;
+    int mxlen = 0, mxtot = 0;
     // offsets of the lane's row pair in chunk j: o[2l], o[2l+1], o[2l+2]; rows past the end of the batch have
     // none (stale shared memory): give them an empty, in-range string
     auto bounds = [&](int j, int& a0, int& len0, int& len1) {
-        const uint32_t oa = so32 + (uint32_t)rc.trow0(j) * 4u;
+        const uint32_t oa = so32 + (uint32_t)j * 256u;
         int o0, o1, o2;
         asm volatile("ld.shared.v2.s32 {%0,%1}, [%2];" : "=r"(o0), "=r"(o1) : "r"(oa));
         asm volatile("ld.shared.s32 %0, [%1+8];" : "=r"(o2) : "r"(oa));
@@ -272,21 +279,24 @@ __device__ __forceinline__ uint32_t utf8_pack_staged(long long base, uint32_t ok
         int a0, len0, len1;
         bounds(j, a0, len0, len1);
         mxlen = max(mxlen, max(len0, len1));
-        need2 |= (uint32_t)(len0 + len1 > 8) << j;
+        mxtot = max(mxtot, len0 + len1);
         const uint64_t w0 = lds_window64(sb32 + (uint32_t)a0);
         const uint64_t k0 = pack_key(w0, len0), k1 = pack_key(shr64c(w0, 8u * (uint32_t)len0), len1);
-        out[2 * j] = ((ok >> (2 * j)) & 1u) ? k0 : 0ULL;
-        out[2 * j + 1] = ((ok >> (2 * j + 1)) & 1u) ? k1 : 0ULL;
+        if constexpr (ALLOK) { out[2 * j] = k0; out[2 * j + 1] = k1; }
+        else {
+            out[2 * j] = ((ok >> (2 * j)) & 1u) ? k0 : 0ULL;
+            out[2 * j + 1] = ((ok >> (2 * j + 1)) & 1u) ? k1 : 0ULL;
+        }
     }
     uint32_t too_long = 0;
-    if (need2 | (uint32_t)(mxlen > 7)) {
+    if (mxtot > 8 || mxlen > 7) {
 #pragma unroll 1
         for (int j = 0; j < NCHUNK; j++) {
             int a0, len0, len1;
             bounds(j, a0, len0, len1);
             too_long |= (uint32_t)(len0 > 7) << (2 * j) | (uint32_t)(len1 > 7) << (2 * j + 1);
-            if ((need2 >> j) & 1u) {
-                const uint64_t k1 = pack_key(lds_window64(sb32 + (uint32_t)(a0 + len0)), len1);
+            if (len0 + len1 > 8) {
+                const uint64_t k1 = pack_key(lds_window64(sb32 + (uint32_t)(a0 + len0)), len1 > 7 ? 7 : len1);
 #pragma unroll
                 for (int jj = 0; jj < NCHUNK; jj++) if (jj == j) out[2 * jj + 1] = ((ok >> (2 * jj + 1)) & 1u) ? k1 : 0ULL;
             }
@@ -303,8 +313,8 @@ __device__ __forceinline__ void utf8_pack(const QCol& c, uint32_t ok, const RowC
     if constexpr (SB >= 0 && SOFF_OFF >= 0) base = rc.bbase[SLOT];
     uint32_t too_long = 0;
     if (base >= 0) {
-        if (rc.full) too_long = utf8_pack_staged<SOFF_OFF, SB, true>(base, ok, rc, out);
-        else too_long = utf8_pack_staged<SOFF_OFF, SB, false>(base, ok, rc, out);
+        if (rc.full) { if (ok == RMASK) too_long = utf8_pack_staged<SOFF_OFF, SB, true, true>(base, ok, rc, out); else too_long = utf8_pack_staged<SOFF_OFF, SB, true, false>(base, ok, rc, out); }
+        else too_long = utf8_pack_staged<SOFF_OFF, SB, false, false>(base, ok, rc, out);
     } else {
         const uint8_t* bytes = reinterpret_cast<const uint8_t*>(c.data);
 #pragma unroll

@@ -435,28 +435,48 @@ def q1_aggregate(E, batch, **kw):
     return agg.finalize()
 
 
-def test_group_key_equality_and_nan_order(G):
-    """R7 on the GPU: NaN == NaN is one group, +0.0 != -0.0, null is a group. MIN/MAX use the total
-    order documented in DESIGN.md (NaN above +inf) where the reference is order-dependent (R9)."""
+def test_group_key_equality_and_nan_order(G, oracle):
+    """R7 on the GPU: NaN == NaN is one group, +0.0 != -0.0, null is a group. MIN/MAX (rule R9, Main.kt:540-555) are
+    checked AGAINST THE ORACLE wherever the reference does not depend on the row order: `value > this.value` never lets a
+    NaN replace a held value, an all-NaN group yields NaN. The one order-dependent residual — a NaN as the FIRST non-null
+    value sticks in the reference — is asserted separately, with both behaviours spelled out."""
     k = pa.array([float("nan"), 0.0, -0.0, float("nan"), None, None, 1.0], pa.float64())
     v = pa.array([1.0, 2.0, 3.0, 4.0, 5.0, 6.0, 7.0], pa.float64())
-    agg = G.HashAggregate([G.col(0)], [("COUNT", G.col(1)), ("MAX", G.col(1))])
-    agg.update(G.RecordBatch.from_arrow([k, v]))
-    keys, cnt, mx = [a.to_pylist() for a in agg.finalize().to_arrow()]
-    got = {}
-    for kk, c, m in zip(keys, cnt, mx):
-        tag = "null" if kk is None else ("nan" if kk != kk else ("-0" if (kk == 0 and math.copysign(1, kk) < 0) else kk))
-        got[tag] = (c, m)
-    assert got == {"nan": (2, 4.0), 0.0: (1, 2.0), "-0": (1, 3.0), "null": (2, 6.0), 1.0: (1, 7.0)}
-    def mm(vals):
-        agg = G.HashAggregate([], [("MAX", G.col(0)), ("MIN", G.col(0)), ("SUM", G.col(0)), ("COUNT", G.col(0))])
-        agg.update(G.RecordBatch.from_arrow([pa.array(vals, pa.float64())]))
+    res = {}
+    for E in (G, oracle):
+        agg = E.HashAggregate([E.col(0)], [("COUNT", E.col(1)), ("MAX", E.col(1))])
+        agg.update(E.RecordBatch.from_arrow([k, v]))
+        keys, cnt, mx = [a.to_pylist() for a in agg.finalize().to_arrow()]
+        got = {}
+        for kk, c, m in zip(keys, cnt, mx):
+            tag = "null" if kk is None else ("nan" if kk != kk else ("-0" if (kk == 0 and math.copysign(1, kk) < 0) else kk))
+            got[tag] = (c, m)
+        res[E is G] = got
+    assert res[True] == res[False] == {"nan": (2, 4.0), 0.0: (1, 2.0), "-0": (1, 3.0), "null": (2, 6.0), 1.0: (1, 7.0)}
+
+    def mm(E, vals):
+        agg = E.HashAggregate([], [("MAX", E.col(0)), ("MIN", E.col(0)), ("SUM", E.col(0)), ("COUNT", E.col(0))])
+        agg.update(E.RecordBatch.from_arrow([pa.array(vals, pa.float64())]))
         return [a.to_pylist()[0] for a in agg.finalize().to_arrow()]
-    r = mm([5.0, float("nan"), -1.0])
-    assert math.isnan(r[0]) and r[1] == -1.0 and r[3] == 3
-    r = mm([0.0, -0.0])
-    assert math.copysign(1, r[0]) == 1 and math.copysign(1, r[1]) == -1
-    assert mm([None, None]) == [None, None, None, 0]
+
+    def eqv(a, b):
+        return all((x is None and y is None) or (x is not None and y is not None and ((x != x and y != y) or x == y)) for x, y in zip(a, b))
+
+    nan, inf = float("nan"), float("inf")
+    # order-independent in the reference: the first non-null value is not a NaN, or every value is
+    for vals in ([5.0, nan, -1.0], [-1.0, nan, 5.0, nan], [nan, nan], [nan], [1.0, inf, nan, -inf], [inf, inf], [None, 2.0, nan, None],
+                 [None, None], [-0.0], [0.0, 0.0]):
+        g, o = mm(G, vals), mm(oracle, vals)
+        assert eqv(g[:2], o[:2]) and g[3] == o[3], (vals, g, o)
+    assert mm(G, [5.0, nan, -1.0])[:2] == [5.0, -1.0]
+    assert mm(G, [None, None]) == [None, None, None, 0]
+    # the residual: a leading NaN sticks in the reference (nothing compares greater than it), the GPU ignores every NaN
+    o, g = mm(oracle, [nan, 5.0, -1.0]), mm(G, [nan, 5.0, -1.0])
+    assert o[0] != o[0] and o[1] != o[1]
+    assert g[:2] == [5.0, -1.0]
+    # equal-comparing zeros: the reference keeps the first seen (order-dependent); the GPU result compares equal to it
+    g, o = mm(G, [0.0, -0.0]), mm(oracle, [0.0, -0.0])
+    assert g[0] == o[0] == 0.0 and g[1] == o[1] == 0.0
 
 
 def test_zero_rows_zero_groups(G):
