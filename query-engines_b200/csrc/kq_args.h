@@ -120,6 +120,7 @@ struct AggArgs {
     unsigned int* ticket;
     uint32_t* err;
     unsigned int* overflow;                // set when an insert finds the table full (optimistically sized table: the host rolls back and grows)
+    unsigned long long* trace;             // debugging (KQ_FE_PROGRESS=<pinned host address>): last checkpoint per warp of block 0
     // front end
     int32_t fe_groups, fe_nsum, fe_nmm;
     int32_t geo_r, geo_warps;              // tile geometry the host chose for this launch (host-side bookkeeping)

@@ -156,9 +156,9 @@ int kq_check_device_errors(kq_ctx* ctx) {
 // kq_status (and message) for the error bits a kernel raised.
 int kq_device_error_status(kq_ctx* ctx, uint32_t e) {
     if (!e) return KQ_OK;
+    if (e & 0xFF00u) return kq_fail(ctx, KQ_ERR_CUDA, "aggregate kernel gave up (internal protocol error, location bits 0x%x)", e & 0xFF00u);
     if (e & KQ_DEV_ERR_DIV0) return kq_fail(ctx, KQ_ERR_ARITHMETIC, "/ by zero");
     if (e & KQ_DEV_ERR_NUMBER_FORMAT) return kq_fail(ctx, KQ_ERR_NUMBER_FORMAT, "For input string: cannot parse as double");
-    if (e & 8u) return kq_fail(ctx, KQ_ERR_UNSUPPORTED, "Utf8->Float64 cast: value outside the exact fast path (>19 digits, |exp10|>22 or hex float)");
     if (e & KQ_DEV_ERR_LONG_KEY) return kq_fail(ctx, KQ_ERR_UNSUPPORTED, "Utf8 group key longer than 7 bytes is not supported yet");
     return kq_fail(ctx, KQ_ERR_CUDA, "unknown device error bits 0x%x", e);
 }

@@ -225,6 +225,8 @@ struct FinArgs {
     FinKey keys[MAX_KEYS];
     FinAgg aggs[2 * MAX_INPUTS + 4];
     unsigned long long* pos;
+    unsigned long long max_rows;            // rows the output columns were allocated for
+    uint32_t* err;
 };
 
 // Output positions are reserved once per warp and chunk of 1024 table slots (one counter bumped by every warp
@@ -250,6 +252,7 @@ __global__ void k_finalize(const __grid_constant__ FinArgs F) {
         base = __shfl_sync(0xffffffffu, base, 0);
         uint64_t row = base + incl - __popc(mine);
         for (; mine; mine &= mine - 1, row++) {
+            if (row >= F.max_rows) { atomicOr(F.err, 0x4000u); break; }      // more FULL records than the group counter said: never write past the columns
             const uint64_t* rec = F.table + (c0 + (uint64_t)(__ffs(mine) - 1) * 32 + lane) * F.stride;
             const uint32_t nullmask = (uint32_t)(rec[0] >> 32);
             for (int k = 0; k < F.nkeys; k++) {
@@ -400,6 +403,7 @@ static void fill_common_args(kq_hashagg* h, AggArgs& A) {
     A.ticket = (unsigned int*)(h->d_counters + 1);
     A.err = (uint32_t*)(h->d_counters + 5);
     A.overflow = (unsigned int*)(h->d_counters + 4);
+    A.trace = getenv("KQ_FE_PROGRESS") ? (unsigned long long*)strtoull(getenv("KQ_FE_PROGRESS"), nullptr, 0) : nullptr;
     A.stop_threshold = ~0ULL;
 }
 
@@ -607,7 +611,7 @@ static int plan_agg(kq_ctx* ctx, kq_hashagg* h, kq_batch* input, int smem_optin,
         auto fe_bytes = [&](int g, int warps, int dir) {
             return dir * 4 + dir * nkw * 8 + g * nkw * 8 + (g + 1) * nmm1 * 8 + g * 8 + ((g + 3) & ~3) * 4 + warps * (g + 1) * gs;
         };
-        const int budget = smem_optin - 1024;
+        const int budget = smem_optin - 2048;      // static shared memory of the kernel (barriers, tile bookkeeping, directory control): ~1.3 KB
         struct Cand { int r, warps; };
         static const Cand CAND[] = {{4, 8}, {4, 7}, {4, 6}, {2, 8}, {4, 5}, {2, 6}, {4, 4}, {2, 4}, {2, 2}};
         int fr = 0, fw = 0, fs = 0;                                   // tuning experiments: KQ_AGG_GEOM="rows,warps[,stages]"
@@ -719,7 +723,9 @@ static int plan_agg(kq_ctx* ctx, kq_hashagg* h, kq_batch* input, int smem_optin,
     *defines_out = "#define KQ_R " + std::to_string(geo.r) + "\n#define KQ_WARPS " + std::to_string(geo.warps) + "\n#define KQ_STAGES " + std::to_string(A.sp.nstages) + "\n#define KQ_FE_GROUPS " + std::to_string(fg) + "\n#define KQ_DIR_SLOTS " +
                                 std::to_string(dir_slots) + (getenv("KQ_L2_PREFETCH") ? "\n#define KQ_L2_PREFETCH " + std::to_string(atoi(getenv("KQ_L2_PREFETCH"))) : std::string()) +
                                 "\n#define KQ_STAGE_BYTES " + (has_bytes ? "1" : "0") + "\n#define KQ_AGG_MODE " + std::to_string(mode) + "\n" +
-                                (getenv("KQ_PART_L2_HINTS") ? "#define KQ_PART_L2_HINTS " + std::to_string(atoi(getenv("KQ_PART_L2_HINTS"))) + "\n" : std::string());
+                                (getenv("KQ_PART_L2_HINTS") ? "#define KQ_PART_L2_HINTS " + std::to_string(atoi(getenv("KQ_PART_L2_HINTS"))) + "\n" : std::string()) +
+                                (getenv("KQ_FE_CHECK") ? "#define KQ_FE_CHECK 1\n" : "") + (getenv("KQ_FE_NOEXACT") ? "#define KQ_FE_NOEXACT 1\n" : "") +
+                                (getenv("KQ_FE_NOREFRESH") ? "#define KQ_FE_NOREFRESH 1\n" : "") + (getenv("KQ_FE_NOMERGE") ? "#define KQ_FE_NOMERGE 1\n" : "");
     return KQ_OK;
 }
 
@@ -886,7 +892,13 @@ static int hashagg_update_fe(kq_ctx* ctx, kq_hashagg* h, kq_batch* input, int64_
         KQ_CUDA(ctx, cudaLaunchKernel(kernel, dim3(grid), dim3(THREADS), kargs, (size_t)A.smem_bytes, ctx->stream));
         ctx->launches++;
         uint64_t c[6];
-        KQ_RET(read_counters(ctx, h, c));
+        {
+            const int rst = read_counters(ctx, h, c);
+            if (getenv("KQ_TRACE_AGG"))
+                fprintf(stderr, "kq fe launch: tiles [%lld, %lld) grid %d cap %llu optimistic %d -> st %d groups %llu tickets %u overflow %u err 0x%x\n", (long long)tile_begin,
+                        (long long)A.ntiles, grid, (unsigned long long)h->capacity, (int)optimistic, rst, (unsigned long long)c[0], (unsigned)c[1], (unsigned)c[4], (unsigned)c[5]);
+            KQ_RET(rst);
+        }
         if ((uint32_t)c[4] != 0) {
             // the table filled up (the hint was far off): discard this launch and redo its tiles with a table sized for the rows in flight
             if (!optimistic) return kq_fail(ctx, KQ_ERR_ILLEGAL_STATE, "aggregation table overflow");
@@ -1067,6 +1079,8 @@ int kq_hashagg_finalize(kq_ctx* ctx, kq_hashagg* h, kq_batch** out) {
     unsigned long long* d_pos = h->d_counters + 2;
     cudaMemsetAsync(d_pos, 0, 8, ctx->stream);
     F.pos = d_pos;
+    F.max_rows = (unsigned long long)G;
+    F.err = (uint32_t*)(h->d_counters + 5);
     if (G > 0) {
         k_finalize<<<small_grid(ctx, h->capacity), 256, 0, ctx->stream>>>(F);
         if ((st = launch_check(ctx, "k_finalize")) != KQ_OK) return fail(st);

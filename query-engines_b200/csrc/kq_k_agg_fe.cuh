@@ -41,6 +41,10 @@ constexpr int NKW = Q::NKEYS > 0 ? Q::NKEYS : 1;          // key words per group
 constexpr int NMM1 = Q::NMM > 0 ? Q::NMM : 1;
 constexpr int GS = Q::NSUM * 256 + Q::NCNT * 128;         // lane-private bytes per group and warp: [NSUM][32] u64, [NCNT][32] u32
 constexpr int REBUILD_ATTEMPTS = 256;
+// Every wait in this kernel is bounded: a spin that exceeds its budget raises a device error (bits 8..) and gives up, so a
+// protocol bug shows up as a failed query with a location code instead of a hung GPU.
+constexpr uint32_t ERR_SPIN_LOCK = 0x100u, ERR_SPIN_MM = 0x200u, ERR_SPIN_SLOW = 0x400u, ERR_SPIN_STAGE = 0x800u;
+constexpr int SPIN_LIMIT = 1 << 22;
 
 // What the generated code fills per tile: selection, key words and aggregate inputs of the R owned rows.
 struct AggSink {
@@ -73,6 +77,7 @@ struct __align__(16) DirCtl {
 struct Fe {                  // shared-memory addresses (32-bit) and pointers of the CTA front end
     uint32_t a_ctl, a_meta, a_keys;     // DirCtl; [DIR] u32 state; [DIR][NKW] u64 key words
     uint32_t a_mm;                      // [FG + 1][NMM] u64 order-mapped extremes (CTA-shared; row FG is a trash row)
+    uint32_t a_lock, a_bound;           // the CTA lock; [NMM] u64 bounds on the extremes of all groups WITH a value, as the input's own bits
     uint32_t a_lane8, a_lane4;          // this warp's lane-private block + lane * 8 / + NSUM*256 + lane * 4
     DirCtl* ctl;
     uint32_t* meta;
@@ -80,14 +85,39 @@ struct Fe {                  // shared-memory addresses (32-bit) and pointers of
     uint64_t* gkeys;                    // [FG][NKW] dense list of the groups, in insertion order
     uint32_t* gnm;                      // [FG] their key null masks
     uint64_t* mm;
-    uint64_t* bound;                    // [NMM] bound on the extremes of all groups WITH a value, as the input's own bits
-    uint32_t* lock;
     uint32_t* limit;                    // no more inserts at this many groups (FG, or fewer after a failed rebuild)
+    uint32_t* err;                      // the aggregate's device error word
+    unsigned long long* trace;          // debugging (AggArgs::trace)
 };
+#define KQ_FTRACE(code) do { if (fe.trace && blockIdx.x < 16 && (threadIdx.x & 31) == 0) reinterpret_cast<volatile unsigned long long*>(fe.trace)[blockIdx.x * 16 + (threadIdx.x >> 5)] = (unsigned long long)(code); \
+                             if (fe.trace && blockIdx.x == 0 && (threadIdx.x >> 5) == 1) reinterpret_cast<volatile unsigned long long*>(fe.trace)[256 + (threadIdx.x & 31)] = (unsigned long long)(code); } while (0)
 
 __device__ __forceinline__ uint32_t lds_u32(uint32_t a) { uint32_t v; asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(a)); return v; }
 __device__ __forceinline__ uint64_t lds_u64(uint32_t a) { uint64_t v; asm volatile("ld.shared.u64 %0, [%1];" : "=l"(v) : "r"(a)); return v; }
 __device__ __forceinline__ uint4 lds_u128(uint32_t a) { uint4 r; asm volatile("ld.shared.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w) : "r"(a)); return r; }
+
+// Shared-space atomics and volatile accesses by 32-bit shared address: no generic-address atomics on shared memory anywhere
+// in this kernel (what the compiler emits for those differs per width — a native ATOM.E for 32 bits, a QSPC test plus a
+// fallback for 64 — and none of it is needed when the state space is known).
+__device__ __forceinline__ uint32_t sh_cas_u32(uint32_t a, uint32_t cmp, uint32_t val) { uint32_t old; asm volatile("atom.shared.cas.b32 %0, [%1], %2, %3;" : "=r"(old) : "r"(a), "r"(cmp), "r"(val) : "memory"); return old; }
+__device__ __forceinline__ uint32_t sh_exch_u32(uint32_t a, uint32_t val) { uint32_t old; asm volatile("atom.shared.exch.b32 %0, [%1], %2;" : "=r"(old) : "r"(a), "r"(val) : "memory"); return old; }
+__device__ __forceinline__ uint64_t sh_cas_u64(uint32_t a, uint64_t cmp, uint64_t val) { uint64_t old; asm volatile("atom.shared.cas.b64 %0, [%1], %2, %3;" : "=l"(old) : "r"(a), "l"(cmp), "l"(val) : "memory"); return old; }
+// 64-bit MIN/MAX as an explicit compare-and-swap loop (the value only ever moves one way, so the loop is bounded by the
+// number of competing writers)
+__device__ __forceinline__ void sh_min_u64(uint32_t a, uint64_t v) {
+    uint64_t cur = 0;
+    asm volatile("ld.volatile.shared.u64 %0, [%1];" : "=l"(cur) : "r"(a) : "memory");
+    for (int i = 0; i < 4096 && v < cur; i++) { const uint64_t old = sh_cas_u64(a, cur, v); if (old == cur) break; cur = old; }
+}
+__device__ __forceinline__ void sh_max_u64(uint32_t a, uint64_t v) {
+    uint64_t cur = 0;
+    asm volatile("ld.volatile.shared.u64 %0, [%1];" : "=l"(cur) : "r"(a) : "memory");
+    for (int i = 0; i < 4096 && v > cur; i++) { const uint64_t old = sh_cas_u64(a, cur, v); if (old == cur) break; cur = old; }
+}
+__device__ __forceinline__ uint32_t sh_ld_u32(uint32_t a) { uint32_t v; asm volatile("ld.volatile.shared.u32 %0, [%1];" : "=r"(v) : "r"(a) : "memory"); return v; }
+__device__ __forceinline__ uint64_t sh_ld_u64(uint32_t a) { uint64_t v; asm volatile("ld.volatile.shared.u64 %0, [%1];" : "=l"(v) : "r"(a) : "memory"); return v; }
+__device__ __forceinline__ void sh_st_u32(uint32_t a, uint32_t v) { asm volatile("st.volatile.shared.u32 [%0], %1;" ::"r"(a), "r"(v) : "memory"); }
+__device__ __forceinline__ void sh_st_u64(uint32_t a, uint64_t v) { asm volatile("st.volatile.shared.u64 [%0], %1;" ::"r"(a), "l"(v) : "memory"); }
 
 // identities of the CTA-shared extremes, in order-mapped form (never produced by a non-NaN value)
 __device__ __forceinline__ constexpr uint64_t mm_identity(int m) { return ((Q::MM_ISMIN >> m) & 1u) ? ~0ULL : 0ULL; }
@@ -113,27 +143,53 @@ __device__ __forceinline__ uint32_t dir_slot(const uint64_t (&kw)[NKW], uint32_t
     return h >> DIR_SHIFT;
 }
 
+// The directory control block as ONE value for the whole warp. Lanes of a warp need not run in lockstep: each would read
+// the (concurrently changing) block at its own time, and a branch on such a value that encloses warp-synchronising
+// operations would split the warp for good. Every shared value that steers warp-level control flow is therefore read by
+// lane 0 and broadcast.
+__device__ __forceinline__ uint4 ctl_snapshot(const Fe& fe) {
+    uint4 c;                                  // {gen, s1, s2, count}: volatile — other warps change it
+    asm volatile("ld.volatile.shared.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(c.x), "=r"(c.y), "=r"(c.z), "=r"(c.w) : "r"(fe.a_ctl) : "memory");
+    c.x = __shfl_sync(0xffffffffu, c.x, 0); c.y = __shfl_sync(0xffffffffu, c.y, 0);
+    c.z = __shfl_sync(0xffffffffu, c.z, 0); c.w = __shfl_sync(0xffffffffu, c.w, 0);
+    return c;
+}
+__device__ __forceinline__ uint32_t sh_ld_u32_uniform(uint32_t a) { return __shfl_sync(0xffffffffu, sh_ld_u32(a), 0); }
+
 // One lock-free probe of the home slot: group id, or -1. Valid only if ctl->gen did not move meanwhile (caller checks).
+template <bool AGAIN = false>          // AGAIN: a repeated probe (the general path) must not be satisfied from registers
 __device__ __forceinline__ int dir_probe(const Fe& fe, const uint64_t (&kw)[NKW], uint32_t nm, uint32_t s1, uint32_t s2) {
     const uint32_t slot = dir_slot(kw, nm, s1, s2);
-    const uint32_t m = lds_u32(fe.a_meta + slot * 4u);
+    const uint32_t m = AGAIN ? sh_ld_u32(fe.a_meta + slot * 4u) : lds_u32(fe.a_meta + slot * 4u);
     bool hit = true;
 #pragma unroll
-    for (int k = 0; k < NKW; k++) hit &= lds_u64(fe.a_keys + slot * (8u * NKW) + 8u * k) == kw[k];
+    for (int k = 0; k < NKW; k++) hit &= (AGAIN ? sh_ld_u64(fe.a_keys + slot * (8u * NKW) + 8u * k) : lds_u64(fe.a_keys + slot * (8u * NKW) + 8u * k)) == kw[k];
     const uint32_t x = Q::KEYS_NULLABLE ? m ^ (nm << 8) : m;
     const uint32_t g = x - 1u;                 // state: 0 = empty, else (gid + 1) | null mask << 8
     return (hit && g < (uint32_t)FG) ? (int)g : -1;
 }
 
-__device__ __forceinline__ void fe_lock(const Fe& fe, int lane) {
-    if (lane == 0) { while (atomicCAS(fe.lock, 0u, 1u) != 0u) __nanosleep(64); }
+// The CTA lock is only ever taken by a whole, converged warp (lane 0 spins, the rest wait at the warp barrier): no thread
+// of a warp ever waits for a lock that another thread of the same warp holds.
+__device__ __forceinline__ void fe_lock(const Fe& fe, int lane, uint32_t site = 1u) {
+    if (lane == 0) {
+        int spins = 0;
+        const uint32_t token = 0x100u + site * 16u + (threadIdx.x >> 5);       // who holds it (debugging: a waiter can tell)
+        uint32_t held;
+        while ((held = sh_cas_u32(fe.a_lock, 0u, token)) != 0u) {
+            __nanosleep(64);
+            ++spins;
+            if ((spins & 0xFFFF) == 0) KQ_FTRACE(0x800000u | held);
+            if (spins > SPIN_LIMIT) { atomicOr(fe.err, ERR_SPIN_LOCK); break; }
+        }
+    }
     __syncwarp();
     __threadfence_block();
 }
 __device__ __forceinline__ void fe_unlock(const Fe& fe, int lane) {
     __threadfence_block();
     __syncwarp();
-    if (lane == 0) atomicExch(fe.lock, 0u);
+    if (lane == 0) sh_exch_u32(fe.a_lock, 0u);
 }
 
 // Place groups [0, n) under the multipliers (s1, s2). Whole warp, under the lock, gen odd. false on any collision.
@@ -147,7 +203,7 @@ __device__ __forceinline__ bool dir_place_all(const Fe& fe, int n, uint32_t s1, 
         for (int k = 0; k < NKW; k++) kw[k] = fe.gkeys[g * NKW + k];
         const uint32_t nm = fe.gnm[g];
         const uint32_t slot = dir_slot(kw, nm, s1, s2);
-        if (atomicCAS(fe.meta + slot, 0u, (uint32_t)(g + 1) | (nm << 8)) != 0u) ok = false;
+        if (sh_cas_u32(fe.a_meta + slot * 4u, 0u, (uint32_t)(g + 1) | (nm << 8)) != 0u) ok = false;
         else {
 #pragma unroll
             for (int k = 0; k < NKW; k++) fe.keys[slot * NKW + k] = kw[k];
@@ -158,10 +214,12 @@ __device__ __forceinline__ bool dir_place_all(const Fe& fe, int n, uint32_t s1, 
 
 // Group id of key (kw, nm), inserting it while there is room; -1: the directory cannot take it (the row goes to the
 // global table). Called by ALL lanes of a warp with the same key.
-__device__ __noinline__ int dir_find_or_insert(const Fe& fe, const uint64_t (&kw)[NKW], uint32_t nm, int lane) {
+__device__ __forceinline__ int dir_find_or_insert(const Fe& fe, const uint64_t (&kw)[NKW], uint32_t nm, int lane) {
+    KQ_FTRACE(0x600000);
     fe_lock(fe, lane);
+    KQ_FTRACE(0x600001);
     volatile DirCtl* ctl = fe.ctl;
-    const int n = (int)ctl->count;
+    const int n = (int)sh_ld_u32_uniform(fe.a_ctl + 12u);
     int found = -1;
     for (int g = lane; g < n; g += 32) {
         bool eq = *reinterpret_cast<volatile uint32_t*>(fe.gnm + g) == nm;
@@ -169,9 +227,12 @@ __device__ __noinline__ int dir_find_or_insert(const Fe& fe, const uint64_t (&kw
         for (int k = 0; k < NKW; k++) eq &= *reinterpret_cast<volatile uint64_t*>(fe.gkeys + g * NKW + k) == kw[k];
         if (eq) found = g;
     }
+    KQ_FTRACE(0x600002 + n * 256);
     const uint32_t f = __ballot_sync(0xffffffffu, found >= 0);
     int gid = f ? __shfl_sync(0xffffffffu, found, __ffs(f) - 1) : -1;
-    if (!f && n < (int)*reinterpret_cast<volatile uint32_t*>(fe.limit)) {
+    KQ_FTRACE(0x600003 + n * 256);
+    const int limit = (int)__shfl_sync(0xffffffffu, *reinterpret_cast<volatile uint32_t*>(fe.limit), 0);
+    if (!f && n < limit) {
         gid = n;
         if (lane == 0) {
 #pragma unroll
@@ -179,9 +240,9 @@ __device__ __noinline__ int dir_find_or_insert(const Fe& fe, const uint64_t (&kw
             fe.gnm[n] = nm;
         }
         __syncwarp();
-        uint32_t s1 = ctl->s1, s2 = ctl->s2;
+        uint32_t s1 = sh_ld_u32_uniform(fe.a_ctl + 4u), s2 = sh_ld_u32_uniform(fe.a_ctl + 8u);
         const uint32_t slot = dir_slot(kw, nm, s1, s2);
-        if (*reinterpret_cast<volatile uint32_t*>(fe.meta + slot) == 0u) {
+        if (sh_ld_u32_uniform(fe.a_meta + slot * 4u) == 0u) {
             // the home slot is free: publish keys, then the state word (readers that miss meanwhile come here and find it)
             if (lane == 0) {
 #pragma unroll
@@ -192,6 +253,7 @@ __device__ __noinline__ int dir_find_or_insert(const Fe& fe, const uint64_t (&kw
             }
         } else {
             // collision: new multipliers until every key of the directory sits in its home slot
+            KQ_FTRACE(0x600004 + n * 256);
             if (lane == 0) ctl->gen = ctl->gen + 1u;          // odd: probes in flight are void
             __threadfence_block();
             __syncwarp();
@@ -215,74 +277,96 @@ __device__ __noinline__ int dir_find_or_insert(const Fe& fe, const uint64_t (&kw
             if (lane == 0) { ctl->s1 = t1; ctl->s2 = t2; ctl->count = (uint32_t)(placed ? n + 1 : n); __threadfence_block(); ctl->gen = ctl->gen + 1u; }
         }
     }
+    KQ_FTRACE(0x600005 + n * 256);
     fe_unlock(fe, lane);
+    KQ_FTRACE(0x600006 + n * 256);
     return gid;
 }
 
-// Exact MIN/MAX update of the CTA-shared extreme (gid, slot m) with value bits v (not NaN for Float64).
-__device__ __noinline__ void mm_update(const Fe& fe, int gid, int m, uint64_t v, bool is_int) {
-    const uint64_t x = order_map(v, is_int);
-    unsigned long long* p = reinterpret_cast<unsigned long long*>(fe.mm + gid * NMM1 + m);
-    const bool ismin = (Q::MM_ISMIN >> m) & 1u;
-    const uint64_t cur = *reinterpret_cast<volatile unsigned long long*>(p);
-    if (cur == mm_identity(m)) {
-        // first value of this group CTA-wide: no bound computed so far covers the group. Reset the bound BEFORE the value
-        // becomes visible; both under the lock that bound refreshes take. The lock is per THREAD here and several lanes of a
-        // warp may want it at once: the critical section sits INSIDE the retry loop, so the lane that wins never waits at
-        // a reconvergence point for the lanes that lost (the SIMT spin-lock deadlock).
-        bool done = false;
-        while (!done) {
-            if (atomicCAS(fe.lock, 0u, 1u) == 0u) {
-                __threadfence_block();
-                *reinterpret_cast<volatile uint64_t*>(fe.bound + m) = bound_none(m, is_int);
-                __threadfence_block();
-                if (ismin) atomicMin(p, (unsigned long long)x); else atomicMax(p, (unsigned long long)x);
-                __threadfence_block();
-                atomicExch(fe.lock, 0u);
-                done = true;
-            } else __nanosleep(32);
+// ---- the exact MIN/MAX path (rare) --------------------------------------------------------------------------------------
+// Sentinels of the CTA-shared extremes (order-mapped): the identity = "no non-null value yet"; a second NaN-patterned value
+// = "only NaNs so far" (any real value replaces it; while a group holds it the refreshed bound is a NaN, so every row
+// takes the exact path — correct, slow, and only for as long as a group has seen nothing but NaNs).
+__device__ __forceinline__ constexpr uint64_t mm_nan_mark(int m) { return ((Q::MM_ISMIN >> m) & 1u) ? ~0ULL - 1ULL : 1ULL; }
+
+// Does row r of this lane touch an extreme that still holds the identity (the group's first value CTA-wide)?
+__device__ __forceinline__ bool fe_exact_needs_lock(const Fe& fe, int gid, const AggSink& sink, int r) {
+    bool need = false;
+#pragma unroll
+    for (int i = 0; i < Q::NIN; i++) {
+        const int FL = Q::IN_FLAGS[i];
+        if (!(FL & (F_MIN | F_MAX))) continue;
+        if (Q::IN_CNT[i] > 0 && !((sink.inok[i] >> r) & 1u)) continue;
+        if (FL & F_MIN) need |= sh_ld_u64(fe.a_mm + (uint32_t)(gid * NMM1 + Q::FE_MIN[i]) * 8u) == mm_identity(Q::FE_MIN[i] < 0 ? 0 : Q::FE_MIN[i]);
+        if (FL & F_MAX) need |= sh_ld_u64(fe.a_mm + (uint32_t)(gid * NMM1 + Q::FE_MAX[i]) * 8u) == mm_identity(Q::FE_MAX[i] < 0 ? 0 : Q::FE_MAX[i]);
+    }
+    return need;
+}
+// The exact update of one row: shared-memory reductions on the order-mapped values. A NaN never replaces a held value
+// (Main.kt:552: `value > this.value`); meeting the identity it leaves the NaN mark (the caller holds the CTA lock then).
+__device__ __forceinline__ void fe_exact_row(const Fe& fe, int gid, const AggSink& sink, int r) {
+#pragma unroll
+    for (int i = 0; i < Q::NIN; i++) {
+        const int FL = Q::IN_FLAGS[i];
+        if (!(FL & (F_MIN | F_MAX))) continue;
+        if (Q::IN_CNT[i] > 0 && !((sink.inok[i] >> r) & 1u)) continue;
+        const uint64_t v = sink.in[i][r];
+        const bool is_int = (FL & F_INT) != 0;
+        const bool isnan = !is_int && as_f64(v) != as_f64(v);
+        const uint64_t x = order_map(v, is_int);
+        if (FL & F_MIN) {
+            const uint32_t a = fe.a_mm + (uint32_t)(gid * NMM1 + Q::FE_MIN[i]) * 8u;
+            if (isnan) sh_cas_u64(a, mm_identity(Q::FE_MIN[i] < 0 ? 0 : Q::FE_MIN[i]), mm_nan_mark(Q::FE_MIN[i] < 0 ? 0 : Q::FE_MIN[i]));
+            else if (x < sh_ld_u64(a)) sh_min_u64(a, x);
         }
-    } else if (ismin ? x < cur : x > cur) {
-        if (ismin) atomicMin(p, (unsigned long long)x); else atomicMax(p, (unsigned long long)x);
+        if (FL & F_MAX) {
+            const uint32_t a = fe.a_mm + (uint32_t)(gid * NMM1 + Q::FE_MAX[i]) * 8u;
+            if (isnan) sh_cas_u64(a, mm_identity(Q::FE_MAX[i] < 0 ? 0 : Q::FE_MAX[i]), mm_nan_mark(Q::FE_MAX[i] < 0 ? 0 : Q::FE_MAX[i]));
+            else if (x > sh_ld_u64(a)) sh_max_u64(a, x);
+        }
     }
 }
-
-// A NaN met the identity: the group now "has a value" as far as first-value detection goes (its lanes' later rows are
-// not first rows any more), so mark it with a second NaN-patterned sentinel that any real value replaces. While a
-// group holds the sentinel the refreshed bound is a NaN, i.e. every row takes the exact path — correct, slow, and only
-// for as long as a group has seen nothing but NaNs.
-__device__ __noinline__ void mm_mark_nan(const Fe& fe, int gid, int m) {
-    unsigned long long* p = reinterpret_cast<unsigned long long*>(fe.mm + gid * NMM1 + m);
-    if (*reinterpret_cast<volatile unsigned long long*>(p) != mm_identity(m)) return;
-    const bool ismin = (Q::MM_ISMIN >> m) & 1u;
-    bool done = false;
-    while (!done) {                 // critical section inside the retry loop: see mm_update
-        if (atomicCAS(fe.lock, 0u, 1u) == 0u) {
-            __threadfence_block();
-            *reinterpret_cast<volatile uint64_t*>(fe.bound + m) = bound_none(m, false);
-            __threadfence_block();
-            atomicCAS(p, (unsigned long long)mm_identity(m), ismin ? ~0ULL - 1ULL : 1ULL);
-            __threadfence_block();
-            atomicExch(fe.lock, 0u);
-            done = true;
-        } else __nanosleep(32);
+// All exact rows of a warp's tile (`rows`: this lane's R-bit mask; gid[r] valid for those). Called by the WHOLE warp.
+// When some row brings a group's first value, the warp takes the CTA lock and resets the bounds BEFORE any value becomes
+// visible (a bound computed earlier does not cover that group; refreshes take the same lock), then everybody updates.
+__device__ __forceinline__ void fe_exact_rows(const Fe& fe, const uint32_t (&gid)[R], uint32_t rows, const AggSink& sink, int lane) {
+    bool need = false;
+#pragma unroll
+    for (int r = 0; r < R; r++) if ((rows >> r) & 1u) need |= fe_exact_needs_lock(fe, (int)gid[r], sink, r);
+    KQ_FTRACE(0x700000);
+    const bool locked = __any_sync(0xffffffffu, need);
+    KQ_FTRACE(0x700001 + (locked ? 16 : 0));
+    if (locked) {
+        fe_lock(fe, lane, 2u);
+        if (lane == 0) {
+#pragma unroll
+            for (int m = 0; m < Q::NMM; m++) sh_st_u64(fe.a_bound + 8u * m, bound_none(m, mm_is_int(m)));
+        }
+        __threadfence_block();
+        __syncwarp();
     }
+#pragma unroll
+    for (int r = 0; r < R; r++) if ((rows >> r) & 1u) fe_exact_row(fe, (int)gid[r], sink, r);
+    KQ_FTRACE(0x700002);
+    if (locked) fe_unlock(fe, lane);
+    KQ_FTRACE(0x700003);
 }
 
 // Recompute the bounds from the extremes of all groups that have a value (one warp, every few tiles, under the lock).
-__device__ __noinline__ void mm_bound_refresh(const Fe& fe, int lane) {
-    if (lane == 0 && atomicCAS(fe.lock, 0u, 1u) != 0u) lane = -1;          // somebody is inserting: try again later
-    if (__shfl_sync(0xffffffffu, lane, 0) < 0) return;
+__device__ __forceinline__ void mm_bound_refresh(const Fe& fe, int lane) {
+    uint32_t got = 1u;
+    if (lane == 0) got = sh_cas_u32(fe.a_lock, 0u, 0x130u + (threadIdx.x >> 5));          // somebody is inserting: try again later
+    if (__shfl_sync(0xffffffffu, got, 0) != 0u) return;
     __threadfence_block();
-    const int n = (int)*reinterpret_cast<volatile uint32_t*>(&fe.ctl->count);
+    const int n = (int)sh_ld_u32_uniform(fe.a_ctl + 12u);
 #pragma unroll
     for (int m = 0; m < Q::NMM; m++) {
         const bool ismin = (Q::MM_ISMIN >> m) & 1u, is_int = mm_is_int(m);
         uint64_t b = ismin ? 0ULL : ~0ULL;               // MIN: the largest group minimum; MAX: the smallest group maximum (order-mapped)
         bool any = false, none = false;
         for (int g = lane; g < n; g += 32) {
-            const uint64_t x = *reinterpret_cast<volatile uint64_t*>(fe.mm + g * NMM1 + m);
-            if (x == mm_identity(m)) { if (is_int) none = true; continue; }      // Int64: the identity is also a value (kq_k_agg_fe.cuh header)
+            const uint64_t x = sh_ld_u64(fe.a_mm + (uint32_t)(g * NMM1 + m) * 8u);
+            if (x == mm_identity(m)) { if (is_int) none = true; continue; }      // Int64: the identity is also a value: no bound then
             any = true;
             b = ismin ? (x > b ? x : b) : (x < b ? x : b);
         }
@@ -292,11 +376,9 @@ __device__ __noinline__ void mm_bound_refresh(const Fe& fe, int lane) {
             b = ismin ? (y > b ? y : b) : (y < b ? y : b);
         }
         any = __any_sync(0xffffffffu, any) && !__any_sync(0xffffffffu, none);
-        if (lane == 0) *reinterpret_cast<volatile uint64_t*>(fe.bound + m) = any ? order_unmap(b, is_int) : bound_none(m, is_int);
+        if (lane == 0) sh_st_u64(fe.a_bound + 8u * m, any ? order_unmap(b, is_int) : bound_none(m, is_int));
     }
-    __threadfence_block();
-    __syncwarp();
-    if (lane == 0) atomicExch(fe.lock, 0u);
+    fe_unlock(fe, lane);
 }
 
 // Accumulate one row into the lane-private slots of group g (FG = trash) — the branch-free per-row path. All loads of
@@ -350,25 +432,6 @@ __device__ __forceinline__ bool fe_accumulate_row(const Fe& fe, uint32_t g, cons
     return exact;
 }
 
-// The exact MIN/MAX path of one row (rare).
-__device__ __forceinline__ void fe_exact_row(const Fe& fe, int gid, const AggSink& sink, int r) {
-#pragma unroll
-    for (int i = 0; i < Q::NIN; i++) {
-        const int FL = Q::IN_FLAGS[i];
-        if (!(FL & (F_MIN | F_MAX))) continue;
-        if (Q::IN_CNT[i] > 0 && !((sink.inok[i] >> r) & 1u)) continue;
-        const uint64_t v = sink.in[i][r];
-        const bool is_int = (FL & F_INT) != 0;
-        if (!is_int && as_f64(v) != as_f64(v)) {                    // NaN never replaces a held value (Main.kt:552: `value > this.value`)
-            if (FL & F_MIN) mm_mark_nan(fe, gid, Q::FE_MIN[i]);
-            if (FL & F_MAX) mm_mark_nan(fe, gid, Q::FE_MAX[i]);
-            continue;
-        }
-        if (FL & F_MIN) mm_update(fe, gid, Q::FE_MIN[i], v, is_int);
-        if (FL & F_MAX) mm_update(fe, gid, Q::FE_MAX[i], v, is_int);
-    }
-}
-
 template <int I>
 __device__ __forceinline__ void global_accumulate_all(const AggArgs& A, uint64_t* rec, const AggSink& sink, int r) {
     if constexpr (I < Q::NIN) {
@@ -403,6 +466,10 @@ __device__ __forceinline__ void fe_merge_input(uint32_t a_warp, uint64_t* rec, i
     }
 }
 
+// debugging: the last checkpoint every warp of blocks 0..15 reached, written to pinned host memory (readable while the kernel hangs)
+#define KQ_TRACE(code) do { if (A.trace && blockIdx.x < 16 && (threadIdx.x & 31) == 0) reinterpret_cast<volatile unsigned long long*>(A.trace)[blockIdx.x * 16 + (threadIdx.x >> 5)] = (unsigned long long)(code); \
+                            if (A.trace && blockIdx.x == 0 && (threadIdx.x >> 5) == 1) reinterpret_cast<volatile unsigned long long*>(A.trace)[256 + (threadIdx.x & 31)] = (unsigned long long)(code); } while (0)
+
 extern "C" __global__ void __launch_bounds__(THREADS, 1) kq_group_aggregate(const __grid_constant__ AggArgs A) {
     // dynamic shared memory: [S stages][directory state][directory keys][dense keys][dense null masks][extremes][gslot]
     //                        [per-warp lane-private blocks of FG + 1 groups]
@@ -426,8 +493,9 @@ extern "C" __global__ void __launch_bounds__(THREADS, 1) kq_group_aggregate(cons
     fe.gnm = reinterpret_cast<uint32_t*>(p0);             p0 += (size_t)((FG + 3) & ~3) * 4;
     unsigned char* lane_blocks = p0;                      p0 += (size_t)WARPS * (FG + 1) * GS;
     const size_t fe_end = (size_t)(p0 - smem);
-    fe.ctl = &s_ctl; fe.lock = &s_lock; fe.limit = &s_limit; fe.bound = s_bound;
+    fe.ctl = &s_ctl; fe.limit = &s_limit; fe.err = A.err; fe.trace = A.trace;
     fe.a_ctl = smem_u32(&s_ctl); fe.a_meta = smem_u32(fe.meta); fe.a_keys = smem_u32(fe.keys); fe.a_mm = smem_u32(fe.mm);
+    fe.a_lock = smem_u32(&s_lock); fe.a_bound = smem_u32(s_bound);
     const uint32_t a_warp = smem_u32(lane_blocks) + (uint32_t)(warp < 0 ? 0 : warp) * (uint32_t)((FG + 1) * GS);
     fe.a_lane8 = a_warp + (uint32_t)lane * 8u;
     fe.a_lane4 = a_warp + (uint32_t)Q::NSUM * 256u + (uint32_t)lane * 4u;
@@ -463,7 +531,7 @@ extern "C" __global__ void __launch_bounds__(THREADS, 1) kq_group_aggregate(cons
             long long next = take();
             for (int kp = 0;; kp++) {
                 const int s = kp % S;
-                while (!mbar_test(&empty[s], ((kp / S) & 1) ^ 1)) __nanosleep(32);
+                { int spins = 0; while (!mbar_test(&empty[s], ((kp / S) & 1) ^ 1)) { __nanosleep(32); if (++spins > SPIN_LIMIT) { atomicOr(A.err, ERR_SPIN_STAGE); break; } } }
                 const long long tile = next;
                 tile_of[s] = tile;
                 if (tile < 0) { mbar_arrive(&full[s]); break; }
@@ -477,8 +545,13 @@ extern "C" __global__ void __launch_bounds__(THREADS, 1) kq_group_aggregate(cons
         int low_tiles = 0;
         for (int k = 0;; k++) {
             const int s = k % S;
-            mbar_wait(&full[s], (k / S) & 1);
+            {
+                int spins = 0;
+                while (!mbar_try_wait(&full[s], (k / S) & 1)) { if (++spins > SPIN_LIMIT) { if (lane == 0) atomicOr(A.err, ERR_SPIN_STAGE); break; } }
+                if (spins > SPIN_LIMIT) break;
+            }
             const long long tile = tile_of[s];
+            KQ_TRACE(0x100000 + k * 16 + 1);
             if (tile < 0) break;
             RowCtx rc;
             rowctx_init(rc, warp, tile, TILE, A.n, A.err, smem + (size_t)s * A.sp.stage_bytes);
@@ -492,6 +565,7 @@ extern "C" __global__ void __launch_bounds__(THREADS, 1) kq_group_aggregate(cons
             Q::eval(A.q, rc, sink);
             __syncwarp();
             if (lane == 0) mbar_arrive(&empty[s]);       // everything needed is in registers now
+            KQ_TRACE(0x100000 + k * 16 + 2);
 
             // canonical key words + null masks of the R owned rows
             uint32_t nm[R];
@@ -512,7 +586,7 @@ extern "C" __global__ void __launch_bounds__(THREADS, 1) kq_group_aggregate(cons
             uint32_t gsel[R];                         // group id, FG (trash) for rows that are filtered out or unresolved
             uint32_t slow = sink.sel;                 // rows that still need the general path
             if (!bypass) {
-                const uint4 c = lds_u128(fe.a_ctl);   // {gen, s1, s2, count}
+                const uint4 c = ctl_snapshot(fe);     // {gen, s1, s2, count}
                 uint32_t miss = 0;
 #pragma unroll
                 for (int r = 0; r < R; r++) {
@@ -524,7 +598,7 @@ extern "C" __global__ void __launch_bounds__(THREADS, 1) kq_group_aggregate(cons
                     gsel[r] = (on && g >= 0) ? (uint32_t)g : (uint32_t)FG;
                     miss |= (uint32_t)(on && g < 0) << r;
                 }
-                const uint32_t gen2 = *reinterpret_cast<volatile uint32_t*>(&s_ctl.gen);
+                const uint32_t gen2 = sh_ld_u32_uniform(fe.a_ctl);
                 if (gen2 != c.x || (c.x & 1u)) {      // a rebuild ran meanwhile: nothing probed counts
 #pragma unroll
                     for (int r = 0; r < R; r++) gsel[r] = (uint32_t)FG;
@@ -536,10 +610,15 @@ extern "C" __global__ void __launch_bounds__(THREADS, 1) kq_group_aggregate(cons
                 for (int r = 0; r < R; r++) gsel[r] = (uint32_t)FG;
             }
 
+#ifdef KQ_FE_CHECK
+#pragma unroll
+            for (int r = 0; r < R; r++) if (gsel[r] > (uint32_t)FG) { atomicOr(A.err, 0x1000u); gsel[r] = (uint32_t)FG; }
+#endif
             // ---- accumulate (branch-free); bounds are read AFTER the probes: they cover every group probed -----------
+            KQ_TRACE(0x100000 + k * 16 + 3);
             uint64_t bnd[NMM1];
 #pragma unroll
-            for (int m = 0; m < Q::NMM; m++) bnd[m] = *reinterpret_cast<volatile uint64_t*>(s_bound + m);
+            for (int m = 0; m < Q::NMM; m++) bnd[m] = sh_ld_u64(fe.a_bound + 8u * m);
             uint32_t exact = 0;
             bool many_exact = false;
             if (!bypass) {
@@ -550,26 +629,31 @@ extern "C" __global__ void __launch_bounds__(THREADS, 1) kq_group_aggregate(cons
                     onmask |= (uint32_t)on << r;
                     exact |= (uint32_t)(fe_accumulate_row(fe, gsel[r], sink, r, bnd) && on) << r;
                 }
+#ifdef KQ_FE_NOEXACT
+                exact = 0;
+#endif
                 if (Q::NMM > 0 && __any_sync(0xffffffffu, exact != 0)) {
                     // a lane that took the exact path may have met a group no bound covers yet (first value): the flags of its
                     // other rows were computed against a possibly stale bound, so all its rows take the exact path
                     if (exact) exact = onmask;
                     many_exact = __popc(__ballot_sync(0xffffffffu, exact != 0)) >= 8;
-#pragma unroll
-                    for (int r = 0; r < R; r++)
-                        if ((exact >> r) & 1u) fe_exact_row(fe, (int)gsel[r], sink, r);
+                    fe_exact_rows(fe, gsel, exact, sink, lane);
                 }
             }
 
             // ---- general path: keys that are not in the directory (yet) ------------------------------------------------
+            KQ_TRACE(0x100000 + k * 16 + 4);
             uint32_t new_groups = 0;
             const int rows = __popc(sink.sel);
             int fe_hits = rows - __popc(slow);
+            int rounds = 0;
             while (__any_sync(0xffffffffu, slow != 0)) {
+                if (++rounds > 64 * R + 4096) { if (lane == 0) atomicOr(A.err, ERR_SPIN_SLOW); break; }      // each round resolves a row or inserts a key
+                KQ_TRACE(0x200000 + rounds * 256 + (slow & 0xff));
                 bool full_dir = true;
                 if (!bypass) {
                     // look again: another warp may have inserted the key meanwhile (no lock needed for that)
-                    const uint4 c = lds_u128(fe.a_ctl);
+                    const uint4 c = ctl_snapshot(fe);
                     int g2[R];
 #pragma unroll
                     for (int r = 0; r < R; r++) {
@@ -578,24 +662,28 @@ extern "C" __global__ void __launch_bounds__(THREADS, 1) kq_group_aggregate(cons
                             uint64_t kw[NKW];
 #pragma unroll
                             for (int k2 = 0; k2 < NKW; k2++) kw[k2] = sink.key[k2][r];
-                            g2[r] = dir_probe(fe, kw, nm[r], c.y, c.z);
+                            g2[r] = dir_probe<true>(fe, kw, nm[r], c.y, c.z);
                         }
                     }
-                    const uint32_t gen2 = *reinterpret_cast<volatile uint32_t*>(&s_ctl.gen);
+                    const uint32_t gen2 = sh_ld_u32_uniform(fe.a_ctl);
                     const bool valid = gen2 == c.x && !(c.x & 1u);
-                    full_dir = valid && c.w >= *reinterpret_cast<volatile uint32_t*>(&s_limit);
+                    full_dir = valid && c.w >= sh_ld_u32_uniform(smem_u32(&s_limit));
                     if (valid) {
                         uint64_t nb[NMM1];
 #pragma unroll
                         for (int m = 0; m < NMM1; m++) nb[m] = 0;
+                        uint32_t hitrows = 0, gh[R];
 #pragma unroll
                         for (int r = 0; r < R; r++) {
+                            gh[r] = (uint32_t)FG;
                             if (g2[r] < 0) continue;
-                            fe_accumulate_row(fe, (uint32_t)g2[r], sink, r, nb);
-                            if (Q::NMM > 0) fe_exact_row(fe, g2[r], sink, r);       // rare path: always the exact compare
+                            gh[r] = (uint32_t)g2[r];
+                            fe_accumulate_row(fe, gh[r], sink, r, nb);
+                            hitrows |= 1u << r;
                             slow &= ~(1u << r);
                             fe_hits++;
                         }
+                        if (Q::NMM > 0 && __any_sync(0xffffffffu, hitrows != 0)) fe_exact_rows(fe, gh, hitrows, sink, lane);      // rare path: always the exact compare
                     }
                     if (!__any_sync(0xffffffffu, slow != 0)) break;
                 }
@@ -629,7 +717,9 @@ extern "C" __global__ void __launch_bounds__(THREADS, 1) kq_group_aggregate(cons
 #pragma unroll
                 for (int k2 = 0; k2 < NKW; k2++) kw[k2] = __shfl_sync(0xffffffffu, kw[k2], leader);
                 knm = __shfl_sync(0xffffffffu, knm, leader);
+                KQ_TRACE(0x300000 + rounds * 256 + leader);
                 const int g = dir_find_or_insert(fe, kw, knm, lane);
+                KQ_TRACE(0x400000 + rounds * 256 + (g & 0xff));
                 if (g < 0 && lane == leader) {
                     // not insertable (directory full or unplaceable): this row goes to the global table now
                     uint64_t kg[MAX_KEYS];
@@ -642,15 +732,19 @@ extern "C" __global__ void __launch_bounds__(THREADS, 1) kq_group_aggregate(cons
                 }
                 // g >= 0: the next round's probe finds the key (for every lane that waits for it)
             }
+            KQ_TRACE(0x100000 + k * 16 + 5);
             // one update of the global group count per warp and tile (a single counter bumped by every insert serialises in the L2)
             if (__any_sync(0xffffffffu, new_groups != 0)) {
                 const uint32_t tot = __reduce_add_sync(0xffffffffu, new_groups);
                 if (lane == 0) atomicAdd(A.ngroups, (unsigned long long)tot);
             }
             // refresh the bounds when they look stale (many rows took the exact path), and every 16 tiles to tighten them
+#ifndef KQ_FE_NOREFRESH
             if (Q::NMM > 0 && (many_exact || ((k + 2 * warp) & 15) == 0)) mm_bound_refresh(fe, lane);
+#endif
             // once the directory is full and this warp mostly misses it, stop probing it (the hint was wrong: high cardinality)
-            if (!bypass && __any_sync(0xffffffffu, fe_hits < rows) && *reinterpret_cast<volatile uint32_t*>(&s_ctl.count) >= *reinterpret_cast<volatile uint32_t*>(&s_limit)) {
+            const bool dir_is_full = sh_ld_u32_uniform(fe.a_ctl + 12u) >= sh_ld_u32_uniform(smem_u32(&s_limit));
+            if (!bypass && __any_sync(0xffffffffu, fe_hits < rows) && dir_is_full) {
                 int hits = fe_hits, tot = rows;
 #pragma unroll
                 for (int o = 16; o; o >>= 1) { hits += __shfl_xor_sync(0xffffffffu, hits, o); tot += __shfl_xor_sync(0xffffffffu, tot, o); }
@@ -661,8 +755,16 @@ extern "C" __global__ void __launch_bounds__(THREADS, 1) kq_group_aggregate(cons
     }
 
     // ---- merge the CTA's groups into the global table ---------------------------------------------------------------
+    KQ_TRACE(0x500000);
     __syncthreads();
-    const int G = (int)s_ctl.count;
+    KQ_TRACE(0x500001);
+    int G = (int)s_ctl.count;
+#ifdef KQ_FE_NOMERGE
+    G = 0;
+#endif
+#ifdef KQ_FE_CHECK
+    if (G > FG) { if (threadIdx.x == 0) atomicOr(A.err, 0x8000u); G = FG; }
+#endif
     for (int g = threadIdx.x; g < G; g += THREADS) {
         uint64_t kw[MAX_KEYS];
 #pragma unroll
@@ -673,7 +775,9 @@ extern "C" __global__ void __launch_bounds__(THREADS, 1) kq_group_aggregate(cons
         if (fresh) atomicAdd(A.ngroups, 1ULL);
         gslot[g] = rec ? (uint64_t)(rec - A.table) : ~0ULL;
     }
+    KQ_TRACE(0x500004);
     __syncthreads();
+    KQ_TRACE(0x500003);
     if (warp >= 0) {
         for (int g = 0; g < G; g++) {
             if (gslot[g] == ~0ULL) continue;
@@ -689,6 +793,7 @@ extern "C" __global__ void __launch_bounds__(THREADS, 1) kq_group_aggregate(cons
             fe_merge_input<0>(a_warp, rec, g, lane, c);
         }
     }
+    KQ_TRACE(0x500002);
     for (int t = threadIdx.x; t < G * Q::NMM; t += THREADS) {
         const int g = t / NMM1, m = t % NMM1;
         if (gslot[g] == ~0ULL) continue;

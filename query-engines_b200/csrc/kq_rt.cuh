@@ -22,6 +22,7 @@
 #endif
 #include "kq_args.h"
 #include "kq_pipe.cuh"
+#include "kq_parse.cuh"
 
 namespace kq {
 
@@ -335,15 +336,15 @@ __device__ __forceinline__ void utf8_pack(const QCol& c, uint32_t ok, const RowC
 
 // CastExpression Utf8 -> Float64: Java Double.parseDouble grammar (rule R5). Decimal inputs with at
 // most 19 significant digits and a decimal exponent in [-22, 22] are converted exactly with one
-// IEEE multiply/divide (Clinger's fast path), which is correctly rounded. Anything else (hex
-// floats, more digits, large exponents) raises ERR_PARSE_RANGE — see DESIGN.md.
+// IEEE multiply/divide (Clinger's fast path), which is correctly rounded. Everything else the grammar
+// accepts (more digits, large exponents, hex floats) takes the exact big-integer tier of kq_parse.cuh.
 __device__ __forceinline__ double kq_p10(int e) {
     double p = 1.0;      // exact: every 10^k, k <= 22, is representable
     for (int i = 0; i < e; i++) p = __dmul_rn(p, 10.0);
     return p;
 }
-// returns 0 = ok, 1 = malformed (NumberFormatException), 2 = valid but outside the exact fast path
-__device__ __forceinline__ int parse_f64(const uint8_t* p, int n, double& out) {
+// returns 0 = ok (fast path), else: not decided here (malformed, or valid but outside the fast path)
+__device__ __forceinline__ int parse_f64_fast(const uint8_t* p, int n, double& out) {
     int b = 0, e = n;
     while (b < e && p[b] <= ' ') b++;
     while (e > b && p[e - 1] <= ' ') e--;
@@ -397,10 +398,18 @@ __device__ __forceinline__ int parse_f64(const uint8_t* p, int n, double& out) {
     out = neg ? -v : v;
     return 0;
 }
+// the exact tier, out of line: ~500 bytes of local memory for the big integer, only on the rows that need it
+static __device__ __noinline__ int parse_f64_exact(const uint8_t* p, int n, double& out) {
+    uint64_t bits = 0;
+    const int st = parse_java_double(p, n, &bits);
+    out = __longlong_as_double((long long)bits);
+    return st;
+}
 static __device__ __noinline__ double parse_f64_row(const uint8_t* p, int n, uint32_t* err, bool active) {
     double v = 0.0;
-    const int pe = parse_f64(p, n, v);
-    if (pe && active) atomicOr(err, pe == 1 ? ERR_NUMBER_FORMAT : ERR_PARSE_RANGE);
+    if (parse_f64_fast(p, n, v) != 0) {
+        if (parse_f64_exact(p, n, v) != 0) { v = 0.0; if (active) atomicOr(err, ERR_NUMBER_FORMAT); }      // NumberFormatException (Main.kt:791)
+    }
     return v;
 }
 template <int SOFF_OFF>

@@ -170,10 +170,35 @@ def test_cast_utf8_to_double(G, oracle):
     got = G.cast(G.col(0), F64).evaluate(G.RecordBatch.from_arrow(arr)).to_arrow()
     want = oracle.cast(oracle.col(0), F64).evaluate(oracle.RecordBatch.from_arrow(arr)).to_arrow()
     same(got, want)
-    for bad in ["", "abc", "1_0", "nan", "inf", "1e", "--1", "1 2"]:
+    for bad in ["", "abc", "1_0", "nan", "inf", "1e", "--1", "1 2", "0x1", "0x.p1"]:
         with pytest.raises(G.KqError) as e:
             G.cast(G.col(0), F64).evaluate(G.RecordBatch.from_arrow([pa.array([bad])])).to_arrow()
         assert e.value.code == 5, bad
+
+
+def test_cast_utf8_to_double_is_exact_for_every_valid_input(G, oracle):
+    """String.toDouble() has no digit or exponent limit (Main.kt:791): inputs outside the one-multiply fast path take the
+    exact big-integer tier (csrc/kq_parse.cuh) on the device. 200 k random decimals (1-40 digits, a few up to 900,
+    exponents +-340), halfway cases, subnormals, overflow, hex floats — bit for bit against the oracle."""
+    import random
+    rng = random.Random(11)
+    vals = ["1e23", "9007199254740993", "123456789012345678901234567890", "0.1e-5000", "1e5000", "4.9e-324", "2.4703282292062327e-324",
+            "2.4703282292062328e-324", "1.7976931348623159e308", "1.7976931348623157e308", "0x1.8p1", "0x1p-1075", "0x1.0000000000001p-1075",
+            "0x1.fffffffffffff8p1023", "0xAbC.dEfp-7f", "-0x1p3D", "8.5e-320", "1" + "0" * 400, "0." + "0" * 400 + "1", "3." + "3" * 800]
+    for _ in range(200_000):
+        nd = rng.randint(1, 40) if rng.random() < 0.97 else rng.randint(40, 900)
+        digs = "".join(rng.choice("0123456789") for _ in range(nd))
+        if rng.random() < 0.6:
+            k = rng.randint(0, nd)
+            digs = digs[:k] + "." + digs[k:]
+        s = ("-" if rng.random() < 0.3 else "") + digs
+        if rng.random() < 0.7:
+            s += rng.choice("eE") + rng.choice(["", "+", "-"]) + str(rng.randint(0, 340))
+        vals.append(s)
+    arr = [pa.array(vals)]
+    got = G.cast(G.col(0), F64).evaluate(G.RecordBatch.from_arrow(arr)).to_arrow()
+    want = oracle.cast(oracle.col(0), F64).evaluate(oracle.RecordBatch.from_arrow(arr)).to_arrow()
+    same(got, want)
 
 
 # ---------------------------------------------------------------- filter
