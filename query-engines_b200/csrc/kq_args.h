@@ -99,6 +99,77 @@ constexpr int FE_MAX_GROUPS = 64;
 
 enum : int32_t { F_SUM = 1, F_MIN = 2, F_MAX = 4, F_INT = 8 };
 
+// Utf8 group keys longer than 7 bytes (kq_rt.cuh utf8_intern): the key word of such a string is a 63-bit hash of its bytes
+// with the top bit set; the bytes live once in a per-aggregate heap, found through an open-addressing table keyed by the
+// word. Every row's bytes are compared with the heap copy, so two different strings with the same hash are an ERROR, never
+// a silently merged group.
+struct KeyHeap {
+    unsigned long long* tab;        // [cap][2]: {word (0 empty, 1 being published), heap offset << 24 | length}; NULL: no long keys in this launch
+    uint64_t cap_mask;
+    uint8_t* bytes;
+    uint64_t bytes_cap;
+    unsigned long long* used;       // [0] entries, [1] heap bytes
+};
+
+__host__ __device__ inline uint64_t heap_home(uint64_t word, uint64_t cap_mask) { return ((word * 0x9E3779B97F4A7C15ULL) >> 20) & cap_mask; }
+// (offset << 24 | length) of a long key word, 0 if absent (finalize)
+__host__ __device__ inline unsigned long long heap_find(const KeyHeap& H, uint64_t word) {
+    uint64_t slot = heap_home(word, H.cap_mask);
+    for (uint64_t probes = 0; probes <= H.cap_mask; probes++) {
+        const unsigned long long w = H.tab[2 * slot];
+        if (w == word) return H.tab[2 * slot + 1];
+        if (w == 0ULL) return 0ULL;
+        slot = (slot + 1) & H.cap_mask;
+    }
+    return 0ULL;
+}
+
+#ifdef __CUDACC__
+// ---- long Utf8 group keys ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint64_t utf8_hash63(const uint8_t* p, int len) {
+    uint64_t h = 0xCBF29CE484222325ULL ^ (uint64_t)(uint32_t)len;
+    for (int i = 0; i < len; i++) h = (h ^ __ldg(p + i)) * 0x100000001B3ULL;        // FNV-1a over the bytes ...
+    h ^= h >> 32; h *= 0xD6E8FEB86659FD93ULL; h ^= h >> 32;                          // ... and a finaliser
+    return h | 0x8000000000000000ULL;                                                // top bit: "long key" (a packed short key has a length <= 7 there)
+}
+// Key word of the string p[0..len), len > 7: find it in the heap (comparing the bytes) or add it. Out of line: rare path.
+static __device__ __noinline__ uint64_t utf8_intern(const KeyHeap* H, const uint8_t* p, int len, uint32_t* err) {
+    const uint64_t word = utf8_hash63(p, len);
+    uint64_t slot = heap_home(word, H->cap_mask);
+    for (uint64_t probes = 0; probes <= H->cap_mask; probes++) {
+        unsigned long long* e = H->tab + 2 * slot;
+        unsigned long long w = *reinterpret_cast<volatile unsigned long long*>(e);
+        if (w == 0ULL) {
+            w = atomicCAS(e, 0ULL, 1ULL);
+            if (w == 0ULL) {                                                         // ours: copy the bytes, then publish
+                const unsigned long long off = atomicAdd(H->used + 1, (unsigned long long)((len + 7) & ~7));
+                if (off + (unsigned long long)len > H->bytes_cap) { atomicOr(err, 32u); *reinterpret_cast<volatile unsigned long long*>(e + 1) = 0ULL; }
+                else {
+                    for (int i = 0; i < len; i++) H->bytes[off + i] = __ldg(p + i);
+                    *reinterpret_cast<volatile unsigned long long*>(e + 1) = (off << 24) | (unsigned long long)(uint32_t)len;
+                }
+                atomicAdd(H->used, 1ULL);
+                __threadfence();
+                *reinterpret_cast<volatile unsigned long long*>(e) = word;
+                return word;
+            }
+        }
+        for (int spins = 0; w == 1ULL && spins < (1 << 20); spins++) w = *reinterpret_cast<volatile unsigned long long*>(e);      // being published
+        if (w == word) {
+            const unsigned long long meta = *reinterpret_cast<volatile unsigned long long*>(e + 1);
+            bool same = (int)(meta & 0xFFFFFFu) == len;
+            const uint8_t* q = H->bytes + (meta >> 24);
+            for (int i = 0; same && i < len; i++) same = __ldcg(q + i) == __ldg(p + i);       // the heap is written by other SMs: not through this SM's L1
+            if (!same) atomicOr(err, 16u);       // two different strings, one 63-bit hash: refuse rather than merge the groups
+            return word;
+        }
+        slot = (slot + 1) & H->cap_mask;
+    }
+    atomicOr(err, 32u);
+    return word;
+}
+#endif  // __CUDACC__
+
 struct AggInput {
     int32_t flags;
     int32_t rec_nn, rec_sum, rec_min, rec_max;   // record word indices (-1 = absent)
@@ -120,6 +191,8 @@ struct AggArgs {
     unsigned int* ticket;
     uint32_t* err;
     unsigned int* overflow;                // set when an insert finds the table full (optimistically sized table: the host rolls back and grows)
+    unsigned int* progress;                // kq_k_agg_fe.cuh: tiles each block has finished in earlier launches over this batch (block b owns tiles b, b + grid, ...)
+    KeyHeap heap;                          // long Utf8 group keys
     unsigned long long* trace;             // debugging (KQ_FE_PROGRESS=<pinned host address>): last checkpoint per warp of block 0
     // front end
     int32_t fe_groups, fe_nsum, fe_nmm;

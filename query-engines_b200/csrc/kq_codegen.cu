@@ -9,6 +9,7 @@
 // 64-bit values are uint64_t[R] arrays, Bool values uint32_t truth masks, validity R-bit masks.
 // Column types, nullability and staging offsets are baked into the text; pointers and literal
 // VALUES are read from `q`, so one compiled kernel serves every query of the same shape.
+#include <algorithm>
 #include <cstring>
 
 #include "kq_codegen.h"
@@ -380,8 +381,9 @@ std::string KqCodegen::plan_stages(int budget, int min_stages, int tile_rows, St
     memset(sp, 0, sizeof *sp);
     int off = 0;
     int cur_slot = 0;
+    int bytes_per_row = 4;           // stage room for Utf8 string bytes: 4 per row unless the column's average length says less
     auto add = [&](int kind, const void* g, int role) -> int {
-        int bytes = kind == SK_W8 ? TILE * 8 : (kind == SK_W4 ? TILE * 4 : (kind == SK_W4_PLUS1 ? TILE * 4 + 16 : (kind == SK_BYTES ? TILE * 4 + 64 : TILE / 8)));
+        int bytes = kind == SK_W8 ? TILE * 8 : (kind == SK_W4 ? TILE * 4 : (kind == SK_W4_PLUS1 ? TILE * 4 + 16 : (kind == SK_BYTES ? TILE * bytes_per_row + 64 : TILE / 8)));
         bytes = (bytes + 127) / 128 * 128;
         if (sp->nbuf >= MAX_STAGE_BUFS || (off + bytes) * min_stages > budget) return -1;   // stays on the direct global path
         if (kind == SK_BIT && TILE % 128 != 0) return -1;                                   // a tile's bit range must start 16-byte aligned for the bulk copy
@@ -406,8 +408,15 @@ std::string KqCodegen::plan_stages(int budget, int min_stages, int tile_rows, St
                 // string bytes: a second-phase copy of the range the tile's offsets span (up to 4 bytes/row on average; longer tiles fall back to global loads)
                 if (stage_bytes && so >= 0 && col_bytes_used[i] && sp->nbytes < MAX_BYTES_BUFS) {
                     const int obuf = sp->nbuf - 1;
+                    // the column's average string length (known for uploaded and generated columns) + 25 %, at most 4 bytes per
+                    // row; a tile whose strings need more falls back to global loads for that tile, nothing else changes
+                    bytes_per_row = 4;
+                    if (c->n > 0 && c->data_bytes >= 0) {
+                        const long long avg125 = (c->data_bytes * 5 + c->n * 4 - 1) / (c->n * 4);
+                        bytes_per_row = (int)std::max<long long>(2, std::min<long long>(4, avg125 + 1));
+                    }
                     sb = add(SK_BYTES, c->data, 0);
-                    if (sb >= 0) { sp->buf[sp->nbuf - 1].aux = obuf | (i << 16); sp->buf[sp->nbuf - 1].cap = TILE * 4 + 64; sp->bytes_buf[sp->nbytes++] = sp->nbuf - 1; }
+                    if (sb >= 0) { sp->buf[sp->nbuf - 1].aux = obuf | (i << 16); sp->buf[sp->nbuf - 1].cap = TILE * bytes_per_row + 64; sp->bytes_buf[sp->nbytes++] = sp->nbuf - 1; }
                 }
                 break;
         }

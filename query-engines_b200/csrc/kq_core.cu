@@ -157,9 +157,11 @@ int kq_check_device_errors(kq_ctx* ctx) {
 int kq_device_error_status(kq_ctx* ctx, uint32_t e) {
     if (!e) return KQ_OK;
     if (e & 0xFF00u) return kq_fail(ctx, KQ_ERR_CUDA, "aggregate kernel gave up (internal protocol error, location bits 0x%x)", e & 0xFF00u);
+    if (e & 16u) return kq_fail(ctx, KQ_ERR_ILLEGAL_STATE, "two different Utf8 group keys share a 63-bit hash: refusing to merge their groups");
+    if (e & 32u) return kq_fail(ctx, KQ_ERR_UNSUPPORTED, "more distinct long Utf8 group keys than the key heap was sized for (raise expected_groups)");
     if (e & KQ_DEV_ERR_DIV0) return kq_fail(ctx, KQ_ERR_ARITHMETIC, "/ by zero");
     if (e & KQ_DEV_ERR_NUMBER_FORMAT) return kq_fail(ctx, KQ_ERR_NUMBER_FORMAT, "For input string: cannot parse as double");
-    if (e & KQ_DEV_ERR_LONG_KEY) return kq_fail(ctx, KQ_ERR_UNSUPPORTED, "Utf8 group key longer than 7 bytes is not supported yet");
+    if (e & KQ_DEV_ERR_LONG_KEY) return kq_fail(ctx, KQ_ERR_UNSUPPORTED, "Utf8 group key longer than 7 bytes in a kernel without a key heap");
     return kq_fail(ctx, KQ_ERR_CUDA, "unknown device error bits 0x%x", e);
 }
 

@@ -94,10 +94,51 @@ __global__ void k_collect_small(const uint64_t* __restrict__ table, uint64_t cap
     }
     if (blockIdx.x == 0 && threadIdx.x == 0) block[1] = *err;
 }
-__global__ void k_collect_small_done(uint64_t* block) { block[0] = block[2]; }
+__global__ void k_collect_small_done(uint64_t* block, const unsigned long long* __restrict__ heap_used) {
+    block[0] = block[2];
+    block[3] = heap_used ? heap_used[0] : 0;          // long Utf8 keys this rank has interned: entries, bytes
+    block[4] = heap_used ? heap_used[1] : 0;
+}
+// This rank's long Utf8 group keys for the other ranks (a merged group's bytes must exist wherever the group ends up):
+// blk[0] strings written, blk[1] 1 = they did not all fit; entries from word 2: {key word, length, bytes padded to 8}.
+constexpr uint64_t STRBLK_WORDS = 8192;         // 64 KB per rank
+__global__ void k_heap_export(const KeyHeap H, unsigned long long* blk) {
+    unsigned long long* cursor = blk + 2;        // words used (starts at 3)
+    for (uint64_t s = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; s <= H.cap_mask; s += (uint64_t)gridDim.x * blockDim.x) {
+        const unsigned long long w = H.tab[2 * s];
+        if (w < 2ULL) continue;
+        const unsigned long long meta = H.tab[2 * s + 1];
+        const uint32_t len = (uint32_t)(meta & 0xFFFFFFu);
+        const uint64_t words = 2 + (len + 7) / 8;
+        const unsigned long long pos = atomicAdd(cursor, (unsigned long long)words);
+        if (pos + words > STRBLK_WORDS) { blk[1] = 1ULL; continue; }
+        blk[pos] = w; blk[pos + 1] = len;
+        const uint8_t* q = H.bytes + (meta >> 24);
+        uint8_t* d = reinterpret_cast<uint8_t*>(blk + pos + 2);
+        for (uint32_t i = 0; i < len; i++) d[i] = q[i];
+        atomicAdd(blk, 1ULL);
+    }
+}
+__global__ void k_heap_import(const KeyHeap H, const unsigned long long* __restrict__ all, int nranks, int me, uint32_t* err) {
+    const int r = blockIdx.x * blockDim.x + threadIdx.x;
+    if (r >= nranks || r == me) return;
+    const unsigned long long* blk = all + (uint64_t)r * STRBLK_WORDS;
+    if (blk[1]) atomicOr(err, 32u);              // that rank's strings did not fit the block: the merged keys would be incomplete
+    uint64_t pos = 3;
+    for (unsigned long long i = 0; i < blk[0] && pos + 2 <= STRBLK_WORDS; i++) {
+        const uint32_t len = (uint32_t)blk[pos + 1];
+        const uint64_t word = kq::utf8_intern(&H, reinterpret_cast<const uint8_t*>(blk + pos + 2), (int)len, err);
+        if (word != blk[pos]) atomicOr(err, 16u);
+        pos += 2 + (len + 7) / 8;
+    }
+}
 // [count, status] of every rank's block -> out[2 * rank]
+// [count, status, heap entries, heap bytes] of every rank's block -> out[4 * rank]
 __global__ void k_merge_heads(const uint64_t* __restrict__ all, uint64_t pitch, int n, unsigned long long* out) {
-    for (int i = threadIdx.x; i < n; i += blockDim.x) { out[2 * i] = all[(uint64_t)i * pitch]; out[2 * i + 1] = all[(uint64_t)i * pitch + 1]; }
+    for (int i = threadIdx.x; i < n; i += blockDim.x) {
+        out[4 * i] = all[(uint64_t)i * pitch]; out[4 * i + 1] = all[(uint64_t)i * pitch + 1];
+        out[4 * i + 2] = all[(uint64_t)i * pitch + 3]; out[4 * i + 3] = all[(uint64_t)i * pitch + 4];
+    }
 }
 // Rebuild this rank's table from the gathered partials, RANK BY RANK in one block: a key occurs at most once per rank,
 // so within a rank no two threads touch the same record, and the barrier between ranks fixes the order of every
@@ -287,18 +328,50 @@ __global__ void k_finalize(const __grid_constant__ FinArgs F) {
 }
 
 struct PackedLen {
-    const uint64_t* packed; const uint32_t* validity;
+    const uint64_t* packed; const uint32_t* validity; KeyHeap heap;
     __device__ __forceinline__ int operator()(long long i) const {
         if (validity && !((validity[i >> 5] >> (i & 31)) & 1u)) return 0;
-        return (int)(packed[i] >> 56);
+        const uint64_t w = packed[i];
+        if (w >> 63) return (int)(heap_find(heap, w) & 0xFFFFFFu);          // a long key: its length is in the key heap
+        return (int)(w >> 56);
     }
 };
-__global__ void k_unpack_utf8(const uint64_t* __restrict__ packed, const int32_t* __restrict__ off, const unsigned long long* __restrict__ nrows, uint8_t* out) {
+__global__ void k_unpack_utf8(const uint64_t* __restrict__ packed, const int32_t* __restrict__ off, const unsigned long long* __restrict__ nrows, uint8_t* out, const KeyHeap heap) {
     const uint64_t n = *nrows;
     for (uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; i < n; i += (uint64_t)gridDim.x * blockDim.x) {
         int len = off[i + 1] - off[i];
         uint64_t p = packed[i];
-        for (int b = 0; b < len; b++) out[off[i] + b] = (uint8_t)(p >> (8 * b));
+        if (p >> 63) {
+            const uint8_t* q = heap.bytes + (heap_find(heap, p) >> 24);
+            for (int b = 0; b < len; b++) out[off[i] + b] = q[b];
+        } else {
+            for (int b = 0; b < len; b++) out[off[i] + b] = (uint8_t)(p >> (8 * b));
+        }
+    }
+}
+
+// ---- long Utf8 group keys (kq_rt.cuh utf8_intern): column statistics and key-heap maintenance ---------------------------------
+__global__ void k_utf8_len_stats(const int32_t* __restrict__ off, int64_t n, unsigned long long* out) {      // out: [0] max length, [1] strings > 7 bytes, [2] their bytes
+    unsigned long long mx = 0, cnt = 0, bytes = 0;
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+        const unsigned long long len = (unsigned long long)(off[i + 1] - off[i]);
+        mx = len > mx ? len : mx;
+        if (len > 7) { cnt++; bytes += len; }
+    }
+#pragma unroll
+    for (int o = 16; o; o >>= 1) {
+        const unsigned long long m2 = __shfl_xor_sync(0xffffffffu, mx, o);
+        mx = m2 > mx ? m2 : mx; cnt += __shfl_xor_sync(0xffffffffu, cnt, o); bytes += __shfl_xor_sync(0xffffffffu, bytes, o);
+    }
+    if ((threadIdx.x & 31) == 0) { atomicMax(out, mx); if (cnt) { atomicAdd(out + 1, cnt); atomicAdd(out + 2, bytes); } }
+}
+__global__ void k_heap_rehash(const unsigned long long* __restrict__ old_tab, uint64_t old_cap, unsigned long long* tab, uint64_t cap_mask) {
+    for (uint64_t s = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; s < old_cap; s += (uint64_t)gridDim.x * blockDim.x) {
+        const unsigned long long w = old_tab[2 * s];
+        if (w < 2ULL) continue;
+        uint64_t slot = heap_home(w, cap_mask);
+        while (atomicCAS(tab + 2 * slot, 0ULL, w) != 0ULL) slot = (slot + 1) & cap_mask;
+        tab[2 * slot + 1] = old_tab[2 * s + 1];
     }
 }
 
@@ -346,6 +419,9 @@ struct kq_hashagg {
     // same status — an unrelated call on the context can neither consume nor hide them.
     uint32_t dev_err = 0;
     bool groups_exact = true;               // ngroups_host is exact (after a merge it is an upper bound until finalize reads the count)
+    // long Utf8 group keys: the key heap (kq_args.h KeyHeap); heap.used = d_counters + 6
+    KeyHeap heap{};
+    uint64_t heap_entries = 0, heap_bytes = 0;      // in use (as of the last counter read)
     // merge buffers (kq_hashagg_merge_allreduce), allocated once per aggregate
     uint64_t* merge_mine = nullptr; uint64_t* merge_all = nullptr; uint64_t merge_words = 0;
 };
@@ -355,7 +431,10 @@ struct kq_hashagg {
 static int sticky_error(kq_ctx* ctx, kq_hashagg* h) { return h->dev_err ? kq_device_error_status(ctx, h->dev_err) : KQ_OK; }
 // counters of a finished launch: remembers device errors (sticky), reports an overflow of a conservatively sized table
 static int read_counters(kq_ctx* ctx, kq_hashagg* h, uint64_t (&c)[6]) {
-    KQ_RET(kq_read_u64(ctx, h->d_counters, 6, c));
+    uint64_t c8[8];
+    KQ_RET(kq_read_u64(ctx, h->d_counters, 8, c8));
+    for (int i = 0; i < 6; i++) c[i] = c8[i];
+    h->heap_entries = c8[6]; h->heap_bytes = c8[7];
     if ((uint32_t)c[5]) { h->dev_err |= (uint32_t)c[5]; return sticky_error(ctx, h); }
     return KQ_OK;
 }
@@ -403,6 +482,7 @@ static void fill_common_args(kq_hashagg* h, AggArgs& A) {
     A.ticket = (unsigned int*)(h->d_counters + 1);
     A.err = (uint32_t*)(h->d_counters + 5);
     A.overflow = (unsigned int*)(h->d_counters + 4);
+    A.heap = h->heap;
     A.trace = getenv("KQ_FE_PROGRESS") ? (unsigned long long*)strtoull(getenv("KQ_FE_PROGRESS"), nullptr, 0) : nullptr;
     A.stop_threshold = ~0ULL;
 }
@@ -471,9 +551,9 @@ int kq_hashagg_create(kq_ctx* ctx, kq_expr* pred, kq_expr* const* group_exprs, i
     kq_hashagg* h = nullptr;
     KQ_RET(hashagg_new(ctx, pred, group_exprs, ngroup, agg_kinds, agg_inputs, nagg, expected_groups, &h));
     // counters and table come from the ctx's caching allocator: creating an aggregate costs no cudaMalloc after the first query
-    int st = kq_dev_alloc(ctx, 256, (void**)&h->d_counters);
+    int st = kq_dev_alloc(ctx, 8192, (void**)&h->d_counters);      // [0, 256): counters; [1024, 4096): per-block progress; [4096, 8192): its snapshot
     if (st != KQ_OK) { kq_hashagg_free(h); return st; }
-    cudaError_t e = cudaMemsetAsync(h->d_counters, 0, 256, ctx->stream);
+    cudaError_t e = cudaMemsetAsync(h->d_counters, 0, 8192, ctx->stream);
     if (e != cudaSuccess) { kq_hashagg_free(h); return kq_cuda_fail(ctx, e, "cudaMemsetAsync"); }
     // sized from the planner's hint: a 50-group query gets a 1024-slot table (64 KB), not one sized for the rows in flight
     uint64_t cap = 1024;
@@ -496,6 +576,8 @@ int kq_hashagg_free(kq_hashagg* h) {
         kq_dev_free(h->ctx, h->snapshot);
         kq_dev_free(h->ctx, h->merge_mine);
         kq_dev_free(h->ctx, h->merge_all);
+        kq_dev_free(h->ctx, h->heap.tab);
+        kq_dev_free(h->ctx, h->heap.bytes);
         delete h;
     }
     return KQ_OK;
@@ -613,7 +695,7 @@ static int plan_agg(kq_ctx* ctx, kq_hashagg* h, kq_batch* input, int smem_optin,
         };
         const int budget = smem_optin - 2048;      // static shared memory of the kernel (barriers, tile bookkeeping, directory control): ~1.3 KB
         struct Cand { int r, warps; };
-        static const Cand CAND[] = {{4, 8}, {4, 7}, {4, 6}, {2, 8}, {4, 5}, {2, 6}, {4, 4}, {2, 4}, {2, 2}};
+        static const Cand CAND[] = {{8, 6}, {8, 5}, {6, 6}, {8, 4}, {4, 7}, {4, 6}, {4, 5}, {4, 4}, {2, 6}, {2, 4}, {2, 2}};      // rows per thread amortise the per-tile cost: 8 first
         int fr = 0, fw = 0, fs = 0;                                   // tuning experiments: KQ_AGG_GEOM="rows,warps[,stages]"
         if (forced) sscanf(forced, "%d,%d,%d", &fr, &fw, &fs);
         bool found = false;
@@ -714,6 +796,17 @@ static int plan_agg(kq_ctx* ctx, kq_hashagg* h, kq_batch* input, int smem_optin,
     consts += arr("int", "FE_MIN", NI, [&](int i) { return h->in[i].fe_min; });
     consts += arr("int", "FE_MAX", NI, [&](int i) { return h->in[i].fe_max; });
     consts += arr("int", "MM_WORD", nm, [&](int i) { return mm_word[(size_t)i]; });
+    {   // MIN/MAX slot -> is its input nullable (kq_k_agg_fe.cuh: a group may then hold no value for it)
+        std::vector<int> mm_nullable((size_t)std::max(nm, 1), 0);
+        bool any = false;
+        for (int i = 0; i < NI; i++) {
+            const bool nl = in_cnt[(size_t)i] > 0;
+            if (h->in[i].fe_min >= 0) { mm_nullable[(size_t)h->in[i].fe_min] = nl; any |= nl; }
+            if (h->in[i].fe_max >= 0) { mm_nullable[(size_t)h->in[i].fe_max] = nl; any |= nl; }
+        }
+        consts += arr("bool", "MM_NULLABLE", nm, [&](int i) { return mm_nullable[(size_t)i]; });
+        consts += std::string("    static constexpr bool ANY_MM_NULLABLE = ") + (any ? "true" : "false") + ";\n";
+    }
     // one input with both MIN and MAX in adjacent, 16-byte aligned record words: the global path reads them with one load
     const bool mm_paired = NI == 1 && nm == 2 && mm_word[1] == mm_word[0] + 1 && mm_word[0] % 2 == 0 && h->in[0].fe_min == 0;
     consts += std::string("    static constexpr bool MM_PAIRED = ") + (mm_paired ? "true" : "false") + ";\n";
@@ -725,7 +818,7 @@ static int plan_agg(kq_ctx* ctx, kq_hashagg* h, kq_batch* input, int smem_optin,
                                 "\n#define KQ_STAGE_BYTES " + (has_bytes ? "1" : "0") + "\n#define KQ_AGG_MODE " + std::to_string(mode) + "\n" +
                                 (getenv("KQ_PART_L2_HINTS") ? "#define KQ_PART_L2_HINTS " + std::to_string(atoi(getenv("KQ_PART_L2_HINTS"))) + "\n" : std::string()) +
                                 (getenv("KQ_FE_CHECK") ? "#define KQ_FE_CHECK 1\n" : "") + (getenv("KQ_FE_NOEXACT") ? "#define KQ_FE_NOEXACT 1\n" : "") +
-                                (getenv("KQ_FE_NOREFRESH") ? "#define KQ_FE_NOREFRESH 1\n" : "") + (getenv("KQ_FE_NOMERGE") ? "#define KQ_FE_NOMERGE 1\n" : "");
+                                (getenv("KQ_FE_NOREFRESH") ? "#define KQ_FE_NOREFRESH 1\n" : "") + (getenv("KQ_FE_PROGRESS") ? "#define KQ_FE_TRACE 1\n" : "") + (getenv("KQ_FE_NOMERGE") ? "#define KQ_FE_NOMERGE 1\n" : "");
     return KQ_OK;
 }
 
@@ -855,9 +948,17 @@ static int hashagg_update_fe(kq_ctx* ctx, kq_hashagg* h, kq_batch* input, int64_
     // rows that may still create groups after a block has decided to continue (conservative rule only)
     const uint64_t margin = (uint64_t)grid * ((uint64_t)(A.sp.nstages + 1) * TILE + FE_MAX_GROUPS);
 
-    int64_t tile_begin = 0;
-    while (tile_begin < A.ntiles) {
-        const uint64_t remaining_rows = (uint64_t)(n - tile_begin * TILE);
+    // Block b owns tiles b, b + grid, ...; `progress` (device, per block) survives relaunches over this batch, `done` counts
+    // the tiles finished so far.
+    if (grid > 512) return kq_fail(ctx, KQ_ERR_UNSUPPORTED, "more than 512 blocks");
+    unsigned int* d_progress = reinterpret_cast<unsigned int*>(h->d_counters + 128);
+    unsigned int* d_progress_snap = reinterpret_cast<unsigned int*>(h->d_counters + 512);
+    KQ_CUDA(ctx, cudaMemsetAsync(d_progress, 0, (size_t)grid * 4, ctx->stream));
+    KQ_CUDA(ctx, cudaMemsetAsync(h->d_counters + 1, 0, 8, ctx->stream));
+    int64_t done = 0;
+    const int64_t tile_begin = 0;
+    while (done < A.ntiles) {
+        const uint64_t remaining_rows = (uint64_t)n;              // blocks advance independently: no prefix of the batch is finished until all of it is
         uint64_t cap = h->capacity;
         bool unthrottled = false;
         const bool optimistic = !h->pessimistic;
@@ -883,11 +984,12 @@ static int hashagg_update_fe(kq_ctx* ctx, kq_hashagg* h, kq_batch* input, int64_
             }
             KQ_CUDA(ctx, cudaMemcpyAsync(h->snapshot, h->table, (size_t)h->capacity * h->stride * 8, cudaMemcpyDeviceToDevice, ctx->stream));
         }
+        if (optimistic) KQ_CUDA(ctx, cudaMemcpyAsync(d_progress_snap, d_progress, (size_t)grid * 4, cudaMemcpyDeviceToDevice, ctx->stream));
         const int64_t groups_before = h->ngroups_host;
         fill_common_args(h, A);
         A.tile_begin = tile_begin;
+        A.progress = d_progress;
         A.stop_threshold = unthrottled ? ~0ULL : h->capacity / 2;
-        KQ_CUDA(ctx, cudaMemsetAsync(h->d_counters + 1, 0, 8, ctx->stream));
         void* kargs[] = {&A};
         KQ_CUDA(ctx, cudaLaunchKernel(kernel, dim3(grid), dim3(THREADS), kargs, (size_t)A.smem_bytes, ctx->stream));
         ctx->launches++;
@@ -895,7 +997,7 @@ static int hashagg_update_fe(kq_ctx* ctx, kq_hashagg* h, kq_batch* input, int64_
         {
             const int rst = read_counters(ctx, h, c);
             if (getenv("KQ_TRACE_AGG"))
-                fprintf(stderr, "kq fe launch: tiles [%lld, %lld) grid %d cap %llu optimistic %d -> st %d groups %llu tickets %u overflow %u err 0x%x\n", (long long)tile_begin,
+                fprintf(stderr, "kq fe launch: done %lld of %lld tiles, grid %d cap %llu optimistic %d -> st %d groups %llu done %u overflow %u err 0x%x\n", (long long)done,
                         (long long)A.ntiles, grid, (unsigned long long)h->capacity, (int)optimistic, rst, (unsigned long long)c[0], (unsigned)c[1], (unsigned)c[4], (unsigned)c[5]);
             KQ_RET(rst);
         }
@@ -904,18 +1006,79 @@ static int hashagg_update_fe(kq_ctx* ctx, kq_hashagg* h, kq_batch* input, int64_
             if (!optimistic) return kq_fail(ctx, KQ_ERR_ILLEGAL_STATE, "aggregation table overflow");
             if (need_snapshot) KQ_CUDA(ctx, cudaMemcpyAsync(h->table, h->snapshot, (size_t)h->capacity * h->stride * 8, cudaMemcpyDeviceToDevice, ctx->stream));
             else KQ_CUDA(ctx, cudaMemsetAsync(h->table, 0, (size_t)(h->capacity + 1) * h->stride * 8, ctx->stream));
-            const unsigned long long restore[1] = {(unsigned long long)groups_before};
-            KQ_CUDA(ctx, cudaMemcpyAsync(h->d_counters, restore, 8, cudaMemcpyHostToDevice, ctx->stream));
+            const unsigned long long restore[2] = {(unsigned long long)groups_before, (unsigned long long)done};
+            KQ_CUDA(ctx, cudaMemcpyAsync(h->d_counters, restore, 16, cudaMemcpyHostToDevice, ctx->stream));
+            KQ_CUDA(ctx, cudaMemcpyAsync(d_progress, d_progress_snap, (size_t)grid * 4, cudaMemcpyDeviceToDevice, ctx->stream));
             KQ_CUDA(ctx, cudaMemsetAsync(h->d_counters + 4, 0, 8, ctx->stream));
             KQ_CUDA(ctx, cudaStreamSynchronize(ctx->stream));          // `restore` lives on this stack frame
             h->pessimistic = true;
             continue;
         }
         h->ngroups_host = (int64_t)c[0];
-        const int64_t taken = (int64_t)(uint32_t)c[1];
-        tile_begin += std::min<int64_t>(taken, A.ntiles - tile_begin);
-        if (tile_begin < A.ntiles) KQ_RET(table_grow(ctx, h, h->capacity * 4));      // stopped early: the table crossed half full
+        const int64_t now_done = (int64_t)(uint32_t)c[1];
+        if (now_done < A.ntiles) {
+            // stopped early: the table crossed half full. (No progress at all with a table that is not at its threshold would repeat forever.)
+            if (now_done == done && (uint64_t)h->ngroups_host <= h->capacity / 2) return kq_fail(ctx, KQ_ERR_ILLEGAL_STATE, "aggregate kernel made no progress");
+            KQ_RET(table_grow(ctx, h, h->capacity * 4));
+        }
+        done = now_done;
     }
+    return KQ_OK;
+}
+
+// Utf8 group keys longer than 7 bytes: make sure the key heap can take every long string this batch may add. The column's
+// length statistics are computed once per column (a pass over its offsets) and kept with it.
+static int key_heap_reserve(kq_ctx* ctx, kq_hashagg* h, uint64_t add_entries, uint64_t add_bytes);
+static int ensure_key_heap(kq_ctx* ctx, kq_hashagg* h, kq_batch* input) {
+    uint64_t n_long = 0, bytes_long = 0, max_len = 0;
+    for (kq_expr* g : h->groups) {
+        const int bc = KqCodegen::bare_column(g);
+        if (bc < 0 || bc >= (int)input->cols.size()) continue;
+        kq_col* c = input->cols[(size_t)bc];
+        if (c->type != KQ_UTF8) continue;
+        if (c->utf8_max_len < 0) {
+            int64_t rows; KQ_RET(kq_col_resolve_rows(ctx, c, &rows));
+            unsigned long long* d = nullptr;
+            KQ_RET(kq_dev_alloc(ctx, 32, (void**)&d));
+            cudaMemsetAsync(d, 0, 32, ctx->stream);
+            if (rows > 0) { k_utf8_len_stats<<<small_grid(ctx, (uint64_t)rows), 256, 0, ctx->stream>>>(c->offsets, rows, d); ctx->launches++; }
+            uint64_t st3[3];
+            const int st = kq_read_u64(ctx, d, 3, st3);
+            kq_dev_free(ctx, d);
+            KQ_RET(st);
+            c->utf8_max_len = (int64_t)st3[0]; c->utf8_n_long = (int64_t)st3[1]; c->utf8_bytes_long = (int64_t)st3[2];
+        }
+        if (c->utf8_max_len > 7) { n_long += (uint64_t)c->utf8_n_long; bytes_long += (uint64_t)c->utf8_bytes_long; max_len = std::max<uint64_t>(max_len, (uint64_t)c->utf8_max_len); }
+    }
+    if (n_long == 0) return KQ_OK;
+    // every long row could be a new string; the planner's hint, when there is one, bounds that far below the row count
+    const uint64_t distinct_cap = h->expected_groups > 0 ? std::max<uint64_t>(4 * (uint64_t)h->expected_groups, 1ULL << 16) : n_long;
+    const uint64_t add = std::min<uint64_t>(std::min(n_long, distinct_cap), 1ULL << 27);
+    return key_heap_reserve(ctx, h, add, std::min<uint64_t>(bytes_long + 8 * n_long, add * (max_len + 8)));
+}
+
+// Room for `add_entries` more strings of `add_bytes` bytes in total (8-byte padded) in the aggregate's key heap.
+static int key_heap_reserve(kq_ctx* ctx, kq_hashagg* h, uint64_t add_entries, uint64_t add_bytes) {
+    const uint64_t need_entries = h->heap_entries + add_entries;
+    const uint64_t need_bytes = h->heap_bytes + add_bytes;
+    uint64_t cap = h->heap.tab ? h->heap.cap_mask + 1 : 1024;
+    while (cap < 2 * need_entries) cap <<= 1;
+    uint64_t bcap = h->heap.bytes ? h->heap.bytes_cap : 4096;
+    while (bcap < need_bytes) bcap <<= 1;
+    if (h->heap.tab && cap == h->heap.cap_mask + 1 && bcap == h->heap.bytes_cap) return KQ_OK;
+    unsigned long long* tab = nullptr; uint8_t* bytes = nullptr;
+    KQ_RET(kq_dev_alloc(ctx, (size_t)cap * 16, (void**)&tab));
+    int st = kq_dev_alloc(ctx, (size_t)bcap + 16, (void**)&bytes);
+    if (st != KQ_OK) { kq_dev_free(ctx, tab); return st; }
+    cudaMemsetAsync(tab, 0, (size_t)cap * 16, ctx->stream);
+    if (h->heap.tab) {
+        k_heap_rehash<<<small_grid(ctx, h->heap.cap_mask + 1), 256, 0, ctx->stream>>>(h->heap.tab, h->heap.cap_mask + 1, tab, cap - 1);
+        ctx->launches++;
+        cudaMemcpyAsync(bytes, h->heap.bytes, (size_t)std::min<uint64_t>(h->heap.bytes_cap, h->heap_bytes + 8), cudaMemcpyDeviceToDevice, ctx->stream);
+        kq_dev_free(ctx, h->heap.tab); kq_dev_free(ctx, h->heap.bytes);
+    }
+    h->heap.tab = tab; h->heap.cap_mask = cap - 1; h->heap.bytes = bytes; h->heap.bytes_cap = bcap;
+    h->heap.used = h->d_counters + 6;
     return KQ_OK;
 }
 
@@ -927,6 +1090,7 @@ int kq_hashagg_update(kq_ctx* ctx, kq_hashagg* h, kq_batch* input) {
     KQ_RET(sticky_error(ctx, h));
     int64_t n; KQ_RET(kq_batch_resolve_rows(ctx, input, &n));
     for (kq_col* c : input->cols) KQ_RET(kq_col_resolve_rows(ctx, c, nullptr));
+    KQ_RET(ensure_key_heap(ctx, h, input));
 
     AggArgs A;
     memset(&A, 0, sizeof A);
@@ -1052,7 +1216,7 @@ int kq_hashagg_finalize(kq_ctx* ctx, kq_hashagg* h, kq_batch** out) {
     for (int k = 0; k < F.nkeys; k++) {
         kq_col* c = nullptr;
         int t = h->key_types[(size_t)k];
-        if ((st = kq_col_new(ctx, t, G, true, t == KQ_UTF8 ? G * 7 : 0, &c)) != KQ_OK) return fail(st);
+        if ((st = kq_col_new(ctx, t, G, true, t == KQ_UTF8 ? G * 7 + (int64_t)h->heap_bytes : 0, &c)) != KQ_OK) return fail(st);
         cols.push_back(c);
         cudaMemsetAsync(c->validity, 0, (size_t)((G + 63) / 64) * 8, ctx->stream);
         if (t == KQ_BOOL) cudaMemsetAsync(c->data, 0, (size_t)((G + 63) / 64) * 8, ctx->stream);
@@ -1094,18 +1258,19 @@ int kq_hashagg_finalize(kq_ctx* ctx, kq_hashagg* h, kq_batch** out) {
         if ((st = kq_dev_alloc(ctx, (size_t)(ntiles + 4) * 8, (void**)&scratch)) != KQ_OK) return fail(st);
         scratches.push_back(scratch);
         cudaMemsetAsync(scratch, 0, (size_t)(ntiles + 4) * 8, ctx->stream);
-        PackedLen pl{packed[(size_t)k], c->validity};
+        PackedLen pl{packed[(size_t)k], c->validity, h->heap};
         int sg = (int)std::max<int64_t>(1, std::min<int64_t>(ntiles, (int64_t)ctx->sm_count * 4));
         k_exclusive_offsets<PackedLen><<<sg, 256, 0, ctx->stream>>>(pl, d_pos, c->offsets, scratch + 4, (unsigned int*)scratch, h->d_counters + 8 + k);
         if ((st = launch_check(ctx, "k_exclusive_offsets")) != KQ_OK) return fail(st);
         if (G > 0) {
-            k_unpack_utf8<<<small_grid(ctx, (uint64_t)G), 256, 0, ctx->stream>>>(packed[(size_t)k], c->offsets, d_pos, (uint8_t*)c->data);
+            k_unpack_utf8<<<small_grid(ctx, (uint64_t)G), 256, 0, ctx->stream>>>(packed[(size_t)k], c->offsets, d_pos, (uint8_t*)c->data, h->heap);
             if ((st = launch_check(ctx, "k_unpack_utf8")) != KQ_OK) return fail(st);
         }
     }
     uint64_t c16[16];
     if ((st = kq_read_u64(ctx, h->d_counters, 8 + MAX_KEYS, c16)) != KQ_OK) return fail(st);
     if ((uint32_t)c16[5]) { h->dev_err |= (uint32_t)c16[5]; return fail(sticky_error(ctx, h)); }
+    h->heap_entries = c16[6]; h->heap_bytes = c16[7];
     const int64_t rows = (int64_t)c16[2];
     h->ngroups_host = (int64_t)c16[0]; h->groups_exact = true;
     for (int k = 0; k < F.nkeys; k++) {
@@ -1150,6 +1315,7 @@ int kq_hashagg_merge_allreduce(kq_ctx* ctx, kq_hashagg* h) {
     cudaSetDevice(ctx->device);
     ncclComm_t comm = (ncclComm_t)ctx->comm;
     const int nr = ctx->nranks, me = ctx->rank, stride = h->stride, nkeys = (int)h->groups.size();
+    (void)me;
     // (a sticky error from an earlier call does not return here: the peers are, or will be, in the all-gather, so this
     //  rank joins it and its status word — d_counters[5] still holds the bits — tells everybody)
 
@@ -1168,7 +1334,7 @@ int kq_hashagg_merge_allreduce(kq_ctx* ctx, kq_hashagg* h) {
             // an allocation failure here cannot be reported before the collective without leaving the peers hanging:
             // nothing else has been allocated yet for this merge, so fail the rank hard (the job's launcher aborts the others)
             int st0 = kq_dev_alloc(ctx, (size_t)blockw * 8, (void**)&h->merge_mine);
-            if (st0 == KQ_OK) st0 = kq_dev_alloc(ctx, (size_t)blockw * 8 * nr + 2 * 64 * 8, (void**)&h->merge_all);
+            if (st0 == KQ_OK) st0 = kq_dev_alloc(ctx, (size_t)blockw * 8 * nr + 4 * 64 * 8, (void**)&h->merge_all);
             if (st0 != KQ_OK) return st0;
             h->merge_words = blockw;
         }
@@ -1177,20 +1343,44 @@ int kq_hashagg_merge_allreduce(kq_ctx* ctx, kq_hashagg* h) {
         if (nr > 64) return kq_fail(ctx, KQ_ERR_UNSUPPORTED, "more than 64 ranks");
         cudaMemsetAsync(mine, 0, MERGE_HDR * 8, ctx->stream);
         k_collect_small<<<small_grid(ctx, h->capacity), 256, 0, ctx->stream>>>(h->table, h->capacity, stride, mine, room, (const uint32_t*)(h->d_counters + 5));
-        k_collect_small_done<<<1, 1, 0, ctx->stream>>>(mine);
+        k_collect_small_done<<<1, 1, 0, ctx->stream>>>(mine, h->heap.tab ? h->heap.used : nullptr);
         ctx->launches += 2;
         ncclResult_t r0 = N->AllGather(mine, all, (size_t)blockw, ncclUint64, comm, ctx->stream);
         if (r0 != ncclSuccess) return kq_nccl_fail(ctx, r0, "ncclAllGather");
         k_merge_heads<<<1, 64, 0, ctx->stream>>>(all, blockw, nr, d_heads);
         ctx->launches++;
-        uint64_t heads[128];
-        KQ_RET(kq_read_u64(ctx, d_heads, 2 * nr > 64 ? 64 : 2 * nr, heads));
-        if (2 * nr > 64) KQ_RET(kq_read_u64(ctx, d_heads + 64, 2 * nr - 64, heads + 64));
-        uint64_t total = 0, maxn = 0; uint32_t status = 0;
-        for (int i = 0; i < nr; i++) { total += heads[2 * i]; maxn = std::max(maxn, heads[2 * i]); status |= (uint32_t)heads[2 * i + 1]; }
+        uint64_t heads[256];
+        for (int off = 0; off < 4 * nr; off += 64) KQ_RET(kq_read_u64(ctx, d_heads + off, std::min(64, 4 * nr - off), heads + off));
+        uint64_t total = 0, maxn = 0, str_entries = 0, str_bytes = 0; uint32_t status = 0;
+        for (int i = 0; i < nr; i++) {
+            total += heads[4 * i]; maxn = std::max(maxn, heads[4 * i]); status |= (uint32_t)heads[4 * i + 1];
+            if (i != me) { str_entries += heads[4 * i + 2]; str_bytes += heads[4 * i + 3] + 8 * heads[4 * i + 2]; }
+        }
+        const bool long_keys = str_entries > 0 || heads[4 * me + 2] > 0;          // some rank interned long Utf8 group keys
         if (status) { h->dev_err |= status; return sticky_error(ctx, h); }       // some rank's kernels raised an error: every rank reports it
         if (total == 0) return KQ_OK;
-        if (maxn <= room && !getenv("KQ_NO_SMALL_MERGE")) {
+        const bool small = maxn <= room && !getenv("KQ_NO_SMALL_MERGE");
+        if (long_keys && !small)       // decided on the same gathered data on every rank
+            return kq_fail(ctx, KQ_ERR_UNSUPPORTED, "merging more than %llu partial groups per rank with Utf8 group keys longer than 7 bytes is not implemented", (unsigned long long)room);
+        if (long_keys) {
+            // the strings behind the long keys go along: every rank ends with all groups, so it needs all their bytes
+            unsigned long long *smine = nullptr, *sall = nullptr;
+            int st2 = kq_dev_alloc(ctx, (size_t)STRBLK_WORDS * 8, (void**)&smine);
+            if (st2 == KQ_OK) st2 = kq_dev_alloc(ctx, (size_t)STRBLK_WORDS * 8 * nr, (void**)&sall);
+            if (st2 == KQ_OK) st2 = key_heap_reserve(ctx, h, str_entries, str_bytes);
+            if (st2 != KQ_OK) { fprintf(stderr, "kqgpu: rank %d cannot allocate the key exchange buffers inside a collective merge; aborting\n", me); abort(); }
+            cudaMemsetAsync(smine, 0, 24, ctx->stream);
+            const unsigned long long three = 3;
+            cudaMemcpyAsync(smine + 2, &three, 8, cudaMemcpyHostToDevice, ctx->stream);
+            if (h->heap.tab && heads[4 * me + 2] > 0) { k_heap_export<<<small_grid(ctx, h->heap.cap_mask + 1), 256, 0, ctx->stream>>>(h->heap, smine); ctx->launches++; }
+            ncclResult_t rs = N->AllGather(smine, sall, (size_t)STRBLK_WORDS, ncclUint64, comm, ctx->stream);
+            if (rs == ncclSuccess) { k_heap_import<<<1, 64, 0, ctx->stream>>>(h->heap, sall, nr, me, (uint32_t*)(h->d_counters + 5)); ctx->launches++; }
+            cudaStreamSynchronize(ctx->stream);          // `three` lives on this frame; the buffers go back to the allocator
+            kq_dev_free(ctx, smine); kq_dev_free(ctx, sall);
+            if (rs != ncclSuccess) return kq_nccl_fail(ctx, rs, "ncclAllGather");
+            h->heap_entries += str_entries; h->heap_bytes += str_bytes;          // upper bounds until the next counter read
+        }
+        if (small) {
             uint64_t cap = 1024;
             while (cap < 4 * total) cap <<= 1;
             if (cap > h->capacity) {
@@ -1216,11 +1406,10 @@ int kq_hashagg_merge_allreduce(kq_ctx* ctx, kq_hashagg* h) {
     //    a rank that cannot allocate must not leave its peers waiting in ncclAllGather.
     uint64_t cnt[64];
     {
-        uint64_t heads[128];
+        uint64_t heads[256];
         unsigned long long* d_heads = reinterpret_cast<unsigned long long*>(h->merge_all + h->merge_words * nr);
-        KQ_RET(kq_read_u64(ctx, d_heads, 2 * nr > 64 ? 64 : 2 * nr, heads));
-        if (2 * nr > 64) KQ_RET(kq_read_u64(ctx, d_heads + 64, 2 * nr - 64, heads + 64));
-        for (int i = 0; i < nr; i++) cnt[i] = heads[2 * i];
+        for (int off = 0; off < 4 * nr; off += 64) KQ_RET(kq_read_u64(ctx, d_heads + off, std::min(64, 4 * nr - off), heads + off));
+        for (int i = 0; i < nr; i++) cnt[i] = heads[4 * i];
     }
     const uint64_t G = cnt[me];
     uint64_t maxn = 0;

@@ -67,6 +67,9 @@ struct kq_col {
     int64_t capacity_rows = 0;    // rows the buffers can hold
     kq_lazy_count* lazy = nullptr; // shared, refcounted: resolves n (and nothing else)
     unsigned long long* d_utf8_bytes = nullptr;  // device slot holding data_bytes while lazy
+    // Utf8 length statistics, computed once per column on first use as a group key (kq_hashagg.cu): longest string, and how many
+    // strings / bytes exceed the 7 bytes a packed key word holds
+    int64_t utf8_max_len = -1, utf8_n_long = 0, utf8_bytes_long = 0;
 };
 
 // Row count that becomes known when an event fires (stream compaction output).

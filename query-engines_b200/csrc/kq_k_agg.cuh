@@ -721,6 +721,7 @@ extern "C" __global__ void __launch_bounds__(THREADS, 1) kq_hash_aggregate(const
             RowCtx rc;
             rowctx_init(rc, warp, tile, TILE, A.n, A.err, smem + (size_t)s * A.sp.stage_bytes);
             rc.bbase = bbase[s];
+            rc.heap = A.heap.tab ? &A.heap : nullptr;
             sink.sel = rc.inr;
             Q::eval(A.q, rc, sink);
             __syncwarp();

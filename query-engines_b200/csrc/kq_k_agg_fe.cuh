@@ -28,6 +28,12 @@
 
 namespace kq {
 
+// Branch weights: the rarely taken paths (inserts, exact MIN/MAX updates, refreshes, ragged tiles) are laid out behind the
+// hot loop, whose ~700 instructions then sit in a few contiguous kilobytes instead of being spread over the whole kernel
+// (measured: instruction-cache misses were the largest single stall reason).
+#define KQ_LIKELY(x) (__builtin_expect(!!(x), 1))
+#define KQ_UNLIKELY(x) (__builtin_expect(!!(x), 0))
+
 constexpr int WARPS = KQ_WARPS;              // consumer warps
 constexpr int PRODUCER_WARP = 0;             // service warp first: the warp arbiter favours high warp ids
 constexpr int THREADS = WARPS * 32 + 32;
@@ -77,7 +83,8 @@ struct __align__(16) DirCtl {
 struct Fe {                  // shared-memory addresses (32-bit) and pointers of the CTA front end
     uint32_t a_ctl, a_meta, a_keys;     // DirCtl; [DIR] u32 state; [DIR][NKW] u64 key words
     uint32_t a_mm;                      // [FG + 1][NMM] u64 order-mapped extremes (CTA-shared; row FG is a trash row)
-    uint32_t a_lock, a_bound;           // the CTA lock; [NMM] u64 bounds on the extremes of all groups WITH a value, as the input's own bits
+    uint32_t a_lock, a_bound;           // the CTA lock (directory inserts); [NMM] u64 bounds on the extremes of all groups, as the input's own bits
+    uint32_t a_btoken, a_started, a_finished, a_refreshing;      // bound validity token; first-value event counters; refresh flag
     uint32_t a_lane8, a_lane4;          // this warp's lane-private block + lane * 8 / + NSUM*256 + lane * 4
     DirCtl* ctl;
     uint32_t* meta;
@@ -89,8 +96,11 @@ struct Fe {                  // shared-memory addresses (32-bit) and pointers of
     uint32_t* err;                      // the aggregate's device error word
     unsigned long long* trace;          // debugging (AggArgs::trace)
 };
-#define KQ_FTRACE(code) do { if (fe.trace && blockIdx.x < 16 && (threadIdx.x & 31) == 0) reinterpret_cast<volatile unsigned long long*>(fe.trace)[blockIdx.x * 16 + (threadIdx.x >> 5)] = (unsigned long long)(code); \
-                             if (fe.trace && blockIdx.x == 0 && (threadIdx.x >> 5) == 1) reinterpret_cast<volatile unsigned long long*>(fe.trace)[256 + (threadIdx.x & 31)] = (unsigned long long)(code); } while (0)
+#ifdef KQ_FE_TRACE
+#define KQ_FTRACE(code) do { if (fe.trace && blockIdx.x < 16 && (threadIdx.x & 31) == 0) reinterpret_cast<volatile unsigned long long*>(fe.trace)[blockIdx.x * 16 + (threadIdx.x >> 5)] = (unsigned long long)(code); } while (0)
+#else
+#define KQ_FTRACE(code) do { } while (0)
+#endif
 
 __device__ __forceinline__ uint32_t lds_u32(uint32_t a) { uint32_t v; asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(a)); return v; }
 __device__ __forceinline__ uint64_t lds_u64(uint32_t a) { uint64_t v; asm volatile("ld.shared.u64 %0, [%1];" : "=l"(v) : "r"(a)); return v; }
@@ -213,11 +223,8 @@ __device__ __forceinline__ bool dir_place_all(const Fe& fe, int n, uint32_t s1, 
 }
 
 // Group id of key (kw, nm), inserting it while there is room; -1: the directory cannot take it (the row goes to the
-// global table). Called by ALL lanes of a warp with the same key.
+// global table). Called by ALL lanes of a warp with the same key, the warp HOLDING the CTA lock.
 __device__ __forceinline__ int dir_find_or_insert(const Fe& fe, const uint64_t (&kw)[NKW], uint32_t nm, int lane) {
-    KQ_FTRACE(0x600000);
-    fe_lock(fe, lane);
-    KQ_FTRACE(0x600001);
     volatile DirCtl* ctl = fe.ctl;
     const int n = (int)sh_ld_u32_uniform(fe.a_ctl + 12u);
     int found = -1;
@@ -277,9 +284,8 @@ __device__ __forceinline__ int dir_find_or_insert(const Fe& fe, const uint64_t (
             if (lane == 0) { ctl->s1 = t1; ctl->s2 = t2; ctl->count = (uint32_t)(placed ? n + 1 : n); __threadfence_block(); ctl->gen = ctl->gen + 1u; }
         }
     }
-    KQ_FTRACE(0x600005 + n * 256);
-    fe_unlock(fe, lane);
-    KQ_FTRACE(0x600006 + n * 256);
+    __threadfence_block();
+    __syncwarp();
     return gid;
 }
 
@@ -289,21 +295,26 @@ __device__ __forceinline__ int dir_find_or_insert(const Fe& fe, const uint64_t (
 // takes the exact path — correct, slow, and only for as long as a group has seen nothing but NaNs).
 __device__ __forceinline__ constexpr uint64_t mm_nan_mark(int m) { return ((Q::MM_ISMIN >> m) & 1u) ? ~0ULL - 1ULL : 1ULL; }
 
-// Does row r of this lane touch an extreme that still holds the identity (the group's first value CTA-wide)?
-__device__ __forceinline__ bool fe_exact_needs_lock(const Fe& fe, int gid, const AggSink& sink, int r) {
-    bool need = false;
-#pragma unroll
-    for (int i = 0; i < Q::NIN; i++) {
-        const int FL = Q::IN_FLAGS[i];
-        if (!(FL & (F_MIN | F_MAX))) continue;
-        if (Q::IN_CNT[i] > 0 && !((sink.inok[i] >> r) & 1u)) continue;
-        if (FL & F_MIN) need |= sh_ld_u64(fe.a_mm + (uint32_t)(gid * NMM1 + Q::FE_MIN[i]) * 8u) == mm_identity(Q::FE_MIN[i] < 0 ? 0 : Q::FE_MIN[i]);
-        if (FL & F_MAX) need |= sh_ld_u64(fe.a_mm + (uint32_t)(gid * NMM1 + Q::FE_MAX[i]) * 8u) == mm_identity(Q::FE_MAX[i] < 0 ? 0 : Q::FE_MAX[i]);
-    }
-    return need;
+// ---- bounds without a lock ----------------------------------------------------------------------------------------------
+// A published bound is valid for a row only if it was computed over EVERY group the row may belong to. Two counters frame
+// the "first value of a group" events (started before the value is written, finished after), and the bound carries a
+// token = (started, groups in the directory) taken while no event was in flight and re-checked after the scan. A reader
+// trusts the bound only while the live token still equals the published one: a group inserted or valued since then
+// changes the token, and the reader's rows simply take the exact path until the next refresh.
+constexpr uint32_t TOKEN_NONE = 0xFFFFFFFFu;
+__device__ __forceinline__ uint32_t bound_token(uint32_t started, uint32_t count) { return ((started & 0xFFFFFFu) << 8) | (count & 0xFFu); }
+
+// The exact update of one row: shared-memory compare-and-swap loops on the order-mapped values. A NaN never replaces a held
+// value (Main.kt:552: `value > this.value`); meeting the identity it leaves the NaN mark.
+__device__ __forceinline__ void fe_exact_slot(const Fe& fe, uint32_t a, int m, uint64_t x, bool isnan) {
+    const bool ismin = (Q::MM_ISMIN >> m) & 1u;
+    const uint64_t cur = sh_ld_u64(a);
+    const bool first = cur == mm_identity(m);
+    if (first) { asm volatile("red.shared.add.u32 [%0], 1;" ::"r"(fe.a_started) : "memory"); __threadfence_block(); }
+    if (isnan) { if (first) sh_cas_u64(a, mm_identity(m), mm_nan_mark(m)); }
+    else if (ismin ? x < cur : x > cur) { if (ismin) sh_min_u64(a, x); else sh_max_u64(a, x); }
+    if (first) { __threadfence_block(); asm volatile("red.shared.add.u32 [%0], 1;" ::"r"(fe.a_finished) : "memory"); }
 }
-// The exact update of one row: shared-memory reductions on the order-mapped values. A NaN never replaces a held value
-// (Main.kt:552: `value > this.value`); meeting the identity it leaves the NaN mark (the caller holds the CTA lock then).
 __device__ __forceinline__ void fe_exact_row(const Fe& fe, int gid, const AggSink& sink, int r) {
 #pragma unroll
     for (int i = 0; i < Q::NIN; i++) {
@@ -314,60 +325,49 @@ __device__ __forceinline__ void fe_exact_row(const Fe& fe, int gid, const AggSin
         const bool is_int = (FL & F_INT) != 0;
         const bool isnan = !is_int && as_f64(v) != as_f64(v);
         const uint64_t x = order_map(v, is_int);
-        if (FL & F_MIN) {
-            const uint32_t a = fe.a_mm + (uint32_t)(gid * NMM1 + Q::FE_MIN[i]) * 8u;
-            if (isnan) sh_cas_u64(a, mm_identity(Q::FE_MIN[i] < 0 ? 0 : Q::FE_MIN[i]), mm_nan_mark(Q::FE_MIN[i] < 0 ? 0 : Q::FE_MIN[i]));
-            else if (x < sh_ld_u64(a)) sh_min_u64(a, x);
-        }
-        if (FL & F_MAX) {
-            const uint32_t a = fe.a_mm + (uint32_t)(gid * NMM1 + Q::FE_MAX[i]) * 8u;
-            if (isnan) sh_cas_u64(a, mm_identity(Q::FE_MAX[i] < 0 ? 0 : Q::FE_MAX[i]), mm_nan_mark(Q::FE_MAX[i] < 0 ? 0 : Q::FE_MAX[i]));
-            else if (x > sh_ld_u64(a)) sh_max_u64(a, x);
-        }
+        if (FL & F_MIN) fe_exact_slot(fe, fe.a_mm + (uint32_t)(gid * NMM1 + Q::FE_MIN[i]) * 8u, Q::FE_MIN[i] < 0 ? 0 : Q::FE_MIN[i], x, isnan);
+        if (FL & F_MAX) fe_exact_slot(fe, fe.a_mm + (uint32_t)(gid * NMM1 + Q::FE_MAX[i]) * 8u, Q::FE_MAX[i] < 0 ? 0 : Q::FE_MAX[i], x, isnan);
     }
 }
-// All exact rows of a warp's tile (`rows`: this lane's R-bit mask; gid[r] valid for those). Called by the WHOLE warp.
-// When some row brings a group's first value, the warp takes the CTA lock and resets the bounds BEFORE any value becomes
-// visible (a bound computed earlier does not cover that group; refreshes take the same lock), then everybody updates.
-__device__ __forceinline__ void fe_exact_rows(const Fe& fe, const uint32_t (&gid)[R], uint32_t rows, const AggSink& sink, int lane) {
-    bool need = false;
-#pragma unroll
-    for (int r = 0; r < R; r++) if ((rows >> r) & 1u) need |= fe_exact_needs_lock(fe, (int)gid[r], sink, r);
-    KQ_FTRACE(0x700000);
-    const bool locked = __any_sync(0xffffffffu, need);
-    KQ_FTRACE(0x700001 + (locked ? 16 : 0));
-    if (locked) {
-        fe_lock(fe, lane, 2u);
-        if (lane == 0) {
-#pragma unroll
-            for (int m = 0; m < Q::NMM; m++) sh_st_u64(fe.a_bound + 8u * m, bound_none(m, mm_is_int(m)));
-        }
-        __threadfence_block();
-        __syncwarp();
-    }
+// All exact rows of a lane's tile (`rows`: R-bit mask; gid[r] valid for those). Per lane: nothing here synchronises the warp.
+__device__ __forceinline__ void fe_exact_rows(const Fe& fe, const uint32_t (&gid)[R], uint32_t rows, const AggSink& sink) {
 #pragma unroll
     for (int r = 0; r < R; r++) if ((rows >> r) & 1u) fe_exact_row(fe, (int)gid[r], sink, r);
-    KQ_FTRACE(0x700002);
-    if (locked) fe_unlock(fe, lane);
-    KQ_FTRACE(0x700003);
 }
 
-// Recompute the bounds from the extremes of all groups that have a value (one warp, every few tiles, under the lock).
+// This lane's view of the bounds for the tile it is about to accumulate: the published values if their token is live,
+// else "no bound" (every row exact).
+__device__ __forceinline__ void bounds_read(const Fe& fe, uint64_t (&bnd)[NMM1]) {
+    const uint32_t t1 = sh_ld_u32(fe.a_btoken);
+#pragma unroll
+    for (int m = 0; m < Q::NMM; m++) bnd[m] = sh_ld_u64(fe.a_bound + 8u * m);
+    const uint32_t t2 = sh_ld_u32(fe.a_btoken);
+    const uint32_t live = bound_token(sh_ld_u32(fe.a_started), sh_ld_u32(fe.a_ctl + 12u));
+    if (KQ_UNLIKELY(t1 != t2 || t1 != live)) {
+#pragma unroll
+        for (int m = 0; m < Q::NMM; m++) bnd[m] = bound_none(m, mm_is_int(m));
+    }
+}
+
+// Recompute the bounds (one warp at a time, whoever gets the flag; nobody waits for it).
 __device__ __forceinline__ void mm_bound_refresh(const Fe& fe, int lane) {
     uint32_t got = 1u;
-    if (lane == 0) got = sh_cas_u32(fe.a_lock, 0u, 0x130u + (threadIdx.x >> 5));          // somebody is inserting: try again later
+    if (lane == 0) got = sh_cas_u32(fe.a_refreshing, 0u, 1u);
     if (__shfl_sync(0xffffffffu, got, 0) != 0u) return;
-    __threadfence_block();
+    const uint32_t fin = sh_ld_u32_uniform(fe.a_finished), sta = sh_ld_u32_uniform(fe.a_started);
     const int n = (int)sh_ld_u32_uniform(fe.a_ctl + 12u);
+    bool ok = fin == sta;                         // no first value in flight
+    uint64_t bv[NMM1];
 #pragma unroll
     for (int m = 0; m < Q::NMM; m++) {
         const bool ismin = (Q::MM_ISMIN >> m) & 1u, is_int = mm_is_int(m);
         uint64_t b = ismin ? 0ULL : ~0ULL;               // MIN: the largest group minimum; MAX: the smallest group maximum (order-mapped)
-        bool any = false, none = false;
+        bool none = false;
         for (int g = lane; g < n; g += 32) {
             const uint64_t x = sh_ld_u64(fe.a_mm + (uint32_t)(g * NMM1 + m) * 8u);
-            if (x == mm_identity(m)) { if (is_int) none = true; continue; }      // Int64: the identity is also a value: no bound then
-            any = true;
+            // a group without a value: with a nullable input its rows are caught by the first-row rule (fe_accumulate_row),
+            // so it is skipped; otherwise (its first value is on its way, or Int64 where the identity is also a value) no bound
+            if (x == mm_identity(m)) { if (is_int || !Q::MM_NULLABLE[m]) none = true; continue; }
             b = ismin ? (x > b ? x : b) : (x < b ? x : b);
         }
 #pragma unroll
@@ -375,10 +375,23 @@ __device__ __forceinline__ void mm_bound_refresh(const Fe& fe, int lane) {
             const uint64_t y = __shfl_xor_sync(0xffffffffu, b, o);
             b = ismin ? (y > b ? y : b) : (y < b ? y : b);
         }
-        any = __any_sync(0xffffffffu, any) && !__any_sync(0xffffffffu, none);
-        if (lane == 0) sh_st_u64(fe.a_bound + 8u * m, any ? order_unmap(b, is_int) : bound_none(m, is_int));
+        none = __any_sync(0xffffffffu, none) || n == 0;
+        bv[m] = none ? bound_none(m, is_int) : order_unmap(b, is_int);
     }
-    fe_unlock(fe, lane);
+    // nothing started, nobody joined the directory while we looked? then the bounds cover every group there is
+    ok = ok && sh_ld_u32_uniform(fe.a_started) == sta && (int)sh_ld_u32_uniform(fe.a_ctl + 12u) == n;
+    if (lane == 0) {
+        if (ok) {
+            sh_st_u32(fe.a_btoken, TOKEN_NONE);
+            __threadfence_block();
+#pragma unroll
+            for (int m = 0; m < Q::NMM; m++) sh_st_u64(fe.a_bound + 8u * m, bv[m]);
+            __threadfence_block();
+            sh_st_u32(fe.a_btoken, bound_token(sta, (uint32_t)n));
+        }
+        __threadfence_block();
+        sh_exch_u32(fe.a_refreshing, 0u);
+    }
 }
 
 // Accumulate one row into the lane-private slots of group g (FG = trash) — the branch-free per-row path. All loads of
@@ -407,7 +420,9 @@ __device__ __forceinline__ bool fe_accumulate_row(const Fe& fe, uint32_t g, cons
     for (int i = 0; i < Q::NIN; i++) {
         const int FL = Q::IN_FLAGS[i];
         const bool nullable = Q::IN_CNT[i] > 0;
-        bool first = c0 == 0u;
+        // first value this lane brings to the group: only a nullable input needs the rule (a group all of whose values were
+        // null so far is skipped by the bounds); with a non-nullable input every group has a value from its first row on
+        bool first = false;
         if (nullable) {
             asm volatile("st.shared.u32 [%0], %1;" ::"r"(ca[i]), "r"(cv[i] + 1u) : "memory");
             first = cv[i] == 0u;
@@ -467,8 +482,11 @@ __device__ __forceinline__ void fe_merge_input(uint32_t a_warp, uint64_t* rec, i
 }
 
 // debugging: the last checkpoint every warp of blocks 0..15 reached, written to pinned host memory (readable while the kernel hangs)
-#define KQ_TRACE(code) do { if (A.trace && blockIdx.x < 16 && (threadIdx.x & 31) == 0) reinterpret_cast<volatile unsigned long long*>(A.trace)[blockIdx.x * 16 + (threadIdx.x >> 5)] = (unsigned long long)(code); \
-                            if (A.trace && blockIdx.x == 0 && (threadIdx.x >> 5) == 1) reinterpret_cast<volatile unsigned long long*>(A.trace)[256 + (threadIdx.x & 31)] = (unsigned long long)(code); } while (0)
+#ifdef KQ_FE_TRACE
+#define KQ_TRACE(code) do { if (A.trace && blockIdx.x < 16 && (threadIdx.x & 31) == 0) reinterpret_cast<volatile unsigned long long*>(A.trace)[blockIdx.x * 16 + (threadIdx.x >> 5)] = (unsigned long long)(code); } while (0)
+#else
+#define KQ_TRACE(code) do { } while (0)
+#endif
 
 extern "C" __global__ void __launch_bounds__(THREADS, 1) kq_group_aggregate(const __grid_constant__ AggArgs A) {
     // dynamic shared memory: [S stages][directory state][directory keys][dense keys][dense null masks][extremes][gslot]
@@ -478,7 +496,7 @@ extern "C" __global__ void __launch_bounds__(THREADS, 1) kq_group_aggregate(cons
     __shared__ long long tile_of[S];
     __shared__ long long bbase[S][MAX_COLS];
     __shared__ DirCtl s_ctl;
-    __shared__ uint32_t s_lock, s_limit;
+    __shared__ uint32_t s_lock, s_limit, s_btoken, s_started, s_finished, s_refreshing;
     __shared__ uint64_t s_bound[NMM1];
     const int wid = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int warp = wid - 1;                 // consumer warp index
@@ -496,6 +514,7 @@ extern "C" __global__ void __launch_bounds__(THREADS, 1) kq_group_aggregate(cons
     fe.ctl = &s_ctl; fe.limit = &s_limit; fe.err = A.err; fe.trace = A.trace;
     fe.a_ctl = smem_u32(&s_ctl); fe.a_meta = smem_u32(fe.meta); fe.a_keys = smem_u32(fe.keys); fe.a_mm = smem_u32(fe.mm);
     fe.a_lock = smem_u32(&s_lock); fe.a_bound = smem_u32(s_bound);
+    fe.a_btoken = smem_u32(&s_btoken); fe.a_started = smem_u32(&s_started); fe.a_finished = smem_u32(&s_finished); fe.a_refreshing = smem_u32(&s_refreshing);
     const uint32_t a_warp = smem_u32(lane_blocks) + (uint32_t)(warp < 0 ? 0 : warp) * (uint32_t)((FG + 1) * GS);
     fe.a_lane8 = a_warp + (uint32_t)lane * 8u;
     fe.a_lane4 = a_warp + (uint32_t)Q::NSUM * 256u + (uint32_t)lane * 4u;
@@ -503,7 +522,7 @@ extern "C" __global__ void __launch_bounds__(THREADS, 1) kq_group_aggregate(cons
     for (size_t i = fe_begin + threadIdx.x * 4; i < fe_end; i += THREADS * 4) *reinterpret_cast<uint32_t*>(smem + i) = 0;
     if (threadIdx.x == 0) {
         s_ctl.gen = 0; s_ctl.s1 = 0x9E3779B1u; s_ctl.s2 = 0x85EBCA6Bu; s_ctl.count = 0;
-        s_lock = 0; s_limit = (uint32_t)FG;
+        s_lock = 0; s_limit = (uint32_t)FG; s_btoken = TOKEN_NONE; s_started = 0; s_finished = 0; s_refreshing = 0;
         for (int m = 0; m < Q::NMM; m++) s_bound[m] = bound_none(m, mm_is_int(m));
         for (int s = 0; s < S; s++) { mbar_init(&full[s], 1); mbar_init(&empty[s], WARPS); }
         mbar_fence_init();
@@ -514,30 +533,47 @@ extern "C" __global__ void __launch_bounds__(THREADS, 1) kq_group_aggregate(cons
 
     if (wid == PRODUCER_WARP) {
         if (lane == 0) {
-            // The next ticket is always requested one step early: the L2 round trip of the atomic and the HBM reads of the
-            // tile's Utf8 boundary offsets (stage_bounds_fetch) overlap the wait for a free stage, so string bytes and
-            // fixed-size buffers of a tile are issued together on one barrier.
-            TileBounds tb = {};
-            auto take = [&]() -> long long {
-                // stop taking tiles once the global table is past its threshold: every ticket taken is processed, so the
-                // rows consumed so far are always a prefix of the batch (the host grows the table and resumes)
-                const unsigned long long g = *reinterpret_cast<volatile unsigned long long*>(A.ngroups);
-                if (g > A.stop_threshold) return -1;
-                const long long t = (long long)atomicAdd(A.ticket, 1u) + A.tile_begin;
-                if (t >= A.ntiles) return -1;
-                if (KQ_STAGE_BYTES) stage_bounds_fetch(A.sp, t, TILE, A.n, tb);
-                return t;
-            };
-            long long next = take();
-            for (int kp = 0;; kp++) {
-                const int s = kp % S;
-                { int spins = 0; while (!mbar_test(&empty[s], ((kp / S) & 1) ^ 1)) { __nanosleep(32); if (++spins > SPIN_LIMIT) { atomicOr(A.err, ERR_SPIN_STAGE); break; } } }
-                const long long tile = next;
-                tile_of[s] = tile;
-                if (tile < 0) { mbar_arrive(&full[s]); break; }
-                stage_issue_all(A.sp, smem + (size_t)s * A.sp.stage_bytes, &full[s], tile, TILE, A.n, tb, bbase[s], 0ULL);
-                next = take();
+            // Tiles are dealt statically: block b owns tiles b, b + grid, b + 2 grid, ... — no ticket atomic on the critical path,
+            // and the HBM reads of a tile's Utf8 boundary offsets (stage_bounds_fetch: the byte range of its strings) are issued
+            // PF tiles ahead, so a tile's string bytes and fixed-size buffers go out together on one barrier the moment a stage
+            // is free. (A ticket per tile cost an L2 atomic plus a dependent HBM load, ~2 us, in front of every 1024-row tile.)
+            // A block that stops early (global table past its threshold) records how far it got; the host grows the table and
+            // relaunches with the same grid, every block resuming its own sequence.
+            constexpr int PF = 4;
+            const long long first = A.progress ? (long long)A.progress[blockIdx.x] : 0;
+            auto tile_at = [&](long long j) -> long long { const long long t = A.tile_begin + (long long)blockIdx.x + j * (long long)gridDim.x; return t < A.ntiles ? t : -1; };
+            TileBounds tb[PF];
+            long long tq[PF];
+#pragma unroll
+            for (int u = 0; u < PF; u++) {
+                tq[u] = tile_at(first + u);
+                tb[u] = TileBounds{};
+                if (KQ_STAGE_BYTES && tq[u] >= 0) stage_bounds_fetch(A.sp, tq[u], TILE, A.n, tb[u]);
             }
+            long long issued = 0;
+            bool more = true;
+            // the group count that stops a throttled launch is read one tile ahead (an L2 round trip otherwise in front of every tile)
+            const bool throttled = A.stop_threshold != ~0ULL;
+            unsigned long long ng = throttled ? *reinterpret_cast<volatile unsigned long long*>(A.ngroups) : 0ULL;
+            for (int kp0 = 0; more; kp0 += PF) {
+#pragma unroll
+                for (int u = 0; u < PF; u++) {
+                    if (!more) break;
+                    const int kp = kp0 + u, s = kp % S;
+                    { int spins = 0; while (!mbar_test(&empty[s], ((kp / S) & 1) ^ 1)) { __nanosleep(32); if (++spins > SPIN_LIMIT) { atomicOr(A.err, ERR_SPIN_STAGE); break; } } }
+                    long long tile = tq[u];
+                    if (tile >= 0 && throttled && ng > A.stop_threshold) tile = -1;
+                    tile_of[s] = tile;
+                    if (tile < 0) { mbar_arrive(&full[s]); more = false; break; }
+                    stage_issue_all(A.sp, smem + (size_t)s * A.sp.stage_bytes, &full[s], tile, TILE, A.n, tb[u], bbase[s], 0ULL);
+                    issued++;
+                    if (throttled) ng = *reinterpret_cast<volatile unsigned long long*>(A.ngroups);
+                    tq[u] = tile_at(first + kp + PF);
+                    if (KQ_STAGE_BYTES && tq[u] >= 0) stage_bounds_fetch(A.sp, tq[u], TILE, A.n, tb[u]);
+                }
+            }
+            if (A.progress) A.progress[blockIdx.x] = (unsigned int)(first + issued);
+            atomicAdd(A.ticket, (unsigned int)issued);           // tiles finished by this launch (the host compares the running total with the batch)
         }
     } else {
         AggSink sink;
@@ -552,10 +588,11 @@ extern "C" __global__ void __launch_bounds__(THREADS, 1) kq_group_aggregate(cons
             }
             const long long tile = tile_of[s];
             KQ_TRACE(0x100000 + k * 16 + 1);
-            if (tile < 0) break;
+            if (KQ_UNLIKELY(tile < 0)) break;
             RowCtx rc;
             rowctx_init(rc, warp, tile, TILE, A.n, A.err, smem + (size_t)s * A.sp.stage_bytes);
             rc.bbase = bbase[s];
+            rc.heap = A.heap.tab ? &A.heap : nullptr;
             sink.sel = rc.inr;
             if constexpr (Q::NKEYS == 0) {
 #pragma unroll
@@ -585,8 +622,11 @@ extern "C" __global__ void __launch_bounds__(THREADS, 1) kq_group_aggregate(cons
             // ---- key -> group: one probe per row ------------------------------------------------------------------
             uint32_t gsel[R];                         // group id, FG (trash) for rows that are filtered out or unresolved
             uint32_t slow = sink.sel;                 // rows that still need the general path
-            if (!bypass) {
-                const uint4 c = ctl_snapshot(fe);     // {gen, s1, s2, count}
+            if (KQ_LIKELY(!bypass)) {
+                // {gen, s1, s2, count}, per lane: nothing below that depends on it synchronises the warp (lanes that read different
+                // generations simply disagree on which of their OWN rows missed)
+                uint4 c;
+                asm volatile("ld.volatile.shared.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(c.x), "=r"(c.y), "=r"(c.z), "=r"(c.w) : "r"(fe.a_ctl) : "memory");
                 uint32_t miss = 0;
 #pragma unroll
                 for (int r = 0; r < R; r++) {
@@ -598,8 +638,8 @@ extern "C" __global__ void __launch_bounds__(THREADS, 1) kq_group_aggregate(cons
                     gsel[r] = (on && g >= 0) ? (uint32_t)g : (uint32_t)FG;
                     miss |= (uint32_t)(on && g < 0) << r;
                 }
-                const uint32_t gen2 = sh_ld_u32_uniform(fe.a_ctl);
-                if (gen2 != c.x || (c.x & 1u)) {      // a rebuild ran meanwhile: nothing probed counts
+                const uint32_t gen2 = sh_ld_u32(fe.a_ctl);
+                if (KQ_UNLIKELY(gen2 != c.x || (c.x & 1u))) {      // a rebuild ran meanwhile: nothing probed counts
 #pragma unroll
                     for (int r = 0; r < R; r++) gsel[r] = (uint32_t)FG;
                     miss = sink.sel;
@@ -618,10 +658,11 @@ extern "C" __global__ void __launch_bounds__(THREADS, 1) kq_group_aggregate(cons
             KQ_TRACE(0x100000 + k * 16 + 3);
             uint64_t bnd[NMM1];
 #pragma unroll
-            for (int m = 0; m < Q::NMM; m++) bnd[m] = sh_ld_u64(fe.a_bound + 8u * m);
+            for (int m = 0; m < NMM1; m++) bnd[m] = 0;
+            if (Q::NMM > 0) bounds_read(fe, bnd);
             uint32_t exact = 0;
             bool many_exact = false;
-            if (!bypass) {
+            if (KQ_LIKELY(!bypass)) {
                 uint32_t onmask = 0;
 #pragma unroll
                 for (int r = 0; r < R; r++) {
@@ -632,12 +673,12 @@ extern "C" __global__ void __launch_bounds__(THREADS, 1) kq_group_aggregate(cons
 #ifdef KQ_FE_NOEXACT
                 exact = 0;
 #endif
-                if (Q::NMM > 0 && __any_sync(0xffffffffu, exact != 0)) {
-                    // a lane that took the exact path may have met a group no bound covers yet (first value): the flags of its
-                    // other rows were computed against a possibly stale bound, so all its rows take the exact path
-                    if (exact) exact = onmask;
-                    many_exact = __popc(__ballot_sync(0xffffffffu, exact != 0)) >= 8;
-                    fe_exact_rows(fe, gsel, exact, sink, lane);
+                if (Q::NMM > 0) {
+                    // a lane whose row was the first value it brought to a group may have used a bound that does not cover the
+                    // group: all its rows take the exact path (nullable inputs only; see fe_accumulate_row)
+                    if (Q::ANY_MM_NULLABLE && exact) exact = onmask;
+                    if (KQ_UNLIKELY(exact != 0)) fe_exact_rows(fe, gsel, exact, sink);
+                    many_exact = __popc(__ballot_sync(0xffffffffu, exact != 0)) >= 4;
                 }
             }
 
@@ -647,8 +688,9 @@ extern "C" __global__ void __launch_bounds__(THREADS, 1) kq_group_aggregate(cons
             const int rows = __popc(sink.sel);
             int fe_hits = rows - __popc(slow);
             int rounds = 0;
-            while (__any_sync(0xffffffffu, slow != 0)) {
-                if (++rounds > 64 * R + 4096) { if (lane == 0) atomicOr(A.err, ERR_SPIN_SLOW); break; }      // each round resolves a row or inserts a key
+            bool have_lock = false;           // taken before the first insert and kept until every key of this tile is placed
+            while (KQ_UNLIKELY(__any_sync(0xffffffffu, slow != 0))) {
+                if (++rounds > 66 * R + 4096) { if (lane == 0) atomicOr(A.err, ERR_SPIN_SLOW); break; }      // each round resolves a row or inserts a key
                 KQ_TRACE(0x200000 + rounds * 256 + (slow & 0xff));
                 bool full_dir = true;
                 if (!bypass) {
@@ -683,7 +725,7 @@ extern "C" __global__ void __launch_bounds__(THREADS, 1) kq_group_aggregate(cons
                             slow &= ~(1u << r);
                             fe_hits++;
                         }
-                        if (Q::NMM > 0 && __any_sync(0xffffffffu, hitrows != 0)) fe_exact_rows(fe, gh, hitrows, sink, lane);      // rare path: always the exact compare
+                        if (Q::NMM > 0 && hitrows) fe_exact_rows(fe, gh, hitrows, sink);      // rare path: always the exact compare
                     }
                     if (!__any_sync(0xffffffffu, slow != 0)) break;
                 }
@@ -701,7 +743,9 @@ extern "C" __global__ void __launch_bounds__(THREADS, 1) kq_group_aggregate(cons
                     slow = 0;
                     break;
                 }
-                // insert the first unresolved key of the first lane that has one (whole warp, under the CTA lock)
+                // insert the first unresolved key of the first lane that has one (whole warp, under the CTA lock; the probes are
+                // repeated once under the lock, when the directory cannot change any more, before anything is inserted)
+                if (!have_lock) { fe_lock(fe, lane); have_lock = true; continue; }
                 const uint32_t b = __ballot_sync(0xffffffffu, slow != 0);
                 const int leader = __ffs(b) - 1;
                 const int r0 = __ffs(slow) - 1;             // meaningful on the leader
@@ -732,19 +776,20 @@ extern "C" __global__ void __launch_bounds__(THREADS, 1) kq_group_aggregate(cons
                 }
                 // g >= 0: the next round's probe finds the key (for every lane that waits for it)
             }
+            if (KQ_UNLIKELY(have_lock)) fe_unlock(fe, lane);
             KQ_TRACE(0x100000 + k * 16 + 5);
             // one update of the global group count per warp and tile (a single counter bumped by every insert serialises in the L2)
-            if (__any_sync(0xffffffffu, new_groups != 0)) {
+            if (KQ_UNLIKELY(rounds > 0) && __any_sync(0xffffffffu, new_groups != 0)) {
                 const uint32_t tot = __reduce_add_sync(0xffffffffu, new_groups);
                 if (lane == 0) atomicAdd(A.ngroups, (unsigned long long)tot);
             }
             // refresh the bounds when they look stale (many rows took the exact path), and every 16 tiles to tighten them
 #ifndef KQ_FE_NOREFRESH
-            if (Q::NMM > 0 && (many_exact || ((k + 2 * warp) & 15) == 0)) mm_bound_refresh(fe, lane);
+            if (Q::NMM > 0 && KQ_UNLIKELY(many_exact || ((k + 2 * warp) & 15) == 0)) mm_bound_refresh(fe, lane);
 #endif
             // once the directory is full and this warp mostly misses it, stop probing it (the hint was wrong: high cardinality)
-            const bool dir_is_full = sh_ld_u32_uniform(fe.a_ctl + 12u) >= sh_ld_u32_uniform(smem_u32(&s_limit));
-            if (!bypass && __any_sync(0xffffffffu, fe_hits < rows) && dir_is_full) {
+            // (only a warp that went through the general path can have missed the directory: `rounds` is warp-uniform)
+            if (KQ_UNLIKELY(!bypass && rounds > 0) && sh_ld_u32_uniform(fe.a_ctl + 12u) >= sh_ld_u32_uniform(smem_u32(&s_limit)) && __any_sync(0xffffffffu, fe_hits < rows)) {
                 int hits = fe_hits, tot = rows;
 #pragma unroll
                 for (int o = 16; o; o >>= 1) { hits += __shfl_xor_sync(0xffffffffu, hits, o); tot += __shfl_xor_sync(0xffffffffu, tot, o); }

@@ -36,7 +36,7 @@ constexpr uint32_t RMASK = (R >= 32) ? 0xFFFFFFFFu : ((1u << R) - 1u);
 
 
 // device error bits OR-ed into the ctx status word (kq_internal.h KQ_DEV_ERR_*)
-constexpr uint32_t ERR_DIV0 = 1u, ERR_LONG_KEY = 2u, ERR_NUMBER_FORMAT = 4u, ERR_PARSE_RANGE = 8u;
+constexpr uint32_t ERR_DIV0 = 1u, ERR_LONG_KEY = 2u, ERR_NUMBER_FORMAT = 4u, ERR_PARSE_RANGE = 8u, ERR_KEY_COLLISION = 16u, ERR_KEY_HEAP_FULL = 32u;
 
 // Per-thread view of the current tile.
 struct RowCtx {
@@ -50,6 +50,7 @@ struct RowCtx {
     const unsigned char* stage;      // shared-memory stage holding this tile's staged buffers
     const long long* bbase;          // per column slot: data-buffer offset its staged string bytes start at (-1: not staged)
     int wrow;                        // first row of this warp inside the tile
+    const KeyHeap* heap;             // long Utf8 group keys (NULL: not available to this kernel)
     __device__ __forceinline__ int64_t row0(int j) const { return warp_base + j * 64 + lane * 2; }
     __device__ __forceinline__ int trow0(int j) const { return wrow + j * 64 + lane * 2; }
 };
@@ -64,7 +65,7 @@ __device__ __forceinline__ void rowctx_init(RowCtx& rc, int warp, int64_t tile, 
     rc.warp_base = tile_base + (int64_t)warp * WARP_ROWS;
     rc.full = tile_base + tile_rows <= n;
     uint32_t m = RMASK;
-    if (!rc.full) {
+    if (__builtin_expect(!rc.full, 0)) {
         m = 0;
 #pragma unroll
         for (int j = 0; j < NCHUNK; j++) {
@@ -77,6 +78,7 @@ __device__ __forceinline__ void rowctx_init(RowCtx& rc, int warp, int64_t tile, 
     rc.active = m;
     rc.err = err;
     rc.bbase = nullptr;
+    rc.heap = nullptr;
 }
 
 __device__ __forceinline__ uint4 ldg_nc_v4(const void* p) {
@@ -290,7 +292,7 @@ __device__ __forceinline__ uint32_t utf8_pack_staged(long long base, uint32_t ok
         }
     }
     uint32_t too_long = 0;
-    if (mxtot > 8 || mxlen > 7) {
+    if (__builtin_expect(mxtot > 8 || mxlen > 7, 0)) {
 #pragma unroll 1
         for (int j = 0; j < NCHUNK; j++) {
             int a0, len0, len1;
@@ -308,30 +310,47 @@ __device__ __forceinline__ uint32_t utf8_pack_staged(long long base, uint32_t ok
 // short string (<= 7 bytes) -> packed u64 group key: bytes little-endian, length in the top byte.
 // SB >= 0: the tile's string bytes are staged at byte offset SB of the stage (when they fit: rc.bbase[SLOT] >= 0);
 // that path is branch-free per row (uniform branches per tile only).
+// One string -> its key word, the slow way (out of line, scalar arguments only so that nothing of the caller's tile is
+// forced into local memory): bytes read from global memory; up to 7 bytes are packed, longer strings are interned in the
+// aggregate's key heap (or raise ERR_LONG_KEY in a kernel that has none).
+static __device__ __noinline__ uint64_t utf8_key_slow(const uint8_t* bytes, int a, int len, const KeyHeap* heap, uint32_t* err, bool active) {
+    if (len <= 7) {
+        uint64_t key = 0;
+        for (int i = 0; i < len; i++) key |= (uint64_t)__ldg(bytes + a + i) << (8 * i);
+        return key | ((uint64_t)len << 56);
+    }
+    if (!active) return 0;
+    if (heap == nullptr) { atomicOr(err, ERR_LONG_KEY); return 0; }
+    return utf8_intern(heap, bytes + a, len, err);
+}
 template <int SOFF_OFF, int SB, int SLOT>
 __device__ __forceinline__ void utf8_pack(const QCol& c, uint32_t ok, const RowCtx& rc, uint64_t (&out)[R]) {
     long long base = -1;
     if constexpr (SB >= 0 && SOFF_OFF >= 0) base = rc.bbase[SLOT];
-    uint32_t too_long = 0;
+    uint32_t redo = 0;             // rows whose key the fast path could not produce
     if (base >= 0) {
-        if (rc.full) { if (ok == RMASK) too_long = utf8_pack_staged<SOFF_OFF, SB, true, true>(base, ok, rc, out); else too_long = utf8_pack_staged<SOFF_OFF, SB, true, false>(base, ok, rc, out); }
-        else too_long = utf8_pack_staged<SOFF_OFF, SB, false, false>(base, ok, rc, out);
+        if (rc.full) { if (ok == RMASK) redo = utf8_pack_staged<SOFF_OFF, SB, true, true>(base, ok, rc, out); else redo = utf8_pack_staged<SOFF_OFF, SB, true, false>(base, ok, rc, out); }
+        else redo = utf8_pack_staged<SOFF_OFF, SB, false, false>(base, ok, rc, out);
+        redo &= ok;
     } else {
-        const uint8_t* bytes = reinterpret_cast<const uint8_t*>(c.data);
+        // the tile's string bytes did not fit the stage (long strings): every row the slow way
+        redo = ok;
 #pragma unroll
-        for (int r = 0; r < R; r++) {
-            uint64_t key = 0;
-            if ((ok >> r) & 1u) {
-                int a, b; utf8_bounds<SOFF_OFF>(c.offsets, rc, r, a, b);
-                int len = b - a;
-                if (len > 7) { too_long |= 1u << r; len = 7; }
-                for (int i = 0; i < len; i++) key |= (uint64_t)__ldg(bytes + a + i) << (8 * i);
-                key |= (uint64_t)len << 56;
-            }
-            out[r] = key;
+        for (int r = 0; r < R; r++) out[r] = 0;
+    }
+    if (redo) {
+#pragma unroll 1
+        for (uint32_t m = redo; m; m &= m - 1) {
+            const int r = __ffs(m) - 1;
+            const int32_t* o;
+            if constexpr (SOFF_OFF >= 0) o = reinterpret_cast<const int32_t*>(rc.stage + SOFF_OFF) + rc.trow0(r >> 1) + (r & 1);
+            else o = c.offsets + rc.row0(r >> 1) + (r & 1);
+            const int a = o[0], b = o[1];
+            const uint64_t key = utf8_key_slow(reinterpret_cast<const uint8_t*>(c.data), a, b - a, rc.heap, rc.err, (rc.active >> r) & 1u);
+#pragma unroll
+            for (int rr = 0; rr < R; rr++) if (rr == r) out[rr] = key;
         }
     }
-    if (too_long & ok & rc.active) atomicOr(rc.err, ERR_LONG_KEY);
 }
 
 // CastExpression Utf8 -> Float64: Java Double.parseDouble grammar (rule R5). Decimal inputs with at

@@ -171,7 +171,7 @@ def test_multi_key_and_wide_aggregates(G, oracle, null_frac):
             masked(rng, rng.integers(9000, 9003, n).astype(np.int32), pa.int32(), null_frac).cast(pa.date32())]
     for j in range(6):
         arrs.append(masked(rng, np.floor(rng.random(n) * 100) - 50, pa.float64() if j % 2 else pa.int64(), null_frac))
-    aggs = [("SUM", 3), ("MIN", 4), ("MAX", 5), ("COUNT", 6), ("SUM", 7), ("MAX", 8), ("MIN", 3), ("COUNT", 0)]
+    aggs = [("SUM", 3), ("MIN", 4), ("MAX", 5), ("COUNT", 6), ("SUM", 7), ("MAX", 8), ("MIN", 3), ("COUNT", 4)]       # six distinct inputs (the limit)
     check(G, oracle, arrs, [0, 1, 2], aggs, hint=64, batches=[0, 1, 30_000, 30_000, n])
     check(G, oracle, arrs, [2, 0], aggs, hint=20)
     check(G, oracle, arrs, [], aggs)

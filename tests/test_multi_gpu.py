@@ -135,3 +135,39 @@ def test_high_cardinality_alltoall_repartition(gpu, oracle, world):
             assert not (keys[i] & keys[j]), "after the repartition every key lives on exactly one rank"
     merged = sorted((t for g in got for t in g), key=lambda t: t[0])
     close(merged, want)
+
+
+@pytest.mark.parametrize("world", [2, 4])
+def test_long_utf8_keys_travel_with_the_merge(gpu, oracle, world):
+    """Utf8 group keys longer than 7 bytes are interned per rank (key heap); the all-gather merge ships the strings along, so
+    every rank can emit every group — also groups none of whose rows it saw itself."""
+    if gpu.device_count() < world:
+        pytest.skip(f"needs {world} GPUs")
+    import numpy as np
+    import pyarrow as pa
+    n = 40_000
+    rng = np.random.default_rng(5)
+    names = np.array(["Stockholm", "Uppsala", "Sthlm", "Göteborg by the sea", "Örnsköldsvik", "rank-private-key-%d"], dtype=object)
+    k = names[rng.integers(0, 5, n)].copy()
+    for r in range(world):                       # one long key that only rank r ever sees
+        lo, hi = r * n // world, (r + 1) * n // world
+        k[lo:lo + 50] = "rank-private-key-%d" % r
+    v = np.floor(rng.random(n) * 100)
+    arrs = [pa.array(k, pa.string()), pa.array(v, pa.float64())]
+
+    def plan(E, a0, a1):
+        a = E.HashAggregate([E.col(0)], [("SUM", E.col(1)), ("MIN", E.col(1)), ("MAX", E.col(1)), ("COUNT", E.col(1))], **({"expected_groups": 16} if E is not oracle else {}))
+        a.update(E.RecordBatch.from_arrow([a0, a1]))
+        return a
+
+    def body(r, ctx, E):
+        lo, hi = r * n // world, (r + 1) * n // world
+        a = plan(E, arrs[0].slice(lo, hi - lo), arrs[1].slice(lo, hi - lo))
+        a.merge_allreduce()
+        return rows_of(a.finalize())
+
+    got = run_ranks(gpu, world, body)
+    want = rows_of(plan(oracle, arrs[0], arrs[1]).finalize())
+    for r in range(world):
+        close(got[r], want)
+    assert all(g == got[0] for g in got)
