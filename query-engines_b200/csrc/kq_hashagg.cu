@@ -2,6 +2,7 @@
 // the per-batch launch of the specialised aggregate kernel (kq_k_agg.cuh via kq_codegen.cu / kq_jit.cu),
 // finalisation into the single output batch (Main.kt:635-650) and the table maintenance kernels.
 #include <algorithm>
+#include <chrono>
 #include <cmath>
 #include <cstdio>
 #include <cstdlib>
@@ -682,7 +683,7 @@ static int plan_agg(kq_ctx* ctx, kq_hashagg* h, kq_batch* input, int smem_optin,
         return std::max(0, std::min(FE_MAX_GROUPS, budget / per_group - 1));
     };
     const char* forced = getenv("KQ_AGG_GEOM");
-    int fe_smem = 0;
+    int fe_smem = 0, ctas = 1;
     if (mode == 3) {
         // kq_k_agg_fe.cuh: lane-private SUM/COUNT blocks per consumer warp (the shared-memory data path bounds this kernel,
         // so the warp count only has to hide latency), a stage ring with at least ~48 KB in flight beyond the stage being
@@ -693,11 +694,16 @@ static int plan_agg(kq_ctx* ctx, kq_hashagg* h, kq_batch* input, int smem_optin,
         auto fe_bytes = [&](int g, int warps, int dir) {
             return dir * 4 + dir * nkw * 8 + g * nkw * 8 + (g + 1) * nmm1 * 8 + g * 8 + ((g + 3) & ~3) * 4 + warps * (g + 1) * gs;
         };
-        const int budget = smem_optin - 2048;      // static shared memory of the kernel (barriers, tile bookkeeping, directory control): ~1.3 KB
+        int fr = 0, fw = 0, fs = 0, fc = 0;                           // tuning experiments: KQ_AGG_GEOM="rows,warps[,stages[,CTAs per SM]]"
+        if (forced) sscanf(forced, "%d,%d,%d,%d", &fr, &fw, &fs, &fc);
+        ctas = fc > 0 ? std::min(fc, 4) : 1;
+        // per CTA: its share of the SM's 228 KB (1 KB per resident CTA is the system's), minus the kernel's static shared
+        // memory (barriers, tile bookkeeping, directory control: ~1.8 KB)
+        const int budget = std::min(smem_optin, (228 * 1024 - ctas * 1024) / ctas) - 2048;
         struct Cand { int r, warps; };
-        static const Cand CAND[] = {{8, 6}, {8, 5}, {6, 6}, {8, 4}, {4, 7}, {4, 6}, {4, 5}, {4, 4}, {2, 6}, {2, 4}, {2, 2}};      // rows per thread amortise the per-tile cost: 8 first
-        int fr = 0, fw = 0, fs = 0;                                   // tuning experiments: KQ_AGG_GEOM="rows,warps[,stages]"
-        if (forced) sscanf(forced, "%d,%d,%d", &fr, &fw, &fs);
+        // measured (B200, configs 3 and 5): the kernel is latency-bound, so consumer warps count most, then rows per thread (8-12; the
+        // producer lane's per-tile work is serial); two stages are enough
+        static const Cand CAND[] = {{12, 6}, {8, 7}, {8, 6}, {8, 5}, {6, 6}, {8, 4}, {4, 7}, {4, 6}, {4, 5}, {4, 4}, {2, 6}, {2, 4}, {2, 2}};
         bool found = false;
         // the first candidate (most consumer warps first) that holds `want` groups; a directory of fewer groups only if nothing does
         for (int g = want; g >= 4 && !found; g = g * 3 / 4) {
@@ -708,8 +714,8 @@ static int plan_agg(kq_ctx* ctx, kq_hashagg* h, kq_batch* input, int smem_optin,
                 StagePlan sp;
                 const std::string defs = cg.plan_stages(1 << 30, 1, w * 32 * r, &sp, true);
                 int fe = fe_bytes(g, w, dir);
-                // three stages at least, and ~40 KB in flight beyond the stage being consumed (HBM latency x the SM's bandwidth share)
-                int ring_min = std::max(3 * sp.stage_bytes, sp.stage_bytes + 40 * 1024);
+                // two stages at least, and ~24 KB in flight beyond the stage being consumed (HBM latency x the SM's bandwidth share)
+                int ring_min = std::max(2 * sp.stage_bytes, sp.stage_bytes + 24 * 1024);
                 if (fr > 0) ring_min = 2 * sp.stage_bytes;
                 if (fe + ring_min > budget) { dir >>= 1; fe = fe_bytes(g, w, dir); }       // 8 slots per group still places within a few attempts
                 if (fe + ring_min <= budget) {
@@ -754,7 +760,7 @@ static int plan_agg(kq_ctx* ctx, kq_hashagg* h, kq_batch* input, int smem_optin,
     for (int b = 0; b < A.sp.nbuf; b++) has_bytes |= A.sp.buf[b].kind == SK_BYTES;
     const int ring = A.sp.nstages * A.sp.stage_bytes;
     A.fe_groups = fg;
-    A.geo_r = geo.r; A.geo_warps = geo.warps;
+    A.geo_r = geo.r; A.geo_warps = geo.warps; A.geo_ctas = ctas;
     A.smem_bytes = ring + dir_slots * entry_words * 8 + std::max(fg, 1) * 12 + (fg + 1) * nm * 8 + WARPS * (fg + 1) * 32 * (8 * ns + 4 * ncnt);
     if (mode == 3) A.smem_bytes = ring + fe_smem;
     if (mode == 1) A.smem_bytes += 16 + nparts * 4;
@@ -815,7 +821,7 @@ static int plan_agg(kq_ctx* ctx, kq_hashagg* h, kq_batch* input, int smem_optin,
                             eval_body + "    }\n};\n}  // namespace kq\n";
     *defines_out = "#define KQ_R " + std::to_string(geo.r) + "\n#define KQ_WARPS " + std::to_string(geo.warps) + "\n#define KQ_STAGES " + std::to_string(A.sp.nstages) + "\n#define KQ_FE_GROUPS " + std::to_string(fg) + "\n#define KQ_DIR_SLOTS " +
                                 std::to_string(dir_slots) + (getenv("KQ_L2_PREFETCH") ? "\n#define KQ_L2_PREFETCH " + std::to_string(atoi(getenv("KQ_L2_PREFETCH"))) : std::string()) +
-                                "\n#define KQ_STAGE_BYTES " + (has_bytes ? "1" : "0") + "\n#define KQ_AGG_MODE " + std::to_string(mode) + "\n" +
+                                "\n#define KQ_CTAS " + std::to_string(ctas) + "\n#define KQ_STAGE_BYTES " + (has_bytes ? "1" : "0") + "\n#define KQ_AGG_MODE " + std::to_string(mode) + "\n" +
                                 (getenv("KQ_PART_L2_HINTS") ? "#define KQ_PART_L2_HINTS " + std::to_string(atoi(getenv("KQ_PART_L2_HINTS"))) + "\n" : std::string()) +
                                 (getenv("KQ_FE_CHECK") ? "#define KQ_FE_CHECK 1\n" : "") + (getenv("KQ_FE_NOEXACT") ? "#define KQ_FE_NOEXACT 1\n" : "") +
                                 (getenv("KQ_FE_NOREFRESH") ? "#define KQ_FE_NOREFRESH 1\n" : "") + (getenv("KQ_FE_PROGRESS") ? "#define KQ_FE_TRACE 1\n" : "") + (getenv("KQ_FE_NOMERGE") ? "#define KQ_FE_NOMERGE 1\n" : "");
@@ -937,20 +943,26 @@ static int hashagg_update_fe(kq_ctx* ctx, kq_hashagg* h, kq_batch* input, int64_
     AggArgs A;
     memset(&A, 0, sizeof A);
     std::string defines, gen;
+    const bool timing = getenv("KQ_TIME_AGG") != nullptr;        // host-side cost of one update, per phase (stderr)
+    auto now = [] { return std::chrono::steady_clock::now(); };
+    auto us = [](std::chrono::steady_clock::time_point a, std::chrono::steady_clock::time_point b) { return (long long)std::chrono::duration_cast<std::chrono::microseconds>(b - a).count(); };
+    const auto t0 = now();
     KQ_RET(plan_agg(ctx, h, input, ctx->max_smem_optin, A, &defines, &gen, 3));
+    const auto t1 = now();
     if (n == 0) return KQ_OK;
     const AggGeometry geo{A.geo_r, A.geo_warps};
     const int TILE = geo.tile(), THREADS = geo.threads();
     A.n = n; A.ntiles = (n + TILE - 1) / TILE;
     void* kernel = nullptr;
     KQ_RET(kq_jit_kernel(ctx, defines, gen, KQ_SKEL_AGG_FE, "kq_group_aggregate", A.smem_bytes, &kernel));
-    const int grid = (int)std::min<int64_t>(A.ntiles, (int64_t)ctx->sm_count);
+    const auto t2 = now();
+    const int grid = (int)std::min<int64_t>(A.ntiles, (int64_t)ctx->sm_count * std::max(1, A.geo_ctas));
     // rows that may still create groups after a block has decided to continue (conservative rule only)
     const uint64_t margin = (uint64_t)grid * ((uint64_t)(A.sp.nstages + 1) * TILE + FE_MAX_GROUPS);
 
     // Block b owns tiles b, b + grid, ...; `progress` (device, per block) survives relaunches over this batch, `done` counts
     // the tiles finished so far.
-    if (grid > 512) return kq_fail(ctx, KQ_ERR_UNSUPPORTED, "more than 512 blocks");
+    if (grid > 768) return kq_fail(ctx, KQ_ERR_UNSUPPORTED, "more than 768 blocks");
     unsigned int* d_progress = reinterpret_cast<unsigned int*>(h->d_counters + 128);
     unsigned int* d_progress_snap = reinterpret_cast<unsigned int*>(h->d_counters + 512);
     KQ_CUDA(ctx, cudaMemsetAsync(d_progress, 0, (size_t)grid * 4, ctx->stream));
@@ -995,7 +1007,9 @@ static int hashagg_update_fe(kq_ctx* ctx, kq_hashagg* h, kq_batch* input, int64_
         ctx->launches++;
         uint64_t c[6];
         {
+            const auto t3 = now();
             const int rst = read_counters(ctx, h, c);
+            if (timing) fprintf(stderr, "kq fe update: plan %lld us, kernel lookup %lld us, table + launch %lld us, wait for counters %lld us\n", us(t0, t1), us(t1, t2), us(t2, t3), us(t3, now()));
             if (getenv("KQ_TRACE_AGG"))
                 fprintf(stderr, "kq fe launch: done %lld of %lld tiles, grid %d cap %llu optimistic %d -> st %d groups %llu done %u overflow %u err 0x%x\n", (long long)done,
                         (long long)A.ntiles, grid, (unsigned long long)h->capacity, (int)optimistic, rst, (unsigned long long)c[0], (unsigned)c[1], (unsigned)c[4], (unsigned)c[5]);
@@ -1216,7 +1230,9 @@ int kq_hashagg_finalize(kq_ctx* ctx, kq_hashagg* h, kq_batch** out) {
     for (int k = 0; k < F.nkeys; k++) {
         kq_col* c = nullptr;
         int t = h->key_types[(size_t)k];
-        if ((st = kq_col_new(ctx, t, G, true, t == KQ_UTF8 ? G * 7 + (int64_t)h->heap_bytes : 0, &c)) != KQ_OK) return fail(st);
+        // Utf8 bytes: 7 per group bound the packed keys; with interned (long) keys in play the exact total is read back first
+        const bool long_keys = h->heap.tab != nullptr;
+        if ((st = kq_col_new(ctx, t, G, true, t == KQ_UTF8 ? (long_keys ? 0 : G * 7) : 0, &c)) != KQ_OK) return fail(st);
         cols.push_back(c);
         cudaMemsetAsync(c->validity, 0, (size_t)((G + 63) / 64) * 8, ctx->stream);
         if (t == KQ_BOOL) cudaMemsetAsync(c->data, 0, (size_t)((G + 63) / 64) * 8, ctx->stream);
@@ -1262,7 +1278,7 @@ int kq_hashagg_finalize(kq_ctx* ctx, kq_hashagg* h, kq_batch** out) {
         int sg = (int)std::max<int64_t>(1, std::min<int64_t>(ntiles, (int64_t)ctx->sm_count * 4));
         k_exclusive_offsets<PackedLen><<<sg, 256, 0, ctx->stream>>>(pl, d_pos, c->offsets, scratch + 4, (unsigned int*)scratch, h->d_counters + 8 + k);
         if ((st = launch_check(ctx, "k_exclusive_offsets")) != KQ_OK) return fail(st);
-        if (G > 0) {
+        if (G > 0 && h->heap.tab == nullptr) {
             k_unpack_utf8<<<small_grid(ctx, (uint64_t)G), 256, 0, ctx->stream>>>(packed[(size_t)k], c->offsets, d_pos, (uint8_t*)c->data, h->heap);
             if ((st = launch_check(ctx, "k_unpack_utf8")) != KQ_OK) return fail(st);
         }
@@ -1276,7 +1292,19 @@ int kq_hashagg_finalize(kq_ctx* ctx, kq_hashagg* h, kq_batch** out) {
     for (int k = 0; k < F.nkeys; k++) {
         kq_col* c = cols[(size_t)k];
         c->n = rows;
-        if (h->key_types[(size_t)k] == KQ_UTF8) c->data_bytes = (int64_t)c16[8 + k];
+        if (h->key_types[(size_t)k] != KQ_UTF8) continue;
+        c->data_bytes = (int64_t)c16[8 + k];
+        if (h->heap.tab != nullptr) {
+            // interned keys: a group's string can be of any length and several groups may share one (multi-key GROUP BYs), so
+            // the bytes are allocated for the total the offsets scan just produced (the one extra round trip of this path)
+            if (c->data_bytes > 2147483647LL) return fail(kq_fail(ctx, KQ_ERR_UNSUPPORTED, "more than 2^31-1 bytes of Utf8 group keys in one output batch"));
+            kq_dev_free(ctx, c->data); c->data = nullptr;
+            if ((st = kq_dev_alloc(ctx, (size_t)std::max<int64_t>(c->data_bytes, 16), &c->data)) != KQ_OK) return fail(st);
+            if (rows > 0) {
+                k_unpack_utf8<<<small_grid(ctx, (uint64_t)rows), 256, 0, ctx->stream>>>(packed[(size_t)k], c->offsets, d_pos, (uint8_t*)c->data, h->heap);
+                if ((st = launch_check(ctx, "k_unpack_utf8")) != KQ_OK) return fail(st);
+            }
+        }
     }
     for (size_t a = (size_t)F.nkeys; a < cols.size(); a++) cols[a]->n = rows;
     for (uint64_t*& p : packed) { kq_dev_free(ctx, p); p = nullptr; }

@@ -304,35 +304,49 @@ __device__ __forceinline__ constexpr uint64_t mm_nan_mark(int m) { return ((Q::M
 constexpr uint32_t TOKEN_NONE = 0xFFFFFFFFu;
 __device__ __forceinline__ uint32_t bound_token(uint32_t started, uint32_t count) { return ((started & 0xFFFFFFu) << 8) | (count & 0xFFu); }
 
-// The exact update of one row: shared-memory compare-and-swap loops on the order-mapped values. A NaN never replaces a held
-// value (Main.kt:552: `value > this.value`); meeting the identity it leaves the NaN mark.
-__device__ __forceinline__ void fe_exact_slot(const Fe& fe, uint32_t a, int m, uint64_t x, bool isnan) {
-    const bool ismin = (Q::MM_ISMIN >> m) & 1u;
+// The exact update of one MIN/MAX slot: shared-memory compare-and-swap loops on the order-mapped values. A NaN never
+// replaces a held value (Main.kt:552: `value > this.value`); meeting the identity it leaves the NaN mark. Out of line and
+// with scalar arguments only (nothing of the caller's tile goes through local memory): every beaten bound comes here —
+// a few rows in ten thousand once the bounds are tight — and the per-tile loop only holds the calls.
+static __device__ __noinline__ void fe_exact_slot(uint32_t a, uint32_t a_started, uint32_t a_finished, uint64_t x, bool ismin, bool isnan) {
+    const uint64_t identity = ismin ? ~0ULL : 0ULL;
     const uint64_t cur = sh_ld_u64(a);
-    const bool first = cur == mm_identity(m);
-    if (first) { asm volatile("red.shared.add.u32 [%0], 1;" ::"r"(fe.a_started) : "memory"); __threadfence_block(); }
-    if (isnan) { if (first) sh_cas_u64(a, mm_identity(m), mm_nan_mark(m)); }
+    const bool first = cur == identity;
+    if (first) { asm volatile("red.shared.add.u32 [%0], 1;" ::"r"(a_started) : "memory"); __threadfence_block(); }
+    if (isnan) { if (first) sh_cas_u64(a, identity, ismin ? ~0ULL - 1ULL : 1ULL); }
     else if (ismin ? x < cur : x > cur) { if (ismin) sh_min_u64(a, x); else sh_max_u64(a, x); }
-    if (first) { __threadfence_block(); asm volatile("red.shared.add.u32 [%0], 1;" ::"r"(fe.a_finished) : "memory"); }
+    if (first) { __threadfence_block(); asm volatile("red.shared.add.u32 [%0], 1;" ::"r"(a_finished) : "memory"); }
 }
-__device__ __forceinline__ void fe_exact_row(const Fe& fe, int gid, const AggSink& sink, int r) {
+// One row's values (v[i], bit i of okmask = input i is non-null) into the extremes of group gid.
+__device__ __forceinline__ void fe_exact_vals(const Fe& fe, uint32_t gid, const uint64_t (&v)[Q::NIN > 0 ? Q::NIN : 1], uint32_t okmask) {
 #pragma unroll
     for (int i = 0; i < Q::NIN; i++) {
         const int FL = Q::IN_FLAGS[i];
         if (!(FL & (F_MIN | F_MAX))) continue;
-        if (Q::IN_CNT[i] > 0 && !((sink.inok[i] >> r) & 1u)) continue;
-        const uint64_t v = sink.in[i][r];
+        if (Q::IN_CNT[i] > 0 && !((okmask >> i) & 1u)) continue;
         const bool is_int = (FL & F_INT) != 0;
-        const bool isnan = !is_int && as_f64(v) != as_f64(v);
-        const uint64_t x = order_map(v, is_int);
-        if (FL & F_MIN) fe_exact_slot(fe, fe.a_mm + (uint32_t)(gid * NMM1 + Q::FE_MIN[i]) * 8u, Q::FE_MIN[i] < 0 ? 0 : Q::FE_MIN[i], x, isnan);
-        if (FL & F_MAX) fe_exact_slot(fe, fe.a_mm + (uint32_t)(gid * NMM1 + Q::FE_MAX[i]) * 8u, Q::FE_MAX[i] < 0 ? 0 : Q::FE_MAX[i], x, isnan);
+        const bool isnan = !is_int && as_f64(v[i]) != as_f64(v[i]);
+        const uint64_t x = order_map(v[i], is_int);
+        if (FL & F_MIN) fe_exact_slot(fe.a_mm + (gid * (uint32_t)NMM1 + (uint32_t)(Q::FE_MIN[i] < 0 ? 0 : Q::FE_MIN[i])) * 8u, fe.a_started, fe.a_finished, x, true, isnan);
+        if (FL & F_MAX) fe_exact_slot(fe.a_mm + (gid * (uint32_t)NMM1 + (uint32_t)(Q::FE_MAX[i] < 0 ? 0 : Q::FE_MAX[i])) * 8u, fe.a_started, fe.a_finished, x, false, isnan);
     }
 }
 // All exact rows of a lane's tile (`rows`: R-bit mask; gid[r] valid for those). Per lane: nothing here synchronises the warp.
+// One row at a time through a select chain, so that the update code exists once.
 __device__ __forceinline__ void fe_exact_rows(const Fe& fe, const uint32_t (&gid)[R], uint32_t rows, const AggSink& sink) {
+#pragma unroll 1
+    for (uint32_t todo = rows; todo; todo &= todo - 1u) {
+        const int r = __ffs(todo) - 1;
+        uint64_t v[Q::NIN > 0 ? Q::NIN : 1];
+        uint32_t g = 0, okmask = 0;
 #pragma unroll
-    for (int r = 0; r < R; r++) if ((rows >> r) & 1u) fe_exact_row(fe, (int)gid[r], sink, r);
+        for (int q = 0; q < R; q++) if (q == r) {
+            g = gid[q];
+#pragma unroll
+            for (int i = 0; i < Q::NIN; i++) { v[i] = sink.in[i][q]; okmask |= ((sink.inok[i] >> q) & 1u) << i; }
+        }
+        fe_exact_vals(fe, g, v, okmask);
+    }
 }
 
 // This lane's view of the bounds for the tile it is about to accumulate: the published values if their token is live,
@@ -350,7 +364,7 @@ __device__ __forceinline__ void bounds_read(const Fe& fe, uint64_t (&bnd)[NMM1])
 }
 
 // Recompute the bounds (one warp at a time, whoever gets the flag; nobody waits for it).
-__device__ __forceinline__ void mm_bound_refresh(const Fe& fe, int lane) {
+static __device__ __noinline__ void mm_bound_refresh(Fe fe, int lane) {
     uint32_t got = 1u;
     if (lane == 0) got = sh_cas_u32(fe.a_refreshing, 0u, 1u);
     if (__shfl_sync(0xffffffffu, got, 0) != 0u) return;
@@ -481,6 +495,100 @@ __device__ __forceinline__ void fe_merge_input(uint32_t a_warp, uint64_t* rec, i
     }
 }
 
+// ---- general path: keys that are not in the directory (yet) --------------------------------------------------------------
+// Called by the whole warp when some lane has rows (`slow`) whose probe missed. Looks again (another warp may have
+// inserted the key), inserts missing keys one at a time under the CTA lock, and sends what the directory cannot take to
+// the global table right away. Rows that ended up in the directory come back as group ids: the caller runs them through
+// its one accumulate path a second time. Out of line, every argument by value — the caller keeps its registers, and the
+// few thousand instructions of inserts, rebuilds and global-table probing stay out of the per-tile loop.
+struct NullMasks { uint32_t m[R]; };
+struct Resolved {
+    uint32_t g[R];             // group of each row resolved to the directory, FG otherwise
+    uint32_t new_groups;       // records this lane created in the global table
+    int hits;                  // rows of this lane resolved to the directory
+};
+static __device__ __noinline__ Resolved fe_resolve_slow(const AggArgs* Ap, Fe fe, AggSink sink, NullMasks nms, uint32_t slow, bool bypass, int lane) {
+    const AggArgs& A = *Ap;
+    Resolved out;
+#pragma unroll
+    for (int r = 0; r < R; r++) out.g[r] = (uint32_t)FG;
+    out.new_groups = 0; out.hits = 0;
+    int rounds = 0;
+    bool have_lock = false;           // taken before the first insert and kept until every key of this tile is placed
+    while (__any_sync(0xffffffffu, slow != 0)) {
+        if (++rounds > 66 * R + 4096) { if (lane == 0) atomicOr(A.err, ERR_SPIN_SLOW); break; }      // each round resolves a row or inserts a key
+        KQ_FTRACE(0x200000 + rounds * 256 + (slow & 0xff));
+        bool full_dir = true;
+        if (!bypass) {
+            // look again: another warp may have inserted the key meanwhile (no lock needed for that)
+            const uint4 c = ctl_snapshot(fe);
+            int g2[R];
+#pragma unroll 1
+            for (int r = 0; r < R; r++) {
+                g2[r] = -1;
+                if ((slow >> r) & 1u) {
+                    uint64_t kw[NKW];
+#pragma unroll
+                    for (int k2 = 0; k2 < NKW; k2++) kw[k2] = sink.key[k2][r];
+                    g2[r] = dir_probe<true>(fe, kw, nms.m[r], c.y, c.z);
+                }
+            }
+            const uint32_t gen2 = sh_ld_u32_uniform(fe.a_ctl);
+            const bool valid = gen2 == c.x && !(c.x & 1u);
+            full_dir = valid && c.w >= sh_ld_u32_uniform(smem_u32(fe.limit));
+            if (valid) {
+#pragma unroll 1
+                for (int r = 0; r < R; r++) {
+                    if (g2[r] < 0) continue;
+                    out.g[r] = (uint32_t)g2[r];          // group ids never change once given
+                    slow &= ~(1u << r);
+                    out.hits++;
+                }
+            }
+            if (!__any_sync(0xffffffffu, slow != 0)) break;
+        }
+        if (full_dir) {
+            // the directory takes no more keys: the rest goes to the global table
+#pragma unroll 1
+            for (int r = 0; r < R; r++) {
+                if (!((slow >> r) & 1u)) continue;
+                uint64_t kw[MAX_KEYS];
+#pragma unroll
+                for (int k2 = 0; k2 < MAX_KEYS; k2++) kw[k2] = k2 < Q::NKEYS ? sink.key[k2][r] : 0;
+                uint64_t* rec = table_find_or_insert(A, hash_key(kw, nms.m[r], Q::NKEYS), kw, nms.m[r], &out.new_groups);
+                if (rec) global_accumulate_all<0>(A, rec, sink, r);
+            }
+            slow = 0;
+            break;
+        }
+        // insert the first unresolved key of the first lane that has one (whole warp, under the CTA lock; the probes are
+        // repeated once under the lock, when the directory cannot change any more, before anything is inserted)
+        if (!have_lock) { fe_lock(fe, lane); have_lock = true; continue; }
+        const uint32_t b = __ballot_sync(0xffffffffu, slow != 0);
+        const int leader = __ffs(b) - 1;
+        const int r0 = slow ? __ffs(slow) - 1 : 0;             // meaningful on the leader
+        uint64_t kw[NKW];
+#pragma unroll
+        for (int k2 = 0; k2 < NKW; k2++) kw[k2] = __shfl_sync(0xffffffffu, sink.key[k2][r0], leader);
+        const uint32_t knm = __shfl_sync(0xffffffffu, nms.m[r0], leader);
+        KQ_FTRACE(0x300000 + rounds * 256 + leader);
+        const int g = dir_find_or_insert(fe, kw, knm, lane);
+        KQ_FTRACE(0x400000 + rounds * 256 + (g & 0xff));
+        if (g < 0 && lane == leader) {
+            // not insertable (directory full or unplaceable): this row goes to the global table now
+            uint64_t kg[MAX_KEYS];
+#pragma unroll
+            for (int k2 = 0; k2 < MAX_KEYS; k2++) kg[k2] = k2 < Q::NKEYS ? kw[k2] : 0;
+            uint64_t* rec = table_find_or_insert(A, hash_key(kg, knm, Q::NKEYS), kg, knm, &out.new_groups);
+            if (rec) global_accumulate_all<0>(A, rec, sink, r0);
+            slow &= ~(1u << r0);
+        }
+        // g >= 0: the next round's probe finds the key (for every lane that waits for it)
+    }
+    if (have_lock) fe_unlock(fe, lane);
+    return out;
+}
+
 // debugging: the last checkpoint every warp of blocks 0..15 reached, written to pinned host memory (readable while the kernel hangs)
 #ifdef KQ_FE_TRACE
 #define KQ_TRACE(code) do { if (A.trace && blockIdx.x < 16 && (threadIdx.x & 31) == 0) reinterpret_cast<volatile unsigned long long*>(A.trace)[blockIdx.x * 16 + (threadIdx.x >> 5)] = (unsigned long long)(code); } while (0)
@@ -488,7 +596,10 @@ __device__ __forceinline__ void fe_merge_input(uint32_t a_warp, uint64_t* rec, i
 #define KQ_TRACE(code) do { } while (0)
 #endif
 
-extern "C" __global__ void __launch_bounds__(THREADS, 1) kq_group_aggregate(const __grid_constant__ AggArgs A) {
+#ifndef KQ_CTAS
+#define KQ_CTAS 1
+#endif
+extern "C" __global__ void __launch_bounds__(THREADS, KQ_CTAS) kq_group_aggregate(const __grid_constant__ AggArgs A) {
     // dynamic shared memory: [S stages][directory state][directory keys][dense keys][dense null masks][extremes][gslot]
     //                        [per-warp lane-private blocks of FG + 1 groups]
     extern __shared__ __align__(128) unsigned char smem[];
@@ -655,131 +766,57 @@ extern "C" __global__ void __launch_bounds__(THREADS, 1) kq_group_aggregate(cons
             for (int r = 0; r < R; r++) if (gsel[r] > (uint32_t)FG) { atomicOr(A.err, 0x1000u); gsel[r] = (uint32_t)FG; }
 #endif
             // ---- accumulate (branch-free); bounds are read AFTER the probes: they cover every group probed -----------
+            // One copy of the accumulate code serves both the rows whose probe hit (pass 1, nearly always the only one) and the
+            // rows the general path resolved to a directory group (pass 2, without bounds: always the exact MIN/MAX compare).
             KQ_TRACE(0x100000 + k * 16 + 3);
             uint64_t bnd[NMM1];
 #pragma unroll
             for (int m = 0; m < NMM1; m++) bnd[m] = 0;
             if (Q::NMM > 0) bounds_read(fe, bnd);
-            uint32_t exact = 0;
-            bool many_exact = false;
-            if (KQ_LIKELY(!bypass)) {
-                uint32_t onmask = 0;
-#pragma unroll
-                for (int r = 0; r < R; r++) {
-                    const bool on = gsel[r] != (uint32_t)FG;
-                    onmask |= (uint32_t)on << r;
-                    exact |= (uint32_t)(fe_accumulate_row(fe, gsel[r], sink, r, bnd) && on) << r;
-                }
-#ifdef KQ_FE_NOEXACT
-                exact = 0;
-#endif
-                if (Q::NMM > 0) {
-                    // a lane whose row was the first value it brought to a group may have used a bound that does not cover the
-                    // group: all its rows take the exact path (nullable inputs only; see fe_accumulate_row)
-                    if (Q::ANY_MM_NULLABLE && exact) exact = onmask;
-                    if (KQ_UNLIKELY(exact != 0)) fe_exact_rows(fe, gsel, exact, sink);
-                    many_exact = __popc(__ballot_sync(0xffffffffu, exact != 0)) >= 4;
-                }
-            }
-
-            // ---- general path: keys that are not in the directory (yet) ------------------------------------------------
-            KQ_TRACE(0x100000 + k * 16 + 4);
+            bool many_exact = false, went_slow = false;
             uint32_t new_groups = 0;
             const int rows = __popc(sink.sel);
             int fe_hits = rows - __popc(slow);
-            int rounds = 0;
-            bool have_lock = false;           // taken before the first insert and kept until every key of this tile is placed
-            while (KQ_UNLIKELY(__any_sync(0xffffffffu, slow != 0))) {
-                if (++rounds > 66 * R + 4096) { if (lane == 0) atomicOr(A.err, ERR_SPIN_SLOW); break; }      // each round resolves a row or inserts a key
-                KQ_TRACE(0x200000 + rounds * 256 + (slow & 0xff));
-                bool full_dir = true;
-                if (!bypass) {
-                    // look again: another warp may have inserted the key meanwhile (no lock needed for that)
-                    const uint4 c = ctl_snapshot(fe);
-                    int g2[R];
+#pragma unroll 1
+            for (;;) {
+                if (KQ_LIKELY(!bypass || went_slow)) {
+                    uint32_t exact = 0, onmask = 0;
 #pragma unroll
                     for (int r = 0; r < R; r++) {
-                        g2[r] = -1;
-                        if ((slow >> r) & 1u) {
-                            uint64_t kw[NKW];
-#pragma unroll
-                            for (int k2 = 0; k2 < NKW; k2++) kw[k2] = sink.key[k2][r];
-                            g2[r] = dir_probe<true>(fe, kw, nm[r], c.y, c.z);
-                        }
+                        const bool on = gsel[r] != (uint32_t)FG;
+                        onmask |= (uint32_t)on << r;
+                        exact |= (uint32_t)(fe_accumulate_row(fe, gsel[r], sink, r, bnd) && on) << r;
                     }
-                    const uint32_t gen2 = sh_ld_u32_uniform(fe.a_ctl);
-                    const bool valid = gen2 == c.x && !(c.x & 1u);
-                    full_dir = valid && c.w >= sh_ld_u32_uniform(smem_u32(&s_limit));
-                    if (valid) {
-                        uint64_t nb[NMM1];
-#pragma unroll
-                        for (int m = 0; m < NMM1; m++) nb[m] = 0;
-                        uint32_t hitrows = 0, gh[R];
-#pragma unroll
-                        for (int r = 0; r < R; r++) {
-                            gh[r] = (uint32_t)FG;
-                            if (g2[r] < 0) continue;
-                            gh[r] = (uint32_t)g2[r];
-                            fe_accumulate_row(fe, gh[r], sink, r, nb);
-                            hitrows |= 1u << r;
-                            slow &= ~(1u << r);
-                            fe_hits++;
-                        }
-                        if (Q::NMM > 0 && hitrows) fe_exact_rows(fe, gh, hitrows, sink);      // rare path: always the exact compare
+#ifdef KQ_FE_NOEXACT
+                    exact = 0;
+#endif
+                    if (Q::NMM > 0) {
+                        // a lane whose row was the first value it brought to a group may have used a bound that does not cover the
+                        // group: all its rows take the exact path (nullable inputs only; see fe_accumulate_row)
+                        if (Q::ANY_MM_NULLABLE && exact) exact = onmask;
+                        if (KQ_UNLIKELY(exact != 0)) fe_exact_rows(fe, gsel, exact, sink);
+                        many_exact = many_exact || __popc(__ballot_sync(0xffffffffu, exact != 0)) >= 4;
                     }
-                    if (!__any_sync(0xffffffffu, slow != 0)) break;
                 }
-                if (full_dir) {
-                    // the directory takes no more keys: the rest goes to the global table
+                KQ_TRACE(0x100000 + k * 16 + 4);
+                if (KQ_LIKELY(went_slow || !__any_sync(0xffffffffu, slow != 0))) break;
+                NullMasks nms;
 #pragma unroll
-                    for (int r = 0; r < R; r++) {
-                        if (!((slow >> r) & 1u)) continue;
-                        uint64_t kw[MAX_KEYS];
+                for (int r = 0; r < R; r++) nms.m[r] = nm[r];
+                const Resolved rs = fe_resolve_slow(&A, fe, sink, nms, slow, bypass, lane);
+                went_slow = true;
+                slow = 0;
+                new_groups = rs.new_groups;
+                fe_hits += rs.hits;
+                if (!__any_sync(0xffffffffu, rs.hits != 0)) break;
 #pragma unroll
-                        for (int k2 = 0; k2 < MAX_KEYS; k2++) kw[k2] = k2 < Q::NKEYS ? sink.key[k2][r] : 0;
-                        uint64_t* rec = table_find_or_insert(A, hash_key(kw, nm[r], Q::NKEYS), kw, nm[r], &new_groups);
-                        if (rec) global_accumulate_all<0>(A, rec, sink, r);
-                    }
-                    slow = 0;
-                    break;
-                }
-                // insert the first unresolved key of the first lane that has one (whole warp, under the CTA lock; the probes are
-                // repeated once under the lock, when the directory cannot change any more, before anything is inserted)
-                if (!have_lock) { fe_lock(fe, lane); have_lock = true; continue; }
-                const uint32_t b = __ballot_sync(0xffffffffu, slow != 0);
-                const int leader = __ffs(b) - 1;
-                const int r0 = __ffs(slow) - 1;             // meaningful on the leader
-                uint64_t kw[NKW];
-                uint32_t knm = 0;
+                for (int r = 0; r < R; r++) gsel[r] = rs.g[r];
 #pragma unroll
-                for (int r = 0; r < R; r++)
-                    if (r == r0) {
-#pragma unroll
-                        for (int k2 = 0; k2 < NKW; k2++) kw[k2] = sink.key[k2][r];
-                        knm = nm[r];
-                    }
-#pragma unroll
-                for (int k2 = 0; k2 < NKW; k2++) kw[k2] = __shfl_sync(0xffffffffu, kw[k2], leader);
-                knm = __shfl_sync(0xffffffffu, knm, leader);
-                KQ_TRACE(0x300000 + rounds * 256 + leader);
-                const int g = dir_find_or_insert(fe, kw, knm, lane);
-                KQ_TRACE(0x400000 + rounds * 256 + (g & 0xff));
-                if (g < 0 && lane == leader) {
-                    // not insertable (directory full or unplaceable): this row goes to the global table now
-                    uint64_t kg[MAX_KEYS];
-#pragma unroll
-                    for (int k2 = 0; k2 < MAX_KEYS; k2++) kg[k2] = k2 < Q::NKEYS ? kw[k2] : 0;
-                    uint64_t* rec = table_find_or_insert(A, hash_key(kg, knm, Q::NKEYS), kg, knm, &new_groups);
-#pragma unroll
-                    for (int r = 0; r < R; r++) if (r == r0 && rec) global_accumulate_all<0>(A, rec, sink, r);
-                    slow &= ~(1u << r0);
-                }
-                // g >= 0: the next round's probe finds the key (for every lane that waits for it)
+                for (int m = 0; m < Q::NMM; m++) bnd[m] = bound_none(m, mm_is_int(m));
             }
-            if (KQ_UNLIKELY(have_lock)) fe_unlock(fe, lane);
             KQ_TRACE(0x100000 + k * 16 + 5);
             // one update of the global group count per warp and tile (a single counter bumped by every insert serialises in the L2)
-            if (KQ_UNLIKELY(rounds > 0) && __any_sync(0xffffffffu, new_groups != 0)) {
+            if (KQ_UNLIKELY(went_slow) && __any_sync(0xffffffffu, new_groups != 0)) {
                 const uint32_t tot = __reduce_add_sync(0xffffffffu, new_groups);
                 if (lane == 0) atomicAdd(A.ngroups, (unsigned long long)tot);
             }
@@ -788,8 +825,8 @@ extern "C" __global__ void __launch_bounds__(THREADS, 1) kq_group_aggregate(cons
             if (Q::NMM > 0 && KQ_UNLIKELY(many_exact || ((k + 2 * warp) & 15) == 0)) mm_bound_refresh(fe, lane);
 #endif
             // once the directory is full and this warp mostly misses it, stop probing it (the hint was wrong: high cardinality)
-            // (only a warp that went through the general path can have missed the directory: `rounds` is warp-uniform)
-            if (KQ_UNLIKELY(!bypass && rounds > 0) && sh_ld_u32_uniform(fe.a_ctl + 12u) >= sh_ld_u32_uniform(smem_u32(&s_limit)) && __any_sync(0xffffffffu, fe_hits < rows)) {
+            // (only a warp that went through the general path can have missed the directory: `went_slow` is warp-uniform)
+            if (KQ_UNLIKELY(!bypass && went_slow) && sh_ld_u32_uniform(fe.a_ctl + 12u) >= sh_ld_u32_uniform(smem_u32(&s_limit)) && __any_sync(0xffffffffu, fe_hits < rows)) {
                 int hits = fe_hits, tot = rows;
 #pragma unroll
                 for (int o = 16; o; o >>= 1) { hits += __shfl_xor_sync(0xffffffffu, hits, o); tot += __shfl_xor_sync(0xffffffffu, tot, o); }

@@ -537,11 +537,11 @@ def test_generator_matches_oracle_bit_for_bit(G, oracle):
 
 
 # ---------------------------------------------------------------- front-end geometry corner cases
-@pytest.mark.parametrize("geom", ["8,8", "4,4", "12,7", "6,10"])
+@pytest.mark.parametrize("geom", ["8,7,2", "4,4", "12,6,2", "6,10", "8,3,2,2", "2,2,6,3"])
 def test_group_by_is_geometry_independent(G, oracle, geom, monkeypatch):
-    """The tile geometry of the aggregate kernel (KQ_AGG_GEOM, a tuning variable) changes the front end's capacity and the
-    directory size: "8,8" leaves room for exactly the 50 groups in a 256-slot directory (keys displaced from their home
-    bucket: the second-chance probe), "6,10" for fewer than 50 (the surplus keys live in the global table only)."""
+    """The tile geometry of the aggregate kernel (KQ_AGG_GEOM = "rows per thread, consumer warps[, stages[, CTAs per SM]]",
+    a tuning variable) changes the CTA directory's capacity: "6,10" leaves room for fewer than the 50 groups (the surplus
+    keys live in the global table only), "8,3,2,2" and "2,2,6,3" run two and three CTAs per SM."""
     states = "ALAKAZARCACOCTDEFLGAHIIDILINIAKSKYLAMEMDMAMIMNMSMOMTNENVNHNJNMNYNCNDOHOKORPARISCSDTNTXUTVTVAWAWVWIWY"
     specs = [dict(kind=5, col_id=0, dict=states, dict_width=2), dict(kind=2, col_id=1, flo=0.0, fhi=1000.0, null_per_10k=100)]
     n = 300_000
