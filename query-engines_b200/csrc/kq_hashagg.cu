@@ -823,7 +823,7 @@ static int plan_agg(kq_ctx* ctx, kq_hashagg* h, kq_batch* input, int smem_optin,
                                 std::to_string(dir_slots) + (getenv("KQ_L2_PREFETCH") ? "\n#define KQ_L2_PREFETCH " + std::to_string(atoi(getenv("KQ_L2_PREFETCH"))) : std::string()) +
                                 "\n#define KQ_CTAS " + std::to_string(ctas) + "\n#define KQ_STAGE_BYTES " + (has_bytes ? "1" : "0") + "\n#define KQ_AGG_MODE " + std::to_string(mode) + "\n" +
                                 (getenv("KQ_PART_L2_HINTS") ? "#define KQ_PART_L2_HINTS " + std::to_string(atoi(getenv("KQ_PART_L2_HINTS"))) + "\n" : std::string()) +
-                                (getenv("KQ_FE_CHECK") ? "#define KQ_FE_CHECK 1\n" : "") + (getenv("KQ_FE_NOEXACT") ? "#define KQ_FE_NOEXACT 1\n" : "") +
+                                (getenv("KQ_NO_STAGE_DRAIN") ? "#define KQ_NO_STAGE_DRAIN 1\n" : "") + (getenv("KQ_RING_CHECK") ? "#define KQ_RING_CHECK " + std::to_string(atoi(getenv("KQ_RING_CHECK"))) + "\n" : std::string()) + (getenv("KQ_PART_SCALAR_MERGE") ? "#define KQ_PART_SCALAR_MERGE 1\n" : "") + (getenv("KQ_PART_DROP_SPILL") ? "#define KQ_PART_DROP_SPILL 1\n" : "") + (getenv("KQ_FE_CHECK") ? "#define KQ_FE_CHECK 1\n" : "") + (getenv("KQ_FE_NOEXACT") ? "#define KQ_FE_NOEXACT 1\n" : "") +
                                 (getenv("KQ_FE_NOREFRESH") ? "#define KQ_FE_NOREFRESH 1\n" : "") + (getenv("KQ_FE_PROGRESS") ? "#define KQ_FE_TRACE 1\n" : "") + (getenv("KQ_FE_NOMERGE") ? "#define KQ_FE_NOMERGE 1\n" : "");
     return KQ_OK;
 }
@@ -867,12 +867,14 @@ static int hashagg_update_partitioned(kq_ctx* ctx, kq_hashagg* h, kq_batch* inpu
     // bucket capacity: the mean fill of a (partition, block) bucket plus slack for hash and scheduling imbalance; a
     // bucket that overflows anyway (skewed keys) spills its rows to the plain global path inside pass 1
     const double mean = (double)chunk_rows / ((double)nparts * grid);
-    const int part_cap = (int)(mean * 1.25 + 4.0 * sqrt(mean) + 16.0);
+    int part_cap = (int)(mean * 1.25 + 4.0 * sqrt(mean) + 16.0);
+    if (const char* e = getenv("KQ_PART_CAP")) part_cap = std::max(part_cap, atoi(e));      // debugging: no bucket overflows
     const int tw = A.part_tw;           // tuple words (plan_agg; the kernel derives the same number from the compiled-in layout)
     uint64_t* scratch = nullptr; uint32_t* counts = nullptr;
     const size_t buckets = (size_t)nparts * grid;
     KQ_RET(kq_dev_alloc(ctx, buckets * (size_t)part_cap * tw * 8, (void**)&scratch));
-    int st = kq_dev_alloc(ctx, buckets * 4 + 64, (void**)&counts);
+    const bool ring_check = getenv("KQ_RING_CHECK") != nullptr;        // debugging: per-tile consumption counters behind the bucket counts
+    int st = kq_dev_alloc(ctx, buckets * 4 + 64 + (ring_check ? (size_t)ntiles * 4 : 0), (void**)&counts);
     if (st != KQ_OK) { kq_dev_free(ctx, scratch); return st; }
     auto done = [&](int s) { kq_dev_free(ctx, scratch); kq_dev_free(ctx, counts); return s; };
     unsigned long long* d_max = h->d_counters + 3;
@@ -896,6 +898,7 @@ static int hashagg_update_partitioned(kq_ctx* ctx, kq_hashagg* h, kq_batch* inpu
         A.part_log2 = 0; while ((1 << A.part_log2) < nparts) A.part_log2++;
         if (cudaMemsetAsync(h->d_counters + 1, 0, 8, ctx->stream) != cudaSuccess || cudaMemsetAsync(counts, 0, buckets * 4, ctx->stream) != cudaSuccess)
             return done(kq_cuda_fail(ctx, cudaGetLastError(), "cudaMemsetAsync"));
+        if (ring_check) { cudaMemsetAsync(counts + buckets + 16, 0, (size_t)ntiles * 4, ctx->stream); A.trace = reinterpret_cast<unsigned long long*>(counts + buckets + 16); }
         void* kargs[] = {&A};
         cudaError_t ce = cudaLaunchKernel(k_scatter, dim3(grid), dim3(THREADS), kargs, (size_t)A.smem_bytes, ctx->stream);
         if (ce != cudaSuccess) return done(kq_cuda_fail(ctx, ce, "cudaLaunchKernel(kq_hash_aggregate, partition scatter)"));
@@ -909,6 +912,17 @@ static int hashagg_update_partitioned(kq_ctx* ctx, kq_hashagg* h, kq_batch* inpu
         h->ngroups_host = (int64_t)c[0];
         const int64_t taken = std::min<int64_t>((int64_t)(uint32_t)c[1], tile_end - tile_begin);
         const uint64_t max_bucket = c[3];
+        if (ring_check) {
+            std::vector<unsigned int> seen((size_t)ntiles);
+            cudaMemcpy(seen.data(), counts + buckets + 16, (size_t)ntiles * 4, cudaMemcpyDeviceToHost);
+            int bad = 0;
+            for (int64_t t = tile_begin; t < tile_end; t++)
+                if ((int)seen[(size_t)t] != geo.warps && bad++ < 20) fprintf(stderr, "kq ring check: tile %lld consumed by %u warps (want %d)\n", (long long)t, seen[(size_t)t], geo.warps);
+            fprintf(stderr, "kq ring check: %d tiles with a wrong consumer count\n", bad);
+        }
+        if (getenv("KQ_TRACE_AGG"))
+            fprintf(stderr, "kq partitioned pass 1: tiles [%lld, %lld) taken %lld, nparts %d grid %d bucket cap %d (max fill %llu), table cap %llu, groups after pass 1 %llu\n", (long long)tile_begin,
+                    (long long)tile_end, (long long)taken, nparts, grid, part_cap, (unsigned long long)max_bucket, (unsigned long long)h->capacity, (unsigned long long)c[0]);
         // ---- pass 2: reduce the partitions; a block in flight may add up to one partition's rows as new groups
         const uint64_t margin2 = (uint64_t)std::min<int64_t>(ctx->sm_count, nparts) * std::max<uint64_t>(1, max_bucket * (uint64_t)grid);
         int part_begin = 0;
@@ -926,6 +940,8 @@ static int hashagg_update_partitioned(kq_ctx* ctx, kq_hashagg* h, kq_batch* inpu
             if ((st = read_counters(ctx, h, c)) != KQ_OK) return done(st);
             if ((uint32_t)c[4] != 0) return done(kq_fail(ctx, KQ_ERR_ILLEGAL_STATE, "aggregation table overflow"));
             h->ngroups_host = (int64_t)c[0];
+            if (getenv("KQ_TRACE_AGG"))
+                fprintf(stderr, "kq partitioned pass 2: from partition %d, tickets %u, table cap %llu, groups %llu\n", part_begin, (unsigned)c[1], (unsigned long long)h->capacity, (unsigned long long)c[0]);
             part_begin += (int)std::min<int64_t>((int64_t)(uint32_t)c[1], nparts - part_begin);
         }
         tile_begin += taken;

@@ -724,8 +724,15 @@ extern "C" __global__ void __launch_bounds__(THREADS, 1) kq_hash_aggregate(const
             rc.heap = A.heap.tab ? &A.heap : nullptr;
             sink.sel = rc.inr;
             Q::eval(A.q, rc, sink);
+#ifdef KQ_RING_CHECK
+            if ((KQ_RING_CHECK & 2) && lane == 0 && A.trace) atomicAdd(reinterpret_cast<unsigned int*>(A.trace) + tile, 1u);      // debugging: warps per tile
+#endif
+#ifdef KQ_NO_STAGE_DRAIN
             __syncwarp();
-            if (lane == 0) mbar_arrive(&empty[s]);       // everything needed is in registers now
+            if (lane == 0) mbar_arrive(&empty[s]);
+#else
+            stage_release(&empty[s], &tile_of[s], (uint32_t)tile, A.err, lane);       // everything needed is in registers now
+#endif
 
             // canonical key words + null masks of the R owned rows
             uint32_t nm[R];
@@ -809,6 +816,9 @@ extern "C" __global__ void __launch_bounds__(THREADS, 1) kq_hash_aggregate(const
             // pass 1 of the partitioned path: rows whose bucket is full (skewed keys) stay in `slow` and take the
             // scalar global path below (table_find_or_insert + global_accumulate_all), like any other overflow row
             if (KQ_AGG_MODE == 1 && slow) { slow = partition_scatter(A, smem_u32(part_cursor), sink, nm, slow); }
+#ifdef KQ_PART_DROP_SPILL
+            if (KQ_AGG_MODE == 1) slow = 0;           // debugging: rows of full buckets vanish
+#endif
 #if KQ_AGG_MODE == 2
             if (true) {
 #pragma unroll
@@ -866,6 +876,9 @@ extern "C" __global__ void __launch_bounds__(THREADS, 1) kq_hash_aggregate(const
                 if (tot >= 64 && hits * 8 < tot) { if (++low_tiles >= 2) bypass = true; }
                 else low_tiles = 0;
             } else low_tiles = 0;
+#ifdef KQ_RING_CHECK
+            if ((KQ_RING_CHECK & 4) && lane == 0 && A.trace) atomicAdd(reinterpret_cast<unsigned int*>(A.trace) + tile, 1u);      // at the END of the tile: timing of the ring untouched
+#endif
         }
     }
 
@@ -1007,7 +1020,11 @@ extern "C" __global__ void __launch_bounds__(PR_THREADS, 1) kq_agg_partition_red
         __syncthreads();
         // merge the table into the global one: once per distinct key of the partition
         uint32_t fresh = 0;
+#ifdef KQ_PART_SCALAR_MERGE
+        part_merge_table(A, T, tid, PR_THREADS, fresh);
+#else
         part_merge_table_batched<4>(A, T, tid, PR_THREADS, fresh);
+#endif
         if (fresh) atomicAdd(&s_new, fresh);
         __syncthreads();
         if (tid == 0 && s_new) atomicAdd(A.ngroups, (unsigned long long)s_new);       // one update per partition, not per group

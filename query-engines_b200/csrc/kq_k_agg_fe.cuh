@@ -711,8 +711,7 @@ extern "C" __global__ void __launch_bounds__(THREADS, KQ_CTAS) kq_group_aggregat
                 sink.keyok[0] = RMASK;
             }
             Q::eval(A.q, rc, sink);
-            __syncwarp();
-            if (lane == 0) mbar_arrive(&empty[s]);       // everything needed is in registers now
+            stage_release(&empty[s], &tile_of[s], (uint32_t)tile, A.err, lane);       // everything needed is in registers now
             KQ_TRACE(0x100000 + k * 16 + 2);
 
             // canonical key words + null masks of the R owned rows

@@ -160,9 +160,11 @@ extern "C" __global__ void __launch_bounds__(THREADS, 1) kq_project(const __grid
     constexpr int S = KQ_STAGES;
     extern __shared__ __align__(128) unsigned char stages[];
     __shared__ uint64_t full[S], empty[S];
+    __shared__ uint32_t drain_word;          // stage_release reads it back (always 0)
     const int wid = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int warp = wid - NSERVICE;         // consumer warp index
     if (threadIdx.x == 0) {
+        drain_word = 0;
         for (int s = 0; s < S; s++) { mbar_init(&full[s], 1); mbar_init(&empty[s], WARPS); }
         mbar_fence_init();
     }
@@ -187,8 +189,7 @@ extern "C" __global__ void __launch_bounds__(THREADS, 1) kq_project(const __grid
         RowCtx rc;
         rowctx_init(rc, warp, tile, TILE, A.n, A.err, stages + (size_t)s * A.sp.stage_bytes);
         Q::project(A.q, rc, sink);
-        __syncwarp();
-        if (lane == 0) mbar_arrive(&empty[s]);
+        stage_release(&empty[s], &drain_word, 0u, A.err, lane);
     }
 }
 #endif  // KQ_KERNEL_PROJECT
@@ -356,8 +357,7 @@ extern "C" __global__ void __launch_bounds__(THREADS, 1) kq_filter_project(const
                 if ((sel >> r) & 1u) selring[(head + sink.rank[r]) & (CAP - 1)] = (int32_t)(rc.row0(r >> 1) + (r & 1));
         }
         head += wt;
-        __syncwarp();
-        if (lane == 0) mbar_arrive(&empty[s]);       // the input stage is free again
+        stage_release(&empty[s], &tile_of[s], (uint32_t)tile, A.err, lane);       // the input stage is free again
         // ---- step B for every pending tile whose prefix has arrived
         while (kb <= k && step_b(false)) {}
     }

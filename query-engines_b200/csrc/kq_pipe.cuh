@@ -50,6 +50,22 @@ __device__ __forceinline__ bool mbar_test(uint64_t* bar, uint32_t parity) {
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
     while (!mbar_try_wait(bar, parity)) {}
 }
+
+// Hand a stage back to the producer: called by ALL lanes of a consumer warp after their last read of the stage.
+// The shared-memory loads of a warp can still be in flight when its next instruction issues, and nothing holds an
+// mbarrier arrive back behind them (the SASS is LDS ...; WARPSYNC; SYNCS.ARRIVE with no scoreboard wait in between).
+// Measured on B200 with heavily skewed consumer warps (tests/test_gpu_parity.py, skewed partition keys): without the
+// drain below a few warp-tiles in ten thousand were read from a stage that had already been refilled. The drain reads
+// one shared word whose value is known (`word` must hold `expect`) and branches on it: loads of a warp return in order,
+// so once this one is back every earlier load of the stage is too. A mismatch is a protocol violation and is reported.
+constexpr uint32_t ERR_STAGE_PROTOCOL = 0x2000u;
+__device__ __forceinline__ void stage_release(uint64_t* empty_bar, const void* word, uint32_t expect, uint32_t* err, int lane) {
+    __syncwarp();
+    uint32_t d;
+    asm volatile("ld.volatile.shared.u32 %0, [%1];" : "=r"(d) : "r"(smem_u32(word)) : "memory");
+    if (d != expect) atomicOr(err, ERR_STAGE_PROTOCOL);
+    if (lane == 0) mbar_arrive(empty_bar);
+}
 // 1-D TMA bulk copy global -> shared, completion counted in bytes on `bar`.
 __device__ __forceinline__ void bulk_g2s(void* dst_smem, const void* src, uint32_t bytes, uint64_t* bar) {
     asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
