@@ -273,13 +273,13 @@ struct FinArgs {
 
 // Output positions are reserved once per warp and chunk of 1024 table slots (one counter bumped by every warp
 // for every 32 slots serialises in the L2 when the table has tens of millions of slots).
+template <int CH>                              // slots per lane and chunk: 32 for big tables (few position atomics), 1 for small ones (every lane busy)
 __global__ void k_finalize(const __grid_constant__ FinArgs F) {
     const int lane = threadIdx.x & 31;
-    constexpr int CH = 32;                      // slots per lane and chunk
     const uint64_t warp0 = (blockIdx.x * (uint64_t)blockDim.x + threadIdx.x) >> 5, nwarps = ((uint64_t)gridDim.x * blockDim.x) >> 5;
     for (uint64_t c0 = warp0 * (32 * CH); c0 < F.cap; c0 += nwarps * (32 * CH)) {
         uint32_t mine = 0;
-#pragma unroll 8
+#pragma unroll (CH < 8 ? CH : 8)
         for (int j = 0; j < CH; j++) {
             const uint64_t s = c0 + (uint64_t)j * 32 + lane;
             if (s < F.cap && (uint32_t)F.table[s * F.stride] == HDR_FULL) mine |= 1u << j;
@@ -703,7 +703,7 @@ static int plan_agg(kq_ctx* ctx, kq_hashagg* h, kq_batch* input, int smem_optin,
         struct Cand { int r, warps; };
         // measured (B200, configs 3 and 5): the kernel is latency-bound, so consumer warps count most, then rows per thread (8-12; the
         // producer lane's per-tile work is serial); two stages are enough
-        static const Cand CAND[] = {{12, 6}, {8, 7}, {8, 6}, {8, 5}, {6, 6}, {8, 4}, {4, 7}, {4, 6}, {4, 5}, {4, 4}, {2, 6}, {2, 4}, {2, 2}};
+        static const Cand CAND[] = {{8, 7}, {12, 6}, {8, 6}, {8, 5}, {6, 6}, {8, 4}, {4, 7}, {4, 6}, {4, 5}, {4, 4}, {2, 6}, {2, 4}, {2, 2}};
         bool found = false;
         // the first candidate (most consumer warps first) that holds `want` groups; a directory of fewer groups only if nothing does
         for (int g = want; g >= 4 && !found; g = g * 3 / 4) {
@@ -1278,7 +1278,8 @@ int kq_hashagg_finalize(kq_ctx* ctx, kq_hashagg* h, kq_batch** out) {
     F.max_rows = (unsigned long long)G;
     F.err = (uint32_t*)(h->d_counters + 5);
     if (G > 0) {
-        k_finalize<<<small_grid(ctx, h->capacity), 256, 0, ctx->stream>>>(F);
+        if (h->capacity <= (1u << 18)) k_finalize<1><<<small_grid(ctx, h->capacity), 256, 0, ctx->stream>>>(F);
+        else k_finalize<32><<<small_grid(ctx, h->capacity), 256, 0, ctx->stream>>>(F);
         if ((st = launch_check(ctx, "k_finalize")) != KQ_OK) return fail(st);
     }
     // Utf8 keys: packed words -> offsets (device-wide scan over d_pos rows) + bytes; the byte total of key k lands in d_counters[8 + k]

@@ -289,6 +289,89 @@ __device__ __forceinline__ int dir_find_or_insert(const Fe& fe, const uint64_t (
     return gid;
 }
 
+// Insert up to 32 keys at once — every lane may propose one (`has`), all of them ABSENT from the directory (the caller
+// probed under the lock). Whole warp, the warp holding the CTA lock. Lanes that propose the same key elect a leader;
+// leaders take consecutive group ids, claim their home slots (BUSY marker -> key words -> state word, so that a lock-free
+// reader never sees a state word next to another key's words) and one rebuild settles all collisions of the batch.
+// Returns the group id of the lane's key, -1 if the directory could not take it (full, or unplaceable).
+// (A CTA's first tile brings all keys of a low-cardinality query at once: three or four of these rounds instead of one
+// round per key — measured 60 us less at the start of every kernel, which is most of a small batch.)
+constexpr uint32_t META_BUSY = 0xFFFFFFFFu;          // fails dir_probe's `g < FG` test under every null mask
+__device__ __forceinline__ int dir_insert_batch(const Fe& fe, bool has, const uint64_t (&kw)[NKW], uint32_t nm, int lane) {
+    volatile DirCtl* ctl = fe.ctl;
+    const uint32_t hasmask = __ballot_sync(0xffffffffu, has);
+    uint32_t grp = 0;                                // lanes proposing the same key as this one
+    if (has) {
+        grp = __match_any_sync(hasmask, nm);
+#pragma unroll
+        for (int k = 0; k < NKW; k++) grp &= __match_any_sync(hasmask, (unsigned long long)kw[k]);
+    }
+    __syncwarp();
+    const int head = has ? __ffs(grp) - 1 : 0;
+    const bool leader = has && head == lane;
+    const uint32_t leaders = __ballot_sync(0xffffffffu, leader);
+    const int n = (int)sh_ld_u32_uniform(fe.a_ctl + 12u);
+    const int limit = (int)sh_ld_u32_uniform(smem_u32(fe.limit));
+    const int room = limit > n ? limit - n : 0;
+    const int rank = __popc(leaders & ((1u << lane) - 1u));
+    int gid = (leader && rank < room) ? n + rank : -1;
+    const int add = min(__popc(leaders), room);
+    if (add > 0) {
+        if (gid >= 0) {
+#pragma unroll
+            for (int k = 0; k < NKW; k++) fe.gkeys[gid * NKW + k] = kw[k];
+            fe.gnm[gid] = nm;
+        }
+        __threadfence_block();
+        __syncwarp();
+        const uint32_t s1 = sh_ld_u32_uniform(fe.a_ctl + 4u), s2 = sh_ld_u32_uniform(fe.a_ctl + 8u);
+        bool collided = false;
+        if (gid >= 0) {
+            const uint32_t slot = dir_slot(kw, nm, s1, s2);
+            if (sh_cas_u32(fe.a_meta + slot * 4u, 0u, META_BUSY) != 0u) collided = true;
+            else {
+#pragma unroll
+                for (int k = 0; k < NKW; k++) sh_st_u64(fe.a_keys + slot * (8u * NKW) + 8u * k, kw[k]);
+                __threadfence_block();
+                sh_st_u32(fe.a_meta + slot * 4u, (uint32_t)(gid + 1) | (nm << 8));
+            }
+        }
+        if (!__any_sync(0xffffffffu, collided)) {
+            __threadfence_block();
+            __syncwarp();
+            if (lane == 0) ctl->count = (uint32_t)(n + add);
+        } else {
+            // some home slot was taken: new multipliers until every key of the directory (old and new) sits in its home slot
+            if (lane == 0) ctl->gen = ctl->gen + 1u;          // odd: probes in flight are void
+            __threadfence_block();
+            __syncwarp();
+            bool placed = false;
+            uint32_t t1 = s1, t2 = s2;
+            for (int a = 0; a < REBUILD_ATTEMPTS && !placed; a++) {
+                t1 = (t1 * 0x2C1B3C6Du + 0x297A2D39u) | 1u;
+                t2 = ((t2 ^ (t1 >> 7)) * 0x9E3779B1u + 0x85EBCA6Bu) | 1u;
+                placed = dir_place_all(fe, n + add, t1, t2, lane);
+                __syncwarp();
+            }
+            int keep = n + add;
+            if (!placed) {
+                // keys no multiplier separates (never seen; possible in principle): keep the old directory, which places its n
+                // keys, stop inserting, and send the batch to the global table
+                dir_place_all(fe, n, s1, s2, lane);
+                t1 = s1; t2 = s2; keep = n; gid = -1;
+                if (lane == 0) *reinterpret_cast<volatile uint32_t*>(fe.limit) = (uint32_t)n;
+            }
+            __threadfence_block();
+            __syncwarp();
+            if (lane == 0) { ctl->s1 = t1; ctl->s2 = t2; ctl->count = (uint32_t)keep; __threadfence_block(); ctl->gen = ctl->gen + 1u; }
+        }
+    }
+    __threadfence_block();
+    __syncwarp();
+    gid = __shfl_sync(0xffffffffu, gid, head);       // the leader's answer for every lane of its key
+    return has ? gid : -1;
+}
+
 // ---- the exact MIN/MAX path (rare) --------------------------------------------------------------------------------------
 // Sentinels of the CTA-shared extremes (order-mapped): the identity = "no non-null value yet"; a second NaN-patterned value
 // = "only NaNs so far" (any real value replaces it; while a group holds it the refreshed bound is a NaN, so every row
@@ -327,8 +410,19 @@ __device__ __forceinline__ void fe_exact_vals(const Fe& fe, uint32_t gid, const 
         const bool is_int = (FL & F_INT) != 0;
         const bool isnan = !is_int && as_f64(v[i]) != as_f64(v[i]);
         const uint64_t x = order_map(v[i], is_int);
-        if (FL & F_MIN) fe_exact_slot(fe.a_mm + (gid * (uint32_t)NMM1 + (uint32_t)(Q::FE_MIN[i] < 0 ? 0 : Q::FE_MIN[i])) * 8u, fe.a_started, fe.a_finished, x, true, isnan);
-        if (FL & F_MAX) fe_exact_slot(fe.a_mm + (gid * (uint32_t)NMM1 + (uint32_t)(Q::FE_MAX[i] < 0 ? 0 : Q::FE_MAX[i])) * 8u, fe.a_started, fe.a_finished, x, false, isnan);
+        // The bounds hold for ALL groups, so most rows that beat one do not beat their own group's extreme (with 50 groups ~4 in
+        // 5): one look at the group's current value settles those here, and only a real improvement (or a first value) pays
+        // for the call and the compare-and-swap.
+        if (FL & F_MIN) {
+            const uint32_t a = fe.a_mm + (gid * (uint32_t)NMM1 + (uint32_t)(Q::FE_MIN[i] < 0 ? 0 : Q::FE_MIN[i])) * 8u;
+            const uint64_t cur = sh_ld_u64(a);
+            if (cur == ~0ULL || (!isnan && x < cur)) fe_exact_slot(a, fe.a_started, fe.a_finished, x, true, isnan);
+        }
+        if (FL & F_MAX) {
+            const uint32_t a = fe.a_mm + (gid * (uint32_t)NMM1 + (uint32_t)(Q::FE_MAX[i] < 0 ? 0 : Q::FE_MAX[i])) * 8u;
+            const uint64_t cur = sh_ld_u64(a);
+            if (cur == 0ULL || (!isnan && x > cur)) fe_exact_slot(a, fe.a_started, fe.a_finished, x, false, isnan);
+        }
     }
 }
 // All exact rows of a lane's tile (`rows`: R-bit mask; gid[r] valid for those). Per lane: nothing here synchronises the warp.
@@ -469,29 +563,37 @@ __device__ __forceinline__ void global_accumulate_all(const AggArgs& A, uint64_t
     }
 }
 
-// Merge the lane-private slots of group g (this warp's copy) into its global record.
+// Merge the lane-private slots of group g — the copies of ALL consumer warps, summed per lane first — into its global
+// record: one atomic per group and slot for the whole CTA (every CTA of the grid updates the same few records at exit; with
+// one atomic per warp those same-address updates were a quarter of a small batch's kernel time).
 template <int I>
-__device__ __forceinline__ void fe_merge_input(uint32_t a_warp, uint64_t* rec, int g, int lane, const unsigned long long (&c)[Q::NCNT]) {
+__device__ __forceinline__ void fe_merge_input(uint32_t a_blocks, uint64_t* rec, int g, int lane, const unsigned long long (&c)[Q::NCNT]) {
     if constexpr (I < Q::NIN) {
         constexpr int FL = Q::IN_FLAGS[I];
+        constexpr uint32_t WB = (uint32_t)((FG + 1) * GS);      // bytes between the blocks of consecutive warps
         const unsigned long long n = c[Q::IN_CNT[I]];
-        if (n != 0) {                                       // this warp saw no non-null value of input I in group g otherwise
+        if (n != 0) {                                       // the CTA saw no non-null value of input I in group g otherwise
             if (lane == 0) atomicAdd(reinterpret_cast<unsigned long long*>(rec + Q::REC_NN[I]), n);
             if constexpr ((FL & F_SUM) != 0) {
-                uint64_t x = lds_u64(a_warp + (uint32_t)g * GS + (uint32_t)Q::FE_SUM[I] * 256u + (uint32_t)lane * 8u);
+                const uint32_t a = a_blocks + (uint32_t)g * GS + (uint32_t)Q::FE_SUM[I] * 256u + (uint32_t)lane * 8u;
                 if constexpr ((FL & F_INT) != 0) {
+                    uint64_t x = 0;
+#pragma unroll
+                    for (int w = 0; w < WARPS; w++) x += lds_u64(a + (uint32_t)w * WB);
 #pragma unroll
                     for (int o = 16; o; o >>= 1) x += __shfl_xor_sync(0xffffffffu, x, o);
                     if (lane == 0) atomicAdd(reinterpret_cast<unsigned long long*>(rec + Q::REC_SUM[I]), (unsigned long long)x);
                 } else {
-                    double f = as_f64(x);
+                    double f = 0.0;
+#pragma unroll
+                    for (int w = 0; w < WARPS; w++) f = __dadd_rn(f, as_f64(lds_u64(a + (uint32_t)w * WB)));
 #pragma unroll
                     for (int o = 16; o; o >>= 1) f = __dadd_rn(f, __shfl_xor_sync(0xffffffffu, f, o));
                     if (lane == 0) atomicAdd(reinterpret_cast<double*>(rec + Q::REC_SUM[I]), f);
                 }
             }
         }
-        fe_merge_input<I + 1>(a_warp, rec, g, lane, c);
+        fe_merge_input<I + 1>(a_blocks, rec, g, lane, c);
     }
 }
 
@@ -515,11 +617,12 @@ static __device__ __noinline__ Resolved fe_resolve_slow(const AggArgs* Ap, Fe fe
     out.new_groups = 0; out.hits = 0;
     int rounds = 0;
     bool have_lock = false;           // taken before the first insert and kept until every key of this tile is placed
+    bool fresh_view = false;          // lock held and probed under it: whatever is still in `slow` is known to be absent from the directory
     while (__any_sync(0xffffffffu, slow != 0)) {
         if (++rounds > 66 * R + 4096) { if (lane == 0) atomicOr(A.err, ERR_SPIN_SLOW); break; }      // each round resolves a row or inserts a key
         KQ_FTRACE(0x200000 + rounds * 256 + (slow & 0xff));
         bool full_dir = true;
-        if (!bypass) {
+        if (!bypass && !fresh_view) {
             // look again: another warp may have inserted the key meanwhile (no lock needed for that)
             const uint4 c = ctl_snapshot(fe);
             int g2[R];
@@ -546,6 +649,9 @@ static __device__ __noinline__ Resolved fe_resolve_slow(const AggArgs* Ap, Fe fe
                 }
             }
             if (!__any_sync(0xffffffffu, slow != 0)) break;
+            fresh_view = have_lock && valid;      // under the lock nobody else changes the directory
+        } else if (!bypass) {
+            full_dir = sh_ld_u32_uniform(fe.a_ctl + 12u) >= sh_ld_u32_uniform(smem_u32(fe.limit));
         }
         if (full_dir) {
             // the directory takes no more keys: the rest goes to the global table
@@ -561,29 +667,41 @@ static __device__ __noinline__ Resolved fe_resolve_slow(const AggArgs* Ap, Fe fe
             slow = 0;
             break;
         }
-        // insert the first unresolved key of the first lane that has one (whole warp, under the CTA lock; the probes are
-        // repeated once under the lock, when the directory cannot change any more, before anything is inserted)
+        // Insert under the CTA lock, a batch per round: the probes are repeated under the lock (only this warp can change the
+        // directory now), then every lane proposes the key of its first unresolved row and dir_insert_batch takes them all.
         if (!have_lock) { fe_lock(fe, lane); have_lock = true; continue; }
-        const uint32_t b = __ballot_sync(0xffffffffu, slow != 0);
-        const int leader = __ffs(b) - 1;
-        const int r0 = slow ? __ffs(slow) - 1 : 0;             // meaningful on the leader
+        if (!fresh_view) continue;                 // a rebuild was in flight during the probe under the lock (cannot be: ours are done) — look again
+        // every lane proposes the key of its first unresolved row
+        const bool has = slow != 0;
+        const int r0 = has ? __ffs(slow) - 1 : 0;
         uint64_t kw[NKW];
 #pragma unroll
-        for (int k2 = 0; k2 < NKW; k2++) kw[k2] = __shfl_sync(0xffffffffu, sink.key[k2][r0], leader);
-        const uint32_t knm = __shfl_sync(0xffffffffu, nms.m[r0], leader);
-        KQ_FTRACE(0x300000 + rounds * 256 + leader);
-        const int g = dir_find_or_insert(fe, kw, knm, lane);
+        for (int k2 = 0; k2 < NKW; k2++) kw[k2] = sink.key[k2][r0];
+        const uint32_t knm = nms.m[r0];
+        KQ_FTRACE(0x300000 + rounds * 256);
+        const int g = dir_insert_batch(fe, has, kw, knm, lane);
         KQ_FTRACE(0x400000 + rounds * 256 + (g & 0xff));
-        if (g < 0 && lane == leader) {
-            // not insertable (directory full or unplaceable): this row goes to the global table now
-            uint64_t kg[MAX_KEYS];
+        if (has) {
+            if (g >= 0) {
+#pragma unroll 1
+                for (int r = 0; r < R; r++) {
+                    if (!((slow >> r) & 1u)) continue;
+                    bool eq = nms.m[r] == knm;
 #pragma unroll
-            for (int k2 = 0; k2 < MAX_KEYS; k2++) kg[k2] = k2 < Q::NKEYS ? kw[k2] : 0;
-            uint64_t* rec = table_find_or_insert(A, hash_key(kg, knm, Q::NKEYS), kg, knm, &out.new_groups);
-            if (rec) global_accumulate_all<0>(A, rec, sink, r0);
-            slow &= ~(1u << r0);
+                    for (int k2 = 0; k2 < NKW; k2++) eq &= sink.key[k2][r] == kw[k2];
+                    if (eq) { out.g[r] = (uint32_t)g; slow &= ~(1u << r); out.hits++; }
+                }
+            } else {
+                // not insertable (directory full or unplaceable): this row goes to the global table now
+                uint64_t kg[MAX_KEYS];
+#pragma unroll
+                for (int k2 = 0; k2 < MAX_KEYS; k2++) kg[k2] = k2 < Q::NKEYS ? kw[k2] : 0;
+                uint64_t* rec = table_find_or_insert(A, hash_key(kg, knm, Q::NKEYS), kg, knm, &out.new_groups);
+                if (rec) global_accumulate_all<0>(A, rec, sink, r0);
+                slow &= ~(1u << r0);
+            }
         }
-        // g >= 0: the next round's probe finds the key (for every lane that waits for it)
+        fresh_view = false;            // other lanes' keys joined the directory: the next round looks again (still under the lock)
     }
     if (have_lock) fe_unlock(fe, lane);
     return out;
@@ -860,18 +978,22 @@ extern "C" __global__ void __launch_bounds__(THREADS, KQ_CTAS) kq_group_aggregat
     __syncthreads();
     KQ_TRACE(0x500003);
     if (warp >= 0) {
-        for (int g = 0; g < G; g++) {
+        const uint32_t a_blocks = smem_u32(lane_blocks);
+        constexpr uint32_t WB = (uint32_t)((FG + 1) * GS);
+        for (int g = warp; g < G; g += WARPS) {             // the groups are dealt to the warps; each sums all warps' copies
             if (gslot[g] == ~0ULL) continue;
             uint64_t* rec = A.table + gslot[g];
             unsigned long long c[Q::NCNT];
 #pragma unroll
             for (int j = 0; j < Q::NCNT; j++) {
-                unsigned long long x = lds_u32(a_warp + (uint32_t)g * GS + (uint32_t)Q::NSUM * 256u + (uint32_t)j * 128u + (uint32_t)lane * 4u);
+                unsigned long long x = 0;
+#pragma unroll
+                for (int w = 0; w < WARPS; w++) x += lds_u32(a_blocks + (uint32_t)w * WB + (uint32_t)g * GS + (uint32_t)Q::NSUM * 256u + (uint32_t)j * 128u + (uint32_t)lane * 4u);
 #pragma unroll
                 for (int o = 16; o; o >>= 1) x += __shfl_xor_sync(0xffffffffu, x, o);
                 c[j] = x;
             }
-            fe_merge_input<0>(a_warp, rec, g, lane, c);
+            fe_merge_input<0>(a_blocks, rec, g, lane, c);
         }
     }
     KQ_TRACE(0x500002);

@@ -64,6 +64,7 @@ __device__ __forceinline__ void stage_release(uint64_t* empty_bar, const void* w
     uint32_t d;
     asm volatile("ld.volatile.shared.u32 %0, [%1];" : "=r"(d) : "r"(smem_u32(word)) : "memory");
     if (d != expect) atomicOr(err, ERR_STAGE_PROTOCOL);
+    __syncwarp();                 // every lane has its word back (lanes do not run in lockstep: lane 0 must not arrive — and let `word` change — before the others looked)
     if (lane == 0) mbar_arrive(empty_bar);
 }
 // 1-D TMA bulk copy global -> shared, completion counted in bytes on `bar`.
