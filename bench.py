@@ -94,8 +94,9 @@ class GroupBy(Workload):
 
     @property
     def kernel(self):
-        # high cardinality runs the partitioned path: scatter (kq_hash_aggregate, KQ_AGG_MODE 1) + kq_agg_partition_reduce
-        return "kq_hash_aggregate+kq_agg_partition_reduce" if self.kind == "high" else "kq_hash_aggregate"
+        # high cardinality runs the partitioned path: scatter (kq_hash_aggregate, KQ_AGG_MODE 1) + kq_agg_partition_reduce;
+        # low cardinality (configs 3 and 5) the CTA-directory kernel of csrc/kq_k_agg_fe.cuh
+        return "kq_hash_aggregate+kq_agg_partition_reduce" if self.kind == "high" else "kq_group_aggregate"
 
     def specs(self):
         if self.kind == "low":

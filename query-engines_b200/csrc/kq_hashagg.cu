@@ -1576,38 +1576,63 @@ int kq_hashagg_repartition_alltoall(kq_ctx* ctx, kq_hashagg* h) {
     ncclComm_t comm = (ncclComm_t)ctx->comm;
     const int nr = ctx->nranks, me = ctx->rank, stride = h->stride, nkeys = (int)h->groups.size();
     if (nr > 64) return kq_fail(ctx, KQ_ERR_UNSUPPORTED, "more than 64 ranks");
-    KQ_RET(kq_check_device_errors(ctx));
-    KQ_RET(refresh_group_count(ctx, h));
+    // Whatever goes wrong on this rank before the exchange (a sticky kernel error, an allocation that fails, a shape this
+    // path does not support) is NOT returned right away: the peers are, or will be, inside the all-gather of step 2, so this
+    // rank joins it with a status word next to its bucket sizes, and every rank leaves with an error on the same data.
+    int lst = sticky_error(ctx, h);
+    if (lst == KQ_OK) lst = kq_check_device_errors(ctx);
+    if (lst == KQ_OK) lst = refresh_group_count(ctx, h);
+    if (lst == KQ_OK && h->heap.tab && h->heap_entries > 0)
+        lst = kq_fail(ctx, KQ_ERR_UNSUPPORTED, "repartitioning an aggregate with Utf8 group keys longer than 7 bytes is not implemented (merge_allreduce carries them)");
     const uint64_t G = (uint64_t)h->ngroups_host;
+    const int W = nr + 1;                     // words per rank in the exchanged matrix: bucket sizes + status
 
     // 1. bucket the partial records by hash(key) % nranks: count, then scatter into contiguous buckets
-    unsigned long long* d_meta = nullptr;     // [0..nr) counts, [nr..2nr) bases, [2nr..3nr) cursors, [3nr..3nr+nr*nr) count matrix
-    KQ_RET(kq_dev_alloc(ctx, (size_t)(3 * nr + nr * nr) * 8, (void**)&d_meta));
+    unsigned long long* d_meta = nullptr;     // [0..nr) counts, [nr..2nr) bases, [2nr..3nr) cursors, [3nr..3nr+nr*W) count matrix (+ status per rank)
+    KQ_RET(kq_dev_alloc(ctx, (size_t)(3 * nr + nr * W) * 8, (void**)&d_meta));      // a few hundred bytes from the context's pool
     uint64_t* sendbuf = nullptr; uint64_t* recvbuf = nullptr; uint64_t* newtab = nullptr;
     auto cleanup = [&](int s) { kq_dev_free(ctx, d_meta); kq_dev_free(ctx, sendbuf); kq_dev_free(ctx, recvbuf); if (s != KQ_OK) kq_dev_free(ctx, newtab); return s; };
-    cudaMemsetAsync(d_meta, 0, (size_t)(3 * nr + nr * nr) * 8, ctx->stream);
-    k_count_parts<<<small_grid(ctx, h->capacity), 256, 0, ctx->stream>>>(h->table, h->capacity, stride, nkeys, nr, d_meta);
-    int st = launch_check(ctx, "k_count_parts");
-    if (st != KQ_OK) return cleanup(st);
+    cudaMemsetAsync(d_meta, 0, (size_t)(3 * nr + nr * W) * 8, ctx->stream);
     uint64_t cnt[64], base[64];
-    if ((st = kq_read_u64(ctx, d_meta, nr, cnt)) != KQ_OK) return cleanup(st);
-    uint64_t acc = 0;
-    for (int p = 0; p < nr; p++) { base[p] = acc; acc += cnt[p]; }
-    cudaMemcpyAsync(d_meta + nr, base, (size_t)nr * 8, cudaMemcpyHostToDevice, ctx->stream);
-    if ((st = kq_dev_alloc(ctx, (size_t)std::max<uint64_t>(G, 1) * stride * 8, (void**)&sendbuf)) != KQ_OK) return cleanup(st);
-    k_collect_records<<<small_grid(ctx, h->capacity), 256, 0, ctx->stream>>>(h->table, h->capacity, stride, nkeys, sendbuf, d_meta + 2 * nr, nr, d_meta + nr);
-    if ((st = launch_check(ctx, "k_collect_records")) != KQ_OK) return cleanup(st);
+    for (int p = 0; p < 64; p++) cnt[p] = base[p] = 0;
+    if (lst == KQ_OK) {
+        k_count_parts<<<small_grid(ctx, h->capacity), 256, 0, ctx->stream>>>(h->table, h->capacity, stride, nkeys, nr, d_meta);
+        lst = launch_check(ctx, "k_count_parts");
+    }
+    if (lst == KQ_OK) lst = kq_read_u64(ctx, d_meta, nr, cnt);
+    if (lst == KQ_OK) {
+        uint64_t acc = 0;
+        for (int p = 0; p < nr; p++) { base[p] = acc; acc += cnt[p]; }
+        cudaMemcpyAsync(d_meta + nr, base, (size_t)nr * 8, cudaMemcpyHostToDevice, ctx->stream);
+        lst = kq_dev_alloc(ctx, (size_t)std::max<uint64_t>(G, 1) * stride * 8, (void**)&sendbuf);
+    }
+    if (lst == KQ_OK) {
+        k_collect_records<<<small_grid(ctx, h->capacity), 256, 0, ctx->stream>>>(h->table, h->capacity, stride, nkeys, sendbuf, d_meta + 2 * nr, nr, d_meta + nr);
+        lst = launch_check(ctx, "k_collect_records");
+    }
 
-    // 2. everybody learns everybody's bucket sizes
+    // 2. everybody learns everybody's bucket sizes — and whether everybody got this far
     unsigned long long* d_mat = d_meta + 3 * nr;
-    cudaMemcpyAsync(d_mat + (size_t)me * nr, d_meta, (size_t)nr * 8, cudaMemcpyDeviceToDevice, ctx->stream);
-    ncclResult_t r = N->AllGather(d_mat + (size_t)me * nr, d_mat, (size_t)nr, ncclUint64, comm, ctx->stream);
+    {
+        uint64_t row[65];
+        for (int p = 0; p < nr; p++) row[p] = lst == KQ_OK ? cnt[p] : 0;
+        row[nr] = lst == KQ_OK ? 0 : 1;
+        cudaMemcpyAsync(d_mat + (size_t)me * W, row, (size_t)W * 8, cudaMemcpyHostToDevice, ctx->stream);
+        cudaStreamSynchronize(ctx->stream);            // `row` and `base` live on this frame
+    }
+    ncclResult_t r = N->AllGather(d_mat + (size_t)me * W, d_mat, (size_t)W, ncclUint64, comm, ctx->stream);
     if (r != ncclSuccess) return cleanup(kq_nccl_fail(ctx, r, "ncclAllGather"));
-    std::vector<uint64_t> mat((size_t)nr * nr);
+    std::vector<uint64_t> mat((size_t)nr * W);
+    int st = KQ_OK;
     for (int s = 0; s < nr; s++)       // kq_read_u64 moves at most 64 words at a time
-        if ((st = kq_read_u64(ctx, d_mat + (size_t)s * nr, nr, mat.data() + (size_t)s * nr)) != KQ_OK) return cleanup(st);
+        for (int off = 0; off < W; off += 64)
+            if ((st = kq_read_u64(ctx, d_mat + (size_t)s * W + off, std::min(64, W - off), mat.data() + (size_t)s * W + off)) != KQ_OK) return cleanup(st);
+    bool peer_failed = false;
+    for (int s = 0; s < nr; s++) peer_failed |= mat[(size_t)s * W + nr] != 0;
+    if (lst != KQ_OK) return cleanup(lst);
+    if (peer_failed) return cleanup(kq_fail(ctx, KQ_ERR_ILLEGAL_STATE, "repartition abandoned: another rank failed before the exchange"));
     uint64_t R = 0, roff[64];
-    for (int s = 0; s < nr; s++) { roff[s] = R; if (s != me) R += mat[(size_t)s * nr + me]; }
+    for (int s = 0; s < nr; s++) { roff[s] = R; if (s != me) R += mat[(size_t)s * W + me]; }
 
     // 3. one-shot all-to-all over NVSwitch: grouped send/recv of the buckets
     if ((st = kq_dev_alloc(ctx, (size_t)std::max<uint64_t>(R, 1) * stride * 8, (void**)&recvbuf)) != KQ_OK) return cleanup(st);
@@ -1615,7 +1640,7 @@ int kq_hashagg_repartition_alltoall(kq_ctx* ctx, kq_hashagg* h) {
     for (int p = 0; p < nr && r == ncclSuccess; p++) {
         if (p == me) continue;
         if (cnt[p]) r = N->Send(sendbuf + base[p] * stride, (size_t)cnt[p] * stride, ncclUint64, p, comm, ctx->stream);
-        const uint64_t rc = mat[(size_t)p * nr + me];
+        const uint64_t rc = mat[(size_t)p * W + me];
         if (r == ncclSuccess && rc) r = N->Recv(recvbuf + roff[p] * stride, (size_t)rc * stride, ncclUint64, p, comm, ctx->stream);
     }
     ncclResult_t r2 = N->GroupEnd();
