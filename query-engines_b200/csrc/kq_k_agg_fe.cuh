@@ -549,7 +549,26 @@ __device__ __forceinline__ bool fe_accumulate_row(const Fe& fe, uint32_t g, cons
                 if (FL & F_MIN) e |= !(as_f64(v) >= as_f64(bnd[Q::FE_MIN[i] < 0 ? 0 : Q::FE_MIN[i]]));
                 if (FL & F_MAX) e |= !(as_f64(v) <= as_f64(bnd[Q::FE_MAX[i] < 0 ? 0 : Q::FE_MAX[i]]));
             }
-            exact |= e && valid[i];
+            e = e && valid[i];
+            // Second look, only for a row that beat a bound (a few per thousand: the bounds hold for ALL groups, so with 50 groups
+            // four in five of those rows do not beat their own group's extreme): the group's current values decide whether
+            // the row leaves the tile loop for the exact path at all. A first value (identity) and the NaN mark always do.
+            if (KQ_UNLIKELY(e) && !first) {
+                const bool is_int = (FL & F_INT) != 0;
+                const bool isnan = !is_int && as_f64(v) != as_f64(v);
+                const uint64_t x = order_map(v, is_int);
+                bool need = false;
+                if (FL & F_MIN) {
+                    const uint64_t cur = sh_ld_u64(fe.a_mm + (g * (uint32_t)NMM1 + (uint32_t)(Q::FE_MIN[i] < 0 ? 0 : Q::FE_MIN[i])) * 8u);
+                    need |= cur == ~0ULL || (!isnan && x < cur);
+                }
+                if (FL & F_MAX) {
+                    const uint64_t cur = sh_ld_u64(fe.a_mm + (g * (uint32_t)NMM1 + (uint32_t)(Q::FE_MAX[i] < 0 ? 0 : Q::FE_MAX[i])) * 8u);
+                    need |= cur == 0ULL || (!isnan && x > cur);
+                }
+                e = need;
+            }
+            exact |= e;
         }
     }
     return exact;
@@ -939,7 +958,8 @@ extern "C" __global__ void __launch_bounds__(THREADS, KQ_CTAS) kq_group_aggregat
             }
             // refresh the bounds when they look stale (many rows took the exact path), and every 16 tiles to tighten them
 #ifndef KQ_FE_NOREFRESH
-            if (Q::NMM > 0 && KQ_UNLIKELY(many_exact || ((k + 2 * warp) & 15) == 0)) mm_bound_refresh(fe, lane);
+            // (the warps take turns: once the CTA is past its first tiles, one refresh per ~16 tiles of the CTA, not of each warp)
+            if (Q::NMM > 0 && KQ_UNLIKELY(many_exact || (k < 64 ? ((k + 2 * warp) & 15) == 0 : ((k + 16 * warp) & (16 * 8 - 1)) == 0))) mm_bound_refresh(fe, lane);
 #endif
             // once the directory is full and this warp mostly misses it, stop probing it (the hint was wrong: high cardinality)
             // (only a warp that went through the general path can have missed the directory: `went_slow` is warp-uniform)

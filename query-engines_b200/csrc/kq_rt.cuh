@@ -66,12 +66,14 @@ __device__ __forceinline__ void rowctx_init(RowCtx& rc, int warp, int64_t tile, 
     rc.full = tile_base + tile_rows <= n;
     uint32_t m = RMASK;
     if (__builtin_expect(!rc.full, 0)) {
+        // closed form (the compiler predicates this block into every tile, so it is kept short): the lane owns the row pairs
+        // base + 64 j, base + 64 j + 1; with t = n - 1 - base, pair j is complete for j < t / 64, pair t / 64 holds row t
+        const int64_t t = n - 1 - rc.row0(0);
         m = 0;
-#pragma unroll
-        for (int j = 0; j < NCHUNK; j++) {
-            const int64_t r0 = rc.row0(j);
-            if (r0 < n) m |= 1u << (2 * j);
-            if (r0 + 1 < n) m |= 2u << (2 * j);
+        if (t >= 0) {
+            const int64_t J = t >> 6;
+            if (J >= NCHUNK) m = RMASK;
+            else m = ((1u << (2 * (int)J)) - 1u) | (1u << (2 * (int)J)) | ((uint32_t)((t & 63) >= 1) << (2 * (int)J + 1));
         }
     }
     rc.inr = m;
