@@ -197,7 +197,7 @@ struct AggArgs {
     // front end
     int32_t fe_groups, fe_nsum, fe_nmm;
     int32_t geo_r, geo_warps;              // tile geometry the host chose for this launch (host-side bookkeeping)
-    int32_t geo_ctas, geo_pad_;            // CTAs per SM the launch is sized for (kq_group_aggregate)
+    int32_t geo_ctas, geo_service;         // CTAs per SM the launch is sized for; service warps per CTA (kq_group_aggregate)
     int32_t fe_sum_word[MAX_INPUTS];       // front-end sum slot -> record word
     uint32_t fe_sum_int;                   // bit s: slot s is an integer sum
     int32_t fe_mm_word[2 * MAX_INPUTS];    // front-end min/max slot -> record word

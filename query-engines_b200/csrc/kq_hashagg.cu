@@ -703,7 +703,7 @@ static int plan_agg(kq_ctx* ctx, kq_hashagg* h, kq_batch* input, int smem_optin,
         struct Cand { int r, warps; };
         // measured (B200, configs 3 and 5): the kernel is latency-bound, so consumer warps count most, then rows per thread (8-12; the
         // producer lane's per-tile work is serial); two stages are enough
-        static const Cand CAND[] = {{8, 7}, {12, 6}, {8, 6}, {8, 5}, {6, 6}, {8, 4}, {4, 7}, {4, 6}, {4, 5}, {4, 4}, {2, 6}, {2, 4}, {2, 2}};
+        static const Cand CAND[] = {{8, 7}, {6, 7}, {12, 6}, {8, 6}, {8, 5}, {6, 6}, {8, 4}, {4, 7}, {4, 6}, {4, 5}, {4, 4}, {2, 6}, {2, 4}, {2, 2}};
         bool found = false;
         // the first candidate (most consumer warps first) that holds `want` groups; a directory of fewer groups only if nothing does
         for (int g = want; g >= 4 && !found; g = g * 3 / 4) {
@@ -760,7 +760,7 @@ static int plan_agg(kq_ctx* ctx, kq_hashagg* h, kq_batch* input, int smem_optin,
     for (int b = 0; b < A.sp.nbuf; b++) has_bytes |= A.sp.buf[b].kind == SK_BYTES;
     const int ring = A.sp.nstages * A.sp.stage_bytes;
     A.fe_groups = fg;
-    A.geo_r = geo.r; A.geo_warps = geo.warps; A.geo_ctas = ctas;
+    A.geo_r = geo.r; A.geo_warps = geo.warps; A.geo_ctas = ctas; A.geo_service = (mode == 3 && nm > 0) ? 2 : 1;
     A.smem_bytes = ring + dir_slots * entry_words * 8 + std::max(fg, 1) * 12 + (fg + 1) * nm * 8 + WARPS * (fg + 1) * 32 * (8 * ns + 4 * ncnt);
     if (mode == 3) A.smem_bytes = ring + fe_smem;
     if (mode == 1) A.smem_bytes += 16 + nparts * 4;
@@ -824,7 +824,7 @@ static int plan_agg(kq_ctx* ctx, kq_hashagg* h, kq_batch* input, int smem_optin,
                                 "\n#define KQ_CTAS " + std::to_string(ctas) + "\n#define KQ_STAGE_BYTES " + (has_bytes ? "1" : "0") + "\n#define KQ_AGG_MODE " + std::to_string(mode) + "\n" +
                                 (getenv("KQ_PART_L2_HINTS") ? "#define KQ_PART_L2_HINTS " + std::to_string(atoi(getenv("KQ_PART_L2_HINTS"))) + "\n" : std::string()) +
                                 (getenv("KQ_NO_STAGE_DRAIN") ? "#define KQ_NO_STAGE_DRAIN 1\n" : "") + (getenv("KQ_RING_CHECK") ? "#define KQ_RING_CHECK " + std::to_string(atoi(getenv("KQ_RING_CHECK"))) + "\n" : std::string()) + (getenv("KQ_PART_SCALAR_MERGE") ? "#define KQ_PART_SCALAR_MERGE 1\n" : "") + (getenv("KQ_PART_DROP_SPILL") ? "#define KQ_PART_DROP_SPILL 1\n" : "") + (getenv("KQ_FE_CHECK") ? "#define KQ_FE_CHECK 1\n" : "") + (getenv("KQ_FE_NOEXACT") ? "#define KQ_FE_NOEXACT 1\n" : "") +
-                                (getenv("KQ_FE_NOREFRESH") ? "#define KQ_FE_NOREFRESH 1\n" : "") + (getenv("KQ_FE_PROGRESS") ? "#define KQ_FE_TRACE 1\n" : "") + (getenv("KQ_FE_NOMERGE") ? "#define KQ_FE_NOMERGE 1\n" : "");
+                                (getenv("KQ_FE_PROGRESS") ? "#define KQ_FE_TRACE 1\n" : "") + (getenv("KQ_FE_NOMERGE") ? "#define KQ_FE_NOMERGE 1\n" : "");
     return KQ_OK;
 }
 
@@ -967,7 +967,7 @@ static int hashagg_update_fe(kq_ctx* ctx, kq_hashagg* h, kq_batch* input, int64_
     const auto t1 = now();
     if (n == 0) return KQ_OK;
     const AggGeometry geo{A.geo_r, A.geo_warps};
-    const int TILE = geo.tile(), THREADS = geo.threads();
+    const int TILE = geo.tile(), THREADS = geo.threads() + 32 * (A.geo_service - 1);       // + the housekeeping warp of queries with MIN/MAX
     A.n = n; A.ntiles = (n + TILE - 1) / TILE;
     void* kernel = nullptr;
     KQ_RET(kq_jit_kernel(ctx, defines, gen, KQ_SKEL_AGG_FE, "kq_group_aggregate", A.smem_bytes, &kernel));

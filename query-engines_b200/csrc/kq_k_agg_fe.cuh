@@ -36,7 +36,11 @@ namespace kq {
 
 constexpr int WARPS = KQ_WARPS;              // consumer warps
 constexpr int PRODUCER_WARP = 0;             // service warp first: the warp arbiter favours high warp ids
-constexpr int THREADS = WARPS * 32 + 32;
+// Service warps (lowest ids): the producer, and — when the query has MIN/MAX — a housekeeping warp that keeps the bounds of the
+// extremes fresh. (Refreshing from a consumer warp delayed that warp's next stage hand-back by ~1 us every couple of tiles,
+// and with a two-stage ring the whole CTA waited for it.)
+constexpr int NSERVICE = Q::NMM > 0 ? 2 : 1;
+constexpr int THREADS = WARPS * 32 + 32 * NSERVICE;
 constexpr int TILE = WARPS * WARP_ROWS;
 constexpr int S = KQ_STAGES;
 constexpr int FG = KQ_FE_GROUPS;             // directory capacity in groups (<= 254)
@@ -744,10 +748,10 @@ extern "C" __global__ void __launch_bounds__(THREADS, KQ_CTAS) kq_group_aggregat
     __shared__ long long tile_of[S];
     __shared__ long long bbase[S][MAX_COLS];
     __shared__ DirCtl s_ctl;
-    __shared__ uint32_t s_lock, s_limit, s_btoken, s_started, s_finished, s_refreshing;
+    __shared__ uint32_t s_lock, s_limit, s_btoken, s_started, s_finished, s_refreshing, s_done;
     __shared__ uint64_t s_bound[NMM1];
     const int wid = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int warp = wid - 1;                 // consumer warp index
+    const int warp = wid - NSERVICE;          // consumer warp index
     unsigned char* p0 = smem + (size_t)S * A.sp.stage_bytes;
     const size_t fe_begin = (size_t)(p0 - smem);
     Fe fe;
@@ -770,7 +774,7 @@ extern "C" __global__ void __launch_bounds__(THREADS, KQ_CTAS) kq_group_aggregat
     for (size_t i = fe_begin + threadIdx.x * 4; i < fe_end; i += THREADS * 4) *reinterpret_cast<uint32_t*>(smem + i) = 0;
     if (threadIdx.x == 0) {
         s_ctl.gen = 0; s_ctl.s1 = 0x9E3779B1u; s_ctl.s2 = 0x85EBCA6Bu; s_ctl.count = 0;
-        s_lock = 0; s_limit = (uint32_t)FG; s_btoken = TOKEN_NONE; s_started = 0; s_finished = 0; s_refreshing = 0;
+        s_lock = 0; s_limit = (uint32_t)FG; s_btoken = TOKEN_NONE; s_started = 0; s_finished = 0; s_refreshing = 0; s_done = 0;
         for (int m = 0; m < Q::NMM; m++) s_bound[m] = bound_none(m, mm_is_int(m));
         for (int s = 0; s < S; s++) { mbar_init(&full[s], 1); mbar_init(&empty[s], WARPS); }
         mbar_fence_init();
@@ -780,48 +784,100 @@ extern "C" __global__ void __launch_bounds__(THREADS, KQ_CTAS) kq_group_aggregat
     __syncthreads();
 
     if (wid == PRODUCER_WARP) {
-        if (lane == 0) {
-            // Tiles are dealt statically: block b owns tiles b, b + grid, b + 2 grid, ... — no ticket atomic on the critical path,
-            // and the HBM reads of a tile's Utf8 boundary offsets (stage_bounds_fetch: the byte range of its strings) are issued
-            // PF tiles ahead, so a tile's string bytes and fixed-size buffers go out together on one barrier the moment a stage
-            // is free. (A ticket per tile cost an L2 atomic plus a dependent HBM load, ~2 us, in front of every 1024-row tile.)
-            // A block that stops early (global table past its threshold) records how far it got; the host grows the table and
-            // relaunches with the same grid, every block resuming its own sequence.
-            constexpr int PF = 4;
-            const long long first = A.progress ? (long long)A.progress[blockIdx.x] : 0;
-            auto tile_at = [&](long long j) -> long long { const long long t = A.tile_begin + (long long)blockIdx.x + j * (long long)gridDim.x; return t < A.ntiles ? t : -1; };
-            TileBounds tb[PF];
-            long long tq[PF];
+        // Tiles are dealt statically: block b owns tiles b, b + grid, b + 2 grid, ... — no ticket atomic on the critical path.
+        // A block that stops early (global table past its threshold) records how far it got; the host grows the table and
+        // relaunches with the same grid, every block resuming its own sequence.
+        //
+        // The whole producer WARP issues a tile, one lane per staged buffer: each lane keeps its buffer's descriptor in
+        // registers, computes its own byte count and source address, the counts are summed with one warp reduction for the
+        // barrier's expect_tx and every lane issues its own bulk copy. (One lane walking all buffers took ~600 dependent
+        // instructions = 1.3 us per tile; with a two-stage ring that sat between a stage being freed and its next data being
+        // requested, and consumers spent 17 % of their time waiting at the full barrier.) A lane that owns a Utf8 byte
+        // buffer reads the two boundary offsets of its column for the tiles PF ahead straight from HBM, so string bytes and
+        // fixed-size buffers of a tile go out together on one barrier the moment a stage is free.
+        constexpr int PF = 4;
+        const long long first = A.progress ? (long long)A.progress[blockIdx.x] : 0;
+        auto tile_at = [&](long long j) -> long long { const long long t = A.tile_begin + (long long)blockIdx.x + j * (long long)gridDim.x; return t < A.ntiles ? t : -1; };
+        // this lane's buffer
+        const bool mine = lane < A.sp.nbuf;
+        const StageBuf sb = A.sp.buf[mine ? lane : 0];
+        bool is_bytes = mine && sb.kind == SK_BYTES, staged_bytes = false;
+        for (int i = 0; i < MAX_BYTES_BUFS; i++) staged_bytes |= is_bytes && i < A.sp.nbytes && A.sp.bytes_buf[i] == lane;
+        const int32_t* offp = is_bytes ? reinterpret_cast<const int32_t*>(A.sp.buf[sb.aux & 0xffff].g) : nullptr;
+        const int bslot = sb.aux >> 16;
+        int32_t blo[PF], bhi[PF];
+        long long tq[PF];
+        auto bounds_fetch = [&](long long tile, int32_t& lo, int32_t& hi) {
+            lo = hi = 0;
+            if (staged_bytes && tile >= 0) {
+                const long long row0 = tile * TILE;
+                const int rows = (int)((A.n - row0) < TILE ? (A.n - row0) : TILE);
+                asm volatile("ld.global.nc.L1::no_allocate.s32 %0, [%1];" : "=r"(lo) : "l"(offp + row0));
+                asm volatile("ld.global.nc.L1::no_allocate.s32 %0, [%1];" : "=r"(hi) : "l"(offp + row0 + rows));
+            }
+        };
+#pragma unroll
+        for (int u = 0; u < PF; u++) { tq[u] = tile_at(first + u); bounds_fetch(tq[u], blo[u], bhi[u]); }
+        long long issued = 0;
+        bool more = true;
+        // the group count that stops a throttled launch is read one tile ahead (an L2 round trip otherwise in front of every tile)
+        const bool throttled = A.stop_threshold != ~0ULL;
+        unsigned long long ng = throttled ? *reinterpret_cast<volatile unsigned long long*>(A.ngroups) : 0ULL;
+        for (int kp0 = 0; more; kp0 += PF) {
 #pragma unroll
             for (int u = 0; u < PF; u++) {
-                tq[u] = tile_at(first + u);
-                tb[u] = TileBounds{};
-                if (KQ_STAGE_BYTES && tq[u] >= 0) stage_bounds_fetch(A.sp, tq[u], TILE, A.n, tb[u]);
-            }
-            long long issued = 0;
-            bool more = true;
-            // the group count that stops a throttled launch is read one tile ahead (an L2 round trip otherwise in front of every tile)
-            const bool throttled = A.stop_threshold != ~0ULL;
-            unsigned long long ng = throttled ? *reinterpret_cast<volatile unsigned long long*>(A.ngroups) : 0ULL;
-            for (int kp0 = 0; more; kp0 += PF) {
-#pragma unroll
-                for (int u = 0; u < PF; u++) {
-                    if (!more) break;
-                    const int kp = kp0 + u, s = kp % S;
-                    { int spins = 0; while (!mbar_test(&empty[s], ((kp / S) & 1) ^ 1)) { __nanosleep(32); if (++spins > SPIN_LIMIT) { atomicOr(A.err, ERR_SPIN_STAGE); break; } } }
-                    long long tile = tq[u];
-                    if (tile >= 0 && throttled && ng > A.stop_threshold) tile = -1;
-                    tile_of[s] = tile;
-                    if (tile < 0) { mbar_arrive(&full[s]); more = false; break; }
-                    stage_issue_all(A.sp, smem + (size_t)s * A.sp.stage_bytes, &full[s], tile, TILE, A.n, tb[u], bbase[s], 0ULL);
-                    issued++;
-                    if (throttled) ng = *reinterpret_cast<volatile unsigned long long*>(A.ngroups);
-                    tq[u] = tile_at(first + kp + PF);
-                    if (KQ_STAGE_BYTES && tq[u] >= 0) stage_bounds_fetch(A.sp, tq[u], TILE, A.n, tb[u]);
+                if (!more) break;
+                const int kp = kp0 + u, s = kp % S;
+                { int spins = 0; while (!mbar_test(&empty[s], ((kp / S) & 1) ^ 1)) { __nanosleep(32); if (++spins > SPIN_LIMIT) { if (lane == 0) atomicOr(A.err, ERR_SPIN_STAGE); break; } } }
+                long long tile = tq[u];
+                if (tile >= 0 && throttled && ng > A.stop_threshold) tile = -1;
+                if (tile < 0) {
+                    if (lane == 0) { tile_of[s] = tile; sh_st_u32(smem_u32(&s_done), 1u); mbar_arrive(&full[s]); }
+                    more = false;
+                    break;
                 }
+                // this lane's share of the tile
+                const long long row0 = tile * TILE;
+                const int rows = (int)((A.n - row0) < TILE ? (A.n - row0) : TILE);
+                uint32_t bytes = 0;
+                const char* src = sb.g;
+                if (mine && !is_bytes) {
+                    long long goff;
+                    if (sb.kind == SK_W8) { bytes = (uint32_t)rows * 8u; goff = row0 * 8; }
+                    else if (sb.kind == SK_W4) { bytes = (uint32_t)rows * 4u; goff = row0 * 4; }
+                    else if (sb.kind == SK_W4_PLUS1) { bytes = (uint32_t)(rows + 1) * 4u; goff = row0 * 4; }
+                    else { bytes = (uint32_t)(rows + 7) / 8u; goff = row0 / 8; }
+                    bytes = (bytes + 15u) & ~15u;
+                    src = sb.g + goff;
+                } else if (staged_bytes) {
+                    const long long lo = (long long)blo[u] & ~15LL, hi = ((long long)bhi[u] + 15LL) & ~15LL;
+                    const bool fits = hi - lo + 16 <= (long long)sb.cap;
+                    if (fits) { bytes = (uint32_t)(hi - lo + 16); src = sb.g + lo; }       // +16: consumers read whole 8-byte words past the end (buffers are padded)
+                    bbase[s][bslot] = fits ? lo : -1LL;
+                }
+                const uint32_t total = __reduce_add_sync(0xffffffffu, bytes);
+                __syncwarp();                                  // the byte lanes' bbase stores before lane 0's release
+                if (lane == 0) { tile_of[s] = tile; mbar_arrive_expect_tx(&full[s], total); }
+                __syncwarp();
+                if (bytes) bulk_g2s(smem + (size_t)s * A.sp.stage_bytes + sb.soff, src, bytes, &full[s]);
+                issued++;
+                if (throttled) ng = *reinterpret_cast<volatile unsigned long long*>(A.ngroups);
+                tq[u] = tile_at(first + kp + PF);
+                bounds_fetch(tq[u], blo[u], bhi[u]);
             }
+        }
+        if (lane == 0) {
             if (A.progress) A.progress[blockIdx.x] = (unsigned int)(first + issued);
             atomicAdd(A.ticket, (unsigned int)issued);           // tiles finished by this launch (the host compares the running total with the batch)
+        }
+    } else if (NSERVICE == 2 && wid == 1) {
+        // housekeeping: recompute the bounds of the extremes all the time (every ~0.3 us while the directory fills, every
+        // ~1.5 us later); nobody waits for this warp
+        uint32_t it = 0;
+        while (sh_ld_u32_uniform(smem_u32(&s_done)) == 0u) {
+            mm_bound_refresh(fe, lane);
+            __nanosleep(it < 256 ? 200 : 1500);
+            it++;
         }
     } else {
         AggSink sink;
@@ -909,7 +965,7 @@ extern "C" __global__ void __launch_bounds__(THREADS, KQ_CTAS) kq_group_aggregat
 #pragma unroll
             for (int m = 0; m < NMM1; m++) bnd[m] = 0;
             if (Q::NMM > 0) bounds_read(fe, bnd);
-            bool many_exact = false, went_slow = false;
+            bool went_slow = false;
             uint32_t new_groups = 0;
             const int rows = __popc(sink.sel);
             int fe_hits = rows - __popc(slow);
@@ -931,7 +987,6 @@ extern "C" __global__ void __launch_bounds__(THREADS, KQ_CTAS) kq_group_aggregat
                         // group: all its rows take the exact path (nullable inputs only; see fe_accumulate_row)
                         if (Q::ANY_MM_NULLABLE && exact) exact = onmask;
                         if (KQ_UNLIKELY(exact != 0)) fe_exact_rows(fe, gsel, exact, sink);
-                        many_exact = many_exact || __popc(__ballot_sync(0xffffffffu, exact != 0)) >= 4;
                     }
                 }
                 KQ_TRACE(0x100000 + k * 16 + 4);
@@ -956,11 +1011,6 @@ extern "C" __global__ void __launch_bounds__(THREADS, KQ_CTAS) kq_group_aggregat
                 const uint32_t tot = __reduce_add_sync(0xffffffffu, new_groups);
                 if (lane == 0) atomicAdd(A.ngroups, (unsigned long long)tot);
             }
-            // refresh the bounds when they look stale (many rows took the exact path), and every 16 tiles to tighten them
-#ifndef KQ_FE_NOREFRESH
-            // (the warps take turns: once the CTA is past its first tiles, one refresh per ~16 tiles of the CTA, not of each warp)
-            if (Q::NMM > 0 && KQ_UNLIKELY(many_exact || (k < 64 ? ((k + 2 * warp) & 15) == 0 : ((k + 16 * warp) & (16 * 8 - 1)) == 0))) mm_bound_refresh(fe, lane);
-#endif
             // once the directory is full and this warp mostly misses it, stop probing it (the hint was wrong: high cardinality)
             // (only a warp that went through the general path can have missed the directory: `went_slow` is warp-uniform)
             if (KQ_UNLIKELY(!bypass && went_slow) && sh_ld_u32_uniform(fe.a_ctl + 12u) >= sh_ld_u32_uniform(smem_u32(&s_limit)) && __any_sync(0xffffffffu, fe_hits < rows)) {
