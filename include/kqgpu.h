@@ -203,7 +203,9 @@ KQ_API int kq_explain_filter_project(kq_expr* pred, kq_expr* const* exprs, int n
 KQ_API int kq_hashagg_create(kq_ctx* ctx, kq_expr* pred, kq_expr* const* group_exprs, int ngroup,
                              const int* agg_kinds, kq_expr* const* agg_inputs, int nagg,
                              int64_t expected_groups, kq_hashagg** out);
-/* One iteration of the drain loop (Main.kt:617-634): state persists across batches (rule R11). */
+/* One iteration of the drain loop (Main.kt:617-634): state persists across batches (rule R11). Group keys may be Utf8
+ * strings of any length (Main.kt:621-627). Errors raised by the aggregate's kernels are sticky: every later call on the
+ * aggregate reports them again. */
 KQ_API int kq_hashagg_update(kq_ctx* ctx, kq_hashagg* agg, kq_batch* input);
 /* Emit the single output batch (Main.kt:635-650): group columns then aggregate columns. Row
  * order is unspecified (the reference's is HashMap iteration order, rule R10). */
@@ -226,11 +228,16 @@ KQ_API int kq_comm_destroy(kq_ctx* ctx);
 KQ_API int kq_comm_barrier(kq_ctx* ctx);
 /* Max over ranks of a float (device-side timing reduction). */
 KQ_API int kq_comm_allreduce_max_f32(kq_ctx* ctx, float* inout);
-/* Low-cardinality merge: all-gather of group keys -> sorted union dictionary -> dense arrays ->
- * ncclAllReduce (sum / min / max). Afterwards every rank holds the full merged result. */
+/* Low-cardinality merge; afterwards every rank holds the full merged result, bit-identical on all ranks. Small unions
+ * (tens to a thousand partial groups per rank): one fixed-size ncclAllGather of the partial records (and of the strings
+ * behind Utf8 group keys longer than 7 bytes), one host synchronisation, a rank-by-rank rebuild. Larger unions: all-gather
+ * -> union dictionary -> dense arrays -> ncclAllReduce (sum / min / max). COLLECTIVE: every rank of the communicator must
+ * call it; a rank whose aggregate carries an error joins the collective and all ranks return that error. */
 KQ_API int kq_hashagg_merge_allreduce(kq_ctx* ctx, kq_hashagg* agg);
 /* High-cardinality merge: partials bucketed by hash(key) % nranks, exchanged with a grouped
- * ncclSend/ncclRecv all-to-all, merged locally. Afterwards each key lives on exactly one rank. */
+ * ncclSend/ncclRecv all-to-all, merged locally. Afterwards each key lives on exactly one rank. COLLECTIVE; the ranks
+ * exchange a status word with the bucket sizes, so an error on one rank (incl. Utf8 group keys longer than 7 bytes,
+ * which this merge does not carry) is returned by all of them instead of leaving the peers waiting. */
 KQ_API int kq_hashagg_repartition_alltoall(kq_ctx* ctx, kq_hashagg* agg);
 
 /* ---- scan side: CsvDataSource (Main.kt:276-357) -------------------------------------------- */

@@ -14,8 +14,9 @@
 //     construction).
 //   * MIN / MAX: kept once per CTA; a row touches them only when its value beats a bound that holds for every group
 //     with a value (register compares per row), or when it is the first value its lane sees in that group.
-// Inserts, rebuilds, first values and bound refreshes are serialised by a CTA lock; they happen a few dozen times per
-// CTA, the per-row path takes no lock. Rows whose key does not fit the directory go to the global table of
+// Inserts and rebuilds are serialised by a CTA lock (whole warps only, a batch of keys per round); first values and bound
+// refreshes are lock-free (a validity token frames them; a housekeeping warp does the refreshing). The per-row path takes
+// no lock. Rows whose key does not fit the directory go to the global table of
 // kq_aggtable.cuh with atomics; the CTA's groups are merged into it once, at exit.
 //
 // Accumulator semantics (oracle: MaxAccumulator, Main.kt:538-562, and the E5-E7 extensions): nulls are skipped; MIN/MAX
@@ -224,73 +225,6 @@ __device__ __forceinline__ bool dir_place_all(const Fe& fe, int n, uint32_t s1, 
         }
     }
     return __all_sync(0xffffffffu, ok);
-}
-
-// Group id of key (kw, nm), inserting it while there is room; -1: the directory cannot take it (the row goes to the
-// global table). Called by ALL lanes of a warp with the same key, the warp HOLDING the CTA lock.
-__device__ __forceinline__ int dir_find_or_insert(const Fe& fe, const uint64_t (&kw)[NKW], uint32_t nm, int lane) {
-    volatile DirCtl* ctl = fe.ctl;
-    const int n = (int)sh_ld_u32_uniform(fe.a_ctl + 12u);
-    int found = -1;
-    for (int g = lane; g < n; g += 32) {
-        bool eq = *reinterpret_cast<volatile uint32_t*>(fe.gnm + g) == nm;
-#pragma unroll
-        for (int k = 0; k < NKW; k++) eq &= *reinterpret_cast<volatile uint64_t*>(fe.gkeys + g * NKW + k) == kw[k];
-        if (eq) found = g;
-    }
-    KQ_FTRACE(0x600002 + n * 256);
-    const uint32_t f = __ballot_sync(0xffffffffu, found >= 0);
-    int gid = f ? __shfl_sync(0xffffffffu, found, __ffs(f) - 1) : -1;
-    KQ_FTRACE(0x600003 + n * 256);
-    const int limit = (int)__shfl_sync(0xffffffffu, *reinterpret_cast<volatile uint32_t*>(fe.limit), 0);
-    if (!f && n < limit) {
-        gid = n;
-        if (lane == 0) {
-#pragma unroll
-            for (int k = 0; k < NKW; k++) fe.gkeys[n * NKW + k] = kw[k];
-            fe.gnm[n] = nm;
-        }
-        __syncwarp();
-        uint32_t s1 = sh_ld_u32_uniform(fe.a_ctl + 4u), s2 = sh_ld_u32_uniform(fe.a_ctl + 8u);
-        const uint32_t slot = dir_slot(kw, nm, s1, s2);
-        if (sh_ld_u32_uniform(fe.a_meta + slot * 4u) == 0u) {
-            // the home slot is free: publish keys, then the state word (readers that miss meanwhile come here and find it)
-            if (lane == 0) {
-#pragma unroll
-                for (int k = 0; k < NKW; k++) fe.keys[slot * NKW + k] = kw[k];
-                __threadfence_block();
-                *reinterpret_cast<volatile uint32_t*>(fe.meta + slot) = (uint32_t)(n + 1) | (nm << 8);
-                ctl->count = (uint32_t)(n + 1);
-            }
-        } else {
-            // collision: new multipliers until every key of the directory sits in its home slot
-            KQ_FTRACE(0x600004 + n * 256);
-            if (lane == 0) ctl->gen = ctl->gen + 1u;          // odd: probes in flight are void
-            __threadfence_block();
-            __syncwarp();
-            bool placed = false;
-            uint32_t t1 = s1, t2 = s2;
-            for (int a = 0; a < REBUILD_ATTEMPTS && !placed; a++) {
-                t1 = (t1 * 0x2C1B3C6Du + 0x297A2D39u) | 1u;
-                t2 = ((t2 ^ (t1 >> 7)) * 0x9E3779B1u + 0x85EBCA6Bu) | 1u;
-                placed = dir_place_all(fe, n + 1, t1, t2, lane);
-                __syncwarp();
-            }
-            if (!placed) {
-                // two keys no multiplier separates (never seen; possible in principle): keep the old directory, which places
-                // its n keys, stop inserting, and send this key to the global table
-                dir_place_all(fe, n, s1, s2, lane);
-                t1 = s1; t2 = s2; gid = -1;
-                if (lane == 0) *reinterpret_cast<volatile uint32_t*>(fe.limit) = (uint32_t)n;
-            }
-            __threadfence_block();
-            __syncwarp();
-            if (lane == 0) { ctl->s1 = t1; ctl->s2 = t2; ctl->count = (uint32_t)(placed ? n + 1 : n); __threadfence_block(); ctl->gen = ctl->gen + 1u; }
-        }
-    }
-    __threadfence_block();
-    __syncwarp();
-    return gid;
 }
 
 // Insert up to 32 keys at once — every lane may propose one (`has`), all of them ABSENT from the directory (the caller
