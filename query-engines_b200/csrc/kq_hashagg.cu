@@ -711,6 +711,7 @@ static int plan_agg(kq_ctx* ctx, kq_hashagg* h, kq_batch* input, int smem_optin,
                 const int r = fr > 0 ? fr : c.r, w = fw > 0 ? fw : c.warps;
                 int dir = 256;
                 while (dir < 16 * g) dir <<= 1;
+                if (const char* e = getenv("KQ_AGG_DIR")) dir = std::max(64, atoi(e));       // tuning experiments
                 StagePlan sp;
                 const std::string defs = cg.plan_stages(1 << 30, 1, w * 32 * r, &sp, true);
                 int fe = fe_bytes(g, w, dir);
@@ -722,6 +723,8 @@ static int plan_agg(kq_ctx* ctx, kq_hashagg* h, kq_batch* input, int smem_optin,
                     int st = std::min((budget - fe) / sp.stage_bytes, 6);
                     if (fs > 0) st = std::min(st, std::max(fs, 2));
                     sp.nstages = st;
+                    if (getenv("KQ_TRACE_AGG"))
+                        fprintf(stderr, "kq fe geometry: %d rows x %d warps, %d stages of %d bytes, directory %d slots for %d groups, front end %d bytes of %d\n", r, w, st, sp.stage_bytes, dir, g, fe, budget);
                     geo = AggGeometry{r, w}; A.sp = sp; stage_defs = defs; fg = g; dir_slots = dir; fe_smem = fe;
                     found = true;
                     break;
