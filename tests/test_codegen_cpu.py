@@ -76,3 +76,46 @@ def test_type_errors_raise_the_reference_exception_classes(E):
     with pytest.raises(kqgpu.KqError) as e:      # column index out of range: IllegalStateException
         E.explain_filter_project(None, [E.col(3)], [F64])
     assert e.value.code == 1
+
+
+def _defines(src):
+    import re
+    return {k: int(v) for k, v in re.findall(r"#define KQ_(R|WARPS|STAGES|FE_GROUPS|DIR_SLOTS|CTAS|AGG_MODE) (\d+)", src)}
+
+
+@pytest.mark.parametrize("hint,mode", [("6", 3), ("50", 3), ("64", 3), ("1000", 2), ("10000000", 0)])
+def test_every_aggregate_kernel_family_compiles_per_cardinality_hint(E, hint, mode, monkeypatch):
+    """The planner's group-count hint picks the kernel: <= 64 groups the CTA-directory kernel (kq_k_agg_fe.cuh, mode 3), a
+    block-shared table up to ~1600 (mode 2), else the global-table kernel (mode 0; the partitioned variant below)."""
+    monkeypatch.setenv("KQ_EXPLAIN_GROUPS", hint)
+    if mode == 2:
+        monkeypatch.setenv("KQ_EXPLAIN_PARTS", "0")          # kq_explain_hashagg: 0 selects the block-shared table variant
+    v = E.col(1)
+    src = E.explain_hashagg([E.col(0)], [("SUM", v), ("MIN", v), ("MAX", v), ("COUNT", v)], [UTF8, F64], [1, 1])
+    d = _defines(src)
+    assert d["AGG_MODE"] == mode
+    if mode == 3:
+        assert d["STAGES"] >= 2 and d["WARPS"] >= 2 and d["FE_GROUPS"] >= min(int(hint), 64) and d["DIR_SLOTS"] >= 8 * d["FE_GROUPS"]
+
+
+def test_partitioned_kernels_compile(E, monkeypatch):
+    monkeypatch.setenv("KQ_EXPLAIN_GROUPS", "10000000")
+    monkeypatch.setenv("KQ_EXPLAIN_PARTS", "2048")
+    v = E.col(1)
+    src = E.explain_hashagg([E.col(0), E.col(2)], [("SUM", v), ("MIN", v), ("MAX", v), ("COUNT", v)], [I64, F64, BOOL], [1, 1, 1])
+    assert _defines(src)["AGG_MODE"] == 1
+
+
+@pytest.mark.parametrize("geom", ["8,7,2", "12,6,2", "4,4", "8,3,2,2", "2,2,6,3"])
+def test_low_cardinality_kernel_compiles_for_the_geometries_the_gpu_tests_force(E, geom, monkeypatch):
+    """KQ_AGG_GEOM = rows per thread, consumer warps[, stages[, CTAs per SM]] (tests/test_gpu_parity.py runs these on the
+    device); with MIN/MAX the kernel also carries the housekeeping warp."""
+    monkeypatch.setenv("KQ_EXPLAIN_GROUPS", "50")
+    monkeypatch.setenv("KQ_AGG_GEOM", geom)
+    v = E.col(1)
+    want = [int(x) for x in geom.split(",")]
+    for aggs in ([("SUM", v), ("MIN", v), ("MAX", v), ("COUNT", v)], [("SUM", v), ("COUNT", v)]):
+        d = _defines(E.explain_hashagg([E.col(0)], aggs, [UTF8, F64]))
+        assert (d["R"], d["WARPS"]) == (want[0], want[1])
+        if len(want) > 3:
+            assert d["CTAS"] == want[3]
