@@ -573,15 +573,19 @@ def run_e2e(kqgpu, ctx, E, wl, batch, dist, steps, world, n_local, rows_total):
     import ctypes as C
     L = kqgpu.lib()
     if isinstance(wl, CsvScan):
-        # the file's bytes in pinned host memory -> kq_csv_scan (H2D inside) -> row count and buffer sizes read back
+        # the file's bytes in pinned host memory -> kq_csv_reader (H2D inside, overlapped) -> row counts and buffer sizes read back
         nb = len(wl.text)
         hp = ctx.host_alloc(nb)
         C.memmove(hp, wl.text, nb)
 
         def one_csv():
-            res = E.csv_scan_ptr(hp, nb, True)
-            sizes = [res.field(i).sizes() for i in range(res.num_columns())]      # the step's result read back: rows and bytes per column
-            return 8 + 24 * len(sizes), res.row_count()
+            d2h = rows = 0
+            for res in E.csv_batches(hp, True, nbytes=nb):                          # Sequence<RecordBatch>: one batch per 64 MiB piece
+                sizes = [res.field(i).sizes() for i in range(res.num_columns())]    # the step's result read back: rows and bytes per column
+                d2h += 8 + 24 * len(sizes)
+                rows += res.row_count()
+            assert rows == n_local, (rows, n_local)
+            return d2h, rows
         d2h, _ = one_csv()
         ctx.sync()
         t0 = time.perf_counter()
@@ -592,7 +596,7 @@ def run_e2e(kqgpu, ctx, E, wl, batch, dist, steps, world, n_local, rows_total):
         ctx.host_free(hp)
         return {"value": rows_total * steps / dt, "unit": "rows/s", "h2d_bytes_per_step": nb, "d2h_bytes_per_step": d2h, "steps": steps,
                 "ms_per_step": dt / steps * 1e3,
-                "how": "CSV text in pinned host memory -> kq_csv_scan (H2D copy + scan kernels) -> row count and column sizes read back, wall clock around synchronised steps"}
+                "how": "CSV text in pinned host memory -> kq_csv_reader (64 MiB pieces, the H2D copy of a piece under the scan of the one before) -> row count and column sizes of every batch read back, wall clock around synchronised steps"}
     cols = [batch.field(i) for i in range(batch.num_columns())]
     host = []
     h2d = 0

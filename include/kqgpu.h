@@ -22,6 +22,8 @@
  *   kq_comm_*, kq_hashagg_merge_* ........... partition -> partial aggregate -> merge of main() (Main.kt:1306-1342)
  *   kq_csv_header, kq_csv_scan .............. CsvDataSource.schema()/inferSchema and scan() + ReaderIterator.createBatch
  *                                             (Main.kt:251-273, 276-357): CSV text -> one batch of Utf8 columns
+ *   kq_csv_reader_open/next/close ........... the same scan as the Sequence<RecordBatch> the reference's ReaderIterator
+ *                                             yields (Main.kt:239-249): files of any size, H2D copies under the scan
  *   kq_generate ............................. bench-only synthetic tables (no reference counterpart)
  *
  * Conventions
@@ -32,7 +34,8 @@
  *     so the shim can rethrow the same class.
  *  - No global mutable state: one kq_ctx per plan/thread (Main.kt:1309-1313 runs 12 plans
  *    concurrently, each with its own ExecutionContext). A ctx may be used from any thread, one at a time.
- *  - The library never retains or frees caller host pointers past the call that received them.
+ *  - The library never retains or frees caller host pointers past the call that received them (one exception, by
+ *    design: an open kq_csv_reader reads the caller's text until kq_csv_reader_close).
  *  - All handles (kq_col, kq_batch, kq_expr, kq_hashagg) are reference counted; *_free drops one reference.
  *  - There is NO CPU fallback: without a CUDA device kq_ctx_create fails with KQ_ERR_NO_DEVICE.
  */
@@ -54,6 +57,7 @@ typedef struct kq_col kq_col;
 typedef struct kq_batch kq_batch;
 typedef struct kq_expr kq_expr;
 typedef struct kq_hashagg kq_hashagg;
+typedef struct kq_csv_reader kq_csv_reader;
 
 typedef enum kq_status {
     KQ_OK = 0,
@@ -252,6 +256,17 @@ KQ_API int kq_csv_header(const uint8_t* text, int64_t nbytes, int has_headers, c
  * maps names to indices as Schema.select does (Main.kt:47-52). Rules C1-C9: csrc/kq_csv.cu. */
 KQ_API int kq_csv_scan(kq_ctx* ctx, const uint8_t* text, int64_t nbytes, int has_headers, const int* projection,
                        int nproj, kq_batch** out);
+/* The same scan as a Sequence<RecordBatch> (CsvDataSource.scan returns ReaderIterator batches, Main.kt:239-249, 323-325):
+ * the text (HOST or DEVICE memory, any size, valid until close) streams through two device buffers in pieces of
+ * `piece_bytes` (0 = 64 MiB; at most 512 MiB); every piece is cut at its last complete record and the copy of the next
+ * piece runs under the scan of the current one (pinned or registered host memory: kq_host_register). kq_csv_reader_next
+ * hands out one batch per piece — the concatenation of all batches equals kq_csv_scan's batch — and *out = NULL after the
+ * last one; batches without rows are not yielded (Main.kt:245-247). A record that does not fit a piece is
+ * KQ_ERR_UNSUPPORTED; an unbalanced quote surfaces with the last piece (KQ_ERR_ILLEGAL_STATE). */
+KQ_API int kq_csv_reader_open(kq_ctx* ctx, const uint8_t* text, int64_t nbytes, int has_headers, const int* projection,
+                              int nproj, int64_t piece_bytes, kq_csv_reader** out);
+KQ_API int kq_csv_reader_next(kq_csv_reader* reader, kq_batch** out);
+KQ_API int kq_csv_reader_close(kq_csv_reader* reader);
 
 /* ---- bench-only: device-side synthetic tables -------------------------------------------- */
 KQ_API int kq_generate(kq_ctx* ctx, const kq_gen_spec* specs, int ncols, uint64_t seed,

@@ -293,69 +293,58 @@ static HostRecord host_first_record(const uint8_t* t, int64_t n, CsvFormat f) {
     return r;
 }
 
-}  // namespace
 
-extern "C" {
-
-int kq_csv_header(const uint8_t* text, int64_t nbytes, int has_headers, char* names, size_t names_cap, int* ncols, char* delimiter) {
-    if (!text || nbytes < 0 || !ncols) return KQ_ERR_ILLEGAL_ARGUMENT;
-    const CsvFormat f = host_detect(text, nbytes);
-    const HostRecord h = host_first_record(text, nbytes, f);
-    *ncols = (int)h.fields.size();
-    if (delimiter) *delimiter = (char)f.delim;
-    if (names && names_cap) {
-        std::string all;
-        for (size_t i = 0; i < h.fields.size(); i++) {
-            all += has_headers ? h.fields[i] : "field_" + std::to_string(i + 1);      // Main.kt:345-349
-            all += '\n';
-        }
-        if (all.size() + 1 > names_cap) return KQ_ERR_ILLEGAL_ARGUMENT;
-        memcpy(names, all.c_str(), all.size() + 1);
-    }
-    return KQ_OK;
-}
-
-int kq_csv_scan(kq_ctx* ctx, const uint8_t* text, int64_t nbytes, int has_headers, const int* projection, int nproj, kq_batch** out) {
-    if (!ctx || !out || nbytes < 0 || (nbytes && !text) || nproj < 0 || (nproj && !projection)) return KQ_ERR_ILLEGAL_ARGUMENT;
-    if (nbytes >= (1LL << 31) - 2 * CSV_BLOCK) return kq_fail(ctx, KQ_ERR_UNSUPPORTED, "CSV text of 2 GiB or more: scan it in pieces (Arrow int32 offsets)");
-    cudaSetDevice(ctx->device);
+// ---- what both entry points (kq_csv_scan, kq_csv_reader_*) do first: where the text lives, format, header, projection ----
+struct CsvSource {
+    bool on_device = false;
+    uint8_t last_byte = 0;
+    CsvFormat f{',', '\n'};
+    int file_cols = 0;
+    std::vector<int> proj;          // file column of every output column
+};
+static int csv_prologue(kq_ctx* ctx, const uint8_t* text, int64_t nbytes, const int* projection, int nproj, CsvSource* src) {
     // `text` may also be a DEVICE pointer (a file already resident in HBM: bench.py's device-resident timing). Format
     // detection and the header record then work on a copy of its first MiB (the first record must end inside it).
-    bool on_device = false;
+    src->on_device = false;
     {
         cudaPointerAttributes at;
-        if (nbytes && cudaPointerGetAttributes(&at, text) == cudaSuccess) on_device = at.type == cudaMemoryTypeDevice;
+        if (nbytes && cudaPointerGetAttributes(&at, text) == cudaSuccess) src->on_device = at.type == cudaMemoryTypeDevice;
         else cudaGetLastError();
     }
     std::vector<uint8_t> prefix;
-    uint8_t last_byte = nbytes && !on_device ? text[nbytes - 1] : 0;
+    src->last_byte = nbytes && !src->on_device ? text[nbytes - 1] : 0;
     const uint8_t* htext = text;
     int64_t hbytes = nbytes;
-    if (on_device) {
+    if (src->on_device) {
         hbytes = std::min<int64_t>(nbytes, 1 << 20);
         prefix.resize((size_t)hbytes);
         KQ_CUDA(ctx, cudaMemcpyAsync(prefix.data(), text, (size_t)hbytes, cudaMemcpyDeviceToHost, ctx->stream));
-        KQ_CUDA(ctx, cudaMemcpyAsync(&last_byte, text + nbytes - 1, 1, cudaMemcpyDeviceToHost, ctx->stream));
+        KQ_CUDA(ctx, cudaMemcpyAsync(&src->last_byte, text + nbytes - 1, 1, cudaMemcpyDeviceToHost, ctx->stream));
         KQ_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
         htext = prefix.data();
     }
-    const CsvFormat f = nbytes ? host_detect(htext, hbytes) : CsvFormat{',', '\n'};
-    const HostRecord head = nbytes ? host_first_record(htext, hbytes, f) : HostRecord();
-    if (on_device && hbytes < nbytes && head.end >= hbytes) return kq_fail(ctx, KQ_ERR_UNSUPPORTED, "first CSV record longer than 1 MiB");
-    const int file_cols = (int)head.fields.size();
-    if (file_cols > CSV_MAX_COLS) return kq_fail(ctx, KQ_ERR_UNSUPPORTED, "more than %d CSV columns", CSV_MAX_COLS);
-    std::vector<int> proj;
-    if (nproj) proj.assign(projection, projection + nproj);
-    else for (int i = 0; i < file_cols; i++) proj.push_back(i);
-    const int nout = (int)proj.size();
-    for (int c : proj)
-        if (c < 0 || c >= file_cols) return kq_fail(ctx, KQ_ERR_ILLEGAL_ARGUMENT, "projected CSV column %d out of range (file has %d)", c, file_cols);   // Schema.select, Main.kt:47-52
+    src->f = nbytes ? host_detect(htext, hbytes) : CsvFormat{',', '\n'};
+    const HostRecord head = nbytes ? host_first_record(htext, hbytes, src->f) : HostRecord();
+    if (src->on_device && hbytes < nbytes && head.end >= hbytes) return kq_fail(ctx, KQ_ERR_UNSUPPORTED, "first CSV record longer than 1 MiB");
+    src->file_cols = (int)head.fields.size();
+    if (src->file_cols > CSV_MAX_COLS) return kq_fail(ctx, KQ_ERR_UNSUPPORTED, "more than %d CSV columns", CSV_MAX_COLS);
+    src->proj.clear();
+    if (nproj) src->proj.assign(projection, projection + nproj);
+    else for (int i = 0; i < src->file_cols; i++) src->proj.push_back(i);
+    for (int c : src->proj)
+        if (c < 0 || c >= src->file_cols) return kq_fail(ctx, KQ_ERR_ILLEGAL_ARGUMENT, "projected CSV column %d out of range (file has %d)", c, src->file_cols);   // Schema.select, Main.kt:47-52
+    return KQ_OK;
+}
 
-    // the text on the device, terminated (a last record without a line separator still ends)
-    const bool add_term = nbytes > 0 && last_byte != f.term;
-    const long long n = nbytes + (add_term ? 1 : 0);
+// Passes 1-6 over `n` bytes of text resident in HBM (16-byte aligned): one batch of the projected columns.
+// Whole text (partial = false): the text ends with a terminator; an unbalanced quote is an error.
+// A reader's piece (partial = true): the text starts at a record start and may stop anywhere, also inside a quoted field.
+// Every record end found is a true one (the quote state is exact from a record start on); *consumed = the byte after the
+// last of them, the rest belongs to the next piece. A piece without any record end is an error.
+static int csv_scan_resident(kq_ctx* ctx, const uint8_t* d_text, long long n, CsvFormat f, int file_cols, const std::vector<int>& proj, int has_headers,
+                             bool partial, kq_batch** out, int64_t* consumed) {
+    const int nout = (int)proj.size();
     const long long nblocks = (n + CSV_BLOCK - 1) / CSV_BLOCK;
-    uint8_t* d_text = nullptr;
     int32_t *d_q = nullptr, *d_r = nullptr;
     unsigned long long* d_scratch = nullptr;        // [0] ticket, [1] total, [2] item count, [4..] tile descriptors
     int32_t *d_s = nullptr, *d_sep = nullptr, *d_last = nullptr;
@@ -365,7 +354,7 @@ int kq_csv_scan(kq_ctx* ctx, const uint8_t* text, int64_t nbytes, int has_header
     // least two bytes, so nblocks * 32 bounds the record count)
     const long long ntiles = (std::max<long long>(nblocks, 1) * (CSV_BLOCK / 2) + SCAN_TILE - 1) / SCAN_TILE + 2;
     auto cleanup = [&](int st) {
-        kq_dev_free(ctx, d_text); kq_dev_free(ctx, d_q); kq_dev_free(ctx, d_r); kq_dev_free(ctx, d_scratch); kq_dev_free(ctx, d_s); kq_dev_free(ctx, d_sep); kq_dev_free(ctx, d_last); kq_dev_free(ctx, d_cols);
+        kq_dev_free(ctx, d_q); kq_dev_free(ctx, d_r); kq_dev_free(ctx, d_scratch); kq_dev_free(ctx, d_s); kq_dev_free(ctx, d_sep); kq_dev_free(ctx, d_last); kq_dev_free(ctx, d_cols);
         if (st != KQ_OK) for (kq_col* c : cols) kq_column_free(c);
         return st;
     };
@@ -377,13 +366,11 @@ int kq_csv_scan(kq_ctx* ctx, const uint8_t* text, int64_t nbytes, int has_header
     };
     int64_t nrec = 0, nsep = 0;
     int st = KQ_OK;
+    if (consumed) *consumed = n;
     if (n > 0) {
-        if ((st = kq_dev_alloc(ctx, (size_t)n + 16, (void**)&d_text)) != KQ_OK) return cleanup(st);
         if ((st = kq_dev_alloc(ctx, (size_t)(nblocks + 1) * 4, (void**)&d_q)) != KQ_OK) return cleanup(st);
         if ((st = kq_dev_alloc(ctx, (size_t)(nblocks + 1) * 4, (void**)&d_r)) != KQ_OK) return cleanup(st);
         if ((st = kq_dev_alloc(ctx, (size_t)(ntiles + 4) * 8, (void**)&d_scratch)) != KQ_OK) return cleanup(st);
-        if (cudaMemcpyAsync(d_text, text, (size_t)nbytes, on_device ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice, ctx->stream) != cudaSuccess) return cleanup(kq_cuda_fail(ctx, cudaGetLastError(), "cudaMemcpyAsync(csv text)"));
-        if (add_term) cudaMemsetAsync(d_text + nbytes, f.term, 1, ctx->stream);
         const unsigned long long items = (unsigned long long)nblocks;
         auto scan_begin = [&](unsigned long long count) {
             cudaMemsetAsync(d_scratch, 0, (size_t)(ntiles + 4) * 8, ctx->stream);
@@ -396,8 +383,10 @@ int kq_csv_scan(kq_ctx* ctx, const uint8_t* text, int64_t nbytes, int has_header
         if (cudaGetLastError() != cudaSuccess) return cleanup(kq_cuda_fail(ctx, cudaGetLastError(), "k_exclusive_offsets(quotes)"));
         ctx->launches++;
         uint64_t total = 0;
-        if ((st = kq_read_u64(ctx, d_scratch + 1, 1, &total)) != KQ_OK) return cleanup(st);
-        if (total & 1) return cleanup(kq_fail(ctx, KQ_ERR_ILLEGAL_STATE, "CSV text ends inside a quoted field"));
+        if (!partial) {
+            if ((st = kq_read_u64(ctx, d_scratch + 1, 1, &total)) != KQ_OK) return cleanup(st);
+            if (total & 1) return cleanup(kq_fail(ctx, KQ_ERR_ILLEGAL_STATE, "CSV text ends inside a quoted field"));
+        }
         // 2. records and separators before every block
         scan_begin(items);
         k_exclusive_offsets<RecordCount><<<sg, 256, 0, ctx->stream>>>(RecordCount{d_text, n, d_q, f}, d_scratch + 2, d_r, d_scratch + 4,
@@ -406,6 +395,7 @@ int kq_csv_scan(kq_ctx* ctx, const uint8_t* text, int64_t nbytes, int has_header
         ctx->launches++;
         if ((st = kq_read_u64(ctx, d_scratch + 1, 1, &total)) != KQ_OK) return cleanup(st);
         nrec = (int64_t)total;
+        if (partial && nrec == 0) return cleanup(kq_fail(ctx, KQ_ERR_UNSUPPORTED, "CSV record longer than the reader's piece (%lld bytes): open the reader with larger pieces", n));
         if ((st = kq_dev_alloc(ctx, (size_t)(nblocks + 1) * 4, (void**)&d_s)) != KQ_OK) return cleanup(st);
         scan_begin(items);
         k_exclusive_offsets<SeparatorCount><<<sg, 256, 0, ctx->stream>>>(SeparatorCount{d_text, n, d_q, f}, d_scratch + 2, d_s, d_scratch + 4,
@@ -417,6 +407,25 @@ int kq_csv_scan(kq_ctx* ctx, const uint8_t* text, int64_t nbytes, int has_header
     }
     const int skip = has_headers && nrec > 0 ? 1 : 0;
     const int64_t rows = nrec - skip;
+    if (nrec > 0 && (partial || (rows > 0 && nout > 0))) {
+        // 3. separator positions and each record's last separator
+        if ((st = kq_dev_alloc(ctx, (size_t)nsep * 4 + 16, (void**)&d_sep)) != KQ_OK) return cleanup(st);
+        if ((st = kq_dev_alloc(ctx, (size_t)nrec * 4 + 16, (void**)&d_last)) != KQ_OK) return cleanup(st);
+        const int g = (int)std::max<long long>(1, std::min<long long>((nblocks + 255) / 256, (long long)ctx->sm_count * 8));
+        k_csv_separators<<<g, 256, 0, ctx->stream>>>(d_text, n, nblocks, d_q, f, d_r, d_s, d_sep, d_last);
+        if (cudaGetLastError() != cudaSuccess) return cleanup(kq_cuda_fail(ctx, cudaGetLastError(), "k_csv_separators"));
+        ctx->launches++;
+        if (partial) {       // where the last complete record ends: separator rec_last[nrec - 1] (delimiters of the unfinished tail follow it)
+            int32_t* h = (int32_t*)ctx->h_scratch;
+            for (int hop = 0; hop < 2; hop++) {
+                const int32_t* from = hop == 0 ? d_last + (nrec - 1) : d_sep + h[0];
+                if (cudaMemcpyAsync(h, from, 4, cudaMemcpyDeviceToHost, ctx->stream) != cudaSuccess || cudaStreamSynchronize(ctx->stream) != cudaSuccess)
+                    return cleanup(kq_cuda_fail(ctx, cudaGetLastError(), "read back the last record end"));
+                if (h[0] < 0 || (hop == 0 && h[0] >= nsep) || (hop == 1 && h[0] >= n)) return cleanup(kq_fail(ctx, KQ_ERR_ILLEGAL_STATE, "CSV separator index out of range"));
+            }
+            *consumed = (int64_t)h[0] + 1;
+        }
+    }
     if (rows <= 0 || nout == 0) {            // no data records: zero-row columns (Main.kt:245-247 yields no batch; one empty batch here, rule R10's shape)
         for (int c = 0; c < nout; c++) {
             kq_col* col = nullptr;
@@ -427,13 +436,6 @@ int kq_csv_scan(kq_ctx* ctx, const uint8_t* text, int64_t nbytes, int has_header
         make_batch(std::max<int64_t>(rows, 0));
         return cleanup(KQ_OK);
     }
-    // 3. separator positions and each record's last separator
-    if ((st = kq_dev_alloc(ctx, (size_t)nsep * 4 + 16, (void**)&d_sep)) != KQ_OK) return cleanup(st);
-    if ((st = kq_dev_alloc(ctx, (size_t)nrec * 4 + 16, (void**)&d_last)) != KQ_OK) return cleanup(st);
-    const int g = (int)std::max<long long>(1, std::min<long long>((nblocks + 255) / 256, (long long)ctx->sm_count * 8));
-    k_csv_separators<<<g, 256, 0, ctx->stream>>>(d_text, n, nblocks, d_q, f, d_r, d_s, d_sep, d_last);
-    if (cudaGetLastError() != cudaSuccess) return cleanup(kq_cuda_fail(ctx, cudaGetLastError(), "k_csv_separators"));
-    ctx->launches++;
     // 4. field lengths (into scratch arrays; the columns' offsets buffers are written by the scans below)
     CsvCols hc;
     memset(&hc, 0, sizeof hc);
@@ -508,6 +510,173 @@ int kq_csv_scan(kq_ctx* ctx, const uint8_t* text, int64_t nbytes, int has_header
     if (st != KQ_OK) return cleanup3(st);
     make_batch(rows);
     return cleanup3(KQ_OK);
+}
+
+
+
+
+// ---- CsvDataSource.scan as a Sequence<RecordBatch> (Main.kt:239-249, 304-326): the text streams through two device
+// buffers piece by piece; the H2D copy of piece k+1 (copy stream) runs under the scan of piece k (compute stream).
+// A piece is cut where its last complete record ends; the unfinished tail is moved in front of the next piece.
+// Buffer layout: [reserve R = piece][payload: piece][terminator + slack]; the text of a piece starts at `start` <= R
+// (16-byte aligned: the bytes between `start` and the carried tail are terminators, i.e. empty lines, rule C3).
+struct CsvPiece {
+    uint8_t* buf = nullptr;
+    int64_t start = 0;          // first byte of this piece's text in buf
+    int64_t len = 0;            // payload bytes uploaded at buf + R
+    bool last = false;          // the payload reaches the end of the text
+    cudaEvent_t uploaded = nullptr;
+};
+}  // namespace
+
+extern "C" {
+
+int kq_csv_header(const uint8_t* text, int64_t nbytes, int has_headers, char* names, size_t names_cap, int* ncols, char* delimiter) {
+    if (!text || nbytes < 0 || !ncols) return KQ_ERR_ILLEGAL_ARGUMENT;
+    const CsvFormat f = host_detect(text, nbytes);
+    const HostRecord h = host_first_record(text, nbytes, f);
+    *ncols = (int)h.fields.size();
+    if (delimiter) *delimiter = (char)f.delim;
+    if (names && names_cap) {
+        std::string all;
+        for (size_t i = 0; i < h.fields.size(); i++) {
+            all += has_headers ? h.fields[i] : "field_" + std::to_string(i + 1);      // Main.kt:345-349
+            all += '\n';
+        }
+        if (all.size() + 1 > names_cap) return KQ_ERR_ILLEGAL_ARGUMENT;
+        memcpy(names, all.c_str(), all.size() + 1);
+    }
+    return KQ_OK;
+}
+
+int kq_csv_scan(kq_ctx* ctx, const uint8_t* text, int64_t nbytes, int has_headers, const int* projection, int nproj, kq_batch** out) {
+    if (!ctx || !out || nbytes < 0 || (nbytes && !text) || nproj < 0 || (nproj && !projection)) return KQ_ERR_ILLEGAL_ARGUMENT;
+    if (nbytes >= (1LL << 31) - 2 * CSV_BLOCK) return kq_fail(ctx, KQ_ERR_UNSUPPORTED, "CSV text of 2 GiB or more: read it through kq_csv_reader_open (Arrow int32 offsets bound one batch)");
+    cudaSetDevice(ctx->device);
+    CsvSource src;
+    KQ_RET(csv_prologue(ctx, text, nbytes, projection, nproj, &src));
+    // the text on the device, terminated (a last record without a line separator still ends)
+    const bool add_term = nbytes > 0 && src.last_byte != src.f.term;
+    const long long n = nbytes + (add_term ? 1 : 0);
+    // a text that is already resident, terminated and 16-byte aligned is scanned where it lies
+    const bool in_place = src.on_device && !add_term && ((uintptr_t)text & 15u) == 0;
+    uint8_t* d_text = nullptr;
+    if (n > 0 && !in_place) {
+        KQ_RET(kq_dev_alloc(ctx, (size_t)n + 16, (void**)&d_text));
+        if (cudaMemcpyAsync(d_text, text, (size_t)nbytes, src.on_device ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice, ctx->stream) != cudaSuccess) {
+            kq_dev_free(ctx, d_text);
+            return kq_cuda_fail(ctx, cudaGetLastError(), "cudaMemcpyAsync(csv text)");
+        }
+        if (add_term) cudaMemsetAsync(d_text + nbytes, src.f.term, 1, ctx->stream);
+    }
+    const int st = csv_scan_resident(ctx, in_place ? text : d_text, n, src.f, src.file_cols, src.proj, has_headers, false, out, nullptr);
+    kq_dev_free(ctx, d_text);
+    return st;
+}
+
+struct kq_csv_reader {
+    kq_ctx* ctx = nullptr;
+    const uint8_t* text = nullptr;
+    int64_t nbytes = 0;
+    int has_headers = 0;
+    CsvSource src;
+    int64_t piece = 0;          // payload bytes per piece = reserve in front of it (multiple of 256)
+    int64_t pos = 0;            // source bytes already handed to a copy
+    CsvPiece p[2];
+    int cur = 0;
+    bool first = true, done = false;
+    int64_t records = 0, batches = 0;
+};
+
+static void csv_reader_upload(kq_csv_reader* r, int slot) {
+    kq_ctx* ctx = r->ctx;
+    CsvPiece& P = r->p[slot];
+    P.len = std::min<int64_t>(r->piece, r->nbytes - r->pos);
+    P.last = r->pos + P.len == r->nbytes;
+    // the buffer may still be read by work queued on the compute stream (the previous scan of this slot, the copy of its tail)
+    cudaEventRecord(ctx->copy_done, ctx->stream);
+    cudaStreamWaitEvent(ctx->copy_stream[0], ctx->copy_done, 0);
+    if (P.len) cudaMemcpyAsync(P.buf + r->piece, r->text + r->pos, (size_t)P.len, r->src.on_device ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice, ctx->copy_stream[0]);
+    cudaEventRecord(P.uploaded, ctx->copy_stream[0]);
+    r->pos += P.len;
+}
+
+int kq_csv_reader_open(kq_ctx* ctx, const uint8_t* text, int64_t nbytes, int has_headers, const int* projection, int nproj,
+                       int64_t piece_bytes, kq_csv_reader** out) {
+    if (!ctx || !out || nbytes < 0 || (nbytes && !text) || nproj < 0 || (nproj && !projection) || piece_bytes < 0) return KQ_ERR_ILLEGAL_ARGUMENT;
+    cudaSetDevice(ctx->device);
+    kq_csv_reader* r = new kq_csv_reader();
+    r->ctx = ctx; r->text = text; r->nbytes = nbytes; r->has_headers = has_headers;
+    int st = csv_prologue(ctx, text, nbytes, projection, nproj, &r->src);
+    if (st != KQ_OK) { delete r; return st; }
+    // piece size: 64 MiB unless the caller says otherwise; never more than the text, at most 512 MiB (carry + piece stay below 2 GiB)
+    int64_t piece = piece_bytes ? piece_bytes : (64LL << 20);
+    piece = std::min<int64_t>(piece, 512LL << 20);
+    piece = std::min<int64_t>(piece, std::max<int64_t>(nbytes, 1));
+    r->piece = std::max<int64_t>(256, (piece + 255) / 256 * 256);
+    for (int i = 0; i < 2 && st == KQ_OK; i++) {
+        st = kq_dev_alloc(ctx, (size_t)(2 * r->piece + 64), (void**)&r->p[i].buf);
+        if (st == KQ_OK && cudaEventCreateWithFlags(&r->p[i].uploaded, cudaEventDisableTiming) != cudaSuccess) st = kq_cuda_fail(ctx, cudaGetLastError(), "cudaEventCreate");
+        r->p[i].start = r->piece;
+    }
+    if (st != KQ_OK) { kq_csv_reader_close(r); return st; }
+    csv_reader_upload(r, 0);
+    *out = r;
+    return KQ_OK;
+}
+
+int kq_csv_reader_next(kq_csv_reader* r, kq_batch** out) {
+    if (!r || !out) return KQ_ERR_ILLEGAL_ARGUMENT;
+    kq_ctx* ctx = r->ctx;
+    cudaSetDevice(ctx->device);
+    *out = nullptr;
+    while (!r->done) {
+        CsvPiece& P = r->p[r->cur];
+        CsvPiece& N = r->p[r->cur ^ 1];
+        const int64_t R = r->piece;
+        cudaStreamWaitEvent(ctx->stream, P.uploaded, 0);
+        if (!P.last) csv_reader_upload(r, r->cur ^ 1);          // runs under the scan below
+        uint8_t* t = P.buf + P.start;
+        long long n = (R - P.start) + P.len;
+        if (P.last && r->nbytes > 0 && r->src.last_byte != r->src.f.term) {       // a last record without a line separator still ends
+            cudaMemsetAsync(P.buf + R + P.len, r->src.f.term, 1, ctx->stream);
+            n++;
+        }
+        kq_batch* b = nullptr;
+        int64_t consumed = n;
+        const int st = csv_scan_resident(ctx, t, n, r->src.f, r->src.file_cols, r->src.proj, r->first && r->has_headers, !P.last, &b, &consumed);
+        if (st != KQ_OK) { r->done = true; return st; }
+        r->first = false;
+        if (P.last) r->done = true;
+        else {
+            // the unfinished tail goes in front of the next piece's payload; the gap down to a 16-byte boundary reads as empty lines
+            const int64_t carry = n - consumed;
+            if (carry > R - 16) { kq_batch_free(b); r->done = true; return kq_fail(ctx, KQ_ERR_UNSUPPORTED, "CSV record longer than the reader's piece (%lld bytes): open the reader with larger pieces", (long long)R); }
+            N.start = (R - carry) / 16 * 16;
+            if (carry) cudaMemcpyAsync(N.buf + R - carry, t + consumed, (size_t)carry, cudaMemcpyDeviceToDevice, ctx->stream);
+            if (R - carry > N.start) cudaMemsetAsync(N.buf + N.start, r->src.f.term, (size_t)(R - carry - N.start), ctx->stream);
+        }
+        r->cur ^= 1;
+        if (b->n > 0) { r->records += b->n; r->batches++; *out = b; return KQ_OK; }      // Main.kt:245-247: a batch is yielded only when it has rows
+        kq_batch_free(b);
+    }
+    return KQ_OK;
+}
+
+int kq_csv_reader_close(kq_csv_reader* r) {
+    if (!r) return KQ_OK;
+    kq_ctx* ctx = r->ctx;
+    cudaSetDevice(ctx->device);
+    // a copy may still be in flight from the caller's text (a reader closed early): the text must be reusable on return
+    cudaStreamSynchronize(ctx->copy_stream[0]);
+    cudaEventRecord(ctx->copy_done, ctx->copy_stream[0]);
+    cudaStreamWaitEvent(ctx->stream, ctx->copy_done, 0);
+    for (int i = 0; i < 2; i++) {
+        kq_dev_free(ctx, r->p[i].buf);
+        if (r->p[i].uploaded) cudaEventDestroy(r->p[i].uploaded);
+    }
+    delete r;
+    return KQ_OK;
 }
 
 }  // extern "C"

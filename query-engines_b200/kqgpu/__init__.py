@@ -115,6 +115,9 @@ SYMBOLS = {
     "kq_generate": (C.c_int, [_P, C.POINTER(GenSpec), C.c_int, C.c_uint64, C.c_int64, C.c_int64, _PP]),
     "kq_csv_header": (C.c_int, [C.c_char_p, C.c_int64, C.c_int, C.c_char_p, C.c_size_t, C.POINTER(C.c_int), C.c_char_p]),
     "kq_csv_scan": (C.c_int, [_P, C.c_char_p, C.c_int64, C.c_int, C.POINTER(C.c_int), C.c_int, _PP]),
+    "kq_csv_reader_open": (C.c_int, [_P, C.c_char_p, C.c_int64, C.c_int, C.POINTER(C.c_int), C.c_int, C.c_int64, _PP]),
+    "kq_csv_reader_next": (C.c_int, [_P, _PP]),
+    "kq_csv_reader_close": (C.c_int, [_P]),
 }
 
 _lib = None
@@ -517,6 +520,38 @@ class Engine(Exprs):
         out = C.c_void_p()
         self.ctx.check(lib().kq_csv_scan(self.ctx.h, text, len(text), int(bool(has_headers)), arr if idx else None, len(idx), C.byref(out)))
         return RecordBatch(self.ctx, out)
+
+    def csv_batches(self, text, has_headers=True, projection=None, piece_bytes=0, nbytes=None, columns=None):
+        """CsvDataSource.scan(projection) as the reference returns it: a Sequence<RecordBatch> (ReaderIterator,
+        Main.kt:239-249). A generator of device batches, one per piece of `piece_bytes` of text (0 = 64 MiB), each cut at a
+        record boundary; the copy of the next piece runs under the scan of the current one. `text`: bytes, or an address
+        (int: pinned/pageable host memory or a device pointer) with `nbytes`; `projection`: column names (bytes input only),
+        `columns`: file column indices."""
+        idx = list(columns or [])
+        if isinstance(text, (bytes, bytearray)):
+            nbytes = len(text)
+            if projection:
+                names, _ = self.csv_header(bytes(text), has_headers)
+                for p in projection:
+                    if p not in names:
+                        raise KqError(3, f"Field {p} not found")        # Main.kt:49
+                    idx.append(names.index(p))
+            src = C.c_char_p(bytes(text))           # kept alive by this frame until the reader is closed
+        else:
+            src = C.cast(C.c_void_p(int(text)), C.c_char_p)
+        arr = (C.c_int * max(len(idx), 1))(*idx)
+        rd = C.c_void_p()
+        self.ctx.check(lib().kq_csv_reader_open(self.ctx.h, src, nbytes, int(bool(has_headers)), arr if idx else None, len(idx),
+                                                int(piece_bytes), C.byref(rd)))
+        try:
+            while True:
+                out = C.c_void_p()
+                self.ctx.check(lib().kq_csv_reader_next(rd, C.byref(out)))
+                if not out.value:
+                    return
+                yield RecordBatch(self.ctx, out)
+        finally:
+            lib().kq_csv_reader_close(rd)
 
     def csv_scan_ptr(self, ptr: int, nbytes: int, has_headers=True, columns=None) -> RecordBatch:
         """kq_csv_scan on a raw buffer: pinned/pageable host memory or a device pointer (text already in HBM);

@@ -88,14 +88,10 @@ def value(text: bytes, first: int, last: int) -> bytes:
     return text[first:last]
 
 
-def scan(text: bytes, has_headers=True):
-    """kq_csv_scan's passes 1-6 -> list of columns (lists of str), all file columns."""
-    if not text:
-        return []
-    delim, term = detect(text)
-    if text[-1] != term:
-        text = text + bytes([term])
-    n = len(text)
+def scan_resident(text: bytes, n: int, delim: int, term: int, ncols: int, skip: int, partial: bool):
+    """csv_scan_resident: passes 1-6 over text[:n] -> (columns of the ncols file columns, consumed). A whole text
+    (partial=False) must balance its quotes; a reader's piece (partial=True) may stop anywhere, `consumed` is the byte
+    after its last complete record and a piece without one is an error."""
     nblocks = (n + BLOCK - 1) // BLOCK
     sep, rec_last, q = [], [], 0
     for i in range(nblocks):
@@ -108,13 +104,13 @@ def scan(text: bytes, has_headers=True):
                 rec_last.append(len(sep) - 1)
             allm &= allm - 1
         q += text[i * BLOCK:min((i + 1) * BLOCK, n)].count(b'"')
-    if q & 1:
+    if not partial and q & 1:
         raise ValueError("CSV text ends inside a quoted field")
     nrec = len(rec_last)
-    if nrec == 0:
-        return []
-    ncols = rec_last[0] + 1                          # fields of the first record
-    skip = 1 if has_headers else 0
+    if partial and nrec == 0:
+        raise OverflowError("CSV record longer than the reader's piece")
+    consumed = sep[rec_last[-1]] + 1 if partial else n
+    skip = skip if nrec else 0
     cols = [[] for _ in range(ncols)]
     for rec in range(skip, nrec):
         k0 = rec_last[rec - 1] + 1 if rec else 0
@@ -125,4 +121,85 @@ def scan(text: bytes, has_headers=True):
                 continue
             a = sep[k0 + c - 1] + 1 if k0 + c else 0
             cols[c].append(value(text, a, sep[k0 + c]).decode("utf-8"))
-    return cols
+    return cols, consumed
+
+
+def first_record_fields(text: bytes, delim: int, term: int) -> int:
+    """host_first_record: the number of fields of the first non-empty record (the file's column count)."""
+    start, inq = 0, False
+    for p in range(len(text) + 1):
+        at_end = p == len(text)
+        c = term if at_end else text[p]
+        if c == 0x22 and not at_end:
+            inq = not inq
+        elif c == term and (not inq or at_end):
+            empty = p == start or (term == 0x0A and p == start + 1 and text[start] == 0x0D)
+            if not empty:
+                k, q = 1, False
+                for ch in text[start:p]:
+                    if ch == 0x22:
+                        q = not q
+                    elif not q and ch == delim:
+                        k += 1
+                return k
+            start = p + 1
+    return 0
+
+
+def scan(text: bytes, has_headers=True):
+    """kq_csv_scan's passes 1-6 -> list of columns (lists of str), all file columns."""
+    if not text:
+        return []
+    delim, term = detect(text)
+    if text[-1] != term:
+        text = text + bytes([term])
+    ncols = first_record_fields(text, delim, term)
+    if ncols == 0:
+        return []
+    return scan_resident(text, len(text), delim, term, ncols, 1 if has_headers else 0, False)[0]
+
+
+def reader(text: bytes, has_headers=True, piece=256):
+    """kq_csv_reader_open/next: the text streams through two buffers [reserve R][payload R][terminator]; a piece is cut
+    after its last complete record, the unfinished tail is moved in front of the next payload, and the gap down to a
+    16-byte boundary is filled with terminators (empty lines). Yields the column lists of every batch that has rows."""
+    assert piece % 16 == 0 and piece >= 32
+    delim, term = detect(text)
+    ncols = first_record_fields(text, delim, term)
+    R = piece
+    buf = [bytearray(2 * R + 64), bytearray(2 * R + 64)]
+    start, length, last = [R, R], [0, 0], [False, False]
+    pos = 0
+
+    def upload(slot):
+        nonlocal pos
+        length[slot] = min(R, len(text) - pos)
+        last[slot] = pos + length[slot] == len(text)
+        buf[slot][R:R + length[slot]] = text[pos:pos + length[slot]]
+        pos += length[slot]
+
+    upload(0)
+    cur, first, done = 0, True, False
+    while not done:
+        nxt = cur ^ 1
+        if not last[cur]:
+            upload(nxt)
+        n = (R - start[cur]) + length[cur]
+        if last[cur] and text and text[-1] != term:
+            buf[cur][R + length[cur]] = term
+            n += 1
+        t = bytes(buf[cur][start[cur]:start[cur] + n])
+        cols, consumed = scan_resident(t, n, delim, term, ncols, 1 if first and has_headers else 0, not last[cur])
+        first = False
+        if last[cur]:
+            done = True
+        else:
+            carry = n - consumed
+            if carry > R - 16:
+                raise OverflowError("CSV record longer than the reader's piece")
+            start[nxt] = (R - carry) // 16 * 16
+            buf[nxt][R - carry:R] = t[consumed:]
+            buf[nxt][start[nxt]:R - carry] = bytes([term]) * (R - carry - start[nxt])
+        cur = nxt
+        if cols and cols[0]:
+            yield cols

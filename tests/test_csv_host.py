@@ -1,0 +1,213 @@
+"""csrc/kq_csv.cu compiled for the HOST (tests/host_shim/: kernels run as plain functions, one call per block and thread, in
+sequence; device memory is host memory) and checked against the oracle: the real host orchestration of kq_csv_scan and of
+the reader kq_csv_reader_open/next/close — format detection, projection, piece cutting, carried tails, alignment padding,
+header skipping, the last piece's terminator, error paths — and the kernels' index arithmetic, where there is no GPU.
+Stream ordering is not modelled (every call completes before it returns); the GPU suite covers that (tests/test_gpu_csv.py)."""
+import ctypes as C
+import os
+import re
+import subprocess
+
+import pytest
+
+from csv_cases import CASES, synthetic
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(HERE)
+CSRC = os.path.join(ROOT, "query-engines_b200", "csrc")
+BUILD = os.path.join(HERE, "_build")
+
+
+def _host_source():
+    """kq_csv.cu with every `kernel<<<grid, block, smem, stream>>>(` rewritten to `KQ_LAUNCH(kernel, grid, block, `."""
+    src = open(os.path.join(CSRC, "kq_csv.cu")).read()
+    pat = re.compile(r"([A-Za-z_]\w*(?:<[^<>()]*>)?)<<<(.*?)>>>\(")
+    def sub(m):
+        cfg = [c.strip() for c in m.group(2).split(",")]
+        assert len(cfg) == 4, m.group(0)
+        return f"KQ_LAUNCH({m.group(1)}, {cfg[0]}, {cfg[1]}, "
+    out, n = pat.subn(sub, src)
+    assert n >= 6 and "<<<" not in out
+    return out
+
+
+@pytest.fixture(scope="module")
+def H():
+    os.makedirs(BUILD, exist_ok=True)
+    gen = os.path.join(BUILD, "kq_csv_host.cpp")
+    with open(gen, "w") as f:
+        f.write(_host_source())
+    so = os.path.join(BUILD, "libkqcsv_host.so")
+    cmd = ["g++", "-std=c++17", "-O1", "-g", "-fPIC", "-shared", "-Wall", "-Wno-unused-function", "-Wno-unknown-pragmas", "-Wno-subobject-linkage",
+           "-I", os.path.join(HERE, "host_shim"), "-I", CSRC, gen, os.path.join(HERE, "csv_host_harness.cpp"), "-o", so]
+    r = subprocess.run(cmd, capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr[-4000:]
+    L = C.CDLL(so)
+    P, PP = C.c_void_p, C.POINTER(C.c_void_p)
+    L.kqh_ctx_new.restype = P
+    L.kqh_ctx_free.argtypes = [P]
+    L.kqh_device_buffer.restype = P
+    L.kqh_device_buffer.argtypes = [P, C.c_char_p, C.c_int64, C.c_int]
+    L.kqh_device_free.argtypes = [P, P]
+    L.kq_last_error.restype = C.c_char_p
+    L.kq_last_error.argtypes = [P]
+    L.kq_csv_scan.argtypes = [P, P, C.c_int64, C.c_int, C.POINTER(C.c_int), C.c_int, PP]
+    L.kq_csv_reader_open.argtypes = [P, P, C.c_int64, C.c_int, C.POINTER(C.c_int), C.c_int, C.c_int64, PP]
+    L.kq_csv_reader_next.argtypes = [P, PP]
+    L.kq_csv_reader_close.argtypes = [P]
+    L.kq_batch_free.argtypes = [P]
+    L.kqh_batch_rows.restype = C.c_int64
+    L.kqh_batch_rows.argtypes = [P]
+    L.kqh_batch_cols.argtypes = [P]
+    L.kqh_col_bytes.restype = C.c_int64
+    L.kqh_col_bytes.argtypes = [P, C.c_int]
+    L.kqh_col_read.argtypes = [P, C.c_int, P, P]
+    L.kqh_live_blocks.restype = C.c_int64
+    return Host(L)
+
+
+class HostError(Exception):
+    pass
+
+
+class Host:
+    def __init__(self, L):
+        self.L = L
+        self.ctx = L.kqh_ctx_new()
+
+    def check(self, st):
+        if st != 0:
+            raise HostError(f"{st}: {self.L.kq_last_error(self.ctx).decode()}")
+
+    def read(self, b):
+        """batch handle -> list of columns (lists of str); frees the batch"""
+        L = self.L
+        rows, cols = L.kqh_batch_rows(b), []
+        for c in range(L.kqh_batch_cols(b)):
+            nb = L.kqh_col_bytes(b, c)
+            off = (C.c_int32 * (rows + 1))()
+            data = C.create_string_buffer(max(nb, 1))
+            L.kqh_col_read(b, c, off, data)
+            assert off[0] == 0 and off[rows] == nb
+            cols.append([data.raw[off[i]:off[i + 1]].decode("utf-8") for i in range(rows)])
+        L.kq_batch_free(b)
+        return cols
+
+    def _src(self, text, device, misalign):
+        if device:
+            p = self.L.kqh_device_buffer(self.ctx, text, len(text), misalign)
+            return p, C.c_void_p(p + misalign)
+        keep = C.create_string_buffer(text, max(len(text), 1))
+        return keep, C.cast(keep, C.c_void_p)
+
+    def scan(self, text, hdr=True, cols=None, device=False, misalign=0):
+        keep, src = self._src(text, device, misalign)
+        idx = list(cols or [])
+        arr = (C.c_int * max(len(idx), 1))(*idx)
+        out = C.c_void_p()
+        try:
+            self.check(self.L.kq_csv_scan(self.ctx, src, len(text), int(hdr), arr if idx else None, len(idx), C.byref(out)))
+            return self.read(out)
+        finally:
+            if device:
+                self.L.kqh_device_free(self.ctx, keep)
+
+    def batches(self, text, hdr=True, cols=None, piece=0, device=False, misalign=0):
+        keep, src = self._src(text, device, misalign)
+        idx = list(cols or [])
+        arr = (C.c_int * max(len(idx), 1))(*idx)
+        rd = C.c_void_p()
+        self.check(self.L.kq_csv_reader_open(self.ctx, src, len(text), int(hdr), arr if idx else None, len(idx), piece, C.byref(rd)))
+        try:
+            while True:
+                out = C.c_void_p()
+                self.check(self.L.kq_csv_reader_next(rd, C.byref(out)))
+                if not out.value:
+                    return
+                yield self.read(out)
+        finally:
+            self.L.kq_csv_reader_close(rd)
+            if device:
+                self.L.kqh_device_free(self.ctx, keep)
+
+    def clean(self):
+        return self.L.kqh_live_blocks() == 0 and self.L.kqh_guard_errors() == 0
+
+
+def columns(batch):
+    return [a.to_pylist() for a in batch.to_arrow()]
+
+
+def concat(batches, ncols):
+    out = [[] for _ in range(ncols)]
+    for b in batches:
+        assert b and b[0]                                         # batches without rows are not yielded (Main.kt:245-247)
+        for acc, col in zip(out, b):
+            acc.extend(col)
+    return out
+
+
+@pytest.mark.parametrize("case", CASES, ids=[c[0] for c in CASES])
+def test_scan_and_reader_on_the_cases(H, case):
+    _, text, hdr, names, want = case
+    assert H.scan(text, hdr) == want
+    if text:
+        assert H.scan(text, hdr, device=True) == want == H.scan(text, hdr, device=True, misalign=5)
+    batches = list(H.batches(text, hdr))
+    assert len(batches) == (1 if want and want[0] else 0)
+    assert concat(batches, len(names)) == want
+    assert H.clean()
+
+
+@pytest.mark.parametrize("rows,crlf", [(1, False), (63, True), (3000, False), (3000, True)])
+def test_synthetic_scan_matches_the_oracle(H, oracle, rows, crlf):
+    text = synthetic(rows, seed=rows, crlf=crlf)
+    want = columns(oracle.csv_scan(text, True))
+    assert H.scan(text, True) == want
+    assert H.scan(text, True, [4, 1, 4]) == [want[4], want[1], want[4]]
+    pad = (-len(text)) % 16
+    assert H.scan(text + (b"\r\n" if crlf else b"\n") * (pad // (2 if crlf else 1)), True, device=True) == want        # in place: resident, aligned, terminated
+    assert H.clean()
+
+
+@pytest.mark.parametrize("rows,crlf,piece", [(3000, False, 256), (3000, True, 256), (3000, True, 512), (3000, False, 4096), (3000, True, 1 << 16),
+                                             (20_000, False, 8192)])
+def test_reader_batches_concatenate_to_the_whole_scan(H, oracle, rows, crlf, piece):
+    text = synthetic(rows, seed=rows + 1, crlf=crlf)
+    want = columns(oracle.csv_scan(text, True))
+    for device, misalign in ((False, 0), (True, 3)):
+        batches = list(H.batches(text, True, piece=piece, device=device, misalign=misalign))
+        assert len(batches) > 1 and sum(len(b[0]) for b in batches) == rows
+        assert concat(batches, 6) == want
+    stripped = text.rstrip(b"\r\n")                                 # a last record without a line separator still ends
+    assert concat(list(H.batches(stripped, True, [5, 0], piece=piece)), 2) == [want[5], want[0]]
+    assert concat(list(H.batches(text, False, piece=piece)), 6) == columns(oracle.csv_scan(text, False))
+    assert H.clean()
+
+
+def test_reader_errors_and_edges(H):
+    long_record = b"a,b\n" + b"x" * 600 + b",1\n2,3\n"
+    with pytest.raises(HostError, match="longer than the reader's piece"):
+        list(H.batches(long_record, True, piece=256))
+    assert concat(list(H.batches(long_record, True, piece=1024)), 2) == [["x" * 600, "2"], ["1", "3"]]
+    text = synthetic(2000, seed=2) + b'7,"open,1,2,3,4\n'
+    seen = 0
+    with pytest.raises(HostError, match="quoted"):
+        for b in H.batches(text, True, piece=4096):
+            seen += len(b[0])
+    assert 0 < seen <= 2000
+    with pytest.raises(HostError, match="quoted"):
+        H.scan(text, True)
+    assert list(H.batches(b"", True)) == [] and list(H.batches(b"a,b\n", True)) == []
+    assert list(H.batches(b"a,b\n1,2", True, cols=[1])) == [[["2"]]]
+    with pytest.raises(HostError, match="out of range"):
+        list(H.batches(b"a,b\n1,2\n", True, cols=[2]))
+    assert H.clean()
+
+
+def test_reader_model_and_host_build_cut_the_same_pieces(H):
+    """The Python model of the reader (tests/csv_device_model.py) and the compiled host code yield the same batches."""
+    import csv_device_model as dm
+    text = synthetic(1500, seed=9, crlf=True)
+    for piece in (256, 768, 2048):
+        assert list(H.batches(text, True, piece=piece)) == list(dm.reader(text, True, piece))

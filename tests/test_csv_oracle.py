@@ -60,7 +60,7 @@ def test_product_header_detection_matches_oracle(oracle, case):
 
 
 # ---------------------------------------------------------------- randomised round trips through Python's csv.writer
-from hypothesis import given, settings, strategies as st
+from hypothesis import assume, given, settings, strategies as st
 
 _ALPHABET = st.sampled_from(list("abcXYZ019 ,;|\t\"'\n\r-_äÅ日") )
 _FIELD = st.text(_ALPHABET, max_size=8)
@@ -126,3 +126,52 @@ def test_device_model_agrees_with_oracle_on_random_tables(oracle, ncols, data, c
             buf.write(eol * data.draw(st.integers(0, 3)))       # empty lines between records (skipped, rule C3)
     text = buf.getvalue().encode("utf-8")
     assert dm.scan(text, True) == columns(oracle.csv_scan(text, True))
+
+
+# ---------------------------------------------------------------- the reader (kq_csv_reader_*): pieces cut at record boundaries
+def _concat(batches, ncols):
+    out = [[] for _ in range(ncols)]
+    for b in batches:
+        for acc, col in zip(out, b):
+            acc.extend(col)
+    return out
+
+
+@pytest.mark.parametrize("rows,crlf", [(1, False), (63, True), (2000, False), (2000, True)])
+@pytest.mark.parametrize("piece", [96, 256, 1024, 1 << 20])
+def test_reader_model_pieces_concatenate_to_the_whole_scan(oracle, rows, crlf, piece):
+    """The reader's piece logic (cut after the last complete record, carry the tail, pad to 16 bytes with terminators,
+    header skipped once, last piece terminated) on files with quoted delimiters, line breaks inside quotes, CRLF and
+    empty lines: the batches concatenate to what the oracle reads from the whole text."""
+    text = synthetic(rows, seed=rows + 1, crlf=crlf)
+    want = columns(oracle.csv_scan(text, True))
+    batches = list(dm.reader(text, True, piece))
+    assert _concat(batches, len(want)) == want
+    assert all(b[0] for b in batches)                              # batches without rows are not yielded (Main.kt:245-247)
+    if piece >= len(text):
+        assert len(batches) == 1
+
+
+@settings(max_examples=200, deadline=None)
+@given(ncols=st.integers(2, 4), data=st.data(), crlf=st.booleans(), blanks=st.booleans(), piece=st.sampled_from([64, 80, 128, 256]),
+       hdr=st.booleans(), end_eol=st.booleans())
+def test_reader_model_on_random_tables(oracle, ncols, data, crlf, blanks, piece, hdr, end_eol):
+    rows = data.draw(st.lists(st.lists(st.text(_ALPHABET, max_size=12), min_size=ncols, max_size=ncols), max_size=12))
+    eol = "\r\n" if crlf else "\n"
+    buf = io.StringIO(newline="")
+    w = csv.writer(buf, lineterminator=eol, quoting=csv.QUOTE_MINIMAL)
+    w.writerow([f"h{i}" for i in range(ncols)])
+    for r in rows:
+        w.writerow(r)
+        if blanks:
+            buf.write(eol * data.draw(st.integers(0, 3)))
+    text = buf.getvalue()
+    if not end_eol:
+        text = text.rstrip("\r\n")                                 # a last record without a line separator still ends
+    text = text.encode("utf-8")
+    want = columns(oracle.csv_scan(text, hdr))
+    try:
+        batches = list(dm.reader(text, hdr, piece))
+    except OverflowError:
+        assume(False)                                               # a record longer than the piece: the reader refuses (tested on the GPU)
+    assert _concat(batches, len(want)) == (want if want and want[0] else [[] for _ in want])
