@@ -658,8 +658,9 @@ struct ko_expr { ExprPtr e; };
 // (Main.kt:289-296, 322), then stores getValue(name, "").trim() of every field (Main.kt:262-264). Restated as rules
 // C1-C9 (query-engines_b200/csrc/kq_csv.cu header), here as a plain character-at-a-time tokenizer:
 //   C1 separator "\n" (CRLF: the CR goes with the terminator) or lone "\r" when the text has no "\n"; delimiter = most
-//      frequent of , ; TAB | outside quotes in the first record.   C2 '"' toggles quoting wherever it stands; a value
-//      whose first non-blank byte is '"' is unquoted ("" -> "), what follows its closing quote is dropped.
+//      frequent of , ; TAB | outside quotes in the first record (found with all four counting as delimiters).
+//   C2 a '"' opens a quoted section only as the first non-blank byte of a field; inside, "" is a literal quote and a single
+//      '"' closes; every other '"' is data. What follows the closing quote of a value is dropped.
 //   C3 lines without a byte are skipped.  C4 header record names the columns.  C5 values are trimmed (<= 0x20).
 //   C6 all columns Utf8, never null; missing field = "".  C7 projection by file column index.  C8 surplus fields ignored.
 struct CsvText {
@@ -684,41 +685,78 @@ static std::string csv_field_value(const std::string& raw) {
     }
     return csv_trim(v);                       // String.trim() on the parsed value (Main.kt:263)
 }
+// Rule C2 one character at a time. Where a character stands: at the start of a field (only blanks so far), in an unquoted
+// value, inside a quoted section, or right behind a '"' met inside a quoted section (it closed the section unless the next
+// character is another '"'). `delims` are the bytes that separate fields (one byte when the delimiter is known; all four
+// candidates while it is being detected).
+struct CsvQuoteRule {
+    enum Where { FieldStart, Unquoted, Quoted, QuoteInQuoted } at = FieldStart;
+    std::string delims;
+    char term;
+    CsvQuoteRule(const std::string& d, char t) : delims(d), term(t) {}
+    bool separates(char c) const { return c == term || delims.find(c) != std::string::npos; }
+    // consumes c; true when c stands outside quotes (so a delimiter or terminator there is a real one)
+    bool outside(char c) {
+        switch (at) {
+            case FieldStart:
+                if (separates(c)) return true;
+                if (c == '"') { at = Quoted; return false; }
+                if ((unsigned char)c > 0x20) at = Unquoted;
+                return true;
+            case Unquoted:
+                if (separates(c)) at = FieldStart;
+                return true;                                       // a '"' here is data
+            case Quoted:
+                if (c == '"') at = QuoteInQuoted;
+                return false;
+            default:                                               // QuoteInQuoted
+                if (c == '"') { at = Quoted; return false; }       // "" = a literal quote
+                at = separates(c) ? FieldStart : Unquoted;         // the quote before c closed the section
+                return true;
+        }
+    }
+};
+// lines: split at terminators outside quotes
+static std::vector<std::string> csv_lines(const std::string& all, const std::string& delims, char term, bool whole_text) {
+    std::vector<std::string> lines;
+    std::string cur;
+    CsvQuoteRule q(delims, term);
+    for (char c : all) {
+        if (q.outside(c) && c == term) { lines.push_back(cur); cur.clear(); }
+        else cur += c;
+    }
+    if (whole_text && q.at == CsvQuoteRule::Quoted) throw KqError(E_ILLEGAL_STATE, "CSV text ends inside a quoted field");
+    if (!cur.empty()) lines.push_back(cur);
+    return lines;
+}
 static CsvText csv_tokenize(const uint8_t* text, int64_t n) {
     CsvText out;
     std::string all((const char*)text, (size_t)n);
     if (all.find('\n') == std::string::npos && all.find('\r') != std::string::npos) out.term = '\r';
-    // lines: split at terminators outside quotes
-    std::vector<std::string> lines;
-    {
-        std::string cur; bool inq = false;
-        for (char c : all) {
-            if (c == '"') inq = !inq;
-            if (c == out.term && !inq) { lines.push_back(cur); cur.clear(); }
-            else cur += c;
-        }
-        if (inq) throw KqError(E_ILLEGAL_STATE, "CSV text ends inside a quoted field");
-        if (!cur.empty()) lines.push_back(cur);
-    }
-    bool first = true;
-    for (std::string& line : lines) {
+    auto empty_line = [&](std::string& line) {
         if (out.term == '\n' && !line.empty() && line.back() == '\r') line.pop_back();     // CRLF
-        if (line.empty()) continue;                                                        // skipEmptyLines (Main.kt:293)
-        if (first) {                            // delimiter detection on the first record (Main.kt:291)
-            first = false;
-            const char cand[4] = {',', ';', '\t', '|'};
-            long cnt[4] = {0, 0, 0, 0};
-            bool inq = false;
-            for (char c : line) { if (c == '"') inq = !inq; else if (!inq) for (int k = 0; k < 4; k++) cnt[k] += c == cand[k]; }
-            int best = 0;
-            for (int k = 1; k < 4; k++) if (cnt[k] > cnt[best]) best = k;
-            out.delim = cand[best];
-        }
+        return line.empty();                                                               // skipEmptyLines (Main.kt:293)
+    };
+    // delimiter detection on the first record (Main.kt:291), found with every candidate counting as a delimiter
+    const std::string cand = ",;\t|";
+    for (std::string& line : csv_lines(all, cand, out.term, false)) {
+        if (empty_line(line)) continue;
+        long cnt[4] = {0, 0, 0, 0};
+        CsvQuoteRule q(cand, out.term);
+        for (char c : line) if (q.outside(c)) for (int k = 0; k < 4; k++) cnt[k] += c == cand[(size_t)k];
+        int best = 0;
+        for (int k = 1; k < 4; k++) if (cnt[k] > cnt[best]) best = k;
+        out.delim = cand[(size_t)best];
+        break;
+    }
+    const std::string delim(1, out.delim);
+    for (std::string& line : csv_lines(all, delim, out.term, true)) {
+        if (empty_line(line)) continue;
         std::vector<std::string> fields;
-        std::string cur; bool inq = false;
+        std::string cur;
+        CsvQuoteRule q(delim, out.term);
         for (char c : line) {
-            if (c == '"') inq = !inq;
-            if (c == out.delim && !inq) { fields.push_back(csv_field_value(cur)); cur.clear(); }
+            if (q.outside(c) && c == out.delim) { fields.push_back(csv_field_value(cur)); cur.clear(); }
             else cur += c;
         }
         fields.push_back(csv_field_value(cur));

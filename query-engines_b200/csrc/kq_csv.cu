@@ -6,9 +6,11 @@
 // then goes through getValue(name, "").trim() into a VarCharVector (Main.kt:262-264). Rules restated here (C1-C9,
 // oracle: ko_csv_scan in oracle/kq_oracle.cpp; parity UNPINNED — see DESIGN.md):
 //   C1 line separator: "\n" (a preceding "\r" is whitespace and trimmed) or, when the text holds no "\n", "\r";
-//      delimiter: the most frequent of , ; TAB | outside quotes in the first record (ties: that order).
-//   C2 quote '"', escaped by doubling; a field whose first non-blank byte is a quote is quoted: delimiters and line
-//      separators inside are data; bytes between the closing quote and the next delimiter are dropped.
+//      delimiter: the most frequent of , ; TAB | outside quotes in the first record (ties: that order; the first record
+//      is found with all four acting as delimiters).
+//   C2 quote '"': a field whose first non-blank byte is a quote is quoted — delimiters and line separators inside are
+//      data, "" is a literal quote, a single '"' closes, bytes between the closing quote and the next delimiter are
+//      dropped. A quote anywhere else (inside an unquoted value, behind a closed section) is data, as CSV parsers treat it.
 //   C3 records without any byte are skipped (skipEmptyLines).   C4 has_headers: the first record names the columns.
 //   C5 each value is trimmed of leading/trailing bytes <= 0x20 (String.trim(), Main.kt:263), quoted or not.
 //   C6 every column is Utf8 and never null: a missing or empty field reads "" (getValue's default, Main.kt:263).
@@ -17,7 +19,8 @@
 //
 // Device pipeline (all HBM-bound byte work; no tensor cores). Passes 1-3 see the text as one bit per byte (SWAR masks
 // over 64-byte blocks), so no pass runs a per-byte state machine:
-//   1. quote scan      : device-wide exclusive sum of '"' counts per block -> quote parity at every block start
+//   1. quote states    : every block's transition over the three quote states (a walk over the block's quotes; most blocks
+//                        have none), composed per chunk of blocks, chained, expanded -> the quote state in front of every block
 //   2. record scan,    : device-wide exclusive sums of (a) terminators outside quotes that end a non-empty record and
 //      separator scan    (b) field separators = those terminators + delimiters outside quotes
 //   3. separators      : the position of every separator in text order + each record's last separator index; field c of
@@ -25,6 +28,9 @@
 //   4. field lengths   : one thread per record, trimmed/unescaped length of every projected field
 //   5. offsets         : one device-wide exclusive sum per projected column -> Arrow int32 offsets
 //   6. copy            : one thread per record writes the field bytes
+// kq_csv_reader_* runs the same passes piece by piece over texts of any size (Sequence<RecordBatch>, Main.kt:239-249).
+// The file is also compiled for the HOST by the CPU test-suite (tests/test_csv_host.py, tests/host_shim/): keep the
+// kernels free of warp-level intrinsics so that they stay checkable against the oracle without a GPU.
 #include <algorithm>
 #include <cstring>
 #include <string>
@@ -44,62 +50,45 @@ struct CsvFormat { uint8_t delim, term; };
 
 __device__ __forceinline__ bool csv_blank(uint8_t c) { return c <= 0x20; }
 
-// number of '"' in block i
-struct QuoteCount {
-    const uint8_t* text; long long n;
-    __device__ __forceinline__ int operator()(long long i) const {
-        const long long b = i * CSV_BLOCK;
-        int k = 0;
-        if (b + CSV_BLOCK <= n) {
-            const uint4* p = reinterpret_cast<const uint4*>(text + b);
-#pragma unroll
-            for (int j = 0; j < CSV_BLOCK / 16; j++) {
-                const uint4 v = __ldg(p + j);
-                const uint32_t w[4] = {v.x, v.y, v.z, v.w};
-#pragma unroll
-                for (int t = 0; t < 4; t++) {
-                    uint32_t x = w[t] ^ 0x22222222u;                            // zero byte where the text has a quote
-                    x = ~(((x & 0x7F7F7F7Fu) + 0x7F7F7F7Fu) | x) & 0x80808080u;  // 0x80 in every zero byte (exact)
-                    k += __popc(x);
-                }
-            }
-        } else {
-            for (long long j = b; j < n; j++) k += text[j] == '"';
-        }
-        return k;
-    }
-};
+// ---- rule C2 on the device ---------------------------------------------------------------------------------------
+// Between two bytes the scan is outside quotes (Q_OUT), inside a quoted section (Q_IN), or outside right behind the quote
+// that closed one (Q_OUTE: a '"' now is the second half of a doubled quote and re-opens the section). Only quotes change
+// the state: IN -"-> OUTE, OUTE -"-> IN, OUT -"-> IN if the quote is the first non-blank byte of its field, else OUT (the
+// quote is data); any other byte takes OUTE to OUT. Whether a quote stands at the start of a field is a LOCAL property
+// once we know we are outside: its nearest non-blank byte in front is a delimiter or terminator (which, being outside as
+// well, is a real one) or the text starts there. So a 64-byte block is one transition over three states, computed by
+// walking the block's quotes (most blocks have none), and the state in front of every block is a prefix composition of
+// those transitions (k_csv_quote_maps -> k_csv_compose_chunks -> k_csv_chunk_states -> k_csv_block_states).
+enum : uint32_t { Q_OUT = 0, Q_IN = 1, Q_OUTE = 2 };
+#ifndef KQ_CSV_CHUNK
+#define KQ_CSV_CHUNK 1024                // the host build of the test-suite also runs with 16, so that small texts span many chunks
+#endif
+constexpr int CSV_CHUNK = KQ_CSV_CHUNK;  // blocks whose transitions one thread composes
+static_assert(CSV_CHUNK % 16 == 0, "chunks start 16-byte aligned in the per-block state array");
 
-// Is the terminator at position p the end of a NON-EMPTY record? (rule C3; p is outside quotes, so are the bytes before it
-// unless they are quotes themselves, which makes the record non-empty anyway)
-__device__ __forceinline__ bool csv_ends_record(const uint8_t* text, long long p, CsvFormat f) {
-    if (p == 0) return false;
-    const uint8_t a = text[p - 1];
-    if (a == f.term) return false;
-    if (f.term == '\n' && a == '\r') return !(p == 1 || text[p - 2] == '\n');
-    return true;
+__device__ __forceinline__ bool csv_pad(uint8_t c, CsvFormat f) { return c <= 0x20 && c != f.delim && c != f.term; }   // blank between a separator and a value
+
+// One bit per byte of block i (bytes past the end of the text: zero)
+struct RawMasks { uint64_t q, t, c, d; int nbytes; };
+__device__ __forceinline__ uint64_t swar_zero4(uint32_t x) {          // bit k = byte k of x is zero
+    x = ~(((x & 0x7F7F7F7Fu) + 0x7F7F7F7Fu) | x) & 0x80808080u;        // 0x80 in every zero byte (exact)
+    return (uint64_t)((((x >> 7) * 0x00204081u) >> 21) & 0xFu);
 }
-
-// One bit per byte of block i: `rec` = terminators outside quotes that end a non-empty record, `delim` = delimiters
-// outside quotes. Whole blocks: SWAR zero-byte test + multiply-gather into 64-bit masks, quote state by prefix XOR, the
-// emptiness test of csv_ends_record by shifted masks (carries: the two bytes in front of the block; the start of the
-// text counts as a terminator at position -1). The last, partial block goes byte by byte.
-struct BlockMasks { uint64_t rec, delim; };
-__device__ __forceinline__ BlockMasks csv_block_masks(const uint8_t* __restrict__ text, long long n, long long i, const int32_t* __restrict__ quotes_before, CsvFormat f) {
+__device__ __forceinline__ RawMasks csv_raw_masks(const uint8_t* __restrict__ text, long long n, long long i, CsvFormat f) {
     const long long b = i * CSV_BLOCK;
-    const uint32_t inq = (uint32_t)quotes_before[i] & 1u;
-    BlockMasks m{0, 0};
+    RawMasks m{0, 0, 0, 0, CSV_BLOCK};
     if (b + CSV_BLOCK > n) {
-        uint32_t q = inq;
+        m.nbytes = (int)(n - b);
         for (long long p = b; p < n; p++) {
             const uint8_t c = text[p];
-            if (c == '"') q ^= 1u;
-            else if (!q && c == f.term) { if (csv_ends_record(text, p, f)) m.rec |= 1ULL << (p - b); }
-            else if (!q && c == f.delim) m.delim |= 1ULL << (p - b);
+            const uint64_t bit = 1ULL << (p - b);
+            if (c == '"') m.q |= bit;
+            if (c == f.term) m.t |= bit;
+            if (c == '\r') m.c |= bit;
+            if (c == f.delim) m.d |= bit;
         }
         return m;
     }
-    uint64_t qm = 0, tm = 0, cm = 0, dm = 0;
     const uint4* p4 = reinterpret_cast<const uint4*>(text + b);
     const uint32_t tpat = f.term * 0x01010101u, dpat = f.delim * 0x01010101u;
 #pragma unroll
@@ -108,48 +97,213 @@ __device__ __forceinline__ BlockMasks csv_block_masks(const uint8_t* __restrict_
         const uint32_t w[4] = {v.x, v.y, v.z, v.w};
 #pragma unroll
         for (int t = 0; t < 4; t++) {
-            auto bits = [](uint32_t x) -> uint64_t {          // bit k = byte k of x is zero
-                x = ~(((x & 0x7F7F7F7Fu) + 0x7F7F7F7Fu) | x) & 0x80808080u;
-                return (uint64_t)((((x >> 7) * 0x00204081u) >> 21) & 0xFu);
-            };
             const int sh = 16 * j + 4 * t;
-            qm |= bits(w[t] ^ 0x22222222u) << sh;
-            tm |= bits(w[t] ^ tpat) << sh;
-            cm |= bits(w[t] ^ 0x0D0D0D0Du) << sh;
-            dm |= bits(w[t] ^ dpat) << sh;
+            m.q |= swar_zero4(w[t] ^ 0x22222222u) << sh;
+            m.t |= swar_zero4(w[t] ^ tpat) << sh;
+            m.c |= swar_zero4(w[t] ^ 0x0D0D0D0Du) << sh;
+            m.d |= swar_zero4(w[t] ^ dpat) << sh;
         }
     }
-    uint64_t x = qm;
-    x ^= x << 1; x ^= x << 2; x ^= x << 4; x ^= x << 8; x ^= x << 16; x ^= x << 32;
-    const uint64_t inside = inq ? ~x : x;                                        // in-quote state at every non-quote byte
-    const bool t1 = b == 0 || text[b - 1] == f.term, t2 = b <= 1 || text[b - 2] == f.term;
-    uint64_t empty = (tm << 1) | (uint64_t)t1;
-    if (f.term == '\n') {
-        const uint64_t prev_c = (cm << 1) | (uint64_t)(b > 0 && text[b - 1] == '\r');
-        const uint64_t prev2_t = (tm << 2) | ((uint64_t)t1 << 1) | (uint64_t)t2;
-        empty |= prev_c & prev2_t;
-    }
-    m.rec = tm & ~inside & ~empty;
-    m.delim = dm & ~inside;
     return m;
 }
+__device__ __forceinline__ bool csv_has_quote(const uint8_t* __restrict__ text, long long n, long long i) {
+    const long long b = i * CSV_BLOCK;
+    if (b + CSV_BLOCK > n) {
+        for (long long p = b; p < n; p++) if (text[p] == '"') return true;
+        return false;
+    }
+    const uint4* p4 = reinterpret_cast<const uint4*>(text + b);
+    uint32_t any = 0;
+#pragma unroll
+    for (int j = 0; j < CSV_BLOCK / 16; j++) {
+        const uint4 v = __ldg(p4 + j);
+        const uint32_t w[4] = {v.x ^ 0x22222222u, v.y ^ 0x22222222u, v.z ^ 0x22222222u, v.w ^ 0x22222222u};
+#pragma unroll
+        for (int t = 0; t < 4; t++) any |= ~(((w[t] & 0x7F7F7F7Fu) + 0x7F7F7F7Fu) | w[t]) & 0x80808080u;
+    }
+    return any != 0;
+}
+// Quotes of block i that can open a quoted section (only evaluated for blocks that hold a quote): field starts — the byte
+// behind every delimiter/terminator, and the block's first byte if the text in front of it ends in [separator][blanks] —
+// are carried through runs of blanks by one addition (the carry ripples through the run and stops behind it).
+__device__ __noinline__ uint64_t csv_opener_candidates(const uint8_t* __restrict__ text, long long n, long long i, const RawMasks m, CsvFormat f) {
+    const long long b = i * CSV_BLOCK;
+    uint64_t blank = 0;
+    if (m.nbytes == CSV_BLOCK) {
+        const uint4* p4 = reinterpret_cast<const uint4*>(text + b);
+#pragma unroll
+        for (int j = 0; j < CSV_BLOCK / 16; j++) {
+            const uint4 v = __ldg(p4 + j);
+            const uint32_t w[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+            for (int t = 0; t < 4; t++) {
+                // 0x80 in every byte <= 0x20: high bit clear and the low seven bits do not carry when 0x5F is added
+                const uint32_t le = ~(((w[t] & 0x7F7F7F7Fu) + 0x5F5F5F5Fu) | w[t]) & 0x80808080u;
+                blank |= (uint64_t)((((le >> 7) * 0x00204081u) >> 21) & 0xFu) << (16 * j + 4 * t);
+            }
+        }
+        blank &= ~(m.d | m.t);
+    } else {
+        for (int j = 0; j < m.nbytes; j++) blank |= (uint64_t)csv_pad(text[b + j], f) << j;
+    }
+    long long p = b - 1;
+    while (p >= 0 && csv_pad(text[p], f)) p--;
+    const uint64_t carry = p < 0 || text[p] == f.delim || text[p] == f.term;
+    const uint64_t start = ((m.d | m.t) << 1) | carry;
+    const uint64_t reach = ((blank + (start & blank)) ^ blank) | start;
+    return m.q & reach;
+}
+// The state behind a block whose quotes are `q` (of which `cand` may open a section), entered in state s; *sq receives the
+// quotes that switch between inside and outside.
+__device__ __forceinline__ uint32_t csv_quote_walk(int nbytes, uint64_t q, uint64_t cand, uint32_t s, uint64_t* sq) {
+    uint64_t toggles = 0;
+    int prev = -1;
+    while (q) {
+        const int j = __ffsll((long long)q) - 1;
+        q &= q - 1;
+        if (s == Q_OUTE && j != prev + 1) s = Q_OUT;
+        if (s == Q_IN) { s = Q_OUTE; toggles |= 1ULL << j; }
+        else if (s == Q_OUTE || ((cand >> j) & 1ULL)) { s = Q_IN; toggles |= 1ULL << j; }
+        prev = j;
+    }
+    if (s == Q_OUTE && prev != nbytes - 1) s = Q_OUT;
+    if (sq) *sq = toggles;
+    return s;
+}
+// transitions are three 2-bit states packed into a byte: bits [2s, 2s+1] = the state behind the block when s is in front
+__device__ __forceinline__ uint32_t qmap_apply(uint32_t map, uint32_t s) { return (map >> (2 * s)) & 3u; }
+__device__ __forceinline__ uint32_t qmap_then(uint32_t first, uint32_t second) {
+    return qmap_apply(second, qmap_apply(first, Q_OUT)) | (qmap_apply(second, qmap_apply(first, Q_IN)) << 2) | (qmap_apply(second, qmap_apply(first, Q_OUTE)) << 4);
+}
+constexpr uint32_t QMAP_ID = Q_OUT | (Q_IN << 2) | (Q_OUTE << 4);
+
+// pass 1a: every block's transition
+__global__ void k_csv_quote_maps(const uint8_t* __restrict__ text, long long n, long long nblocks, CsvFormat f, uint8_t* __restrict__ qstate) {
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < nblocks; i += (long long)gridDim.x * blockDim.x) {
+        uint32_t map = Q_OUT | (Q_IN << 2) | (Q_OUT << 4);            // no quote in the block
+        if (csv_has_quote(text, n, i)) {
+            const RawMasks m = csv_raw_masks(text, n, i, f);
+            const uint64_t cand = csv_opener_candidates(text, n, i, m, f);
+            map = csv_quote_walk(m.nbytes, m.q, cand, Q_OUT, nullptr) | (csv_quote_walk(m.nbytes, m.q, cand, Q_IN, nullptr) << 2) |
+                  (csv_quote_walk(m.nbytes, m.q, cand, Q_OUTE, nullptr) << 4);
+        }
+        qstate[i] = (uint8_t)map;
+    }
+}
+// pass 1b: one transition per chunk of CSV_CHUNK blocks (16 transitions per load; chunks start 16-byte aligned)
+__global__ void k_csv_compose_chunks(const uint8_t* __restrict__ qstate, long long nblocks, long long nchunks, uint8_t* __restrict__ chunk_map) {
+    for (long long k = blockIdx.x * (long long)blockDim.x + threadIdx.x; k < nchunks; k += (long long)gridDim.x * blockDim.x) {
+        const long long i1 = (k + 1) * CSV_CHUNK < nblocks ? (k + 1) * CSV_CHUNK : nblocks;
+        long long i = k * CSV_CHUNK;
+        uint32_t map = QMAP_ID;
+        for (; i + 16 <= i1; i += 16) {
+            const uint4 v = *reinterpret_cast<const uint4*>(qstate + i);
+            const uint32_t w[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+            for (int t = 0; t < 4; t++)
+#pragma unroll
+                for (int j = 0; j < 4; j++) map = qmap_then(map, (w[t] >> (8 * j)) & 0xFFu);
+        }
+        for (; i < i1; i++) map = qmap_then(map, qstate[i]);
+        chunk_map[k] = (uint8_t)map;
+    }
+}
+// pass 1c (one thread): the state in front of every chunk (replaces the chunk's transition), and behind the text
+__global__ void k_csv_chunk_states(uint8_t* chunk_map, long long nchunks, unsigned long long* final_state) {
+    if (blockIdx.x != 0 || threadIdx.x != 0) return;
+    uint32_t s = Q_OUT;
+    long long k = 0;
+    for (; k + 8 <= nchunks; k += 8) {
+        unsigned long long w = *reinterpret_cast<const unsigned long long*>(chunk_map + k), o = 0;
+#pragma unroll
+        for (int j = 0; j < 8; j++) {
+            o |= (unsigned long long)s << (8 * j);
+            s = qmap_apply((uint32_t)(w >> (8 * j)) & 0xFFu, s);
+        }
+        *reinterpret_cast<unsigned long long*>(chunk_map + k) = o;
+    }
+    for (; k < nchunks; k++) {
+        const uint32_t map = chunk_map[k];
+        chunk_map[k] = (uint8_t)s;
+        s = qmap_apply(map, s);
+    }
+    *final_state = s;
+}
+// pass 1d: the state in front of every block (replaces the block's transition in place)
+__global__ void k_csv_block_states(uint8_t* __restrict__ qstate, long long nblocks, long long nchunks, const uint8_t* __restrict__ chunk_state) {
+    for (long long k = blockIdx.x * (long long)blockDim.x + threadIdx.x; k < nchunks; k += (long long)gridDim.x * blockDim.x) {
+        const long long i1 = (k + 1) * CSV_CHUNK < nblocks ? (k + 1) * CSV_CHUNK : nblocks;
+        long long i = k * CSV_CHUNK;
+        uint32_t s = chunk_state[k];
+        for (; i + 16 <= i1; i += 16) {
+            const uint4 v = *reinterpret_cast<const uint4*>(qstate + i);
+            uint32_t w[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+            for (int t = 0; t < 4; t++) {
+                uint32_t o = 0;
+#pragma unroll
+                for (int j = 0; j < 4; j++) {
+                    o |= s << (8 * j);
+                    s = qmap_apply((w[t] >> (8 * j)) & 0xFFu, s);
+                }
+                w[t] = o;
+            }
+            uint4 r; r.x = w[0]; r.y = w[1]; r.z = w[2]; r.w = w[3];
+            *reinterpret_cast<uint4*>(qstate + i) = r;
+        }
+        for (; i < i1; i++) {
+            const uint32_t map = qstate[i];
+            qstate[i] = (uint8_t)s;
+            s = qmap_apply(map, s);
+        }
+    }
+}
+
+// One bit per byte of block i: `rec` = terminators outside quotes that end a NON-EMPTY record (rule C3), `delim` =
+// delimiters outside quotes. Quote state by prefix XOR over the quotes that switch it; a terminator ends an empty record
+// when the byte in front of it is a terminator too (or a CR behind a terminator), tested with shifted masks (carries: the
+// two bytes in front of the block; the start of the text counts as a terminator at position -1).
+struct BlockMasks { uint64_t rec, delim; };
+__device__ __forceinline__ BlockMasks csv_block_masks(const uint8_t* __restrict__ text, long long n, long long i, const uint8_t* __restrict__ qstate, CsvFormat f) {
+    const long long b = i * CSV_BLOCK;
+    const RawMasks m = csv_raw_masks(text, n, i, f);
+    const uint32_t s = qstate[i];
+    uint64_t inside = 0;
+    if (m.q || s == Q_IN) {
+        uint64_t x = 0;
+        if (m.q) csv_quote_walk(m.nbytes, m.q, csv_opener_candidates(text, n, i, m, f), s, &x);
+        x ^= x << 1; x ^= x << 2; x ^= x << 4; x ^= x << 8; x ^= x << 16; x ^= x << 32;
+        inside = s == Q_IN ? ~x : x;                                          // in-quote state at every non-quote byte
+    }
+    const bool t1 = b == 0 || text[b - 1] == f.term, t2 = b <= 1 || text[b - 2] == f.term;
+    uint64_t empty = (m.t << 1) | (uint64_t)t1;
+    if (f.term == '\n') {
+        const uint64_t prev_c = (m.c << 1) | (uint64_t)(b > 0 && text[b - 1] == '\r');
+        const uint64_t prev2_t = (m.t << 2) | ((uint64_t)t1 << 1) | (uint64_t)t2;
+        empty |= prev_c & prev2_t;
+    }
+    BlockMasks r;
+    r.rec = m.t & ~inside & ~empty;
+    r.delim = m.d & ~inside;
+    return r;
+}
 struct RecordCount {          // records ending in block i
-    const uint8_t* text; long long n; const int32_t* quotes_before; CsvFormat f;
-    __device__ __forceinline__ int operator()(long long i) const { return __popcll(csv_block_masks(text, n, i, quotes_before, f).rec); }
+    const uint8_t* text; long long n; const uint8_t* qstate; CsvFormat f;
+    __device__ __forceinline__ int operator()(long long i) const { return __popcll(csv_block_masks(text, n, i, qstate, f).rec); }
 };
 struct SeparatorCount {       // field separators in block i: delimiters + record ends
-    const uint8_t* text; long long n; const int32_t* quotes_before; CsvFormat f;
+    const uint8_t* text; long long n; const uint8_t* qstate; CsvFormat f;
     __device__ __forceinline__ int operator()(long long i) const {
-        const BlockMasks m = csv_block_masks(text, n, i, quotes_before, f);
+        const BlockMasks m = csv_block_masks(text, n, i, qstate, f);
         return __popcll(m.rec | m.delim);
     }
 };
 // pass 3: the position of every separator, in text order, and for every record the index of its LAST separator (its end):
 // field c of record r is the text between separators rec_last[r-1] + c and rec_last[r-1] + c + 1.
-__global__ void k_csv_separators(const uint8_t* __restrict__ text, long long n, long long nblocks, const int32_t* __restrict__ quotes_before, CsvFormat f,
+__global__ void k_csv_separators(const uint8_t* __restrict__ text, long long n, long long nblocks, const uint8_t* __restrict__ qstate, CsvFormat f,
                                  const int32_t* __restrict__ recs_before, const int32_t* __restrict__ seps_before, int32_t* sep, int32_t* rec_last) {
     for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < nblocks; i += (long long)gridDim.x * blockDim.x) {
-        const BlockMasks m = csv_block_masks(text, n, i, quotes_before, f);
+        const BlockMasks m = csv_block_masks(text, n, i, qstate, f);
         uint64_t all = m.rec | m.delim;
         int32_t k = seps_before[i], r = recs_before[i];
         while (all) {
@@ -231,36 +385,44 @@ static void host_trim(std::string& s) {
     while (b > a && (unsigned char)s[b - 1] <= 0x20) b--;
     s = s.substr(a, b - a);
 }
-// First NON-EMPTY record (rule C3, the same test as csv_ends_record): [b, e) without its terminator; false if there is none.
-static bool host_first_line(const uint8_t* t, int64_t n, uint8_t term, int64_t* b, int64_t* e) {
+// The first NON-EMPTY record under rules C2 and C3, with the bytes of `delims` separating fields: its bytes [b, e) without
+// the terminator and the positions of its delimiters outside quotes; false if the text holds no record. The same state
+// machine as the device's (csv_quote_walk), one byte at a time; `fresh` = only blanks since the last separator.
+static bool host_first_span(const uint8_t* t, int64_t n, const char* delims, uint8_t term, int64_t* b, int64_t* e, std::vector<int64_t>* seps) {
     int64_t start = 0;
-    bool inq = false;
+    uint32_t state = Q_OUT;
+    bool fresh = true;
+    seps->clear();
     for (int64_t p = 0; p <= n; p++) {
         const bool at_end = p == n;
         const uint8_t c = at_end ? term : t[p];
-        if (c == '"' && !at_end) inq = !inq;
-        else if (c == term && (!inq || at_end)) {
-            int64_t end = p;
-            const bool empty = end == start || (term == '\n' && end == start + 1 && t[start] == '\r');
-            if (!empty) { *b = start; *e = end; return true; }
-            start = p + 1;
+        if (c == '"' && !at_end) {
+            if (state == Q_IN) state = Q_OUTE;
+            else if (state == Q_OUTE) state = Q_IN;
+            else { if (fresh) state = Q_IN; fresh = false; }
+            continue;
         }
+        if (state == Q_OUTE) state = Q_OUT;
+        if (state == Q_IN && !at_end) continue;
+        if (c == term) {
+            const bool empty = p == start || (term == '\n' && p == start + 1 && t[start] == '\r');
+            if (!empty) { *b = start; *e = p; return true; }
+            start = p + 1; fresh = true; seps->clear();
+        } else if (c && strchr(delims, c)) { seps->push_back(p); fresh = true; }
+        else if (c > 0x20) fresh = false;
     }
     return false;
 }
 static CsvFormat host_detect(const uint8_t* t, int64_t n) {
     CsvFormat f{',', '\n'};
     if (!memchr(t, '\n', (size_t)n) && memchr(t, '\r', (size_t)n)) f.term = '\r';
+    // the first record is found with all four candidates acting as delimiters; the most frequent outside quotes wins
     int64_t b, e;
-    if (!host_first_line(t, n, f.term, &b, &e)) return f;
+    std::vector<int64_t> seps;
+    if (!host_first_span(t, n, ",;\t|", f.term, &b, &e, &seps)) return f;
     int64_t cnt[4] = {0, 0, 0, 0};
     const uint8_t cand[4] = {',', ';', '\t', '|'};
-    bool inq = false;
-    for (int64_t p = b; p < e; p++) {
-        const uint8_t c = t[p];
-        if (c == '"') inq = !inq;
-        else if (!inq) for (int k = 0; k < 4; k++) cnt[k] += c == cand[k];
-    }
+    for (int64_t p : seps) for (int k = 0; k < 4; k++) cnt[k] += t[p] == cand[k];
     int best = 0;
     for (int k = 1; k < 4; k++) if (cnt[k] > cnt[best]) best = k;
     f.delim = cand[best];
@@ -269,30 +431,27 @@ static CsvFormat host_detect(const uint8_t* t, int64_t n) {
 static HostRecord host_first_record(const uint8_t* t, int64_t n, CsvFormat f) {
     HostRecord r;
     int64_t b, e;
-    if (!host_first_line(t, n, f.term, &b, &e)) { r.end = n; return r; }
+    std::vector<int64_t> seps;
+    const char delims[2] = {(char)f.delim, 0};
+    if (!host_first_span(t, n, delims, f.term, &b, &e, &seps)) { r.end = n; return r; }
     r.end = e;
+    seps.push_back(e);
     int64_t first = b;
-    bool inq = false;
-    for (int64_t p = b; p <= e; p++) {
-        const uint8_t c = p < e ? t[p] : f.delim;
-        if (c == '"' && p < e) { inq = !inq; continue; }
-        if (p == e || (!inq && c == f.delim)) {
-            std::string raw((const char*)t + first, (size_t)(p - first));
-            host_trim(raw);
-            if (!raw.empty() && raw[0] == '"') {
-                std::string v;
-                size_t q = 1;
-                while (q < raw.size() && !(raw[q] == '"' && !(q + 1 < raw.size() && raw[q + 1] == '"'))) { v += raw[q]; q += raw[q] == '"' ? 2 : 1; }
-                host_trim(v);
-                raw = v;
-            }
-            r.fields.push_back(raw);
-            first = p + 1;
+    for (int64_t p : seps) {
+        std::string raw((const char*)t + first, (size_t)(p - first));
+        host_trim(raw);
+        if (!raw.empty() && raw[0] == '"') {            // csv_value on the host
+            std::string v;
+            size_t q = 1;
+            while (q < raw.size() && !(raw[q] == '"' && !(q + 1 < raw.size() && raw[q + 1] == '"'))) { v += raw[q]; q += raw[q] == '"' ? 2 : 1; }
+            host_trim(v);
+            raw = v;
         }
+        r.fields.push_back(raw);
+        first = p + 1;
     }
     return r;
 }
-
 
 // ---- what both entry points (kq_csv_scan, kq_csv_reader_*) do first: where the text lives, format, header, projection ----
 struct CsvSource {
@@ -345,7 +504,8 @@ static int csv_scan_resident(kq_ctx* ctx, const uint8_t* d_text, long long n, Cs
                              bool partial, kq_batch** out, int64_t* consumed) {
     const int nout = (int)proj.size();
     const long long nblocks = (n + CSV_BLOCK - 1) / CSV_BLOCK;
-    int32_t *d_q = nullptr, *d_r = nullptr;
+    uint8_t *d_q = nullptr, *d_chunk = nullptr;     // per block: quote transition, then the quote state in front of it; per chunk likewise
+    int32_t* d_r = nullptr;
     unsigned long long* d_scratch = nullptr;        // [0] ticket, [1] total, [2] item count, [4..] tile descriptors
     int32_t *d_s = nullptr, *d_sep = nullptr, *d_last = nullptr;
     CsvCols* d_cols = nullptr;
@@ -354,7 +514,7 @@ static int csv_scan_resident(kq_ctx* ctx, const uint8_t* d_text, long long n, Cs
     // least two bytes, so nblocks * 32 bounds the record count)
     const long long ntiles = (std::max<long long>(nblocks, 1) * (CSV_BLOCK / 2) + SCAN_TILE - 1) / SCAN_TILE + 2;
     auto cleanup = [&](int st) {
-        kq_dev_free(ctx, d_q); kq_dev_free(ctx, d_r); kq_dev_free(ctx, d_scratch); kq_dev_free(ctx, d_s); kq_dev_free(ctx, d_sep); kq_dev_free(ctx, d_last); kq_dev_free(ctx, d_cols);
+        kq_dev_free(ctx, d_q); kq_dev_free(ctx, d_chunk); kq_dev_free(ctx, d_r); kq_dev_free(ctx, d_scratch); kq_dev_free(ctx, d_s); kq_dev_free(ctx, d_sep); kq_dev_free(ctx, d_last); kq_dev_free(ctx, d_cols);
         if (st != KQ_OK) for (kq_col* c : cols) kq_column_free(c);
         return st;
     };
@@ -368,7 +528,9 @@ static int csv_scan_resident(kq_ctx* ctx, const uint8_t* d_text, long long n, Cs
     int st = KQ_OK;
     if (consumed) *consumed = n;
     if (n > 0) {
-        if ((st = kq_dev_alloc(ctx, (size_t)(nblocks + 1) * 4, (void**)&d_q)) != KQ_OK) return cleanup(st);
+        const long long nchunks = (nblocks + CSV_CHUNK - 1) / CSV_CHUNK;
+        if ((st = kq_dev_alloc(ctx, (size_t)nblocks + 16, (void**)&d_q)) != KQ_OK) return cleanup(st);
+        if ((st = kq_dev_alloc(ctx, (size_t)nchunks + 16, (void**)&d_chunk)) != KQ_OK) return cleanup(st);
         if ((st = kq_dev_alloc(ctx, (size_t)(nblocks + 1) * 4, (void**)&d_r)) != KQ_OK) return cleanup(st);
         if ((st = kq_dev_alloc(ctx, (size_t)(ntiles + 4) * 8, (void**)&d_scratch)) != KQ_OK) return cleanup(st);
         const unsigned long long items = (unsigned long long)nblocks;
@@ -377,15 +539,19 @@ static int csv_scan_resident(kq_ctx* ctx, const uint8_t* d_text, long long n, Cs
             cudaMemcpyAsync(d_scratch + 2, &count, 8, cudaMemcpyHostToDevice, ctx->stream);
         };
         const int sg = (int)std::max<long long>(1, std::min<long long>((nblocks + SCAN_TILE - 1) / SCAN_TILE, (long long)ctx->sm_count * 4));
-        // 1. quotes before every block
-        scan_begin(items);
-        k_exclusive_offsets<QuoteCount><<<sg, 256, 0, ctx->stream>>>(QuoteCount{d_text, n}, d_scratch + 2, d_q, d_scratch + 4, (unsigned int*)d_scratch, d_scratch + 1);
-        if (cudaGetLastError() != cudaSuccess) return cleanup(kq_cuda_fail(ctx, cudaGetLastError(), "k_exclusive_offsets(quotes)"));
-        ctx->launches++;
+        // 1. the quote state in front of every block (rule C2): block transitions, composed per chunk, chained, expanded
+        const int gq = (int)std::max<long long>(1, std::min<long long>((nblocks + 255) / 256, (long long)ctx->sm_count * 8));
+        const int gc = (int)std::max<long long>(1, std::min<long long>((nchunks + 63) / 64, (long long)ctx->sm_count * 8));
+        k_csv_quote_maps<<<gq, 256, 0, ctx->stream>>>(d_text, n, nblocks, f, d_q);
+        k_csv_compose_chunks<<<gc, 64, 0, ctx->stream>>>(d_q, nblocks, nchunks, d_chunk);
+        k_csv_chunk_states<<<1, 32, 0, ctx->stream>>>(d_chunk, nchunks, d_scratch + 1);
+        k_csv_block_states<<<gc, 64, 0, ctx->stream>>>(d_q, nblocks, nchunks, d_chunk);
+        if (cudaGetLastError() != cudaSuccess) return cleanup(kq_cuda_fail(ctx, cudaGetLastError(), "k_csv_quote_maps .. k_csv_block_states"));
+        ctx->launches += 4;
         uint64_t total = 0;
         if (!partial) {
             if ((st = kq_read_u64(ctx, d_scratch + 1, 1, &total)) != KQ_OK) return cleanup(st);
-            if (total & 1) return cleanup(kq_fail(ctx, KQ_ERR_ILLEGAL_STATE, "CSV text ends inside a quoted field"));
+            if (total == Q_IN) return cleanup(kq_fail(ctx, KQ_ERR_ILLEGAL_STATE, "CSV text ends inside a quoted field"));
         }
         // 2. records and separators before every block
         scan_begin(items);

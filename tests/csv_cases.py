@@ -22,6 +22,12 @@ CASES = [
     ("utf8", "namn,ort\nPärsson,Åre\n日本,東京\n".encode("utf-8"), True, ["namn", "ort"], [["Pärsson", "日本"], ["Åre", "東京"]]),
     ("single_column", b"v\n1\n2\n3\n", True, ["v"], [["1", "2", "3"]]),
     ("blank_field_line", b"a\n \n1\n", True, ["a"], [["", "1"]]),
+    # rule C2: a quote opens a quoted section only as the first non-blank byte of a field; anywhere else it is data
+    ("stray_quote_is_data", b'a,b\n5" pipe,x\n6,y"z\n', True, ["a", "b"], [['5" pipe', "6"], ["x", 'y"z']]),
+    ("stray_quote_keeps_lines", b'a,b\nit"s,1\nnext,2\n"q,""r""\n",3\n', True, ["a", "b"], [['it"s', "next", 'q,"r"'], ["1", "2", "3"]]),
+    ("quote_after_closed_section", b'a,b\n"v" "w,2\n"x""",3\n', True, ["a", "b"], [["v", 'x"'], ["2", "3"]]),
+    ("quoted_after_blanks", b'a;b\n1;  "x;y"  \n\t"p""";2\n', True, ["a", "b"], [["1", 'p"'], ["x;y", "2"]]),
+    ("stray_quote_in_header", b'wi"dth,he"ight\n1,2\n', True, ['wi"dth', 'he"ight'], [["1"], ["2"]]),
 ]
 
 

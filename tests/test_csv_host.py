@@ -31,14 +31,17 @@ def _host_source():
     return out
 
 
-@pytest.fixture(scope="module")
-def H():
+@pytest.fixture(scope="module", params=[1024, 16], ids=["chunk1024", "chunk16"])
+def H(request):
+    """The host build; with 16 blocks per chunk (1 KiB of text) the chunk composition of the quote states, its vector
+    loads and its tails are exercised by texts of a few KiB."""
     os.makedirs(BUILD, exist_ok=True)
     gen = os.path.join(BUILD, "kq_csv_host.cpp")
     with open(gen, "w") as f:
         f.write(_host_source())
-    so = os.path.join(BUILD, "libkqcsv_host.so")
+    so = os.path.join(BUILD, f"libkqcsv_host_{request.param}.so")
     cmd = ["g++", "-std=c++17", "-O1", "-g", "-fPIC", "-shared", "-Wall", "-Wno-unused-function", "-Wno-unknown-pragmas", "-Wno-subobject-linkage",
+           f"-DKQ_CSV_CHUNK={request.param}",
            "-I", os.path.join(HERE, "host_shim"), "-I", CSRC, gen, os.path.join(HERE, "csv_host_harness.cpp"), "-o", so]
     r = subprocess.run(cmd, capture_output=True, text=True)
     assert r.returncode == 0, r.stderr[-4000:]
@@ -211,3 +214,74 @@ def test_reader_model_and_host_build_cut_the_same_pieces(H):
     text = synthetic(1500, seed=9, crlf=True)
     for piece in (256, 768, 2048):
         assert list(H.batches(text, True, piece=piece)) == list(dm.reader(text, True, piece))
+
+
+# ---------------------------------------------------------------- rule C2 under fire: quotes anywhere, not only where a CSV writer puts them
+from hypothesis import given, settings, strategies as st
+
+_RAW = st.text(st.sampled_from(list('ab1 ,,,;\t"""\n\n\r|é')), max_size=200)
+
+
+@settings(max_examples=600, deadline=None)
+@given(body=_RAW, hdr=st.booleans(), lead=st.sampled_from(["h1,h2,h3\n", "h1;h2\r\n", "", 'x"y,z\n', '"h,1",h2\n']))
+def test_raw_texts_with_stray_quotes_match_the_oracle(H, oracle, body, hdr, lead):
+    """Arbitrary bytes from a small alphabet rich in quotes, separators, blanks and line breaks — texts no CSV writer
+    would emit: quotes inside unquoted values, behind closed sections, doubled at block edges, unbalanced. The compiled
+    device code, the Python model of it and the oracle's character-at-a-time tokenizer agree on every one, error or not."""
+    import csv_device_model as dm
+    from oracle.oracle import OracleError
+    text = (lead + body).encode("utf-8")
+    try:
+        want = columns(oracle.csv_scan(text, hdr))
+    except OracleError as e:
+        assert "quoted" in str(e)
+        with pytest.raises(HostError, match="quoted"):
+            H.scan(text, hdr)
+        with pytest.raises(ValueError, match="quoted"):
+            dm.scan(text, hdr)
+        return
+    assert H.scan(text, hdr) == want
+    model = dm.scan(text, hdr)
+    assert model == want or (model == [] and all(c == [] for c in want))
+    nonempty = want and want[0]
+    for piece in (256, 512):
+        try:
+            got = list(H.batches(text, hdr, piece=piece))
+        except HostError as e:
+            assert "longer than the reader's piece" in str(e)
+            continue
+        assert concat(got, len(want)) == (want if nonempty else [[] for _ in want])
+    assert H.clean()
+
+
+@settings(max_examples=150, deadline=None)
+@given(parts=st.lists(st.tuples(st.integers(0, 130), st.sampled_from(['"', '""', '" "', ',"', '"\n', '\n"', ' " ', '"x"', ',', '\n'])), max_size=12))
+def test_quotes_at_every_block_offset(H, oracle, parts):
+    """Runs of filler with a quote pattern dropped at arbitrary distances, so that patterns meet the 64-byte block edges
+    (a doubled quote split over two blocks, an opener as a block's first byte behind blanks that end the block before)."""
+    from oracle.oracle import OracleError
+    text = "k,v\n" + "".join(("f" * (n % 7) + " " * (n // 7 % 5) + "," * (n % 2) + "g" * (n // 35)) + pat for n, pat in parts)
+    text = text.encode()
+    try:
+        want = columns(oracle.csv_scan(text, True))
+    except OracleError:
+        with pytest.raises(HostError, match="quoted"):
+            H.scan(text, True)
+        return
+    assert H.scan(text, True) == want
+    assert H.scan(text, True, device=True, misalign=7) == want
+
+
+def test_a_quoted_section_that_spans_many_blocks_and_chunks(H, oracle):
+    """A 9 KiB quoted value full of delimiters, line breaks and doubled quotes, records in front of it and behind it:
+    every block inside it is entered in the `inside` state, which only the composition of the blocks in front can tell."""
+    inner = 'l,""i""\n' * 1100
+    text = ('a,b\n' + '1,2\n' * 300 + '"' + inner + '",x\n' + '3,"4"\n' * 300 + 'it"s,"5\n6"\n').encode()
+    want = columns(oracle.csv_scan(text, True))
+    assert want[0][300] == inner.replace('""', '"').strip() and want[1][-1] == "5\n6" and want[0][-1] == 'it"s'
+    assert H.scan(text, True) == want
+    assert H.scan(text, True, device=True, misalign=9) == want
+    assert concat(list(H.batches(text, True, piece=16384)), 2) == want
+    with pytest.raises(HostError, match="longer than the reader's piece"):
+        list(H.batches(text, True, piece=4096))
+    assert H.clean()
