@@ -32,6 +32,7 @@
 // The file is also compiled for the HOST by the CPU test-suite (tests/test_csv_host.py, tests/host_shim/): keep the
 // kernels free of warp-level intrinsics so that they stay checkable against the oracle without a GPU.
 #include <algorithm>
+#include <cstdlib>
 #include <cstring>
 #include <string>
 #include <vector>
@@ -345,7 +346,8 @@ struct CsvCols {
     int16_t file_col[CSV_MAX_COLS];     // output column -> file column (materialised columns only; -1: shares another column's buffers)
     int32_t* lens[CSV_MAX_COLS];        // per output column: lengths, later Arrow offsets (device)
     uint8_t* data[CSV_MAX_COLS];
-    int nout;
+    int16_t mat[CSV_MAX_COLS];          // the materialised output columns, densely (k_csv_fields_split)
+    int nout, nmat;
 };
 
 // Raw bytes [a, b) of file column c of record `rec` (a missing field: a == b, rule C6)
@@ -369,6 +371,22 @@ __global__ void k_csv_fields(const uint8_t* __restrict__ text, const int32_t* __
             if (COPY) csv_value(text, a, b, cols->data[oc] + cols->lens[oc][r]);
             else cols->lens[oc][r] = csv_value(text, a, b, nullptr);
         }
+    }
+}
+// The same two passes with one thread per (record, materialised column): neighbouring threads read neighbouring fields of
+// the same record, so a warp's byte loads fall into a handful of sectors instead of one per lane, and a thread walks one
+// field instead of a whole record. Chosen with KQ_CSV_FIELDS=field (default: per record; DESIGN.md has the measurement).
+template <bool COPY>
+__global__ void k_csv_fields_split(const uint8_t* __restrict__ text, const int32_t* __restrict__ sep, const int32_t* __restrict__ rec_last, long long rows, int skip,
+                                   const CsvCols* __restrict__ cols) {
+    const long long nmat = cols->nmat, total = rows * nmat;
+    for (long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x; idx < total; idx += (long long)gridDim.x * blockDim.x) {
+        const long long r = idx / nmat;
+        const int oc = cols->mat[idx - r * nmat];
+        long long a, b;
+        csv_field(sep, rec_last, r + skip, cols->file_col[oc], a, b);
+        if (COPY) csv_value(text, a, b, cols->data[oc] + cols->lens[oc][r]);
+        else cols->lens[oc][r] = csv_value(text, a, b, nullptr);
     }
 }
 struct LenAt {
@@ -607,6 +625,7 @@ static int csv_scan_resident(kq_ctx* ctx, const uint8_t* d_text, long long n, Cs
     memset(&hc, 0, sizeof hc);
     for (int i = 0; i < CSV_MAX_COLS; i++) hc.file_col[i] = -1;
     hc.nout = nout;
+    hc.nmat = 0;
     std::vector<int32_t*> d_len((size_t)nout, nullptr);
     auto cleanup2 = [&](int s2) { for (int32_t* p : d_len) kq_dev_free(ctx, p); return cleanup(s2); };
     // a file column projected twice is materialised once and shared (ColumnExpression aliasing, rule R4)
@@ -615,13 +634,17 @@ static int csv_scan_resident(kq_ctx* ctx, const uint8_t* d_text, long long n, Cs
         if (first_out[(size_t)proj[(size_t)c]] >= 0) continue;
         first_out[(size_t)proj[(size_t)c]] = c;
         hc.file_col[c] = (int16_t)proj[(size_t)c];
+        hc.mat[hc.nmat++] = (int16_t)c;
         if ((st = kq_dev_alloc(ctx, (size_t)(rows + 1) * 4, (void**)&d_len[(size_t)c])) != KQ_OK) return cleanup2(st);
         hc.lens[c] = d_len[(size_t)c];
     }
     if ((st = kq_dev_alloc(ctx, sizeof hc, (void**)&d_cols)) != KQ_OK) return cleanup2(st);
     cudaMemcpyAsync(d_cols, &hc, sizeof hc, cudaMemcpyHostToDevice, ctx->stream);
     const int gr = (int)std::max<long long>(1, std::min<long long>((rows + 127) / 128, (long long)ctx->sm_count * 16));
-    k_csv_fields<false><<<gr, 128, 0, ctx->stream>>>(d_text, d_sep, d_last, nrec, skip, d_cols);
+    static const bool by_field = [] { const char* e = getenv("KQ_CSV_FIELDS"); return e && !strcmp(e, "field"); }();
+    const int gf = (int)std::max<long long>(1, std::min<long long>((rows * hc.nmat + 127) / 128, (long long)ctx->sm_count * 16));
+    if (by_field) k_csv_fields_split<false><<<gf, 128, 0, ctx->stream>>>(d_text, d_sep, d_last, rows, skip, d_cols);
+    else k_csv_fields<false><<<gr, 128, 0, ctx->stream>>>(d_text, d_sep, d_last, nrec, skip, d_cols);
     if (cudaGetLastError() != cudaSuccess) return cleanup2(kq_cuda_fail(ctx, cudaGetLastError(), "k_csv_fields(lengths)"));
     ctx->launches++;
     // 5. offsets per materialised column, then the data buffers
@@ -667,7 +690,8 @@ static int csv_scan_resident(kq_ctx* ctx, const uint8_t* d_text, long long n, Cs
     CsvCols* d_cols2 = nullptr;
     if ((st = kq_dev_alloc(ctx, sizeof hc, (void**)&d_cols2)) != KQ_OK) return cleanup3(st);
     cudaMemcpyAsync(d_cols2, &hc, sizeof hc, cudaMemcpyHostToDevice, ctx->stream);
-    k_csv_fields<true><<<gr, 128, 0, ctx->stream>>>(d_text, d_sep, d_last, nrec, skip, d_cols2);
+    if (by_field) k_csv_fields_split<true><<<gf, 128, 0, ctx->stream>>>(d_text, d_sep, d_last, rows, skip, d_cols2);
+    else k_csv_fields<true><<<gr, 128, 0, ctx->stream>>>(d_text, d_sep, d_last, nrec, skip, d_cols2);
     st = cudaGetLastError() != cudaSuccess ? kq_cuda_fail(ctx, cudaGetLastError(), "k_csv_fields(copy)") : KQ_OK;
     ctx->launches++;
     // hc lives on the host stack: the two pageable uploads above were staged synchronously by the runtime

@@ -31,17 +31,20 @@ def _host_source():
     return out
 
 
-@pytest.fixture(scope="module", params=[1024, 16], ids=["chunk1024", "chunk16"])
+@pytest.fixture(scope="module", params=[(1024, "record"), (16, "field"), (1024, "field")], ids=["chunk1024-record", "chunk16-field", "chunk1024-field"])
 def H(request):
     """The host build; with 16 blocks per chunk (1 KiB of text) the chunk composition of the quote states, its vector
-    loads and its tails are exercised by texts of a few KiB."""
+    loads and its tails are exercised by texts of a few KiB. KQ_CSV_FIELDS picks the field kernels (one thread per record
+    or per field); the library reads it once, at its first scan, so every variant gets its own copy of the library."""
+    chunk, fields = request.param
+    os.environ["KQ_CSV_FIELDS"] = fields
     os.makedirs(BUILD, exist_ok=True)
     gen = os.path.join(BUILD, "kq_csv_host.cpp")
     with open(gen, "w") as f:
         f.write(_host_source())
-    so = os.path.join(BUILD, f"libkqcsv_host_{request.param}.so")
+    so = os.path.join(BUILD, f"libkqcsv_host_{chunk}_{fields}.so")
     cmd = ["g++", "-std=c++17", "-O1", "-g", "-fPIC", "-shared", "-Wall", "-Wno-unused-function", "-Wno-unknown-pragmas", "-Wno-subobject-linkage",
-           f"-DKQ_CSV_CHUNK={request.param}",
+           f"-DKQ_CSV_CHUNK={chunk}",
            "-I", os.path.join(HERE, "host_shim"), "-I", CSRC, gen, os.path.join(HERE, "csv_host_harness.cpp"), "-o", so]
     r = subprocess.run(cmd, capture_output=True, text=True)
     assert r.returncode == 0, r.stderr[-4000:]
@@ -66,7 +69,10 @@ def H(request):
     L.kqh_col_bytes.argtypes = [P, C.c_int]
     L.kqh_col_read.argtypes = [P, C.c_int, P, P]
     L.kqh_live_blocks.restype = C.c_int64
-    return Host(L)
+    h = Host(L)
+    assert h.scan(b"a,b\n1,2\n") == [["1"], ["2"]]           # the first scan fixes the variant
+    os.environ.pop("KQ_CSV_FIELDS", None)
+    return h
 
 
 class HostError(Exception):
