@@ -264,7 +264,7 @@ __global__ void k_csv_block_states(uint8_t* __restrict__ qstate, long long nbloc
 // delimiters outside quotes. Quote state by prefix XOR over the quotes that switch it; a terminator ends an empty record
 // when the byte in front of it is a terminator too (or a CR behind a terminator), tested with shifted masks (carries: the
 // two bytes in front of the block; the start of the text counts as a terminator at position -1).
-struct BlockMasks { uint64_t rec, delim; };
+struct alignas(16) BlockMasks { uint64_t rec, delim; };
 __device__ __forceinline__ BlockMasks csv_block_masks(const uint8_t* __restrict__ text, long long n, long long i, const uint8_t* __restrict__ qstate, CsvFormat f) {
     const long long b = i * CSV_BLOCK;
     const RawMasks m = csv_raw_masks(text, n, i, f);
@@ -305,6 +305,35 @@ __global__ void k_csv_separators(const uint8_t* __restrict__ text, long long n, 
                                  const int32_t* __restrict__ recs_before, const int32_t* __restrict__ seps_before, int32_t* sep, int32_t* rec_last) {
     for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < nblocks; i += (long long)gridDim.x * blockDim.x) {
         const BlockMasks m = csv_block_masks(text, n, i, qstate, f);
+        uint64_t all = m.rec | m.delim;
+        int32_t k = seps_before[i], r = recs_before[i];
+        while (all) {
+            const int j = __ffsll((long long)all) - 1;
+            sep[k] = (int32_t)(i * CSV_BLOCK + j);
+            if ((m.rec >> j) & 1ULL) rec_last[r++] = k;
+            k++;
+            all &= all - 1;
+        }
+    }
+}
+
+// The same three passes over masks computed ONCE and kept in HBM (16 bytes per 64-byte block) instead of being rebuilt from
+// the text by each of them. Chosen with KQ_CSV_MASKS=stored (default: recompute; DESIGN.md has the measurement).
+__global__ void k_csv_store_masks(const uint8_t* __restrict__ text, long long n, long long nblocks, const uint8_t* __restrict__ qstate, CsvFormat f, BlockMasks* __restrict__ masks) {
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < nblocks; i += (long long)gridDim.x * blockDim.x) masks[i] = csv_block_masks(text, n, i, qstate, f);
+}
+struct StoredRecordCount {
+    const BlockMasks* masks;
+    __device__ __forceinline__ int operator()(long long i) const { return __popcll(masks[i].rec); }
+};
+struct StoredSeparatorCount {
+    const BlockMasks* masks;
+    __device__ __forceinline__ int operator()(long long i) const { const BlockMasks m = masks[i]; return __popcll(m.rec | m.delim); }
+};
+__global__ void k_csv_separators_stored(const BlockMasks* __restrict__ masks, long long nblocks, const int32_t* __restrict__ recs_before, const int32_t* __restrict__ seps_before,
+                                        int32_t* sep, int32_t* rec_last) {
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < nblocks; i += (long long)gridDim.x * blockDim.x) {
+        const BlockMasks m = masks[i];
         uint64_t all = m.rec | m.delim;
         int32_t k = seps_before[i], r = recs_before[i];
         while (all) {
@@ -522,7 +551,9 @@ static int csv_scan_resident(kq_ctx* ctx, const uint8_t* d_text, long long n, Cs
                              bool partial, kq_batch** out, int64_t* consumed) {
     const int nout = (int)proj.size();
     const long long nblocks = (n + CSV_BLOCK - 1) / CSV_BLOCK;
+    static const bool stored_masks = [] { const char* e = getenv("KQ_CSV_MASKS"); return e && !strcmp(e, "stored"); }();
     uint8_t *d_q = nullptr, *d_chunk = nullptr;     // per block: quote transition, then the quote state in front of it; per chunk likewise
+    BlockMasks* d_masks = nullptr;                  // per block: record-end and delimiter bits (KQ_CSV_MASKS=stored)
     int32_t* d_r = nullptr;
     unsigned long long* d_scratch = nullptr;        // [0] ticket, [1] total, [2] item count, [4..] tile descriptors
     int32_t *d_s = nullptr, *d_sep = nullptr, *d_last = nullptr;
@@ -532,7 +563,7 @@ static int csv_scan_resident(kq_ctx* ctx, const uint8_t* d_text, long long n, Cs
     // least two bytes, so nblocks * 32 bounds the record count)
     const long long ntiles = (std::max<long long>(nblocks, 1) * (CSV_BLOCK / 2) + SCAN_TILE - 1) / SCAN_TILE + 2;
     auto cleanup = [&](int st) {
-        kq_dev_free(ctx, d_q); kq_dev_free(ctx, d_chunk); kq_dev_free(ctx, d_r); kq_dev_free(ctx, d_scratch); kq_dev_free(ctx, d_s); kq_dev_free(ctx, d_sep); kq_dev_free(ctx, d_last); kq_dev_free(ctx, d_cols);
+        kq_dev_free(ctx, d_q); kq_dev_free(ctx, d_chunk); kq_dev_free(ctx, d_masks); kq_dev_free(ctx, d_r); kq_dev_free(ctx, d_scratch); kq_dev_free(ctx, d_s); kq_dev_free(ctx, d_sep); kq_dev_free(ctx, d_last); kq_dev_free(ctx, d_cols);
         if (st != KQ_OK) for (kq_col* c : cols) kq_column_free(c);
         return st;
     };
@@ -572,8 +603,15 @@ static int csv_scan_resident(kq_ctx* ctx, const uint8_t* d_text, long long n, Cs
             if (total == Q_IN) return cleanup(kq_fail(ctx, KQ_ERR_ILLEGAL_STATE, "CSV text ends inside a quoted field"));
         }
         // 2. records and separators before every block
+        if (stored_masks) {
+            if ((st = kq_dev_alloc(ctx, (size_t)nblocks * sizeof(BlockMasks), (void**)&d_masks)) != KQ_OK) return cleanup(st);
+            k_csv_store_masks<<<gq, 256, 0, ctx->stream>>>(d_text, n, nblocks, d_q, f, d_masks);
+            ctx->launches++;
+        }
         scan_begin(items);
-        k_exclusive_offsets<RecordCount><<<sg, 256, 0, ctx->stream>>>(RecordCount{d_text, n, d_q, f}, d_scratch + 2, d_r, d_scratch + 4,
+        if (stored_masks) k_exclusive_offsets<StoredRecordCount><<<sg, 256, 0, ctx->stream>>>(StoredRecordCount{d_masks}, d_scratch + 2, d_r, d_scratch + 4,
+                                                                                           (unsigned int*)d_scratch, d_scratch + 1);
+        else k_exclusive_offsets<RecordCount><<<sg, 256, 0, ctx->stream>>>(RecordCount{d_text, n, d_q, f}, d_scratch + 2, d_r, d_scratch + 4,
                                                                        (unsigned int*)d_scratch, d_scratch + 1);
         if (cudaGetLastError() != cudaSuccess) return cleanup(kq_cuda_fail(ctx, cudaGetLastError(), "k_exclusive_offsets(records)"));
         ctx->launches++;
@@ -582,7 +620,9 @@ static int csv_scan_resident(kq_ctx* ctx, const uint8_t* d_text, long long n, Cs
         if (partial && nrec == 0) return cleanup(kq_fail(ctx, KQ_ERR_UNSUPPORTED, "CSV record longer than the reader's piece (%lld bytes): open the reader with larger pieces", n));
         if ((st = kq_dev_alloc(ctx, (size_t)(nblocks + 1) * 4, (void**)&d_s)) != KQ_OK) return cleanup(st);
         scan_begin(items);
-        k_exclusive_offsets<SeparatorCount><<<sg, 256, 0, ctx->stream>>>(SeparatorCount{d_text, n, d_q, f}, d_scratch + 2, d_s, d_scratch + 4,
+        if (stored_masks) k_exclusive_offsets<StoredSeparatorCount><<<sg, 256, 0, ctx->stream>>>(StoredSeparatorCount{d_masks}, d_scratch + 2, d_s, d_scratch + 4,
+                                                                                              (unsigned int*)d_scratch, d_scratch + 1);
+        else k_exclusive_offsets<SeparatorCount><<<sg, 256, 0, ctx->stream>>>(SeparatorCount{d_text, n, d_q, f}, d_scratch + 2, d_s, d_scratch + 4,
                                                                           (unsigned int*)d_scratch, d_scratch + 1);
         if (cudaGetLastError() != cudaSuccess) return cleanup(kq_cuda_fail(ctx, cudaGetLastError(), "k_exclusive_offsets(separators)"));
         ctx->launches++;
@@ -596,7 +636,8 @@ static int csv_scan_resident(kq_ctx* ctx, const uint8_t* d_text, long long n, Cs
         if ((st = kq_dev_alloc(ctx, (size_t)nsep * 4 + 16, (void**)&d_sep)) != KQ_OK) return cleanup(st);
         if ((st = kq_dev_alloc(ctx, (size_t)nrec * 4 + 16, (void**)&d_last)) != KQ_OK) return cleanup(st);
         const int g = (int)std::max<long long>(1, std::min<long long>((nblocks + 255) / 256, (long long)ctx->sm_count * 8));
-        k_csv_separators<<<g, 256, 0, ctx->stream>>>(d_text, n, nblocks, d_q, f, d_r, d_s, d_sep, d_last);
+        if (stored_masks) k_csv_separators_stored<<<g, 256, 0, ctx->stream>>>(d_masks, nblocks, d_r, d_s, d_sep, d_last);
+        else k_csv_separators<<<g, 256, 0, ctx->stream>>>(d_text, n, nblocks, d_q, f, d_r, d_s, d_sep, d_last);
         if (cudaGetLastError() != cudaSuccess) return cleanup(kq_cuda_fail(ctx, cudaGetLastError(), "k_csv_separators"));
         ctx->launches++;
         if (partial) {       // where the last complete record ends: separator rec_last[nrec - 1] (delimiters of the unfinished tail follow it)

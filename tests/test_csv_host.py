@@ -31,18 +31,19 @@ def _host_source():
     return out
 
 
-@pytest.fixture(scope="module", params=[(1024, "record"), (16, "field"), (1024, "field")], ids=["chunk1024-record", "chunk16-field", "chunk1024-field"])
+@pytest.fixture(scope="module", params=[(1024, "record", "recompute"), (16, "field", "stored"), (1024, "field", "recompute"), (1024, "record", "stored")],
+                ids=["chunk1024-record-recompute", "chunk16-field-stored", "chunk1024-field-recompute", "chunk1024-record-stored"])
 def H(request):
     """The host build; with 16 blocks per chunk (1 KiB of text) the chunk composition of the quote states, its vector
     loads and its tails are exercised by texts of a few KiB. KQ_CSV_FIELDS picks the field kernels (one thread per record
-    or per field); the library reads it once, at its first scan, so every variant gets its own copy of the library."""
-    chunk, fields = request.param
-    os.environ["KQ_CSV_FIELDS"] = fields
+    or per field) and KQ_CSV_MASKS whether passes 2-3 rebuild the block masks or read stored ones; the library reads them once, at its first scan, so every variant gets its own copy of the library."""
+    chunk, fields, masks = request.param
+    os.environ["KQ_CSV_FIELDS"], os.environ["KQ_CSV_MASKS"] = fields, masks
     os.makedirs(BUILD, exist_ok=True)
     gen = os.path.join(BUILD, "kq_csv_host.cpp")
     with open(gen, "w") as f:
         f.write(_host_source())
-    so = os.path.join(BUILD, f"libkqcsv_host_{chunk}_{fields}.so")
+    so = os.path.join(BUILD, f"libkqcsv_host_{chunk}_{fields}_{masks}.so")
     cmd = ["g++", "-std=c++17", "-O1", "-g", "-fPIC", "-shared", "-Wall", "-Wno-unused-function", "-Wno-unknown-pragmas", "-Wno-subobject-linkage",
            f"-DKQ_CSV_CHUNK={chunk}",
            "-I", os.path.join(HERE, "host_shim"), "-I", CSRC, gen, os.path.join(HERE, "csv_host_harness.cpp"), "-o", so]
@@ -72,6 +73,7 @@ def H(request):
     h = Host(L)
     assert h.scan(b"a,b\n1,2\n") == [["1"], ["2"]]           # the first scan fixes the variant
     os.environ.pop("KQ_CSV_FIELDS", None)
+    os.environ.pop("KQ_CSV_MASKS", None)
     return h
 
 
