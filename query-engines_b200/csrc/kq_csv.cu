@@ -171,6 +171,26 @@ __device__ __forceinline__ uint32_t csv_quote_walk(int nbytes, uint64_t q, uint6
     if (sq) *sq = toggles;
     return s;
 }
+// The block's transition: csv_quote_walk for the three states in front of it at once (one pass over the quotes)
+__device__ __forceinline__ uint32_t csv_quote_map(int nbytes, uint64_t q, uint64_t cand) {
+    uint32_t s[3] = {Q_OUT, Q_IN, Q_OUTE};
+    int prev = -1;
+    while (q) {
+        const int j = __ffsll((long long)q) - 1;
+        q &= q - 1;
+        const bool adjacent = j == prev + 1, opener = (cand >> j) & 1ULL;
+#pragma unroll
+        for (int k = 0; k < 3; k++) {
+            uint32_t x = s[k];
+            if (x == Q_OUTE && !adjacent) x = Q_OUT;
+            s[k] = x == Q_IN ? Q_OUTE : (x == Q_OUTE || opener) ? Q_IN : Q_OUT;
+        }
+        prev = j;
+    }
+#pragma unroll
+    for (int k = 0; k < 3; k++) if (s[k] == Q_OUTE && prev != nbytes - 1) s[k] = Q_OUT;
+    return s[0] | (s[1] << 2) | (s[2] << 4);
+}
 // transitions are three 2-bit states packed into a byte: bits [2s, 2s+1] = the state behind the block when s is in front
 __device__ __forceinline__ uint32_t qmap_apply(uint32_t map, uint32_t s) { return (map >> (2 * s)) & 3u; }
 __device__ __forceinline__ uint32_t qmap_then(uint32_t first, uint32_t second) {
@@ -178,18 +198,37 @@ __device__ __forceinline__ uint32_t qmap_then(uint32_t first, uint32_t second) {
 }
 constexpr uint32_t QMAP_ID = Q_OUT | (Q_IN << 2) | (Q_OUTE << 4);
 
-// pass 1a: every block's transition
-__global__ void k_csv_quote_maps(const uint8_t* __restrict__ text, long long n, long long nblocks, CsvFormat f, uint8_t* __restrict__ qstate) {
-    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < nblocks; i += (long long)gridDim.x * blockDim.x) {
-        uint32_t map = Q_OUT | (Q_IN << 2) | (Q_OUT << 4);            // no quote in the block
-        if (csv_has_quote(text, n, i)) {
-            const RawMasks m = csv_raw_masks(text, n, i, f);
-            const uint64_t cand = csv_opener_candidates(text, n, i, m, f);
-            map = csv_quote_walk(m.nbytes, m.q, cand, Q_OUT, nullptr) | (csv_quote_walk(m.nbytes, m.q, cand, Q_IN, nullptr) << 2) |
-                  (csv_quote_walk(m.nbytes, m.q, cand, Q_OUTE, nullptr) << 4);
+// Passes over all blocks whose rare blocks (those that hold a quote) need much more work than the rest: a thread first does
+// the cheap part of `batch` blocks, remembering which of them need the rest, then the expensive parts one after another —
+// the lanes of a warp then work on their few expensive blocks together instead of each making the other 31 wait at every block.
+template <class Light, class Heavy>
+__device__ __forceinline__ void csv_for_blocks(long long nblocks, int batch, Light light, Heavy heavy) {
+    const long long stride = (long long)gridDim.x * blockDim.x;
+    for (long long i0 = blockIdx.x * (long long)blockDim.x + threadIdx.x; i0 < nblocks; i0 += stride * batch) {
+        uint32_t todo = 0;
+        for (int k = 0; k < batch; k++) {
+            const long long i = i0 + k * stride;
+            if (i < nblocks && light(i)) todo |= 1u << k;
         }
-        qstate[i] = (uint8_t)map;
+        while (todo) {
+            const int k = __ffs((int)todo) - 1;
+            todo &= todo - 1;
+            heavy(i0 + k * stride);
+        }
     }
+}
+// pass 1a: every block's transition
+__global__ void k_csv_quote_maps(const uint8_t* __restrict__ text, long long n, long long nblocks, CsvFormat f, int batch, uint8_t* __restrict__ qstate) {
+    csv_for_blocks(nblocks, batch,
+        [&](long long i) {
+            if (csv_has_quote(text, n, i)) return true;
+            qstate[i] = (uint8_t)(Q_OUT | (Q_IN << 2) | (Q_OUT << 4));            // no quote in the block
+            return false;
+        },
+        [&](long long i) {
+            const RawMasks m = csv_raw_masks(text, n, i, f);
+            qstate[i] = (uint8_t)csv_quote_map(m.nbytes, m.q, csv_opener_candidates(text, n, i, m, f));
+        });
 }
 // pass 1b: one transition per chunk of CSV_CHUNK blocks (16 transitions per load; chunks start 16-byte aligned)
 __global__ void k_csv_compose_chunks(const uint8_t* __restrict__ qstate, long long nblocks, long long nchunks, uint8_t* __restrict__ chunk_map) {
@@ -265,17 +304,7 @@ __global__ void k_csv_block_states(uint8_t* __restrict__ qstate, long long nbloc
 // when the byte in front of it is a terminator too (or a CR behind a terminator), tested with shifted masks (carries: the
 // two bytes in front of the block; the start of the text counts as a terminator at position -1).
 struct alignas(16) BlockMasks { uint64_t rec, delim; };
-__device__ __forceinline__ BlockMasks csv_block_masks(const uint8_t* __restrict__ text, long long n, long long i, const uint8_t* __restrict__ qstate, CsvFormat f) {
-    const long long b = i * CSV_BLOCK;
-    const RawMasks m = csv_raw_masks(text, n, i, f);
-    const uint32_t s = qstate[i];
-    uint64_t inside = 0;
-    if (m.q || s == Q_IN) {
-        uint64_t x = 0;
-        if (m.q) csv_quote_walk(m.nbytes, m.q, csv_opener_candidates(text, n, i, m, f), s, &x);
-        x ^= x << 1; x ^= x << 2; x ^= x << 4; x ^= x << 8; x ^= x << 16; x ^= x << 32;
-        inside = s == Q_IN ? ~x : x;                                          // in-quote state at every non-quote byte
-    }
+__device__ __forceinline__ BlockMasks csv_block_masks(const uint8_t* __restrict__ text, long long b, const RawMasks m, uint64_t inside, CsvFormat f) {
     const bool t1 = b == 0 || text[b - 1] == f.term, t2 = b <= 1 || text[b - 2] == f.term;
     uint64_t empty = (m.t << 1) | (uint64_t)t1;
     if (f.term == '\n') {
@@ -288,49 +317,37 @@ __device__ __forceinline__ BlockMasks csv_block_masks(const uint8_t* __restrict_
     r.delim = m.d & ~inside;
     return r;
 }
+// pass 2a: the masks of every block, computed once and kept in HBM (16 bytes per 64-byte block) for the two scans and the
+// separator pass (rebuilding them from the text in each of the three was 13 % slower)
+__global__ void k_csv_store_masks(const uint8_t* __restrict__ text, long long n, long long nblocks, const uint8_t* __restrict__ qstate, CsvFormat f, int batch,
+                                  BlockMasks* __restrict__ masks) {
+    csv_for_blocks(nblocks, batch,
+        [&](long long i) {
+            const RawMasks m = csv_raw_masks(text, n, i, f);
+            if (m.q) return true;
+            masks[i] = csv_block_masks(text, i * CSV_BLOCK, m, qstate[i] == Q_IN ? ~0ULL : 0ULL, f);      // no quote: the whole block is inside or outside
+            return false;
+        },
+        [&](long long i) {
+            const RawMasks m = csv_raw_masks(text, n, i, f);
+            const uint32_t s = qstate[i];
+            uint64_t x = 0;
+            csv_quote_walk(m.nbytes, m.q, csv_opener_candidates(text, n, i, m, f), s, &x);
+            x ^= x << 1; x ^= x << 2; x ^= x << 4; x ^= x << 8; x ^= x << 16; x ^= x << 32;       // prefix XOR over the quotes that switch the state
+            masks[i] = csv_block_masks(text, i * CSV_BLOCK, m, s == Q_IN ? ~x : x, f);             // in-quote state at every non-quote byte
+        });
+}
 struct RecordCount {          // records ending in block i
-    const uint8_t* text; long long n; const uint8_t* qstate; CsvFormat f;
-    __device__ __forceinline__ int operator()(long long i) const { return __popcll(csv_block_masks(text, n, i, qstate, f).rec); }
-};
-struct SeparatorCount {       // field separators in block i: delimiters + record ends
-    const uint8_t* text; long long n; const uint8_t* qstate; CsvFormat f;
-    __device__ __forceinline__ int operator()(long long i) const {
-        const BlockMasks m = csv_block_masks(text, n, i, qstate, f);
-        return __popcll(m.rec | m.delim);
-    }
-};
-// pass 3: the position of every separator, in text order, and for every record the index of its LAST separator (its end):
-// field c of record r is the text between separators rec_last[r-1] + c and rec_last[r-1] + c + 1.
-__global__ void k_csv_separators(const uint8_t* __restrict__ text, long long n, long long nblocks, const uint8_t* __restrict__ qstate, CsvFormat f,
-                                 const int32_t* __restrict__ recs_before, const int32_t* __restrict__ seps_before, int32_t* sep, int32_t* rec_last) {
-    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < nblocks; i += (long long)gridDim.x * blockDim.x) {
-        const BlockMasks m = csv_block_masks(text, n, i, qstate, f);
-        uint64_t all = m.rec | m.delim;
-        int32_t k = seps_before[i], r = recs_before[i];
-        while (all) {
-            const int j = __ffsll((long long)all) - 1;
-            sep[k] = (int32_t)(i * CSV_BLOCK + j);
-            if ((m.rec >> j) & 1ULL) rec_last[r++] = k;
-            k++;
-            all &= all - 1;
-        }
-    }
-}
-
-// The same three passes over masks computed ONCE and kept in HBM (16 bytes per 64-byte block) instead of being rebuilt from
-// the text by each of them. Chosen with KQ_CSV_MASKS=stored (default: recompute; DESIGN.md has the measurement).
-__global__ void k_csv_store_masks(const uint8_t* __restrict__ text, long long n, long long nblocks, const uint8_t* __restrict__ qstate, CsvFormat f, BlockMasks* __restrict__ masks) {
-    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < nblocks; i += (long long)gridDim.x * blockDim.x) masks[i] = csv_block_masks(text, n, i, qstate, f);
-}
-struct StoredRecordCount {
     const BlockMasks* masks;
     __device__ __forceinline__ int operator()(long long i) const { return __popcll(masks[i].rec); }
 };
-struct StoredSeparatorCount {
+struct SeparatorCount {       // field separators in block i: delimiters + record ends
     const BlockMasks* masks;
     __device__ __forceinline__ int operator()(long long i) const { const BlockMasks m = masks[i]; return __popcll(m.rec | m.delim); }
 };
-__global__ void k_csv_separators_stored(const BlockMasks* __restrict__ masks, long long nblocks, const int32_t* __restrict__ recs_before, const int32_t* __restrict__ seps_before,
+// pass 3: the position of every separator, in text order, and for every record the index of its LAST separator (its end):
+// field c of record r is the text between separators rec_last[r-1] + c and rec_last[r-1] + c + 1.
+__global__ void k_csv_separators(const BlockMasks* __restrict__ masks, long long nblocks, const int32_t* __restrict__ recs_before, const int32_t* __restrict__ seps_before,
                                         int32_t* sep, int32_t* rec_last) {
     for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < nblocks; i += (long long)gridDim.x * blockDim.x) {
         const BlockMasks m = masks[i];
@@ -375,8 +392,7 @@ struct CsvCols {
     int16_t file_col[CSV_MAX_COLS];     // output column -> file column (materialised columns only; -1: shares another column's buffers)
     int32_t* lens[CSV_MAX_COLS];        // per output column: lengths, later Arrow offsets (device)
     uint8_t* data[CSV_MAX_COLS];
-    int16_t mat[CSV_MAX_COLS];          // the materialised output columns, densely (k_csv_fields_split)
-    int nout, nmat;
+    int nout;
 };
 
 // Raw bytes [a, b) of file column c of record `rec` (a missing field: a == b, rule C6)
@@ -400,22 +416,6 @@ __global__ void k_csv_fields(const uint8_t* __restrict__ text, const int32_t* __
             if (COPY) csv_value(text, a, b, cols->data[oc] + cols->lens[oc][r]);
             else cols->lens[oc][r] = csv_value(text, a, b, nullptr);
         }
-    }
-}
-// The same two passes with one thread per (record, materialised column): neighbouring threads read neighbouring fields of
-// the same record, so a warp's byte loads fall into a handful of sectors instead of one per lane, and a thread walks one
-// field instead of a whole record. Chosen with KQ_CSV_FIELDS=field (default: per record; DESIGN.md has the measurement).
-template <bool COPY>
-__global__ void k_csv_fields_split(const uint8_t* __restrict__ text, const int32_t* __restrict__ sep, const int32_t* __restrict__ rec_last, long long rows, int skip,
-                                   const CsvCols* __restrict__ cols) {
-    const long long nmat = cols->nmat, total = rows * nmat;
-    for (long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x; idx < total; idx += (long long)gridDim.x * blockDim.x) {
-        const long long r = idx / nmat;
-        const int oc = cols->mat[idx - r * nmat];
-        long long a, b;
-        csv_field(sep, rec_last, r + skip, cols->file_col[oc], a, b);
-        if (COPY) csv_value(text, a, b, cols->data[oc] + cols->lens[oc][r]);
-        else cols->lens[oc][r] = csv_value(text, a, b, nullptr);
     }
 }
 struct LenAt {
@@ -551,9 +551,9 @@ static int csv_scan_resident(kq_ctx* ctx, const uint8_t* d_text, long long n, Cs
                              bool partial, kq_batch** out, int64_t* consumed) {
     const int nout = (int)proj.size();
     const long long nblocks = (n + CSV_BLOCK - 1) / CSV_BLOCK;
-    static const bool stored_masks = [] { const char* e = getenv("KQ_CSV_MASKS"); return e && !strcmp(e, "stored"); }();
+    static const int batch = [] { const char* e = getenv("KQ_CSV_BATCH"); const int b = e ? atoi(e) : 16; return b < 1 ? 1 : b > 32 ? 32 : b; }();
     uint8_t *d_q = nullptr, *d_chunk = nullptr;     // per block: quote transition, then the quote state in front of it; per chunk likewise
-    BlockMasks* d_masks = nullptr;                  // per block: record-end and delimiter bits (KQ_CSV_MASKS=stored)
+    BlockMasks* d_masks = nullptr;                  // per block: record-end and delimiter bits
     int32_t* d_r = nullptr;
     unsigned long long* d_scratch = nullptr;        // [0] ticket, [1] total, [2] item count, [4..] tile descriptors
     int32_t *d_s = nullptr, *d_sep = nullptr, *d_last = nullptr;
@@ -591,7 +591,7 @@ static int csv_scan_resident(kq_ctx* ctx, const uint8_t* d_text, long long n, Cs
         // 1. the quote state in front of every block (rule C2): block transitions, composed per chunk, chained, expanded
         const int gq = (int)std::max<long long>(1, std::min<long long>((nblocks + 255) / 256, (long long)ctx->sm_count * 8));
         const int gc = (int)std::max<long long>(1, std::min<long long>((nchunks + 63) / 64, (long long)ctx->sm_count * 8));
-        k_csv_quote_maps<<<gq, 256, 0, ctx->stream>>>(d_text, n, nblocks, f, d_q);
+        k_csv_quote_maps<<<gq, 256, 0, ctx->stream>>>(d_text, n, nblocks, f, batch, d_q);
         k_csv_compose_chunks<<<gc, 64, 0, ctx->stream>>>(d_q, nblocks, nchunks, d_chunk);
         k_csv_chunk_states<<<1, 32, 0, ctx->stream>>>(d_chunk, nchunks, d_scratch + 1);
         k_csv_block_states<<<gc, 64, 0, ctx->stream>>>(d_q, nblocks, nchunks, d_chunk);
@@ -602,17 +602,12 @@ static int csv_scan_resident(kq_ctx* ctx, const uint8_t* d_text, long long n, Cs
             if ((st = kq_read_u64(ctx, d_scratch + 1, 1, &total)) != KQ_OK) return cleanup(st);
             if (total == Q_IN) return cleanup(kq_fail(ctx, KQ_ERR_ILLEGAL_STATE, "CSV text ends inside a quoted field"));
         }
-        // 2. records and separators before every block
-        if (stored_masks) {
-            if ((st = kq_dev_alloc(ctx, (size_t)nblocks * sizeof(BlockMasks), (void**)&d_masks)) != KQ_OK) return cleanup(st);
-            k_csv_store_masks<<<gq, 256, 0, ctx->stream>>>(d_text, n, nblocks, d_q, f, d_masks);
-            ctx->launches++;
-        }
+        // 2. the block masks, then records and separators before every block
+        if ((st = kq_dev_alloc(ctx, (size_t)nblocks * sizeof(BlockMasks), (void**)&d_masks)) != KQ_OK) return cleanup(st);
+        k_csv_store_masks<<<gq, 256, 0, ctx->stream>>>(d_text, n, nblocks, d_q, f, batch, d_masks);
+        ctx->launches++;
         scan_begin(items);
-        if (stored_masks) k_exclusive_offsets<StoredRecordCount><<<sg, 256, 0, ctx->stream>>>(StoredRecordCount{d_masks}, d_scratch + 2, d_r, d_scratch + 4,
-                                                                                           (unsigned int*)d_scratch, d_scratch + 1);
-        else k_exclusive_offsets<RecordCount><<<sg, 256, 0, ctx->stream>>>(RecordCount{d_text, n, d_q, f}, d_scratch + 2, d_r, d_scratch + 4,
-                                                                       (unsigned int*)d_scratch, d_scratch + 1);
+        k_exclusive_offsets<RecordCount><<<sg, 256, 0, ctx->stream>>>(RecordCount{d_masks}, d_scratch + 2, d_r, d_scratch + 4, (unsigned int*)d_scratch, d_scratch + 1);
         if (cudaGetLastError() != cudaSuccess) return cleanup(kq_cuda_fail(ctx, cudaGetLastError(), "k_exclusive_offsets(records)"));
         ctx->launches++;
         if ((st = kq_read_u64(ctx, d_scratch + 1, 1, &total)) != KQ_OK) return cleanup(st);
@@ -620,10 +615,7 @@ static int csv_scan_resident(kq_ctx* ctx, const uint8_t* d_text, long long n, Cs
         if (partial && nrec == 0) return cleanup(kq_fail(ctx, KQ_ERR_UNSUPPORTED, "CSV record longer than the reader's piece (%lld bytes): open the reader with larger pieces", n));
         if ((st = kq_dev_alloc(ctx, (size_t)(nblocks + 1) * 4, (void**)&d_s)) != KQ_OK) return cleanup(st);
         scan_begin(items);
-        if (stored_masks) k_exclusive_offsets<StoredSeparatorCount><<<sg, 256, 0, ctx->stream>>>(StoredSeparatorCount{d_masks}, d_scratch + 2, d_s, d_scratch + 4,
-                                                                                              (unsigned int*)d_scratch, d_scratch + 1);
-        else k_exclusive_offsets<SeparatorCount><<<sg, 256, 0, ctx->stream>>>(SeparatorCount{d_text, n, d_q, f}, d_scratch + 2, d_s, d_scratch + 4,
-                                                                          (unsigned int*)d_scratch, d_scratch + 1);
+        k_exclusive_offsets<SeparatorCount><<<sg, 256, 0, ctx->stream>>>(SeparatorCount{d_masks}, d_scratch + 2, d_s, d_scratch + 4, (unsigned int*)d_scratch, d_scratch + 1);
         if (cudaGetLastError() != cudaSuccess) return cleanup(kq_cuda_fail(ctx, cudaGetLastError(), "k_exclusive_offsets(separators)"));
         ctx->launches++;
         if ((st = kq_read_u64(ctx, d_scratch + 1, 1, &total)) != KQ_OK) return cleanup(st);
@@ -636,8 +628,7 @@ static int csv_scan_resident(kq_ctx* ctx, const uint8_t* d_text, long long n, Cs
         if ((st = kq_dev_alloc(ctx, (size_t)nsep * 4 + 16, (void**)&d_sep)) != KQ_OK) return cleanup(st);
         if ((st = kq_dev_alloc(ctx, (size_t)nrec * 4 + 16, (void**)&d_last)) != KQ_OK) return cleanup(st);
         const int g = (int)std::max<long long>(1, std::min<long long>((nblocks + 255) / 256, (long long)ctx->sm_count * 8));
-        if (stored_masks) k_csv_separators_stored<<<g, 256, 0, ctx->stream>>>(d_masks, nblocks, d_r, d_s, d_sep, d_last);
-        else k_csv_separators<<<g, 256, 0, ctx->stream>>>(d_text, n, nblocks, d_q, f, d_r, d_s, d_sep, d_last);
+        k_csv_separators<<<g, 256, 0, ctx->stream>>>(d_masks, nblocks, d_r, d_s, d_sep, d_last);
         if (cudaGetLastError() != cudaSuccess) return cleanup(kq_cuda_fail(ctx, cudaGetLastError(), "k_csv_separators"));
         ctx->launches++;
         if (partial) {       // where the last complete record ends: separator rec_last[nrec - 1] (delimiters of the unfinished tail follow it)
@@ -666,7 +657,6 @@ static int csv_scan_resident(kq_ctx* ctx, const uint8_t* d_text, long long n, Cs
     memset(&hc, 0, sizeof hc);
     for (int i = 0; i < CSV_MAX_COLS; i++) hc.file_col[i] = -1;
     hc.nout = nout;
-    hc.nmat = 0;
     std::vector<int32_t*> d_len((size_t)nout, nullptr);
     auto cleanup2 = [&](int s2) { for (int32_t* p : d_len) kq_dev_free(ctx, p); return cleanup(s2); };
     // a file column projected twice is materialised once and shared (ColumnExpression aliasing, rule R4)
@@ -675,17 +665,13 @@ static int csv_scan_resident(kq_ctx* ctx, const uint8_t* d_text, long long n, Cs
         if (first_out[(size_t)proj[(size_t)c]] >= 0) continue;
         first_out[(size_t)proj[(size_t)c]] = c;
         hc.file_col[c] = (int16_t)proj[(size_t)c];
-        hc.mat[hc.nmat++] = (int16_t)c;
         if ((st = kq_dev_alloc(ctx, (size_t)(rows + 1) * 4, (void**)&d_len[(size_t)c])) != KQ_OK) return cleanup2(st);
         hc.lens[c] = d_len[(size_t)c];
     }
     if ((st = kq_dev_alloc(ctx, sizeof hc, (void**)&d_cols)) != KQ_OK) return cleanup2(st);
     cudaMemcpyAsync(d_cols, &hc, sizeof hc, cudaMemcpyHostToDevice, ctx->stream);
     const int gr = (int)std::max<long long>(1, std::min<long long>((rows + 127) / 128, (long long)ctx->sm_count * 16));
-    static const bool by_field = [] { const char* e = getenv("KQ_CSV_FIELDS"); return e && !strcmp(e, "field"); }();
-    const int gf = (int)std::max<long long>(1, std::min<long long>((rows * hc.nmat + 127) / 128, (long long)ctx->sm_count * 16));
-    if (by_field) k_csv_fields_split<false><<<gf, 128, 0, ctx->stream>>>(d_text, d_sep, d_last, rows, skip, d_cols);
-    else k_csv_fields<false><<<gr, 128, 0, ctx->stream>>>(d_text, d_sep, d_last, nrec, skip, d_cols);
+    k_csv_fields<false><<<gr, 128, 0, ctx->stream>>>(d_text, d_sep, d_last, nrec, skip, d_cols);
     if (cudaGetLastError() != cudaSuccess) return cleanup2(kq_cuda_fail(ctx, cudaGetLastError(), "k_csv_fields(lengths)"));
     ctx->launches++;
     // 5. offsets per materialised column, then the data buffers
@@ -731,8 +717,7 @@ static int csv_scan_resident(kq_ctx* ctx, const uint8_t* d_text, long long n, Cs
     CsvCols* d_cols2 = nullptr;
     if ((st = kq_dev_alloc(ctx, sizeof hc, (void**)&d_cols2)) != KQ_OK) return cleanup3(st);
     cudaMemcpyAsync(d_cols2, &hc, sizeof hc, cudaMemcpyHostToDevice, ctx->stream);
-    if (by_field) k_csv_fields_split<true><<<gf, 128, 0, ctx->stream>>>(d_text, d_sep, d_last, rows, skip, d_cols2);
-    else k_csv_fields<true><<<gr, 128, 0, ctx->stream>>>(d_text, d_sep, d_last, nrec, skip, d_cols2);
+    k_csv_fields<true><<<gr, 128, 0, ctx->stream>>>(d_text, d_sep, d_last, nrec, skip, d_cols2);
     st = cudaGetLastError() != cudaSuccess ? kq_cuda_fail(ctx, cudaGetLastError(), "k_csv_fields(copy)") : KQ_OK;
     ctx->launches++;
     // hc lives on the host stack: the two pageable uploads above were staged synchronously by the runtime

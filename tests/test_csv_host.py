@@ -31,19 +31,17 @@ def _host_source():
     return out
 
 
-@pytest.fixture(scope="module", params=[(1024, "record", "recompute"), (16, "field", "stored"), (1024, "field", "recompute"), (1024, "record", "stored")],
-                ids=["chunk1024-record-recompute", "chunk16-field-stored", "chunk1024-field-recompute", "chunk1024-record-stored"])
+@pytest.fixture(scope="module", params=[1024, 16], ids=["chunk1024", "chunk16"])
 def H(request):
     """The host build; with 16 blocks per chunk (1 KiB of text) the chunk composition of the quote states, its vector
-    loads and its tails are exercised by texts of a few KiB. KQ_CSV_FIELDS picks the field kernels (one thread per record
-    or per field) and KQ_CSV_MASKS whether passes 2-3 rebuild the block masks or read stored ones; the library reads them once, at its first scan, so every variant gets its own copy of the library."""
-    chunk, fields, masks = request.param
-    os.environ["KQ_CSV_FIELDS"], os.environ["KQ_CSV_MASKS"] = fields, masks
+    loads and its tails are exercised by texts of a few KiB."""
+    chunk = request.param
+    os.environ["KQ_CSV_BATCH"] = "1" if chunk == 16 else "16"      # read once per library, at its first scan
     os.makedirs(BUILD, exist_ok=True)
     gen = os.path.join(BUILD, "kq_csv_host.cpp")
     with open(gen, "w") as f:
         f.write(_host_source())
-    so = os.path.join(BUILD, f"libkqcsv_host_{chunk}_{fields}_{masks}.so")
+    so = os.path.join(BUILD, f"libkqcsv_host_{chunk}.so")
     cmd = ["g++", "-std=c++17", "-O1", "-g", "-fPIC", "-shared", "-Wall", "-Wno-unused-function", "-Wno-unknown-pragmas", "-Wno-subobject-linkage",
            f"-DKQ_CSV_CHUNK={chunk}",
            "-I", os.path.join(HERE, "host_shim"), "-I", CSRC, gen, os.path.join(HERE, "csv_host_harness.cpp"), "-o", so]
@@ -71,9 +69,8 @@ def H(request):
     L.kqh_col_read.argtypes = [P, C.c_int, P, P]
     L.kqh_live_blocks.restype = C.c_int64
     h = Host(L)
-    assert h.scan(b"a,b\n1,2\n") == [["1"], ["2"]]           # the first scan fixes the variant
-    os.environ.pop("KQ_CSV_FIELDS", None)
-    os.environ.pop("KQ_CSV_MASKS", None)
+    assert h.scan(b"a,b\n1,2\n") == [["1"], ["2"]]
+    os.environ.pop("KQ_CSV_BATCH", None)
     return h
 
 
