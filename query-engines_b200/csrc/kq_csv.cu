@@ -248,24 +248,32 @@ __global__ void k_csv_compose_chunks(const uint8_t* __restrict__ qstate, long lo
         chunk_map[k] = (uint8_t)map;
     }
 }
-// pass 1c (one thread): the state in front of every chunk (replaces the chunk's transition), and behind the text
-__global__ void k_csv_chunk_states(uint8_t* chunk_map, long long nchunks, unsigned long long* final_state) {
+// pass 1c (one thread): the state in front of every chunk, and behind the text. Separate input and output arrays: stores
+// into the array being read made every load of this dependent chain miss (110 us per 6000 chunks when done in place).
+__global__ void k_csv_chunk_states(const uint8_t* __restrict__ chunk_map, long long nchunks, uint8_t* __restrict__ chunk_state, unsigned long long* final_state) {
     if (blockIdx.x != 0 || threadIdx.x != 0) return;
     uint32_t s = Q_OUT;
     long long k = 0;
-    for (; k + 8 <= nchunks; k += 8) {
-        unsigned long long w = *reinterpret_cast<const unsigned long long*>(chunk_map + k), o = 0;
+#pragma unroll 4
+    for (; k + 16 <= nchunks; k += 16) {
+        const uint4 v = __ldg(reinterpret_cast<const uint4*>(chunk_map + k));
+        uint32_t w[4] = {v.x, v.y, v.z, v.w};
 #pragma unroll
-        for (int j = 0; j < 8; j++) {
-            o |= (unsigned long long)s << (8 * j);
-            s = qmap_apply((uint32_t)(w >> (8 * j)) & 0xFFu, s);
+        for (int t = 0; t < 4; t++) {
+            uint32_t o = 0;
+#pragma unroll
+            for (int j = 0; j < 4; j++) {
+                o |= s << (8 * j);
+                s = qmap_apply((w[t] >> (8 * j)) & 0xFFu, s);
+            }
+            w[t] = o;
         }
-        *reinterpret_cast<unsigned long long*>(chunk_map + k) = o;
+        uint4 r; r.x = w[0]; r.y = w[1]; r.z = w[2]; r.w = w[3];
+        *reinterpret_cast<uint4*>(chunk_state + k) = r;
     }
     for (; k < nchunks; k++) {
-        const uint32_t map = chunk_map[k];
-        chunk_map[k] = (uint8_t)s;
-        s = qmap_apply(map, s);
+        chunk_state[k] = (uint8_t)s;
+        s = qmap_apply(chunk_map[k], s);
     }
     *final_state = s;
 }
@@ -403,20 +411,28 @@ __device__ __forceinline__ void csv_field(const int32_t* __restrict__ sep, const
     a = k0 + c ? (long long)sep[k0 + c - 1] + 1 : 0;      // bytes of skipped empty lines in front of a record are blanks: trimmed with the value
     b = sep[k0 + c];
 }
-// pass 4: lengths of the projected fields of every data record; pass 6 (COPY): the bytes, at the offsets pass 5 produced
+// pass 4: lengths of the projected fields of every data record; pass 6 (COPY): the bytes, at the offsets pass 5 produced.
+// The column table travels as a kernel parameter (4.6 KB, read through the constant bank), not as a host-to-device copy.
 template <bool COPY>
 __global__ void k_csv_fields(const uint8_t* __restrict__ text, const int32_t* __restrict__ sep, const int32_t* __restrict__ rec_last, long long nrec, int skip,
-                             const CsvCols* __restrict__ cols) {
+                             const __grid_constant__ CsvCols cols) {
     for (long long r = blockIdx.x * (long long)blockDim.x + threadIdx.x; r + skip < nrec; r += (long long)gridDim.x * blockDim.x) {
-        for (int oc = 0; oc < cols->nout; oc++) {
-            const int c = cols->file_col[oc];
+        for (int oc = 0; oc < cols.nout; oc++) {
+            const int c = cols.file_col[oc];
             if (c < 0) continue;
             long long a, b;
             csv_field(sep, rec_last, r + skip, c, a, b);
-            if (COPY) csv_value(text, a, b, cols->data[oc] + cols->lens[oc][r]);
-            else cols->lens[oc][r] = csv_value(text, a, b, nullptr);
+            if (COPY) csv_value(text, a, b, cols.data[oc] + cols.lens[oc][r]);
+            else cols.lens[oc][r] = csv_value(text, a, b, nullptr);
         }
     }
+}
+// Start of a device-wide scan: ticket, total and tile descriptors cleared, the item count in word 2 — for `nscans` scans
+// whose scratch areas of `words` 64-bit words lie back to back. A kernel, not a memset plus a small host-to-device copy:
+// such copies queue on the copy engine behind the reader's upload of the next piece and would serialise scan and upload.
+__global__ void k_csv_scan_begin(unsigned long long* scratch, long long words, int nscans, unsigned long long count) {
+    const long long total = words * nscans;
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) scratch[i] = (i % words == 2) ? count : 0ULL;
 }
 struct LenAt {
     const int32_t* lens;
@@ -557,13 +573,12 @@ static int csv_scan_resident(kq_ctx* ctx, const uint8_t* d_text, long long n, Cs
     int32_t* d_r = nullptr;
     unsigned long long* d_scratch = nullptr;        // [0] ticket, [1] total, [2] item count, [4..] tile descriptors
     int32_t *d_s = nullptr, *d_sep = nullptr, *d_last = nullptr;
-    CsvCols* d_cols = nullptr;
     std::vector<kq_col*> cols;
     // tile descriptors of the device-wide scans: over 64-byte blocks (passes 1-2) and over records (pass 5; a record has at
     // least two bytes, so nblocks * 32 bounds the record count)
     const long long ntiles = (std::max<long long>(nblocks, 1) * (CSV_BLOCK / 2) + SCAN_TILE - 1) / SCAN_TILE + 2;
     auto cleanup = [&](int st) {
-        kq_dev_free(ctx, d_q); kq_dev_free(ctx, d_chunk); kq_dev_free(ctx, d_masks); kq_dev_free(ctx, d_r); kq_dev_free(ctx, d_scratch); kq_dev_free(ctx, d_s); kq_dev_free(ctx, d_sep); kq_dev_free(ctx, d_last); kq_dev_free(ctx, d_cols);
+        kq_dev_free(ctx, d_q); kq_dev_free(ctx, d_chunk); kq_dev_free(ctx, d_masks); kq_dev_free(ctx, d_r); kq_dev_free(ctx, d_scratch); kq_dev_free(ctx, d_s); kq_dev_free(ctx, d_sep); kq_dev_free(ctx, d_last);
         if (st != KQ_OK) for (kq_col* c : cols) kq_column_free(c);
         return st;
     };
@@ -579,13 +594,14 @@ static int csv_scan_resident(kq_ctx* ctx, const uint8_t* d_text, long long n, Cs
     if (n > 0) {
         const long long nchunks = (nblocks + CSV_CHUNK - 1) / CSV_CHUNK;
         if ((st = kq_dev_alloc(ctx, (size_t)nblocks + 16, (void**)&d_q)) != KQ_OK) return cleanup(st);
-        if ((st = kq_dev_alloc(ctx, (size_t)nchunks + 16, (void**)&d_chunk)) != KQ_OK) return cleanup(st);
+        const size_t chunk_pitch = ((size_t)nchunks + 255) / 256 * 256;         // [transitions][states], both 16-byte aligned
+        if ((st = kq_dev_alloc(ctx, 2 * chunk_pitch, (void**)&d_chunk)) != KQ_OK) return cleanup(st);
         if ((st = kq_dev_alloc(ctx, (size_t)(nblocks + 1) * 4, (void**)&d_r)) != KQ_OK) return cleanup(st);
         if ((st = kq_dev_alloc(ctx, (size_t)(ntiles + 4) * 8, (void**)&d_scratch)) != KQ_OK) return cleanup(st);
         const unsigned long long items = (unsigned long long)nblocks;
         auto scan_begin = [&](unsigned long long count) {
-            cudaMemsetAsync(d_scratch, 0, (size_t)(ntiles + 4) * 8, ctx->stream);
-            cudaMemcpyAsync(d_scratch + 2, &count, 8, cudaMemcpyHostToDevice, ctx->stream);
+            const int gb = (int)std::min<long long>((ntiles + 4 + 255) / 256, 1024);
+            k_csv_scan_begin<<<gb, 256, 0, ctx->stream>>>(d_scratch, ntiles + 4, 1, count);
         };
         const int sg = (int)std::max<long long>(1, std::min<long long>((nblocks + SCAN_TILE - 1) / SCAN_TILE, (long long)ctx->sm_count * 4));
         // 1. the quote state in front of every block (rule C2): block transitions, composed per chunk, chained, expanded
@@ -593,8 +609,8 @@ static int csv_scan_resident(kq_ctx* ctx, const uint8_t* d_text, long long n, Cs
         const int gc = (int)std::max<long long>(1, std::min<long long>((nchunks + 63) / 64, (long long)ctx->sm_count * 8));
         k_csv_quote_maps<<<gq, 256, 0, ctx->stream>>>(d_text, n, nblocks, f, batch, d_q);
         k_csv_compose_chunks<<<gc, 64, 0, ctx->stream>>>(d_q, nblocks, nchunks, d_chunk);
-        k_csv_chunk_states<<<1, 32, 0, ctx->stream>>>(d_chunk, nchunks, d_scratch + 1);
-        k_csv_block_states<<<gc, 64, 0, ctx->stream>>>(d_q, nblocks, nchunks, d_chunk);
+        k_csv_chunk_states<<<1, 32, 0, ctx->stream>>>(d_chunk, nchunks, d_chunk + chunk_pitch, d_scratch + 1);
+        k_csv_block_states<<<gc, 64, 0, ctx->stream>>>(d_q, nblocks, nchunks, d_chunk + chunk_pitch);
         if (cudaGetLastError() != cudaSuccess) return cleanup(kq_cuda_fail(ctx, cudaGetLastError(), "k_csv_quote_maps .. k_csv_block_states"));
         ctx->launches += 4;
         uint64_t total = 0;
@@ -668,10 +684,8 @@ static int csv_scan_resident(kq_ctx* ctx, const uint8_t* d_text, long long n, Cs
         if ((st = kq_dev_alloc(ctx, (size_t)(rows + 1) * 4, (void**)&d_len[(size_t)c])) != KQ_OK) return cleanup2(st);
         hc.lens[c] = d_len[(size_t)c];
     }
-    if ((st = kq_dev_alloc(ctx, sizeof hc, (void**)&d_cols)) != KQ_OK) return cleanup2(st);
-    cudaMemcpyAsync(d_cols, &hc, sizeof hc, cudaMemcpyHostToDevice, ctx->stream);
     const int gr = (int)std::max<long long>(1, std::min<long long>((rows + 127) / 128, (long long)ctx->sm_count * 16));
-    k_csv_fields<false><<<gr, 128, 0, ctx->stream>>>(d_text, d_sep, d_last, nrec, skip, d_cols);
+    k_csv_fields<false><<<gr, 128, 0, ctx->stream>>>(d_text, d_sep, d_last, nrec, skip, hc);
     if (cudaGetLastError() != cudaSuccess) return cleanup2(kq_cuda_fail(ctx, cudaGetLastError(), "k_csv_fields(lengths)"));
     ctx->launches++;
     // 5. offsets per materialised column, then the data buffers
@@ -684,13 +698,13 @@ static int csv_scan_resident(kq_ctx* ctx, const uint8_t* d_text, long long n, Cs
     unsigned long long* d_scratch2 = nullptr;
     if ((st = kq_dev_alloc(ctx, scratch_words * 8 * (size_t)nout, (void**)&d_scratch2)) != KQ_OK) return cleanup3(st);
     auto cleanup4 = [&](int s2) { kq_dev_free(ctx, d_scratch2); return cleanup3(s2); };
-    cudaMemsetAsync(d_scratch2, 0, scratch_words * 8 * (size_t)nout, ctx->stream);
     const unsigned long long count = (unsigned long long)rows;
+    const int gb2 = (int)std::min<long long>(((long long)scratch_words * nout + 255) / 256, 1024);
+    k_csv_scan_begin<<<gb2, 256, 0, ctx->stream>>>(d_scratch2, (long long)scratch_words, nout, count);
     for (int c = 0; c < nout; c++) {
         if (!d_len[(size_t)c]) continue;
         if ((st = kq_dev_alloc(ctx, (size_t)(rows + 1) * 4, (void**)&d_off[(size_t)c])) != KQ_OK) return cleanup4(st);
         unsigned long long* sc = d_scratch2 + scratch_words * (size_t)c;
-        cudaMemcpyAsync(sc + 2, &count, 8, cudaMemcpyHostToDevice, ctx->stream);
         k_exclusive_offsets<LenAt><<<sgr, 256, 0, ctx->stream>>>(LenAt{d_len[(size_t)c]}, sc + 2, d_off[(size_t)c], sc + 4, (unsigned int*)sc, sc + 1);
         if (cudaGetLastError() != cudaSuccess) return cleanup4(kq_cuda_fail(ctx, cudaGetLastError(), "k_exclusive_offsets(column)"));
         ctx->launches++;
@@ -706,7 +720,9 @@ static int csv_scan_resident(kq_ctx* ctx, const uint8_t* d_text, long long n, Cs
         if (!d_len[(size_t)c]) continue;
         kq_col* col = nullptr;
         if ((st = kq_col_new(ctx, KQ_UTF8, rows, false, (int64_t)bytes[(size_t)c], &col)) != KQ_OK) { cols.erase(std::remove(cols.begin(), cols.end(), nullptr), cols.end()); return cleanup3(st); }
-        cudaMemcpyAsync(col->offsets, d_off[(size_t)c], (size_t)(rows + 1) * 4, cudaMemcpyDeviceToDevice, ctx->stream);
+        kq_dev_free(ctx, col->offsets);             // the scan's output IS the offsets buffer (same size and allocator): no copy
+        col->offsets = d_off[(size_t)c];
+        d_off[(size_t)c] = nullptr;
         cols[(size_t)c] = col;
         hc.lens[c] = col->offsets;
         hc.data[c] = (uint8_t*)col->data;
@@ -714,15 +730,10 @@ static int csv_scan_resident(kq_ctx* ctx, const uint8_t* d_text, long long n, Cs
     for (int c = 0; c < nout; c++)
         if (!cols[(size_t)c]) { kq_col* src = cols[(size_t)first_out[(size_t)proj[(size_t)c]]]; src->rc.fetch_add(1); cols[(size_t)c] = src; }
     // 6. the bytes (the table of pointers changed: lens now = offsets)
-    CsvCols* d_cols2 = nullptr;
-    if ((st = kq_dev_alloc(ctx, sizeof hc, (void**)&d_cols2)) != KQ_OK) return cleanup3(st);
-    cudaMemcpyAsync(d_cols2, &hc, sizeof hc, cudaMemcpyHostToDevice, ctx->stream);
-    k_csv_fields<true><<<gr, 128, 0, ctx->stream>>>(d_text, d_sep, d_last, nrec, skip, d_cols2);
+    k_csv_fields<true><<<gr, 128, 0, ctx->stream>>>(d_text, d_sep, d_last, nrec, skip, hc);
     st = cudaGetLastError() != cudaSuccess ? kq_cuda_fail(ctx, cudaGetLastError(), "k_csv_fields(copy)") : KQ_OK;
     ctx->launches++;
-    // hc lives on the host stack: the two pageable uploads above were staged synchronously by the runtime
     if (st == KQ_OK) st = cudaStreamSynchronize(ctx->stream) == cudaSuccess ? KQ_OK : kq_cuda_fail(ctx, cudaGetLastError(), "cudaStreamSynchronize(csv)");
-    kq_dev_free(ctx, d_cols2);
     if (st != KQ_OK) return cleanup3(st);
     make_batch(rows);
     return cleanup3(KQ_OK);

@@ -16,6 +16,7 @@
 #define __host__
 #define __forceinline__ inline __attribute__((always_inline))
 #define __launch_bounds__(...)
+#define __grid_constant__
 #define __noinline__ /* empty: libstdc++ spells __attribute__((__noinline__)) */
 
 struct uint3 { unsigned x, y, z; };
