@@ -602,6 +602,7 @@ static int csv_scan_resident(kq_ctx* ctx, const uint8_t* d_text, long long n, Cs
         auto scan_begin = [&](unsigned long long count) {
             const int gb = (int)std::min<long long>((ntiles + 4 + 255) / 256, 1024);
             k_csv_scan_begin<<<gb, 256, 0, ctx->stream>>>(d_scratch, ntiles + 4, 1, count);
+            ctx->launches++;
         };
         const int sg = (int)std::max<long long>(1, std::min<long long>((nblocks + SCAN_TILE - 1) / SCAN_TILE, (long long)ctx->sm_count * 4));
         // 1. the quote state in front of every block (rule C2): block transitions, composed per chunk, chained, expanded
@@ -701,6 +702,7 @@ static int csv_scan_resident(kq_ctx* ctx, const uint8_t* d_text, long long n, Cs
     const unsigned long long count = (unsigned long long)rows;
     const int gb2 = (int)std::min<long long>(((long long)scratch_words * nout + 255) / 256, 1024);
     k_csv_scan_begin<<<gb2, 256, 0, ctx->stream>>>(d_scratch2, (long long)scratch_words, nout, count);
+    ctx->launches++;
     for (int c = 0; c < nout; c++) {
         if (!d_len[(size_t)c]) continue;
         if ((st = kq_dev_alloc(ctx, (size_t)(rows + 1) * 4, (void**)&d_off[(size_t)c])) != KQ_OK) return cleanup4(st);

@@ -63,3 +63,78 @@ def test_no_cpu_fallback(libpath):
     ex = L.kq_expr_binary(5, L.kq_expr_column(0), L.kq_expr_literal_i64(7))
     assert ex
     L.kq_expr_free(ex)
+
+
+def test_kotlin_ffm_descriptors_match_the_binding_table(libpath):
+    """INTEGRATION.md's Kotlin shim cannot be compiled here (no JDK), but its Panama FunctionDescriptors can be read: every
+    `fn("kq_...", RET, ARGS...)` must name an exported symbol and agree with the ctypes table (itself checked against the
+    header) in arity and in the class of every argument — 32-bit int, 64-bit int, double, float, address."""
+    import ctypes as C
+    import kqgpu
+    text = open(os.path.join(ROOT, "INTEGRATION.md")).read()
+    found = re.findall(r'fn\("(kq_\w+)",\s*([^)]*)\)', text)
+    assert len(found) >= 25
+
+    def cls(t):
+        if t is None:
+            return "void"
+        if t in (C.c_int, C.c_int32, C.c_uint32):
+            return "JAVA_INT"
+        if t in (C.c_int64, C.c_uint64, C.c_size_t):
+            return "JAVA_LONG"
+        if t is C.c_double:
+            return "JAVA_DOUBLE"
+        if t is C.c_float:
+            return "JAVA_FLOAT"
+        return "ADDRESS"            # c_void_p, c_char_p, POINTER(...)
+
+    for name, sig in found:
+        assert name in kqgpu.SYMBOLS, f"INTEGRATION.md binds {name}, which include/kqgpu.h does not declare"
+        parts = [p.strip() for p in sig.split(",") if p.strip()]
+        ret, args = parts[0], parts[1:]
+        res, argtypes = kqgpu.SYMBOLS[name]
+        want = [cls(res)] + [cls(a) for a in argtypes]
+        got = ["void" if ret == "null" else ret] + args
+        assert got == want, f"{name}: Kotlin descriptor {got} != C signature {want}"
+
+
+def test_binding_table_matches_the_header_signatures():
+    """The ctypes table against the C declarations themselves: return class and the class of every parameter."""
+    import ctypes as C
+    import kqgpu
+    text = re.sub(r"/\*.*?\*/", " ", open(HEADER).read(), flags=re.S)
+    decls = re.findall(r"KQ_API\s+([\w\s\*]+?)\b(kq_\w+)\s*\(([^;]*?)\)\s*;", text, flags=re.S)
+    assert len(decls) == len(declared_symbols())
+
+    def c_class(decl):
+        decl = decl.strip()
+        if "*" in decl or "[" in decl:          # an array parameter is a pointer
+            return "ptr"
+        base = decl.replace("const", " ").split()
+        base = [w for w in base if w not in ("unsigned", "signed")]
+        if decl == "void":
+            return "void"
+        ty = base[0]
+        return {"int": "i32", "int32_t": "i32", "uint32_t": "i32", "int64_t": "i64", "uint64_t": "i64", "size_t": "i64",
+                "double": "f64", "float": "f32"}[ty]
+
+    def py_class(t):
+        if t is None:
+            return "void"
+        if t in (C.c_int, C.c_int32, C.c_uint32):
+            return "i32"
+        if t in (C.c_int64, C.c_uint64, C.c_size_t):
+            return "i64"
+        if t is C.c_double:
+            return "f64"
+        if t is C.c_float:
+            return "f32"
+        return "ptr"
+
+    for ret, name, params in decls:
+        params = [p.strip() for p in params.replace("\n", " ").split(",")]
+        params = [] if params == ["void"] else params
+        want = [c_class(ret)] + [c_class(p) for p in params]
+        res, argtypes = kqgpu.SYMBOLS[name]
+        got = [py_class(res)] + [py_class(a) for a in argtypes]
+        assert got == want, f"{name}: ctypes {got} != header {want}"
