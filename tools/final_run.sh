@@ -12,6 +12,7 @@ $L --log-file $O/launches.csv python bench.py --steps 2 --warmup 3 --no-sub --no
 $L --log-file $O/launches_cfg5.csv python bench.py --workload cfg5 --steps 2 --warmup 3 --no-e2e --no-cpu-baseline > $O/ncu_launches5.log 2>&1
 $L --log-file $O/launches_cfg2f.csv python bench.py --workload cfg2f --steps 2 --warmup 3 --no-e2e --no-cpu-baseline > $O/ncu_launches2f.log 2>&1
 $L --log-file $O/launches_cfg4.csv python bench.py --workload cfg4 --rows 100000000 --steps 2 --warmup 3 --no-e2e --no-cpu-baseline > $O/ncu_launches4.log 2>&1
+$L --log-file $O/launches_csv.csv python bench.py --workload csv --steps 2 --warmup 3 --no-e2e --no-cpu-baseline > $O/ncu_launches_csv.log 2>&1
 N="ncu --set full --clock-control none --import-source on -c 1"
 B="python bench.py --steps 2 --no-sub --no-e2e --no-cpu-baseline"
 $N -k regex:kq_group_aggregate -s 3 -o $O/agg_cfg3 -f $B --workload cfg3 > $O/ncu_cfg3.log 2>&1
