@@ -11,7 +11,8 @@ STRONG-scaled: with N > 1 (torchrun, one rank per GPU) the 1 B rows are split N 
 tables are merged over NCCL inside the timed region (partition -> partial -> merge, Main.kt:1309-1325).
 `sub` carries the same measurement for configs[1] (cfg2f, fused filter+project, 100 M rows per GPU, no
 exchange), configs[4] (cfg5, TPC-H Q1 shape, 600 M rows split N ways) and configs[3] (cfg4, 10 M groups
-over 1 B rows split N ways, NCCL all-to-all repartition), so all four are on the driver's clock.
+over 1 B rows split N ways, NCCL all-to-all repartition), so all four are on the driver's clock; at N = 1
+also `csv` (CsvDataSource.scan over 10 M records: device-resident, and end to end through the reader).
 
 One JSON line on stdout (rank 0). `value` is device-resident throughput (CUDA events on the kernel
 stream, max over ranks); `e2e` is the same metric through the C ABI with HOST buffers (pinned
@@ -552,6 +553,15 @@ def main():
             r = measure(kqgpu, ctx, E, swl, args, dist, rank, world, max(3, min(args.steps, 10)), 3, not args.no_e2e, False)
             sub[name] = {k: r[k] for k in ("value", "ms_per_step", "scaling", "dtype", "config", "roofline", "e2e", "gpu_launches", "check", "steps", "output_rows_rank0")}
             sub[name]["unit"] = "rows/s"
+        if args.workload == "cfg3" and world == 1:
+            # the scan side on the same clock: CsvDataSource.scan over 10 M records, device-resident and end to
+            # end through the reader. Last and guarded: whatever happens here, the line above is printed.
+            try:
+                r = measure(kqgpu, ctx, E, WORKLOADS["csv"](0), args, dist, rank, world, 5, 3, not args.no_e2e, False)
+                sub["csv"] = {k: r[k] for k in ("value", "ms_per_step", "scaling", "dtype", "config", "roofline", "e2e", "gpu_launches", "check", "steps", "output_rows_rank0")}
+                sub["csv"]["unit"] = "rows/s"
+            except Exception as e:      # noqa: BLE001
+                sub["csv"] = {"error": repr(e)[:300]}
 
     if rank == 0:
         line = {"metric": "rows/s", "value": m["value"], "unit": "rows/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
