@@ -741,9 +741,6 @@ static int csv_scan_resident(kq_ctx* ctx, const uint8_t* d_text, long long n, Cs
     return cleanup3(KQ_OK);
 }
 
-
-
-
 // ---- CsvDataSource.scan as a Sequence<RecordBatch> (Main.kt:239-249, 304-326): the text streams through two device
 // buffers piece by piece; the H2D copy of piece k+1 (copy stream) runs under the scan of piece k (compute stream).
 // A piece is cut where its last complete record ends; the unfinished tail is moved in front of the next piece.
@@ -814,7 +811,6 @@ struct kq_csv_reader {
     CsvPiece p[2];
     int cur = 0;
     bool first = true, done = false;
-    int64_t records = 0, batches = 0;
 };
 
 static void csv_reader_upload(kq_csv_reader* r, int slot) {
@@ -886,7 +882,7 @@ int kq_csv_reader_next(kq_csv_reader* r, kq_batch** out) {
             if (R - carry > N.start) cudaMemsetAsync(N.buf + N.start, r->src.f.term, (size_t)(R - carry - N.start), ctx->stream);
         }
         r->cur ^= 1;
-        if (b->n > 0) { r->records += b->n; r->batches++; *out = b; return KQ_OK; }      // Main.kt:245-247: a batch is yielded only when it has rows
+        if (b->n > 0) { *out = b; return KQ_OK; }      // Main.kt:245-247: a batch is yielded only when it has rows
         kq_batch_free(b);
     }
     return KQ_OK;
