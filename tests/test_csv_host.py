@@ -97,7 +97,8 @@ class Host:
             data = C.create_string_buffer(max(nb, 1))
             L.kqh_col_read(b, c, off, data)
             assert off[0] == 0 and off[rows] == nb
-            cols.append([data.raw[off[i]:off[i + 1]].decode("utf-8") for i in range(rows)])
+            raw, o = data.raw, list(off)                            # one copy each (ctypes makes a new object on every access)
+            cols.append([raw[o[i]:o[i + 1]].decode("utf-8") for i in range(rows)])
         L.kq_batch_free(b)
         return cols
 
@@ -289,4 +290,23 @@ def test_a_quoted_section_that_spans_many_blocks_and_chunks(H, oracle):
     assert concat(list(H.batches(text, True, piece=16384)), 2) == want
     with pytest.raises(HostError, match="longer than the reader's piece"):
         list(H.batches(text, True, piece=4096))
+    assert H.clean()
+
+
+def test_bench_text_at_reduced_size_is_periodic_like_its_blocks(H, oracle):
+    """The GPU suite's full-size CSV check (tests/test_gpu_full_size.py: 10 M records) at a size the host build walks in
+    seconds: bench.py's text of 250 000 records = a 100 000-record block repeated plus a cut block; the columns must be
+    the oracle's columns of one block, repeated — here with every chunk of the quote-state composition several times over."""
+    import sys
+    sys.path.insert(0, ROOT)
+    import bench
+    wl = bench.WORKLOADS["csv"](250_000)
+    text = wl.make_text(wl.rows)
+    got = H.scan(text, True)
+    block = columns(oracle.csv_scan(wl.make_text(100_000), True))
+    tail = columns(oracle.csv_scan(wl.make_text(50_000), True))
+    assert len(got) == 6 and len(got[0]) == 250_000
+    for c in range(6):
+        assert got[c][:100_000] == block[c] and got[c][100_000:200_000] == block[c] and got[c][200_000:] == tail[c]
+    assert concat(list(H.batches(text, True, piece=1 << 20)), 6) == got
     assert H.clean()
