@@ -434,6 +434,12 @@ __global__ void k_csv_scan_begin(unsigned long long* scratch, long long words, i
     const long long total = words * nscans;
     for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) scratch[i] = (i % words == 2) ? count : 0ULL;
 }
+// a reader's piece: the byte behind its last complete record (0: indices out of range)
+__global__ void k_csv_last_end(const int32_t* __restrict__ sep, const int32_t* __restrict__ rec_last, long long nrec, long long nsep, unsigned long long* out) {
+    if (blockIdx.x != 0 || threadIdx.x != 0) return;
+    const long long k = rec_last[nrec - 1];
+    *out = k >= 0 && k < nsep && sep[k] >= 0 ? (unsigned long long)sep[k] + 1ULL : 0ULL;
+}
 struct LenAt {
     const int32_t* lens;
     __device__ __forceinline__ int operator()(long long i) const { return lens[i]; }
@@ -571,14 +577,17 @@ static int csv_scan_resident(kq_ctx* ctx, const uint8_t* d_text, long long n, Cs
     uint8_t *d_q = nullptr, *d_chunk = nullptr;     // per block: quote transition, then the quote state in front of it; per chunk likewise
     BlockMasks* d_masks = nullptr;                  // per block: record-end and delimiter bits
     int32_t* d_r = nullptr;
-    unsigned long long* d_scratch = nullptr;        // [0] ticket, [1] total, [2] item count, [4..] tile descriptors
+    unsigned long long* d_scratch = nullptr;        // two scan areas of [0] ticket, [1] unused, [2] item count, [4..] tile descriptors
+    // what the host reads back, with as few synchronisations as there are decisions to take: [0] quote state behind the text,
+    // [1] records, [2] separators, [3] end of the last complete record (a reader's piece), [8 + c] bytes of output column c
+    unsigned long long* d_res = nullptr;
     int32_t *d_s = nullptr, *d_sep = nullptr, *d_last = nullptr;
     std::vector<kq_col*> cols;
-    // tile descriptors of the device-wide scans: over 64-byte blocks (passes 1-2) and over records (pass 5; a record has at
+    // tile descriptors of the device-wide scans: over 64-byte blocks (pass 2) and over records (pass 5; a record has at
     // least two bytes, so nblocks * 32 bounds the record count)
     const long long ntiles = (std::max<long long>(nblocks, 1) * (CSV_BLOCK / 2) + SCAN_TILE - 1) / SCAN_TILE + 2;
     auto cleanup = [&](int st) {
-        kq_dev_free(ctx, d_q); kq_dev_free(ctx, d_chunk); kq_dev_free(ctx, d_masks); kq_dev_free(ctx, d_r); kq_dev_free(ctx, d_scratch); kq_dev_free(ctx, d_s); kq_dev_free(ctx, d_sep); kq_dev_free(ctx, d_last);
+        kq_dev_free(ctx, d_q); kq_dev_free(ctx, d_chunk); kq_dev_free(ctx, d_masks); kq_dev_free(ctx, d_r); kq_dev_free(ctx, d_scratch); kq_dev_free(ctx, d_res); kq_dev_free(ctx, d_s); kq_dev_free(ctx, d_sep); kq_dev_free(ctx, d_last);
         if (st != KQ_OK) for (kq_col* c : cols) kq_column_free(c);
         return st;
     };
@@ -597,46 +606,36 @@ static int csv_scan_resident(kq_ctx* ctx, const uint8_t* d_text, long long n, Cs
         const size_t chunk_pitch = ((size_t)nchunks + 255) / 256 * 256;         // [transitions][states], both 16-byte aligned
         if ((st = kq_dev_alloc(ctx, 2 * chunk_pitch, (void**)&d_chunk)) != KQ_OK) return cleanup(st);
         if ((st = kq_dev_alloc(ctx, (size_t)(nblocks + 1) * 4, (void**)&d_r)) != KQ_OK) return cleanup(st);
-        if ((st = kq_dev_alloc(ctx, (size_t)(ntiles + 4) * 8, (void**)&d_scratch)) != KQ_OK) return cleanup(st);
-        const unsigned long long items = (unsigned long long)nblocks;
-        auto scan_begin = [&](unsigned long long count) {
-            const int gb = (int)std::min<long long>((ntiles + 4 + 255) / 256, 1024);
-            k_csv_scan_begin<<<gb, 256, 0, ctx->stream>>>(d_scratch, ntiles + 4, 1, count);
-            ctx->launches++;
-        };
+        const long long words = ntiles + 4;
+        if ((st = kq_dev_alloc(ctx, (size_t)words * 2 * 8, (void**)&d_scratch)) != KQ_OK) return cleanup(st);
+        if ((st = kq_dev_alloc(ctx, (size_t)(8 + nout) * 8, (void**)&d_res)) != KQ_OK) return cleanup(st);
+        if ((st = kq_dev_alloc(ctx, (size_t)(nblocks + 1) * 4, (void**)&d_s)) != KQ_OK) return cleanup(st);
+        if ((st = kq_dev_alloc(ctx, (size_t)nblocks * sizeof(BlockMasks), (void**)&d_masks)) != KQ_OK) return cleanup(st);
         const int sg = (int)std::max<long long>(1, std::min<long long>((nblocks + SCAN_TILE - 1) / SCAN_TILE, (long long)ctx->sm_count * 4));
         // 1. the quote state in front of every block (rule C2): block transitions, composed per chunk, chained, expanded
         const int gq = (int)std::max<long long>(1, std::min<long long>((nblocks + 255) / 256, (long long)ctx->sm_count * 8));
         const int gc = (int)std::max<long long>(1, std::min<long long>((nchunks + 63) / 64, (long long)ctx->sm_count * 8));
         k_csv_quote_maps<<<gq, 256, 0, ctx->stream>>>(d_text, n, nblocks, f, batch, d_q);
         k_csv_compose_chunks<<<gc, 64, 0, ctx->stream>>>(d_q, nblocks, nchunks, d_chunk);
-        k_csv_chunk_states<<<1, 32, 0, ctx->stream>>>(d_chunk, nchunks, d_chunk + chunk_pitch, d_scratch + 1);
+        k_csv_chunk_states<<<1, 32, 0, ctx->stream>>>(d_chunk, nchunks, d_chunk + chunk_pitch, d_res);
         k_csv_block_states<<<gc, 64, 0, ctx->stream>>>(d_q, nblocks, nchunks, d_chunk + chunk_pitch);
-        if (cudaGetLastError() != cudaSuccess) return cleanup(kq_cuda_fail(ctx, cudaGetLastError(), "k_csv_quote_maps .. k_csv_block_states"));
-        ctx->launches += 4;
-        uint64_t total = 0;
-        if (!partial) {
-            if ((st = kq_read_u64(ctx, d_scratch + 1, 1, &total)) != KQ_OK) return cleanup(st);
-            if (total == Q_IN) return cleanup(kq_fail(ctx, KQ_ERR_ILLEGAL_STATE, "CSV text ends inside a quoted field"));
-        }
-        // 2. the block masks, then records and separators before every block
-        if ((st = kq_dev_alloc(ctx, (size_t)nblocks * sizeof(BlockMasks), (void**)&d_masks)) != KQ_OK) return cleanup(st);
+        // 2. the block masks, then records and separators before every block: two scans queued back to back, each with its own
+        //    ticket and tile descriptors, their totals next to the quote state — one read-back for the three
         k_csv_store_masks<<<gq, 256, 0, ctx->stream>>>(d_text, n, nblocks, d_q, f, batch, d_masks);
-        ctx->launches++;
-        scan_begin(items);
-        k_exclusive_offsets<RecordCount><<<sg, 256, 0, ctx->stream>>>(RecordCount{d_masks}, d_scratch + 2, d_r, d_scratch + 4, (unsigned int*)d_scratch, d_scratch + 1);
-        if (cudaGetLastError() != cudaSuccess) return cleanup(kq_cuda_fail(ctx, cudaGetLastError(), "k_exclusive_offsets(records)"));
-        ctx->launches++;
-        if ((st = kq_read_u64(ctx, d_scratch + 1, 1, &total)) != KQ_OK) return cleanup(st);
-        nrec = (int64_t)total;
+        const int gb = (int)std::min<long long>((2 * words + 255) / 256, 1024);
+        k_csv_scan_begin<<<gb, 256, 0, ctx->stream>>>(d_scratch, words, 2, (unsigned long long)nblocks);
+        unsigned long long* sa = d_scratch;
+        unsigned long long* sb = d_scratch + words;
+        k_exclusive_offsets<RecordCount><<<sg, 256, 0, ctx->stream>>>(RecordCount{d_masks}, sa + 2, d_r, sa + 4, (unsigned int*)sa, d_res + 1);
+        k_exclusive_offsets<SeparatorCount><<<sg, 256, 0, ctx->stream>>>(SeparatorCount{d_masks}, sb + 2, d_s, sb + 4, (unsigned int*)sb, d_res + 2);
+        if (cudaGetLastError() != cudaSuccess) return cleanup(kq_cuda_fail(ctx, cudaGetLastError(), "CSV passes 1-2"));
+        ctx->launches += 8;
+        uint64_t res[3] = {0, 0, 0};
+        if ((st = kq_read_u64(ctx, d_res, 3, res)) != KQ_OK) return cleanup(st);
+        if (!partial && res[0] == Q_IN) return cleanup(kq_fail(ctx, KQ_ERR_ILLEGAL_STATE, "CSV text ends inside a quoted field"));
+        nrec = (int64_t)res[1];
+        nsep = (int64_t)res[2];
         if (partial && nrec == 0) return cleanup(kq_fail(ctx, KQ_ERR_UNSUPPORTED, "CSV record longer than the reader's piece (%lld bytes): open the reader with larger pieces", n));
-        if ((st = kq_dev_alloc(ctx, (size_t)(nblocks + 1) * 4, (void**)&d_s)) != KQ_OK) return cleanup(st);
-        scan_begin(items);
-        k_exclusive_offsets<SeparatorCount><<<sg, 256, 0, ctx->stream>>>(SeparatorCount{d_masks}, d_scratch + 2, d_s, d_scratch + 4, (unsigned int*)d_scratch, d_scratch + 1);
-        if (cudaGetLastError() != cudaSuccess) return cleanup(kq_cuda_fail(ctx, cudaGetLastError(), "k_exclusive_offsets(separators)"));
-        ctx->launches++;
-        if ((st = kq_read_u64(ctx, d_scratch + 1, 1, &total)) != KQ_OK) return cleanup(st);
-        nsep = (int64_t)total;
     }
     const int skip = has_headers && nrec > 0 ? 1 : 0;
     const int64_t rows = nrec - skip;
@@ -649,14 +648,12 @@ static int csv_scan_resident(kq_ctx* ctx, const uint8_t* d_text, long long n, Cs
         if (cudaGetLastError() != cudaSuccess) return cleanup(kq_cuda_fail(ctx, cudaGetLastError(), "k_csv_separators"));
         ctx->launches++;
         if (partial) {       // where the last complete record ends: separator rec_last[nrec - 1] (delimiters of the unfinished tail follow it)
-            int32_t* h = (int32_t*)ctx->h_scratch;
-            for (int hop = 0; hop < 2; hop++) {
-                const int32_t* from = hop == 0 ? d_last + (nrec - 1) : d_sep + h[0];
-                if (cudaMemcpyAsync(h, from, 4, cudaMemcpyDeviceToHost, ctx->stream) != cudaSuccess || cudaStreamSynchronize(ctx->stream) != cudaSuccess)
-                    return cleanup(kq_cuda_fail(ctx, cudaGetLastError(), "read back the last record end"));
-                if (h[0] < 0 || (hop == 0 && h[0] >= nsep) || (hop == 1 && h[0] >= n)) return cleanup(kq_fail(ctx, KQ_ERR_ILLEGAL_STATE, "CSV separator index out of range"));
-            }
-            *consumed = (int64_t)h[0] + 1;
+            k_csv_last_end<<<1, 32, 0, ctx->stream>>>(d_sep, d_last, nrec, nsep, d_res + 3);
+            ctx->launches++;
+            uint64_t end = 0;
+            if ((st = kq_read_u64(ctx, d_res + 3, 1, &end)) != KQ_OK) return cleanup(st);
+            if (end == 0 || end > (uint64_t)n) return cleanup(kq_fail(ctx, KQ_ERR_ILLEGAL_STATE, "CSV separator index out of range"));
+            *consumed = (int64_t)end;
         }
     }
     if (rows <= 0 || nout == 0) {            // no data records: zero-row columns (Main.kt:245-247 yields no batch; one empty batch here, rule R10's shape)
@@ -707,13 +704,14 @@ static int csv_scan_resident(kq_ctx* ctx, const uint8_t* d_text, long long n, Cs
         if (!d_len[(size_t)c]) continue;
         if ((st = kq_dev_alloc(ctx, (size_t)(rows + 1) * 4, (void**)&d_off[(size_t)c])) != KQ_OK) return cleanup4(st);
         unsigned long long* sc = d_scratch2 + scratch_words * (size_t)c;
-        k_exclusive_offsets<LenAt><<<sgr, 256, 0, ctx->stream>>>(LenAt{d_len[(size_t)c]}, sc + 2, d_off[(size_t)c], sc + 4, (unsigned int*)sc, sc + 1);
+        k_exclusive_offsets<LenAt><<<sgr, 256, 0, ctx->stream>>>(LenAt{d_len[(size_t)c]}, sc + 2, d_off[(size_t)c], sc + 4, (unsigned int*)sc, d_res + 8 + c);
         if (cudaGetLastError() != cudaSuccess) return cleanup4(kq_cuda_fail(ctx, cudaGetLastError(), "k_exclusive_offsets(column)"));
         ctx->launches++;
     }
+    for (int c0 = 0; c0 < nout; c0 += 64)           // the totals of all column scans: one read-back per 64 columns
+        if ((st = kq_read_u64(ctx, d_res + 8 + c0, std::min(64, nout - c0), bytes.data() + c0)) != KQ_OK) return cleanup4(st);
     for (int c = 0; c < nout; c++) {
-        if (!d_len[(size_t)c]) continue;
-        if ((st = kq_read_u64(ctx, d_scratch2 + scratch_words * (size_t)c + 1, 1, &bytes[(size_t)c])) != KQ_OK) return cleanup4(st);
+        if (!d_len[(size_t)c]) { bytes[(size_t)c] = 0; continue; }       // shares another column's buffers: its slot was never written
         if (bytes[(size_t)c] >= (1ULL << 31)) return cleanup4(kq_fail(ctx, KQ_ERR_UNSUPPORTED, "CSV column of 2 GiB or more"));
     }
     kq_dev_free(ctx, d_scratch2);
