@@ -717,12 +717,17 @@ struct CsvQuoteRule {
     }
 };
 // lines: split at terminators outside quotes
-static std::vector<std::string> csv_lines(const std::string& all, const std::string& delims, char term, bool whole_text) {
+// (first_record_only: stop behind the first line that is not empty — all that delimiter detection looks at)
+static std::vector<std::string> csv_lines(const std::string& all, const std::string& delims, char term, bool whole_text, bool first_record_only = false) {
     std::vector<std::string> lines;
     std::string cur;
     CsvQuoteRule q(delims, term);
     for (char c : all) {
-        if (q.outside(c) && c == term) { lines.push_back(cur); cur.clear(); }
+        if (q.outside(c) && c == term) {
+            const bool blank = cur.empty() || (term == '\n' && cur == "\r");
+            lines.push_back(cur); cur.clear();
+            if (first_record_only && !blank) return lines;
+        }
         else cur += c;
     }
     if (whole_text && q.at == CsvQuoteRule::Quoted) throw KqError(E_ILLEGAL_STATE, "CSV text ends inside a quoted field");
@@ -739,7 +744,7 @@ static CsvText csv_tokenize(const uint8_t* text, int64_t n) {
     };
     // delimiter detection on the first record (Main.kt:291), found with every candidate counting as a delimiter
     const std::string cand = ",;\t|";
-    for (std::string& line : csv_lines(all, cand, out.term, false)) {
+    for (std::string& line : csv_lines(all, cand, out.term, false, true)) {
         if (empty_line(line)) continue;
         long cnt[4] = {0, 0, 0, 0};
         CsvQuoteRule q(cand, out.term);
