@@ -8,6 +8,7 @@ the symbol table can be checked on a CPU box) but creating a Context without a C
 ColumnExpression (Main.kt:452-460), cast is CastExpression (772-805), project is
 ProjectionExec.execute for one batch (589-594), HashAggregate is HashAggregateExec (605-660);
 literals, binary expressions, filter and SUM/MIN/COUNT are the extensions of SURVEY.md §8 a12.
+The layer above — DataFrame, logical plan, planner, SQL — is in the submodules `plan` and `sql`.
 """
 from __future__ import annotations
 
