@@ -635,3 +635,11 @@ def createPhysicalPlan(plan: LogicalPlan, engine) -> PhysicalPlan:
             aggregateExpr.append((a.name, createPhysicalExpr(a.expr, plan.input, engine)))
         return HashAggregateExec(engine, input, groupExpr, aggregateExpr, plan.schema(), predicate)
     raise IllegalStateException("Unknown physical plan")
+
+
+def printQueryResult(queryResult, file=None):
+    """Main.kt:1344-1353: every row of every batch, cells separated by a blank (the batches are downloaded here)."""
+    for batch in queryResult:
+        cols = [a.to_pylist() for a in batch.to_arrow()]
+        for row in zip(*cols):
+            print(" ".join(str(v) for v in row) + " ", file=file)

@@ -229,9 +229,64 @@ def test_where_below_an_aggregate_is_fused_and_order_of_select_list_is_kept(orac
     assert got == {r[0]: (r[1], r[2]) for r in rows([a.finalize()])}
 
 
+def test_print_query_result(ctx, capsys):
+    P.printQueryResult(ctx.execute(ctx.sql("SELECT id, last_name FROM employee")))
+    assert capsys.readouterr().out == "1 Johansson \n2 Person \n3 Pärsson \n"
+
+
 def test_zero_input_rows_give_one_batch_without_rows(oracle):
     """Rule R10: HashAggregateExec always yields exactly one batch, also for no input (and for a global aggregate)."""
     c = P.ExecutionContext(oracle)
     c.registerDataSource("t", P.InMemoryDataSource(oracle, P.Schema([P.Field("v", P.DoubleType)]), []))
     out = list(c.execute(c.sql("SELECT MAX(v) FROM t")))
     assert len(out) == 1 and out[0].row_count() == 0
+
+
+# ---------------------------------------------------------------- generated queries against numpy
+import numpy as np
+from hypothesis import given, settings, strategies as st
+
+_LEAF = st.one_of(st.sampled_from(["a", "b", "c"]), st.floats(0.0, 2.0, allow_nan=False).map(lambda v: round(v, 3)))
+_ARITH = st.recursive(_LEAF, lambda kids: st.tuples(st.sampled_from(["+", "-", "*", "/"]), kids, kids), max_leaves=5)
+_CMP = st.tuples(st.sampled_from(["<", "<=", ">", ">=", "=", "!="]), _ARITH, _ARITH)
+_PRED = st.recursive(_CMP, lambda kids: st.tuples(st.sampled_from(["AND", "OR"]), kids, kids), max_leaves=4)
+_PREC = {"OR": 20, "AND": 30, "<": 40, "<=": 40, ">": 40, ">=": 40, "=": 40, "!=": 40, "+": 50, "-": 50, "*": 60, "/": 60}
+
+
+def _sql(t, parent=0, right=False):
+    """The tree as SQL with only the parentheses precedence and left-associativity require."""
+    if isinstance(t, str):
+        return t
+    if isinstance(t, float):
+        return repr(t)
+    op, l, r = t
+    p = _PREC[op]
+    s = f"{_sql(l, p)} {op} {_sql(r, p, True)}"
+    return f"({s})" if p < parent or (p == parent and right) else s
+
+
+def _np(t, cols):
+    if isinstance(t, str):
+        return cols[t]
+    if isinstance(t, float):
+        return np.full_like(cols["a"], t)
+    op, l, r = t
+    x, y = _np(l, cols), _np(r, cols)
+    with np.errstate(all="ignore"):
+        return {"+": np.add, "-": np.subtract, "*": np.multiply, "/": np.divide, "<": np.less, "<=": np.less_equal, ">": np.greater,
+                ">=": np.greater_equal, "=": np.equal, "!=": np.not_equal, "AND": np.logical_and, "OR": np.logical_or}[op](x, y)
+
+
+@settings(max_examples=120, deadline=None)
+@given(proj=_ARITH.filter(lambda t: not isinstance(t, float)), pred=_PRED)
+def test_generated_select_where_matches_numpy(oracle, proj, pred):
+    """SELECT <arithmetic> FROM t WHERE <predicate>: parser precedences and associativity, the planner, and the expression
+    rules E2-E4 (separately rounded IEEE arithmetic, comparisons, AND/OR) against numpy on the same columns, bit for bit."""
+    batch = oracle.generate(SPECS2, 7, 0, 2000)
+    cols = dict(zip("abc", [a.to_numpy(zero_copy_only=False) for a in batch.to_arrow()]))
+    c = P.ExecutionContext(oracle)
+    c.registerDataSource("t", P.InMemoryDataSource(oracle, P.Schema([P.Field(n, P.DoubleType) for n in "abc"]), [batch]))
+    sql = f"SELECT {_sql(proj)} AS r FROM t WHERE {_sql(pred)}"
+    got = np.array([v for b in c.execute(c.sql(sql)) for v in b.to_arrow()[0].to_pylist()], dtype=np.float64)
+    want = _np(proj, cols)[_np(pred, cols)]
+    assert got.tobytes() == want.astype(np.float64).tobytes(), sql
