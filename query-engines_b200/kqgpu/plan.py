@@ -206,6 +206,9 @@ def lit(value) -> Literal:
         return Literal(value, DoubleType)
     if isinstance(value, str):
         return Literal(value, StringType)
+    import datetime
+    if isinstance(value, datetime.date):
+        return Literal((value - datetime.date(1970, 1, 1)).days, Date32Type)
     raise IllegalStateException(f"Unsupported literal: {value!r}")
 
 
@@ -542,8 +545,9 @@ class ProjectionExec(PhysicalPlan):
     """ProjectionExec (Main.kt:582-603): one output batch per input batch. With a predicate it is the fused
     filter+projection kernel (one pass, ordered compaction) — a Selection directly below a Projection."""
 
-    def __init__(self, engine, input: PhysicalPlan, schema: Schema, expr, predicate=None):
+    def __init__(self, engine, input: PhysicalPlan, schema: Schema, expr, predicate=None, bare=None):
         self.engine, self.input, self._schema, self.expr, self.predicate = engine, input, schema, list(expr), predicate
+        self.bare = list(bare) if bare is not None else [False] * len(self.expr)      # expr k is a column reference: an alias, or a gather below a filter
 
     def schema(self):
         return self._schema
@@ -626,7 +630,9 @@ def createPhysicalPlan(plan: LogicalPlan, engine) -> PhysicalPlan:
         input = createPhysicalPlan(source, engine)
         if isinstance(plan, Projection):
             expr = [createPhysicalExpr(e, plan.input, engine) for e in plan.expr]
-            return ProjectionExec(engine, input, Schema([e.toField(plan.input) for e in plan.expr]), expr, predicate)
+            def bare(e):
+                return bare(e.expr) if isinstance(e, Alias) else isinstance(e, (Column, ColumnIndex))
+            return ProjectionExec(engine, input, Schema([e.toField(plan.input) for e in plan.expr]), expr, predicate, [bare(e) for e in plan.expr])
         groupExpr = [createPhysicalExpr(e, plan.input, engine) for e in plan.groupExpr]
         aggregateExpr = []
         for a in plan.aggExpr:
@@ -635,6 +641,33 @@ def createPhysicalPlan(plan: LogicalPlan, engine) -> PhysicalPlan:
             aggregateExpr.append((a.name, createPhysicalExpr(a.expr, plan.input, engine)))
         return HashAggregateExec(engine, input, groupExpr, aggregateExpr, plan.schema(), predicate)
     raise IllegalStateException("Unknown physical plan")
+
+
+def explain(plan: PhysicalPlan, nullable: bool = False, compile: bool = True):
+    """The CUDA source the engine generates for every operator of a physical plan — [(operator, source), ...], children
+    first — compiled for sm_100a when `compile` (NVRTC needs no device: with kqgpu.Exprs() as the engine this runs on a CPU
+    box, from the query string to the cubin). `nullable`: whether the scanned columns may hold nulls (CSV columns never do,
+    rule C6). Operators without a kernel of their own (ScanExec) are left out."""
+    out = []
+    for c in plan.children():
+        out += explain(c, nullable, compile)
+    if isinstance(plan, (ProjectionExec, SelectionExec, HashAggregateExec)):
+        fields = plan.input.schema().fields
+        types, nulls = [f.dataType.kq_type for f in fields], [int(nullable)] * len(fields)
+        # a bare column reference is not kernel work: without a filter it is an alias of the input column (rule R4), below a
+        # filter a fixed-width column is compacted by the kernel and a Utf8 column is gathered by its selection vector
+        if isinstance(plan, ProjectionExec):
+            exprs = [e for e, b, f in zip(plan.expr, plan.bare, plan.schema().fields)
+                     if not b or (plan.predicate is not None and f.dataType.kq_type != UTF8)]
+            if not exprs and plan.predicate is None:
+                return out                                   # only aliases: no kernel at all
+            src = plan.engine.explain_filter_project(plan.predicate, exprs, types, nulls, compile)
+        elif isinstance(plan, SelectionExec):
+            src = plan.engine.explain_filter_project(plan.predicate, [plan.engine.col(i) for i, t in enumerate(types) if t != UTF8], types, nulls, compile)
+        else:
+            src = plan.engine.explain_hashagg(plan.groupExpr, plan.aggregateExpr, types, nulls, plan.predicate, compile)
+        out.append((plan, src))
+    return out
 
 
 def printQueryResult(queryResult, file=None):

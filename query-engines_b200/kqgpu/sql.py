@@ -4,7 +4,7 @@ extensions SURVEY.md §8 f4 names so that BASELINE.json's query strings run thro
     reference : SELECT exprs FROM table [GROUP BY exprs] [ORDER BY exprs];  identifiers, `quoted identifiers`, CAST(x AS double),
                 MAX(x), x AS alias.  ORDER BY is parsed and ignored (there is no Sort operator, Main.kt:1276-1279).
     [+]       : WHERE; SUM / MIN / COUNT; long, double and string literals; = != <> < <= > >= AND OR + - * / with the usual
-                precedences and parentheses; a select list without aggregates plans a plain projection.
+                precedences and parentheses; DATE 'yyyy-mm-dd'; a select list without aggregates plans a plain projection.
 
 Errors follow the reference: SQLException for unknown tables, columns, data types and functions, IllegalStateException for
 tokens the parser does not expect (Main.kt:1108, 1129, 1136, 1181, 1218-1290).
@@ -15,7 +15,7 @@ from .plan import (AggregateExpr, Alias, BinaryExpr, CastExpr, Column, ColumnInd
                    IllegalStateException, Int64Type, LogicalExpr, Max, Min, SQLException, StringType, Sum, lit)
 
 KEYWORDS = {"AS", "BY", "CAST", "DOUBLE", "FROM", "GROUP", "MAX", "ORDER", "SELECT",          # Main.kt:807-822
-            "WHERE", "AND", "OR", "SUM", "MIN", "COUNT", "ASC", "DESC"}                           # [+]
+            "WHERE", "AND", "OR", "SUM", "MIN", "COUNT", "ASC", "DESC", "DATE"}                   # [+]
 SYMBOLS = ["<=", ">=", "!=", "<>", "(", ")", ",", "=", "<", ">", "+", "-", "*", "/"]               # longest first; ( ) , are the reference's
 
 
@@ -218,6 +218,15 @@ class SqlParser:
                 return self.parseCast()
             if key in ("MAX", "MIN", "SUM", "COUNT", "DOUBLE"):
                 return SqlIdentifier(t.text)
+            if key == "DATE":                            # DATE 'yyyy-mm-dd' -> a Date32 literal (days since 1970-01-01)
+                d = self.tokens.next()
+                if d is None or d.type != "STRING":
+                    raise IllegalStateException(f"Expected a date string after DATE, found {d}")
+                import datetime
+                try:
+                    return SqlLiteral(datetime.date.fromisoformat(d.text))
+                except ValueError:
+                    raise SQLException(f"Invalid date '{d.text}'")
         elif t.type == "IDENTIFIER":
             return SqlIdentifier(t.text)
         elif t.type == "LONG":

@@ -290,3 +290,96 @@ def test_generated_select_where_matches_numpy(oracle, proj, pred):
     got = np.array([v for b in c.execute(c.sql(sql)) for v in b.to_arrow()[0].to_pylist()], dtype=np.float64)
     want = _np(proj, cols)[_np(pred, cols)]
     assert got.tobytes() == want.astype(np.float64).tobytes(), sql
+
+
+# ---------------------------------------------------------------- from the query string to the sm_100a kernel, without a device
+class _Described(P.DataSource):
+    """A table that is only a schema: enough to plan and to generate kernels."""
+
+    def __init__(self, fields):
+        self._schema = P.Schema([P.Field(n, t) for n, t in fields])
+
+    def schema(self):
+        return self._schema
+
+    def scan(self, projection):
+        raise AssertionError("planning must not scan")
+
+
+@pytest.fixture(scope="module")
+def X():
+    import build
+    build.build()
+    import kqgpu
+    return kqgpu.Exprs()          # the product's expression factory and code generator: host objects, no device needed
+
+
+def test_baseline_query_strings_compile_to_kernels(X):
+    c = P.ExecutionContext(X)
+    c.registerDataSource("employee", _Described([(n, P.StringType) for n in ("id", "first_name", "last_name", "state", "job_title", "salary")]))
+    c.registerDataSource("t2", _Described([(n, P.DoubleType) for n in "abc"]))
+    c.registerDataSource("t3", _Described([("state", P.StringType), ("v", P.DoubleType)]))
+    c.registerDataSource("lineitem", _Described([("l_shipdate", P.Date32Type), ("l_returnflag", P.StringType), ("l_linestatus", P.StringType)] +
+                                                [(n, P.DoubleType) for n in ("l_quantity", "l_extendedprice", "l_discount", "l_tax")]))
+
+    def kernels(sql):
+        phys = P.createPhysicalPlan(P.ProjectionPushDownRule().optimize(c.sql(sql).logicalPlan()), X)
+        return phys, P.explain(phys)
+
+    # configs[0]: one fused filter+projection kernel with the Utf8 comparison, five Utf8 columns passed through
+    phys, ks = kernels("SELECT id, first_name, last_name, state, salary FROM employee WHERE state = 'CO'")
+    assert [type(n).__name__ for n, _ in ks] == ["ProjectionExec"] and "KQ_KERNEL_FILTER" in ks[0][1]
+    # configs[1]: a*b+c as two separately rounded operations, never an FMA
+    _, ks = kernels("SELECT a * b + c FROM t2 WHERE a > 0.5 AND b < 0.5")
+    assert "__dmul_rn" in ks[0][1] and "__dadd_rn" in ks[0][1] and "fma" not in ks[0][1].lower()
+    # configs[2]: the aggregate kernel, then the projection that orders the select list (bare columns: aliases, no kernel work)
+    _, ks = kernels("SELECT state, SUM(v), MIN(v), MAX(v), COUNT(v) FROM t3 GROUP BY state")
+    assert [type(n).__name__ for n, _ in ks] == ["HashAggregateExec"]
+    # the reference's own query (Main.kt:1336): the cast is fused into the aggregate kernel
+    _, ks = kernels("SELECT state, MAX(CAST(salary AS double)) AS max_amount FROM employee GROUP BY state")
+    assert type(ks[0][0]).__name__ == "HashAggregateExec" and len(ks[0][1]) > 1000
+    # configs[4], TPC-H Q1 shape: date filter, derived projections, two group keys — by SQL and through the DataFrame API
+    q1_sql = ("SELECT l_returnflag, l_linestatus, SUM(l_quantity), SUM(l_extendedprice), SUM(l_extendedprice * (1.0 - l_discount)), "
+              "SUM(l_extendedprice * (1.0 - l_discount) * (1.0 + l_tax)), COUNT(l_quantity) FROM lineitem "
+              "WHERE l_shipdate <= DATE '1998-09-02' GROUP BY l_returnflag, l_linestatus")
+    phys_sql, ks = kernels(q1_sql)
+    li = c.sql("SELECT l_returnflag FROM lineitem").logicalPlan().children()[0]
+    one = P.lit(1.0)
+    disc_price = P.BinaryExpr("MUL", P.col("l_extendedprice"), P.BinaryExpr("SUB", one, P.col("l_discount")))
+    charge = P.BinaryExpr("MUL", disc_price, P.BinaryExpr("ADD", one, P.col("l_tax")))
+    q1 = P.DataFrame(li).filter(P.BinaryExpr("LE", P.col("l_shipdate"), P.Literal(10471, P.Date32Type))).aggregate(
+        [P.col("l_returnflag"), P.col("l_linestatus")],
+        [P.Sum(P.col("l_quantity")), P.Sum(P.col("l_extendedprice")), P.Sum(disc_price), P.Sum(charge), P.Count(P.col("l_quantity"))])
+    phys = P.createPhysicalPlan(P.ProjectionPushDownRule().optimize(q1.logicalPlan()), X)
+    assert type(phys).__name__ == "HashAggregateExec" and phys.predicate is not None            # the date filter runs inside the aggregate kernel
+    assert str(phys_sql.children()[0].children()[0]) == str(phys.children()[0])                   # the same scan below both
+    assert [src for _, src in ks] == [src for _, src in P.explain(phys)]                           # and the same kernel: 1998-09-02 = day 10471
+
+
+def test_baseline_config5_query_string_runs_like_the_bench_workload(oracle):
+    """configs[4] (TPC-H Q1 shape) by SQL on bench.py's synthetic lineitem, against the operator calls bench.py itself makes."""
+    import sys
+    sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+    import bench
+    wl = bench.WORKLOADS["cfg5"](30_000)
+    names = ["l_shipdate", "l_returnflag", "l_linestatus", "l_quantity", "l_extendedprice", "l_discount", "l_tax"]
+    types = [P.Date32Type, P.StringType, P.StringType] + [P.DoubleType] * 4
+    parts = [oracle.generate(wl.specs(), 42, i * 10_000, (i + 1) * 10_000) for i in range(3)]
+    c = P.ExecutionContext(oracle)
+    c.registerDataSource("lineitem", P.InMemoryDataSource(oracle, P.Schema([P.Field(n, t) for n, t in zip(names, types)]), parts))
+    df = c.sql("SELECT l_returnflag, l_linestatus, SUM(l_quantity), SUM(l_extendedprice), SUM(l_extendedprice * (1.0 - l_discount)), "
+               "SUM(l_extendedprice * (1.0 - l_discount) * (1.0 + l_tax)), COUNT(l_quantity) FROM lineitem "
+               "WHERE l_shipdate <= DATE '1998-09-02' GROUP BY l_returnflag, l_linestatus")
+    got = sorted(rows(c.execute(df)))
+    E = oracle
+    one = E.lit_f64(1.0)
+    dp = E.binary("MUL", E.col(4), E.binary("SUB", one, E.col(5)))
+    ch = E.binary("MUL", dp, E.binary("ADD", one, E.col(6)))
+    agg = E.HashAggregate([E.col(1), E.col(2)], [("SUM", E.col(3)), ("SUM", E.col(4)), ("SUM", dp), ("SUM", ch), ("COUNT", E.col(3))],
+                          pred=E.binary("LE", E.col(0), E.lit_date32(10471)))
+    agg.update(oracle.generate(wl.specs(), 42, 0, 30_000))
+    want = sorted(rows([agg.finalize()]))
+    assert len(got) == len(want) == 6
+    for g, w in zip(got, want):
+        assert g[:2] == w[:2] and g[6] == w[6] and g[2] == w[2]              # keys, COUNT, and the integer-valued SUM(l_quantity): exact
+        assert all(abs(a - b) <= 1e-9 * abs(b) for a, b in zip(g[3:6], w[3:6]))
