@@ -340,8 +340,14 @@ class DataFrame:
 class ExecutionContext:
     """ExecutionContext (Main.kt:387-419), bound to the engine that runs the physical operators."""
 
-    def __init__(self, engine):
-        self.engine = engine
+    def __init__(self, engine, merge=None):
+        """merge: None, "allreduce" or "repartition" — when every rank of a communicator (kq_comm_init on the engine's
+        context) runs the same plan over its shard of the rows, the aggregate merges the partial tables with that collective
+        after draining its input: main()'s partition -> partial -> merge (Main.kt:1309-1325) inside the operator instead of a
+        second query. Every rank must execute the plan (the merges are collectives)."""
+        if merge not in (None, "allreduce", "repartition"):
+            raise IllegalArgumentException(f"unknown merge {merge!r}")
+        self.engine, self.merge = engine, merge
         self._tables = {}
 
     def sql(self, sql: str) -> DataFrame:
@@ -366,7 +372,7 @@ class ExecutionContext:
     def execute(self, df):
         """Sequence<RecordBatch> of the engine's batches (Main.kt:411-419): optimise, plan, run."""
         plan = df.logicalPlan() if isinstance(df, DataFrame) else df
-        return createPhysicalPlan(ProjectionPushDownRule().optimize(plan), self.engine).execute()
+        return createPhysicalPlan(ProjectionPushDownRule().optimize(plan), self.engine, self.merge).execute()
 
 
 # ---- data sources ---------------------------------------------------------------------------------------------------------
@@ -588,8 +594,9 @@ class HashAggregateExec(PhysicalPlan):
     """HashAggregateExec (Main.kt:605-660): drains its input, then yields exactly ONE batch — group columns, then aggregates
     (rule R10; zero input rows give one batch without rows). With a predicate the filter runs inside the aggregate kernel."""
 
-    def __init__(self, engine, input: PhysicalPlan, groupExpr, aggregateExpr, schema: Schema, predicate=None):
+    def __init__(self, engine, input: PhysicalPlan, groupExpr, aggregateExpr, schema: Schema, predicate=None, merge=None):
         self.engine, self.input, self.groupExpr, self.aggregateExpr, self._schema, self.predicate = engine, input, list(groupExpr), list(aggregateExpr), schema, predicate
+        self.merge = merge          # "allreduce" / "repartition": the collective merge of the ranks' partial tables (ExecutionContext)
 
     def schema(self):
         return self._schema
@@ -601,6 +608,10 @@ class HashAggregateExec(PhysicalPlan):
             agg.update(batch)
             fed = True
         if fed:
+            if self.merge == "allreduce":
+                agg.merge_allreduce()               # afterwards every rank holds the complete result
+            elif self.merge == "repartition":
+                agg.repartition_alltoall()          # afterwards every key lives on exactly one rank
             yield agg.finalize()
         else:       # no input batch at all: the engine never saw a column type; the plan knows them
             import pyarrow as pa
@@ -615,19 +626,19 @@ class HashAggregateExec(PhysicalPlan):
                 + (" (fused with the selection below)" if self.predicate is not None else ""))
 
 
-def createPhysicalPlan(plan: LogicalPlan, engine) -> PhysicalPlan:
+def createPhysicalPlan(plan: LogicalPlan, engine, merge=None) -> PhysicalPlan:
     """Main.kt:680-706 — the one place where operators are chosen. A Selection directly below a Projection or an
     Aggregate is folded into that operator's kernel instead of materialising the filtered batch."""
     if isinstance(plan, Scan):
         return ScanExec(plan.dataSource, plan.projection)
     if isinstance(plan, Selection):
-        return SelectionExec(engine, createPhysicalPlan(plan.input, engine), createPhysicalExpr(plan.expr, plan.input, engine))
+        return SelectionExec(engine, createPhysicalPlan(plan.input, engine, merge), createPhysicalExpr(plan.expr, plan.input, engine))
     if isinstance(plan, (Projection, Aggregate)):
         source, predicate = plan.input, None
         if isinstance(source, Selection):
             predicate = createPhysicalExpr(source.expr, source.input, engine)
             source = source.input
-        input = createPhysicalPlan(source, engine)
+        input = createPhysicalPlan(source, engine, merge)
         if isinstance(plan, Projection):
             expr = [createPhysicalExpr(e, plan.input, engine) for e in plan.expr]
             def bare(e):
@@ -639,7 +650,7 @@ def createPhysicalPlan(plan: LogicalPlan, engine) -> PhysicalPlan:
             if not isinstance(a, (Max, Min, Sum, Count)):
                 raise IllegalStateException(f"Unsupported aggregate function: {a}")      # Main.kt:696
             aggregateExpr.append((a.name, createPhysicalExpr(a.expr, plan.input, engine)))
-        return HashAggregateExec(engine, input, groupExpr, aggregateExpr, plan.schema(), predicate)
+        return HashAggregateExec(engine, input, groupExpr, aggregateExpr, plan.schema(), predicate, merge)
     raise IllegalStateException("Unknown physical plan")
 
 

@@ -171,3 +171,31 @@ def test_long_utf8_keys_travel_with_the_merge(gpu, oracle, world):
     for r in range(world):
         close(got[r], want)
     assert all(g == got[0] for g in got)
+
+
+@pytest.mark.parametrize("world", [2])
+def test_sql_query_with_the_merge_inside_the_aggregate(gpu, oracle, world):
+    """main() (Main.kt:1306-1342) at the level of the reference's API: every rank runs the same SQL over its shard with
+    ExecutionContext(engine, merge="allreduce"); the aggregate merges the partial tables collectively, so every rank's single
+    output batch is the answer over the whole table (checked against the oracle running the query on the unsharded table)."""
+    if gpu.device_count() < world:
+        pytest.skip(f"needs {world} GPUs")
+    from kqgpu import plan as P
+    n = 200_000
+    specs = [dict(kind=5, col_id=0, dict=STATES, dict_width=2), dict(kind=2, col_id=1, flo=0.0, fhi=1000.0)]
+    sql = "SELECT state, SUM(v), MIN(v), MAX(v), COUNT(v) FROM t WHERE v >= 10.0 GROUP BY state"
+    schema = P.Schema([P.Field("state", P.StringType), P.Field("v", P.DoubleType)])
+
+    def query(E, lo, hi, merge):
+        q = P.ExecutionContext(E, merge=merge)
+        mid = (lo + hi) // 2
+        q.registerDataSource("t", P.InMemoryDataSource(E, schema, [E.generate(specs, 11, lo, mid), E.generate(specs, 11, mid, hi)]))
+        out = list(q.execute(q.sql(sql)))
+        assert len(out) == 1
+        return rows_of(out[0])
+
+    got = run_ranks(gpu, world, lambda r, ctx, E: query(E, r * n // world, (r + 1) * n // world, "allreduce"))
+    want = query(oracle, 0, n, None)
+    assert len(want) == 50
+    for r in range(world):
+        close(got[r], want)
