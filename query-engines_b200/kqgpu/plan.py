@@ -12,10 +12,11 @@ host language the tests use, with the reference's names and error behaviour, so 
     ScanExec, ProjectionExec, HashAggregateExec (564-660) [+ SelectionExec, fused into its parent where one kernel does both]
     DataSource: CsvDataSource (276-357), InMemoryDataSource (1292-1304)
 
-`engine` is anything with the operator vocabulary of kqgpu.Engine — col, cast, lit_*, binary, project, filter,
-filter_project, HashAggregate, csv_header, csv_scan (and csv_batches) — i.e. kqgpu.Engine(ctx) for the GPU, or the module
-oracle/oracle.py, which is how the CPU test-suite checks this layer without a device. Nothing here computes on data:
-planning, schemas and names only. What the reference lacks is marked [+ ...] above.
+`engine` is the object that runs the operators: kqgpu.Engine(ctx). This module only needs its vocabulary — col, cast,
+lit_*, binary, project, filter, filter_project, HashAggregate, csv_header, csv_scan / csv_batches — and imports nothing
+else, which is what lets the test-suite hand it a checker with the same vocabulary and verify this layer without a
+device; there is no fallback in here: nothing in this module computes on data (planning, schemas and names only), and
+without an engine nothing runs. What the reference lacks is marked [+ ...] above.
 """
 from __future__ import annotations
 
