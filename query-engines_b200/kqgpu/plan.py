@@ -432,6 +432,12 @@ class InMemoryDataSource(DataSource):
 
     def __init__(self, engine, schema: Schema, data):
         self.engine, self._schema, self.data = engine, schema, list(data)
+        for batch in self.data:                     # a schema that lies about its columns fails here, not inside a kernel
+            if batch.num_columns() != len(schema.fields):
+                raise IllegalStateException(f"batch with {batch.num_columns()} columns under a schema of {len(schema.fields)} fields")
+            for i, f in enumerate(schema.fields):
+                if batch.field(i).type() != f.dataType.kq_type:
+                    raise IllegalStateException(f"column {f.name}: the batch holds {ArrowType(batch.field(i).type())}, the schema says {f.dataType}")
 
     def schema(self):
         return self._schema

@@ -383,3 +383,65 @@ def test_baseline_config5_query_string_runs_like_the_bench_workload(oracle):
     for g, w in zip(got, want):
         assert g[:2] == w[:2] and g[6] == w[6] and g[2] == w[2]              # keys, COUNT, and the integer-valued SUM(l_quantity): exact
         assert all(abs(a - b) <= 1e-9 * abs(b) for a, b in zip(g[3:6], w[3:6]))
+
+
+_ILEAF = st.one_of(st.sampled_from(["a", "b", "c"]), st.integers(0, 1 << 40))
+_IARITH = st.recursive(_ILEAF, lambda kids: st.tuples(st.sampled_from(["+", "-", "*"]), kids, kids), max_leaves=5)
+_ICMP = st.tuples(st.sampled_from(["<", "<=", ">", ">=", "=", "!="]), _IARITH, _IARITH)
+
+
+def _isql(t, parent=0, right=False):
+    if isinstance(t, (str, int)):
+        return str(t)
+    op, l, r = t
+    p = _PREC[op]
+    s = f"{_isql(l, p)} {op} {_isql(r, p, True)}"
+    return f"({s})" if p < parent or (p == parent and right) else s
+
+
+def _inp(t, cols):
+    if isinstance(t, str):
+        return cols[t]
+    if isinstance(t, int):
+        return np.full_like(cols["a"], t)
+    op, l, r = t
+    x, y = _inp(l, cols), _inp(r, cols)
+    with np.errstate(all="ignore"):
+        return {"+": np.add, "-": np.subtract, "*": np.multiply, "<": np.less, "<=": np.less_equal, ">": np.greater,
+                ">=": np.greater_equal, "=": np.equal, "!=": np.not_equal}[op](x, y)
+
+
+@settings(max_examples=80, deadline=None)
+@given(proj=_IARITH.filter(lambda t: not isinstance(t, int)), pred=_ICMP)
+def test_generated_int64_queries_wrap_like_kotlin_long(oracle, proj, pred):
+    """Rule E1: Int64 arithmetic wraps in two's complement like Kotlin's Long (numpy's int64 does the same), through the
+    SQL front-end; products of 40-bit operands overflow often."""
+    specs = [dict(kind=1, col_id=i, ilo=0, ihi=1 << 40) for i in range(3)]
+    batch = oracle.generate(specs, 9, 0, 1500)
+    cols = dict(zip("abc", [a.to_numpy(zero_copy_only=False).astype(np.int64) for a in batch.to_arrow()]))
+    c = P.ExecutionContext(oracle)
+    c.registerDataSource("t", P.InMemoryDataSource(oracle, P.Schema([P.Field(n, P.Int64Type) for n in "abc"]), [batch]))
+    sql = f"SELECT {_isql(proj)} AS r FROM t WHERE {_isql(pred)}"
+    got = np.array([v for b in c.execute(c.sql(sql)) for v in b.to_arrow()[0].to_pylist()], dtype=np.int64)
+    want = _inp(proj, cols)[_inp(pred, cols)]
+    assert np.array_equal(got, want), sql
+
+
+def test_int64_division_truncates_and_by_zero_is_arithmetic_exception(oracle):
+    """Rule E4: Kotlin's Long division truncates toward zero; dividing by zero throws ArithmeticException — only for rows
+    that pass the filter, as in a row-at-a-time engine."""
+    import pyarrow as pa
+    batch = oracle.RecordBatch.from_arrow([pa.array([7, -7, 7, -7, 5], pa.int64()), pa.array([2, 2, -2, -2, 0], pa.int64())])
+    c = P.ExecutionContext(oracle)
+    c.registerDataSource("t", P.InMemoryDataSource(oracle, P.Schema([P.Field("x", P.Int64Type), P.Field("y", P.Int64Type)]), [batch]))
+    assert rows(c.execute(c.sql("SELECT x / y FROM t WHERE y != 0"))) == [(3,), (-3,), (-3,), (3,)]
+    with pytest.raises(oracle.OracleError, match="Arithmetic"):
+        list(c.execute(c.sql("SELECT x / y FROM t")))
+
+
+def test_in_memory_source_checks_its_schema(oracle):
+    batch = oracle.generate([dict(kind=2, col_id=0, flo=0.0, fhi=1.0)], 1, 0, 10)
+    with pytest.raises(P.IllegalStateException, match="the schema says Int\\(64, true\\)"):
+        P.InMemoryDataSource(oracle, P.Schema([P.Field("v", P.Int64Type)]), [batch])
+    with pytest.raises(P.IllegalStateException, match="columns under a schema"):
+        P.InMemoryDataSource(oracle, P.Schema([P.Field("v", P.DoubleType), P.Field("w", P.DoubleType)]), [batch])

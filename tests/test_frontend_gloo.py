@@ -13,7 +13,7 @@ import torch.multiprocessing as mp
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 STATES = "ALAKAZARCACOCTDEFLGAHIIDILINIAKSKYLAMEMDMAMIMNMSMOMTNENVNHNJNMNYNCNDOHOKORPARISCSDTNTXUTVTVAWAWVWIWY"
-SPECS = [dict(kind=5, col_id=0, dict=STATES, dict_width=2), dict(kind=3, col_id=1, ilo=0, ihi=1000)]      # Utf8 key, Int64 values: sums are exact
+SPECS = [dict(kind=5, col_id=0, dict=STATES, dict_width=2), dict(kind=1, col_id=1, ilo=0, ihi=1000)]      # Utf8 key, Int64 values (generator kind 1): sums are exact
 N_PER_RANK = 30_000
 PARTIAL = "SELECT state, MAX(v) AS max_v, MIN(v) AS min_v, SUM(v) AS sum_v, COUNT(v) AS n FROM t GROUP BY state"
 MERGE = "SELECT state, MAX(max_v), MIN(min_v), SUM(sum_v), SUM(n) FROM partials GROUP BY state ORDER BY state"
