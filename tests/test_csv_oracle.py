@@ -175,3 +175,19 @@ def test_reader_model_on_random_tables(oracle, ncols, data, crlf, blanks, piece,
     except OverflowError:
         assume(False)                                               # a record longer than the piece: the reader refuses (tested on the GPU)
     assert _concat(batches, len(want)) == (want if want and want[0] else [[] for _ in want])
+
+
+@settings(max_examples=400, deadline=None)
+@given(body=st.text(st.sampled_from(list('ab1 ,,;;\t|"""\n\n\r')), max_size=120), hdr=st.booleans(),
+       lead=st.sampled_from(["", "h1,h2\n", 'x"y;z\n', '"h,1";h2\r\n', " \n\n", "a|b|c\n", "a\tb\n"]))
+def test_product_header_detection_on_raw_texts(oracle, body, hdr, lead):
+    """kq_csv_header of the shipped library (host code: terminator and delimiter detection, first record under rule C2) on
+    arbitrary texts rich in quotes and all four candidate delimiters, against the oracle's tokenizer."""
+    import kqgpu
+    from oracle.oracle import OracleError
+    text = (lead + body).encode("utf-8")
+    try:
+        want = oracle.csv_header(text, hdr)
+    except OracleError:
+        return                      # the text ends inside a quoted field: the scan reports it (the header call reads one record)
+    assert kqgpu.Engine.csv_header(text, hdr) == want
